@@ -1,0 +1,131 @@
+/* =============================================================================
+ * ttcross_b200.h — C-ABI of the B200-native TT-cross sweep.
+ *
+ * Drop-in boundary for ONE hot path of aukeschaap/ttcross: the parallel greedy
+ * TT-cross sweep `dtt_dmrgg` (reference lib/dmrgg.f90:11-1050) and the
+ * quadrature `dtt_quad` (lib/dmrgg.f90:1261-1415).  Plain pointers and sizes
+ * only; callable from Fortran `bind(C)` (fortran/dmrgg_cuda_lib.f90), from C/C++
+ * (ttcross_b200/drivers/) and from ctypes (ttcross_b200/api.py).
+ *
+ * Every function returns 0 on success or a non-zero ttc_status; the message of
+ * the last failure is available from ttc_last_error().  Where the reference
+ * does `write(*,*) msg; stop` (e.g. lib/dmrgg.f90:114-117), this ABI returns the
+ * status and the same message; the Fortran shim reproduces the `stop`.
+ *
+ * All reals are IEEE double, all indices are 32-bit and 1-based exactly as in
+ * the reference, all arrays are column-major.
+ * ========================================================================== */
+#ifndef TTCROSS_B200_H
+#define TTCROSS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ttc_handle ttc_handle;
+
+/* integrand families (replace the `external fun` argument, lib/dmrgg.f90:18) */
+enum {
+    TTC_ISING = 1,   /* test_crs_ising.f90:176-218; C/D/E selected by par(2n+1) = 1/2/3 like the reference */
+    TTC_STDNORM = 4, /* test_crs_stdnorm.f90:154-170 */
+    TTC_MVN = 5      /* lib/mvn_pdf.f90:63-83 via test_crs_mvn.f90:156-172; aux = mu(d) | inv_cov(d,d) | denom */
+};
+
+enum ttc_status {
+    TTC_OK = 0,
+    TTC_ERR_ARG = 1,        /* bad argument */
+    TTC_ERR_NPROC = 2,      /* "nproc exceeds or equal dimension, cannot proceed" (lib/dmrgg.f90:114-117) */
+    TTC_ERR_PIVOTING = 3,   /* "unknown pivoting" (lib/dmrgg.f90:590-592) */
+    TTC_ERR_CUDA = 4,       /* CUDA runtime failure, or no CUDA device: there is NO CPU fallback */
+    TTC_ERR_STATE = 5,      /* call order (e.g. results queried before ttc_dmrgg) */
+    TTC_ERR_RANK = 6,       /* rank capacity exceeded */
+    TTC_ERR_COMM = 7        /* multi-GPU communicator failure */
+};
+
+/* ---- problem description --------------------------------------------------
+ * Replaces the (fun, par) pair of dtt_dmrgg (lib/dmrgg.f90:18-19) and the
+ * arg%l, arg%m, arg%n fields of type(dtt) (lib/tt.f90:18-26).
+ *   d     number of cores (arg%m - arg%l + 1, with l = 1)
+ *   n     mode sizes n(1:d)
+ *   par   the opaque parameter blob the driver hands to `fun` (copied)
+ *   aux   integrand-private state that the reference keeps in module variables
+ *         (mvn_pdf.f90:4-11): MVN -> mu(d) | inv_cov(d,d) column-major | denominator
+ */
+int ttc_create(ttc_handle** out, int kind, int d, const int* n, const double* par, long npar,
+               const double* aux, long naux);
+void ttc_destroy(ttc_handle* h);
+const char* ttc_last_error(const ttc_handle* h);   /* h may be NULL: message of the last failed ttc_create */
+
+/* ---- optional arguments of dtt_dmrgg (lib/dmrgg.f90:19-26) ------------------ */
+int ttc_set_device(ttc_handle* h, int cuda_device);                 /* default 0 */
+int ttc_set_partition(ttc_handle* h, int nparts, const int* own);   /* mybonds(0:nparts); own == NULL -> share() of lib/default.f90:80-97 */
+int ttc_set_quad(ttc_handle* h, const double* quad);                /* quad=: rank-1 weights, n(1)+...+n(d) doubles; NULL removes */
+int ttc_set_tru(ttc_handle* h, int present, double tru);            /* tru=: only switches ' cnv ' to ' err ' in the sweep log */
+int ttc_set_seed(ttc_handle* h, unsigned long long seed);           /* uniform stream of the lottery (rnd.f90:120 is unseeded) */
+/* Alternative uniform source: cb(ctx, vrank, count, out) must write `count` uniforms in [0,1) for virtual rank `vrank`. */
+typedef void (*ttc_uniform_cb)(void* ctx, int vrank, int count, double* out);
+int ttc_set_uniform_callback(ttc_handle* h, ttc_uniform_cb cb, void* ctx);
+int ttc_set_verbose(ttc_handle* h, int verbose);                    /* 1: print the reference's per-sweep lines on stdout */
+
+/* ---- the sweep: dtt_dmrgg (lib/dmrgg.f90:11) -------------------------------
+ *   maxrank   <= 0 : absent          accuracy  < 0 : absent
+ *   pivoting  -1 full superblock, 0 one cross, >= 1 rook depth (reference default 3)
+ */
+int ttc_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting);
+
+/* ---- results (valid after ttc_dmrgg) --------------------------------------- */
+int ttc_ranks(const ttc_handle* h, int* r);            /* r(0:d) -> arg%r */
+int ttc_core(ttc_handle* h, int k, double* out);       /* arg%u(k)%p : r(k-1)*n(k)*r(k) doubles, column-major, k = 1..d */
+long long ttc_neval(const ttc_handle* h);              /* neval= */
+int ttc_nsweeps(const ttc_handle* h);
+double ttc_seconds(const ttc_handle* h);               /* wall time of the last ttc_dmrgg call (timef difference) */
+/* per-sweep series, nsweeps+1 entries (entry 0 = the '0::' line): 0 val, 1 n_evals, 2 amax, 3 pivotmax, 4 erank, 5 time */
+int ttc_sweep_series(const ttc_handle* h, int which, double* out);
+/* pivot tape: one record per bond visit {it, vrank, bond, ii, jj, kk, qq, upd} + the pivot value */
+long ttc_pivlog_count(const ttc_handle* h);
+int ttc_pivlog(const ttc_handle* h, int* ints8, double* pivots);
+long ttc_text(const ttc_handle* h, char* buf, long cap);   /* the sweep log (reference format, dmrgg.f90:293-300,971-1008) */
+
+/* dtt_quad(arg, quad) on the finalised train (lib/dmrgg.f90:1261); uses the weights of ttc_set_quad, or plain sums */
+int ttc_quad(ttc_handle* h, double* val);
+
+/* ---- host-side helpers the reference drivers use --------------------------- */
+void ttc_lgwt(int n, double* x, double* w);                         /* lib/quad.f90:97-131 */
+void ttc_share(int first, int last, int nproc, int* own);           /* lib/default.f90:80-97 */
+double ttc_stream_uniform(unsigned long long seed, int vrank, unsigned long long k);  /* the built-in uniform stream */
+
+/* ---- kernel-level entry points (measurement and kernel parity tests) --------
+ * Superblock kernel of the pivoting = -1 branch (lib/dmrgg.f90:341-396) on the handle's CURRENT state
+ * (after ttc_dmrgg): evaluates a(i,j,k,q) over r(p-1) x n(p) x n(p+1) x r(p+1) for bond p, forms the residual
+ * against col*row (K = r(p)) and returns both first-index argmaxes.  store != 0 also writes `a` to HBM.
+ *   out_idx[0] = argmax|a| (0-based linear), out_idx[1] = argmax|b|; out_val[0] = a at argmax, out_val[1] = b at argmax
+ *   ms      average device time per launch over `reps` launches (CUDA events)
+ */
+int ttc_superblock_probe(ttc_handle* h, int bond, int store, int reps, long long* out_idx, double* out_val,
+                         double* ms, long long* count);
+/* Fiber kernel probe: column fiber (isrow=0) or row fiber (isrow=1) of bond p through pivot (ii,jj,kk,qq); returns
+ * the fiber values (r(p-1)*n(p) or n(p+1)*r(p+1) doubles) and its residual. */
+int ttc_fiber_probe(ttc_handle* h, int bond, int isrow, int ii, int jj, int kk, int qq, double* fiber, double* resid,
+                    int reps, double* ms);
+/* Counters: kernels launched by this handle since creation, device time of the last ttc_dmrgg (CUDA events, ms) */
+long long ttc_launch_count(const ttc_handle* h);
+/* write `bytes` (> L2 size) of scratch HBM so the next timed run starts with a cold L2 (measurement hygiene) */
+int ttc_l2_flush(ttc_handle* h, long long bytes);
+double ttc_device_ms(const ttc_handle* h);
+/* per-kernel-class accounting of the last ttc_dmrgg: names[i] (static strings), launches, total ms (events, only when
+ * profiling was enabled with ttc_set_profile(h, 1)) */
+int ttc_set_profile(ttc_handle* h, int on);
+int ttc_profile(const ttc_handle* h, int cap, const char** names, long long* launches, double* ms);
+
+/* ---- multi-GPU: one process per GPU, core blocks partitioned over ranks ------
+ * The communicator id is an NCCL unique id (128 bytes) created on rank 0 and broadcast by the caller (e.g. through
+ * torch.distributed or MPI_Bcast); virtual partitions [vfirst, vlast] of ttc_set_partition are mapped to this rank. */
+int ttc_comm_unique_id(void* id128);
+int ttc_comm_init(ttc_handle* h, int nranks, int rank, const void* id128);
+
+int ttc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTCROSS_B200_H */

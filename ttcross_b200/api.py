@@ -1,0 +1,245 @@
+"""ctypes binding of include/ttcross_b200.h.
+
+`TTCross` mirrors the reference call `dtt_dmrgg(tt, fun, par, maxrank=, accuracy=, pivoting=, neval=, quad=, tru=)`
+(lib/dmrgg.f90:11-26) followed by `dtt_quad(tt, qq)` (lib/dmrgg.f90:1261).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import build as _build
+
+ISING, STDNORM, MVN = 1, 4, 5
+
+_lib = None
+_dp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+
+
+class TTCrossError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"ttcross_b200 status {status}: {msg}")
+        self.status = status
+        self.msg = msg
+
+
+def load_library(build_if_missing: bool = True):
+    """Load libttcross_b200.so (in-tree).  Fails loudly if it is missing and cannot be built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if build_if_missing and _build.needs_build() and os.path.exists(_build.NVCC):
+        _build.build()
+    if not os.path.exists(path):
+        raise TTCrossError(-1, f"{path} is missing: run `python -m ttcross_b200.build` (nvcc, sm_100a); there is no CPU fallback")
+    L = C.CDLL(path)
+    vp = C.c_void_p
+    L.ttc_create.restype = C.c_int
+    L.ttc_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, _ip, _dp, C.c_long, _dp, C.c_long]
+    L.ttc_destroy.argtypes = [vp]
+    L.ttc_last_error.restype = C.c_char_p
+    L.ttc_last_error.argtypes = [vp]
+    L.ttc_set_device.argtypes = [vp, C.c_int]
+    L.ttc_set_partition.argtypes = [vp, C.c_int, _ip]
+    L.ttc_set_quad.argtypes = [vp, _dp]
+    L.ttc_set_tru.argtypes = [vp, C.c_int, C.c_double]
+    L.ttc_set_seed.argtypes = [vp, C.c_ulonglong]
+    L.ttc_set_verbose.argtypes = [vp, C.c_int]
+    L.ttc_set_profile.argtypes = [vp, C.c_int]
+    L.ttc_dmrgg.argtypes = [vp, C.c_int, C.c_double, C.c_int]
+    L.ttc_ranks.argtypes = [vp, _ip]
+    L.ttc_core.argtypes = [vp, C.c_int, _dp]
+    L.ttc_neval.restype = C.c_longlong
+    L.ttc_neval.argtypes = [vp]
+    L.ttc_nsweeps.argtypes = [vp]
+    L.ttc_seconds.restype = C.c_double
+    L.ttc_seconds.argtypes = [vp]
+    L.ttc_sweep_series.argtypes = [vp, C.c_int, _dp]
+    L.ttc_pivlog_count.restype = C.c_long
+    L.ttc_pivlog_count.argtypes = [vp]
+    L.ttc_pivlog.argtypes = [vp, _ip, _dp]
+    L.ttc_text.restype = C.c_long
+    L.ttc_text.argtypes = [vp, C.c_char_p, C.c_long]
+    L.ttc_quad.argtypes = [vp, _dp]
+    L.ttc_lgwt.argtypes = [C.c_int, _dp, _dp]
+    L.ttc_share.argtypes = [C.c_int, C.c_int, C.c_int, _ip]
+    L.ttc_stream_uniform.restype = C.c_double
+    L.ttc_stream_uniform.argtypes = [C.c_ulonglong, C.c_int, C.c_ulonglong]
+    L.ttc_superblock_probe.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), _dp, _dp, C.POINTER(C.c_longlong)]
+    L.ttc_fiber_probe.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp]
+    L.ttc_launch_count.restype = C.c_longlong
+    L.ttc_launch_count.argtypes = [vp]
+    L.ttc_l2_flush.argtypes = [vp, C.c_longlong]
+    L.ttc_device_ms.restype = C.c_double
+    L.ttc_device_ms.argtypes = [vp]
+    L.ttc_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_longlong), _dp]
+    L.ttc_comm_unique_id.argtypes = [C.c_void_p]
+    L.ttc_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_void_p]
+    L.ttc_version.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+@dataclass
+class CrossResult:
+    nsweeps: int
+    neval: int
+    ranks: np.ndarray
+    vals: np.ndarray
+    nevals: np.ndarray
+    amaxs: np.ndarray
+    pivotmaxs: np.ndarray
+    pivlog: np.ndarray       # int32 [count, 8]: it, vrank, bond, ii, jj, kk, qq, upd
+    pivots: np.ndarray
+    text: str
+    seconds: float
+    device_ms: float
+    launches: int
+
+
+class TTCross:
+    """One TT-cross problem on one GPU (handle of the C-ABI)."""
+
+    def __init__(self, kind: int, n, par, aux=None, device: int = 0):
+        L = load_library()
+        self._L = L
+        self.n = np.ascontiguousarray(n, dtype=np.int32)
+        self.d = int(self.n.size)
+        self._par = np.ascontiguousarray(par, dtype=np.float64)
+        self._aux = np.ascontiguousarray(aux if aux is not None else np.zeros(0), dtype=np.float64)
+        h = C.c_void_p()
+        st = L.ttc_create(C.byref(h), kind, self.d, _i(self.n), _d(self._par), self._par.size,
+                          _d(self._aux) if self._aux.size else None, self._aux.size)
+        if st != 0:
+            raise TTCrossError(st, L.ttc_last_error(None).decode())
+        self.h = h
+        self._check(L.ttc_set_device(h, device))
+        self.kind = kind
+
+    def _check(self, st):
+        if st != 0:
+            raise TTCrossError(st, self._L.ttc_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.ttc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- optional arguments of dtt_dmrgg
+    def set_partition(self, nparts: int, own=None):
+        if own is None:
+            self._check(self._L.ttc_set_partition(self.h, nparts, None))
+        else:
+            a = np.ascontiguousarray(own, dtype=np.int32)
+            self._check(self._L.ttc_set_partition(self.h, nparts, _i(a)))
+
+    def set_quad(self, quad):
+        if quad is None:
+            self._check(self._L.ttc_set_quad(self.h, None))
+        else:
+            a = np.ascontiguousarray(quad, dtype=np.float64)
+            assert a.size == int(self.n.sum())
+            self._check(self._L.ttc_set_quad(self.h, _d(a)))
+
+    def set_tru(self, tru):
+        self._check(self._L.ttc_set_tru(self.h, 0 if tru is None else 1, 0.0 if tru is None else float(tru)))
+
+    def set_seed(self, seed: int):
+        self._check(self._L.ttc_set_seed(self.h, seed))
+
+    def set_verbose(self, v: bool):
+        self._check(self._L.ttc_set_verbose(self.h, int(v)))
+
+    def set_profile(self, on: bool):
+        self._check(self._L.ttc_set_profile(self.h, int(on)))
+
+    # ---- dtt_dmrgg
+    def dmrgg(self, maxrank: int = -1, accuracy: float = -1.0, pivoting: int = 3) -> CrossResult:
+        L = self._L
+        self._check(L.ttc_dmrgg(self.h, maxrank, accuracy, pivoting))
+        ns = L.ttc_nsweeps(self.h)
+        ranks = np.zeros(self.d + 1, dtype=np.int32)
+        self._check(L.ttc_ranks(self.h, _i(ranks)))
+        series = []
+        for which in range(4):
+            a = np.zeros(ns + 1)
+            self._check(L.ttc_sweep_series(self.h, which, _d(a)))
+            series.append(a)
+        cnt = L.ttc_pivlog_count(self.h)
+        pl = np.zeros((cnt, 8), dtype=np.int32)
+        pv = np.zeros(cnt)
+        if cnt:
+            self._check(L.ttc_pivlog(self.h, _i(pl), _d(pv)))
+        self.ranks = ranks
+        return CrossResult(ns, L.ttc_neval(self.h), ranks, series[0], series[1].astype(np.int64), series[2], series[3],
+                           pl, pv, self.text(), L.ttc_seconds(self.h), L.ttc_device_ms(self.h), L.ttc_launch_count(self.h))
+
+    def text(self) -> str:
+        ln = self._L.ttc_text(self.h, None, 0)
+        buf = C.create_string_buffer(ln + 1)
+        self._L.ttc_text(self.h, buf, ln + 1)
+        return buf.value.decode()
+
+    def core(self, k: int) -> np.ndarray:
+        shp = (int(self.ranks[k - 1]), int(self.n[k - 1]), int(self.ranks[k]))
+        a = np.zeros(shp, order="F")
+        self._check(self._L.ttc_core(self.h, k, _d(a)))
+        return a
+
+    def cores(self):
+        return [self.core(k) for k in range(1, self.d + 1)]
+
+    # ---- dtt_quad
+    def quad(self) -> float:
+        v = C.c_double()
+        self._check(self._L.ttc_quad(self.h, C.byref(v)))
+        return v.value
+
+    # ---- probes
+    def superblock_probe(self, bond: int, store: bool = False, reps: int = 1):
+        idx = (C.c_longlong * 2)()
+        val = (C.c_double * 2)()
+        ms = C.c_double()
+        cnt = C.c_longlong()
+        self._check(self._L.ttc_superblock_probe(self.h, bond, int(store), reps, idx, val, C.byref(ms), C.byref(cnt)))
+        return {"argmax_a": idx[0], "argmax_b": idx[1], "a": val[0], "b": val[1], "ms": ms.value, "count": cnt.value}
+
+    def fiber_probe(self, bond: int, isrow: bool, ii: int, jj: int, kk: int, qq: int, reps: int = 1):
+        cnt = (int(self.n[bond]) * int(self.ranks[bond + 1])) if isrow else (int(self.ranks[bond - 1]) * int(self.n[bond - 1]))
+        f = np.zeros(cnt)
+        r = np.zeros(cnt)
+        ms = C.c_double()
+        self._check(self._L.ttc_fiber_probe(self.h, bond, int(isrow), ii, jj, kk, qq, _d(f), _d(r), reps, C.byref(ms)))
+        return f, r, ms.value
+
+    def profile(self):
+        cap = 32
+        names = (C.c_char_p * cap)()
+        launches = (C.c_longlong * cap)()
+        ms = (C.c_double * cap)()
+        cnt = self._L.ttc_profile(self.h, cap, names, launches, ms)
+        return {names[i].decode(): (int(launches[i]), float(ms[i])) for i in range(cnt)}
+
+    def l2_flush(self, nbytes: int = 256 << 20):
+        self._check(self._L.ttc_l2_flush(self.h, nbytes))
+
+    def launch_count(self) -> int:
+        return int(self._L.ttc_launch_count(self.h))

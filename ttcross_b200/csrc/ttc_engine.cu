@@ -1,0 +1,983 @@
+// =============================================================================
+// ttc_engine.cu — host side of the B200-native TT-cross sweep + the C-ABI of
+// include/ttcross_b200.h.
+//
+// Control flow follows dtt_dmrgg (reference lib/dmrgg.f90:11-1050); every bond
+// visit is a short chain of kernels whose control flow (rook-loop termination,
+// accept test) lives on the device.  The host's only per-visit duties are the
+// lottery (rnd.f90:105-144; kept on the host because its sequentially accumulated
+// cumulative weights define the reference semantics) and mirroring the
+// pivot tape.  There is no CPU fallback: without a CUDA device every entry point
+// that computes returns TTC_ERR_CUDA.
+// =============================================================================
+#include "../../include/ttcross_b200.h"
+#include "ttc_device.cuh"
+
+#include <algorithm>
+#include <array>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace ttc;
+
+namespace {
+
+typedef unsigned long long u64;
+
+// ----------------------------------------------------------------------------
+// built-in uniform stream (counter based, so a later device-side lottery can index it)
+// ----------------------------------------------------------------------------
+inline u64 mix64(u64 z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+inline double stream_uniform(u64 seed, int vrank, u64 k) {
+    const u64 G = 0x9E3779B97F4A7C15ULL;
+    u64 base = mix64(seed + G * (u64)(vrank + 1));
+    u64 z = mix64(base + G * (k + 1));
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// rnd.f90:128-144
+inline int find_d(int n, const double* x, double y) {
+    if (n == 0) return 0;
+    if (y < x[0]) return 0;
+    if (x[n - 1] <= y) return n;
+    int s = 1, t = n, pos = (t + s) / 2;
+    while (t - s > 1) {
+        if (y < x[pos - 1]) t = pos; else s = pos;
+        pos = (s + t) / 2;
+    }
+    return pos;
+}
+
+// tt.f90:1228-1245
+double erank(int d, const std::vector<int>& n /*1..d*/, const std::vector<int>& r /*0..d*/) {
+    if (d <= 0) return -1.0;
+    if (d == 1) return 0.0;
+    double rk = 0.0;
+    for (int i = 1; i <= d; ++i) rk = rk + (double)(r[i - 1] * n[i] * r[i]);
+    if (rk == 0.0) return rk;
+    int b = r[0] * n[1] + n[d] * r[d];
+    if (d == 2) return rk / b;
+    int a = 0;
+    for (int i = 2; i <= d - 1; ++i) a += n[i];
+    return (std::sqrt((double)b * b + 4.0 * a * rk) - b) / (2.0 * a);
+}
+
+// Fortran 'e' edit descriptor
+std::string fmt_e(double v, int w, int dgt) {
+    char buf[128];
+    std::string s;
+    if (v == 0.0) s = "0." + std::string(dgt, '0') + "E+00";
+    else if (std::isnan(v)) s = "NaN";
+    else if (std::isinf(v)) s = v > 0 ? "Infinity" : "-Infinity";
+    else {
+        std::snprintf(buf, sizeof buf, "%.*e", dgt - 1, std::fabs(v));
+        std::string t = buf;
+        size_t epos = t.find('e');
+        int ex = std::atoi(t.c_str() + epos + 1) + 1;
+        std::string digits;
+        for (size_t i = 0; i < epos; ++i) if (t[i] != '.') digits += t[i];
+        s = std::string(v < 0 ? "-" : "") + "0." + digits;
+        char eb[16];
+        std::snprintf(eb, sizeof eb, "E%c%02d", ex < 0 ? '-' : '+', std::abs(ex));
+        s += eb;
+        if ((int)s.size() > w) { size_t z = (s[0] == '-') ? 1 : 0; if (s[z] == '0') s.erase(z, 1); }
+    }
+    if ((int)s.size() > w) s = std::string(w, '*');
+    if ((int)s.size() < w) s = std::string(w - s.size(), ' ') + s;
+    return s;
+}
+
+struct PivRec { int it, vrank, bond, ii, jj, kk, qq, upd; double pivot; };
+
+enum KClass { KC_LOT = 0, KC_FIBER, KC_REDUCE, KC_SUPERBLOCK, KC_ACCEPT, KC_UPDATE, KC_NBR, KC_EXCHANGE, KC_QUAD, KC_INIT, KC_FINAL, KC_MISC, KC_COUNT };
+const char* kclass_names[KC_COUNT] = {"lottery_eval", "fiber_eval_residual", "argmax_reduce", "superblock", "accept", "rank1_update",
+                                      "neighbour_factors", "exchange", "quadrature", "init", "finalise", "misc"};
+
+}  // namespace
+
+struct ttc_handle {
+    // problem
+    int kind = TTC_ISING, d = 0, ising_id = 1;
+    std::vector<int> n;                 // 1..d (n[0] = n[d+1] = 1)
+    std::vector<double> par, aux, quad; // quad concatenated, empty = absent
+    bool has_tru = false; double tru = 0;
+    int P = 1; std::vector<int> own; bool own_given = false;
+    u64 seed = 1; ttc_uniform_cb ucb = nullptr; void* ucb_ctx = nullptr;
+    int verbose = 0, device = 0, profile = 0;
+    std::string err;
+
+    // run parameters / state
+    bool ran = false;
+    int Rmax = 0, nmax = 0, nlotmax = 0, piv = 3;
+    std::vector<int> rk_h, rks_h;
+    std::vector<std::vector<std::array<int, 4>>> vip_h;
+    std::vector<u64> rng_k;
+    DevPlan plan;
+    std::vector<void*> allocs;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int* lot_h = nullptr; VisitOut* out_h = nullptr; SweepOut* sweep_h = nullptr;   // pinned
+    double* pack_d = nullptr; size_t pack_cap = 0;
+    void* flush_d = nullptr; size_t flush_cap = 0;
+    double* initb = nullptr;
+    int nsm = 148;
+
+    std::vector<int> setup_sig;
+    std::vector<double> quad_or_ones() const {
+        if (!quad.empty()) return quad;
+        size_t tot = 0; for (int p = 1; p <= d; ++p) tot += n[p];
+        return std::vector<double>(tot, 1.0);
+    }
+
+    // results
+    i64 neval = 0; int nsweeps = 0; double seconds = 0, device_ms = 0;
+    std::vector<double> s_val, s_neval, s_amax, s_pivotmax, s_erank, s_time;
+    std::vector<PivRec> pivlog;
+    std::string text;
+    long long launches = 0;
+    long long kc_launch[KC_COUNT] = {0};
+    double kc_ms[KC_COUNT] = {0};
+};
+
+namespace {
+
+std::string g_create_err;
+
+#define CUDA_TRY(h, call)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess) {                                                                            \
+            (h)->err = std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call;                 \
+            return TTC_ERR_CUDA;                                                                            \
+        }                                                                                                   \
+    } while (0)
+
+template <class T>
+int dev_alloc(ttc_handle* h, T** p, size_t count, bool zero = true) {
+    void* q = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CUDA_TRY(h, cudaMalloc(&q, bytes));
+    if (zero) CUDA_TRY(h, cudaMemsetAsync(q, 0, bytes, h->stream));
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+template <class T>
+int dev_upload(ttc_handle* h, T** p, const std::vector<T>& v) {
+    int st = dev_alloc(h, p, v.size(), false);
+    if (st) return st;
+    if (!v.empty()) CUDA_TRY(h, cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+void free_device(ttc_handle* h) {
+    h->setup_sig.clear();
+    for (void* p : h->allocs) cudaFree(p);
+    h->allocs.clear();
+    if (h->lot_h) { cudaFreeHost(h->lot_h); h->lot_h = nullptr; }
+    if (h->out_h) { cudaFreeHost(h->out_h); h->out_h = nullptr; }
+    if (h->sweep_h) { cudaFreeHost(h->sweep_h); h->sweep_h = nullptr; }
+    if (h->pack_d) { cudaFree(h->pack_d); h->pack_d = nullptr; h->pack_cap = 0; }
+    if (h->ev0) { cudaEventDestroy(h->ev0); h->ev0 = nullptr; }
+    if (h->ev1) { cudaEventDestroy(h->ev1); h->ev1 = nullptr; }
+    if (h->stream) { cudaStreamDestroy(h->stream); h->stream = nullptr; }
+}
+
+// kernel launch with accounting; in profile mode each launch is bracketed by events (serialising, diagnostic only)
+struct Launcher {
+    ttc_handle* h;
+    cudaEvent_t a = nullptr, b = nullptr;
+    explicit Launcher(ttc_handle* hh) : h(hh) {
+        if (h->profile) { cudaEventCreate(&a); cudaEventCreate(&b); }
+    }
+    ~Launcher() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    template <class F>
+    void operator()(KClass kc, F&& f) {
+        if (h->profile) cudaEventRecord(a, h->stream);
+        f();
+        h->launches += 1;
+        h->kc_launch[kc] += 1;
+        if (h->profile) {
+            cudaEventRecord(b, h->stream);
+            cudaEventSynchronize(b);
+            float ms = 0; cudaEventElapsedTime(&ms, a, b);
+            h->kc_ms[kc] += ms;
+        }
+    }
+};
+
+inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
+
+// dispatch on the integrand family
+#define KIND_SWITCH(kind, ...)                                                   \
+    switch (kind) {                                                              \
+        case TTC_ISING:   { constexpr int K = KIND_ISING;   __VA_ARGS__; } break; \
+        case TTC_STDNORM: { constexpr int K = KIND_STDNORM; __VA_ARGS__; } break; \
+        default:          { constexpr int K = KIND_MVN;     __VA_ARGS__; } break; \
+    }
+
+int threads_for(const ttc_handle* h) { return h->kind == TTC_MVN ? 64 : 256; }
+size_t aux_smem(const ttc_handle* h) { return (size_t)h->plan.auxsm * sizeof(double); }
+
+int check_device(ttc_handle* h) {
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt <= 0) {
+        h->err = std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                 "); ttcross_b200 has no CPU fallback";
+        return TTC_ERR_CUDA;
+    }
+    if (h->device < 0 || h->device >= cnt) { h->err = "bad CUDA device index"; return TTC_ERR_ARG; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return 0;
+}
+
+// ----------------------------------------------------------------------------
+// device state construction
+// ----------------------------------------------------------------------------
+int setup_device(ttc_handle* h, int maxrank) {
+    // device buffers are kept between runs of the same shape (nothing needs re-zeroing: every slice is written
+    // before it is read), so a repeated ttc_dmrgg does not pay cudaMalloc again
+    std::vector<int> sig = {h->d, h->P, maxrank > 0 ? maxrank : 64, h->kind, h->device};
+    sig.insert(sig.end(), h->own.begin(), h->own.end());
+    if (h->stream && sig == h->setup_sig) {
+        int st0 = check_device(h);
+        if (st0) return st0;
+        h->plan.piv = h->piv;
+        CUDA_TRY(h, cudaMemcpyAsync(const_cast<double*>(h->plan.quadw), h->quad_or_ones().data(), h->quad_or_ones().size() * sizeof(double),
+                                    cudaMemcpyHostToDevice, h->stream));
+        return 0;
+    }
+    free_device(h);
+    h->setup_sig = sig;
+    int st = check_device(h);
+    if (st) return st;
+    cudaDeviceProp prop;
+    CUDA_TRY(h, cudaGetDeviceProperties(&prop, h->device));
+    h->nsm = prop.multiProcessorCount;
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaEventCreate(&h->ev0));
+    CUDA_TRY(h, cudaEventCreate(&h->ev1));
+
+    const int d = h->d, P = h->P;
+    h->Rmax = maxrank > 0 ? maxrank : 64;
+    h->nmax = *std::max_element(h->n.begin() + 1, h->n.begin() + d + 1);
+    h->nlotmax = 2 * h->Rmax + 2 * h->nmax;
+    const int Rmax = h->Rmax;
+    DevPlan& D = h->plan;
+    std::memset(&D, 0, sizeof D);
+    D.d = d; D.P = P; D.Rmax = Rmax; D.nmax = h->nmax; D.piv = h->piv; D.kind = h->kind; D.ising_id = h->ising_id;
+    D.nlotmax = h->nlotmax;
+    D.auxsm = 0;
+    if (h->kind == TTC_MVN) {
+        size_t need = (size_t)d * d * sizeof(double) + (size_t)Rmax * sizeof(double);
+        if (need <= 200 * 1024) D.auxsm = d * d;
+    }
+
+    std::vector<i64> offL(d + 2, 0), offR(d + 2, 0), coreOff(d + 2, 0), quadOff(d + 2, 0);
+    i64 accL = 0, accR = 0, accC = 0, accQ = 0;
+    for (int p = 0; p <= d; ++p) { offL[p] = accL; accL += (i64)Rmax * p; }
+    offL[d + 1] = accL;
+    for (int p = 0; p <= d + 1; ++p) { offR[p] = accR; if (p <= d) accR += (i64)Rmax * std::max(0, d - p); }
+    for (int p = 1; p <= d; ++p) { coreOff[p] = accC; accC += (i64)Rmax * h->n[p] * Rmax; quadOff[p] = accQ; accQ += h->n[p]; }
+
+    int *dn, *down, *drk, *drks, *dvip, *dL, *dR, *dlot;
+    i64 *doffL, *doffR, *dcoreOff, *dquadOff;
+    double *dpar, *daux, *darg, *dcol, *drow, *dinv, *da1, *db1, *da2, *db2, *dlraw, *dlres, *dquad, *dttqq, *dch, *dch2;
+    Partial* dpart; VState* dst; VisitOut* dout; SweepOut* dsw;
+    std::vector<int> nv(h->n.begin(), h->n.end());
+#define TRY(x) do { int s_ = (x); if (s_) return s_; } while (0)
+    TRY(dev_upload(h, &dn, nv));
+    TRY(dev_upload(h, &down, h->own));
+    TRY(dev_upload(h, &dpar, h->par));
+    std::vector<double> auxv = h->aux; if (auxv.empty()) auxv.push_back(0.0);
+    TRY(dev_upload(h, &daux, auxv));
+    TRY(dev_upload(h, &doffL, offL));
+    TRY(dev_upload(h, &doffR, offR));
+    TRY(dev_upload(h, &dcoreOff, coreOff));
+    TRY(dev_upload(h, &dquadOff, quadOff));
+    std::vector<double> qv = h->quad_or_ones();
+    TRY(dev_upload(h, &dquad, qv));
+    TRY(dev_alloc(h, &dL, (size_t)accL + 1));
+    TRY(dev_alloc(h, &dR, (size_t)accR + 1));
+    TRY(dev_alloc(h, &dvip, (size_t)(d + 1) * Rmax * 4));
+    TRY(dev_alloc(h, &drk, (size_t)d + 2));
+    TRY(dev_alloc(h, &drks, (size_t)d + 2));
+    TRY(dev_alloc(h, &darg, (size_t)accC));
+    TRY(dev_alloc(h, &dcol, (size_t)accC));
+    TRY(dev_alloc(h, &drow, (size_t)accC));
+    TRY(dev_alloc(h, &dinv, (size_t)(d + 1) * Rmax * Rmax));
+    const size_t fsz = (size_t)P * Rmax * h->nmax;
+    TRY(dev_alloc(h, &da1, fsz)); TRY(dev_alloc(h, &db1, fsz)); TRY(dev_alloc(h, &da2, fsz)); TRY(dev_alloc(h, &db2, fsz));
+    TRY(dev_alloc(h, &dlot, (size_t)P * 4 * h->nlotmax));
+    TRY(dev_alloc(h, &dlraw, (size_t)P * h->nlotmax)); TRY(dev_alloc(h, &dlres, (size_t)P * h->nlotmax));
+    TRY(dev_alloc(h, &dpart, (size_t)P * 2 * GMAX));
+    TRY(dev_alloc(h, &dst, (size_t)P)); TRY(dev_alloc(h, &dout, (size_t)P)); TRY(dev_alloc(h, &dsw, 1));
+    TRY(dev_alloc(h, &dttqq, (size_t)(d + 1) * Rmax * Rmax));
+    TRY(dev_alloc(h, &dch, (size_t)(P + 1) * Rmax * Rmax)); TRY(dev_alloc(h, &dch2, (size_t)(P + 1) * Rmax * Rmax));
+#undef TRY
+    D.n = dn; D.own = down; D.par = dpar; D.aux = daux; D.Lidx = dL; D.Ridx = dR; D.offL = doffL; D.offR = doffR;
+    D.vip = dvip; D.rk = drk; D.rks = drks; D.arg = darg; D.col = dcol; D.rowT = drow; D.coreOff = dcoreOff; D.inv = dinv;
+    D.acol1 = da1; D.bcol1 = db1; D.arow1 = da2; D.brow1 = db2; D.lot = dlot; D.lraw = dlraw; D.lres = dlres;
+    D.part = dpart; D.st = dst; D.out = dout; D.quadw = dquad; D.quadOff = dquadOff; D.ttqq = dttqq; D.chain = dch;
+    D.chain2 = dch2; D.sweep_out = dsw;
+
+    {
+        const int nn0 = *std::min_element(h->n.begin() + 1, h->n.begin() + d + 1);
+        int s0 = dev_alloc(h, &h->initb, (size_t)nn0 * std::max(8, P));
+        if (s0) return s0;
+    }
+    CUDA_TRY(h, cudaMallocHost((void**)&h->lot_h, (size_t)P * 4 * h->nlotmax * sizeof(int)));
+    CUDA_TRY(h, cudaMallocHost((void**)&h->out_h, (size_t)P * sizeof(VisitOut)));
+    CUDA_TRY(h, cudaMallocHost((void**)&h->sweep_h, sizeof(SweepOut)));
+
+    // kernels that stage the MVN matrix need more than the default 48 KB of dynamic shared memory when d > ~75
+    if (D.auxsm) {
+        int bytes = (int)(aux_smem(h) + (size_t)Rmax * sizeof(double));
+        if (bytes > 48 * 1024) {
+            cudaFuncSetAttribute(k_lot<KIND_MVN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            cudaFuncSetAttribute(k_fiber<KIND_MVN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            cudaFuncSetAttribute(k_fiber<KIND_MVN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            cudaFuncSetAttribute(k_superblock<KIND_MVN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            cudaFuncSetAttribute(k_superblock<KIND_MVN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            cudaFuncSetAttribute(k_exchange_corner<KIND_MVN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            cudaFuncSetAttribute(k_init_search<KIND_MVN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            cudaFuncSetAttribute(k_init_cross<KIND_MVN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        }
+    }
+    return 0;
+}
+
+// ----------------------------------------------------------------------------
+// host lottery for one bond visit of one virtual rank (dmrgg.f90:425-452, rnd.f90:105-126)
+// ----------------------------------------------------------------------------
+void host_lottery(ttc_handle* h, int v, int p, int r0, int r1, int n1, int n2, int r2, int* lot /*[4][nlotmax]*/,
+                  std::vector<double>& pcol, std::vector<double>& prow, std::vector<double>& u) {
+    const int nlot = r0 + n1 + n2 + r2;
+    const int m = r0 * n1, n = n2 * r2;
+    pcol.assign(m + 1, 1.0); prow.assign(n + 1, 1.0);    // slot x+1 temporarily holds weight x
+    for (int s = 0; s < r1; ++s) {
+        const auto& t = h->vip_h[p][s];
+        pcol[(t[0] - 1) + (size_t)r0 * (t[1] - 1) + 1] = 0.0;
+        prow[(t[2] - 1) + (size_t)n2 * (t[3] - 1) + 1] = 0.0;
+    }
+    double scol = 0.0, srow = 0.0;
+    for (int i = 1; i <= m; ++i) scol = scol + pcol[i];
+    for (int j = 1; j <= n; ++j) srow = srow + prow[j];
+    pcol[0] = 0.0; for (int i = 1; i <= m; ++i) pcol[i] = pcol[i - 1] + pcol[i] / scol;
+    prow[0] = 0.0; for (int j = 1; j <= n; ++j) prow[j] = prow[j - 1] + prow[j] / srow;
+    u.resize(2 * (size_t)nlot);
+    if (h->ucb) h->ucb(h->ucb_ctx, v, 2 * nlot, u.data());
+    else for (int x = 0; x < 2 * nlot; ++x) u[x] = stream_uniform(h->seed, v, h->rng_k[v] + x);
+    h->rng_k[v] += 2 * (u64)nlot;
+    const int L = h->nlotmax;
+    for (int x = 0; x < nlot; ++x) {
+        int c = find_d(m + 1, pcol.data(), u[x]);        if (c > m) c = m;
+        int w = find_d(n + 1, prow.data(), u[nlot + x]); if (w > n) w = n;
+        lot[x] = (c - 1) % r0 + 1;
+        lot[L + x] = (c - 1) / r0 + 1;
+        lot[2 * L + x] = (w - 1) % n2 + 1;
+        lot[3 * L + x] = (w - 1) / n2 + 1;
+    }
+}
+
+void host_dims(const ttc_handle* h, int v, int dir, int pp, int& active, int& p, int& r0, int& r1, int& r2) {
+    int lo = h->own[v], hi = h->own[v + 1];
+    active = (pp <= hi - lo);
+    p = (dir == 1) ? lo + pp - 1 : hi - pp;
+    if (!active) p = lo;
+    r0 = (p - 1 >= lo) ? h->rk_h[p - 1] : h->rks_h[p - 1];
+    r1 = h->rk_h[p];
+    r2 = (p + 1 <= hi - 1) ? h->rk_h[p + 1] : h->rks_h[p + 1];
+}
+
+// quadrature of the current cores -> sweep_out->val.  with_lua: the per-sweep path of dmrgg.f90:975-993
+int launch_quad(ttc_handle* h, Launcher& L, bool with_lua, bool use_weights) {
+    const DevPlan& D = h->plan;
+    cudaStream_t s = h->stream;
+    L(KC_QUAD, [&] { k_quad_contract<<<dim3(cdiv((i64)h->Rmax * h->Rmax, 256), h->d), 256, 0, s>>>(D, use_weights ? 1 : 0); });
+    if (with_lua) L(KC_QUAD, [&] { k_quad_lua<<<h->d, 128, 0, s>>>(D); });
+    L(KC_QUAD, [&] { k_quad_chain<<<h->P, 256, 0, s>>>(D); });
+    L(KC_QUAD, [&] { k_quad_tree<<<1, 256, 0, s>>>(D); });
+    return 0;
+}
+
+// ----------------------------------------------------------------------------
+// the sweep
+// ----------------------------------------------------------------------------
+int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
+    h->ran = false;
+    h->pivlog.clear(); h->text.clear();
+    h->s_val.clear(); h->s_neval.clear(); h->s_amax.clear(); h->s_pivotmax.clear(); h->s_erank.clear(); h->s_time.clear();
+    std::fill(h->kc_launch, h->kc_launch + KC_COUNT, 0); std::fill(h->kc_ms, h->kc_ms + KC_COUNT, 0.0);
+    auto tstart = std::chrono::steady_clock::now();
+    auto timef = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - tstart).count(); };
+
+    const int d = h->d, m = d, l = 1;
+    if (h->P >= m) { h->err = "nproc exceeds or equal dimension, cannot proceed"; h->text += h->err + "\n"; return TTC_ERR_NPROC; }
+    if (pivoting < -1) { h->err = "dtt_dmrgg: unknown pivoting"; return TTC_ERR_PIVOTING; }
+    h->piv = pivoting;
+    if (!h->own_given) { h->own.assign(h->P + 1, 0); ttc_share(l, m - 1, h->P, h->own.data()); }
+    for (int v = 0; v < h->P; ++v)
+        if (h->own[v + 1] < h->own[v] || h->own[0] != 1 || h->own[h->P] != m) { h->err = "bad partition"; return TTC_ERR_ARG; }
+    int st = setup_device(h, maxrank);
+    if (st) return st;
+    const int P = h->P, Rmax = h->Rmax;
+    DevPlan& D = h->plan;
+    cudaStream_t s = h->stream;
+    Launcher L(h);
+    const int TB = threads_for(h);
+    const size_t smA = aux_smem(h);
+    const size_t smF = smA + (size_t)Rmax * sizeof(double);
+    const double eps = 2.220446049250313e-16;
+    const double small_element = 10 * eps, small_pivot = 1.e-5;
+    const bool has_quad = !h->quad.empty();
+    char line[512];
+
+    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+
+    // ---- initial cross search (dmrgg.f90:150-217)
+    const int snum = std::max(8, P);
+    const int nn = *std::min_element(h->n.begin() + 1, h->n.begin() + d + 1);
+    std::vector<int> shifts(P + 1);
+    for (int p = 0; p < P; ++p) shifts[p] = (int)((double)snum * (double)p / P);
+    shifts[P] = snum;
+    double* db = h->initb;
+    KIND_SWITCH(h->kind, L(KC_INIT, [&] { k_init_search<K><<<cdiv((i64)nn * snum, TB), TB, smA, s>>>(D, nn, snum, db); }));
+    std::vector<double> b((size_t)nn * snum);
+    CUDA_TRY(h, cudaMemcpyAsync(b.data(), db, b.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    int gilot = 1; double gmax = std::fabs(b[0]);
+    for (int x = 2; x <= nn * snum; ++x) if (std::fabs(b[x - 1]) > gmax) { gmax = std::fabs(b[x - 1]); gilot = x; }
+    std::vector<double> amax_v(P, gmax);
+    std::vector<i64> neval_v(P, 0);
+    if (P == 1) amax_v[0] = gmax;
+    else {
+        // each rank's own local maximum is overwritten by the MAXLOC result (dmrgg.f90:193-203)
+    }
+    for (int v = 0; v < P; ++v) neval_v[v] = (i64)nn * (shifts[v + 1] - shifts[v]);
+    std::vector<int> ind0(d + 2, 1);
+    {
+        int sft = (gilot - 1) / nn, k = (gilot - 1) % nn + 1;
+        for (int p = 1; p <= d; ++p) ind0[p] = (k - 1 + sft * (p - 1)) % h->n[p] + 1;
+    }
+    // pivot 1 of every bond: vip, flat index tables, ranks
+    {
+        std::vector<int> vip((size_t)(d + 1) * Rmax * 4, 0), rk(d + 2, 1);
+        for (int p = 0; p <= d; ++p) {
+            int* t = &vip[(size_t)p * Rmax * 4];
+            t[0] = 1; t[3] = 1;
+            t[1] = (p >= 1 && p <= d - 1) ? ind0[p] : 1;
+            t[2] = (p >= 1 && p <= d - 1) ? ind0[p + 1] : 1;
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(D.vip, vip.data(), vip.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(h, cudaMemcpyAsync(D.rk, rk.data(), rk.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(h, cudaMemcpyAsync(D.rks, rk.data(), rk.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+        i64 accL = (i64)Rmax * d * (d + 1) / 2, accR = accL;
+        std::vector<int> Lt((size_t)accL + 1, 0), Rt((size_t)accR + 1, 0);
+        i64 oL = 0, oR = 0;
+        for (int p = 0; p <= d; ++p) {
+            for (int pos = 0; pos < p; ++pos) Lt[(size_t)(oL + (i64)pos * Rmax)] = ind0[pos + 1];
+            oL += (i64)Rmax * p;
+            for (int pos = 0; pos < d - p; ++pos) Rt[(size_t)(oR + (i64)pos * Rmax)] = ind0[p + pos + 1];
+            oR += (i64)Rmax * (d - p);
+        }
+        // sizes: sum_{p=0..d} Rmax*p == Rmax*d*(d+1)/2 for both tables
+        CUDA_TRY(h, cudaMemcpyAsync(D.Lidx, Lt.data(), (size_t)accL * sizeof(int), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(h, cudaMemcpyAsync(D.Ridx, Rt.data(), (size_t)accR * sizeof(int), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+    }
+    h->rk_h.assign(d + 2, 1); h->rks_h.assign(d + 2, 1);
+    h->vip_h.assign(d + 1, {});
+    for (int p = 0; p <= d; ++p)
+        h->vip_h[p].push_back({1, (p >= 1 && p <= d - 1) ? ind0[p] : 1, (p >= 1 && p <= d - 1) ? ind0[p + 1] : 1, 1});
+    h->rng_k.assign(P, 0);
+
+    // ---- initial cross fibers and factors (dmrgg.f90:220-248)
+    KIND_SWITCH(h->kind, L(KC_INIT, [&] { k_init_cross<K><<<dim3(cdiv(h->nmax, TB), d), TB, smA, s>>>(D); }));
+    L(KC_INIT, [&] { k_init_factors<<<dim3(cdiv(h->nmax, 256), d), 256, 0, s>>>(D); });
+    // fibers back to the host for the scalar bookkeeping of the '0::' line
+    std::vector<std::vector<double>> fib(d + 1);
+    for (int p = 1; p <= d; ++p) fib[p].resize(h->n[p]);
+    {
+        // one strided copy per core
+        i64 off = 0;
+        for (int p = 1; p <= d; ++p) {
+            CUDA_TRY(h, cudaMemcpy2DAsync(fib[p].data(), sizeof(double), D.arg + off, (size_t)Rmax * sizeof(double), sizeof(double),
+                                          h->n[p], cudaMemcpyDeviceToHost, s));
+            off += (i64)Rmax * h->n[p] * Rmax;
+        }
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+    }
+    for (int v = 0; v < P; ++v) {
+        for (int p = h->own[v]; p <= h->own[v + 1]; ++p) {
+            neval_v[v] += h->n[p];
+            for (int j = 0; j < h->n[p]; ++j) amax_v[v] = std::max(amax_v[v], std::fabs(fib[p][j]));
+        }
+    }
+    {
+        std::vector<VState> sv(P);
+        std::memset(sv.data(), 0, sizeof(VState) * P);
+        for (int v = 0; v < P; ++v) {
+            sv[v].amax = amax_v[v]; sv[v].pivotmax = -1; sv[v].pivotmin = -1; sv[v].pivotmax_prev = amax_v[v]; sv[v].neval = neval_v[v];
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(D.st, sv.data(), sizeof(VState) * P, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+    }
+    double val = 0, val_prev = 0;
+    if (has_quad) {
+        std::vector<double> part(P);
+        std::vector<i64> qoff(d + 2, 0);
+        for (int p = 1; p <= d; ++p) qoff[p + 1] = qoff[p] + h->n[p];
+        auto ddot = [&](int p) { double t = 0.0; for (int j = 0; j < h->n[p]; ++j) t = t + fib[p][j] * h->quad[(size_t)qoff[p] + j]; return t; };
+        for (int v = 0; v < P; ++v) {
+            double x = 1.0;
+            for (int p = h->own[v]; p <= h->own[v + 1] - 1; ++p) x = x * ddot(p) / fib[p][ind0[p] - 1];
+            if (v == P - 1) x = x * ddot(m);
+            part[v] = x;
+        }
+        val = part[0];
+        for (int v = 1; v < P; ++v) val = val * part[v];
+        val_prev = val;
+    }
+    i64 nevalall = 0; for (int v = 0; v < P; ++v) nevalall += neval_v[v];
+    auto push_series = [&](double v_, i64 ne, double am, double pm, double er, double t) {
+        h->s_val.push_back(v_); h->s_neval.push_back((double)ne); h->s_amax.push_back(am); h->s_pivotmax.push_back(pm);
+        h->s_erank.push_back(er); h->s_time.push_back(t);
+    };
+    {
+        double t2 = timef();
+        double er = erank(d, h->n, h->rk_h);
+        std::snprintf(line, sizeof line, "%3d%2s rank%5.1f time: %s n_evals: %10lld", 0, "::", er, fmt_e(t2, 9, 3).c_str(), nevalall);
+        std::string str = line;
+        if (has_quad) str += " val " + fmt_e(val, 20, 14);
+        h->text += str + "\n";
+        if (h->verbose) { std::puts(str.c_str()); std::fflush(stdout); }
+        push_series(val, nevalall, amax_v[0], -1.0, er, t2);
+    }
+
+    // ---- main loop (dmrgg.f90:309-1020)
+    int it = 0, strike = 0;
+    bool ready = false;
+    if (maxrank > 0) ready = (it + 1 >= maxrank);
+    int maxnb = 0;
+    for (int v = 0; v < P; ++v) maxnb = std::max(maxnb, h->own[v + 1] - h->own[v]);
+    std::vector<double> pcol, prow, ubuf;
+    std::vector<PivRec> sweep_log;
+
+    while (!ready) {
+        it += 1;
+        const int dir = 2 - it % 2;
+        const char* sdir = dir == 1 ? ">>" : "<<";
+        if (it + 1 > Rmax && maxrank <= 0) { h->err = "rank capacity exceeded (pass maxrank)"; return TTC_ERR_RANK; }
+        L(KC_MISC, [&] { k_sweep_begin<<<cdiv(std::max(d + 1, P), 128), 128, 0, s>>>(D); });
+        h->rks_h = h->rk_h;
+
+        for (int pp = 1; pp <= maxnb; ++pp) {
+            // geometry of this visit on every virtual rank (host mirror)
+            int maxcol = 1, maxrow = 1, maxlot = 1; i64 maxsb = 1;
+            for (int v = 0; v < P; ++v) {
+                int active, p, r0, r1, r2;
+                host_dims(h, v, dir, pp, active, p, r0, r1, r2);
+                if (!active) continue;
+                const int n1 = h->n[p], n2 = h->n[p + 1];
+                maxcol = std::max(maxcol, r0 * n1); maxrow = std::max(maxrow, n2 * r2);
+                maxlot = std::max(maxlot, r0 + n1 + n2 + r2);
+                maxsb = std::max(maxsb, (i64)r0 * n1 * n2 * r2);
+                if (h->piv >= 0) host_lottery(h, v, p, r0, r1, n1, n2, r2, h->lot_h + (size_t)v * 4 * h->nlotmax, pcol, prow, ubuf);
+            }
+            const int Gc = std::min(GMAX, cdiv(maxcol, TB)), Gr = std::min(GMAX, cdiv(maxrow, TB));
+            if (h->piv == -1) {
+                const int Gs = (int)std::min<i64>(GMAX, std::max<i64>(1, (maxsb + TB - 1) / TB));
+                KIND_SWITCH(h->kind, L(KC_SUPERBLOCK, [&] { k_superblock<K, 0><<<dim3(Gs, P), TB, smA, s>>>(D, dir, pp, 0, 0, nullptr); }));
+                L(KC_REDUCE, [&] { k_superblock_reduce<<<dim3(1, P), 128, 0, s>>>(D, dir, pp, Gs, 0, 0, nullptr); });
+                KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, P), TB, smF, s>>>(D, dir, pp, 2); }));
+                KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, P), TB, smF, s>>>(D, dir, pp, 2); }));
+            } else {
+                CUDA_TRY(h, cudaMemcpyAsync(D.lot, h->lot_h, (size_t)P * 4 * h->nlotmax * sizeof(int), cudaMemcpyHostToDevice, s));
+                const int Gl = std::min(GMAX, cdiv(maxlot, TB));
+                KIND_SWITCH(h->kind, L(KC_LOT, [&] { k_lot<K><<<dim3(Gl, P), TB, smA, s>>>(D, dir, pp); }));
+                L(KC_REDUCE, [&] { k_lot_reduce<<<dim3(1, P), 128, 0, s>>>(D, dir, pp, Gl); });
+                if (h->piv == 0) {
+                    KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, P), TB, smF, s>>>(D, dir, pp, 1); }));
+                    L(KC_REDUCE, [&] { k_fiber_reduce<0><<<dim3(1, P), 128, 0, s>>>(D, dir, pp, 1, Gc); });
+                    KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, P), TB, smF, s>>>(D, dir, pp, 1); }));
+                    L(KC_REDUCE, [&] { k_fiber_reduce<1><<<dim3(1, P), 128, 0, s>>>(D, dir, pp, 1, Gr); });
+                } else {
+                    // rook loop (dmrgg.f90:515-582): at most 2*piv fibers, alternating, starting with the row in '<<' sweeps
+                    int isrow = (dir == 2) ? 1 : 0;
+                    for (int c = 0; c < 2 * h->piv; ++c) {
+                        if (!isrow) {
+                            KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, P), TB, smF, s>>>(D, dir, pp, 0); }));
+                            L(KC_REDUCE, [&] { k_fiber_reduce<0><<<dim3(1, P), 128, 0, s>>>(D, dir, pp, 0, Gc); });
+                        } else {
+                            KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, P), TB, smF, s>>>(D, dir, pp, 0); }));
+                            L(KC_REDUCE, [&] { k_fiber_reduce<1><<<dim3(1, P), 128, 0, s>>>(D, dir, pp, 0, Gr); });
+                        }
+                        isrow ^= 1;
+                    }
+                }
+            }
+            L(KC_ACCEPT, [&] { k_accept<<<dim3(1, P), 128, 0, s>>>(D, dir, pp, small_element, small_pivot); });
+            L(KC_UPDATE, [&] { k_update_main<<<dim3(std::min(GMAX, cdiv(maxcol + maxrow, 256)), P), 256, 0, s>>>(D, dir, pp); });
+            L(KC_NBR, [&] { k_update_nbr<<<dim3(cdiv(2 * h->nmax, 64), P), 64, 0, s>>>(D, dir, pp); });
+            L(KC_MISC, [&] { k_end_visit<<<cdiv(P, 64), 64, 0, s>>>(D, dir, pp); });
+            CUDA_TRY(h, cudaMemcpyAsync(h->out_h, D.out, (size_t)P * sizeof(VisitOut), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(h, cudaStreamSynchronize(s));
+            for (int v = 0; v < P; ++v) {
+                const VisitOut& O = h->out_h[v];
+                if (!O.active) continue;
+                sweep_log.push_back({it, v, O.bond, O.ii, O.jj, O.kk, O.qq, O.upd, O.pivot});
+                if (O.upd) {
+                    if (h->rk_h[O.bond] >= Rmax) { h->err = "rank capacity exceeded"; return TTC_ERR_RANK; }
+                    h->vip_h[O.bond].push_back({O.ii, O.jj, O.kk, O.qq});
+                    h->rk_h[O.bond] += 1;
+                }
+            }
+        }
+        // tape order of the reference: rank by rank, each rank's bonds in visit order
+        std::stable_sort(sweep_log.begin(), sweep_log.end(), [](const PivRec& a, const PivRec& b) { return a.vrank < b.vrank; });
+        h->pivlog.insert(h->pivlog.end(), sweep_log.begin(), sweep_log.end());
+        sweep_log.clear();
+        if (P > 1) {
+            L(KC_EXCHANGE, [&] { k_allreduce<<<1, 32, 0, s>>>(D); });
+            KIND_SWITCH(h->kind, L(KC_EXCHANGE, [&] { k_exchange_corner<K><<<dim3(1, P - 1), TB, smA, s>>>(D); }));
+            L(KC_EXCHANGE, [&] { k_exchange_extend<<<dim3(cdiv(2 * h->nmax, 64), P - 1), 64, 0, s>>>(D); });
+        }
+        L(KC_MISC, [&] { k_sweep_end<<<1, 32, 0, s>>>(D); });
+        if (has_quad) launch_quad(h, L, true, true);
+        CUDA_TRY(h, cudaMemcpyAsync(h->sweep_h, D.sweep_out, sizeof(SweepOut), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        CUDA_TRY(h, cudaGetLastError());
+        const SweepOut& SO = *h->sweep_h;
+        nevalall = SO.neval;
+
+        double t2 = timef();
+        double er = erank(d, h->n, h->rk_h);
+        std::snprintf(line, sizeof line, "%3d%2s rank%5.1f time: %s n_evals: %10lld", it, sdir, er, fmt_e(t2, 9, 3).c_str(), nevalall);
+        std::string str = line;
+        if (has_quad) {
+            val = SO.val;
+            if (h->has_tru) str += " err " + fmt_e(std::fabs(1.0 - val / h->tru), 8, 3) + " val " + fmt_e(val, 20, 14);
+            else str += " cnv " + fmt_e(std::fabs(1.0 - val / val_prev), 8, 3) + " val " + fmt_e(val, 20, 14);
+            val_prev = val;
+        }
+        h->text += str + "\n";
+        if (h->verbose) { std::puts(str.c_str()); std::fflush(stdout); }
+        push_series(val, nevalall, SO.amax, SO.pivotmax, er, t2);
+
+        if (maxrank > 0) ready = ready || (it + 1 >= maxrank);
+        if (accuracy >= 0) {
+            if (SO.pivotmax <= accuracy * SO.amax) strike += 1; else strike = 0;
+            ready = ready || (strike >= 3);
+        }
+    }
+    h->nsweeps = it;
+
+    // ---- finalise (dmrgg.f90:1028-1029)
+    L(KC_FINAL, [&] { k_lua_r<<<dim3(cdiv((i64)h->nmax * Rmax, 128), d), 128, 0, s>>>(D); });
+    L(KC_FINAL, [&] { k_lua_l<<<dim3(cdiv((i64)h->nmax * Rmax, 128), d), 128, 0, s>>>(D); });
+    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    CUDA_TRY(h, cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->device_ms = ms;
+    h->neval = nevalall;
+    h->seconds = timef();
+    h->ran = true;
+    return TTC_OK;
+}
+
+}  // namespace
+
+// =============================================================================
+// C-ABI
+// =============================================================================
+extern "C" {
+
+int ttc_version(void) { return 100; }
+
+int ttc_create(ttc_handle** out, int kind, int d, const int* n, const double* par, long npar, const double* aux, long naux) {
+    if (!out) { g_create_err = "ttc_create: out is NULL"; return TTC_ERR_ARG; }
+    *out = nullptr;
+    if (kind != TTC_ISING && kind != TTC_STDNORM && kind != TTC_MVN) { g_create_err = "ttc_create: unknown integrand kind"; return TTC_ERR_ARG; }
+    if (d < 2 || !n || !par || npar <= 0) { g_create_err = "ttc_create: need d >= 2, n and par"; return TTC_ERR_ARG; }
+    for (int i = 0; i < d; ++i) if (n[i] < 1) { g_create_err = "ttc_create: mode sizes must be positive"; return TTC_ERR_ARG; }
+    if (kind == TTC_ISING) {
+        for (int i = 1; i < d; ++i) if (n[i] != n[0]) { g_create_err = "ttc_create: the Ising integrand needs equal mode sizes"; return TTC_ERR_ARG; }
+        if (npar < 2L * n[0] + 1) { g_create_err = "ttc_create: Ising par must hold nodes(n) | weights(n) | id"; return TTC_ERR_ARG; }
+        int id = (int)par[2 * n[0]];
+        if (id < 1 || id > 3) { g_create_err = "unknown id"; return TTC_ERR_ARG; }
+    } else {
+        int nm = *std::max_element(n, n + d);
+        if (npar < nm) { g_create_err = "ttc_create: par must hold the nodes"; return TTC_ERR_ARG; }
+    }
+    if (kind == TTC_MVN && (!aux || naux < (long)d + (long)d * d + 1)) { g_create_err = "ttc_create: MVN aux must hold mu(d) | inv_cov(d,d) | denom"; return TTC_ERR_ARG; }
+    ttc_handle* h = new ttc_handle();
+    h->kind = kind; h->d = d;
+    h->n.assign(d + 2, 1);
+    for (int i = 0; i < d; ++i) h->n[i + 1] = n[i];
+    h->par.assign(par, par + npar);
+    if (aux && naux > 0) h->aux.assign(aux, aux + naux);
+    if (kind == TTC_ISING) h->ising_id = (int)par[2 * n[0]];
+    h->P = 1; h->own = {1, d};
+    std::memset(&h->plan, 0, sizeof h->plan);
+    *out = h;
+    return TTC_OK;
+}
+
+void ttc_destroy(ttc_handle* h) {
+    if (!h) return;
+    if (h->stream || !h->allocs.empty()) { cudaSetDevice(h->device); free_device(h); }
+    if (h->flush_d) cudaFree(h->flush_d);
+    delete h;
+}
+
+const char* ttc_last_error(const ttc_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int ttc_set_device(ttc_handle* h, int dev) { if (!h) return TTC_ERR_ARG; h->device = dev; return TTC_OK; }
+int ttc_set_partition(ttc_handle* h, int nparts, const int* own) {
+    if (!h || nparts < 1) return TTC_ERR_ARG;
+    h->P = nparts;
+    if (own) { h->own.assign(own, own + nparts + 1); h->own_given = true; }
+    else { h->own_given = false; h->own.assign(nparts + 1, 0); ttc_share(1, h->d - 1, nparts, h->own.data()); }
+    return TTC_OK;
+}
+int ttc_set_quad(ttc_handle* h, const double* quad) {
+    if (!h) return TTC_ERR_ARG;
+    h->quad.clear();
+    if (quad) { size_t tot = 0; for (int p = 1; p <= h->d; ++p) tot += h->n[p]; h->quad.assign(quad, quad + tot); }
+    return TTC_OK;
+}
+int ttc_set_tru(ttc_handle* h, int present, double tru) { if (!h) return TTC_ERR_ARG; h->has_tru = present != 0; h->tru = tru; return TTC_OK; }
+int ttc_set_seed(ttc_handle* h, unsigned long long seed) { if (!h) return TTC_ERR_ARG; h->seed = seed; return TTC_OK; }
+int ttc_set_uniform_callback(ttc_handle* h, ttc_uniform_cb cb, void* ctx) { if (!h) return TTC_ERR_ARG; h->ucb = cb; h->ucb_ctx = ctx; return TTC_OK; }
+int ttc_set_verbose(ttc_handle* h, int v) { if (!h) return TTC_ERR_ARG; h->verbose = v; return TTC_OK; }
+int ttc_set_profile(ttc_handle* h, int on) { if (!h) return TTC_ERR_ARG; h->profile = on; return TTC_OK; }
+
+int ttc_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
+    if (!h) return TTC_ERR_ARG;
+    h->err.clear();
+    return run_dmrgg(h, maxrank, accuracy, pivoting);
+}
+
+int ttc_ranks(const ttc_handle* h, int* r) {
+    if (!h || !r) return TTC_ERR_ARG;
+    if (!h->ran) return TTC_ERR_STATE;
+    for (int p = 0; p <= h->d; ++p) r[p] = h->rk_h[p];
+    return TTC_OK;
+}
+int ttc_core(ttc_handle* h, int k, double* out) {
+    if (!h || !out || k < 1 || k > h->d) return TTC_ERR_ARG;
+    if (!h->ran) { h->err = "ttc_core before ttc_dmrgg"; return TTC_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    size_t cnt = (size_t)h->rk_h[k - 1] * h->n[k] * h->rk_h[k];
+    if (cnt > h->pack_cap) {
+        if (h->pack_d) cudaFree(h->pack_d);
+        h->pack_d = nullptr; h->pack_cap = 0;
+        CUDA_TRY(h, cudaMalloc((void**)&h->pack_d, cnt * sizeof(double)));
+        h->pack_cap = cnt;
+    }
+    k_pack_core<<<std::min(1024, cdiv((i64)cnt, 256)), 256, 0, h->stream>>>(h->plan, k, h->pack_d);
+    h->launches += 1;
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->pack_d, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return TTC_OK;
+}
+long long ttc_neval(const ttc_handle* h) { return h ? h->neval : 0; }
+int ttc_nsweeps(const ttc_handle* h) { return h ? h->nsweeps : 0; }
+double ttc_seconds(const ttc_handle* h) { return h ? h->seconds : 0; }
+int ttc_sweep_series(const ttc_handle* h, int which, double* out) {
+    if (!h || !out) return TTC_ERR_ARG;
+    const std::vector<double>* v = nullptr;
+    switch (which) {
+        case 0: v = &h->s_val; break; case 1: v = &h->s_neval; break; case 2: v = &h->s_amax; break;
+        case 3: v = &h->s_pivotmax; break; case 4: v = &h->s_erank; break; case 5: v = &h->s_time; break;
+        default: return TTC_ERR_ARG;
+    }
+    std::copy(v->begin(), v->end(), out);
+    return TTC_OK;
+}
+long ttc_pivlog_count(const ttc_handle* h) { return h ? (long)h->pivlog.size() : 0; }
+int ttc_pivlog(const ttc_handle* h, int* ints, double* vals) {
+    if (!h || !ints || !vals) return TTC_ERR_ARG;
+    for (size_t i = 0; i < h->pivlog.size(); ++i) {
+        const PivRec& r = h->pivlog[i];
+        int* o = ints + 8 * i;
+        o[0] = r.it; o[1] = r.vrank; o[2] = r.bond; o[3] = r.ii; o[4] = r.jj; o[5] = r.kk; o[6] = r.qq; o[7] = r.upd;
+        vals[i] = r.pivot;
+    }
+    return TTC_OK;
+}
+long ttc_text(const ttc_handle* h, char* buf, long cap) {
+    if (!h) return 0;
+    if (buf && cap > 0) { long c = std::min<long>(cap - 1, (long)h->text.size()); std::memcpy(buf, h->text.data(), c); buf[c] = 0; }
+    return (long)h->text.size();
+}
+
+int ttc_quad(ttc_handle* h, double* val) {
+    if (!h || !val) return TTC_ERR_ARG;
+    if (!h->ran) { h->err = "ttc_quad before ttc_dmrgg"; return TTC_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    Launcher L(h);
+    launch_quad(h, L, false, !h->quad.empty());
+    CUDA_TRY(h, cudaMemcpyAsync(h->sweep_h, h->plan.sweep_out, sizeof(SweepOut), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *val = h->sweep_h->val;
+    return TTC_OK;
+}
+
+// lib/quad.f90:97-131
+void ttc_lgwt(int n, double* x, double* w) {
+    const double tpi = 6.283185307179586476925286766559005768394338798750211641949889184615632812572417997256069650684234;
+    const double small = 5 * 2.220446049250313e-16;
+    const int m = (n + 1) / 2;
+    for (int i = 1; i <= m; ++i) {
+        double z = std::cos((tpi * (4 * i - 1)) / (8 * n + 4));
+        double p1, p2, p3, pp, z1;
+        do {
+            p1 = 1.0; p2 = 0.0;
+            for (int j = 1; j <= n; ++j) { p3 = p2; p2 = p1; p1 = ((2 * j - 1) * z * p2 - (j - 1) * p3) / j; }
+            pp = n * (z * p1 - p2) / (z * z - 1);
+            z1 = z;
+            z = z1 - p1 / pp;
+        } while (std::fabs(z - z1) > small);
+        x[i - 1] = -z; x[n - i] = z;
+        w[i - 1] = 2.0 / ((1 - z * z) * pp * pp);
+        w[n - i] = w[i - 1];
+    }
+}
+// lib/default.f90:80-97
+void ttc_share(int first, int last, int nproc, int* own) {
+    own[0] = first;
+    for (int p = 1; p <= nproc - 1; ++p) own[p] = first + (int)((double)(last - first + 1) * (double)p / nproc);
+    own[nproc] = last + 1;
+}
+double ttc_stream_uniform(unsigned long long seed, int vrank, unsigned long long k) { return stream_uniform(seed, vrank, k); }
+
+int ttc_l2_flush(ttc_handle* h, long long bytes) {
+    if (!h || bytes <= 0) return TTC_ERR_ARG;
+    int st = check_device(h);
+    if (st) return st;
+    if ((size_t)bytes > h->flush_cap) {
+        if (h->flush_d) cudaFree(h->flush_d);
+        h->flush_d = nullptr; h->flush_cap = 0;
+        CUDA_TRY(h, cudaMalloc(&h->flush_d, (size_t)bytes));
+        h->flush_cap = (size_t)bytes;
+    }
+    CUDA_TRY(h, cudaMemset(h->flush_d, 1, (size_t)bytes));
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    return TTC_OK;
+}
+
+long long ttc_launch_count(const ttc_handle* h) { return h ? h->launches : 0; }
+double ttc_device_ms(const ttc_handle* h) { return h ? h->device_ms : 0; }
+int ttc_profile(const ttc_handle* h, int cap, const char** names, long long* launches, double* ms) {
+    if (!h) return 0;
+    int c = std::min(cap, (int)KC_COUNT);
+    for (int i = 0; i < c; ++i) { if (names) names[i] = kclass_names[i]; if (launches) launches[i] = h->kc_launch[i]; if (ms) ms[i] = h->kc_ms[i]; }
+    return KC_COUNT;
+}
+
+int ttc_superblock_probe(ttc_handle* h, int bond, int store, int reps, long long* out_idx, double* out_val, double* ms, long long* count) {
+    if (!h || bond < 1 || bond > h->d - 1 || reps < 1) return TTC_ERR_ARG;
+    if (!h->ran) { h->err = "ttc_superblock_probe before ttc_dmrgg"; return TTC_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const DevPlan& D = h->plan;
+    cudaStream_t s = h->stream;
+    const i64 tot = (i64)h->rk_h[bond - 1] * h->n[bond] * h->n[bond + 1] * h->rk_h[bond + 1];
+    if (count) *count = tot;
+    double* a_out = nullptr;
+    if (store) CUDA_TRY(h, cudaMalloc((void**)&a_out, (size_t)tot * sizeof(double)));
+    Partial* pout = nullptr;
+    CUDA_TRY(h, cudaMalloc((void**)&pout, 2 * sizeof(Partial)));
+    const int TB = threads_for(h);
+    // persistent-style grid: a few CTAs per SM, grid-stride over the superblock
+    const int Gs = (int)std::min<i64>(GMAX, std::max<i64>(1, std::min<i64>((tot + TB - 1) / TB, (i64)h->nsm * (h->kind == TTC_MVN ? 8 : 6))));
+    const size_t smA = aux_smem(h);
+    auto launch = [&]() {
+        if (store) { KIND_SWITCH(h->kind, k_superblock<K, 1><<<Gs, TB, smA, s>>>(D, 1, 1, bond, 0, a_out)); }
+        else       { KIND_SWITCH(h->kind, k_superblock<K, 0><<<Gs, TB, smA, s>>>(D, 1, 1, bond, 0, nullptr)); }
+        h->launches += 1;
+    };
+    launch();   // warm-up
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, s);
+    for (int r = 0; r < reps; ++r) launch();
+    cudaEventRecord(b, s);
+    k_superblock_reduce<<<1, 128, 0, s>>>(D, 1, 1, Gs, bond, 0, pout);
+    h->launches += 1;
+    Partial hp[2];
+    cudaError_t e = cudaMemcpyAsync(hp, pout, sizeof hp, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    float t = 0; cudaEventElapsedTime(&t, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(pout); if (a_out) cudaFree(a_out);
+    if (e != cudaSuccess) { h->err = std::string("CUDA error: ") + cudaGetErrorString(e); return TTC_ERR_CUDA; }
+    if (ms) *ms = t / reps;
+    if (out_idx) { out_idx[0] = hp[0].idx; out_idx[1] = hp[1].idx; }
+    if (out_val) { out_val[0] = hp[0].val; out_val[1] = hp[1].val; }
+    return TTC_OK;
+}
+
+int ttc_fiber_probe(ttc_handle* h, int bond, int isrow, int ii, int jj, int kk, int qq, double* fiber, double* resid, int reps, double* ms) {
+    if (!h || bond < 1 || bond > h->d - 1 || reps < 1) return TTC_ERR_ARG;
+    if (!h->ran) { h->err = "ttc_fiber_probe before ttc_dmrgg"; return TTC_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const DevPlan& D = h->plan;
+    cudaStream_t s = h->stream;
+    int v = 0;
+    while (v < h->P - 1 && bond >= h->own[v + 1]) ++v;
+    const int pp = bond - h->own[v] + 1;
+    k_sweep_begin<<<cdiv(std::max(h->d + 1, h->P), 128), 128, 0, s>>>(D);   // rks := rk so every rank sees current sizes
+    VState S;
+    CUDA_TRY(h, cudaMemcpyAsync(&S, D.st + v, sizeof S, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    VState S0 = S;
+    S.ii = ii; S.jj = jj; S.kk = kk; S.qq = qq; S.done = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(D.st + v, &S, sizeof S, cudaMemcpyHostToDevice, s));
+    const int TB = threads_for(h);
+    const int cnt = isrow ? h->n[bond + 1] * h->rk_h[bond + 1] : h->rk_h[bond - 1] * h->n[bond];
+    const int G = std::min(GMAX, cdiv(cnt, TB));
+    const size_t smF = aux_smem(h) + (size_t)h->Rmax * sizeof(double);
+    // only virtual rank v must run: launch a 1-wide grid in y and shift the plan so blockIdx.y = 0 maps to v
+    DevPlan Dv = D;
+    Dv.own = D.own + v; Dv.P = 1; Dv.st = D.st + v; Dv.part = D.part + (size_t)v * 2 * GMAX;
+    Dv.acol1 = D.acol1 + (size_t)v * h->Rmax * h->nmax; Dv.bcol1 = D.bcol1 + (size_t)v * h->Rmax * h->nmax;
+    Dv.arow1 = D.arow1 + (size_t)v * h->Rmax * h->nmax; Dv.brow1 = D.brow1 + (size_t)v * h->Rmax * h->nmax;
+    auto launch = [&]() {
+        if (isrow) { KIND_SWITCH(h->kind, k_fiber<K, 1><<<dim3(G, 1), TB, smF, s>>>(Dv, 1, pp, 1)); }
+        else       { KIND_SWITCH(h->kind, k_fiber<K, 0><<<dim3(G, 1), TB, smF, s>>>(Dv, 1, pp, 1)); }
+        h->launches += 1;
+    };
+    launch();
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, s);
+    for (int r = 0; r < reps; ++r) launch();
+    cudaEventRecord(b, s);
+    cudaError_t e = cudaSuccess;
+    if (fiber) e = cudaMemcpyAsync(fiber, isrow ? Dv.arow1 : Dv.acol1, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && resid) e = cudaMemcpyAsync(resid, isrow ? Dv.brow1 : Dv.bcol1, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(D.st + v, &S0, sizeof S0, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    float t = 0; cudaEventElapsedTime(&t, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    if (e != cudaSuccess) { h->err = std::string("CUDA error: ") + cudaGetErrorString(e); return TTC_ERR_CUDA; }
+    if (ms) *ms = t / reps;
+    return TTC_OK;
+}
+
+// multi-GPU communicator: implemented in ttc_comm.cu
+int ttc_comm_unique_id(void* id128);
+int ttc_comm_init(ttc_handle* h, int nranks, int rank, const void* id128);
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+"""Host mirror of the reference driver programs' problem setup.
+
+test_crs_ising.f90:39-153, test_crs_mvn.f90:41-133, test_crs_stdnorm.f90:39-131, lib/mvn_pdf.f90:15-60.
+Only input generation lives here (nodes, weights, par blob, quadrature weights, analytic values); the
+sweep itself is the C-ABI library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import api
+
+EPS = 2.220446049250313e-16
+_dp = C.POINTER(C.c_double)
+
+
+def lgwt(n: int):
+    """Gauss-Legendre nodes/weights on [-1,1] (lib/quad.f90:97-131), computed by the library's host helper."""
+    L = api.load_library()
+    x = np.zeros(n)
+    w = np.zeros(n)
+    L.ttc_lgwt(n, x.ctypes.data_as(_dp), w.ctypes.data_as(_dp))
+    return x, w
+
+
+_TPI = 6.2831853071795864769
+_LOG2 = 0.69314718055994530942
+_ZETA3 = 1.2020569031595942854
+_C3 = 0.78130241289648629687
+# test_crs_ising.f90:71-100 rounded to double
+ISING_TRU = {
+    ("c", 2): 1.0, ("c", 3): _C3, ("c", 4): 0.70119986017642999982, ("c", 5): 0.66575980019993742832,
+    ("c", 6): 0.64863420903100707526, ("c", 8): 0.63548402675916322614, ("c", 16): 0.63050394617323726351,
+    ("c", 32): 0.63047350420733980638, ("c", 64): 0.63047350337438679649, ("c", 128): 0.63047350337438679612,
+    ("c", 256): 0.63047350337438679612, ("c", 512): 0.63047350337438679612, ("c", 1024): 0.63047350337438679612,
+    ("d", 2): 1.0 / 3, ("d", 3): 8.0 + _TPI ** 2 / 3 - 27.0 * _C3, ("d", 4): _TPI ** 2 / 9.0 - 1.0 / 6 - 7.0 * _ZETA3 / 2,
+    ("d", 5): 0.0024846057623403154800, ("d", 6): 0.00048914170018803477510,
+    ("e", 2): 6.0 - 8.0 * _LOG2, ("e", 3): 10.0 - _TPI ** 2 / 2 - 8.0 * _LOG2 + 32.0 * _LOG2 ** 2,
+    ("e", 4): 22.0 - 82.0 * _ZETA3 - 24.0 * _LOG2 + 176.0 * _LOG2 ** 2 - 256.0 * _LOG2 ** 3 / 3
+    + 4.0 * (_TPI ** 2) * _LOG2 - 11.0 * _TPI ** 2 / 6.0,
+    ("e", 5): 0.0034936537117295217407, ("e", 6): 0.00068783287182640943700,
+}
+
+
+@dataclass
+class Problem:
+    kind: int
+    d: int
+    n: np.ndarray
+    par: np.ndarray
+    aux: np.ndarray
+    quad: np.ndarray
+    accuracy: float
+    tru: float          # 0.0 = absent
+    label: str = ""
+    extra: dict = field(default_factory=dict)
+
+    def make(self, device: int = 0, use_quad: bool = True, use_tru: bool = True) -> "api.TTCross":
+        t = api.TTCross(self.kind, self.n, self.par, self.aux, device=device)
+        if use_quad:
+            t.set_quad(self.quad)
+        if use_tru and self.tru != 0.0:
+            t.set_tru(self.tru)
+        return t
+
+
+def ising(a: str, index: int, n: int) -> Problem:
+    a = a.lower()
+    if a not in ("c", "d", "e"):
+        raise ValueError(f"unknown integral type: {a}")
+    m = index
+    if n % 2 == 0:
+        n += 1
+    x, w = lgwt(n)
+    w = 0.5 * w
+    x = (x + 1.0) / 2
+    rescale = a in ("d", "e") and m >= 10
+    val = float(n // 2)
+    w = ((5.0 * val) if rescale else val) * w
+    par = np.zeros(2 * n + 1)
+    par[:n] = x
+    par[n:2 * n] = w
+    par[2 * n] = {"c": 1.0, "d": 2.0, "e": 3.0}[a]
+    d = m - 1
+    return Problem(api.ISING, d, np.full(d, n, dtype=np.int32), par, np.zeros(0), np.full(d * n, 1.0 / val), 500 * EPS,
+                   ISING_TRU.get((a, m), 0.0), f"test_crs_ising {a} {m} {n}", {"rescale": rescale})
+
+
+def _interval(n: int, a: float, b: float):
+    if n % 2 == 0:
+        n += 1
+    x, w = lgwt(n)
+    return n, 0.5 * ((b - a) * x + (a + b)), (0.5 * (b - a)) * w
+
+
+def stdnorm(d: int, n: int) -> Problem:
+    n, x, w = _interval(n, -10.0, 10.0)
+    return Problem(api.STDNORM, d, np.full(d, n, dtype=np.int32), np.concatenate([x, w]), np.zeros(0), np.tile(w, d), 5 * EPS,
+                   math.sqrt(3.141592653589793238) ** d, f"test_crs_stdnorm {d} {n}")
+
+
+def _powi(x: float, m: int) -> float:
+    n = abs(m)
+    y = x if n % 2 else 1.0
+    n >>= 1
+    while n:
+        x = x * x
+        if n % 2:
+            y *= x
+        n >>= 1
+    return 1.0 / y if m < 0 else y
+
+
+def mvn_init(n: int, r: float = 0.0, T: float = 1.0):
+    """lib/mvn_pdf.f90:15-60,85-111 (dgetrf/dgetri through numpy's LAPACK)."""
+    sigma, corr = 0.4, 0.5
+    mu = np.full(n, math.log(100.0) + (r - 0.5 * (sigma * sigma)) * T)
+    cov = np.full((n, n), (sigma * corr * sigma) * T)
+    np.fill_diagonal(cov, (sigma * sigma) * T)
+    inv = np.linalg.inv(cov)
+    sign, logdet = np.linalg.slogdet(cov)
+    det = float(sign * math.exp(logdet)) if n > 40 else float(np.linalg.det(cov))
+    return mu, inv, det
+
+
+def mvn(d: int, n: int) -> Problem:
+    a = float(np.float32(0.525170))   # single-precision literals in test_crs_mvn.f90:75-76
+    b = float(np.float32(8.525170))
+    n, x, w = _interval(n, a, b)
+    mu, inv, det = mvn_init(d)
+    denom = math.sqrt(_powi(2.0 * 3.141592653589793, d) * det)
+    aux = np.concatenate([mu, np.asfortranarray(inv).ravel(order="F"), [denom]])
+    return Problem(api.MVN, d, np.full(d, n, dtype=np.int32), np.concatenate([x, w]), aux, np.tile(w, d), 500 * EPS, 1.0,
+                   f"test_crs_mvn {d} {n}")
