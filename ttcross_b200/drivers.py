@@ -115,15 +115,32 @@ def _powi(x: float, m: int) -> float:
     return 1.0 / y if m < 0 else y
 
 
+def _inv_det(a):
+    """Gauss-Jordan with partial pivoting, elementwise IEEE operations only (bit-deterministic on every host; the reference
+    uses LAPACK dgetrf/dgetri whose bits depend on the linked BLAS, so any correct inverse is admissible: it is input data)."""
+    n = a.shape[0]
+    m = np.concatenate([np.array(a, dtype=np.float64), np.eye(n)], axis=1)
+    det = 1.0
+    for k in range(n):
+        piv = k + int(np.argmax(np.abs(m[k:, k])))
+        if piv != k:
+            m[[k, piv]] = m[[piv, k]]
+            det = -det
+        det = det * m[k, k]
+        m[k] = m[k] / m[k, k]
+        for i in range(n):
+            if i != k and m[i, k] != 0.0:
+                m[i] = m[i] - m[i, k] * m[k]
+    return m[:, n:].copy(), det
+
+
 def mvn_init(n: int, r: float = 0.0, T: float = 1.0):
-    """lib/mvn_pdf.f90:15-60,85-111 (dgetrf/dgetri through numpy's LAPACK)."""
+    """lib/mvn_pdf.f90:15-60,85-111 (dgetrf/dgetri -> a deterministic Gauss-Jordan)."""
     sigma, corr = 0.4, 0.5
     mu = np.full(n, math.log(100.0) + (r - 0.5 * (sigma * sigma)) * T)
     cov = np.full((n, n), (sigma * corr * sigma) * T)
     np.fill_diagonal(cov, (sigma * sigma) * T)
-    inv = np.linalg.inv(cov)
-    sign, logdet = np.linalg.slogdet(cov)
-    det = float(sign * math.exp(logdet)) if n > 40 else float(np.linalg.det(cov))
+    inv, det = _inv_det(cov)
     return mu, inv, det
 
 
