@@ -65,6 +65,10 @@ int ttc_set_seed(ttc_handle* h, unsigned long long seed);           /* uniform s
 /* Alternative uniform source: cb(ctx, vrank, count, out) must write `count` uniforms in [0,1) for virtual rank `vrank`. */
 typedef void (*ttc_uniform_cb)(void* ctx, int vrank, int count, double* out);
 int ttc_set_uniform_callback(ttc_handle* h, ttc_uniform_cb cb, void* ctx);
+/* 0 (default): lottery on the device, sweeps enqueued asynchronously; 1: lottery on the host exactly as rnd.f90:105-126
+ * writes it (one stream synchronisation per bond visit; implied by a uniform callback); 2: device lottery, synchronous.
+ * All three produce identical pivots; modes 1 and 2 exist to prove that. */
+int ttc_set_lottery_mode(ttc_handle* h, int mode);
 int ttc_set_verbose(ttc_handle* h, int verbose);                    /* 1: print the reference's per-sweep lines on stdout */
 
 /* ---- the sweep: dtt_dmrgg (lib/dmrgg.f90:11) -------------------------------
@@ -107,6 +111,9 @@ int ttc_superblock_probe(ttc_handle* h, int bond, int store, int reps, long long
  * the fiber values (r(p-1)*n(p) or n(p+1)*r(p+1) doubles) and its residual. */
 int ttc_fiber_probe(ttc_handle* h, int bond, int isrow, int ii, int jj, int kk, int qq, double* fiber, double* resid,
                     int reps, double* ms);
+/* The device lottery's closed-form cumulative weights, executed on the host (test hook): cells[x] = the 1-based cell that
+ * lottery2 (rnd.f90:105-126) picks for uniform u[x] among m cells of weight 1 except the listed zero-weight cells. */
+int ttc_lottery_closed_form(int m, const int* zeros_sorted_distinct, int nz, const double* u, int count, int* cells);
 /* Counters: kernels launched by this handle since creation, device time of the last ttc_dmrgg (CUDA events, ms) */
 long long ttc_launch_count(const ttc_handle* h);
 /* write `bytes` (> L2 size) of scratch HBM so the next timed run starts with a cold L2 (measurement hygiene) */

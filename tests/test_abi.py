@@ -114,3 +114,37 @@ def test_product_never_touches_the_oracle():
                     assert needle not in src, f"{f} references the oracle ({needle})"
     out = subprocess.check_output(["ldd", T.build.LIB], text=True)
     assert "oracle" not in out
+
+
+def test_closed_form_lottery_matches_literal_loop():
+    """The device lottery evaluates lottery2's sequentially accumulated cumulative weights in closed form (piecewise linear
+    in exact integer arithmetic).  Here the same code runs on the host and is compared with the literal loop of
+    rnd.f90:115-125 (the oracle), including uniforms placed exactly on and next to the cumulative boundaries."""
+    L = T.load_library()
+    L.ttc_lottery_closed_form.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]
+    rng = np.random.default_rng(1)
+    for trial in range(60):
+        m = int(rng.integers(2, 40000)) if trial % 3 else int(rng.integers(2, 200))
+        nz = int(rng.integers(0, min(64, m - 1) + 1))
+        zeros = np.sort(rng.choice(m, nz, replace=False) + 1).astype(np.int32)
+        w = np.ones(m)
+        w[zeros - 1] = 0
+        cnt = 1000
+        u = rng.random(cnt)
+        scol = m - nz
+        Tt = np.zeros(scol + 1)
+        for c in range(1, scol + 1):
+            Tt[c] = Tt[c - 1] + 1.0 / scol
+        pick = rng.integers(1, scol + 1, size=600)
+        u[:200] = Tt[pick[:200]]
+        u[200:400] = np.nextafter(Tt[pick[200:400]], 0)
+        u[400:600] = np.nextafter(Tt[pick[400:600]], 2)
+        u[600:604] = [0.0, np.nextafter(1.0, 0), Tt[scol], np.nextafter(Tt[scol], 0)]
+        u = np.clip(u, 0, np.nextafter(1.0, 0))
+        cells = np.zeros(cnt, dtype=np.int32)
+        assert L.ttc_lottery_closed_form(m, zeros.ctypes.data_as(C.POINTER(C.c_int)), nz, u.ctypes.data_as(C.POINTER(C.c_double)),
+                                         cnt, cells.ctypes.data_as(C.POINTER(C.c_int))) == 0
+        uu = np.concatenate([u, np.zeros(cnt)])
+        pts = np.zeros(2 * cnt, dtype=np.int32)
+        O.lib().tto_lottery2(cnt, m, 1, O._dp(w), O._dp(np.ones(1)), O._dp(uu), O._ip(pts))
+        assert np.array_equal(pts[:cnt], cells), f"trial {trial}: m={m} nz={nz}"

@@ -60,3 +60,40 @@ def test_mvn(d, n, R, piv, P):
     p = T.drivers.mvn(d, n)
     t, g, o = run_both(p, R, piv, P=P)
     assert_parity(t, g, o, exact=False, rtol=1e-10)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("kind,index,n,R,piv,P", [("c", 6, 64, 16, 1, 1), ("d", 6, 16, 8, 2, 2), ("c", 10, 32, 10, 2, 8)])
+def test_lottery_modes_agree(mode, kind, index, n, R, piv, P):
+    """mode 1 draws the lottery on the host with the literal loop of rnd.f90; mode 0/2 draw it on the device in closed form."""
+    p = T.drivers.ising(kind, index, n)
+    t0 = p.make(); t0.set_partition(P); g0 = t0.dmrgg(R, p.accuracy, piv)
+    t1 = p.make(); t1.set_partition(P); t1.set_lottery_mode(mode); g1 = t1.dmrgg(R, p.accuracy, piv)
+    assert np.array_equal(g0.pivlog, g1.pivlog) and np.array_equal(g0.pivots, g1.pivots)
+    assert np.array_equal(g0.vals, g1.vals) and g0.neval == g1.neval
+    assert g0.text.split("time:")[0] == g1.text.split("time:")[0]
+
+
+def test_accuracy_exit_and_log_format():
+    # loose accuracy: three consecutive sweeps with pivotmax <= accuracy * amax end the run (dmrgg.f90:1012-1019)
+    p = T.drivers.ising("c", 6, 32)
+    t, g, o = run_both(p, 30, 1, accuracy=1e-6)
+    assert_parity(t, g, o, exact=True)
+    assert g.nsweeps < 29
+    lines_g, lines_o = g.text.strip().split("\n"), o.text.strip().split("\n")
+    assert len(lines_g) == len(lines_o) == g.nsweeps + 1
+    import re
+    strip = lambda x: re.sub(r"time: \S+", "time: *", x)
+    for a, b in zip(lines_g, lines_o):
+        assert strip(a) == strip(b), (a, b)       # identical apart from the time field
+
+
+def test_repeated_runs_reuse_buffers_and_agree():
+    p = T.drivers.ising("c", 6, 32)
+    t = p.make(); t.set_partition(2)
+    g1 = t.dmrgg(10, p.accuracy, 2)
+    c1 = t.cores()
+    g2 = t.dmrgg(10, p.accuracy, 2)
+    assert np.array_equal(g1.pivlog, g2.pivlog) and np.array_equal(g1.vals, g2.vals)
+    for a, b in zip(c1, t.cores()):
+        assert np.array_equal(a, b)

@@ -49,6 +49,7 @@ def load_library(build_if_missing: bool = True):
     L.ttc_set_tru.argtypes = [vp, C.c_int, C.c_double]
     L.ttc_set_seed.argtypes = [vp, C.c_ulonglong]
     L.ttc_set_verbose.argtypes = [vp, C.c_int]
+    L.ttc_set_lottery_mode.argtypes = [vp, C.c_int]
     L.ttc_set_profile.argtypes = [vp, C.c_int]
     L.ttc_dmrgg.argtypes = [vp, C.c_int, C.c_double, C.c_int]
     L.ttc_ranks.argtypes = [vp, _ip]
@@ -164,6 +165,9 @@ class TTCross:
 
     def set_seed(self, seed: int):
         self._check(self._L.ttc_set_seed(self.h, seed))
+
+    def set_lottery_mode(self, mode: int):
+        self._check(self._L.ttc_set_lottery_mode(self.h, mode))
 
     def set_verbose(self, v: bool):
         self._check(self._L.ttc_set_verbose(self.h, int(v)))

@@ -18,6 +18,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
+#include <math.h>
 
 namespace ttc {
 
@@ -36,6 +38,7 @@ struct VState {            // one per virtual rank, device resident
     int upd, pad0;
     double amax, pivotmax, pivotmin, pivotmax_prev;
     i64 neval;
+    unsigned long long rng_k;   // position in this virtual rank's uniform stream
 };
 struct VisitOut {          // what the host reads back after a bond visit
     int active, upd, bond, ii, jj, kk, qq, pad;
@@ -44,7 +47,19 @@ struct VisitOut {          // what the host reads back after a bond visit
 struct SweepOut {
     double val, amax, pivotmax, pivotmin;
     i64 neval;
+    unsigned long long t_ns;    // %globaltimer at the end of the sweep
+    int valid, pad;
 };
+struct Ctrl {                   // device-side control of the asynchronous sweep loop
+    int ready;                  // exit condition reached (dmrgg.f90:1010-1019): later sweeps are no-ops
+    int strike;
+    int error;                  // 1: rank capacity exceeded
+    int nsweeps;                // sweeps actually performed
+    unsigned long long t0_ns;
+};
+// exact restatement of lottery2's cumulative weights (rnd.f90:115-125) for 0/1 weights, see build_segments()
+struct LotSeg { long long M; long long k; int c0; int J; int E; int pad; };
+constexpr int MAXSEG = 128;
 
 struct DevPlan {
     int d, P, Rmax, nmax, piv, kind, ising_id, nlotmax;
@@ -69,6 +84,15 @@ struct DevPlan {
     double* chain;         // [P+1][Rmax*Rmax] partial products
     double* chain2;        // scratch, same size
     SweepOut* sweep_out;
+    // asynchronous mode: nothing below needs the host during the sweeps
+    unsigned long long seed;
+    int dev_lottery;       // 1: lottery on the device (built-in uniform stream), 0: host fills `lot`
+    int maxnb, maxsweeps;
+    int has_accuracy; double accuracy;
+    Ctrl* ctrl;
+    VisitOut* vlog;        // [maxsweeps][maxnb][P]
+    SweepOut* slog;        // [maxsweeps + 1]
+    int* rklog;            // [maxsweeps + 1][d + 1]
 };
 
 // ----------------------------------------------------------------------------
@@ -256,10 +280,113 @@ __device__ __forceinline__ Partial amax_block(Partial a, Partial* sh) {
 }
 
 // ----------------------------------------------------------------------------
+// device-side lottery (rnd.f90:105-144 + dmrgg.f90:425-452), bit-exact.
+//
+// The reference draws a cell from cumulative weights pcol(i) = pcol(i-1) + |w_i|/scol accumulated SEQUENTIALLY in
+// double precision.  Weights are 1 except 0 at the existing pivots, so pcol(i) = T[c(i)] with c(i) = number of non-zero
+// weights among the first i cells and T[c] = fl(T[c-1] + delta), delta = fl(1/scol).  T is strictly increasing, hence
+// find_d's bisection returns the unique cell whose count c* satisfies T[c*-1] <= y < T[c*] whatever path it takes.
+// T is evaluated in closed form: inside one binade the rounded increment is a constant integer number of ulps
+// (round-to-nearest; a tie settles into a constant after one step), so T is piecewise linear in exact integer
+// arithmetic; the (few) steps that cross a binade are done with a real floating-point addition.
+// ----------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ double stream_uniform(unsigned long long seed, int vrank, unsigned long long k) {
+    const unsigned long long G = 0x9E3779B97F4A7C15ULL;
+    unsigned long long base = mix64(seed + G * (unsigned long long)(vrank + 1));
+    unsigned long long z = mix64(base + G * (k + 1));
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+__host__ __device__ __forceinline__ long long dbl_bits(double x) {
+#ifdef __CUDA_ARCH__
+    return __double_as_longlong(x);
+#else
+    long long b; memcpy(&b, &x, sizeof b); return b;
+#endif
+}
+// segments cover counts 1..scol; returns the number of segments
+__host__ __device__ inline int build_segments(int scol, LotSeg* seg) {
+    const double delta = 1.0 / (double)scol;
+    const long long db = dbl_bits(delta);
+    const int Ed = (int)((db >> 52) & 0x7ff) - 1023;
+    const long long Md = (db & ((1LL << 52) - 1)) | (1LL << 52);
+    int c = 1, ns = 0;
+    double T = delta;
+    while (true) {
+        const long long tb = dbl_bits(T);
+        const int E = (int)((tb >> 52) & 0x7ff) - 1023;
+        const long long M = (tb & ((1LL << 52) - 1)) | (1LL << 52);
+        const int sh = E - Ed;
+        const long long q = Md >> sh;
+        const long long rem = Md & ((1LL << sh) - 1);
+        const long long half = sh ? (1LL << (sh - 1)) : 0;
+        long long k = q;
+        bool single = false;
+        if (sh > 0) {
+            if (rem > half) k = q + 1;
+            else if (rem == half) { if (M & 1) single = true; else k = q + (q & 1); }   // ties to even
+        }
+        // a step from mantissa m is an in-binade step iff m + q <= 2^53 - 1 (exact sum stays below the next power of two)
+        const long long lim = (1LL << 53) - 1 - q - M;
+        long long J = (single || lim < 0) ? 0 : lim / k + 1;
+        if (J > scol - c) J = scol - c;
+        if (ns < MAXSEG) { seg[ns].M = M; seg[ns].k = k; seg[ns].c0 = c; seg[ns].J = (int)J; seg[ns].E = E; ++ns; }
+        c += (int)J;
+        if (c >= scol) break;
+        T = scalbn((double)(M + J * k), E - 52);
+        T = T + delta;              // binade-crossing (or odd-tie) step: hardware rounding
+        c += 1;
+    }
+    return ns;
+}
+__host__ __device__ __forceinline__ double lot_T(const LotSeg* seg, int ns, int c) {   // T[c], 1 <= c <= scol
+    int lo = 0, hi = ns - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (seg[mid].c0 <= c) lo = mid; else hi = mid - 1; }
+    const LotSeg& g = seg[lo];
+    return scalbn((double)(g.M + (long long)(c - g.c0) * g.k), g.E - 52);
+}
+// one draw: 1-based cell index in 1..m (zeros = sorted distinct 1-based zero-weight cells)
+__host__ __device__ __forceinline__ int lot_draw(const LotSeg* seg, int ns, int scol, int m, const int* zeros, int nz, double y) {
+    if (!(y < lot_T(seg, ns, scol))) return m;          // x(n) <= y  ->  n = m+1, clamped to m (rnd.f90:122)
+    int lo = 1, hi = scol;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (y < lot_T(seg, ns, mid)) hi = mid; else lo = mid + 1; }
+    int sidx = lo;                                       // the lo-th cell of non-zero weight
+    for (int z = 0; z < nz; ++z) { if (zeros[z] <= sidx) ++sidx; else break; }
+    return sidx;
+}
+// sorted distinct zero-weight cells (1-based) of one side of bond p; thread-parallel rank sort over the r1 pivots.
+// tmp, zeros: shared int[>= r1]; *nz: shared int.  side 0: (i,j) with stride r0; side 1: (k,q) with stride n2.
+__device__ __forceinline__ void lot_zeros(const int* vip_p, int r1, int side, int stride, int* tmp, int* zeros, int* nz) {
+    for (int t = threadIdx.x; t < r1; t += blockDim.x)
+        zeros[t] = (vip_p[4 * t + 2 * side] - 1) + stride * (vip_p[4 * t + 2 * side + 1] - 1) + 1;
+    __syncthreads();
+    for (int t = threadIdx.x; t < r1; t += blockDim.x) {          // stable rank sort (duplicates kept)
+        int me = zeros[t], rank = 0;
+        for (int u = 0; u < r1; ++u) { int o = zeros[u]; rank += (o < me) || (o == me && u < t); }
+        tmp[rank] = me;
+    }
+    __syncthreads();
+    int keep = 0, pos = 0;
+    for (int t = threadIdx.x; t < r1; t += blockDim.x) {          // compact the distinct values (r1 <= blockDim.x expected, loop anyway)
+        keep = (t == 0) || (tmp[t] != tmp[t - 1]);
+        pos = 0;
+        for (int u = 1; u <= t; ++u) pos += (tmp[u] != tmp[u - 1]);
+        if (keep) zeros[pos] = tmp[t];
+        if (t == r1 - 1) *nz = pos + 1;
+    }
+    __syncthreads();
+}
+
+// ----------------------------------------------------------------------------
 // K1: lottery candidates (dmrgg.f90:447-484): evaluate, residual by sequential ddot, two argmaxes
 // ----------------------------------------------------------------------------
 template <int KIND>
 __global__ void k_lot(DevPlan P, int dir, int pp) {
+    if (P.ctrl->ready) return;
     extern __shared__ double smem[];
     __shared__ Partial shp[32];
     const int v = blockIdx.y;
@@ -267,7 +394,34 @@ __global__ void k_lot(DevPlan P, int dir, int pp) {
     if (!D.active) return;
     const double* A = stage_aux<KIND>(P, smem);
     const int nlot = D.r0 + D.n1 + D.n2 + D.r2;
-    const int* lot = P.lot + (i64)v * 4 * P.nlotmax;
+    int* lot = P.lot + (i64)v * 4 * P.nlotmax;
+    if (P.dev_lottery) {
+        // every CTA rebuilds the (tiny) cumulative-weight description; each thread then draws its own candidates
+        __shared__ LotSeg seg[2][MAXSEG];
+        __shared__ int s_ns[2], s_nz[2];
+        int* ibuf = (int*)(smem + P.auxsm);           // tmp[Rmax] | zeros_col[Rmax] | zeros_row[Rmax]
+        int* tmp = ibuf; int* zc = ibuf + P.Rmax; int* zr = ibuf + 2 * P.Rmax;
+        const int* vip_p = P.vip + (i64)D.p * P.Rmax * 4;
+        const int m = D.r0 * D.n1, n = D.n2 * D.r2;
+        lot_zeros(vip_p, D.r1, 0, D.r0, tmp, zc, &s_nz[0]);
+        lot_zeros(vip_p, D.r1, 1, D.n2, tmp, zr, &s_nz[1]);
+        if (threadIdx.x == 0)  s_ns[0] = build_segments(m - s_nz[0], seg[0]);
+        if (threadIdx.x == 32 % blockDim.x && blockDim.x > 32) s_ns[1] = build_segments(n - s_nz[1], seg[1]);
+        if (blockDim.x <= 32 && threadIdx.x == 0) s_ns[1] = build_segments(n - s_nz[1], seg[1]);
+        __syncthreads();
+        const unsigned long long k0 = P.st[v].rng_k;
+        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < nlot; x += gridDim.x * blockDim.x) {
+            double uc = stream_uniform(P.seed, v, k0 + (unsigned long long)x);
+            double ur = stream_uniform(P.seed, v, k0 + (unsigned long long)(nlot + x));
+            int c = lot_draw(seg[0], s_ns[0], m - s_nz[0], m, zc, s_nz[0], uc);
+            int w = lot_draw(seg[1], s_ns[1], n - s_nz[1], n, zr, s_nz[1], ur);
+            lot[x] = (c - 1) % D.r0 + 1;
+            lot[P.nlotmax + x] = (c - 1) / D.r0 + 1;
+            lot[2 * P.nlotmax + x] = (w - 1) % D.n2 + 1;
+            lot[3 * P.nlotmax + x] = (w - 1) / D.n2 + 1;
+        }
+        // (each thread reads back only the entries it wrote itself)
+    }
     const double* colp = P.col + P.coreOff[D.p];
     const double* rowp = P.rowT + P.coreOff[D.p + 1];
     const i64 cs = (i64)P.Rmax * D.n1;       // stride of s in col(i,j,s)
@@ -302,6 +456,7 @@ __device__ __forceinline__ Partial reduce_parts(const Partial* parts, int G, Par
 }
 
 __global__ void k_lot_reduce(DevPlan P, int dir, int pp, int G) {
+    if (P.ctrl->ready) return;
     __shared__ Partial shp[32];
     const int v = blockIdx.y;
     const Dims D = load_dims(P, v, dir, pp);
@@ -318,6 +473,7 @@ __global__ void k_lot_reduce(DevPlan P, int dir, int pp, int G) {
         S.pivot = bres.val;
         S.done = 0; S.havecol = 0; S.haverow = 0; S.crs = 0; S.upd = 0;
         S.neval += nlot;
+        S.rng_k += 2ULL * (unsigned long long)nlot;     // one random_number(d(npnt,2)) call (rnd.f90:120)
     }
 }
 
@@ -329,6 +485,7 @@ __global__ void k_lot_reduce(DevPlan P, int dir, int pp, int G) {
 // ----------------------------------------------------------------------------
 template <int KIND, int ISROW>
 __global__ void k_fiber(DevPlan P, int dir, int pp, int mode) {
+    if (P.ctrl->ready) return;
     extern __shared__ double smem[];
     __shared__ Partial shp[32];
     const int v = blockIdx.y;
@@ -386,6 +543,7 @@ __global__ void k_fiber(DevPlan P, int dir, int pp, int mode) {
 // the scalar bookkeeping after a fiber (dmrgg.f90:527-547, 560-580)
 template <int ISROW>
 __global__ void k_fiber_reduce(DevPlan P, int dir, int pp, int mode, int G) {
+    if (P.ctrl->ready) return;
     __shared__ Partial shp[32];
     const int v = blockIdx.y;
     const Dims D = load_dims(P, v, dir, pp);
@@ -435,6 +593,7 @@ __global__ void k_superblock(DevPlan P, int dir, int pp, int fixed_bond, int fix
         D.active = 1; D.p = fixed_bond; D.r0 = P.rk[D.p - 1]; D.r1 = P.rk[D.p]; D.r2 = P.rk[D.p + 1];
         D.n1 = P.n[D.p]; D.n2 = P.n[D.p + 1];
     } else {
+        if (P.ctrl->ready) return;
         D = load_dims(P, v, dir, pp);
     }
     if (!D.active) return;
@@ -476,6 +635,7 @@ __global__ void k_superblock_reduce(DevPlan P, int dir, int pp, int G, int fixed
         D.active = 1; D.p = fixed_bond; D.r0 = P.rk[D.p - 1]; D.r1 = P.rk[D.p]; D.r2 = P.rk[D.p + 1];
         D.n1 = P.n[D.p]; D.n2 = P.n[D.p + 1];
     } else {
+        if (P.ctrl->ready) return;
         D = load_dims(P, v, dir, pp);
     }
     if (!D.active) return;
@@ -499,16 +659,18 @@ __global__ void k_superblock_reduce(DevPlan P, int dir, int pp, int G, int fixed
 // ----------------------------------------------------------------------------
 // K4: accept test and index-set update (dmrgg.f90:598-660)
 // ----------------------------------------------------------------------------
-__global__ void k_accept(DevPlan P, int dir, int pp, double small_element, double small_pivot) {
+__global__ void k_accept(DevPlan P, int it, int dir, int pp, double small_element, double small_pivot) {
+    if (P.ctrl->ready) return;
     const int v = blockIdx.y;
     const Dims D = load_dims(P, v, dir, pp);
-    VisitOut& O = P.out[v];
+    VisitOut& O = P.vlog[((i64)(it - 1) * P.maxnb + (pp - 1)) * P.P + v];
     if (!D.active) { if (threadIdx.x == 0) { O.active = 0; O.upd = 0; } return; }
     VState& S = P.st[v];
     __shared__ int s_upd;
     if (threadIdx.x == 0) {
         double ap = fabs(S.pivot);
         int upd = (ap > small_element * S.amax) && (ap > small_pivot * S.pivotmax_prev);
+        if (upd && D.r1 >= P.Rmax) { upd = 0; P.ctrl->error = 1; }      // rank capacity (only without maxrank)
         s_upd = upd;
         S.upd = upd;
         O.active = 1; O.upd = upd; O.bond = D.p; O.ii = S.ii; O.jj = S.jj; O.kk = S.kk; O.qq = S.qq; O.pivot = S.pivot;
@@ -550,6 +712,7 @@ __global__ void k_accept(DevPlan P, int dir, int pp, double small_element, doubl
 // the residual of the last column (row) fiber IS the dgemv of d2_lual (d2_luar) with the same operands and order.
 // ----------------------------------------------------------------------------
 __global__ void k_update_main(DevPlan P, int dir, int pp) {
+    if (P.ctrl->ready) return;
     const int v = blockIdx.y;
     const Dims D = load_dims(P, v, dir, pp);
     if (!D.active) return;
@@ -584,6 +747,7 @@ __global__ void k_update_main(DevPlan P, int dir, int pp) {
 // neighbour factors (dmrgg.f90:715-749): new column of row(p) through d2_luar(inv(p-1)), new row of col(p+1)
 // through d2_lual(inv(p+1)).  One thread per mode index; the triangular recurrences are sequential by definition.
 __global__ void k_update_nbr(DevPlan P, int dir, int pp) {
+    if (P.ctrl->ready) return;
     const int v = blockIdx.y;
     const Dims D = load_dims(P, v, dir, pp);
     if (!D.active) return;
@@ -631,6 +795,7 @@ __global__ void k_update_nbr(DevPlan P, int dir, int pp) {
 }
 
 __global__ void k_end_visit(DevPlan P, int dir, int pp) {
+    if (P.ctrl->ready) return;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= P.P) return;
     const Dims D = load_dims(P, v, dir, pp);
@@ -642,12 +807,14 @@ __global__ void k_end_visit(DevPlan P, int dir, int pp) {
 // sweep begin / end
 // ----------------------------------------------------------------------------
 __global__ void k_sweep_begin(DevPlan P) {
+    if (P.ctrl->ready) return;
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x <= P.d) P.rks[x] = P.rk[x];
     if (x < P.P) { P.st[x].pivotmax = -1.0; P.st[x].pivotmin = -1.0; }
 }
 // MPI_ALLREDUCE(MAX) of (amax, pivotmax, -pivotmin) (dmrgg.f90:852-870); single thread, P is small
 __global__ void k_allreduce(DevPlan P) {
+    if (P.ctrl->ready) return;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (P.P > 1) {
         double c1 = P.st[0].amax, c2 = P.st[0].pivotmax, c3 = (P.st[0].pivotmin > 0.0) ? -P.st[0].pivotmin : -999e9;
@@ -662,6 +829,7 @@ __global__ void k_allreduce(DevPlan P) {
     }
 }
 __global__ void k_sweep_end(DevPlan P) {
+    if (P.ctrl->ready) return;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     i64 ne = 0;
     for (int v = 0; v < P.P; ++v) ne += P.st[v].neval;
@@ -670,6 +838,36 @@ __global__ void k_sweep_end(DevPlan P) {
     P.sweep_out->pivotmax = P.st[0].pivotmax;
     P.sweep_out->pivotmin = P.st[0].pivotmin;
     for (int v = 0; v < P.P; ++v) P.st[v].pivotmax_prev = P.st[v].pivotmax;   // dmrgg.f90:961
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void k_run_begin(DevPlan P) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    P.ctrl->ready = 0; P.ctrl->strike = 0; P.ctrl->error = 0; P.ctrl->nsweeps = 0;
+    P.ctrl->t0_ns = globaltimer_ns();
+}
+// record of sweep `it` (after the quadrature) + the exit test of dmrgg.f90:1010-1019
+__global__ void k_sweep_log(DevPlan P, int it, int maxrank) {
+    if (P.ctrl->ready) return;
+    for (int x = threadIdx.x; x <= P.d; x += blockDim.x) P.rklog[(i64)it * (P.d + 1) + x] = P.rk[x];
+    if (threadIdx.x != 0) return;
+    SweepOut o = *P.sweep_out;
+    o.t_ns = globaltimer_ns() - P.ctrl->t0_ns;
+    o.valid = 1;
+    P.slog[it] = o;
+    P.ctrl->nsweeps = it;
+    int ready = 0;
+    if (maxrank > 0) ready = (it + 1 >= maxrank);
+    if (P.has_accuracy) {
+        if (o.pivotmax <= P.accuracy * o.amax) P.ctrl->strike += 1; else P.ctrl->strike = 0;
+        ready = ready || (P.ctrl->strike >= 3);
+    }
+    if (P.ctrl->error) ready = 1;
+    __threadfence();
+    P.ctrl->ready = ready;
 }
 
 // ----------------------------------------------------------------------------
@@ -680,6 +878,7 @@ __global__ void k_sweep_end(DevPlan P) {
 // ----------------------------------------------------------------------------
 template <int KIND>
 __global__ void k_exchange_corner(DevPlan P) {
+    if (P.ctrl->ready) return;
     extern __shared__ double smem[];
     __shared__ Partial shp[32];
     const int b = blockIdx.y;
@@ -708,6 +907,7 @@ __global__ void k_exchange_corner(DevPlan P) {
     }
 }
 __global__ void k_exchange_extend(DevPlan P) {
+    if (P.ctrl->ready) return;
     const int b = blockIdx.y;
     const int c = P.own[b + 1];
     const int rc1 = P.rk[c - 1], rc1s = P.rks[c - 1], rc = P.rk[c], rcs = P.rks[c];
@@ -774,6 +974,7 @@ __global__ void k_quad_contract(DevPlan P, int use_weights) {
 // dtt_lua on the contracted train: core p is an r0 x r1 matrix with leading dimension Rmax.
 // One CTA per core: d2_luar over columns (thread per column), then d2_lual over rows (thread per row).
 __global__ void k_quad_lua(DevPlan P) {
+    if (P.ctrl->ready) return;
     const int p = blockIdx.x + 1;
     const int r0 = P.rk[p - 1], r1 = P.rk[p];
     double* m = P.ttqq + (i64)p * P.Rmax * P.Rmax;

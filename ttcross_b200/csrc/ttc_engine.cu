@@ -29,21 +29,6 @@ namespace {
 
 typedef unsigned long long u64;
 
-// ----------------------------------------------------------------------------
-// built-in uniform stream (counter based, so a later device-side lottery can index it)
-// ----------------------------------------------------------------------------
-inline u64 mix64(u64 z) {
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    return z ^ (z >> 31);
-}
-inline double stream_uniform(u64 seed, int vrank, u64 k) {
-    const u64 G = 0x9E3779B97F4A7C15ULL;
-    u64 base = mix64(seed + G * (u64)(vrank + 1));
-    u64 z = mix64(base + G * (k + 1));
-    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
-}
-
 // rnd.f90:128-144
 inline int find_d(int n, const double* x, double y) {
     if (n == 0) return 0;
@@ -129,6 +114,8 @@ struct ttc_handle {
     double* pack_d = nullptr; size_t pack_cap = 0;
     void* flush_d = nullptr; size_t flush_cap = 0;
     double* initb = nullptr;
+    int* ready_h = nullptr;              // pinned mirror of Ctrl::ready
+    int force_sync = 0, force_host_lottery = 0;
     int nsm = 148;
 
     std::vector<int> setup_sig;
@@ -186,6 +173,7 @@ void free_device(ttc_handle* h) {
     if (h->lot_h) { cudaFreeHost(h->lot_h); h->lot_h = nullptr; }
     if (h->out_h) { cudaFreeHost(h->out_h); h->out_h = nullptr; }
     if (h->sweep_h) { cudaFreeHost(h->sweep_h); h->sweep_h = nullptr; }
+    if (h->ready_h) { cudaFreeHost(h->ready_h); h->ready_h = nullptr; }
     if (h->pack_d) { cudaFree(h->pack_d); h->pack_d = nullptr; h->pack_cap = 0; }
     if (h->ev0) { cudaEventDestroy(h->ev0); h->ev0 = nullptr; }
     if (h->ev1) { cudaEventDestroy(h->ev1); h->ev1 = nullptr; }
@@ -339,10 +327,22 @@ int setup_device(ttc_handle* h, int maxrank) {
     CUDA_TRY(h, cudaMallocHost((void**)&h->lot_h, (size_t)P * 4 * h->nlotmax * sizeof(int)));
     CUDA_TRY(h, cudaMallocHost((void**)&h->out_h, (size_t)P * sizeof(VisitOut)));
     CUDA_TRY(h, cudaMallocHost((void**)&h->sweep_h, sizeof(SweepOut)));
+    CUDA_TRY(h, cudaMallocHost((void**)&h->ready_h, sizeof(int)));
+    {
+        int maxnb0 = 0;
+        for (int v = 0; v < P; ++v) maxnb0 = std::max(maxnb0, h->own[v + 1] - h->own[v]);
+        D.maxnb = maxnb0; D.maxsweeps = Rmax;
+        Ctrl* dctrl; VisitOut* dvlog; SweepOut* dslog; int* drklog;
+        int s1 = dev_alloc(h, &dctrl, 1); if (s1) return s1;
+        s1 = dev_alloc(h, &dvlog, (size_t)Rmax * maxnb0 * P); if (s1) return s1;
+        s1 = dev_alloc(h, &dslog, (size_t)Rmax + 1); if (s1) return s1;
+        s1 = dev_alloc(h, &drklog, (size_t)(Rmax + 1) * (d + 1)); if (s1) return s1;
+        D.ctrl = dctrl; D.vlog = dvlog; D.slog = dslog; D.rklog = drklog;
+    }
 
     // kernels that stage the MVN matrix need more than the default 48 KB of dynamic shared memory when d > ~75
     if (D.auxsm) {
-        int bytes = (int)(aux_smem(h) + (size_t)Rmax * sizeof(double));
+        int bytes = (int)(aux_smem(h) + (size_t)(3 * Rmax + 8) * sizeof(double));
         if (bytes > 48 * 1024) {
             cudaFuncSetAttribute(k_lot<KIND_MVN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
             cudaFuncSetAttribute(k_fiber<KIND_MVN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -443,7 +443,9 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     const bool has_quad = !h->quad.empty();
     char line[512];
 
+    D.seed = h->seed; D.has_accuracy = accuracy >= 0 ? 1 : 0; D.accuracy = accuracy; D.piv = h->piv;
     CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+    L(KC_MISC, [&] { k_run_begin<<<1, 32, 0, s>>>(D); });
 
     // ---- initial cross search (dmrgg.f90:150-217)
     const int snum = std::max(8, P);
@@ -566,25 +568,28 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     }
 
     // ---- main loop (dmrgg.f90:309-1020)
-    int it = 0, strike = 0;
-    bool ready = false;
-    if (maxrank > 0) ready = (it + 1 >= maxrank);
+    // Two host modes.  ASYNC (default): the lottery runs on the device, so every sweep is enqueued without waiting;
+    // the exit test lives in k_sweep_log and later sweeps turn into no-ops once it fires.  The host polls a
+    // pinned mirror of the ready flag only to stop enqueuing early.  SYNC (uniform callback, or verbose progress
+    // lines): one stream synchronisation per bond visit so that the host can draw the lottery / print.
+    const bool sync_mode = (h->ucb != nullptr) || h->verbose || h->force_sync;
+    const bool dev_lot = (h->ucb == nullptr) && !h->force_host_lottery;
+    D.dev_lottery = dev_lot ? 1 : 0;
     int maxnb = 0;
     for (int v = 0; v < P; ++v) maxnb = std::max(maxnb, h->own[v + 1] - h->own[v]);
+    const int last_sweep = (maxrank > 0) ? maxrank - 1 : Rmax - 1;
     std::vector<double> pcol, prow, ubuf;
-    std::vector<PivRec> sweep_log;
+    const size_t smL = smA + (size_t)(3 * Rmax + 8) * sizeof(int);
+    int it = 0;
 
-    while (!ready) {
-        it += 1;
-        const int dir = 2 - it % 2;
-        const char* sdir = dir == 1 ? ">>" : "<<";
-        if (it + 1 > Rmax && maxrank <= 0) { h->err = "rank capacity exceeded (pass maxrank)"; return TTC_ERR_RANK; }
-        L(KC_MISC, [&] { k_sweep_begin<<<cdiv(std::max(d + 1, P), 128), 128, 0, s>>>(D); });
-        h->rks_h = h->rk_h;
+    auto visit_log_index = [&](int it_, int pp_, int v_) { return ((size_t)(it_ - 1) * maxnb + (pp_ - 1)) * P + v_; };
 
-        for (int pp = 1; pp <= maxnb; ++pp) {
-            // geometry of this visit on every virtual rank (host mirror)
-            int maxcol = 1, maxrow = 1, maxlot = 1; i64 maxsb = 1;
+    auto enqueue_visit = [&](int it_, int dir, int pp, int rb) -> int {
+        // rb: upper bound of every rank during sweep it_ (ranks grow by at most one per sweep)
+        int maxcol = rb * h->nmax, maxrow = rb * h->nmax, maxlot = 2 * rb + 2 * h->nmax;
+        i64 maxsb = (i64)maxcol * maxrow;
+        if (sync_mode) {
+            maxcol = maxrow = maxlot = 1; maxsb = 1;
             for (int v = 0; v < P; ++v) {
                 int active, p, r0, r1, r2;
                 host_dims(h, v, dir, pp, active, p, r0, r1, r2);
@@ -593,61 +598,64 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
                 maxcol = std::max(maxcol, r0 * n1); maxrow = std::max(maxrow, n2 * r2);
                 maxlot = std::max(maxlot, r0 + n1 + n2 + r2);
                 maxsb = std::max(maxsb, (i64)r0 * n1 * n2 * r2);
-                if (h->piv >= 0) host_lottery(h, v, p, r0, r1, n1, n2, r2, h->lot_h + (size_t)v * 4 * h->nlotmax, pcol, prow, ubuf);
+                if (h->piv >= 0 && !dev_lot)
+                    host_lottery(h, v, p, r0, r1, n1, n2, r2, h->lot_h + (size_t)v * 4 * h->nlotmax, pcol, prow, ubuf);
             }
-            const int Gc = std::min(GMAX, cdiv(maxcol, TB)), Gr = std::min(GMAX, cdiv(maxrow, TB));
-            if (h->piv == -1) {
-                const int Gs = (int)std::min<i64>(GMAX, std::max<i64>(1, (maxsb + TB - 1) / TB));
-                KIND_SWITCH(h->kind, L(KC_SUPERBLOCK, [&] { k_superblock<K, 0><<<dim3(Gs, P), TB, smA, s>>>(D, dir, pp, 0, 0, nullptr); }));
-                L(KC_REDUCE, [&] { k_superblock_reduce<<<dim3(1, P), 128, 0, s>>>(D, dir, pp, Gs, 0, 0, nullptr); });
-                KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, P), TB, smF, s>>>(D, dir, pp, 2); }));
-                KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, P), TB, smF, s>>>(D, dir, pp, 2); }));
+        }
+        const int Gc = std::min(GMAX, cdiv(maxcol, TB)), Gr = std::min(GMAX, cdiv(maxrow, TB));
+        if (h->piv == -1) {
+            const int Gs = (int)std::min<i64>(GMAX, std::max<i64>(1, (maxsb + TB - 1) / TB));
+            KIND_SWITCH(h->kind, L(KC_SUPERBLOCK, [&] { k_superblock<K, 0><<<dim3(Gs, P), TB, smA, s>>>(D, dir, pp, 0, 0, nullptr); }));
+            L(KC_REDUCE, [&] { k_superblock_reduce<<<dim3(1, P), 128, 0, s>>>(D, dir, pp, Gs, 0, 0, nullptr); });
+            KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, P), TB, smF, s>>>(D, dir, pp, 2); }));
+            KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, P), TB, smF, s>>>(D, dir, pp, 2); }));
+        } else {
+            if (!dev_lot) CUDA_TRY(h, cudaMemcpyAsync(D.lot, h->lot_h, (size_t)P * 4 * h->nlotmax * sizeof(int), cudaMemcpyHostToDevice, s));
+            const int Gl = std::min(GMAX, cdiv(maxlot, TB));
+            KIND_SWITCH(h->kind, L(KC_LOT, [&] { k_lot<K><<<dim3(Gl, P), TB, smL, s>>>(D, dir, pp); }));
+            L(KC_REDUCE, [&] { k_lot_reduce<<<dim3(1, P), 128, 0, s>>>(D, dir, pp, Gl); });
+            if (h->piv == 0) {
+                KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, P), TB, smF, s>>>(D, dir, pp, 1); }));
+                L(KC_REDUCE, [&] { k_fiber_reduce<0><<<dim3(1, P), 128, 0, s>>>(D, dir, pp, 1, Gc); });
+                KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, P), TB, smF, s>>>(D, dir, pp, 1); }));
+                L(KC_REDUCE, [&] { k_fiber_reduce<1><<<dim3(1, P), 128, 0, s>>>(D, dir, pp, 1, Gr); });
             } else {
-                CUDA_TRY(h, cudaMemcpyAsync(D.lot, h->lot_h, (size_t)P * 4 * h->nlotmax * sizeof(int), cudaMemcpyHostToDevice, s));
-                const int Gl = std::min(GMAX, cdiv(maxlot, TB));
-                KIND_SWITCH(h->kind, L(KC_LOT, [&] { k_lot<K><<<dim3(Gl, P), TB, smA, s>>>(D, dir, pp); }));
-                L(KC_REDUCE, [&] { k_lot_reduce<<<dim3(1, P), 128, 0, s>>>(D, dir, pp, Gl); });
-                if (h->piv == 0) {
-                    KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, P), TB, smF, s>>>(D, dir, pp, 1); }));
-                    L(KC_REDUCE, [&] { k_fiber_reduce<0><<<dim3(1, P), 128, 0, s>>>(D, dir, pp, 1, Gc); });
-                    KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, P), TB, smF, s>>>(D, dir, pp, 1); }));
-                    L(KC_REDUCE, [&] { k_fiber_reduce<1><<<dim3(1, P), 128, 0, s>>>(D, dir, pp, 1, Gr); });
-                } else {
-                    // rook loop (dmrgg.f90:515-582): at most 2*piv fibers, alternating, starting with the row in '<<' sweeps
-                    int isrow = (dir == 2) ? 1 : 0;
-                    for (int c = 0; c < 2 * h->piv; ++c) {
-                        if (!isrow) {
-                            KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, P), TB, smF, s>>>(D, dir, pp, 0); }));
-                            L(KC_REDUCE, [&] { k_fiber_reduce<0><<<dim3(1, P), 128, 0, s>>>(D, dir, pp, 0, Gc); });
-                        } else {
-                            KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, P), TB, smF, s>>>(D, dir, pp, 0); }));
-                            L(KC_REDUCE, [&] { k_fiber_reduce<1><<<dim3(1, P), 128, 0, s>>>(D, dir, pp, 0, Gr); });
-                        }
-                        isrow ^= 1;
+                // rook loop (dmrgg.f90:515-582): at most 2*piv fibers, alternating, starting with the row in '<<' sweeps
+                int isrow = (dir == 2) ? 1 : 0;
+                for (int c = 0; c < 2 * h->piv; ++c) {
+                    if (!isrow) {
+                        KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, P), TB, smF, s>>>(D, dir, pp, 0); }));
+                        L(KC_REDUCE, [&] { k_fiber_reduce<0><<<dim3(1, P), 128, 0, s>>>(D, dir, pp, 0, Gc); });
+                    } else {
+                        KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, P), TB, smF, s>>>(D, dir, pp, 0); }));
+                        L(KC_REDUCE, [&] { k_fiber_reduce<1><<<dim3(1, P), 128, 0, s>>>(D, dir, pp, 0, Gr); });
                     }
+                    isrow ^= 1;
                 }
             }
-            L(KC_ACCEPT, [&] { k_accept<<<dim3(1, P), 128, 0, s>>>(D, dir, pp, small_element, small_pivot); });
-            L(KC_UPDATE, [&] { k_update_main<<<dim3(std::min(GMAX, cdiv(maxcol + maxrow, 256)), P), 256, 0, s>>>(D, dir, pp); });
-            L(KC_NBR, [&] { k_update_nbr<<<dim3(cdiv(2 * h->nmax, 64), P), 64, 0, s>>>(D, dir, pp); });
-            L(KC_MISC, [&] { k_end_visit<<<cdiv(P, 64), 64, 0, s>>>(D, dir, pp); });
-            CUDA_TRY(h, cudaMemcpyAsync(h->out_h, D.out, (size_t)P * sizeof(VisitOut), cudaMemcpyDeviceToHost, s));
+        }
+        L(KC_ACCEPT, [&] { k_accept<<<dim3(1, P), 128, 0, s>>>(D, it_, dir, pp, small_element, small_pivot); });
+        L(KC_UPDATE, [&] { k_update_main<<<dim3(std::min(GMAX, cdiv(maxcol + maxrow, 256)), P), 256, 0, s>>>(D, dir, pp); });
+        L(KC_NBR, [&] { k_update_nbr<<<dim3(cdiv(2 * h->nmax, 64), P), 64, 0, s>>>(D, dir, pp); });
+        L(KC_MISC, [&] { k_end_visit<<<cdiv(P, 64), 64, 0, s>>>(D, dir, pp); });
+        if (sync_mode) {
+            VisitOut* src = D.vlog + visit_log_index(it_, pp, 0);
+            CUDA_TRY(h, cudaMemcpyAsync(h->out_h, src, (size_t)P * sizeof(VisitOut), cudaMemcpyDeviceToHost, s));
             CUDA_TRY(h, cudaStreamSynchronize(s));
             for (int v = 0; v < P; ++v) {
                 const VisitOut& O = h->out_h[v];
                 if (!O.active) continue;
-                sweep_log.push_back({it, v, O.bond, O.ii, O.jj, O.kk, O.qq, O.upd, O.pivot});
-                if (O.upd) {
-                    if (h->rk_h[O.bond] >= Rmax) { h->err = "rank capacity exceeded"; return TTC_ERR_RANK; }
-                    h->vip_h[O.bond].push_back({O.ii, O.jj, O.kk, O.qq});
-                    h->rk_h[O.bond] += 1;
-                }
+                if (O.upd) { h->vip_h[O.bond].push_back({O.ii, O.jj, O.kk, O.qq}); h->rk_h[O.bond] += 1; }
             }
         }
-        // tape order of the reference: rank by rank, each rank's bonds in visit order
-        std::stable_sort(sweep_log.begin(), sweep_log.end(), [](const PivRec& a, const PivRec& b) { return a.vrank < b.vrank; });
-        h->pivlog.insert(h->pivlog.end(), sweep_log.begin(), sweep_log.end());
-        sweep_log.clear();
+        return 0;
+    };
+    auto enqueue_sweep = [&](int it_) -> int {
+        const int dir = 2 - it_ % 2;
+        const int rb = std::min(it_ + 1, Rmax);
+        L(KC_MISC, [&] { k_sweep_begin<<<cdiv(std::max(d + 1, P), 128), 128, 0, s>>>(D); });
+        if (sync_mode) h->rks_h = h->rk_h;
+        for (int pp = 1; pp <= maxnb; ++pp) { int e = enqueue_visit(it_, dir, pp, rb); if (e) return e; }
         if (P > 1) {
             L(KC_EXCHANGE, [&] { k_allreduce<<<1, 32, 0, s>>>(D); });
             KIND_SWITCH(h->kind, L(KC_EXCHANGE, [&] { k_exchange_corner<K><<<dim3(1, P - 1), TB, smA, s>>>(D); }));
@@ -655,40 +663,89 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         }
         L(KC_MISC, [&] { k_sweep_end<<<1, 32, 0, s>>>(D); });
         if (has_quad) launch_quad(h, L, true, true);
-        CUDA_TRY(h, cudaMemcpyAsync(h->sweep_h, D.sweep_out, sizeof(SweepOut), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(h, cudaStreamSynchronize(s));
-        CUDA_TRY(h, cudaGetLastError());
-        const SweepOut& SO = *h->sweep_h;
-        nevalall = SO.neval;
+        L(KC_MISC, [&] { k_sweep_log<<<1, 64, 0, s>>>(D, it_, maxrank); });
+        return 0;
+    };
 
-        double t2 = timef();
-        double er = erank(d, h->n, h->rk_h);
-        std::snprintf(line, sizeof line, "%3d%2s rank%5.1f time: %s n_evals: %10lld", it, sdir, er, fmt_e(t2, 9, 3).c_str(), nevalall);
-        std::string str = line;
-        if (has_quad) {
-            val = SO.val;
-            if (h->has_tru) str += " err " + fmt_e(std::fabs(1.0 - val / h->tru), 8, 3) + " val " + fmt_e(val, 20, 14);
-            else str += " cnv " + fmt_e(std::fabs(1.0 - val / val_prev), 8, 3) + " val " + fmt_e(val, 20, 14);
-            val_prev = val;
-        }
-        h->text += str + "\n";
-        if (h->verbose) { std::puts(str.c_str()); std::fflush(stdout); }
-        push_series(val, nevalall, SO.amax, SO.pivotmax, er, t2);
-
-        if (maxrank > 0) ready = ready || (it + 1 >= maxrank);
-        if (accuracy >= 0) {
-            if (SO.pivotmax <= accuracy * SO.amax) strike += 1; else strike = 0;
-            ready = ready || (strike >= 3);
+    *h->ready_h = 0;
+    int enq = 0;
+    for (it = 1; it <= last_sweep; ++it) {
+        if (*(volatile int*)h->ready_h) break;          // device already reached its exit condition
+        int e = enqueue_sweep(it);
+        if (e) return e;
+        enq = it;
+        CUDA_TRY(h, cudaMemcpyAsync(h->ready_h, &D.ctrl->ready, sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (sync_mode) {
+            CUDA_TRY(h, cudaStreamSynchronize(s));
+            CUDA_TRY(h, cudaGetLastError());
+            if (h->verbose) {
+                SweepOut so; std::vector<int> rkl(d + 1);
+                CUDA_TRY(h, cudaMemcpy(&so, D.slog + it, sizeof so, cudaMemcpyDeviceToHost));
+                if (so.valid) {
+                    double er = erank(d, h->n, h->rk_h);
+                    std::snprintf(line, sizeof line, "%3d%2s rank%5.1f time: %s n_evals: %10lld", it, (2 - it % 2) == 1 ? ">>" : "<<", er,
+                                  fmt_e(timef(), 9, 3).c_str(), so.neval);
+                    std::string str = line;
+                    if (has_quad) str += (h->has_tru ? " err " + fmt_e(std::fabs(1.0 - so.val / h->tru), 8, 3) : " cnv " + fmt_e(std::fabs(1.0 - so.val / val_prev), 8, 3)) + " val " + fmt_e(so.val, 20, 14);
+                    val_prev = so.val;
+                    std::puts(str.c_str()); std::fflush(stdout);
+                }
+            }
         }
     }
-    h->nsweeps = it;
+    (void)enq;
 
-    // ---- finalise (dmrgg.f90:1028-1029)
+    // ---- finalise (dmrgg.f90:1028-1029); not gated by the ready flag
     L(KC_FINAL, [&] { k_lua_r<<<dim3(cdiv((i64)h->nmax * Rmax, 128), d), 128, 0, s>>>(D); });
     L(KC_FINAL, [&] { k_lua_l<<<dim3(cdiv((i64)h->nmax * Rmax, 128), d), 128, 0, s>>>(D); });
     CUDA_TRY(h, cudaEventRecord(h->ev1, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     CUDA_TRY(h, cudaGetLastError());
+
+    // ---- read the logs back and rebuild the reference's report
+    Ctrl ctrl;
+    CUDA_TRY(h, cudaMemcpy(&ctrl, D.ctrl, sizeof ctrl, cudaMemcpyDeviceToHost));
+    if (ctrl.error) { h->err = "rank capacity exceeded (pass maxrank)"; return TTC_ERR_RANK; }
+    it = ctrl.nsweeps;
+    {
+        std::vector<SweepOut> slog(it + 1);
+        std::vector<int> rklog((size_t)(it + 1) * (d + 1));
+        std::vector<VisitOut> vlog((size_t)std::max(it, 1) * maxnb * P);
+        if (it > 0) {
+            CUDA_TRY(h, cudaMemcpy(slog.data(), D.slog, slog.size() * sizeof(SweepOut), cudaMemcpyDeviceToHost));
+            CUDA_TRY(h, cudaMemcpy(rklog.data(), D.rklog, rklog.size() * sizeof(int), cudaMemcpyDeviceToHost));
+            CUDA_TRY(h, cudaMemcpy(vlog.data(), D.vlog, (size_t)it * maxnb * P * sizeof(VisitOut), cudaMemcpyDeviceToHost));
+        }
+        double vprev = h->s_val.empty() ? 0.0 : h->s_val[0];
+        for (int sw = 1; sw <= it; ++sw) {
+            const SweepOut& SO = slog[sw];
+            std::vector<int> rkv(rklog.begin() + (size_t)sw * (d + 1), rklog.begin() + (size_t)(sw + 1) * (d + 1));
+            rkv.push_back(1);
+            // tape order of the reference: rank by rank, each rank's bonds in visit order
+            for (int v = 0; v < P; ++v)
+                for (int pp = 1; pp <= maxnb; ++pp) {
+                    const VisitOut& O = vlog[visit_log_index(sw, pp, v)];
+                    if (O.active) h->pivlog.push_back({sw, v, O.bond, O.ii, O.jj, O.kk, O.qq, O.upd, O.pivot});
+                }
+            double t2 = 1e-9 * (double)SO.t_ns;
+            double er = erank(d, h->n, rkv);
+            std::snprintf(line, sizeof line, "%3d%2s rank%5.1f time: %s n_evals: %10lld", sw, (2 - sw % 2) == 1 ? ">>" : "<<", er,
+                          fmt_e(t2, 9, 3).c_str(), SO.neval);
+            std::string str = line;
+            if (has_quad) {
+                if (h->has_tru) str += " err " + fmt_e(std::fabs(1.0 - SO.val / h->tru), 8, 3) + " val " + fmt_e(SO.val, 20, 14);
+                else str += " cnv " + fmt_e(std::fabs(1.0 - SO.val / vprev), 8, 3) + " val " + fmt_e(SO.val, 20, 14);
+                vprev = SO.val;
+            }
+            h->text += str + "\n";
+            push_series(has_quad ? SO.val : 0.0, SO.neval, SO.amax, SO.pivotmax, er, t2);
+            nevalall = SO.neval;
+        }
+        std::vector<int> rkf(d + 2, 1);
+        CUDA_TRY(h, cudaMemcpy(rkf.data(), D.rk, (size_t)(d + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+        h->rk_h = rkf;
+    }
+    h->nsweeps = it;
     float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     h->device_ms = ms;
     h->neval = nevalall;
@@ -762,6 +819,11 @@ int ttc_set_tru(ttc_handle* h, int present, double tru) { if (!h) return TTC_ERR
 int ttc_set_seed(ttc_handle* h, unsigned long long seed) { if (!h) return TTC_ERR_ARG; h->seed = seed; return TTC_OK; }
 int ttc_set_uniform_callback(ttc_handle* h, ttc_uniform_cb cb, void* ctx) { if (!h) return TTC_ERR_ARG; h->ucb = cb; h->ucb_ctx = ctx; return TTC_OK; }
 int ttc_set_verbose(ttc_handle* h, int v) { if (!h) return TTC_ERR_ARG; h->verbose = v; return TTC_OK; }
+int ttc_set_lottery_mode(ttc_handle* h, int mode) {
+    if (!h || mode < 0 || mode > 2) return TTC_ERR_ARG;
+    h->force_host_lottery = (mode == 1); h->force_sync = (mode >= 1);
+    return TTC_OK;
+}
 int ttc_set_profile(ttc_handle* h, int on) { if (!h) return TTC_ERR_ARG; h->profile = on; return TTC_OK; }
 
 int ttc_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
@@ -876,6 +938,16 @@ int ttc_l2_flush(ttc_handle* h, long long bytes) {
     }
     CUDA_TRY(h, cudaMemset(h->flush_d, 1, (size_t)bytes));
     CUDA_TRY(h, cudaDeviceSynchronize());
+    return TTC_OK;
+}
+
+// host execution of the closed-form lottery used by the device (unit-test hook: compared against the literal rnd.f90 loop)
+int ttc_lottery_closed_form(int m, const int* zeros_sorted_distinct, int nz, const double* u, int count, int* cells) {
+    if (m < 1 || nz < 0 || nz >= m || !u || !cells) return TTC_ERR_ARG;
+    std::vector<LotSeg> seg(MAXSEG);
+    int ns = build_segments(m - nz, seg.data());
+    if (ns >= MAXSEG) return TTC_ERR_ARG;
+    for (int x = 0; x < count; ++x) cells[x] = lot_draw(seg.data(), ns, m - nz, m, zeros_sorted_distinct, nz, u[x]);
     return TTC_OK;
 }
 
