@@ -67,7 +67,8 @@ typedef void (*ttc_uniform_cb)(void* ctx, int vrank, int count, double* out);
 int ttc_set_uniform_callback(ttc_handle* h, ttc_uniform_cb cb, void* ctx);
 /* 0 (default): lottery on the device, sweeps enqueued asynchronously; 1: lottery on the host exactly as rnd.f90:105-126
  * writes it (one stream synchronisation per bond visit; implied by a uniform callback); 2: device lottery, synchronous.
- * All three produce identical pivots; modes 1 and 2 exist to prove that. */
+ * 3: device lottery, asynchronous, but the plain one-thread-per-chain support kernels instead of the warp-wavefront /
+ * shared-memory ones.  All modes produce identical results; modes 1-3 exist to prove that. */
 int ttc_set_lottery_mode(ttc_handle* h, int mode);
 int ttc_set_verbose(ttc_handle* h, int verbose);                    /* 1: print the reference's per-sweep lines on stdout */
 
@@ -80,6 +81,7 @@ int ttc_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting);
 /* ---- results (valid after ttc_dmrgg) --------------------------------------- */
 int ttc_ranks(const ttc_handle* h, int* r);            /* r(0:d) -> arg%r */
 int ttc_core(ttc_handle* h, int k, double* out);       /* arg%u(k)%p : r(k-1)*n(k)*r(k) doubles, column-major, k = 1..d */
+int ttc_cores(ttc_handle* h, double* out, long long cap); /* all cores, concatenated in core order (cap = doubles available) */
 long long ttc_neval(const ttc_handle* h);              /* neval= */
 int ttc_nsweeps(const ttc_handle* h);
 double ttc_seconds(const ttc_handle* h);               /* wall time of the last ttc_dmrgg call (timef difference) */

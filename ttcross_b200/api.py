@@ -54,6 +54,7 @@ def load_library(build_if_missing: bool = True):
     L.ttc_dmrgg.argtypes = [vp, C.c_int, C.c_double, C.c_int]
     L.ttc_ranks.argtypes = [vp, _ip]
     L.ttc_core.argtypes = [vp, C.c_int, _dp]
+    L.ttc_cores.argtypes = [vp, _dp, C.c_longlong]
     L.ttc_neval.restype = C.c_longlong
     L.ttc_neval.argtypes = [vp]
     L.ttc_nsweeps.argtypes = [vp]
@@ -209,7 +210,14 @@ class TTCross:
         return a
 
     def cores(self):
-        return [self.core(k) for k in range(1, self.d + 1)]
+        sizes = [int(self.ranks[k - 1]) * int(self.n[k - 1]) * int(self.ranks[k]) for k in range(1, self.d + 1)]
+        buf = np.empty(sum(sizes))
+        self._check(self._L.ttc_cores(self.h, _d(buf), buf.size))
+        out, off = [], 0
+        for k, sz in enumerate(sizes, start=1):
+            out.append(buf[off:off + sz].reshape((int(self.ranks[k - 1]), int(self.n[k - 1]), int(self.ranks[k])), order="F"))
+            off += sz
+        return out
 
     # ---- dtt_quad
     def quad(self) -> float:

@@ -56,6 +56,10 @@ struct Ctrl {                   // device-side control of the asynchronous sweep
     int error;                  // 1: rank capacity exceeded
     int nsweeps;                // sweeps actually performed
     unsigned long long t0_ns;
+    int it;                     // current sweep (advanced by k_sweep_begin, so captured graphs carry no sweep number)
+    int has_accuracy;
+    double accuracy;
+    unsigned long long seed;    // uniform stream seed
 };
 // exact restatement of lottery2's cumulative weights (rnd.f90:115-125) for 0/1 weights, see build_segments()
 struct LotSeg { long long M; long long k; int c0; int J; int E; int pad; };
@@ -64,6 +68,9 @@ constexpr int MAXSEG = 128;
 struct DevPlan {
     int d, P, Rmax, nmax, piv, kind, ising_id, nlotmax;
     int auxsm;             // doubles of dynamic shared memory reserved for the MVN matrix (0: read it from global)
+    int stage;             // 1: evaluating kernels stage node/weight values of all pivots in shared memory
+    int stage_max;         // doubles reserved for that staging area
+    unsigned int* tickets; // [P] arrival counters of the last-CTA reductions
     const int* n;          // n[1..d]; n[0] = n[d+1] = 1
     const int* own;        // own[0..P]
     const double* par;     // nodes | weights | ...
@@ -85,10 +92,8 @@ struct DevPlan {
     double* chain2;        // scratch, same size
     SweepOut* sweep_out;
     // asynchronous mode: nothing below needs the host during the sweeps
-    unsigned long long seed;
     int dev_lottery;       // 1: lottery on the device (built-in uniform stream), 0: host fills `lot`
     int maxnb, maxsweeps;
-    int has_accuracy; double accuracy;
     Ctrl* ctrl;
     VisitOut* vlog;        // [maxsweeps][maxnb][P]
     SweepOut* slog;        // [maxsweeps + 1]
@@ -143,21 +148,47 @@ struct DiagSrc {   // wrapped diagonals of the initial search (dmrgg.f90:171-173
 };
 
 // ----------------------------------------------------------------------------
-// integrands
+// integrands.  A "value source" V supplies the node value x(pos) and the quadrature weight w(pos) of the mode index
+// at 1-based position pos; the arithmetic below is the reference's, operation for operation.
 // ----------------------------------------------------------------------------
-// test_crs_ising.f90:176-218.  Pure + - * / : bit-reproducible.
+// values straight from global memory through an index source (initial cross, fallback when staging does not fit)
 template <class Src>
-__device__ double eval_ising(const DevPlan& P, const Src& s) {
+struct GlobalVals {
+    Src s; const double* par; int nw;    // nw: offset of the weights inside par (Ising: n)
+    __device__ __forceinline__ double x(int pos) const { return par[s(pos) - 1]; }
+    __device__ __forceinline__ double w(int pos) const { return par[nw + s(pos) - 1]; }
+};
+// values staged in shared memory by stage_bond(): left table XL[pos][i], right table XR[pos][q], nodes/weights of the
+// two free modes
+struct StagedVals {
+    const double* XL; const double* WL; int nl, rl, i;      // positions 1..nl, pivot i of rl
+    double xj, wj, xk, wk; int hask;                        // position nl+1 (and nl+2)
+    const double* XR; const double* WR; int rr, q;          // remaining positions, pivot q of rr
+    __device__ __forceinline__ double x(int pos) const {
+        if (pos <= nl) return XL[(pos - 1) * rl + (i - 1)];
+        if (pos == nl + 1) return xj;
+        if (hask && pos == nl + 2) return xk;
+        return XR[(pos - nl - 2 - hask) * rr + (q - 1)];
+    }
+    __device__ __forceinline__ double w(int pos) const {
+        if (pos <= nl) return WL[(pos - 1) * rl + (i - 1)];
+        if (pos == nl + 1) return wj;
+        if (hask && pos == nl + 2) return wk;
+        return WR[(pos - nl - 2 - hask) * rr + (q - 1)];
+    }
+};
+
+// test_crs_ising.f90:176-218.  Pure + - * / : bit-reproducible.
+template <class V>
+__device__ double eval_ising(const DevPlan& P, const V& v) {
     const int m = P.d;
     const int id = P.ising_id;
-    const double* nodes = P.par - 1;
-    const double* weights = P.par + P.n[1] - 1;
     double a = 0.0, b = 0.0, f;
     if (id == 2 || id == 3) {
         a = 1.0;
         if (m <= MAXD_LOCAL) {
             double x[MAXD_LOCAL];
-            for (int j = 1; j <= m; ++j) x[j - 1] = nodes[s(j)];
+            for (int j = 1; j <= m; ++j) x[j - 1] = v.x(j);
             for (int i = 0; i <= m; ++i) {
                 double uij = 1.0;
                 for (int j = i + 1; j <= m; ++j) {
@@ -170,7 +201,7 @@ __device__ double eval_ising(const DevPlan& P, const Src& s) {
             for (int i = 0; i <= m; ++i) {
                 double uij = 1.0;
                 for (int j = i + 1; j <= m; ++j) {
-                    uij = uij * nodes[s(j)];
+                    uij = uij * v.x(j);
                     double t = (uij - 1.0) / (uij + 1.0);
                     a = a * (t * t);
                 }
@@ -178,46 +209,46 @@ __device__ double eval_ising(const DevPlan& P, const Src& s) {
         }
     }
     if (id == 1 || id == 2) {
-        double v = 1.0, w = 1.0, vk = 1.0, wk = 1.0;
+        double vv = 1.0, w = 1.0, vk = 1.0, wk = 1.0;
         for (int i = 1; i <= m; ++i) {
-            vk = vk * nodes[s(m - i + 1)];
-            wk = wk * nodes[s(i)];
-            v = v + vk;
+            vk = vk * v.x(m - i + 1);
+            wk = wk * v.x(i);
+            vv = vv + vk;
             w = w + wk;
         }
-        b = 1.0 / (v * w);
+        b = 1.0 / (vv * w);
     }
     if (id == 1) f = 2 * b;
     else if (id == 2) f = 2 * a * b;
     else f = 2 * a;
-    for (int i = 1; i <= m; ++i) f = f * weights[s(i)];
+    for (int i = 1; i <= m; ++i) f = f * v.w(i);
     return f;
 }
 // test_crs_stdnorm.f90:154-170
-template <class Src>
-__device__ double eval_stdnorm(const DevPlan& P, const Src& s) {
+template <class V>
+__device__ double eval_stdnorm(const DevPlan& P, const V& v) {
     double sum = 0.0;
-    for (int i = 1; i <= P.d; ++i) { double x = P.par[s(i) - 1]; sum = sum + x * x; }
+    for (int i = 1; i <= P.d; ++i) { double x = v.x(i); sum = sum + x * x; }
     return exp(-sum);
 }
 // lib/mvn_pdf.f90:63-83 (through test_crs_mvn.f90:156-172); A = inv_cov column-major, staged by the caller
-template <class Src>
-__device__ double eval_mvn(const DevPlan& P, const Src& s, const double* __restrict__ A /*d*d*/) {
+template <class V>
+__device__ double eval_mvn(const DevPlan& P, const V& v, const double* __restrict__ A /*d*d*/) {
     const int m = P.d;
     const double* mu = P.aux;
     const double denom = P.aux[m + (i64)m * m];
     double e = 0.0;
     if (m <= MAXD_LOCAL) {
         double diff[MAXD_LOCAL];
-        for (int i = 0; i < m; ++i) diff[i] = P.par[s(i + 1) - 1] - mu[i];
+        for (int i = 0; i < m; ++i) diff[i] = v.x(i + 1) - mu[i];
         for (int i = 0; i < m; ++i) {
             const double di = diff[i];
             for (int j = 0; j < m; ++j) e = e + di * A[i + (i64)j * m] * diff[j];
         }
     } else {
         for (int i = 0; i < m; ++i) {
-            const double di = P.par[s(i + 1) - 1] - mu[i];
-            for (int j = 0; j < m; ++j) e = e + di * A[i + (i64)j * m] * (P.par[s(j + 1) - 1] - mu[j]);
+            const double di = v.x(i + 1) - mu[i];
+            for (int j = 0; j < m; ++j) e = e + di * A[i + (i64)j * m] * (v.x(j + 1) - mu[j]);
         }
     }
     return exp(-0.5 * e) / denom;
@@ -236,11 +267,67 @@ __device__ __forceinline__ const double* stage_aux(const DevPlan& P, double* sme
     }
     return A;
 }
+template <int KIND, class V>
+__device__ __forceinline__ double eval_point(const DevPlan& P, const V& v, const double* A) {
+    if (KIND == KIND_ISING) return eval_ising(P, v);
+    if (KIND == KIND_STDNORM) return eval_stdnorm(P, v);
+    return eval_mvn(P, v, A);
+}
 template <int KIND, class Src>
-__device__ __forceinline__ double eval_point(const DevPlan& P, const Src& s, const double* A) {
-    if (KIND == KIND_ISING) return eval_ising(P, s);
-    if (KIND == KIND_STDNORM) return eval_stdnorm(P, s);
-    return eval_mvn(P, s, A);
+__device__ __forceinline__ double eval_src(const DevPlan& P, const Src& s, const double* A) {
+    GlobalVals<Src> v{s, P.par, P.n[1]};
+    return eval_point<KIND>(P, v, A);
+}
+
+// ----------------------------------------------------------------------------
+// per-CTA staging of everything an evaluation reads: node/weight values of the two free modes and of every pivot of
+// the left table (bond pl, nl positions, rl pivots) and of the right table (bond pr, nr positions, rr pivots).
+// Shared-memory layout (doubles): NX[n1] NW[n1] NX2[n2] NW2[n2] XL[nl*rl] WL[nl*rl] XR[nr*rr] WR[nr*rr]
+// ----------------------------------------------------------------------------
+struct Stage {
+    const double *NX, *NW, *NX2, *NW2, *XL, *WL, *XR, *WR;
+    int nl, rl, nr, rr, hask;
+    __device__ __forceinline__ StagedVals point(int i, int j, int k, int q) const {
+        StagedVals v;
+        v.XL = XL; v.WL = WL; v.nl = nl; v.rl = rl; v.i = i;
+        v.xj = NX[j - 1]; v.wj = NW[j - 1];
+        v.hask = hask;
+        v.xk = hask ? NX2[k - 1] : 0.0; v.wk = hask ? NW2[k - 1] : 0.0;
+        v.XR = XR; v.WR = WR; v.rr = rr; v.q = q;
+        return v;
+    }
+};
+__host__ __device__ __forceinline__ i64 stage_doubles(int n1, int n2, int nl, int rl, int nr, int rr) {
+    return 2LL * n1 + 2LL * n2 + 2LL * nl * rl + 2LL * nr * rr;
+}
+// pl: bond whose left multi-indices feed positions 1..nl (nl = pl); pr: bond whose right multi-indices feed the tail.
+// c1/c2: the cores of the free modes (c2 = 0 when there is a single free mode).
+__device__ __forceinline__ Stage stage_bond(const DevPlan& P, double* sm, int pl, int rl, int c1, int c2, int pr, int rr) {
+    Stage S;
+    const int n1 = P.n[c1], n2 = c2 ? P.n[c2] : 0;
+    const int nl = pl, nr = P.d - pr;
+    const bool hasw = (P.kind == KIND_ISING);
+    const int nwoff = P.n[1];
+    double* NX = sm; double* NW = NX + n1; double* NX2 = NW + n1; double* NW2 = NX2 + n2;
+    double* XL = NW2 + n2; double* WL = XL + nl * rl; double* XR = WL + nl * rl; double* WR = XR + nr * rr;
+    for (int x = threadIdx.x; x < n1; x += blockDim.x) { NX[x] = P.par[x]; NW[x] = hasw ? P.par[nwoff + x] : 0.0; }
+    for (int x = threadIdx.x; x < n2; x += blockDim.x) { NX2[x] = P.par[x]; NW2[x] = hasw ? P.par[nwoff + x] : 0.0; }
+    const int* L = P.Lidx + P.offL[pl];
+    for (int x = threadIdx.x; x < nl * rl; x += blockDim.x) {
+        int pos = x / rl, t = x - pos * rl;
+        int idx = L[(i64)pos * P.Rmax + t];
+        XL[x] = P.par[idx - 1]; WL[x] = hasw ? P.par[nwoff + idx - 1] : 0.0;
+    }
+    const int* R = P.Ridx + P.offR[pr];
+    for (int x = threadIdx.x; x < nr * rr; x += blockDim.x) {
+        int pos = x / rr, t = x - pos * rr;
+        int idx = R[(i64)pos * P.Rmax + t];
+        XR[x] = P.par[idx - 1]; WR[x] = hasw ? P.par[nwoff + idx - 1] : 0.0;
+    }
+    __syncthreads();
+    S.NX = NX; S.NW = NW; S.NX2 = NX2; S.NW2 = NW2; S.XL = XL; S.WL = WL; S.XR = XR; S.WR = WR;
+    S.nl = nl; S.rl = rl; S.nr = nr; S.rr = rr; S.hask = c2 ? 1 : 0;
+    return S;
 }
 
 // ----------------------------------------------------------------------------
@@ -382,7 +469,94 @@ __device__ __forceinline__ void lot_zeros(const int* vip_p, int r1, int side, in
 }
 
 // ----------------------------------------------------------------------------
-// K1: lottery candidates (dmrgg.f90:447-484): evaluate, residual by sequential ddot, two argmaxes
+// shared helpers of the evaluating kernels
+// ----------------------------------------------------------------------------
+// grid-wide first-index argmax without a second launch: every CTA publishes its partials, the last CTA to arrive
+// (atomic ticket) folds them and updates the visit state (the classic threadfence reduction).
+// Returns true in the last CTA; `raw`/`res` then hold the folded results in thread 0.
+__device__ __forceinline__ bool fold_partials(const DevPlan& P, int v, Partial& raw, Partial& res, Partial* shp) {
+    __shared__ int s_last;
+    __threadfence();                 // this thread's fiber / lottery stores, before the CTA announces itself
+    raw = amax_block(raw, shp);
+    res = amax_block(res, shp);
+    Partial* part = P.part + (i64)v * 2 * GMAX;
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = raw;
+        part[GMAX + blockIdx.x] = res;
+        __threadfence();
+        unsigned t = atomicAdd(P.tickets + v, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    const volatile Partial* vp = part;
+    Partial a = amax_init(), b2 = amax_init();
+    for (int x = threadIdx.x; x < (int)gridDim.x; x += blockDim.x) {
+        Partial t1, t2;
+        t1.absv = vp[x].absv; t1.val = vp[x].val; t1.idx = vp[x].idx;
+        t2.absv = vp[GMAX + x].absv; t2.val = vp[GMAX + x].val; t2.idx = vp[GMAX + x].idx;
+        amax_merge(a, t1); amax_merge(b2, t2);
+    }
+    raw = amax_block(a, shp);
+    res = amax_block(b2, shp);
+    if (threadIdx.x == 0) P.tickets[v] = 0;
+    return true;
+}
+// residuals in the reference's orders, with the factor loads issued in batches (they do not depend on the sum)
+constexpr int RU = 8;
+// dgemv 'n' / dgemm order: res = f; res += (-x_s) * a_s, s ascending   (a_s = base[s*stride])
+__device__ __forceinline__ double resid_axpy(double f, const double* base, i64 stride, const double* xs, int r) {
+    double res = f;
+    int s0 = 0;
+    for (; s0 + RU <= r; s0 += RU) {
+        double a[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) a[u] = base[(s0 + u) * stride];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) res = res + (-xs[s0 + u]) * a[u];
+    }
+    for (; s0 < r; ++s0) res = res + (-xs[s0]) * base[s0 * stride];
+    return res;
+}
+// dgemv 't' order: t = sum_s a_s * x_s from 0, ascending; result f + (-t)
+__device__ __forceinline__ double resid_dot(double f, const double* base, i64 stride, const double* xs, int r) {
+    double t = 0.0;
+    int s0 = 0;
+    for (; s0 + RU <= r; s0 += RU) {
+        double a[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) a[u] = base[(s0 + u) * stride];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) t = t + a[u] * xs[s0 + u];
+    }
+    for (; s0 < r; ++s0) t = t + base[s0 * stride] * xs[s0];
+    return f + (-t);
+}
+// ddot(r, col(i,j,1), ldc, row(1,k,q), 1) (dmrgg.f90:474): t = sum_s c_s * r_s from 0; result f - t
+__device__ __forceinline__ double resid_ddot2(double f, const double* c, i64 cs, const double* r, i64 rs, int r1) {
+    double t = 0.0;
+    int s0 = 0;
+    for (; s0 + RU <= r1; s0 += RU) {
+        double a[RU], b[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) { a[u] = c[(s0 + u) * cs]; b[u] = r[(s0 + u) * rs]; }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) t = t + a[u] * b[u];
+    }
+    for (; s0 < r1; ++s0) t = t + c[s0 * cs] * r[s0 * rs];
+    return f - t;
+}
+template <int KIND>
+__device__ __forceinline__ double eval_bond(const DevPlan& P, const Stage& S, int p, int i, int j, int k, int q, const double* A) {
+    if (P.stage) { StagedVals v = S.point(i, j, k, q); return eval_point<KIND>(P, v, A); }
+    return eval_src<KIND>(P, bond_point(P, p, i, j, k, q), A);
+}
+
+// ----------------------------------------------------------------------------
+// K1: lottery candidates (dmrgg.f90:425-484): draw (device lottery), evaluate, residual by sequential ddot,
+// two first-index argmaxes, and the scalar bookkeeping of dmrgg.f90:465-490 in the last CTA.
+// dynamic smem: A[auxsm] | stage | ints[3*Rmax]
 // ----------------------------------------------------------------------------
 template <int KIND>
 __global__ void k_lot(DevPlan P, int dir, int pp) {
@@ -393,26 +567,29 @@ __global__ void k_lot(DevPlan P, int dir, int pp) {
     const Dims D = load_dims(P, v, dir, pp);
     if (!D.active) return;
     const double* A = stage_aux<KIND>(P, smem);
+    double* stg = smem + P.auxsm;
+    Stage S;
+    if (P.stage) S = stage_bond(P, stg, D.p - 1, D.r0, D.p, D.p + 1, D.p + 1, D.r2);
     const int nlot = D.r0 + D.n1 + D.n2 + D.r2;
     int* lot = P.lot + (i64)v * 4 * P.nlotmax;
     if (P.dev_lottery) {
         // every CTA rebuilds the (tiny) cumulative-weight description; each thread then draws its own candidates
         __shared__ LotSeg seg[2][MAXSEG];
         __shared__ int s_ns[2], s_nz[2];
-        int* ibuf = (int*)(smem + P.auxsm);           // tmp[Rmax] | zeros_col[Rmax] | zeros_row[Rmax]
+        int* ibuf = (int*)(stg + P.stage_max);         // tmp[Rmax] | zeros_col[Rmax] | zeros_row[Rmax]
         int* tmp = ibuf; int* zc = ibuf + P.Rmax; int* zr = ibuf + 2 * P.Rmax;
         const int* vip_p = P.vip + (i64)D.p * P.Rmax * 4;
         const int m = D.r0 * D.n1, n = D.n2 * D.r2;
         lot_zeros(vip_p, D.r1, 0, D.r0, tmp, zc, &s_nz[0]);
         lot_zeros(vip_p, D.r1, 1, D.n2, tmp, zr, &s_nz[1]);
-        if (threadIdx.x == 0)  s_ns[0] = build_segments(m - s_nz[0], seg[0]);
-        if (threadIdx.x == 32 % blockDim.x && blockDim.x > 32) s_ns[1] = build_segments(n - s_nz[1], seg[1]);
-        if (blockDim.x <= 32 && threadIdx.x == 0) s_ns[1] = build_segments(n - s_nz[1], seg[1]);
+        if (threadIdx.x == 0) s_ns[0] = build_segments(m - s_nz[0], seg[0]);
+        if (threadIdx.x == 32) s_ns[1] = build_segments(n - s_nz[1], seg[1]);
         __syncthreads();
         const unsigned long long k0 = P.st[v].rng_k;
+        const unsigned long long seed = P.ctrl->seed;
         for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < nlot; x += gridDim.x * blockDim.x) {
-            double uc = stream_uniform(P.seed, v, k0 + (unsigned long long)x);
-            double ur = stream_uniform(P.seed, v, k0 + (unsigned long long)(nlot + x));
+            double uc = stream_uniform(seed, v, k0 + (unsigned long long)x);
+            double ur = stream_uniform(seed, v, k0 + (unsigned long long)(nlot + x));
             int c = lot_draw(seg[0], s_ns[0], m - s_nz[0], m, zc, s_nz[0], uc);
             int w = lot_draw(seg[1], s_ns[1], n - s_nz[1], n, zr, s_nz[1], ur);
             lot[x] = (c - 1) % D.r0 + 1;
@@ -429,59 +606,33 @@ __global__ void k_lot(DevPlan P, int dir, int pp) {
     Partial braw = amax_init(), bres = amax_init();
     for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < nlot; x += gridDim.x * blockDim.x) {
         int i = lot[x], j = lot[P.nlotmax + x], k = lot[2 * P.nlotmax + x], q = lot[3 * P.nlotmax + x];
-        PointSrc s = bond_point(P, D.p, i, j, k, q);
-        double f = eval_point<KIND>(P, s, A);
-        const double* c = colp + (i - 1) + (i64)P.Rmax * (j - 1);
-        const double* r = rowp + (k - 1) + (i64)D.n2 * (q - 1);
-        double t = 0.0;
-        for (int sidx = 0; sidx < D.r1; ++sidx) t = t + c[sidx * cs] * r[sidx * rs];
-        double res = f - t;
-        P.lraw[(i64)v * P.nlotmax + x] = f;
+        double f = eval_bond<KIND>(P, S, D.p, i, j, k, q, A);
+        double res = resid_ddot2(f, colp + (i - 1) + (i64)P.Rmax * (j - 1), cs, rowp + (k - 1) + (i64)D.n2 * (q - 1), rs, D.r1);
         P.lres[(i64)v * P.nlotmax + x] = res;
         amax_take(braw, f, x);
         amax_take(bres, res, x);
     }
-    braw = amax_block(braw, shp);
-    bres = amax_block(bres, shp);
+    if (!fold_partials(P, v, braw, bres, shp)) return;
     if (threadIdx.x == 0) {
-        P.part[((i64)v * 2 + 0) * GMAX + blockIdx.x] = braw;
-        P.part[((i64)v * 2 + 1) * GMAX + blockIdx.x] = bres;
-    }
-}
-
-__device__ __forceinline__ Partial reduce_parts(const Partial* parts, int G, Partial* shp) {
-    Partial a = amax_init();
-    for (int x = threadIdx.x; x < G; x += blockDim.x) amax_merge(a, parts[x]);
-    return amax_block(a, shp);
-}
-
-__global__ void k_lot_reduce(DevPlan P, int dir, int pp, int G) {
-    if (P.ctrl->ready) return;
-    __shared__ Partial shp[32];
-    const int v = blockIdx.y;
-    const Dims D = load_dims(P, v, dir, pp);
-    if (!D.active) return;
-    Partial braw = reduce_parts(P.part + ((i64)v * 2 + 0) * GMAX, G, shp);
-    Partial bres = reduce_parts(P.part + ((i64)v * 2 + 1) * GMAX, G, shp);
-    if (threadIdx.x == 0) {
-        VState& S = P.st[v];
-        const int nlot = D.r0 + D.n1 + D.n2 + D.r2;
-        const int* lot = P.lot + (i64)v * 4 * P.nlotmax;
-        S.amax = fmax(S.amax, braw.absv);
+        VState& St = P.st[v];
+        St.amax = fmax(St.amax, braw.absv);
         int x = (int)bres.idx;
-        S.ii = lot[x]; S.jj = lot[P.nlotmax + x]; S.kk = lot[2 * P.nlotmax + x]; S.qq = lot[3 * P.nlotmax + x];
-        S.pivot = bres.val;
-        S.done = 0; S.havecol = 0; S.haverow = 0; S.crs = 0; S.upd = 0;
-        S.neval += nlot;
-        S.rng_k += 2ULL * (unsigned long long)nlot;     // one random_number(d(npnt,2)) call (rnd.f90:120)
+        const volatile int* vl = lot;
+        St.ii = vl[x]; St.jj = vl[P.nlotmax + x]; St.kk = vl[2 * P.nlotmax + x]; St.qq = vl[3 * P.nlotmax + x];
+        St.pivot = bres.val;
+        St.done = 0; St.havecol = 0; St.haverow = 0; St.crs = 0; St.upd = 0;
+        St.neval += nlot;
+        St.rng_k += 2ULL * (unsigned long long)nlot;     // one random_number(d(npnt,2)) call (rnd.f90:120)
     }
 }
 
 // ----------------------------------------------------------------------------
-// K2: cross fibers of the rook search (dmrgg.f90:519-581) fused with their residuals
+// K2: cross fibers of the rook search (dmrgg.f90:519-581) fused with their residuals and the scalar bookkeeping
 //   column fiber: acol1(i,j) = f(i,j,kk,qq); bcol1 = acol1 - col(p)(:,:,1:r) * row(p+1)(1:r,kk,qq)   [dgemv 'n' order]
 //   row fiber   : arow1(k,q) = f(ii,jj,k,q); brow1 = arow1 - row(p+1)(1:r,:,:)^T col(p)(ii,jj,1:r)   [dgemv 't' order]
-// mode 0: rook step (skipped when the visit is already `done`); mode 1: unconditional (piv = 0 and piv = -1 branches)
+// mode 0: rook step (skipped when the visit is already `done`); mode 1: piv = 0 (no argmax, dmrgg.f90:492-513);
+// mode 2: piv = -1 (the fibers are slices of the superblock: nothing to account)
+// dynamic smem: A[auxsm] | xs[Rmax] | stage
 // ----------------------------------------------------------------------------
 template <int KIND, int ISROW>
 __global__ void k_fiber(DevPlan P, int dir, int pp, int mode) {
@@ -491,20 +642,21 @@ __global__ void k_fiber(DevPlan P, int dir, int pp, int mode) {
     const int v = blockIdx.y;
     const Dims D = load_dims(P, v, dir, pp);
     if (!D.active) return;
-    const VState& S = P.st[v];
-    if (mode == 0 && S.done) return;
-    // coefficient vector of the residual: row(p+1)(1:r1,kk,qq) or col(p)(ii,jj,1:r1)
-    double* xs = smem;                         // [Rmax]
-    double* Asm = smem + P.Rmax;
+    const VState& St0 = P.st[v];
+    if (mode == 0 && St0.done) return;
+    const int ii = St0.ii, jj = St0.jj, kk = St0.kk, qq = St0.qq;
+    const double* A = stage_aux<KIND>(P, smem);
+    double* xs = smem + P.auxsm;               // [Rmax] coefficient vector of the residual
+    double* stg = xs + P.Rmax;
     const double* colp = P.col + P.coreOff[D.p];
     const double* rowp = P.rowT + P.coreOff[D.p + 1];
     const i64 cs = (i64)P.Rmax * D.n1;
     const i64 rs = (i64)D.n2 * P.Rmax;
-    const int ii = S.ii, jj = S.jj, kk = S.kk, qq = S.qq;
     for (int s = threadIdx.x; s < D.r1; s += blockDim.x)
         xs[s] = ISROW ? colp[(ii - 1) + (i64)P.Rmax * (jj - 1) + s * cs] : rowp[(kk - 1) + (i64)D.n2 * (qq - 1) + s * rs];
-    __syncthreads();
-    const double* A = stage_aux<KIND>(P, Asm);
+    Stage S;
+    if (P.stage) S = stage_bond(P, stg, D.p - 1, D.r0, D.p, D.p + 1, D.p + 1, D.r2);
+    else __syncthreads();
     const int count = ISROW ? D.n2 * D.r2 : D.r0 * D.n1;
     double* fa = (ISROW ? P.arow1 : P.acol1) + (i64)v * P.Rmax * P.nmax;
     double* fb = (ISROW ? P.brow1 : P.bcol1) + (i64)v * P.Rmax * P.nmax;
@@ -513,78 +665,53 @@ __global__ void k_fiber(DevPlan P, int dir, int pp, int mode) {
         double f, res;
         if (!ISROW) {
             int j = e / D.r0 + 1, i = e % D.r0 + 1;
-            PointSrc s = bond_point(P, D.p, i, j, kk, qq);
-            f = eval_point<KIND>(P, s, A);
-            const double* c = colp + (i - 1) + (i64)P.Rmax * (j - 1);
-            res = f;
-            for (int sidx = 0; sidx < D.r1; ++sidx) res = res + (-xs[sidx]) * c[sidx * cs];
+            f = eval_bond<KIND>(P, S, D.p, i, j, kk, qq, A);
+            res = resid_axpy(f, colp + (i - 1) + (i64)P.Rmax * (j - 1), cs, xs, D.r1);
         } else {
             int q = e / D.n2 + 1, k = e % D.n2 + 1;
-            PointSrc s = bond_point(P, D.p, ii, jj, k, q);
-            f = eval_point<KIND>(P, s, A);
-            const double* r = rowp + (k - 1) + (i64)D.n2 * (q - 1);
-            double t = 0.0;
-            for (int sidx = 0; sidx < D.r1; ++sidx) t = t + r[sidx * rs] * xs[sidx];
-            res = f + (-t);
+            f = eval_bond<KIND>(P, S, D.p, ii, jj, k, q, A);
+            res = resid_dot(f, rowp + (k - 1) + (i64)D.n2 * (q - 1), rs, xs, D.r1);
         }
         fa[e] = f;
         fb[e] = res;
         amax_take(braw, f, e);
         amax_take(bres, res, e);
     }
-    braw = amax_block(braw, shp);
-    bres = amax_block(bres, shp);
-    if (threadIdx.x == 0) {
-        P.part[((i64)v * 2 + 0) * GMAX + blockIdx.x] = braw;
-        P.part[((i64)v * 2 + 1) * GMAX + blockIdx.x] = bres;
-    }
-}
-
-// the scalar bookkeeping after a fiber (dmrgg.f90:527-547, 560-580)
-template <int ISROW>
-__global__ void k_fiber_reduce(DevPlan P, int dir, int pp, int mode, int G) {
-    if (P.ctrl->ready) return;
-    __shared__ Partial shp[32];
-    const int v = blockIdx.y;
-    const Dims D = load_dims(P, v, dir, pp);
-    if (!D.active) return;
-    VState& S = P.st[v];
-    if (mode == 0 && S.done) return;
-    Partial braw = reduce_parts(P.part + ((i64)v * 2 + 0) * GMAX, G, shp);
-    Partial bres = reduce_parts(P.part + ((i64)v * 2 + 1) * GMAX, G, shp);
-    if (threadIdx.x == 0) {
-        const int count = ISROW ? D.n2 * D.r2 : D.r0 * D.n1;
-        if (mode == 2) return;                       // piv = -1: fibers are slices of the superblock, nothing to account
-        S.neval += count;
-        if (mode == 1) { S.havecol = 1; S.haverow = 1; S.done = 1; return; }   // piv = 0 (dmrgg.f90:492-513)
-        S.amax = fmax(S.amax, braw.absv);
-        if (ISROW) S.haverow = 1; else S.havecol = 1;
-        S.crs += 1;
-        int done = S.havecol && S.haverow && (S.crs >= 2 * P.piv);
+    if (!fold_partials(P, v, braw, bres, shp)) return;
+    if (threadIdx.x == 0) {      // dmrgg.f90:527-547, 560-580
+        VState& St = P.st[v];
+        if (mode == 2) return;
+        St.neval += count;
+        if (mode == 1) { St.havecol = 1; St.haverow = 1; St.done = 1; return; }
+        St.amax = fmax(St.amax, braw.absv);
+        if (ISROW) St.haverow = 1; else St.havecol = 1;
+        St.crs += 1;
+        int done = St.havecol && St.haverow && (St.crs >= 2 * P.piv);
         if (!done) {
             int e = (int)bres.idx;
             if (!ISROW) {
                 int j = e / D.r0 + 1, i = e % D.r0 + 1;
-                done = S.havecol && S.haverow && (i == S.ii && j == S.jj);
-                S.ii = i; S.jj = j;
+                done = St.havecol && St.haverow && (i == St.ii && j == St.jj);
+                St.ii = i; St.jj = j;
             } else {
                 int q = e / D.n2 + 1, k = e % D.n2 + 1;
-                done = S.havecol && S.haverow && (k == S.kk && q == S.qq);
-                S.kk = k; S.qq = q;
+                done = St.havecol && St.haverow && (k == St.kk && q == St.qq);
+                St.kk = k; St.qq = q;
             }
-            S.pivot = bres.val;
+            St.pivot = bres.val;
         }
-        S.done = done;
+        St.done = done;
     }
 }
 
 // ----------------------------------------------------------------------------
 // K3: full-pivoting superblock (dmrgg.f90:341-396), fused: evaluate a(i,j,k,q), residual against col*row in
 // dgemm order (K = r(p)), first-index argmax of |a| and of |b|.  STORE also writes `a` to HBM (HBM-bound variant).
-// Tile: blockDim.x threads walk the linear index (i fastest) so stores and col reads are coalesced.
+// probe_out != nullptr: measurement entry (fixed bond, results to probe_out instead of the visit state).
+// dynamic smem: A[auxsm] | stage
 // ----------------------------------------------------------------------------
 template <int KIND, int STORE>
-__global__ void k_superblock(DevPlan P, int dir, int pp, int fixed_bond, int fixed_v, double* a_out) {
+__global__ void k_superblock(DevPlan P, int dir, int pp, int fixed_bond, int fixed_v, double* a_out, Partial* probe_out) {
     extern __shared__ double smem[];
     __shared__ Partial shp[32];
     const int v = (fixed_bond > 0) ? fixed_v : blockIdx.y;
@@ -598,6 +725,9 @@ __global__ void k_superblock(DevPlan P, int dir, int pp, int fixed_bond, int fix
     }
     if (!D.active) return;
     const double* A = stage_aux<KIND>(P, smem);
+    double* stg = smem + P.auxsm;
+    Stage S;
+    if (P.stage) S = stage_bond(P, stg, D.p - 1, D.r0, D.p, D.p + 1, D.p + 1, D.r2);
     const double* colp = P.col + P.coreOff[D.p];
     const double* rowp = P.rowT + P.coreOff[D.p + 1];
     const i64 cs = (i64)P.Rmax * D.n1;
@@ -609,8 +739,7 @@ __global__ void k_superblock(DevPlan P, int dir, int pp, int fixed_bond, int fix
         i64 kq = x / m1; int ij = (int)(x - kq * m1);
         int q = (int)(kq / D.n2) + 1, k = (int)(kq % D.n2) + 1;
         int j = ij / D.r0 + 1, i = ij % D.r0 + 1;
-        PointSrc s = bond_point(P, D.p, i, j, k, q);
-        double f = eval_point<KIND>(P, s, A);
+        double f = eval_bond<KIND>(P, S, D.p, i, j, k, q, A);
         const double* c = colp + (i - 1) + (i64)P.Rmax * (j - 1);
         const double* r = rowp + (k - 1) + (i64)D.n2 * (q - 1);
         double res = f;
@@ -619,48 +748,27 @@ __global__ void k_superblock(DevPlan P, int dir, int pp, int fixed_bond, int fix
         amax_take(braw, f, x);
         amax_take(bres, res, x);
     }
-    braw = amax_block(braw, shp);
-    bres = amax_block(bres, shp);
-    if (threadIdx.x == 0) {
-        P.part[((i64)v * 2 + 0) * GMAX + blockIdx.x] = braw;
-        P.part[((i64)v * 2 + 1) * GMAX + blockIdx.x] = bres;
-    }
-}
-
-__global__ void k_superblock_reduce(DevPlan P, int dir, int pp, int G, int fixed_bond, int fixed_v, Partial* probe_out) {
-    __shared__ Partial shp[32];
-    const int v = (fixed_bond > 0) ? fixed_v : blockIdx.y;
-    Dims D;
-    if (fixed_bond > 0) {
-        D.active = 1; D.p = fixed_bond; D.r0 = P.rk[D.p - 1]; D.r1 = P.rk[D.p]; D.r2 = P.rk[D.p + 1];
-        D.n1 = P.n[D.p]; D.n2 = P.n[D.p + 1];
-    } else {
-        if (P.ctrl->ready) return;
-        D = load_dims(P, v, dir, pp);
-    }
-    if (!D.active) return;
-    Partial braw = reduce_parts(P.part + ((i64)v * 2 + 0) * GMAX, G, shp);
-    Partial bres = reduce_parts(P.part + ((i64)v * 2 + 1) * GMAX, G, shp);
+    if (!fold_partials(P, v, braw, bres, shp)) return;
     if (threadIdx.x == 0) {
         if (probe_out) { probe_out[0] = braw; probe_out[1] = bres; return; }
-        VState& S = P.st[v];
-        const i64 m1 = (i64)D.r0 * D.n1;
-        S.amax = fmax(S.amax, braw.absv);
+        VState& St = P.st[v];
+        St.amax = fmax(St.amax, braw.absv);
         i64 x = bres.idx;
         i64 kq = x / m1; int ij = (int)(x - kq * m1);
-        S.qq = (int)(kq / D.n2) + 1; S.kk = (int)(kq % D.n2) + 1;
-        S.jj = ij / D.r0 + 1; S.ii = ij % D.r0 + 1;
-        S.pivot = bres.val;
-        S.done = 1; S.havecol = 1; S.haverow = 1; S.crs = 0; S.upd = 0;
-        S.neval += m1 * D.n2 * D.r2;
+        St.qq = (int)(kq / D.n2) + 1; St.kk = (int)(kq % D.n2) + 1;
+        St.jj = ij / D.r0 + 1; St.ii = ij % D.r0 + 1;
+        St.pivot = bres.val;
+        St.done = 1; St.havecol = 1; St.haverow = 1; St.crs = 0; St.upd = 0;
+        St.neval += m1 * D.n2 * D.r2;
     }
 }
 
 // ----------------------------------------------------------------------------
 // K4: accept test and index-set update (dmrgg.f90:598-660)
 // ----------------------------------------------------------------------------
-__global__ void k_accept(DevPlan P, int it, int dir, int pp, double small_element, double small_pivot) {
+__global__ void k_accept(DevPlan P, int dir, int pp, double small_element, double small_pivot) {
     if (P.ctrl->ready) return;
+    const int it = P.ctrl->it;
     const int v = blockIdx.y;
     const Dims D = load_dims(P, v, dir, pp);
     VisitOut& O = P.vlog[((i64)(it - 1) * P.maxnb + (pp - 1)) * P.P + v];
@@ -742,6 +850,14 @@ __global__ void k_update_main(DevPlan P, int dir, int pp) {
             rowp[k + (i64)D.n2 * (q + (i64)P.Rmax * t)] = brow1[x];
         }
     }
+    // r(p) = r(p) + 1 (dmrgg.f90:752) once every CTA of this virtual rank has finished reading the old rank
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tk = atomicAdd(P.tickets + v, 1u);
+        s_last = (tk == gridDim.x - 1);
+        if (s_last) { P.tickets[v] = 0; P.rk[D.p] = D.r1 + 1; }
+    }
 }
 
 // neighbour factors (dmrgg.f90:715-749): new column of row(p) through d2_luar(inv(p-1)), new row of col(p+1)
@@ -794,24 +910,9 @@ __global__ void k_update_nbr(DevPlan P, int dir, int pp) {
     }
 }
 
-__global__ void k_end_visit(DevPlan P, int dir, int pp) {
-    if (P.ctrl->ready) return;
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= P.P) return;
-    const Dims D = load_dims(P, v, dir, pp);
-    if (!D.active) return;
-    if (P.st[v].upd) P.rk[D.p] = D.r1 + 1;
-}
-
 // ----------------------------------------------------------------------------
 // sweep begin / end
 // ----------------------------------------------------------------------------
-__global__ void k_sweep_begin(DevPlan P) {
-    if (P.ctrl->ready) return;
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x <= P.d) P.rks[x] = P.rk[x];
-    if (x < P.P) { P.st[x].pivotmax = -1.0; P.st[x].pivotmin = -1.0; }
-}
 // MPI_ALLREDUCE(MAX) of (amax, pivotmax, -pivotmin) (dmrgg.f90:852-870); single thread, P is small
 __global__ void k_allreduce(DevPlan P) {
     if (P.ctrl->ready) return;
@@ -828,44 +929,47 @@ __global__ void k_allreduce(DevPlan P) {
         }
     }
 }
-__global__ void k_sweep_end(DevPlan P) {
-    if (P.ctrl->ready) return;
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    i64 ne = 0;
-    for (int v = 0; v < P.P; ++v) ne += P.st[v].neval;
-    P.sweep_out->neval = ne;
-    P.sweep_out->amax = P.st[0].amax;
-    P.sweep_out->pivotmax = P.st[0].pivotmax;
-    P.sweep_out->pivotmin = P.st[0].pivotmin;
-    for (int v = 0; v < P.P; ++v) P.st[v].pivotmax_prev = P.st[v].pivotmax;   // dmrgg.f90:961
-}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__global__ void k_run_begin(DevPlan P) {
+__global__ void k_run_begin(DevPlan P, unsigned long long seed, int has_accuracy, double accuracy) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    P.ctrl->ready = 0; P.ctrl->strike = 0; P.ctrl->error = 0; P.ctrl->nsweeps = 0;
+    P.ctrl->ready = 0; P.ctrl->strike = 0; P.ctrl->error = 0; P.ctrl->nsweeps = 0; P.ctrl->it = 1;
+    P.ctrl->seed = seed; P.ctrl->has_accuracy = has_accuracy; P.ctrl->accuracy = accuracy;
     P.ctrl->t0_ns = globaltimer_ns();
+    for (int v = 0; v < P.P; ++v) P.tickets[v] = 0;
 }
-// record of sweep `it` (after the quadrature) + the exit test of dmrgg.f90:1010-1019
-__global__ void k_sweep_log(DevPlan P, int it, int maxrank) {
+// end of sweep `it`: the scalar reductions of dmrgg.f90:961-967, the record of the sweep (after the quadrature), the exit
+// test of dmrgg.f90:1010-1019, and the preparation of the next sweep (rr = r snapshot of :325, pivotmax = pivotmin = -1)
+__global__ void k_sweep_log(DevPlan P, int maxrank) {
     if (P.ctrl->ready) return;
-    for (int x = threadIdx.x; x <= P.d; x += blockDim.x) P.rklog[(i64)it * (P.d + 1) + x] = P.rk[x];
+    const int it = P.ctrl->it;
+    for (int x = threadIdx.x; x <= P.d; x += blockDim.x) { int r = P.rk[x]; P.rklog[(i64)it * (P.d + 1) + x] = r; P.rks[x] = r; }
+    __syncthreads();
     if (threadIdx.x != 0) return;
-    SweepOut o = *P.sweep_out;
+    i64 ne = 0;
+    for (int v = 0; v < P.P; ++v) ne += P.st[v].neval;
+    SweepOut o;
+    o.val = P.sweep_out->val;
+    o.neval = ne; o.amax = P.st[0].amax; o.pivotmax = P.st[0].pivotmax; o.pivotmin = P.st[0].pivotmin;
     o.t_ns = globaltimer_ns() - P.ctrl->t0_ns;
-    o.valid = 1;
+    o.valid = 1; o.pad = 0;
     P.slog[it] = o;
+    for (int v = 0; v < P.P; ++v) {
+        P.st[v].pivotmax_prev = P.st[v].pivotmax;        // dmrgg.f90:961
+        P.st[v].pivotmax = -1.0; P.st[v].pivotmin = -1.0; // dmrgg.f90:326-327 of the next sweep
+    }
     P.ctrl->nsweeps = it;
     int ready = 0;
     if (maxrank > 0) ready = (it + 1 >= maxrank);
-    if (P.has_accuracy) {
-        if (o.pivotmax <= P.accuracy * o.amax) P.ctrl->strike += 1; else P.ctrl->strike = 0;
+    if (P.ctrl->has_accuracy) {
+        if (o.pivotmax <= P.ctrl->accuracy * o.amax) P.ctrl->strike += 1; else P.ctrl->strike = 0;
         ready = ready || (P.ctrl->strike >= 3);
     }
     if (P.ctrl->error) ready = 1;
+    P.ctrl->it = it + 1;
     __threadfence();
     P.ctrl->ready = ready;
 }
@@ -893,7 +997,7 @@ __global__ void k_exchange_corner(DevPlan P) {
         PointSrc s;
         s.L = P.Lidx + P.offL[c - 1]; s.nl = c - 1; s.i = rc1; s.j = j + 1; s.k = 0; s.hask = 0;
         s.R = P.Ridx + P.offR[c]; s.q = rc; s.Rmax = P.Rmax;
-        double f = eval_point<KIND>(P, s, A);
+        double f = eval_src<KIND>(P, s, A);
         argc[(rc1 - 1) + (i64)P.Rmax * (j + (i64)nc * (rc - 1))] = f;
         amax_take(best, f, j);
     }
@@ -1115,7 +1219,7 @@ __global__ void k_init_search(DevPlan P, int nn, int snum, double* b) {
     const double* A = stage_aux<KIND>(P, smem);
     for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < nn * snum; x += gridDim.x * blockDim.x) {
         DiagSrc s; s.n = P.n; s.k = x % nn + 1; s.s = x / nn;
-        b[x] = eval_point<KIND>(P, s, A);
+        b[x] = eval_src<KIND>(P, s, A);
     }
 }
 // fiber of core p through the initial cross: arg(p)(1,j,1) = f(ind0 with position p := j); tables hold pivot 1 already
@@ -1130,7 +1234,322 @@ __global__ void k_init_cross(DevPlan P) {
         PointSrc s;
         s.L = P.Lidx + P.offL[p - 1]; s.nl = p - 1; s.i = 1; s.j = j + 1; s.k = 0; s.hask = 0;
         s.R = P.Ridx + P.offR[p]; s.q = 1; s.Rmax = P.Rmax;
-        a[(i64)P.Rmax * j] = eval_point<KIND>(P, s, A);
+        a[(i64)P.Rmax * j] = eval_src<KIND>(P, s, A);
+    }
+}
+
+// =============================================================================
+// Warp-cooperative triangular recurrences (d2_luar / d2_lual, lr.f90:124-154).
+//
+// The recurrences are sequential by definition, but only along ONE chain per output: row s of d2_luar needs
+// tmp_s = sum_{u<s} y(u)*g(s,u) accumulated in ascending u, and y(u) is final after step u-1.  A warp therefore runs
+// the chain as a wavefront: lane s keeps tmp_s, at step u the final y(u) is broadcast and every lane s > u adds its
+// term — the same additions in the same order as the reference, r steps instead of r^2/2, no memory on the chain.
+// Lanes own rows s = lane + 32*t, t < MAXRPL (r <= 32*MAXRPL).
+// =============================================================================
+constexpr int MAXRPL = 4;
+constexpr unsigned FULLMASK = 0xffffffffu;
+
+template <class GF>
+__device__ __forceinline__ void warp_luar(double (&y)[MAXRPL], int r, GF g) {
+    const int lane = threadIdx.x & 31;
+    double tmp[MAXRPL];
+#pragma unroll
+    for (int t = 0; t < MAXRPL; ++t) tmp[t] = 0.0;
+    for (int u = 0; u + 1 < r; ++u) {
+        double yu = 0.0;
+#pragma unroll
+        for (int t = 0; t < MAXRPL; ++t) if (t == (u >> 5)) yu = y[t];
+        yu = __shfl_sync(FULLMASK, yu, u & 31);
+#pragma unroll
+        for (int t = 0; t < MAXRPL; ++t) {
+            const int s = lane + 32 * t;
+            if (s > u && s < r) tmp[t] = tmp[t] + yu * g(s, u);
+        }
+        const int s1 = u + 1;
+#pragma unroll
+        for (int t = 0; t < MAXRPL; ++t) if (t == (s1 >> 5) && lane == (s1 & 31)) y[t] = y[t] + (-tmp[t]);
+    }
+}
+// d2_lual on one row: val(c) = y(c) + sum_{u<c} (-g(c,u))*y(u) (ascending u), then val(c) *= dinv(c); gl(c,u), dinv(c) functors
+template <class GF, class DF>
+__device__ __forceinline__ void warp_lual(double (&y)[MAXRPL], int r, GF g, DF dinv) {
+    const int lane = threadIdx.x & 31;
+    if (r > 0 && lane == 0) y[0] = dinv(0) * y[0];
+    for (int u = 0; u + 1 < r; ++u) {
+        double yu = 0.0;
+#pragma unroll
+        for (int t = 0; t < MAXRPL; ++t) if (t == (u >> 5)) yu = y[t];
+        yu = __shfl_sync(FULLMASK, yu, u & 31);
+#pragma unroll
+        for (int t = 0; t < MAXRPL; ++t) {
+            const int c = lane + 32 * t;
+            if (c > u && c < r) y[t] = y[t] + (-g(c, u)) * yu;
+        }
+        const int c1 = u + 1;
+#pragma unroll
+        for (int t = 0; t < MAXRPL; ++t) if (t == (c1 >> 5) && lane == (c1 & 31)) y[t] = dinv(c1) * y[t];
+    }
+}
+// packed LU accessors (dmrgg.f90:650-660): row part g(s^2 + u), column part g((c+1)^2 - (c+1) + u), pivot g((c+1)^2 - 1)
+struct GLuar { const double* g; __device__ __forceinline__ double operator()(int s, int u) const { return g[(i64)s * s + u]; } };
+struct GLual { const double* g; __device__ __forceinline__ double operator()(int c, int u) const { return g[(i64)(c + 1) * (c + 1) - (c + 1) + u]; } };
+struct GDinv { const double* g; __device__ __forceinline__ double operator()(int c) const { return 1.0 / g[(i64)(c + 1) * (c + 1) - 1]; } };
+// transposed shared-memory copies: T[u*ld + s]; lanes read consecutive s -> conflict free
+struct GSm { const double* T; int ld; __device__ __forceinline__ double operator()(int s, int u) const { return T[u * ld + s]; } };
+struct DSm { const double* d; __device__ __forceinline__ double operator()(int c) const { return d[c]; } };
+__device__ __forceinline__ void stage_luar(const double* g, int r, double* T) {
+    for (int x = threadIdx.x; x < r * r; x += blockDim.x) { int s = x / r, u = x - s * r; if (u < s) T[u * r + s] = g[(i64)s * s + u]; }
+}
+__device__ __forceinline__ void stage_lual(const double* g, int r, double* T, double* dinv) {
+    for (int x = threadIdx.x; x < r * r; x += blockDim.x) { int c = x / r, u = x - c * r; if (u < c) T[u * r + c] = g[(i64)(c + 1) * (c + 1) - (c + 1) + u]; }
+    for (int c = threadIdx.x; c < r; c += blockDim.x) dinv[c] = 1.0 / g[(i64)(c + 1) * (c + 1) - 1];
+}
+
+// ----------------------------------------------------------------------------
+// quadrature, shared-memory versions (same arithmetic as k_quad_contract / k_quad_lua / k_quad_chain / k_quad_tree)
+// ----------------------------------------------------------------------------
+// ttqq(p)(i,k) = sum_j arg(p)(i,j,k)*w(j): CTA (k, p) stages the slice arg(p)(:,:,k) chunk by chunk with all threads
+// (deep memory-level parallelism), then r0 threads run the ordered sums out of shared memory.
+__global__ void k_quad_contract_sm(DevPlan P, int use_weights, int chunk_doubles) {
+    extern __shared__ double smem[];
+    const int p = blockIdx.y + 1, k = blockIdx.x;
+    const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
+    if (k >= r1) return;
+    const double* a = P.arg + P.coreOff[p] + (i64)P.Rmax * n * k;
+    const double* w = P.quadw + P.quadOff[p];
+    int Jc = chunk_doubles / r0; if (Jc > n) Jc = n;
+    double y = 0.0;
+    for (int j0 = 0; j0 < n; j0 += Jc) {
+        const int jc = min(Jc, n - j0);
+        for (int e = threadIdx.x; e < r0 * jc; e += blockDim.x) { int jj = e / r0, i = e - jj * r0; smem[e] = a[i + (i64)P.Rmax * (j0 + jj)]; }
+        __syncthreads();
+        if (threadIdx.x < r0) {
+            if (use_weights) for (int jj = 0; jj < jc; ++jj) y = y + w[j0 + jj] * smem[threadIdx.x + r0 * jj];
+            else             for (int jj = 0; jj < jc; ++jj) y = y + smem[threadIdx.x + r0 * jj];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < r0) P.ttqq[(i64)p * P.Rmax * P.Rmax + threadIdx.x + (i64)P.Rmax * k] = y;
+}
+// dtt_lua on the contracted cores: one CTA per core, matrix and both packed LUs staged in shared memory,
+// one warp per column (d2_luar) then one warp per row (d2_lual).  Requires r <= 32*MAXRPL.
+__global__ void k_quad_lua_sm(DevPlan P) {
+    extern __shared__ double smem[];
+    if (P.ctrl->ready) return;
+    const int p = blockIdx.x + 1;
+    const int r0 = P.rk[p - 1], r1 = P.rk[p];
+    double* M = smem;                          // r0 x r1, ld r0
+    double* TL = M + r0 * r1;                  // luar table of inv(p-1), r0 x r0
+    double* TR = TL + r0 * r0;                 // lual table of inv(p), r1 x r1
+    double* DI = TR + r1 * r1;                 // r1
+    double* gm = P.ttqq + (i64)p * P.Rmax * P.Rmax;
+    for (int x = threadIdx.x; x < r0 * r1; x += blockDim.x) { int k = x / r0, i = x - k * r0; M[x] = gm[i + (i64)P.Rmax * k]; }
+    stage_luar(P.inv + (i64)(p - 1) * P.Rmax * P.Rmax, r0, TL);
+    if (p < P.d) stage_lual(P.inv + (i64)p * P.Rmax * P.Rmax, r1, TR, DI);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int k = wid; k < r1; k += nw) {
+        double y[MAXRPL];
+#pragma unroll
+        for (int t = 0; t < MAXRPL; ++t) { int sidx = lane + 32 * t; y[t] = (sidx < r0) ? M[sidx + r0 * k] : 0.0; }
+        warp_luar(y, r0, GSm{TL, r0});
+#pragma unroll
+        for (int t = 0; t < MAXRPL; ++t) { int sidx = lane + 32 * t; if (sidx < r0) M[sidx + r0 * k] = y[t]; }
+    }
+    __syncthreads();
+    if (p < P.d) {
+        for (int i = wid; i < r0; i += nw) {
+            double y[MAXRPL];
+#pragma unroll
+            for (int t = 0; t < MAXRPL; ++t) { int c = lane + 32 * t; y[t] = (c < r1) ? M[i + r0 * c] : 0.0; }
+            warp_lual(y, r1, GSm{TR, r1}, DSm{DI});
+#pragma unroll
+            for (int t = 0; t < MAXRPL; ++t) { int c = lane + 32 * t; if (c < r1) M[i + r0 * c] = y[t]; }
+        }
+        __syncthreads();
+    }
+    for (int x = threadIdx.x; x < r0 * r1; x += blockDim.x) { int k = x / r0, i = x - k * r0; gm[i + (i64)P.Rmax * k] = M[x]; }
+}
+// C(m x n) = A(m x kd) * B(kd x n), all in shared memory with leading dimension ld, dgemm order
+__device__ __forceinline__ void mat_mul_sm(const double* A, int m, int kd, const double* B, int n, double* C, int ld) {
+    for (int e = threadIdx.x; e < m * n; e += blockDim.x) {
+        int j = e / m, i = e - j * m;
+        double c = 0.0;
+        for (int l = 0; l < kd; ++l) c = c + B[l + ld * j] * A[i + ld * l];
+        C[i + ld * j] = c;
+    }
+}
+__device__ __forceinline__ void mat_load_sm(const double* g, int m, int n, int ldg, double* S, int ld) {
+    for (int e = threadIdx.x; e < m * n; e += blockDim.x) { int j = e / m, i = e - j * m; S[i + ld * j] = g[i + (i64)ldg * j]; }
+}
+// chain product per virtual rank (dmrgg.f90:1323-1345): CTA v, three shared buffers of Rmax^2
+__global__ void k_quad_chain_sm(DevPlan P) {
+    extern __shared__ double smem[];
+    const int v = blockIdx.x;
+    const int first = P.own[v];
+    int last = P.own[v + 1] - 1;
+    if (v == P.P - 1) last = P.d;
+    const int ld = P.Rmax;
+    const i64 msz = (i64)ld * ld;
+    double* cur = smem; double* nxt = smem + msz; double* B = smem + 2 * msz;
+    const int m = P.rk[first - 1];
+    mat_load_sm(P.ttqq + (i64)first * msz, m, P.rk[first], ld, cur, ld);
+    __syncthreads();
+    for (int p = first + 1; p <= last; ++p) {
+        mat_load_sm(P.ttqq + (i64)p * msz, P.rk[p - 1], P.rk[p], ld, B, ld);
+        __syncthreads();
+        mat_mul_sm(cur, m, P.rk[p - 1], B, P.rk[p], nxt, ld);
+        __syncthreads();
+        double* t = cur; cur = nxt; nxt = t;
+    }
+    double* out = P.chain + (i64)v * msz;
+    const int nl = P.rk[last];
+    for (int e = threadIdx.x; e < m * nl; e += blockDim.x) { int j = e / m, i = e - j * m; out[i + (i64)ld * j] = cur[i + ld * j]; }
+    if (P.P == 1 && threadIdx.x == 0) P.sweep_out->val = cur[0];
+}
+// binary tree over virtual ranks (dmrgg.f90:1355-1405): level `q`, CTA per receiving rank; launched once per level
+__global__ void k_quad_tree_sm(DevPlan P, int q, int last_level) {
+    extern __shared__ double smem[];
+    const int me = blockIdx.x * 2 * q, her = me + q;
+    const int ld = P.Rmax;
+    const i64 msz = (i64)ld * ld;
+    if (her < P.P) {
+        double* A = smem; double* B = smem + msz; double* C = smem + 2 * msz;
+        int herend = her + q; if (herend > P.P) herend = P.P;
+        const int m = P.rk[P.own[me] - 1], kd = P.rk[P.own[her] - 1];
+        const int n = (herend == P.P) ? P.rk[P.d] : P.rk[P.own[herend] - 1];
+        mat_load_sm(P.chain + (i64)me * msz, m, kd, ld, A, ld);
+        mat_load_sm(P.chain + (i64)her * msz, kd, n, ld, B, ld);
+        __syncthreads();
+        mat_mul_sm(A, m, kd, B, n, C, ld);
+        __syncthreads();
+        double* out = P.chain + (i64)me * msz;
+        for (int e = threadIdx.x; e < m * n; e += blockDim.x) { int j = e / m, i = e - j * m; out[i + (i64)ld * j] = C[i + ld * j]; }
+        if (last_level && me == 0 && threadIdx.x == 0) P.sweep_out->val = C[0];
+    }
+}
+
+// ----------------------------------------------------------------------------
+// warp-per-fiber versions of the factor extensions (k_update_nbr, k_exchange_extend): the packed LU is staged
+// transposed in shared memory once per CTA, every warp runs one mode index as a wavefront.
+// blockIdx.z = 0: d2_luar part, 1: d2_lual part.
+// ----------------------------------------------------------------------------
+struct ExtJob {               // one batch of independent recurrences sharing one packed LU
+    const double* g; int r;   // packed LU and its size
+    int count;                // number of independent chains (mode indices)
+    const double* src; i64 src_chain, src_elem;   // chain x, element s : src[x*src_chain + s*src_elem]
+    double* dst; i64 dst_chain, dst_elem;
+};
+__device__ __forceinline__ void run_ext_luar(const ExtJob& J, double* sm) {
+    stage_luar(J.g, J.r, sm);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int x = blockIdx.x * nw + wid; x < J.count; x += gridDim.x * nw) {
+        double y[MAXRPL];
+#pragma unroll
+        for (int t = 0; t < MAXRPL; ++t) { int sidx = lane + 32 * t; y[t] = (sidx < J.r) ? J.src[x * J.src_chain + sidx * J.src_elem] : 0.0; }
+        warp_luar(y, J.r, GSm{sm, J.r});
+#pragma unroll
+        for (int t = 0; t < MAXRPL; ++t) { int sidx = lane + 32 * t; if (sidx < J.r) J.dst[x * J.dst_chain + sidx * J.dst_elem] = y[t]; }
+    }
+}
+__device__ __forceinline__ void run_ext_lual(const ExtJob& J, double* sm) {
+    double* di = sm + J.r * J.r;
+    stage_lual(J.g, J.r, sm, di);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int x = blockIdx.x * nw + wid; x < J.count; x += gridDim.x * nw) {
+        double y[MAXRPL];
+#pragma unroll
+        for (int t = 0; t < MAXRPL; ++t) { int c = lane + 32 * t; y[t] = (c < J.r) ? J.src[x * J.src_chain + c * J.src_elem] : 0.0; }
+        warp_lual(y, J.r, GSm{sm, J.r}, DSm{di});
+#pragma unroll
+        for (int t = 0; t < MAXRPL; ++t) { int c = lane + 32 * t; if (c < J.r) J.dst[x * J.dst_chain + c * J.dst_elem] = y[t]; }
+    }
+}
+// neighbour factors after an accepted pivot (dmrgg.f90:715-749)
+__global__ void k_update_nbr_w(DevPlan P, int dir, int pp) {
+    extern __shared__ double smem[];
+    if (P.ctrl->ready) return;
+    const int v = blockIdx.y;
+    const Dims D = load_dims(P, v, dir, pp);
+    if (!D.active || !P.st[v].upd) return;
+    const int lo = P.own[v], hi = P.own[v + 1], t = D.r1;
+    if (blockIdx.z == 0) {
+        if (D.p <= lo || D.r0 < 1) return;
+        ExtJob J;   // chains j (n1 of them), elements s < r0: src acol1(s,j), dst rowT(p)(s, j, q = t)
+        J.g = P.inv + (i64)(D.p - 1) * P.Rmax * P.Rmax; J.r = D.r0; J.count = D.n1;
+        J.src = P.acol1 + (i64)v * P.Rmax * P.nmax; J.src_chain = D.r0; J.src_elem = 1;
+        J.dst = P.rowT + P.coreOff[D.p] + (i64)D.n1 * t; J.dst_chain = 1; J.dst_elem = (i64)D.n1 * P.Rmax;
+        run_ext_luar(J, smem);
+    } else {
+        if (D.p >= hi - 1 || D.r2 < 1) return;
+        ExtJob J;   // chains k (n2), elements c < r2: src arow1(k,c), dst col(p+1)(t, k, c)
+        J.g = P.inv + (i64)(D.p + 1) * P.Rmax * P.Rmax; J.r = D.r2; J.count = D.n2;
+        J.src = P.arow1 + (i64)v * P.Rmax * P.nmax; J.src_chain = 1; J.src_elem = D.n2;
+        J.dst = P.col + P.coreOff[D.p + 1] + t; J.dst_chain = P.Rmax; J.dst_elem = (i64)P.Rmax * D.n2;
+        run_ext_lual(J, smem);
+    }
+}
+// factor extensions of the neighbour exchange (dmrgg.f90:939-951, dmrggmp.f90:616-626)
+__global__ void k_exchange_extend_w(DevPlan P) {
+    extern __shared__ double smem[];
+    if (P.ctrl->ready) return;
+    const int b = blockIdx.y;
+    const int c = P.own[b + 1];
+    const int rc1 = P.rk[c - 1], rc1s = P.rks[c - 1], rc = P.rk[c], rcs = P.rks[c];
+    const int nc = P.n[c];
+    const double* argc = P.arg + P.coreOff[c];
+    if (blockIdx.z == 0) {
+        if (!(rc > rcs)) return;
+        ExtJob J;   // LEFT receiver: chains k, elements s < rc1: src arg(c)(s,k,rc), dst rowT(c)(s,k,rc)
+        J.g = P.inv + (i64)(c - 1) * P.Rmax * P.Rmax; J.r = rc1; J.count = nc;
+        J.src = argc + (i64)P.Rmax * nc * (rc - 1); J.src_chain = P.Rmax; J.src_elem = 1;
+        J.dst = P.rowT + P.coreOff[c] + (i64)nc * (rc - 1); J.dst_chain = 1; J.dst_elem = (i64)nc * P.Rmax;
+        run_ext_luar(J, smem);
+    } else {
+        if (!(rc1 > rc1s)) return;
+        ExtJob J;   // RIGHT receiver: chains j, elements cc < rc: src arg(c)(rc1,j,cc), dst col(c)(rc1,j,cc)
+        J.g = P.inv + (i64)c * P.Rmax * P.Rmax; J.r = rc; J.count = nc;
+        J.src = argc + (rc1 - 1); J.src_chain = P.Rmax; J.src_elem = (i64)P.Rmax * nc;
+        J.dst = P.col + P.coreOff[c] + (rc1 - 1); J.dst_chain = P.Rmax; J.dst_elem = (i64)P.Rmax * nc;
+        run_ext_lual(J, smem);
+    }
+}
+// finalisation with wavefronts: d2_luar over the n*r1 columns, then d2_lual over the r0*n rows of every core
+__global__ void k_lua_r_w(DevPlan P) {
+    extern __shared__ double smem[];
+    const int p = blockIdx.y + 1;
+    const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
+    if (r0 < 2) return;
+    ExtJob J;
+    J.g = P.inv + (i64)(p - 1) * P.Rmax * P.Rmax; J.r = r0; J.count = n * r1;
+    J.src = P.arg + P.coreOff[p]; J.src_chain = P.Rmax; J.src_elem = 1;
+    J.dst = P.arg + P.coreOff[p]; J.dst_chain = P.Rmax; J.dst_elem = 1;
+    run_ext_luar(J, smem);
+}
+__global__ void k_lua_l_w(DevPlan P) {
+    extern __shared__ double smem[];
+    const int p = blockIdx.y + 1;
+    if (p >= P.d) return;
+    const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
+    // chains are the rows (i,j): x = i + r0*j lives at i + Rmax*j -> two-level stride; run per j with chain index i
+    double* di = smem + r1 * r1;
+    stage_lual(P.inv + (i64)p * P.Rmax * P.Rmax, r1, smem, di);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double* a = P.arg + P.coreOff[p];
+    const i64 ys = (i64)P.Rmax * n;
+    for (int x = blockIdx.x * nw + wid; x < r0 * n; x += gridDim.x * nw) {
+        const int j = x / r0, i = x - j * r0;
+        double* base = a + i + (i64)P.Rmax * j;
+        double y[MAXRPL];
+#pragma unroll
+        for (int t = 0; t < MAXRPL; ++t) { int c = lane + 32 * t; y[t] = (c < r1) ? base[c * ys] : 0.0; }
+        warp_lual(y, r1, GSm{smem, r1}, DSm{di});
+#pragma unroll
+        for (int t = 0; t < MAXRPL; ++t) { int c = lane + 32 * t; if (c < r1) base[c * ys] = y[t]; }
     }
 }
 

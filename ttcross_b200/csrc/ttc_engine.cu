@@ -20,6 +20,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -107,7 +109,9 @@ struct ttc_handle {
     std::vector<std::vector<std::array<int, 4>>> vip_h;
     std::vector<u64> rng_k;
     DevPlan plan;
-    std::vector<void*> allocs;
+    std::vector<void*> allocs; std::vector<size_t> alloc_bytes;
+    std::vector<std::pair<void*, size_t>> host_blocks;
+    double* stage_h = nullptr; size_t stage_cap = 0;   // pinned staging for result copy-out
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int* lot_h = nullptr; VisitOut* out_h = nullptr; SweepOut* sweep_h = nullptr;   // pinned
@@ -115,7 +119,15 @@ struct ttc_handle {
     void* flush_d = nullptr; size_t flush_cap = 0;
     double* initb = nullptr;
     int* ready_h = nullptr;              // pinned mirror of Ctrl::ready
-    int force_sync = 0, force_host_lottery = 0;
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    std::vector<long long> graph_sig;
+    long long graph_nodes[2] = {0, 0};
+    long long graph_kc[2][16] = {{0}};
+    long long setup_serial = 0;
+    int no_graph = 0;
+    bool use_wave = true;                // warp-wavefront / shared-memory support kernels (needs Rmax <= 32*MAXRPL)
+    size_t sm_contract = 0, sm_lua = 0, sm_mat3 = 0, sm_ext = 0, sm_lot = 0, sm_fiber = 0, sm_sb = 0;
+    int force_sync = 0, force_host_lottery = 0, force_simple = 0;
     int nsm = 148;
 
     std::vector<int> setup_sig;
@@ -148,11 +160,52 @@ std::string g_create_err;
         }                                                                                                   \
     } while (0)
 
+// ----------------------------------------------------------------------------
+// process-level caching of device and pinned-host blocks: a handle created for the same problem shape as a
+// destroyed one gets its blocks back without cudaMalloc / cudaMallocHost (both cost far more than a sweep)
+// ----------------------------------------------------------------------------
+struct BlockPool {
+    std::multimap<std::pair<int, size_t>, void*> free_dev, free_host;
+    size_t cached_dev = 0, cached_host = 0;
+    static size_t round(size_t b) { return (b + 511) & ~(size_t)511; }
+    cudaError_t get_dev(int dev, size_t bytes, void** p) {
+        bytes = round(bytes);
+        auto it = free_dev.find({dev, bytes});
+        if (it != free_dev.end()) { *p = it->second; free_dev.erase(it); cached_dev -= bytes; return cudaSuccess; }
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e != cudaSuccess) { trim(); e = cudaMalloc(p, bytes); }
+        return e;
+    }
+    void put_dev(int dev, size_t bytes, void* p) {
+        bytes = round(bytes);
+        if (cached_dev + bytes > ((size_t)4 << 30)) { cudaFree(p); return; }
+        free_dev.insert({{dev, bytes}, p}); cached_dev += bytes;
+    }
+    cudaError_t get_host(size_t bytes, void** p) {
+        bytes = round(bytes);
+        auto it = free_host.find({0, bytes});
+        if (it != free_host.end()) { *p = it->second; free_host.erase(it); cached_host -= bytes; return cudaSuccess; }
+        return cudaMallocHost(p, bytes);
+    }
+    void put_host(size_t bytes, void* p) {
+        bytes = round(bytes);
+        if (cached_host + bytes > ((size_t)256 << 20)) { cudaFreeHost(p); return; }
+        free_host.insert({{0, bytes}, p}); cached_host += bytes;
+    }
+    void trim() {
+        for (auto& kv : free_dev) cudaFree(kv.second);
+        free_dev.clear(); cached_dev = 0;
+    }
+};
+BlockPool g_pool;
+std::mutex g_pool_mu;
+
 template <class T>
 int dev_alloc(ttc_handle* h, T** p, size_t count, bool zero = true) {
     void* q = nullptr;
     size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-    CUDA_TRY(h, cudaMalloc(&q, bytes));
+    { std::lock_guard<std::mutex> lk(g_pool_mu); CUDA_TRY(h, g_pool.get_dev(h->device, bytes, &q)); }
+    h->alloc_bytes.push_back(bytes);
     if (zero) CUDA_TRY(h, cudaMemsetAsync(q, 0, bytes, h->stream));
     h->allocs.push_back(q);
     *p = (T*)q;
@@ -168,13 +221,18 @@ int dev_upload(ttc_handle* h, T** p, const std::vector<T>& v) {
 
 void free_device(ttc_handle* h) {
     h->setup_sig.clear();
-    for (void* p : h->allocs) cudaFree(p);
-    h->allocs.clear();
-    if (h->lot_h) { cudaFreeHost(h->lot_h); h->lot_h = nullptr; }
-    if (h->out_h) { cudaFreeHost(h->out_h); h->out_h = nullptr; }
-    if (h->sweep_h) { cudaFreeHost(h->sweep_h); h->sweep_h = nullptr; }
-    if (h->ready_h) { cudaFreeHost(h->ready_h); h->ready_h = nullptr; }
-    if (h->pack_d) { cudaFree(h->pack_d); h->pack_d = nullptr; h->pack_cap = 0; }
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int g = 0; g < 2; ++g) if (h->gexec[g]) { cudaGraphExecDestroy(h->gexec[g]); h->gexec[g] = nullptr; }
+    h->graph_sig.clear();
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (size_t i = 0; i < h->allocs.size(); ++i) g_pool.put_dev(h->device, h->alloc_bytes[i], h->allocs[i]);
+        for (auto& hb : h->host_blocks) g_pool.put_host(hb.second, hb.first);
+        if (h->pack_d) { g_pool.put_dev(h->device, h->pack_cap * sizeof(double), h->pack_d); }
+    }
+    h->allocs.clear(); h->alloc_bytes.clear(); h->host_blocks.clear();
+    h->lot_h = nullptr; h->out_h = nullptr; h->sweep_h = nullptr; h->ready_h = nullptr; h->stage_h = nullptr; h->stage_cap = 0;
+    h->pack_d = nullptr; h->pack_cap = 0;
     if (h->ev0) { cudaEventDestroy(h->ev0); h->ev0 = nullptr; }
     if (h->ev1) { cudaEventDestroy(h->ev1); h->ev1 = nullptr; }
     if (h->stream) { cudaStreamDestroy(h->stream); h->stream = nullptr; }
@@ -216,6 +274,24 @@ inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
 int threads_for(const ttc_handle* h) { return h->kind == TTC_MVN ? 64 : 256; }
 size_t aux_smem(const ttc_handle* h) { return (size_t)h->plan.auxsm * sizeof(double); }
 
+int ensure_pack(ttc_handle* h, size_t cnt) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (cnt > h->pack_cap) {
+        if (h->pack_d) g_pool.put_dev(h->device, h->pack_cap * sizeof(double), h->pack_d);
+        h->pack_d = nullptr; h->pack_cap = 0;
+        void* q = nullptr;
+        CUDA_TRY(h, g_pool.get_dev(h->device, cnt * sizeof(double), &q));
+        h->pack_d = (double*)q; h->pack_cap = cnt;
+    }
+    if (cnt > h->stage_cap) {
+        void* q = nullptr;
+        CUDA_TRY(h, g_pool.get_host(cnt * sizeof(double), &q));
+        h->host_blocks.push_back({q, cnt * sizeof(double)});
+        h->stage_h = (double*)q; h->stage_cap = cnt;
+    }
+    return 0;
+}
+
 int check_device(ttc_handle* h) {
     int cnt = 0;
     cudaError_t e = cudaGetDeviceCount(&cnt);
@@ -247,11 +323,10 @@ int setup_device(ttc_handle* h, int maxrank) {
     }
     free_device(h);
     h->setup_sig = sig;
+    h->setup_serial += 1;
     int st = check_device(h);
     if (st) return st;
-    cudaDeviceProp prop;
-    CUDA_TRY(h, cudaGetDeviceProperties(&prop, h->device));
-    h->nsm = prop.multiProcessorCount;
+    CUDA_TRY(h, cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, h->device));   // (cudaGetDeviceProperties costs milliseconds)
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CUDA_TRY(h, cudaEventCreate(&h->ev0));
     CUDA_TRY(h, cudaEventCreate(&h->ev1));
@@ -268,7 +343,17 @@ int setup_device(ttc_handle* h, int maxrank) {
     D.auxsm = 0;
     if (h->kind == TTC_MVN) {
         size_t need = (size_t)d * d * sizeof(double) + (size_t)Rmax * sizeof(double);
-        if (need <= 200 * 1024) D.auxsm = d * d;
+        if (need <= 100 * 1024) D.auxsm = d * d;
+    }
+    // shared-memory staging of node/weight values (left + right tables of a bond visit hold d-2 positions in total)
+    {
+        const size_t stage_d = 4 * (size_t)h->nmax + 2 * (size_t)std::max(0, d - 2) * Rmax;
+        const size_t need = ((size_t)D.auxsm + Rmax + stage_d) * sizeof(double) + (size_t)(3 * Rmax + 8) * sizeof(int);
+        D.stage = (need <= 200 * 1024 && !h->force_simple) ? 1 : 0;
+        D.stage_max = D.stage ? (int)stage_d : 0;
+        h->sm_lot = ((size_t)D.auxsm + D.stage_max) * sizeof(double) + (size_t)(3 * Rmax + 8) * sizeof(int);
+        h->sm_fiber = ((size_t)D.auxsm + Rmax + D.stage_max) * sizeof(double);
+        h->sm_sb = ((size_t)D.auxsm + D.stage_max) * sizeof(double);
     }
 
     std::vector<i64> offL(d + 2, 0), offR(d + 2, 0), coreOff(d + 2, 0), quadOff(d + 2, 0);
@@ -295,17 +380,17 @@ int setup_device(ttc_handle* h, int maxrank) {
     TRY(dev_upload(h, &dquadOff, quadOff));
     std::vector<double> qv = h->quad_or_ones();
     TRY(dev_upload(h, &dquad, qv));
-    TRY(dev_alloc(h, &dL, (size_t)accL + 1));
-    TRY(dev_alloc(h, &dR, (size_t)accR + 1));
+    TRY(dev_alloc(h, &dL, (size_t)accL + 1, false));
+    TRY(dev_alloc(h, &dR, (size_t)accR + 1, false));
     TRY(dev_alloc(h, &dvip, (size_t)(d + 1) * Rmax * 4));
     TRY(dev_alloc(h, &drk, (size_t)d + 2));
     TRY(dev_alloc(h, &drks, (size_t)d + 2));
-    TRY(dev_alloc(h, &darg, (size_t)accC));
-    TRY(dev_alloc(h, &dcol, (size_t)accC));
-    TRY(dev_alloc(h, &drow, (size_t)accC));
-    TRY(dev_alloc(h, &dinv, (size_t)(d + 1) * Rmax * Rmax));
+    TRY(dev_alloc(h, &darg, (size_t)accC, false));
+    TRY(dev_alloc(h, &dcol, (size_t)accC, false));
+    TRY(dev_alloc(h, &drow, (size_t)accC, false));
+    TRY(dev_alloc(h, &dinv, (size_t)(d + 1) * Rmax * Rmax, false));
     const size_t fsz = (size_t)P * Rmax * h->nmax;
-    TRY(dev_alloc(h, &da1, fsz)); TRY(dev_alloc(h, &db1, fsz)); TRY(dev_alloc(h, &da2, fsz)); TRY(dev_alloc(h, &db2, fsz));
+    TRY(dev_alloc(h, &da1, fsz, false)); TRY(dev_alloc(h, &db1, fsz, false)); TRY(dev_alloc(h, &da2, fsz, false)); TRY(dev_alloc(h, &db2, fsz, false));
     TRY(dev_alloc(h, &dlot, (size_t)P * 4 * h->nlotmax));
     TRY(dev_alloc(h, &dlraw, (size_t)P * h->nlotmax)); TRY(dev_alloc(h, &dlres, (size_t)P * h->nlotmax));
     TRY(dev_alloc(h, &dpart, (size_t)P * 2 * GMAX));
@@ -324,10 +409,19 @@ int setup_device(ttc_handle* h, int maxrank) {
         int s0 = dev_alloc(h, &h->initb, (size_t)nn0 * std::max(8, P));
         if (s0) return s0;
     }
-    CUDA_TRY(h, cudaMallocHost((void**)&h->lot_h, (size_t)P * 4 * h->nlotmax * sizeof(int)));
-    CUDA_TRY(h, cudaMallocHost((void**)&h->out_h, (size_t)P * sizeof(VisitOut)));
-    CUDA_TRY(h, cudaMallocHost((void**)&h->sweep_h, sizeof(SweepOut)));
-    CUDA_TRY(h, cudaMallocHost((void**)&h->ready_h, sizeof(int)));
+    {
+        // one pinned block: lot | out | sweep | ready
+        size_t b_lot = ((size_t)P * 4 * h->nlotmax * sizeof(int) + 63) & ~(size_t)63;
+        size_t b_out = ((size_t)P * sizeof(VisitOut) + 63) & ~(size_t)63;
+        size_t b_sw = (sizeof(SweepOut) + 63) & ~(size_t)63;
+        size_t tot = b_lot + b_out + b_sw + 64;
+        void* hb = nullptr;
+        { std::lock_guard<std::mutex> lk(g_pool_mu); CUDA_TRY(h, g_pool.get_host(tot, &hb)); }
+        h->host_blocks.push_back({hb, tot});
+        char* c = (char*)hb;
+        h->lot_h = (int*)c; h->out_h = (VisitOut*)(c + b_lot); h->sweep_h = (SweepOut*)(c + b_lot + b_out);
+        h->ready_h = (int*)(c + b_lot + b_out + b_sw);
+    }
     {
         int maxnb0 = 0;
         for (int v = 0; v < P; ++v) maxnb0 = std::max(maxnb0, h->own[v + 1] - h->own[v]);
@@ -338,21 +432,43 @@ int setup_device(ttc_handle* h, int maxrank) {
         s1 = dev_alloc(h, &dslog, (size_t)Rmax + 1); if (s1) return s1;
         s1 = dev_alloc(h, &drklog, (size_t)(Rmax + 1) * (d + 1)); if (s1) return s1;
         D.ctrl = dctrl; D.vlog = dvlog; D.slog = dslog; D.rklog = drklog;
+        unsigned int* dtick; s1 = dev_alloc(h, &dtick, (size_t)P + 1); if (s1) return s1;
+        D.tickets = dtick;
     }
 
-    // kernels that stage the MVN matrix need more than the default 48 KB of dynamic shared memory when d > ~75
-    if (D.auxsm) {
-        int bytes = (int)(aux_smem(h) + (size_t)(3 * Rmax + 8) * sizeof(double));
-        if (bytes > 48 * 1024) {
-            cudaFuncSetAttribute(k_lot<KIND_MVN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-            cudaFuncSetAttribute(k_fiber<KIND_MVN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-            cudaFuncSetAttribute(k_fiber<KIND_MVN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-            cudaFuncSetAttribute(k_superblock<KIND_MVN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-            cudaFuncSetAttribute(k_superblock<KIND_MVN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-            cudaFuncSetAttribute(k_exchange_corner<KIND_MVN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-            cudaFuncSetAttribute(k_init_search<KIND_MVN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-            cudaFuncSetAttribute(k_init_cross<KIND_MVN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    {
+        const size_t R = (size_t)Rmax;
+        h->use_wave = (Rmax <= 32 * MAXRPL) && !h->force_simple;
+        h->sm_contract = std::min<size_t>(R * h->nmax * sizeof(double), 96 * 1024);
+        h->sm_contract = std::max<size_t>(h->sm_contract, R * sizeof(double));
+        h->sm_lua = (3 * R * R + R) * sizeof(double);
+        h->sm_mat3 = 3 * R * R * sizeof(double);
+        h->sm_ext = (R * R + R) * sizeof(double);
+        if (h->sm_lua > 200 * 1024) h->use_wave = false;
+        if (h->use_wave) {
+            cudaFuncSetAttribute(k_quad_contract_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_contract);
+            cudaFuncSetAttribute(k_quad_lua_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_lua);
+            cudaFuncSetAttribute(k_quad_chain_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_mat3);
+            cudaFuncSetAttribute(k_quad_tree_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_mat3);
+            cudaFuncSetAttribute(k_update_nbr_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_ext);
+            cudaFuncSetAttribute(k_exchange_extend_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_ext);
+            cudaFuncSetAttribute(k_lua_r_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_ext);
+            cudaFuncSetAttribute(k_lua_l_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_ext);
         }
+    }
+    // opt in to more than 48 KB of dynamic shared memory where the staging areas need it
+    {
+        const int bl = (int)h->sm_lot, bf = (int)h->sm_fiber, bs = (int)h->sm_sb, ba = (int)aux_smem(h);
+        KIND_SWITCH(h->kind,
+            if (bl > 48 * 1024) cudaFuncSetAttribute(k_lot<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, bl);
+            if (bf > 48 * 1024) { cudaFuncSetAttribute(k_fiber<K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf);
+                                  cudaFuncSetAttribute(k_fiber<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf); }
+            if (bs > 48 * 1024) { cudaFuncSetAttribute(k_superblock<K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs);
+                                  cudaFuncSetAttribute(k_superblock<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs); }
+            if (ba > 48 * 1024) { cudaFuncSetAttribute(k_exchange_corner<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba);
+                                  cudaFuncSetAttribute(k_init_search<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba);
+                                  cudaFuncSetAttribute(k_init_cross<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba); }
+        );
     }
     return 0;
 }
@@ -404,17 +520,40 @@ void host_dims(const ttc_handle* h, int v, int dir, int pp, int& active, int& p,
 int launch_quad(ttc_handle* h, Launcher& L, bool with_lua, bool use_weights) {
     const DevPlan& D = h->plan;
     cudaStream_t s = h->stream;
-    L(KC_QUAD, [&] { k_quad_contract<<<dim3(cdiv((i64)h->Rmax * h->Rmax, 256), h->d), 256, 0, s>>>(D, use_weights ? 1 : 0); });
-    if (with_lua) L(KC_QUAD, [&] { k_quad_lua<<<h->d, 128, 0, s>>>(D); });
-    L(KC_QUAD, [&] { k_quad_chain<<<h->P, 256, 0, s>>>(D); });
-    L(KC_QUAD, [&] { k_quad_tree<<<1, 256, 0, s>>>(D); });
+    const int R = h->Rmax;
+    if (!h->use_wave) {
+        L(KC_QUAD, [&] { k_quad_contract<<<dim3(cdiv((i64)R * R, 256), h->d), 256, 0, s>>>(D, use_weights ? 1 : 0); });
+        if (with_lua) L(KC_QUAD, [&] { k_quad_lua<<<h->d, 128, 0, s>>>(D); });
+        L(KC_QUAD, [&] { k_quad_chain<<<h->P, 256, 0, s>>>(D); });
+        L(KC_QUAD, [&] { k_quad_tree<<<1, 256, 0, s>>>(D); });
+        return 0;
+    }
+    L(KC_QUAD, [&] { k_quad_contract_sm<<<dim3(R, h->d), 256, h->sm_contract, s>>>(D, use_weights ? 1 : 0, (int)(h->sm_contract / sizeof(double))); });
+    if (with_lua) L(KC_QUAD, [&] { k_quad_lua_sm<<<h->d, 512, h->sm_lua, s>>>(D); });
+    L(KC_QUAD, [&] { k_quad_chain_sm<<<h->P, 512, h->sm_mat3, s>>>(D); });
+    for (int q = 1; q < h->P; q *= 2) {
+        const int last = (2 * q >= h->P) ? 1 : 0;
+        L(KC_QUAD, [&] { k_quad_tree_sm<<<cdiv(h->P, 2 * q), 512, h->sm_mat3, s>>>(D, q, last); });
+    }
     return 0;
 }
 
 // ----------------------------------------------------------------------------
 // the sweep
 // ----------------------------------------------------------------------------
+struct Trace {
+    bool on; std::chrono::steady_clock::time_point t0; const char* what;
+    Trace(const char* w) : on(std::getenv("TTC_TRACE") != nullptr), t0(std::chrono::steady_clock::now()), what(w) {}
+    void lap(const char* tag) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[ttc trace] %s/%s: %.3f ms\n", what, tag, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
+    Trace tr("dmrgg");
     h->ran = false;
     h->pivlog.clear(); h->text.clear();
     h->s_val.clear(); h->s_neval.clear(); h->s_amax.clear(); h->s_pivotmax.clear(); h->s_erank.clear(); h->s_time.clear();
@@ -431,21 +570,22 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         if (h->own[v + 1] < h->own[v] || h->own[0] != 1 || h->own[h->P] != m) { h->err = "bad partition"; return TTC_ERR_ARG; }
     int st = setup_device(h, maxrank);
     if (st) return st;
+    tr.lap("setup_device");
     const int P = h->P, Rmax = h->Rmax;
     DevPlan& D = h->plan;
     cudaStream_t s = h->stream;
     Launcher L(h);
     const int TB = threads_for(h);
     const size_t smA = aux_smem(h);
-    const size_t smF = smA + (size_t)Rmax * sizeof(double);
+    const size_t smF = h->sm_fiber, smL = h->sm_lot, smS = h->sm_sb;
     const double eps = 2.220446049250313e-16;
     const double small_element = 10 * eps, small_pivot = 1.e-5;
     const bool has_quad = !h->quad.empty();
     char line[512];
 
-    D.seed = h->seed; D.has_accuracy = accuracy >= 0 ? 1 : 0; D.accuracy = accuracy; D.piv = h->piv;
+    D.piv = h->piv;
     CUDA_TRY(h, cudaEventRecord(h->ev0, s));
-    L(KC_MISC, [&] { k_run_begin<<<1, 32, 0, s>>>(D); });
+    L(KC_MISC, [&] { k_run_begin<<<1, 32, 0, s>>>(D, h->seed, accuracy >= 0 ? 1 : 0, accuracy); });
 
     // ---- initial cross search (dmrgg.f90:150-217)
     const int snum = std::max(8, P);
@@ -504,6 +644,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         h->vip_h[p].push_back({1, (p >= 1 && p <= d - 1) ? ind0[p] : 1, (p >= 1 && p <= d - 1) ? ind0[p + 1] : 1, 1});
     h->rng_k.assign(P, 0);
 
+    tr.lap("init_search+tables");
     // ---- initial cross fibers and factors (dmrgg.f90:220-248)
     KIND_SWITCH(h->kind, L(KC_INIT, [&] { k_init_cross<K><<<dim3(cdiv(h->nmax, TB), d), TB, smA, s>>>(D); }));
     L(KC_INIT, [&] { k_init_factors<<<dim3(cdiv(h->nmax, 256), d), 256, 0, s>>>(D); });
@@ -579,13 +720,12 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     for (int v = 0; v < P; ++v) maxnb = std::max(maxnb, h->own[v + 1] - h->own[v]);
     const int last_sweep = (maxrank > 0) ? maxrank - 1 : Rmax - 1;
     std::vector<double> pcol, prow, ubuf;
-    const size_t smL = smA + (size_t)(3 * Rmax + 8) * sizeof(int);
-    int it = 0;
+    int it = 0, cur_it = 0;
 
     auto visit_log_index = [&](int it_, int pp_, int v_) { return ((size_t)(it_ - 1) * maxnb + (pp_ - 1)) * P + v_; };
 
-    auto enqueue_visit = [&](int it_, int dir, int pp, int rb) -> int {
-        // rb: upper bound of every rank during sweep it_ (ranks grow by at most one per sweep)
+    auto enqueue_visit = [&](int dir, int pp, int rb) -> int {
+        // rb: upper bound of every rank during this sweep (ranks grow by at most one per sweep)
         int maxcol = rb * h->nmax, maxrow = rb * h->nmax, maxlot = 2 * rb + 2 * h->nmax;
         i64 maxsb = (i64)maxcol * maxrow;
         if (sync_mode) {
@@ -605,41 +745,35 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         const int Gc = std::min(GMAX, cdiv(maxcol, TB)), Gr = std::min(GMAX, cdiv(maxrow, TB));
         if (h->piv == -1) {
             const int Gs = (int)std::min<i64>(GMAX, std::max<i64>(1, (maxsb + TB - 1) / TB));
-            KIND_SWITCH(h->kind, L(KC_SUPERBLOCK, [&] { k_superblock<K, 0><<<dim3(Gs, P), TB, smA, s>>>(D, dir, pp, 0, 0, nullptr); }));
-            L(KC_REDUCE, [&] { k_superblock_reduce<<<dim3(1, P), 128, 0, s>>>(D, dir, pp, Gs, 0, 0, nullptr); });
+            KIND_SWITCH(h->kind, L(KC_SUPERBLOCK, [&] { k_superblock<K, 0><<<dim3(Gs, P), TB, smS, s>>>(D, dir, pp, 0, 0, nullptr, nullptr); }));
             KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, P), TB, smF, s>>>(D, dir, pp, 2); }));
             KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, P), TB, smF, s>>>(D, dir, pp, 2); }));
         } else {
             if (!dev_lot) CUDA_TRY(h, cudaMemcpyAsync(D.lot, h->lot_h, (size_t)P * 4 * h->nlotmax * sizeof(int), cudaMemcpyHostToDevice, s));
             const int Gl = std::min(GMAX, cdiv(maxlot, TB));
             KIND_SWITCH(h->kind, L(KC_LOT, [&] { k_lot<K><<<dim3(Gl, P), TB, smL, s>>>(D, dir, pp); }));
-            L(KC_REDUCE, [&] { k_lot_reduce<<<dim3(1, P), 128, 0, s>>>(D, dir, pp, Gl); });
             if (h->piv == 0) {
                 KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, P), TB, smF, s>>>(D, dir, pp, 1); }));
-                L(KC_REDUCE, [&] { k_fiber_reduce<0><<<dim3(1, P), 128, 0, s>>>(D, dir, pp, 1, Gc); });
                 KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, P), TB, smF, s>>>(D, dir, pp, 1); }));
-                L(KC_REDUCE, [&] { k_fiber_reduce<1><<<dim3(1, P), 128, 0, s>>>(D, dir, pp, 1, Gr); });
             } else {
                 // rook loop (dmrgg.f90:515-582): at most 2*piv fibers, alternating, starting with the row in '<<' sweeps
                 int isrow = (dir == 2) ? 1 : 0;
                 for (int c = 0; c < 2 * h->piv; ++c) {
-                    if (!isrow) {
-                        KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, P), TB, smF, s>>>(D, dir, pp, 0); }));
-                        L(KC_REDUCE, [&] { k_fiber_reduce<0><<<dim3(1, P), 128, 0, s>>>(D, dir, pp, 0, Gc); });
-                    } else {
-                        KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, P), TB, smF, s>>>(D, dir, pp, 0); }));
-                        L(KC_REDUCE, [&] { k_fiber_reduce<1><<<dim3(1, P), 128, 0, s>>>(D, dir, pp, 0, Gr); });
-                    }
+                    if (!isrow) { KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, P), TB, smF, s>>>(D, dir, pp, 0); })); }
+                    else        { KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, P), TB, smF, s>>>(D, dir, pp, 0); })); }
                     isrow ^= 1;
                 }
             }
         }
-        L(KC_ACCEPT, [&] { k_accept<<<dim3(1, P), 128, 0, s>>>(D, it_, dir, pp, small_element, small_pivot); });
+        L(KC_ACCEPT, [&] { k_accept<<<dim3(1, P), 128, 0, s>>>(D, dir, pp, small_element, small_pivot); });
+        // neighbour factors first (they read the old rank), then the rank-1 append whose last CTA bumps r(p)
+        if (maxnb > 1) {
+            if (h->use_wave) L(KC_NBR, [&] { k_update_nbr_w<<<dim3(cdiv(h->nmax, 8), P, 2), 256, h->sm_ext, s>>>(D, dir, pp); });
+            else L(KC_NBR, [&] { k_update_nbr<<<dim3(cdiv(2 * h->nmax, 64), P), 64, 0, s>>>(D, dir, pp); });
+        }
         L(KC_UPDATE, [&] { k_update_main<<<dim3(std::min(GMAX, cdiv(maxcol + maxrow, 256)), P), 256, 0, s>>>(D, dir, pp); });
-        L(KC_NBR, [&] { k_update_nbr<<<dim3(cdiv(2 * h->nmax, 64), P), 64, 0, s>>>(D, dir, pp); });
-        L(KC_MISC, [&] { k_end_visit<<<cdiv(P, 64), 64, 0, s>>>(D, dir, pp); });
         if (sync_mode) {
-            VisitOut* src = D.vlog + visit_log_index(it_, pp, 0);
+            VisitOut* src = D.vlog + visit_log_index(cur_it, pp, 0);
             CUDA_TRY(h, cudaMemcpyAsync(h->out_h, src, (size_t)P * sizeof(VisitOut), cudaMemcpyDeviceToHost, s));
             CUDA_TRY(h, cudaStreamSynchronize(s));
             for (int v = 0; v < P; ++v) {
@@ -650,28 +784,64 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         }
         return 0;
     };
-    auto enqueue_sweep = [&](int it_) -> int {
-        const int dir = 2 - it_ % 2;
-        const int rb = std::min(it_ + 1, Rmax);
-        L(KC_MISC, [&] { k_sweep_begin<<<cdiv(std::max(d + 1, P), 128), 128, 0, s>>>(D); });
+    auto enqueue_sweep = [&](int dir, int rb) -> int {
         if (sync_mode) h->rks_h = h->rk_h;
-        for (int pp = 1; pp <= maxnb; ++pp) { int e = enqueue_visit(it_, dir, pp, rb); if (e) return e; }
+        for (int pp = 1; pp <= maxnb; ++pp) { int e = enqueue_visit(dir, pp, rb); if (e) return e; }
         if (P > 1) {
             L(KC_EXCHANGE, [&] { k_allreduce<<<1, 32, 0, s>>>(D); });
             KIND_SWITCH(h->kind, L(KC_EXCHANGE, [&] { k_exchange_corner<K><<<dim3(1, P - 1), TB, smA, s>>>(D); }));
-            L(KC_EXCHANGE, [&] { k_exchange_extend<<<dim3(cdiv(2 * h->nmax, 64), P - 1), 64, 0, s>>>(D); });
+            if (h->use_wave) L(KC_EXCHANGE, [&] { k_exchange_extend_w<<<dim3(cdiv(h->nmax, 8), P - 1, 2), 256, h->sm_ext, s>>>(D); });
+            else L(KC_EXCHANGE, [&] { k_exchange_extend<<<dim3(cdiv(2 * h->nmax, 64), P - 1), 64, 0, s>>>(D); });
         }
-        L(KC_MISC, [&] { k_sweep_end<<<1, 32, 0, s>>>(D); });
         if (has_quad) launch_quad(h, L, true, true);
-        L(KC_MISC, [&] { k_sweep_log<<<1, 64, 0, s>>>(D, it_, maxrank); });
+        L(KC_MISC, [&] { k_sweep_log<<<1, 128, 0, s>>>(D, maxrank); });
         return 0;
     };
 
+    tr.lap("init_cross");
     *h->ready_h = 0;
+    // In asynchronous mode a sweep is a fixed kernel sequence (sweep number, seed and thresholds live in device memory),
+    // so it is captured once per direction into a CUDA graph and replayed: one graph launch per sweep instead of ~25
+    // kernel launches.  Grids are sized for the rank capacity; surplus CTAs exit at once.
+    const bool use_graph = !sync_mode && !h->profile && !h->no_graph;
+    if (use_graph) {
+        std::vector<long long> gsig = {(long long)h->piv, (long long)has_quad, (long long)maxrank, (long long)h->use_wave, (long long)dev_lot,
+                                       (long long)h->setup_serial};
+        if (gsig != h->graph_sig) {
+            for (int gdir = 0; gdir < 2; ++gdir) {
+                if (h->gexec[gdir]) { cudaGraphExecDestroy(h->gexec[gdir]); h->gexec[gdir] = nullptr; }
+                cudaGraph_t g = nullptr;
+                CUDA_TRY(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+                long long l0 = h->launches;
+                long long kc0[KC_COUNT];
+                std::copy(h->kc_launch, h->kc_launch + KC_COUNT, kc0);
+                int e = enqueue_sweep(gdir == 0 ? 1 : 2, Rmax);
+                h->graph_nodes[gdir] = h->launches - l0;
+                h->launches = l0;
+                for (int c = 0; c < KC_COUNT; ++c) { h->graph_kc[gdir][c] = h->kc_launch[c] - kc0[c]; h->kc_launch[c] = kc0[c]; }
+                cudaError_t ce = cudaStreamEndCapture(s, &g);
+                if (e) return e;
+                CUDA_TRY(h, ce);
+                CUDA_TRY(h, cudaGraphInstantiate(&h->gexec[gdir], g, 0));
+                cudaGraphDestroy(g);
+            }
+            h->graph_sig = gsig;
+        }
+    }
+    tr.lap("graph_capture");
     int enq = 0;
     for (it = 1; it <= last_sweep; ++it) {
         if (*(volatile int*)h->ready_h) break;          // device already reached its exit condition
-        int e = enqueue_sweep(it);
+        int e = 0;
+        if (use_graph) {
+            const int gdir = (it % 2 == 1) ? 0 : 1;     // graph 0: odd sweeps ('>>'), graph 1: even sweeps ('<<')
+            CUDA_TRY(h, cudaGraphLaunch(h->gexec[gdir], s));
+            h->launches += h->graph_nodes[gdir];
+            for (int c = 0; c < KC_COUNT; ++c) h->kc_launch[c] += h->graph_kc[gdir][c];
+        } else {
+            cur_it = it;
+            e = enqueue_sweep(2 - it % 2, std::min(it + 1, Rmax));
+        }
         if (e) return e;
         enq = it;
         CUDA_TRY(h, cudaMemcpyAsync(h->ready_h, &D.ctrl->ready, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -696,12 +866,18 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     (void)enq;
 
     // ---- finalise (dmrgg.f90:1028-1029); not gated by the ready flag
-    L(KC_FINAL, [&] { k_lua_r<<<dim3(cdiv((i64)h->nmax * Rmax, 128), d), 128, 0, s>>>(D); });
-    L(KC_FINAL, [&] { k_lua_l<<<dim3(cdiv((i64)h->nmax * Rmax, 128), d), 128, 0, s>>>(D); });
+    if (h->use_wave) {
+        L(KC_FINAL, [&] { k_lua_r_w<<<dim3(std::min(512, cdiv((i64)h->nmax * Rmax, 8)), d), 256, h->sm_ext, s>>>(D); });
+        L(KC_FINAL, [&] { k_lua_l_w<<<dim3(std::min(512, cdiv((i64)h->nmax * Rmax, 8)), d), 256, h->sm_ext, s>>>(D); });
+    } else {
+        L(KC_FINAL, [&] { k_lua_r<<<dim3(cdiv((i64)h->nmax * Rmax, 128), d), 128, 0, s>>>(D); });
+        L(KC_FINAL, [&] { k_lua_l<<<dim3(cdiv((i64)h->nmax * Rmax, 128), d), 128, 0, s>>>(D); });
+    }
     CUDA_TRY(h, cudaEventRecord(h->ev1, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     CUDA_TRY(h, cudaGetLastError());
 
+    tr.lap("sweeps+finalise");
     // ---- read the logs back and rebuild the reference's report
     Ctrl ctrl;
     CUDA_TRY(h, cudaMemcpy(&ctrl, D.ctrl, sizeof ctrl, cudaMemcpyDeviceToHost));
@@ -745,6 +921,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         CUDA_TRY(h, cudaMemcpy(rkf.data(), D.rk, (size_t)(d + 1) * sizeof(int), cudaMemcpyDeviceToHost));
         h->rk_h = rkf;
     }
+    tr.lap("logs");
     h->nsweeps = it;
     float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     h->device_ms = ms;
@@ -820,8 +997,10 @@ int ttc_set_seed(ttc_handle* h, unsigned long long seed) { if (!h) return TTC_ER
 int ttc_set_uniform_callback(ttc_handle* h, ttc_uniform_cb cb, void* ctx) { if (!h) return TTC_ERR_ARG; h->ucb = cb; h->ucb_ctx = ctx; return TTC_OK; }
 int ttc_set_verbose(ttc_handle* h, int v) { if (!h) return TTC_ERR_ARG; h->verbose = v; return TTC_OK; }
 int ttc_set_lottery_mode(ttc_handle* h, int mode) {
-    if (!h || mode < 0 || mode > 2) return TTC_ERR_ARG;
-    h->force_host_lottery = (mode == 1); h->force_sync = (mode >= 1);
+    if (!h || mode < 0 || mode > 3) return TTC_ERR_ARG;
+    h->force_host_lottery = (mode == 1); h->force_sync = (mode == 1 || mode == 2);
+    h->force_simple = (mode == 3);      // 3: the plain (non-wavefront) support kernels, asynchronous
+    h->setup_sig.clear();
     return TTC_OK;
 }
 int ttc_set_profile(ttc_handle* h, int on) { if (!h) return TTC_ERR_ARG; h->profile = on; return TTC_OK; }
@@ -843,16 +1022,33 @@ int ttc_core(ttc_handle* h, int k, double* out) {
     if (!h->ran) { h->err = "ttc_core before ttc_dmrgg"; return TTC_ERR_STATE; }
     CUDA_TRY(h, cudaSetDevice(h->device));
     size_t cnt = (size_t)h->rk_h[k - 1] * h->n[k] * h->rk_h[k];
-    if (cnt > h->pack_cap) {
-        if (h->pack_d) cudaFree(h->pack_d);
-        h->pack_d = nullptr; h->pack_cap = 0;
-        CUDA_TRY(h, cudaMalloc((void**)&h->pack_d, cnt * sizeof(double)));
-        h->pack_cap = cnt;
-    }
+    { int st = ensure_pack(h, cnt); if (st) return st; }
     k_pack_core<<<std::min(1024, cdiv((i64)cnt, 256)), 256, 0, h->stream>>>(h->plan, k, h->pack_d);
     h->launches += 1;
-    CUDA_TRY(h, cudaMemcpyAsync(out, h->pack_d, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->stage_h, h->pack_d, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    std::memcpy(out, h->stage_h, cnt * sizeof(double));
+    return TTC_OK;
+}
+// all cores at once, concatenated in core order (one gather pass, one pinned device-to-host copy)
+int ttc_cores(ttc_handle* h, double* out, long long cap) {
+    if (!h || !out) return TTC_ERR_ARG;
+    if (!h->ran) { h->err = "ttc_cores before ttc_dmrgg"; return TTC_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    size_t tot = 0;
+    for (int k = 1; k <= h->d; ++k) tot += (size_t)h->rk_h[k - 1] * h->n[k] * h->rk_h[k];
+    if ((long long)tot > cap) { h->err = "ttc_cores: output buffer too small"; return TTC_ERR_ARG; }
+    { int st = ensure_pack(h, tot); if (st) return st; }
+    size_t off = 0;
+    for (int k = 1; k <= h->d; ++k) {
+        size_t cnt = (size_t)h->rk_h[k - 1] * h->n[k] * h->rk_h[k];
+        k_pack_core<<<std::min(1024, cdiv((i64)cnt, 256)), 256, 0, h->stream>>>(h->plan, k, h->pack_d + off);
+        h->launches += 1;
+        off += cnt;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->stage_h, h->pack_d, tot * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    std::memcpy(out, h->stage_h, tot * sizeof(double));
     return TTC_OK;
 }
 long long ttc_neval(const ttc_handle* h) { return h ? h->neval : 0; }
@@ -977,8 +1173,8 @@ int ttc_superblock_probe(ttc_handle* h, int bond, int store, int reps, long long
     const int Gs = (int)std::min<i64>(GMAX, std::max<i64>(1, std::min<i64>((tot + TB - 1) / TB, (i64)h->nsm * (h->kind == TTC_MVN ? 8 : 6))));
     const size_t smA = aux_smem(h);
     auto launch = [&]() {
-        if (store) { KIND_SWITCH(h->kind, k_superblock<K, 1><<<Gs, TB, smA, s>>>(D, 1, 1, bond, 0, a_out)); }
-        else       { KIND_SWITCH(h->kind, k_superblock<K, 0><<<Gs, TB, smA, s>>>(D, 1, 1, bond, 0, nullptr)); }
+        if (store) { KIND_SWITCH(h->kind, k_superblock<K, 1><<<Gs, TB, h->sm_sb, s>>>(D, 1, 1, bond, 0, a_out, pout)); }
+        else       { KIND_SWITCH(h->kind, k_superblock<K, 0><<<Gs, TB, h->sm_sb, s>>>(D, 1, 1, bond, 0, nullptr, pout)); }
         h->launches += 1;
     };
     launch();   // warm-up
@@ -986,8 +1182,6 @@ int ttc_superblock_probe(ttc_handle* h, int bond, int store, int reps, long long
     cudaEventRecord(a, s);
     for (int r = 0; r < reps; ++r) launch();
     cudaEventRecord(b, s);
-    k_superblock_reduce<<<1, 128, 0, s>>>(D, 1, 1, Gs, bond, 0, pout);
-    h->launches += 1;
     Partial hp[2];
     cudaError_t e = cudaMemcpyAsync(hp, pout, sizeof hp, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
@@ -1010,7 +1204,7 @@ int ttc_fiber_probe(ttc_handle* h, int bond, int isrow, int ii, int jj, int kk, 
     int v = 0;
     while (v < h->P - 1 && bond >= h->own[v + 1]) ++v;
     const int pp = bond - h->own[v] + 1;
-    k_sweep_begin<<<cdiv(std::max(h->d + 1, h->P), 128), 128, 0, s>>>(D);   // rks := rk so every rank sees current sizes
+    CUDA_TRY(h, cudaMemcpyAsync(D.rks, D.rk, (size_t)(h->d + 1) * sizeof(int), cudaMemcpyDeviceToDevice, s));   // rks := rk
     VState S;
     CUDA_TRY(h, cudaMemcpyAsync(&S, D.st + v, sizeof S, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
@@ -1020,10 +1214,10 @@ int ttc_fiber_probe(ttc_handle* h, int bond, int isrow, int ii, int jj, int kk, 
     const int TB = threads_for(h);
     const int cnt = isrow ? h->n[bond + 1] * h->rk_h[bond + 1] : h->rk_h[bond - 1] * h->n[bond];
     const int G = std::min(GMAX, cdiv(cnt, TB));
-    const size_t smF = aux_smem(h) + (size_t)h->Rmax * sizeof(double);
+    const size_t smF = h->sm_fiber;
     // only virtual rank v must run: launch a 1-wide grid in y and shift the plan so blockIdx.y = 0 maps to v
     DevPlan Dv = D;
-    Dv.own = D.own + v; Dv.P = 1; Dv.st = D.st + v; Dv.part = D.part + (size_t)v * 2 * GMAX;
+    Dv.own = D.own + v; Dv.P = 1; Dv.st = D.st + v; Dv.part = D.part + (size_t)v * 2 * GMAX; Dv.tickets = D.tickets + v;
     Dv.acol1 = D.acol1 + (size_t)v * h->Rmax * h->nmax; Dv.bcol1 = D.bcol1 + (size_t)v * h->Rmax * h->nmax;
     Dv.arow1 = D.arow1 + (size_t)v * h->Rmax * h->nmax; Dv.brow1 = D.brow1 + (size_t)v * h->Rmax * h->nmax;
     auto launch = [&]() {
