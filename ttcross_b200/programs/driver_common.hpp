@@ -1,0 +1,83 @@
+// Shared pieces of the C++ twins of the reference driver programs (test_crs_ising.f90, test_crs_mvn.f90,
+// test_crs_stdnorm.f90): same positional CLI (readarg, lib/default.f90:40-78), same banner, same final lines.
+// The Fortran originals cannot be compiled in this image (no Fortran compiler); fortran/ holds the ISO_C_BINDING
+// versions for sites that have one.
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include <chrono>
+
+#include "../../include/ttcross_b200.h"
+
+namespace drv {
+
+inline int arg_i(int argc, char** argv, int pos, int def) { return (pos < argc && argv[pos][0]) ? std::atoi(argv[pos]) : def; }
+inline char arg_a(int argc, char** argv, int pos, char def) { return (pos < argc && argv[pos][0]) ? argv[pos][0] : def; }
+
+inline std::string fmt_e(double v, int w, int dgt) {
+    char buf[128];
+    std::string s;
+    if (v == 0.0) s = "0." + std::string(dgt, '0') + "E+00";
+    else {
+        std::snprintf(buf, sizeof buf, "%.*e", dgt - 1, std::fabs(v));
+        std::string t = buf;
+        size_t epos = t.find('e');
+        int ex = std::atoi(t.c_str() + epos + 1) + 1;
+        std::string digits;
+        for (size_t i = 0; i < epos; ++i) if (t[i] != '.') digits += t[i];
+        s = std::string(v < 0 ? "-" : "") + "0." + digits;
+        char eb[16];
+        if (std::abs(ex) < 100) std::snprintf(eb, sizeof eb, "E%c%02d", ex < 0 ? '-' : '+', std::abs(ex));
+        else std::snprintf(eb, sizeof eb, "%c%03d", ex < 0 ? '-' : '+', std::abs(ex));
+        s += eb;
+        if ((int)s.size() > w) { size_t z = (s[0] == '-') ? 1 : 0; if (s[z] == '0') s.erase(z, 1); }
+    }
+    if ((int)s.size() > w) s = std::string(w, '*');
+    if ((int)s.size() < w) s = std::string(w - s.size(), ' ') + s;
+    return s;
+}
+
+inline void banner_common(int n, int adj, int r, int piv, int nparts) {
+    if (adj == 0) std::printf("   quadratur:%10d\n", n); else std::printf("   quadratur:%10d (adjusted)\n", n);
+    std::printf("   TT ranks :%10d\n", r);
+    std::printf("   pivoting :%10d\n", piv);
+    std::printf("   MPI procs:%10d\n", nparts);          // virtual partitions take the place of MPI ranks
+    std::printf("   OMP thrds:%10d\n", 1);
+    std::printf("   sizeof(d):%10d\n", 64);
+    std::printf("   epsilon  :%s\n", fmt_e(2.220446049250313e-16, 10, 3).c_str());
+}
+
+inline void die(ttc_handle* h, int st, const char* what) {
+    std::fprintf(stderr, "%s failed (%d): %s\n", what, st, ttc_last_error(h));
+    std::exit(1);
+}
+
+// Runs the cross and prints the reference's closing lines.  rescale_pow >= 0 prints ' / (5**k)' like test_crs_ising.f90:160-161.
+inline int run_and_report(ttc_handle* h, int maxrank, double acc, int piv, double tru, bool has_tru, int rescale_pow) {
+    int nparts = std::getenv("TTC_PARTITIONS") ? std::atoi(std::getenv("TTC_PARTITIONS")) : 1;
+    if (nparts > 1) { int st = ttc_set_partition(h, nparts, nullptr); if (st) die(h, st, "ttc_set_partition"); }
+    if (std::getenv("TTC_SEED")) ttc_set_seed(h, std::strtoull(std::getenv("TTC_SEED"), nullptr, 10));
+    ttc_set_verbose(h, std::getenv("TTC_QUIET") ? 0 : 1);
+    auto t1 = std::chrono::steady_clock::now();
+    int st = ttc_dmrgg(h, maxrank, acc, piv);
+    if (st) { std::printf("%s\n", ttc_last_error(h)); return 1; }   // write(*,*) msg; stop
+    double tcrs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+    if (std::getenv("TTC_QUIET")) { std::vector<char> buf(ttc_text(h, nullptr, 0) + 1); ttc_text(h, buf.data(), (long)buf.size()); std::fputs(buf.data(), stdout); }
+    std::printf("...with%12lld evaluations completed in %s sec.\n", ttc_neval(h), fmt_e(tcrs, 12, 4).c_str());
+    double val = 0;
+    st = ttc_quad(h, &val);
+    if (st) die(h, st, "ttc_quad");
+    if (rescale_pow >= 0) std::printf("computed value:%s / (5**%4d)\n", fmt_e(val, 50, 40).c_str(), rescale_pow);
+    else std::printf("computed value:%s\n", fmt_e(val, 50, 40).c_str());
+    if (has_tru) {
+        std::printf("analytic value:%s\n", fmt_e(tru, 50, 40).c_str());
+        std::printf("correct digits:%7.2f\n", -std::log(std::fabs(1.0 - val / tru)) / std::log(10.0));
+    }
+    std::printf("Good bye.\n");
+    return 0;
+}
+
+}  // namespace drv
