@@ -148,7 +148,9 @@ def main():
     t = prob.make(device=local_rank)
     t.set_partition(PARTITIONS)
     if world > 1:
-        raise SystemExit("multi-GPU block partition is not wired into bench.py yet")
+        # the P = 8 core blocks are mapped block-wise onto the N ranks; the library's own NCCL communicator carries the
+        # per-sweep exchange (pivot tape + boundary fibers + quadrature chains); torch.distributed only hands over its id
+        T.multi.attach(t, dist)
     for _ in range(max(args.warmup, 3)):
         g = t.dmrgg(R, prob.accuracy, piv)
     launches0 = t.launch_count()
@@ -177,22 +179,40 @@ def main():
     h2d = prob.par.nbytes + prob.quad.nbytes + prob.n.nbytes
     d2h = 0
     for it in range(args.steps + 1):
+        barrier()
         t0 = time.perf_counter()
-        te = prob.make(device=local_rank)
-        te.set_partition(PARTITIONS)
+        if world == 1:
+            te = prob.make(device=local_rank)           # ttc_create + par/quad upload from host buffers
+            te.set_partition(PARTITIONS)
+        else:
+            te = t                                       # the communicator is set up once (like mpi_init); inputs travel every step
+            te.set_par(prob.par)
+            te.set_quad(prob.quad)
         ge = te.dmrgg(R, prob.accuracy, piv)
-        cores = te.cores()
+        cores = te.cores()                               # device -> host: every core this rank holds
         val = te.quad()
+        barrier()
         dt = time.perf_counter() - t0
         d2h = sum(c.nbytes for c in cores) + 8 + ge.pivlog.nbytes
-        te.close()
+        if world == 1:
+            te.close()
         if it > 0:
             e2e_t.append(dt)
-    e2e_val = g.neval / float(np.mean(e2e_t))
+    e2e_mean = float(np.mean(e2e_t))
+    if dist is not None:
+        import torch
+        x = torch.tensor([e2e_mean, float(d2h)], device="cuda", dtype=torch.float64)
+        y = x.clone()
+        dist.all_reduce(x, op=dist.ReduceOp.MAX)
+        dist.all_reduce(y, op=dist.ReduceOp.SUM)
+        e2e_mean = float(x[0].item())
+        d2h = int(y[1].item())                           # all ranks' copies
+        h2d *= world
+    e2e_val = g.neval / e2e_mean
     clocks = sampler.stop(local_rank)
 
     # ---- roofline of the dominant kernel: per-class device times from a profiled pass (events around every launch)
-    t.set_profile(True)
+    t.set_profile(True)                                  # collective like every ttc_dmrgg call when world > 1
     gp = t.dmrgg(R, prob.accuracy, piv)
     prof = t.profile()
     t.set_profile(False)
@@ -208,7 +228,7 @@ def main():
         r0, r1, r2 = int(ranks[p - 1]), int(ranks[p]), int(ranks[p + 1])
         per_bond.append(8.0 * (r0 * nn * r1 + 2 * r0 * nn))       # column fiber: col core + acol1 + bcol1
         per_bond.append(8.0 * (r1 * nn * r2 + 2 * nn * r2))       # row fiber
-    fiber_bytes = float(np.mean(per_bond)) * PARTITIONS
+    fiber_bytes = float(np.mean(per_bond)) * PARTITIONS / world       # partitions batched in one launch on this GPU
     fl, fms = prof["fiber_eval_residual"]
     fiber_avg_ms = fms / max(fl, 1)
     achieved = fiber_bytes / (fiber_avg_ms * 1e-3) / 1e9
@@ -221,11 +241,13 @@ def main():
         "metric": "integrand_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "test_crs_ising c 10 256 32 2", "partitions": PARTITIONS, "neval_per_step": int(g.neval),
+        "config": {"workload": "test_crs_ising c 10 256 32 2", "partitions": PARTITIONS,
+                   "partition_map": f"{PARTITIONS} core blocks block-mapped onto {world} GPU(s); per-sweep exchange over the library's NCCL communicator" if world > 1 else f"{PARTITIONS} core blocks batched on one GPU",
+                   "neval_per_step": int(g.neval),
                    "sweeps": int(g.nsweeps), "final_ranks": [int(x) for x in g.ranks], "l2": "flushed between timed steps (256 MiB write)",
                    "integral": float(g.vals[-1])},
         "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * float(np.mean(e2e_t))},
+                "ms_per_step": 1e3 * e2e_mean},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -234,7 +256,7 @@ def main():
     }
 
     # ---- superblock kernel (pivoting = -1 branch) at the workload's shape: the roofline-sized kernel of this path
-    if not args.no_superblock and rank == 0:
+    if not args.no_superblock and rank == 0 and world == 1:
         try:
             bond = prob.d // 2
             sb = t.superblock_probe(bond, store=False, reps=3)

@@ -59,6 +59,7 @@ const char* ttc_last_error(const ttc_handle* h);   /* h may be NULL: message of 
 /* ---- optional arguments of dtt_dmrgg (lib/dmrgg.f90:19-26) ------------------ */
 int ttc_set_device(ttc_handle* h, int cuda_device);                 /* default 0 */
 int ttc_set_partition(ttc_handle* h, int nparts, const int* own);   /* mybonds(0:nparts); own == NULL -> share() of lib/default.f90:80-97 */
+int ttc_set_par(ttc_handle* h, const double* par, long npar);       /* new parameter blob of the same length (next ttc_dmrgg uploads it) */
 int ttc_set_quad(ttc_handle* h, const double* quad);                /* quad=: rank-1 weights, n(1)+...+n(d) doubles; NULL removes */
 int ttc_set_tru(ttc_handle* h, int present, double tru);            /* tru=: only switches ' cnv ' to ' err ' in the sweep log */
 int ttc_set_seed(ttc_handle* h, unsigned long long seed);           /* uniform stream of the lottery (rnd.f90:120 is unseeded) */
@@ -127,10 +128,18 @@ int ttc_set_profile(ttc_handle* h, int on);
 int ttc_profile(const ttc_handle* h, int cap, const char** names, long long* launches, double* ms);
 
 /* ---- multi-GPU: one process per GPU, core blocks partitioned over ranks ------
- * The communicator id is an NCCL unique id (128 bytes) created on rank 0 and broadcast by the caller (e.g. through
- * torch.distributed or MPI_Bcast); virtual partitions [vfirst, vlast] of ttc_set_partition are mapped to this rank. */
+ * Replaces MPI_COMM_WORLD of the reference (lib/dmrgg.f90:86-95, 763-959, 1209-1246, 1355-1405).  The communicator id
+ * is an NCCL unique id (128 bytes) created on rank 0 by ttc_comm_unique_id and broadcast by the caller (MPI_Bcast in a
+ * Fortran/MPI driver, torch.distributed in bench.py).  The nparts partitions of ttc_set_partition (nparts >= nranks)
+ * are mapped block-wise onto the ranks: rank g runs partitions floor(nparts*g/nranks) .. floor(nparts*(g+1)/nranks)-1.
+ * Results (pivots, ranks, values) are a function of the partition, not of nranks.  After ttc_comm_init, ttc_dmrgg and
+ * ttc_quad are COLLECTIVE: every rank must call them with the same arguments.  Sweep log, ranks, pivot tape, neval
+ * and values are complete on every rank; cores are held by their owners only (like the reference, lib/dmrgg.f90:1248-1257):
+ * ttc_core_range gives the cores [first, last] of this rank. */
 int ttc_comm_unique_id(void* id128);
 int ttc_comm_init(ttc_handle* h, int nranks, int rank, const void* id128);
+int ttc_comm_rank(const ttc_handle* h, int* nranks, int* rank);
+int ttc_core_range(const ttc_handle* h, int* first, int* last);
 
 int ttc_version(void);
 

@@ -6,3 +6,4 @@ ctypes bindings (`api`) and the reference drivers' problem setup (`drivers`).  T
 """
 from .api import TTCross, TTCrossError, load_library, ISING, STDNORM, MVN  # noqa: F401
 from . import drivers  # noqa: F401
+from . import multi  # noqa: F401

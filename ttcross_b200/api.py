@@ -45,6 +45,7 @@ def load_library(build_if_missing: bool = True):
     L.ttc_last_error.argtypes = [vp]
     L.ttc_set_device.argtypes = [vp, C.c_int]
     L.ttc_set_partition.argtypes = [vp, C.c_int, _ip]
+    L.ttc_set_par.argtypes = [vp, _dp, C.c_long]
     L.ttc_set_quad.argtypes = [vp, _dp]
     L.ttc_set_tru.argtypes = [vp, C.c_int, C.c_double]
     L.ttc_set_seed.argtypes = [vp, C.c_ulonglong]
@@ -81,6 +82,8 @@ def load_library(build_if_missing: bool = True):
     L.ttc_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_longlong), _dp]
     L.ttc_comm_unique_id.argtypes = [C.c_void_p]
     L.ttc_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_void_p]
+    L.ttc_comm_rank.argtypes = [vp, _ip, _ip]
+    L.ttc_core_range.argtypes = [vp, _ip, _ip]
     L.ttc_version.restype = C.c_int
     _lib = L
     return L
@@ -153,6 +156,11 @@ class TTCross:
             a = np.ascontiguousarray(own, dtype=np.int32)
             self._check(self._L.ttc_set_partition(self.h, nparts, _i(a)))
 
+    def set_par(self, par):
+        a = np.ascontiguousarray(par, dtype=np.float64)
+        self._check(self._L.ttc_set_par(self.h, _d(a), a.size))
+        self._par = a
+
     def set_quad(self, quad):
         if quad is None:
             self._check(self._L.ttc_set_quad(self.h, None))
@@ -203,6 +211,25 @@ class TTCross:
         self._L.ttc_text(self.h, buf, ln + 1)
         return buf.value.decode()
 
+    # ---- several processes, one per GPU (replaces MPI_COMM_WORLD of the reference)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        L = load_library()
+        buf = C.create_string_buffer(128)
+        st = L.ttc_comm_unique_id(buf)
+        if st != 0:
+            raise TTCrossError(st, L.ttc_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes):
+        assert len(uid) == 128
+        self._check(self._L.ttc_comm_init(self.h, nranks, rank, C.c_char_p(uid)))
+
+    def core_range(self):
+        lo, hi = C.c_int(), C.c_int()
+        self._check(self._L.ttc_core_range(self.h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
     def core(self, k: int) -> np.ndarray:
         shp = (int(self.ranks[k - 1]), int(self.n[k - 1]), int(self.ranks[k]))
         a = np.zeros(shp, order="F")
@@ -210,11 +237,13 @@ class TTCross:
         return a
 
     def cores(self):
-        sizes = [int(self.ranks[k - 1]) * int(self.n[k - 1]) * int(self.ranks[k]) for k in range(1, self.d + 1)]
+        """The cores this rank holds (all of them on a single GPU), in core order."""
+        lo, hi = self.core_range()
+        sizes = [int(self.ranks[k - 1]) * int(self.n[k - 1]) * int(self.ranks[k]) for k in range(lo, hi + 1)]
         buf = np.empty(sum(sizes))
         self._check(self._L.ttc_cores(self.h, _d(buf), buf.size))
         out, off = [], 0
-        for k, sz in enumerate(sizes, start=1):
+        for k, sz in zip(range(lo, hi + 1), sizes):
             out.append(buf[off:off + sz].reshape((int(self.ranks[k - 1]), int(self.n[k - 1]), int(self.ranks[k])), order="F"))
             off += sz
         return out

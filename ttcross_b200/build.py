@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libttcross_b200.so")
-SOURCES = ["ttc_engine.cu", "ttc_comm.cu"]
+SOURCES = ["ttc_engine.cu"]
 NVCC = os.environ.get("TTC_NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -16,7 +16,7 @@ FLAGS = [
     "-fmad=false",                 # reference arithmetic has no FMA contraction
     "-Xcompiler", "-fPIC", "-shared",
     "-ccbin", "/usr/bin/g++",
-    "-cudart", "shared",
+    "-cudart", "shared", "-ldl",
 ]
 
 

@@ -98,7 +98,23 @@ struct DevPlan {
     VisitOut* vlog;        // [maxsweeps][maxnb][P]
     SweepOut* slog;        // [maxsweeps + 1]
     int* rklog;            // [maxsweeps + 1][d + 1]
+    // core blocks partitioned over processes (one process per GPU): this process runs virtual ranks v0 .. v0+nv-1 and
+    // contracts / finalises cores c_lo .. c_hi (the dtt_lua / dtt_quad ownership of dmrgg.f90:1209-1257).  Metadata
+    // (vip, Lidx, Ridx, rk, st) is replicated: foreign pivots are replayed from the all-gathered visit records.
+    int v0, nv, nproc, prank, vper, c_lo, c_hi;
+    unsigned long long* mb1_send; unsigned long long* mb1_recv;   // phase 1: per virtual rank [VisitOut x maxnb | VState]
+    double* mb2_send; double* mb2_recv;                           // phase 2: per virtual rank [chain Rmax^2 | amax | neval | error | pad]
+    double* nb_send_l; double* nb_recv_l;   // to/from the left neighbour process : send column slab [Rmax*nmax]; recv row [nmax*Rmax] | inv [Rmax^2]
+    double* nb_send_r; double* nb_recv_r;   // to/from the right neighbour process: send row | inv; recv column slab
 };
+__host__ __device__ __forceinline__ int proc_v0(int P, int nproc, int g) { return (int)((long long)P * g / nproc); }
+__device__ __forceinline__ bool own_vrank(const DevPlan& P, int v) { return v >= P.v0 && v < P.v0 + P.nv; }
+// boundaries b (between virtual ranks b and b+1) that touch this process's virtual ranks: first one, and how many
+__host__ __device__ __forceinline__ int first_boundary(const DevPlan& P) { return P.v0 > 0 ? P.v0 - 1 : 0; }
+__host__ __device__ __forceinline__ int boundary_count(const DevPlan& P) {
+    int last = P.v0 + P.nv - 1; if (last > P.P - 2) last = P.P - 2;
+    return last - first_boundary(P) + 1;
+}
 
 // ----------------------------------------------------------------------------
 // bond-visit geometry (dmrgg.f90:329-331 and the rr/r snapshot of :325)
@@ -563,7 +579,7 @@ __global__ void k_lot(DevPlan P, int dir, int pp) {
     if (P.ctrl->ready) return;
     extern __shared__ double smem[];
     __shared__ Partial shp[32];
-    const int v = blockIdx.y;
+    const int v = P.v0 + blockIdx.y;
     const Dims D = load_dims(P, v, dir, pp);
     if (!D.active) return;
     const double* A = stage_aux<KIND>(P, smem);
@@ -639,7 +655,7 @@ __global__ void k_fiber(DevPlan P, int dir, int pp, int mode) {
     if (P.ctrl->ready) return;
     extern __shared__ double smem[];
     __shared__ Partial shp[32];
-    const int v = blockIdx.y;
+    const int v = P.v0 + blockIdx.y;
     const Dims D = load_dims(P, v, dir, pp);
     if (!D.active) return;
     const VState& St0 = P.st[v];
@@ -714,7 +730,7 @@ template <int KIND, int STORE>
 __global__ void k_superblock(DevPlan P, int dir, int pp, int fixed_bond, int fixed_v, double* a_out, Partial* probe_out) {
     extern __shared__ double smem[];
     __shared__ Partial shp[32];
-    const int v = (fixed_bond > 0) ? fixed_v : blockIdx.y;
+    const int v = (fixed_bond > 0) ? fixed_v : P.v0 + blockIdx.y;
     Dims D;
     if (fixed_bond > 0) {
         D.active = 1; D.p = fixed_bond; D.r0 = P.rk[D.p - 1]; D.r1 = P.rk[D.p]; D.r2 = P.rk[D.p + 1];
@@ -769,7 +785,7 @@ __global__ void k_superblock(DevPlan P, int dir, int pp, int fixed_bond, int fix
 __global__ void k_accept(DevPlan P, int dir, int pp, double small_element, double small_pivot) {
     if (P.ctrl->ready) return;
     const int it = P.ctrl->it;
-    const int v = blockIdx.y;
+    const int v = P.v0 + blockIdx.y;
     const Dims D = load_dims(P, v, dir, pp);
     VisitOut& O = P.vlog[((i64)(it - 1) * P.maxnb + (pp - 1)) * P.P + v];
     if (!D.active) { if (threadIdx.x == 0) { O.active = 0; O.upd = 0; } return; }
@@ -821,7 +837,7 @@ __global__ void k_accept(DevPlan P, int dir, int pp, double small_element, doubl
 // ----------------------------------------------------------------------------
 __global__ void k_update_main(DevPlan P, int dir, int pp) {
     if (P.ctrl->ready) return;
-    const int v = blockIdx.y;
+    const int v = P.v0 + blockIdx.y;
     const Dims D = load_dims(P, v, dir, pp);
     if (!D.active) return;
     const VState& S = P.st[v];
@@ -864,7 +880,7 @@ __global__ void k_update_main(DevPlan P, int dir, int pp) {
 // through d2_lual(inv(p+1)).  One thread per mode index; the triangular recurrences are sequential by definition.
 __global__ void k_update_nbr(DevPlan P, int dir, int pp) {
     if (P.ctrl->ready) return;
-    const int v = blockIdx.y;
+    const int v = P.v0 + blockIdx.y;
     const Dims D = load_dims(P, v, dir, pp);
     if (!D.active) return;
     const VState& S = P.st[v];
@@ -985,7 +1001,7 @@ __global__ void k_exchange_corner(DevPlan P) {
     if (P.ctrl->ready) return;
     extern __shared__ double smem[];
     __shared__ Partial shp[32];
-    const int b = blockIdx.y;
+    const int b = first_boundary(P) + blockIdx.y;
     const int c = P.own[b + 1];
     const int rc1 = P.rk[c - 1], rc1s = P.rks[c - 1], rc = P.rk[c], rcs = P.rks[c];
     if (!(rc1 > rc1s && rc > rcs)) return;
@@ -1005,6 +1021,7 @@ __global__ void k_exchange_corner(DevPlan P) {
     if (threadIdx.x == 0) {
         // virtual rank b+1 is also touched by the CTA of boundary b+1: atomics (amax >= 0, so the bit pattern orders like the value)
         for (int v = b; v <= b + 1; ++v) {
+            if (!own_vrank(P, v)) continue;     // the other side of a process boundary evaluates (and counts) its own copy
             atomicMax((long long*)&P.st[v].amax, __double_as_longlong(best.absv));
             atomicAdd((unsigned long long*)&P.st[v].neval, (unsigned long long)nc);
         }
@@ -1012,14 +1029,14 @@ __global__ void k_exchange_corner(DevPlan P) {
 }
 __global__ void k_exchange_extend(DevPlan P) {
     if (P.ctrl->ready) return;
-    const int b = blockIdx.y;
+    const int b = first_boundary(P) + blockIdx.y;
     const int c = P.own[b + 1];
     const int rc1 = P.rk[c - 1], rc1s = P.rks[c - 1], rc = P.rk[c], rcs = P.rks[c];
     const int nc = P.n[c];
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const double* argc = P.arg + P.coreOff[c];
     if (e < nc) {
-        if (rc > rcs) {
+        if (rc > rcs && own_vrank(P, b)) {
             // LEFT receiver (virtual rank b): row(c)(:, k, rc) = d2_luar(n(c), rc1, inv(c-1)) of arg(c)(:, :, rc)
             const int k = e;
             const double* g = P.inv + (i64)(c - 1) * P.Rmax * P.Rmax;
@@ -1038,7 +1055,7 @@ __global__ void k_exchange_extend(DevPlan P) {
             }
         }
     } else if (e - nc < nc) {
-        if (rc1 > rc1s) {
+        if (rc1 > rc1s && own_vrank(P, b + 1)) {
             // RIGHT receiver (virtual rank b+1): col(c)(rc1, j, :) = d2_lual(n(c), rc, inv(c)) of arg(c)(rc1, :, :)
             const int j = e - nc;
             const double* g = P.inv + (i64)c * P.Rmax * P.Rmax;
@@ -1061,7 +1078,7 @@ __global__ void k_exchange_extend(DevPlan P) {
 // ----------------------------------------------------------------------------
 // ttqq(p)(i,k) = sum_j arg(p)(i,j,k) * w_p(j), accumulated from 0 in ascending j (dgemv 'n', beta = 0)
 __global__ void k_quad_contract(DevPlan P, int use_weights) {
-    const int p = blockIdx.y + 1;
+    const int p = P.c_lo + blockIdx.y;
     const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
     const double* a = P.arg + P.coreOff[p];
     const double* w = P.quadw + P.quadOff[p];
@@ -1079,7 +1096,7 @@ __global__ void k_quad_contract(DevPlan P, int use_weights) {
 // One CTA per core: d2_luar over columns (thread per column), then d2_lual over rows (thread per row).
 __global__ void k_quad_lua(DevPlan P) {
     if (P.ctrl->ready) return;
-    const int p = blockIdx.x + 1;
+    const int p = P.c_lo + blockIdx.x;
     const int r0 = P.rk[p - 1], r1 = P.rk[p];
     double* m = P.ttqq + (i64)p * P.Rmax * P.Rmax;
     const double* gl = P.inv + (i64)(p - 1) * P.Rmax * P.Rmax;
@@ -1119,7 +1136,7 @@ __device__ __forceinline__ void mat_mul(const double* A, int m, int kdim, const 
     }
 }
 __global__ void k_quad_chain(DevPlan P) {
-    const int v = blockIdx.x;
+    const int v = P.v0 + blockIdx.x;
     const int first = P.own[v];
     int last = P.own[v + 1] - 1;
     if (v == P.P - 1) last = P.d;
@@ -1164,7 +1181,7 @@ __global__ void k_quad_tree(DevPlan P) {
 
 // finalisation: dtt_lua on the real cores, in place (dmrgg.f90:1248-1257)
 __global__ void k_lua_r(DevPlan P) {   // d2_luar(n*r1, r0, inv(p-1)): thread per column (j,k)
-    const int p = blockIdx.y + 1;
+    const int p = P.c_lo + blockIdx.y;
     const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
     if (r0 < 2) return;
     const double* g = P.inv + (i64)(p - 1) * P.Rmax * P.Rmax;
@@ -1181,7 +1198,7 @@ __global__ void k_lua_r(DevPlan P) {   // d2_luar(n*r1, r0, inv(p-1)): thread pe
     }
 }
 __global__ void k_lua_l(DevPlan P) {   // d2_lual(r0*n, r1, inv(p)): thread per row (i,j); cores 1..d-1
-    const int p = blockIdx.y + 1;
+    const int p = P.c_lo + blockIdx.y;
     if (p >= P.d) return;
     const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
     const double* g = P.inv + (i64)p * P.Rmax * P.Rmax;
@@ -1313,7 +1330,7 @@ __device__ __forceinline__ void stage_lual(const double* g, int r, double* T, do
 // (deep memory-level parallelism), then r0 threads run the ordered sums out of shared memory.
 __global__ void k_quad_contract_sm(DevPlan P, int use_weights, int chunk_doubles) {
     extern __shared__ double smem[];
-    const int p = blockIdx.y + 1, k = blockIdx.x;
+    const int p = P.c_lo + blockIdx.y, k = blockIdx.x;
     const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
     if (k >= r1) return;
     const double* a = P.arg + P.coreOff[p] + (i64)P.Rmax * n * k;
@@ -1337,7 +1354,7 @@ __global__ void k_quad_contract_sm(DevPlan P, int use_weights, int chunk_doubles
 __global__ void k_quad_lua_sm(DevPlan P) {
     extern __shared__ double smem[];
     if (P.ctrl->ready) return;
-    const int p = blockIdx.x + 1;
+    const int p = P.c_lo + blockIdx.x;
     const int r0 = P.rk[p - 1], r1 = P.rk[p];
     double* M = smem;                          // r0 x r1, ld r0
     double* TL = M + r0 * r1;                  // luar table of inv(p-1), r0 x r0
@@ -1386,7 +1403,7 @@ __device__ __forceinline__ void mat_load_sm(const double* g, int m, int n, int l
 // chain product per virtual rank (dmrgg.f90:1323-1345): CTA v, three shared buffers of Rmax^2
 __global__ void k_quad_chain_sm(DevPlan P) {
     extern __shared__ double smem[];
-    const int v = blockIdx.x;
+    const int v = P.v0 + blockIdx.x;
     const int first = P.own[v];
     int last = P.own[v + 1] - 1;
     if (v == P.P - 1) last = P.d;
@@ -1472,7 +1489,7 @@ __device__ __forceinline__ void run_ext_lual(const ExtJob& J, double* sm) {
 __global__ void k_update_nbr_w(DevPlan P, int dir, int pp) {
     extern __shared__ double smem[];
     if (P.ctrl->ready) return;
-    const int v = blockIdx.y;
+    const int v = P.v0 + blockIdx.y;
     const Dims D = load_dims(P, v, dir, pp);
     if (!D.active || !P.st[v].upd) return;
     const int lo = P.own[v], hi = P.own[v + 1], t = D.r1;
@@ -1496,20 +1513,20 @@ __global__ void k_update_nbr_w(DevPlan P, int dir, int pp) {
 __global__ void k_exchange_extend_w(DevPlan P) {
     extern __shared__ double smem[];
     if (P.ctrl->ready) return;
-    const int b = blockIdx.y;
+    const int b = first_boundary(P) + blockIdx.y;
     const int c = P.own[b + 1];
     const int rc1 = P.rk[c - 1], rc1s = P.rks[c - 1], rc = P.rk[c], rcs = P.rks[c];
     const int nc = P.n[c];
     const double* argc = P.arg + P.coreOff[c];
     if (blockIdx.z == 0) {
-        if (!(rc > rcs)) return;
+        if (!(rc > rcs) || !own_vrank(P, b)) return;
         ExtJob J;   // LEFT receiver: chains k, elements s < rc1: src arg(c)(s,k,rc), dst rowT(c)(s,k,rc)
         J.g = P.inv + (i64)(c - 1) * P.Rmax * P.Rmax; J.r = rc1; J.count = nc;
         J.src = argc + (i64)P.Rmax * nc * (rc - 1); J.src_chain = P.Rmax; J.src_elem = 1;
         J.dst = P.rowT + P.coreOff[c] + (i64)nc * (rc - 1); J.dst_chain = 1; J.dst_elem = (i64)nc * P.Rmax;
         run_ext_luar(J, smem);
     } else {
-        if (!(rc1 > rc1s)) return;
+        if (!(rc1 > rc1s) || !own_vrank(P, b + 1)) return;
         ExtJob J;   // RIGHT receiver: chains j, elements cc < rc: src arg(c)(rc1,j,cc), dst col(c)(rc1,j,cc)
         J.g = P.inv + (i64)c * P.Rmax * P.Rmax; J.r = rc; J.count = nc;
         J.src = argc + (rc1 - 1); J.src_chain = P.Rmax; J.src_elem = (i64)P.Rmax * nc;
@@ -1520,7 +1537,7 @@ __global__ void k_exchange_extend_w(DevPlan P) {
 // finalisation with wavefronts: d2_luar over the n*r1 columns, then d2_lual over the r0*n rows of every core
 __global__ void k_lua_r_w(DevPlan P) {
     extern __shared__ double smem[];
-    const int p = blockIdx.y + 1;
+    const int p = P.c_lo + blockIdx.y;
     const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
     if (r0 < 2) return;
     ExtJob J;
@@ -1531,7 +1548,7 @@ __global__ void k_lua_r_w(DevPlan P) {
 }
 __global__ void k_lua_l_w(DevPlan P) {
     extern __shared__ double smem[];
-    const int p = blockIdx.y + 1;
+    const int p = P.c_lo + blockIdx.y;
     if (p >= P.d) return;
     const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
     // chains are the rows (i,j): x = i + r0*j lives at i + Rmax*j -> two-level stride; run per j with chain index i
@@ -1575,6 +1592,145 @@ __global__ void k_init_factors(DevPlan P) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         P.inv[(i64)p * P.Rmax * P.Rmax] = pivot;
         if (p == 1) P.inv[0] = 1.0;
+    }
+}
+
+// =============================================================================
+// Core blocks over several processes (one per GPU).  The reference moves, after every sweep, the pivot tape
+// (dmrgg.f90:763-850), three scalars (:852-870) and the new column / row of every shared core
+// (:872-958, dmrggmp.f90:572-629) between MPI ranks, and dtt_lua hands inv(last bond) to the right (:1209-1246).
+// Here every process packs (1) the visit records + scalar state of its virtual ranks into an all-gather mailbox and
+// (2) the boundary slabs for its two neighbour processes; NCCL moves them (ttc_engine.cu); the kernels below replay
+// the foreign pivots into the replicated index tables and drop the slabs into place.  After that the single-process
+// exchange kernels (corner, factor extension) run unchanged on the boundaries this process touches.
+// =============================================================================
+constexpr int VO_WORDS = sizeof(VisitOut) / 8, VS_WORDS = sizeof(VState) / 8;
+__host__ __device__ __forceinline__ int mb1_slot_words(int maxnb) { return maxnb * VO_WORDS + VS_WORDS; }
+__host__ __device__ __forceinline__ int mb2_slot_doubles(int Rmax) { return Rmax * Rmax + 4; }
+
+// grid: nv + 2 CTAs.  CTA b < nv: mailbox slot of virtual rank v0+b.  CTA nv: slab for the left process.  CTA nv+1: right.
+__global__ void k_mp_pack1(DevPlan P) {
+    if (P.ctrl->ready) return;
+    const int it = P.ctrl->it;
+    const int b = blockIdx.x;
+    if (b < P.nv) {
+        const int v = P.v0 + b;
+        unsigned long long* slot = P.mb1_send + (i64)b * mb1_slot_words(P.maxnb);
+        for (int x = threadIdx.x; x < P.maxnb * VO_WORDS; x += blockDim.x) {
+            const int pp = x / VO_WORDS, w = x - pp * VO_WORDS;
+            slot[x] = ((const unsigned long long*)&P.vlog[((i64)(it - 1) * P.maxnb + pp) * P.P + v])[w];
+        }
+        for (int x = threadIdx.x; x < VS_WORDS; x += blockDim.x)
+            slot[P.maxnb * VO_WORDS + x] = ((const unsigned long long*)&P.st[v])[x];
+    } else if (b == P.nv) {
+        if (P.v0 == 0) return;
+        const int c = P.own[P.v0];                       // shared with the left process; our bond c
+        if (!(P.rk[c] > P.rks[c])) return;
+        const int n = P.n[c];
+        const double* slab = P.arg + P.coreOff[c] + (i64)P.Rmax * n * P.rks[c];   // new slice, contiguous
+        for (int x = threadIdx.x; x < P.Rmax * n; x += blockDim.x) P.nb_send_l[x] = slab[x];
+    } else {
+        if (P.v0 + P.nv >= P.P) return;
+        const int c = P.own[P.v0 + P.nv];                // shared with the right process; our bond c-1
+        const int n = P.n[c];
+        const double* g = P.inv + (i64)(c - 1) * P.Rmax * P.Rmax;
+        double* ginv = P.nb_send_r + (i64)P.nmax * P.Rmax;
+        for (int x = threadIdx.x; x < P.Rmax * P.Rmax; x += blockDim.x) ginv[x] = g[x];
+        if (!(P.rk[c - 1] > P.rks[c - 1])) return;
+        const double* a = P.arg + P.coreOff[c] + P.rks[c - 1];                    // new row t, stride Rmax
+        for (int x = threadIdx.x; x < n * P.Rmax; x += blockDim.x) P.nb_send_r[x] = a[(i64)P.Rmax * x];
+    }
+}
+// grid: P CTAs, CTA v handles foreign virtual rank v: state + visit records, then the replay of its accepted pivots
+// (the index-set half of k_accept) in visit order.
+__global__ void k_mp_unpack1(DevPlan P) {
+    if (P.ctrl->ready) return;
+    const int v = blockIdx.x;
+    if (own_vrank(P, v)) return;
+    const int it = P.ctrl->it;
+    int g = 0;
+    while (g + 1 < P.nproc && proc_v0(P.P, P.nproc, g + 1) <= v) ++g;
+    const unsigned long long* slot = P.mb1_recv + ((i64)g * P.vper + (v - proc_v0(P.P, P.nproc, g))) * mb1_slot_words(P.maxnb);
+    for (int x = threadIdx.x; x < P.maxnb * VO_WORDS; x += blockDim.x) {
+        const int pp = x / VO_WORDS, w = x - pp * VO_WORDS;
+        ((unsigned long long*)&P.vlog[((i64)(it - 1) * P.maxnb + pp) * P.P + v])[w] = slot[x];
+    }
+    for (int x = threadIdx.x; x < VS_WORDS; x += blockDim.x) ((unsigned long long*)&P.st[v])[x] = slot[P.maxnb * VO_WORDS + x];
+    __syncthreads();
+    for (int pp = 0; pp < P.maxnb; ++pp) {
+        const VisitOut& O = P.vlog[((i64)(it - 1) * P.maxnb + pp) * P.P + v];
+        if (!(O.active && O.upd)) continue;               // uniform over the CTA
+        const int p = O.bond, t = P.rk[p];
+        if (t >= P.Rmax) { if (threadIdx.x == 0) P.ctrl->error = 1; continue; }
+        const int ii = O.ii, jj = O.jj, kk = O.kk, qq = O.qq;
+        if (threadIdx.x == 0) { int* vp = P.vip + ((i64)p * P.Rmax + t) * 4; vp[0] = ii; vp[1] = jj; vp[2] = kk; vp[3] = qq; }
+        int* Lp = P.Lidx + P.offL[p];
+        const int* Lm = P.Lidx + P.offL[p - 1];
+        for (int pos = threadIdx.x; pos < p; pos += blockDim.x)
+            Lp[(i64)pos * P.Rmax + t] = (pos < p - 1) ? Lm[(i64)pos * P.Rmax + (ii - 1)] : jj;
+        int* Rp = P.Ridx + P.offR[p];
+        const int* Rn = P.Ridx + P.offR[p + 1];
+        for (int pos = threadIdx.x; pos < P.d - p; pos += blockDim.x)
+            Rp[(i64)pos * P.Rmax + t] = (pos == 0) ? kk : Rn[(i64)(pos - 1) * P.Rmax + (qq - 1)];
+        __syncthreads();
+        if (threadIdx.x == 0) P.rk[p] = t + 1;
+        __syncthreads();
+    }
+}
+// grid: (NB, 2).  y = 0: what the left process sent (new row of core own[v0] + inv of its last bond);
+// y = 1: what the right process sent (new column slab of core own[v0+nv]).  Runs after k_mp_unpack1 (ranks replayed).
+__global__ void k_mp_unpack1b(DevPlan P) {
+    if (P.ctrl->ready) return;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if (blockIdx.y == 0) {
+        if (P.v0 == 0) return;
+        const int c = P.own[P.v0];
+        double* g = P.inv + (i64)(c - 1) * P.Rmax * P.Rmax;
+        const double* ginv = P.nb_recv_l + (i64)P.nmax * P.Rmax;
+        for (int x = tid; x < P.Rmax * P.Rmax; x += nth) g[x] = ginv[x];
+        if (!(P.rk[c - 1] > P.rks[c - 1])) return;
+        const int n = P.n[c], t = P.rks[c - 1], rq = P.rks[c];       // the sender saw bond c at its sweep-start rank
+        double* a = P.arg + P.coreOff[c] + t;
+        for (int x = tid; x < n * rq; x += nth) a[(i64)P.Rmax * x] = P.nb_recv_l[x];
+    } else {
+        if (P.v0 + P.nv >= P.P) return;
+        const int c = P.own[P.v0 + P.nv];
+        if (!(P.rk[c] > P.rks[c])) return;
+        const int n = P.n[c], ri = P.rks[c - 1];                      // the sender saw bond c-1 at its sweep-start rank
+        double* slab = P.arg + P.coreOff[c] + (i64)P.Rmax * n * P.rks[c];
+        for (int x = tid; x < P.Rmax * n; x += nth) { if (x % P.Rmax < ri) slab[x] = P.nb_recv_r[x]; }
+    }
+}
+// phase 2 (after the corner evaluations and the per-rank quadrature chains): chain products, amax, neval, error flag
+// final != 0: the collective ttc_quad after the run (not gated by the ready flag; only the chain products travel)
+__global__ void k_mp_pack2(DevPlan P, int final) {
+    if (!final && P.ctrl->ready) return;
+    const int b = blockIdx.x, v = P.v0 + b;
+    const int msz = P.Rmax * P.Rmax;
+    double* slot = P.mb2_send + (i64)b * mb2_slot_doubles(P.Rmax);
+    const double* ch = P.chain + (i64)v * msz;
+    for (int x = threadIdx.x; x < msz; x += blockDim.x) slot[x] = ch[x];
+    if (threadIdx.x == 0) {
+        slot[msz] = P.st[v].amax;
+        slot[msz + 1] = __longlong_as_double(P.st[v].neval);
+        slot[msz + 2] = __longlong_as_double((long long)P.ctrl->error);
+        slot[msz + 3] = 0.0;
+    }
+}
+__global__ void k_mp_unpack2(DevPlan P, int final) {
+    if (!final && P.ctrl->ready) return;
+    const int v = blockIdx.x;
+    if (own_vrank(P, v)) return;
+    int g = 0;
+    while (g + 1 < P.nproc && proc_v0(P.P, P.nproc, g + 1) <= v) ++g;
+    const int msz = P.Rmax * P.Rmax;
+    const double* slot = P.mb2_recv + ((i64)g * P.vper + (v - proc_v0(P.P, P.nproc, g))) * mb2_slot_doubles(P.Rmax);
+    double* ch = P.chain + (i64)v * msz;
+    for (int x = threadIdx.x; x < msz; x += blockDim.x) ch[x] = slot[x];
+    if (threadIdx.x == 0 && !final) {
+        P.st[v].amax = slot[msz];
+        P.st[v].neval = __double_as_longlong(slot[msz + 1]);
+        if (__double_as_longlong(slot[msz + 2]) != 0) P.ctrl->error = 1;
     }
 }
 

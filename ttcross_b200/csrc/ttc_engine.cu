@@ -12,6 +12,7 @@
 // =============================================================================
 #include "../../include/ttcross_b200.h"
 #include "ttc_device.cuh"
+#include "ttc_nccl.hpp"
 
 #include <algorithm>
 #include <array>
@@ -97,6 +98,7 @@ struct ttc_handle {
     std::vector<int> n;                 // 1..d (n[0] = n[d+1] = 1)
     std::vector<double> par, aux, quad; // quad concatenated, empty = absent
     bool has_tru = false; double tru = 0;
+    bool par_dirty = false;
     int P = 1; std::vector<int> own; bool own_given = false;
     u64 seed = 1; ttc_uniform_cb ucb = nullptr; void* ucb_ctx = nullptr;
     int verbose = 0, device = 0, profile = 0;
@@ -129,6 +131,9 @@ struct ttc_handle {
     size_t sm_contract = 0, sm_lua = 0, sm_mat3 = 0, sm_ext = 0, sm_lot = 0, sm_fiber = 0, sm_sb = 0;
     int force_sync = 0, force_host_lottery = 0, force_simple = 0;
     int nsm = 148;
+    // core blocks over processes (one per GPU): NCCL communicator of ttc_comm_init, this process's rank
+    NcclComm comm = nullptr; int nproc = 1, prank = 0;
+    size_t mb1_bytes = 0, mb2_count = 0, nbl_send = 0, nbl_recv = 0;   // message sizes per process / neighbour
 
     std::vector<int> setup_sig;
     std::vector<double> quad_or_ones() const {
@@ -151,6 +156,14 @@ namespace {
 
 std::string g_create_err;
 
+#define NCCL_TRY(h, call)                                                                                   \
+    do {                                                                                                    \
+        int e_ = (call);                                                                                    \
+        if (e_ != 0) {                                                                                      \
+            (h)->err = std::string("NCCL error: ") + nccl_api().GetErrorString(e_) + " at " #call;          \
+            return TTC_ERR_COMM;                                                                            \
+        }                                                                                                   \
+    } while (0)
 #define CUDA_TRY(h, call)                                                                                   \
     do {                                                                                                    \
         cudaError_t e_ = (call);                                                                            \
@@ -311,18 +324,23 @@ int check_device(ttc_handle* h) {
 int setup_device(ttc_handle* h, int maxrank) {
     // device buffers are kept between runs of the same shape (nothing needs re-zeroing: every slice is written
     // before it is read), so a repeated ttc_dmrgg does not pay cudaMalloc again
-    std::vector<int> sig = {h->d, h->P, maxrank > 0 ? maxrank : 64, h->kind, h->device};
+    std::vector<int> sig = {h->d, h->P, maxrank > 0 ? maxrank : 64, h->kind, h->device, h->nproc, h->prank};
     sig.insert(sig.end(), h->own.begin(), h->own.end());
     if (h->stream && sig == h->setup_sig) {
         int st0 = check_device(h);
         if (st0) return st0;
         h->plan.piv = h->piv;
+        if (h->par_dirty) {
+            CUDA_TRY(h, cudaMemcpyAsync(const_cast<double*>(h->plan.par), h->par.data(), h->par.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            h->par_dirty = false;
+        }
         CUDA_TRY(h, cudaMemcpyAsync(const_cast<double*>(h->plan.quadw), h->quad_or_ones().data(), h->quad_or_ones().size() * sizeof(double),
                                     cudaMemcpyHostToDevice, h->stream));
         return 0;
     }
     free_device(h);
     h->setup_sig = sig;
+    h->par_dirty = false;
     h->setup_serial += 1;
     int st = check_device(h);
     if (st) return st;
@@ -340,6 +358,12 @@ int setup_device(ttc_handle* h, int maxrank) {
     std::memset(&D, 0, sizeof D);
     D.d = d; D.P = P; D.Rmax = Rmax; D.nmax = h->nmax; D.piv = h->piv; D.kind = h->kind; D.ising_id = h->ising_id;
     D.nlotmax = h->nlotmax;
+    D.nproc = h->nproc; D.prank = h->prank;
+    D.v0 = proc_v0(P, h->nproc, h->prank); D.nv = proc_v0(P, h->nproc, h->prank + 1) - D.v0;
+    D.vper = 0;
+    for (int g = 0; g < h->nproc; ++g) D.vper = std::max(D.vper, proc_v0(P, h->nproc, g + 1) - proc_v0(P, h->nproc, g));
+    D.c_lo = h->own[D.v0];
+    D.c_hi = (D.v0 + D.nv == P) ? d : h->own[D.v0 + D.nv] - 1;
     D.auxsm = 0;
     if (h->kind == TTC_MVN) {
         size_t need = (size_t)d * d * sizeof(double) + (size_t)Rmax * sizeof(double);
@@ -434,6 +458,18 @@ int setup_device(ttc_handle* h, int maxrank) {
         D.ctrl = dctrl; D.vlog = dvlog; D.slog = dslog; D.rklog = drklog;
         unsigned int* dtick; s1 = dev_alloc(h, &dtick, (size_t)P + 1); if (s1) return s1;
         D.tickets = dtick;
+        if (h->nproc > 1) {
+            const size_t w1 = (size_t)mb1_slot_words(maxnb0) * D.vper, w2 = (size_t)mb2_slot_doubles(Rmax) * D.vper;
+            const size_t slab = (size_t)Rmax * h->nmax, rowinv = slab + (size_t)Rmax * Rmax;
+            unsigned long long *s1, *r1; double *s2, *r2, *sl, *rl, *sr, *rr;
+            s1 = nullptr; r1 = nullptr; s2 = r2 = sl = rl = sr = rr = nullptr;
+            if ((s1 = nullptr, dev_alloc(h, &s1, w1)) || dev_alloc(h, &r1, w1 * h->nproc) || dev_alloc(h, &s2, w2) ||
+                dev_alloc(h, &r2, w2 * h->nproc) || dev_alloc(h, &sl, slab) || dev_alloc(h, &rl, rowinv) ||
+                dev_alloc(h, &sr, rowinv) || dev_alloc(h, &rr, slab)) return TTC_ERR_CUDA;
+            D.mb1_send = s1; D.mb1_recv = r1; D.mb2_send = s2; D.mb2_recv = r2;
+            D.nb_send_l = sl; D.nb_recv_l = rl; D.nb_send_r = sr; D.nb_recv_r = rr;
+            h->mb1_bytes = w1 * 8; h->mb2_count = w2; h->nbl_send = slab; h->nbl_recv = rowinv;
+        }
     }
 
     {
@@ -516,21 +552,65 @@ void host_dims(const ttc_handle* h, int v, int dir, int pp, int& active, int& p,
     r2 = (p + 1 <= hi - 1) ? h->rk_h[p + 1] : h->rks_h[p + 1];
 }
 
-// quadrature of the current cores -> sweep_out->val.  with_lua: the per-sweep path of dmrgg.f90:975-993
-int launch_quad(ttc_handle* h, Launcher& L, bool with_lua, bool use_weights) {
+// ----------------------------------------------------------------------------
+// exchange between processes (one per GPU) after a sweep.  Phase 1 replaces the tape chains, the MAX allreduce inputs
+// and the LEFT/RIGHT block share of the reference (dmrgg.f90:763-958, dmrggmp.f90:572-629) plus dtt_lua's inv hand-off
+// (:1209-1246): ONE NCCL group = an all-gather of the per-virtual-rank mailboxes + a send/recv pair per neighbour.
+// Phase 2 (after the corner evaluations and the per-rank quadrature chains) all-gathers chain products, amax, neval.
+// Message sizes are capacity-sized (the ranks live on the device; the host never waits for them).
+// ----------------------------------------------------------------------------
+int mp_phase1(ttc_handle* h, Launcher& L) {
+    const DevPlan& D = h->plan;
+    cudaStream_t s = h->stream;
+    NcclApi& N = nccl_api();
+    L(KC_EXCHANGE, [&] { k_mp_pack1<<<D.nv + 2, 256, 0, s>>>(D); });
+    NCCL_TRY(h, N.GroupStart());
+    int e = N.AllGather(D.mb1_send, D.mb1_recv, h->mb1_bytes, NCCL_INT8, h->comm, s);
+    if (!e && h->prank > 0) {
+        e = N.Send(D.nb_send_l, h->nbl_send, NCCL_FLOAT64, h->prank - 1, h->comm, s);
+        if (!e) e = N.Recv(D.nb_recv_l, h->nbl_recv, NCCL_FLOAT64, h->prank - 1, h->comm, s);
+    }
+    if (!e && h->prank < h->nproc - 1) {
+        e = N.Send(D.nb_send_r, h->nbl_recv, NCCL_FLOAT64, h->prank + 1, h->comm, s);
+        if (!e) e = N.Recv(D.nb_recv_r, h->nbl_send, NCCL_FLOAT64, h->prank + 1, h->comm, s);
+    }
+    int e2 = N.GroupEnd();
+    NCCL_TRY(h, e);
+    NCCL_TRY(h, e2);
+    L(KC_EXCHANGE, [&] { k_mp_unpack1<<<D.P, 128, 0, s>>>(D); });
+    L(KC_EXCHANGE, [&] { k_mp_unpack1b<<<dim3(8, 2), 256, 0, s>>>(D); });
+    return 0;
+}
+int mp_phase2(ttc_handle* h, Launcher& L, int final) {
+    const DevPlan& D = h->plan;
+    cudaStream_t s = h->stream;
+    NcclApi& N = nccl_api();
+    L(KC_EXCHANGE, [&] { k_mp_pack2<<<D.nv, 256, 0, s>>>(D, final); });
+    NCCL_TRY(h, N.AllGather(D.mb2_send, D.mb2_recv, h->mb2_count, NCCL_FLOAT64, h->comm, s));
+    L(KC_EXCHANGE, [&] { k_mp_unpack2<<<D.P, 256, 0, s>>>(D, final); });
+    return 0;
+}
+
+// quadrature of the current cores -> sweep_out->val.  with_lua: the per-sweep path of dmrgg.f90:975-993.
+// Several processes: each contracts its own cores and chains its own virtual ranks; the chain products are
+// all-gathered (phase 2) and every process runs the reference's binary tree (dmrgg.f90:1355-1405) on all of them.
+int launch_quad(ttc_handle* h, Launcher& L, bool with_lua, bool use_weights, int final = 0) {
     const DevPlan& D = h->plan;
     cudaStream_t s = h->stream;
     const int R = h->Rmax;
+    const int ncore = D.c_hi - D.c_lo + 1;
     if (!h->use_wave) {
-        L(KC_QUAD, [&] { k_quad_contract<<<dim3(cdiv((i64)R * R, 256), h->d), 256, 0, s>>>(D, use_weights ? 1 : 0); });
-        if (with_lua) L(KC_QUAD, [&] { k_quad_lua<<<h->d, 128, 0, s>>>(D); });
-        L(KC_QUAD, [&] { k_quad_chain<<<h->P, 256, 0, s>>>(D); });
+        L(KC_QUAD, [&] { k_quad_contract<<<dim3(cdiv((i64)R * R, 256), ncore), 256, 0, s>>>(D, use_weights ? 1 : 0); });
+        if (with_lua) L(KC_QUAD, [&] { k_quad_lua<<<ncore, 128, 0, s>>>(D); });
+        L(KC_QUAD, [&] { k_quad_chain<<<D.nv, 256, 0, s>>>(D); });
+        if (h->nproc > 1) { int e = mp_phase2(h, L, final); if (e) return e; }
         L(KC_QUAD, [&] { k_quad_tree<<<1, 256, 0, s>>>(D); });
         return 0;
     }
-    L(KC_QUAD, [&] { k_quad_contract_sm<<<dim3(R, h->d), 256, h->sm_contract, s>>>(D, use_weights ? 1 : 0, (int)(h->sm_contract / sizeof(double))); });
-    if (with_lua) L(KC_QUAD, [&] { k_quad_lua_sm<<<h->d, 512, h->sm_lua, s>>>(D); });
-    L(KC_QUAD, [&] { k_quad_chain_sm<<<h->P, 512, h->sm_mat3, s>>>(D); });
+    L(KC_QUAD, [&] { k_quad_contract_sm<<<dim3(R, ncore), 256, h->sm_contract, s>>>(D, use_weights ? 1 : 0, (int)(h->sm_contract / sizeof(double))); });
+    if (with_lua) L(KC_QUAD, [&] { k_quad_lua_sm<<<ncore, 512, h->sm_lua, s>>>(D); });
+    L(KC_QUAD, [&] { k_quad_chain_sm<<<D.nv, 512, h->sm_mat3, s>>>(D); });
+    if (h->nproc > 1) { int e = mp_phase2(h, L, final); if (e) return e; }
     for (int q = 1; q < h->P; q *= 2) {
         const int last = (2 * q >= h->P) ? 1 : 0;
         L(KC_QUAD, [&] { k_quad_tree_sm<<<cdiv(h->P, 2 * q), 512, h->sm_mat3, s>>>(D, q, last); });
@@ -568,6 +648,8 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     if (!h->own_given) { h->own.assign(h->P + 1, 0); ttc_share(l, m - 1, h->P, h->own.data()); }
     for (int v = 0; v < h->P; ++v)
         if (h->own[v + 1] < h->own[v] || h->own[0] != 1 || h->own[h->P] != m) { h->err = "bad partition"; return TTC_ERR_ARG; }
+    if (h->nproc > h->P) { h->err = "more processes than partitions: call ttc_set_partition with nparts >= the communicator size"; return TTC_ERR_ARG; }
+    if (h->nproc > 1 && h->ucb) { h->err = "a uniform callback needs the host lottery, which the multi-process sweep does not support"; return TTC_ERR_ARG; }
     int st = setup_device(h, maxrank);
     if (st) return st;
     tr.lap("setup_device");
@@ -713,8 +795,11 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     // the exit test lives in k_sweep_log and later sweeps turn into no-ops once it fires.  The host polls a
     // pinned mirror of the ready flag only to stop enqueuing early.  SYNC (uniform callback, or verbose progress
     // lines): one stream synchronisation per bond visit so that the host can draw the lottery / print.
-    const bool sync_mode = (h->ucb != nullptr) || h->verbose || h->force_sync;
-    const bool dev_lot = (h->ucb == nullptr) && !h->force_host_lottery;
+    const bool multi = h->nproc > 1;      // several processes: always asynchronous with the device lottery, every process
+                                          // enqueues the same number of sweeps (their NCCL calls must pair up)
+    const bool sync_mode = !multi && ((h->ucb != nullptr) || h->verbose || h->force_sync);
+    const bool dev_lot = multi || ((h->ucb == nullptr) && !h->force_host_lottery);
+    const int NV = D.nv;
     D.dev_lottery = dev_lot ? 1 : 0;
     int maxnb = 0;
     for (int v = 0; v < P; ++v) maxnb = std::max(maxnb, h->own[v + 1] - h->own[v]);
@@ -745,33 +830,33 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         const int Gc = std::min(GMAX, cdiv(maxcol, TB)), Gr = std::min(GMAX, cdiv(maxrow, TB));
         if (h->piv == -1) {
             const int Gs = (int)std::min<i64>(GMAX, std::max<i64>(1, (maxsb + TB - 1) / TB));
-            KIND_SWITCH(h->kind, L(KC_SUPERBLOCK, [&] { k_superblock<K, 0><<<dim3(Gs, P), TB, smS, s>>>(D, dir, pp, 0, 0, nullptr, nullptr); }));
-            KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, P), TB, smF, s>>>(D, dir, pp, 2); }));
-            KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, P), TB, smF, s>>>(D, dir, pp, 2); }));
+            KIND_SWITCH(h->kind, L(KC_SUPERBLOCK, [&] { k_superblock<K, 0><<<dim3(Gs, NV), TB, smS, s>>>(D, dir, pp, 0, 0, nullptr, nullptr); }));
+            KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, NV), TB, smF, s>>>(D, dir, pp, 2); }));
+            KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, NV), TB, smF, s>>>(D, dir, pp, 2); }));
         } else {
             if (!dev_lot) CUDA_TRY(h, cudaMemcpyAsync(D.lot, h->lot_h, (size_t)P * 4 * h->nlotmax * sizeof(int), cudaMemcpyHostToDevice, s));
             const int Gl = std::min(GMAX, cdiv(maxlot, TB));
-            KIND_SWITCH(h->kind, L(KC_LOT, [&] { k_lot<K><<<dim3(Gl, P), TB, smL, s>>>(D, dir, pp); }));
+            KIND_SWITCH(h->kind, L(KC_LOT, [&] { k_lot<K><<<dim3(Gl, NV), TB, smL, s>>>(D, dir, pp); }));
             if (h->piv == 0) {
-                KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, P), TB, smF, s>>>(D, dir, pp, 1); }));
-                KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, P), TB, smF, s>>>(D, dir, pp, 1); }));
+                KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, NV), TB, smF, s>>>(D, dir, pp, 1); }));
+                KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, NV), TB, smF, s>>>(D, dir, pp, 1); }));
             } else {
                 // rook loop (dmrgg.f90:515-582): at most 2*piv fibers, alternating, starting with the row in '<<' sweeps
                 int isrow = (dir == 2) ? 1 : 0;
                 for (int c = 0; c < 2 * h->piv; ++c) {
-                    if (!isrow) { KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, P), TB, smF, s>>>(D, dir, pp, 0); })); }
-                    else        { KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, P), TB, smF, s>>>(D, dir, pp, 0); })); }
+                    if (!isrow) { KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, NV), TB, smF, s>>>(D, dir, pp, 0); })); }
+                    else        { KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, NV), TB, smF, s>>>(D, dir, pp, 0); })); }
                     isrow ^= 1;
                 }
             }
         }
-        L(KC_ACCEPT, [&] { k_accept<<<dim3(1, P), 128, 0, s>>>(D, dir, pp, small_element, small_pivot); });
+        L(KC_ACCEPT, [&] { k_accept<<<dim3(1, NV), 128, 0, s>>>(D, dir, pp, small_element, small_pivot); });
         // neighbour factors first (they read the old rank), then the rank-1 append whose last CTA bumps r(p)
         if (maxnb > 1) {
-            if (h->use_wave) L(KC_NBR, [&] { k_update_nbr_w<<<dim3(cdiv(h->nmax, 8), P, 2), 256, h->sm_ext, s>>>(D, dir, pp); });
-            else L(KC_NBR, [&] { k_update_nbr<<<dim3(cdiv(2 * h->nmax, 64), P), 64, 0, s>>>(D, dir, pp); });
+            if (h->use_wave) L(KC_NBR, [&] { k_update_nbr_w<<<dim3(cdiv(h->nmax, 8), NV, 2), 256, h->sm_ext, s>>>(D, dir, pp); });
+            else L(KC_NBR, [&] { k_update_nbr<<<dim3(cdiv(2 * h->nmax, 64), NV), 64, 0, s>>>(D, dir, pp); });
         }
-        L(KC_UPDATE, [&] { k_update_main<<<dim3(std::min(GMAX, cdiv(maxcol + maxrow, 256)), P), 256, 0, s>>>(D, dir, pp); });
+        L(KC_UPDATE, [&] { k_update_main<<<dim3(std::min(GMAX, cdiv(maxcol + maxrow, 256)), NV), 256, 0, s>>>(D, dir, pp); });
         if (sync_mode) {
             VisitOut* src = D.vlog + visit_log_index(cur_it, pp, 0);
             CUDA_TRY(h, cudaMemcpyAsync(h->out_h, src, (size_t)P * sizeof(VisitOut), cudaMemcpyDeviceToHost, s));
@@ -788,12 +873,15 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         if (sync_mode) h->rks_h = h->rk_h;
         for (int pp = 1; pp <= maxnb; ++pp) { int e = enqueue_visit(dir, pp, rb); if (e) return e; }
         if (P > 1) {
+            if (multi) { int e = mp_phase1(h, L); if (e) return e; }
+            const int nbnd = boundary_count(D);
             L(KC_EXCHANGE, [&] { k_allreduce<<<1, 32, 0, s>>>(D); });
-            KIND_SWITCH(h->kind, L(KC_EXCHANGE, [&] { k_exchange_corner<K><<<dim3(1, P - 1), TB, smA, s>>>(D); }));
-            if (h->use_wave) L(KC_EXCHANGE, [&] { k_exchange_extend_w<<<dim3(cdiv(h->nmax, 8), P - 1, 2), 256, h->sm_ext, s>>>(D); });
-            else L(KC_EXCHANGE, [&] { k_exchange_extend<<<dim3(cdiv(2 * h->nmax, 64), P - 1), 64, 0, s>>>(D); });
+            KIND_SWITCH(h->kind, L(KC_EXCHANGE, [&] { k_exchange_corner<K><<<dim3(1, nbnd), TB, smA, s>>>(D); }));
+            if (h->use_wave) L(KC_EXCHANGE, [&] { k_exchange_extend_w<<<dim3(cdiv(h->nmax, 8), nbnd, 2), 256, h->sm_ext, s>>>(D); });
+            else L(KC_EXCHANGE, [&] { k_exchange_extend<<<dim3(cdiv(2 * h->nmax, 64), nbnd), 64, 0, s>>>(D); });
         }
-        if (has_quad) launch_quad(h, L, true, true);
+        if (has_quad) { int e = launch_quad(h, L, true, true); if (e) return e; }
+        else if (multi) { int e = mp_phase2(h, L, 0); if (e) return e; }
         L(KC_MISC, [&] { k_sweep_log<<<1, 128, 0, s>>>(D, maxrank); });
         return 0;
     };
@@ -803,7 +891,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     // In asynchronous mode a sweep is a fixed kernel sequence (sweep number, seed and thresholds live in device memory),
     // so it is captured once per direction into a CUDA graph and replayed: one graph launch per sweep instead of ~25
     // kernel launches.  Grids are sized for the rank capacity; surplus CTAs exit at once.
-    const bool use_graph = !sync_mode && !h->profile && !h->no_graph;
+    const bool use_graph = !sync_mode && !h->profile && !h->no_graph && (!multi || std::getenv("TTC_MP_GRAPH") != nullptr);
     if (use_graph) {
         std::vector<long long> gsig = {(long long)h->piv, (long long)has_quad, (long long)maxrank, (long long)h->use_wave, (long long)dev_lot,
                                        (long long)h->setup_serial};
@@ -831,7 +919,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     tr.lap("graph_capture");
     int enq = 0;
     for (it = 1; it <= last_sweep; ++it) {
-        if (*(volatile int*)h->ready_h) break;          // device already reached its exit condition
+        if (!multi && *(volatile int*)h->ready_h) break;   // device already reached its exit condition
         int e = 0;
         if (use_graph) {
             const int gdir = (it % 2 == 1) ? 0 : 1;     // graph 0: odd sweeps ('>>'), graph 1: even sweeps ('<<')
@@ -865,13 +953,14 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     }
     (void)enq;
 
-    // ---- finalise (dmrgg.f90:1028-1029); not gated by the ready flag
+    // ---- finalise (dmrgg.f90:1028-1029); not gated by the ready flag.  Each process finalises the cores it owns.
+    const int ncore_own = D.c_hi - D.c_lo + 1;
     if (h->use_wave) {
-        L(KC_FINAL, [&] { k_lua_r_w<<<dim3(std::min(512, cdiv((i64)h->nmax * Rmax, 8)), d), 256, h->sm_ext, s>>>(D); });
-        L(KC_FINAL, [&] { k_lua_l_w<<<dim3(std::min(512, cdiv((i64)h->nmax * Rmax, 8)), d), 256, h->sm_ext, s>>>(D); });
+        L(KC_FINAL, [&] { k_lua_r_w<<<dim3(std::min(512, cdiv((i64)h->nmax * Rmax, 8)), ncore_own), 256, h->sm_ext, s>>>(D); });
+        L(KC_FINAL, [&] { k_lua_l_w<<<dim3(std::min(512, cdiv((i64)h->nmax * Rmax, 8)), ncore_own), 256, h->sm_ext, s>>>(D); });
     } else {
-        L(KC_FINAL, [&] { k_lua_r<<<dim3(cdiv((i64)h->nmax * Rmax, 128), d), 128, 0, s>>>(D); });
-        L(KC_FINAL, [&] { k_lua_l<<<dim3(cdiv((i64)h->nmax * Rmax, 128), d), 128, 0, s>>>(D); });
+        L(KC_FINAL, [&] { k_lua_r<<<dim3(cdiv((i64)h->nmax * Rmax, 128), ncore_own), 128, 0, s>>>(D); });
+        L(KC_FINAL, [&] { k_lua_l<<<dim3(cdiv((i64)h->nmax * Rmax, 128), ncore_own), 128, 0, s>>>(D); });
     }
     CUDA_TRY(h, cudaEventRecord(h->ev1, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
@@ -972,6 +1061,7 @@ int ttc_create(ttc_handle** out, int kind, int d, const int* n, const double* pa
 void ttc_destroy(ttc_handle* h) {
     if (!h) return;
     if (h->stream || !h->allocs.empty()) { cudaSetDevice(h->device); free_device(h); }
+    if (h->comm) { cudaSetDevice(h->device); nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->flush_d) cudaFree(h->flush_d);
     delete h;
 }
@@ -990,6 +1080,14 @@ int ttc_set_quad(ttc_handle* h, const double* quad) {
     if (!h) return TTC_ERR_ARG;
     h->quad.clear();
     if (quad) { size_t tot = 0; for (int p = 1; p <= h->d; ++p) tot += h->n[p]; h->quad.assign(quad, quad + tot); }
+    return TTC_OK;
+}
+int ttc_set_par(ttc_handle* h, const double* par, long npar) {
+    if (!h || !par) return TTC_ERR_ARG;
+    if ((size_t)npar != h->par.size()) { h->err = "ttc_set_par: the parameter blob must keep its length"; return TTC_ERR_ARG; }
+    if (h->kind == TTC_ISING && (int)par[2 * h->n[1]] != h->ising_id) { h->err = "ttc_set_par: the integrand id must not change"; return TTC_ERR_ARG; }
+    h->par.assign(par, par + npar);
+    h->par_dirty = true;
     return TTC_OK;
 }
 int ttc_set_tru(ttc_handle* h, int present, double tru) { if (!h) return TTC_ERR_ARG; h->has_tru = present != 0; h->tru = tru; return TTC_OK; }
@@ -1020,6 +1118,10 @@ int ttc_ranks(const ttc_handle* h, int* r) {
 int ttc_core(ttc_handle* h, int k, double* out) {
     if (!h || !out || k < 1 || k > h->d) return TTC_ERR_ARG;
     if (!h->ran) { h->err = "ttc_core before ttc_dmrgg"; return TTC_ERR_STATE; }
+    if (k < h->plan.c_lo || k > h->plan.c_hi) {   // like the reference: on return each rank holds only its own cores
+        h->err = "ttc_core: core " + std::to_string(k) + " is held by another rank (see ttc_core_range)";
+        return TTC_ERR_STATE;
+    }
     CUDA_TRY(h, cudaSetDevice(h->device));
     size_t cnt = (size_t)h->rk_h[k - 1] * h->n[k] * h->rk_h[k];
     { int st = ensure_pack(h, cnt); if (st) return st; }
@@ -1035,12 +1137,13 @@ int ttc_cores(ttc_handle* h, double* out, long long cap) {
     if (!h || !out) return TTC_ERR_ARG;
     if (!h->ran) { h->err = "ttc_cores before ttc_dmrgg"; return TTC_ERR_STATE; }
     CUDA_TRY(h, cudaSetDevice(h->device));
+    const int klo = h->plan.c_lo, khi = h->plan.c_hi;      // several processes: this rank's own cores only
     size_t tot = 0;
-    for (int k = 1; k <= h->d; ++k) tot += (size_t)h->rk_h[k - 1] * h->n[k] * h->rk_h[k];
+    for (int k = klo; k <= khi; ++k) tot += (size_t)h->rk_h[k - 1] * h->n[k] * h->rk_h[k];
     if ((long long)tot > cap) { h->err = "ttc_cores: output buffer too small"; return TTC_ERR_ARG; }
     { int st = ensure_pack(h, tot); if (st) return st; }
     size_t off = 0;
-    for (int k = 1; k <= h->d; ++k) {
+    for (int k = klo; k <= khi; ++k) {
         size_t cnt = (size_t)h->rk_h[k - 1] * h->n[k] * h->rk_h[k];
         k_pack_core<<<std::min(1024, cdiv((i64)cnt, 256)), 256, 0, h->stream>>>(h->plan, k, h->pack_d + off);
         h->launches += 1;
@@ -1087,7 +1190,7 @@ int ttc_quad(ttc_handle* h, double* val) {
     if (!h->ran) { h->err = "ttc_quad before ttc_dmrgg"; return TTC_ERR_STATE; }
     CUDA_TRY(h, cudaSetDevice(h->device));
     Launcher L(h);
-    launch_quad(h, L, false, !h->quad.empty());
+    { int st = launch_quad(h, L, false, !h->quad.empty(), 1); if (st) return st; }   // collective when there are several processes
     CUDA_TRY(h, cudaMemcpyAsync(h->sweep_h, h->plan.sweep_out, sizeof(SweepOut), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     *val = h->sweep_h->val;
@@ -1159,6 +1262,7 @@ int ttc_profile(const ttc_handle* h, int cap, const char** names, long long* lau
 int ttc_superblock_probe(ttc_handle* h, int bond, int store, int reps, long long* out_idx, double* out_val, double* ms, long long* count) {
     if (!h || bond < 1 || bond > h->d - 1 || reps < 1) return TTC_ERR_ARG;
     if (!h->ran) { h->err = "ttc_superblock_probe before ttc_dmrgg"; return TTC_ERR_STATE; }
+    if (bond < h->own[h->plan.v0] || bond >= h->own[h->plan.v0 + h->plan.nv]) { h->err = "ttc_superblock_probe: bond belongs to another rank"; return TTC_ERR_STATE; }
     CUDA_TRY(h, cudaSetDevice(h->device));
     const DevPlan& D = h->plan;
     cudaStream_t s = h->stream;
@@ -1203,6 +1307,7 @@ int ttc_fiber_probe(ttc_handle* h, int bond, int isrow, int ii, int jj, int kk, 
     cudaStream_t s = h->stream;
     int v = 0;
     while (v < h->P - 1 && bond >= h->own[v + 1]) ++v;
+    if (v < h->plan.v0 || v >= h->plan.v0 + h->plan.nv) { h->err = "ttc_fiber_probe: bond belongs to another rank"; return TTC_ERR_STATE; }
     const int pp = bond - h->own[v] + 1;
     CUDA_TRY(h, cudaMemcpyAsync(D.rks, D.rk, (size_t)(h->d + 1) * sizeof(int), cudaMemcpyDeviceToDevice, s));   // rks := rk
     VState S;
@@ -1217,7 +1322,7 @@ int ttc_fiber_probe(ttc_handle* h, int bond, int isrow, int ii, int jj, int kk, 
     const size_t smF = h->sm_fiber;
     // only virtual rank v must run: launch a 1-wide grid in y and shift the plan so blockIdx.y = 0 maps to v
     DevPlan Dv = D;
-    Dv.own = D.own + v; Dv.P = 1; Dv.st = D.st + v; Dv.part = D.part + (size_t)v * 2 * GMAX; Dv.tickets = D.tickets + v;
+    Dv.v0 = 0; Dv.nv = 1; Dv.own = D.own + v; Dv.P = 1; Dv.st = D.st + v; Dv.part = D.part + (size_t)v * 2 * GMAX; Dv.tickets = D.tickets + v;
     Dv.acol1 = D.acol1 + (size_t)v * h->Rmax * h->nmax; Dv.bcol1 = D.bcol1 + (size_t)v * h->Rmax * h->nmax;
     Dv.arow1 = D.arow1 + (size_t)v * h->Rmax * h->nmax; Dv.brow1 = D.brow1 + (size_t)v * h->Rmax * h->nmax;
     auto launch = [&]() {
@@ -1242,8 +1347,43 @@ int ttc_fiber_probe(ttc_handle* h, int bond, int isrow, int ii, int jj, int kk, 
     return TTC_OK;
 }
 
-// multi-GPU communicator: implemented in ttc_comm.cu
-int ttc_comm_unique_id(void* id128);
-int ttc_comm_init(ttc_handle* h, int nranks, int rank, const void* id128);
+int ttc_core_range(const ttc_handle* h, int* first, int* last) {
+    if (!h || !first || !last) return TTC_ERR_ARG;
+    if (!h->ran) return TTC_ERR_STATE;
+    *first = h->plan.c_lo; *last = h->plan.c_hi;
+    return TTC_OK;
+}
+
+// ---- multi-GPU: one process per GPU (NCCL bound at run time, ttc_nccl.hpp)
+int ttc_comm_unique_id(void* id128) {
+    if (!id128) return TTC_ERR_ARG;
+    NcclApi& N = nccl_api();
+    if (!N.load()) { g_create_err = N.err; return TTC_ERR_COMM; }
+    NcclUniqueId id;
+    int e = N.GetUniqueId(&id);
+    if (e != 0) { g_create_err = std::string("ncclGetUniqueId: ") + N.GetErrorString(e); return TTC_ERR_COMM; }
+    std::memcpy(id128, &id, sizeof id);
+    return TTC_OK;
+}
+int ttc_comm_init(ttc_handle* h, int nranks, int rank, const void* id128) {
+    if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) { if (h) h->err = "ttc_comm_init: bad arguments"; return TTC_ERR_ARG; }
+    if (h->comm) { h->err = "ttc_comm_init: communicator already initialised"; return TTC_ERR_STATE; }
+    int st = check_device(h);          // no CUDA device -> TTC_ERR_CUDA: there is no CPU fallback
+    if (st) return st;
+    NcclApi& N = nccl_api();
+    if (!N.load()) { h->err = N.err; return TTC_ERR_COMM; }
+    NcclUniqueId id;
+    std::memcpy(&id, id128, sizeof id);
+    NCCL_TRY(h, N.CommInitRank(&h->comm, nranks, id, rank));
+    h->nproc = nranks; h->prank = rank;
+    h->setup_sig.clear();
+    return TTC_OK;
+}
+int ttc_comm_rank(const ttc_handle* h, int* nranks, int* rank) {
+    if (!h) return TTC_ERR_ARG;
+    if (nranks) *nranks = h->nproc;
+    if (rank) *rank = h->prank;
+    return TTC_OK;
+}
 
 }  // extern "C"
