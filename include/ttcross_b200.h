@@ -69,7 +69,8 @@ int ttc_set_uniform_callback(ttc_handle* h, ttc_uniform_cb cb, void* ctx);
 /* 0 (default): lottery on the device, sweeps enqueued asynchronously; 1: lottery on the host exactly as rnd.f90:105-126
  * writes it (one stream synchronisation per bond visit; implied by a uniform callback); 2: device lottery, synchronous.
  * 3: device lottery, asynchronous, but the plain one-thread-per-chain support kernels instead of the warp-wavefront /
- * shared-memory ones.  All modes produce identical results; modes 1-3 exist to prove that. */
+ * shared-memory ones.  4: device lottery, asynchronous, one kernel per step of a bond visit instead of the cluster kernel
+ * that runs a virtual rank's whole visit list.  All modes produce identical results; modes 1-4 exist to prove that. */
 int ttc_set_lottery_mode(ttc_handle* h, int mode);
 int ttc_set_verbose(ttc_handle* h, int verbose);                    /* 1: print the reference's per-sweep lines on stdout */
 
@@ -125,6 +126,10 @@ double ttc_device_ms(const ttc_handle* h);
 /* per-kernel-class accounting of the last ttc_dmrgg: names[i] (static strings), launches, total ms (events, only when
  * profiling was enabled with ttc_set_profile(h, 1)) */
 int ttc_set_profile(ttc_handle* h, int on);
+/* diagnostic device timeline of the next ttc_dmrgg: every kernel stamps %globaltimer when its first CTA starts (id = index
+ * into names[]; id 100 = a fused argmax fold finished).  Returns the number of stamps. */
+int ttc_set_timeline(ttc_handle* h, int on);
+long ttc_timeline(const ttc_handle* h, long cap, int* ids, unsigned long long* t_ns, const char** names, int names_cap);
 int ttc_profile(const ttc_handle* h, int cap, const char** names, long long* launches, double* ms);
 
 /* ---- multi-GPU: one process per GPU, core blocks partitioned over ranks ------

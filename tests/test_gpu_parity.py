@@ -62,7 +62,7 @@ def test_mvn(d, n, R, piv, P):
     assert_parity(t, g, o, exact=False, rtol=1e-10)
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
 @pytest.mark.parametrize("kind,index,n,R,piv,P", [("c", 6, 64, 16, 1, 1), ("d", 6, 16, 8, 2, 2), ("c", 10, 32, 10, 2, 8)])
 def test_lottery_modes_agree(mode, kind, index, n, R, piv, P):
     """mode 1 draws the lottery on the host with the literal loop of rnd.f90; mode 0/2 draw it on the device in closed form."""

@@ -80,6 +80,9 @@ def load_library(build_if_missing: bool = True):
     L.ttc_device_ms.restype = C.c_double
     L.ttc_device_ms.argtypes = [vp]
     L.ttc_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_longlong), _dp]
+    L.ttc_set_timeline.argtypes = [vp, C.c_int]
+    L.ttc_timeline.restype = C.c_long
+    L.ttc_timeline.argtypes = [vp, C.c_long, _ip, C.POINTER(C.c_ulonglong), C.POINTER(C.c_char_p), C.c_int]
     L.ttc_comm_unique_id.argtypes = [C.c_void_p]
     L.ttc_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_void_p]
     L.ttc_comm_rank.argtypes = [vp, _ip, _ip]
@@ -278,6 +281,25 @@ class TTCross:
         ms = (C.c_double * cap)()
         cnt = self._L.ttc_profile(self.h, cap, names, launches, ms)
         return {names[i].decode(): (int(launches[i]), float(ms[i])) for i in range(cnt)}
+
+    def set_timeline(self, on: bool):
+        self._check(self._L.ttc_set_timeline(self.h, int(on)))
+
+    def timeline(self):
+        """[(kernel name, t_ns)] stamps of the last run, in time order (diagnostic)."""
+        cap = 65536
+        ids = np.zeros(cap, dtype=np.int32)
+        ts = np.zeros(2 * cap, dtype=np.uint64)
+        names = (C.c_char_p * 64)()
+        n = self._L.ttc_timeline(self.h, 2 * cap, _i(ids), ts.ctypes.data_as(C.POINTER(C.c_ulonglong)), names, 64)
+        self.timeline_clocks = {int(t): int(c) for t, c in zip(ts[:n], ts[n:2 * n])}
+        nm = [x.decode() if x else "?" for x in names]
+        special = {40: "k_visits", 100: "fold_done", 41: "v:staged", 42: "v:lot_setup", 43: "v:lot_eval", 44: "v:lot_fold",
+                   45: "v:fiber_eval", 46: "v:fiber_fold", 47: "v:rook_done", 48: "v:nbr_done", 49: "v:append_done", 50: "f:xs_staged", 51: "f:pref_issued", 52: "f:eval_done",
+                   53: "f:resid_done", 54: "f:stored", 34: "k_quad_inc", 60: "q:lu_staged", 61: "q:chunk_staged", 62: "q:chunk_summed",
+                   63: "q:luar_done", 64: "q:end"}
+        out = [(special.get(int(i), nm[i] if i < 64 else "?"), int(t)) for i, t in zip(ids[:n], ts[:n])]
+        return sorted(out, key=lambda x: x[1])
 
     def l2_flush(self, nbytes: int = 256 << 20):
         self._check(self._L.ttc_l2_flush(self.h, nbytes))

@@ -106,7 +106,19 @@ struct DevPlan {
     double* mb2_send; double* mb2_recv;                           // phase 2: per virtual rank [chain Rmax^2 | amax | neval | error | pad]
     double* nb_send_l; double* nb_recv_l;   // to/from the left neighbour process : send column slab [Rmax*nmax]; recv row [nmax*Rmax] | inv [Rmax^2]
     double* nb_send_r; double* nb_recv_r;   // to/from the right neighbour process: send row | inv; recv column slab
+    double* ttqy;          // [(d+1)][Rmax*Rmax] contracted cores after d2_luar (incremental per-sweep quadrature, k_quad_inc)
+    int* qext;             // [(d+1)][2] extents of ttqy/ttqq already computed
+    // diagnostic timeline (ttc_set_timeline): every kernel stamps %globaltimer when its first CTA starts
+    unsigned long long* tlog; int* tlog_n; int tlog_cap;
 };
+__device__ __forceinline__ void tl_stamp(const DevPlan& P, int id) {
+    if (P.tlog && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        int k = atomicAdd(P.tlog_n, 1);
+        if (k < P.tlog_cap) { P.tlog[3 * k] = (unsigned long long)id; P.tlog[3 * k + 1] = t; P.tlog[3 * k + 2] = (unsigned long long)clock64(); }
+    }
+}
 __host__ __device__ __forceinline__ int proc_v0(int P, int nproc, int g) { return (int)((long long)P * g / nproc); }
 __device__ __forceinline__ bool own_vrank(const DevPlan& P, int v) { return v >= P.v0 && v < P.v0 + P.nv; }
 // boundaries b (between virtual ranks b and b+1) that touch this process's virtual ranks: first one, and how many
@@ -116,6 +128,14 @@ __host__ __device__ __forceinline__ int boundary_count(const DevPlan& P) {
     return last - first_boundary(P) + 1;
 }
 
+__device__ __forceinline__ void tl_mark0(const DevPlan& P, int id) {     // diagnostic: phase stamps of the middle CTA
+    if (P.tlog && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        int k = atomicAdd(P.tlog_n, 1);
+        if (k < P.tlog_cap) { P.tlog[3 * k] = (unsigned long long)id; P.tlog[3 * k + 1] = t; P.tlog[3 * k + 2] = (unsigned long long)clock64(); }
+    }
+}
 // ----------------------------------------------------------------------------
 // bond-visit geometry (dmrgg.f90:329-331 and the rr/r snapshot of :325)
 // ----------------------------------------------------------------------------
@@ -173,6 +193,15 @@ struct GlobalVals {
     Src s; const double* par; int nw;    // nw: offset of the weights inside par (Ising: n)
     __device__ __forceinline__ double x(int pos) const { return par[s(pos) - 1]; }
     __device__ __forceinline__ double w(int pos) const { return par[nw + s(pos) - 1]; }
+    // all m positions at once: the index loads, then the value loads, are independent of each other (memory-level
+    // parallelism instead of one dependent chain per accessor call)
+    __device__ __forceinline__ void gather(int m, double* xv, double* wv, bool needw) const {
+        for (int pos = 1; pos <= m; ++pos) {
+            const int idx = s(pos) - 1;
+            xv[pos - 1] = par[idx];
+            wv[pos - 1] = needw ? par[nw + idx] : 0.0;
+        }
+    }
 };
 // values staged in shared memory by stage_bond(): left table XL[pos][i], right table XR[pos][q], nodes/weights of the
 // two free modes
@@ -192,35 +221,68 @@ struct StagedVals {
         if (hask && pos == nl + 2) return wk;
         return WR[(pos - nl - 2 - hask) * rr + (q - 1)];
     }
+    // all m positions at once: three branch-free runs of independent shared-memory loads
+    __device__ __forceinline__ void gather(int m, double* xv, double* wv, bool needw) const {
+        const double* xl = XL + (i - 1); const double* wl = WL + (i - 1);
+        for (int pos = 0; pos < nl; ++pos) { xv[pos] = xl[pos * rl]; wv[pos] = needw ? wl[pos * rl] : 0.0; }
+        xv[nl] = xj; wv[nl] = wj;
+        int o = nl + 1;
+        if (hask) { xv[o] = xk; wv[o] = wk; ++o; }
+        const double* xr = XR + (q - 1); const double* wr = WR + (q - 1);
+        for (int t = 0; o + t < m; ++t) { xv[o + t] = xr[t * rr]; wv[o + t] = needw ? wr[t * rr] : 0.0; }
+    }
 };
 
 // test_crs_ising.f90:176-218.  Pure + - * / : bit-reproducible.
+// The node values / weights of the m positions are gathered first (independent loads), then the reference's
+// recurrences run on the arrays: same operations in the same order, without a branchy accessor inside every step.
 template <class V>
-__device__ double eval_ising(const DevPlan& P, const V& v) {
+__device__ __noinline__ double eval_ising(const DevPlan& P, const V& v) {
     const int m = P.d;
     const int id = P.ising_id;
     double a = 0.0, b = 0.0, f;
-    if (id == 2 || id == 3) {
-        a = 1.0;
-        if (m <= MAXD_LOCAL) {
-            double x[MAXD_LOCAL];
-            for (int j = 1; j <= m; ++j) x[j - 1] = v.x(j);
+    if (m <= MAXD_LOCAL) {
+        double x[MAXD_LOCAL], wq[MAXD_LOCAL];
+        v.gather(m, x, wq, true);
+        if (id == 2 || id == 3) {
+            a = 1.0;
+#pragma unroll 1
             for (int i = 0; i <= m; ++i) {
                 double uij = 1.0;
+#pragma unroll 2
                 for (int j = i + 1; j <= m; ++j) {
                     uij = uij * x[j - 1];
                     double t = (uij - 1.0) / (uij + 1.0);
                     a = a * (t * t);
                 }
             }
-        } else {
-            for (int i = 0; i <= m; ++i) {
-                double uij = 1.0;
-                for (int j = i + 1; j <= m; ++j) {
-                    uij = uij * v.x(j);
-                    double t = (uij - 1.0) / (uij + 1.0);
-                    a = a * (t * t);
-                }
+        }
+        if (id == 1 || id == 2) {
+            double vv = 1.0, w = 1.0, vk = 1.0, wk = 1.0;
+#pragma unroll 4
+            for (int i = 1; i <= m; ++i) {
+                vk = vk * x[m - i];
+                wk = wk * x[i - 1];
+                vv = vv + vk;
+                w = w + wk;
+            }
+            b = 1.0 / (vv * w);
+        }
+        if (id == 1) f = 2 * b;
+        else if (id == 2) f = 2 * a * b;
+        else f = 2 * a;
+#pragma unroll 4
+        for (int i = 0; i < m; ++i) f = f * wq[i];
+        return f;
+    }
+    if (id == 2 || id == 3) {
+        a = 1.0;
+        for (int i = 0; i <= m; ++i) {
+            double uij = 1.0;
+            for (int j = i + 1; j <= m; ++j) {
+                uij = uij * v.x(j);
+                double t = (uij - 1.0) / (uij + 1.0);
+                a = a * (t * t);
             }
         }
     }
@@ -242,21 +304,28 @@ __device__ double eval_ising(const DevPlan& P, const V& v) {
 }
 // test_crs_stdnorm.f90:154-170
 template <class V>
-__device__ double eval_stdnorm(const DevPlan& P, const V& v) {
+__device__ __noinline__ double eval_stdnorm(const DevPlan& P, const V& v) {
     double sum = 0.0;
+    if (P.d <= MAXD_LOCAL) {
+        double x[MAXD_LOCAL], wq[MAXD_LOCAL];
+        v.gather(P.d, x, wq, false);
+        for (int i = 0; i < P.d; ++i) sum = sum + x[i] * x[i];
+        return exp(-sum);
+    }
     for (int i = 1; i <= P.d; ++i) { double x = v.x(i); sum = sum + x * x; }
     return exp(-sum);
 }
 // lib/mvn_pdf.f90:63-83 (through test_crs_mvn.f90:156-172); A = inv_cov column-major, staged by the caller
 template <class V>
-__device__ double eval_mvn(const DevPlan& P, const V& v, const double* __restrict__ A /*d*d*/) {
+__device__ __noinline__ double eval_mvn(const DevPlan& P, const V& v, const double* __restrict__ A /*d*d*/) {
     const int m = P.d;
     const double* mu = P.aux;
     const double denom = P.aux[m + (i64)m * m];
     double e = 0.0;
     if (m <= MAXD_LOCAL) {
-        double diff[MAXD_LOCAL];
-        for (int i = 0; i < m; ++i) diff[i] = v.x(i + 1) - mu[i];
+        double diff[MAXD_LOCAL], wq[MAXD_LOCAL];
+        v.gather(m, diff, wq, false);
+        for (int i = 0; i < m; ++i) diff[i] = diff[i] - mu[i];
         for (int i = 0; i < m; ++i) {
             const double di = diff[i];
             for (int j = 0; j < m; ++j) e = e + di * A[i + (i64)j * m] * diff[j];
@@ -412,7 +481,7 @@ __host__ __device__ __forceinline__ long long dbl_bits(double x) {
 #endif
 }
 // segments cover counts 1..scol; returns the number of segments
-__host__ __device__ inline int build_segments(int scol, LotSeg* seg) {
+__host__ __device__ __noinline__ int build_segments(int scol, LotSeg* seg) {
     const double delta = 1.0 / (double)scol;
     const long long db = dbl_bits(delta);
     const int Ed = (int)((db >> 52) & 0x7ff) - 1023;
@@ -446,17 +515,22 @@ __host__ __device__ inline int build_segments(int scol, LotSeg* seg) {
     }
     return ns;
 }
-__host__ __device__ __forceinline__ double lot_T(const LotSeg* seg, int ns, int c) {   // T[c], 1 <= c <= scol
+__host__ __device__ __noinline__ double lot_T(const LotSeg* seg, int ns, int c) {   // T[c], 1 <= c <= scol
     int lo = 0, hi = ns - 1;
     while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (seg[mid].c0 <= c) lo = mid; else hi = mid - 1; }
     const LotSeg& g = seg[lo];
     return scalbn((double)(g.M + (long long)(c - g.c0) * g.k), g.E - 52);
 }
 // one draw: 1-based cell index in 1..m (zeros = sorted distinct 1-based zero-weight cells)
-__host__ __device__ __forceinline__ int lot_draw(const LotSeg* seg, int ns, int scol, int m, const int* zeros, int nz, double y) {
+__host__ __device__ __noinline__ int lot_draw(const LotSeg* seg, int ns, int scol, int m, const int* zeros, int nz, double y) {
     if (!(y < lot_T(seg, ns, scol))) return m;          // x(n) <= y  ->  n = m+1, clamped to m (rnd.f90:122)
-    int lo = 1, hi = scol;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (y < lot_T(seg, ns, mid)) hi = mid; else lo = mid + 1; }
+    // smallest count c with y < T[c].  T[c] is c/scol up to a few ulps, so start next to y*scol and walk (1-2 steps)
+    // instead of bisecting: every lot_T is a dependent chain of shared-memory loads.
+    int lo = (int)(y * (double)scol) + 1;
+    if (lo < 1) lo = 1;
+    if (lo > scol) lo = scol;
+    while (lo < scol && !(y < lot_T(seg, ns, lo))) ++lo;
+    while (lo > 1 && y < lot_T(seg, ns, lo - 1)) --lo;
     int sidx = lo;                                       // the lo-th cell of non-zero weight
     for (int z = 0; z < nz; ++z) { if (zeros[z] <= sidx) ++sidx; else break; }
     return sidx;
@@ -480,6 +554,37 @@ __device__ __forceinline__ void lot_zeros(const int* vip_p, int r1, int side, in
         for (int u = 1; u <= t; ++u) pos += (tmp[u] != tmp[u - 1]);
         if (keep) zeros[pos] = tmp[t];
         if (t == r1 - 1) *nz = pos + 1;
+    }
+    __syncthreads();
+}
+
+// both sides in one pass (three block barriers instead of six).  tmp: shared int[2*r1]
+__device__ __forceinline__ void lot_zeros2(const int* vip_p, int r1, int r0, int n2, int* tmp, int* zc, int* zr, int* nz /*[2]*/) {
+    int* tc = tmp; int* tr = tmp + r1;
+    for (int t = threadIdx.x; t < r1; t += blockDim.x) {
+        const int4 vp = *reinterpret_cast<const int4*>(vip_p + 4 * t);
+        zc[t] = (vp.x - 1) + r0 * (vp.y - 1) + 1;
+        zr[t] = (vp.z - 1) + n2 * (vp.w - 1) + 1;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < r1; t += blockDim.x) {
+        const int mc = zc[t], mr = zr[t];
+        int rc = 0, rr = 0;
+        for (int u = 0; u < r1; ++u) {
+            const int oc = zc[u], orr = zr[u];
+            rc += (oc < mc) || (oc == mc && u < t);
+            rr += (orr < mr) || (orr == mr && u < t);
+        }
+        tc[rc] = mc; tr[rr] = mr;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < r1; t += blockDim.x) {
+        const int kc = (t == 0) || (tc[t] != tc[t - 1]), kr = (t == 0) || (tr[t] != tr[t - 1]);
+        int pc = 0, pr = 0;
+        for (int u = 1; u <= t; ++u) { pc += (tc[u] != tc[u - 1]); pr += (tr[u] != tr[u - 1]); }
+        if (kc) zc[pc] = tc[t];
+        if (kr) zr[pr] = tr[t];
+        if (t == r1 - 1) { nz[0] = pc + 1; nz[1] = pr + 1; }
     }
     __syncthreads();
 }
@@ -516,7 +621,15 @@ __device__ __forceinline__ bool fold_partials(const DevPlan& P, int v, Partial& 
     }
     raw = amax_block(a, shp);
     res = amax_block(b2, shp);
-    if (threadIdx.x == 0) P.tickets[v] = 0;
+    if (threadIdx.x == 0) {
+        P.tickets[v] = 0;
+        if (P.tlog && v == P.v0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            int k = atomicAdd(P.tlog_n, 1);
+            if (k < P.tlog_cap) { P.tlog[3 * k] = 100ULL; P.tlog[3 * k + 1] = t; P.tlog[3 * k + 2] = (unsigned long long)clock64(); }
+        }
+    }
     return true;
 }
 // residuals in the reference's orders, with the factor loads issued in batches (they do not depend on the sum)
@@ -576,6 +689,7 @@ __device__ __forceinline__ double eval_bond(const DevPlan& P, const Stage& S, in
 // ----------------------------------------------------------------------------
 template <int KIND>
 __global__ void k_lot(DevPlan P, int dir, int pp) {
+    tl_stamp(P, 0);
     if (P.ctrl->ready) return;
     extern __shared__ double smem[];
     __shared__ Partial shp[32];
@@ -652,6 +766,7 @@ __global__ void k_lot(DevPlan P, int dir, int pp) {
 // ----------------------------------------------------------------------------
 template <int KIND, int ISROW>
 __global__ void k_fiber(DevPlan P, int dir, int pp, int mode) {
+    tl_stamp(P, 1);
     if (P.ctrl->ready) return;
     extern __shared__ double smem[];
     __shared__ Partial shp[32];
@@ -728,6 +843,7 @@ __global__ void k_fiber(DevPlan P, int dir, int pp, int mode) {
 // ----------------------------------------------------------------------------
 template <int KIND, int STORE>
 __global__ void k_superblock(DevPlan P, int dir, int pp, int fixed_bond, int fixed_v, double* a_out, Partial* probe_out) {
+    tl_stamp(P, 2);
     extern __shared__ double smem[];
     __shared__ Partial shp[32];
     const int v = (fixed_bond > 0) ? fixed_v : P.v0 + blockIdx.y;
@@ -783,6 +899,7 @@ __global__ void k_superblock(DevPlan P, int dir, int pp, int fixed_bond, int fix
 // K4: accept test and index-set update (dmrgg.f90:598-660)
 // ----------------------------------------------------------------------------
 __global__ void k_accept(DevPlan P, int dir, int pp, double small_element, double small_pivot) {
+    tl_stamp(P, 3);
     if (P.ctrl->ready) return;
     const int it = P.ctrl->it;
     const int v = P.v0 + blockIdx.y;
@@ -836,6 +953,7 @@ __global__ void k_accept(DevPlan P, int dir, int pp, double small_element, doubl
 // the residual of the last column (row) fiber IS the dgemv of d2_lual (d2_luar) with the same operands and order.
 // ----------------------------------------------------------------------------
 __global__ void k_update_main(DevPlan P, int dir, int pp) {
+    tl_stamp(P, 4);
     if (P.ctrl->ready) return;
     const int v = P.v0 + blockIdx.y;
     const Dims D = load_dims(P, v, dir, pp);
@@ -879,6 +997,7 @@ __global__ void k_update_main(DevPlan P, int dir, int pp) {
 // neighbour factors (dmrgg.f90:715-749): new column of row(p) through d2_luar(inv(p-1)), new row of col(p+1)
 // through d2_lual(inv(p+1)).  One thread per mode index; the triangular recurrences are sequential by definition.
 __global__ void k_update_nbr(DevPlan P, int dir, int pp) {
+    tl_stamp(P, 5);
     if (P.ctrl->ready) return;
     const int v = P.v0 + blockIdx.y;
     const Dims D = load_dims(P, v, dir, pp);
@@ -931,6 +1050,7 @@ __global__ void k_update_nbr(DevPlan P, int dir, int pp) {
 // ----------------------------------------------------------------------------
 // MPI_ALLREDUCE(MAX) of (amax, pivotmax, -pivotmin) (dmrgg.f90:852-870); single thread, P is small
 __global__ void k_allreduce(DevPlan P) {
+    tl_stamp(P, 6);
     if (P.ctrl->ready) return;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (P.P > 1) {
@@ -951,32 +1071,39 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 __global__ void k_run_begin(DevPlan P, unsigned long long seed, int has_accuracy, double accuracy) {
+    tl_stamp(P, 7);
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     P.ctrl->ready = 0; P.ctrl->strike = 0; P.ctrl->error = 0; P.ctrl->nsweeps = 0; P.ctrl->it = 1;
     P.ctrl->seed = seed; P.ctrl->has_accuracy = has_accuracy; P.ctrl->accuracy = accuracy;
     P.ctrl->t0_ns = globaltimer_ns();
-    for (int v = 0; v < P.P; ++v) P.tickets[v] = 0;
+    for (int v = 0; v <= P.P; ++v) P.tickets[v] = 0;
+    for (int x = 0; x < 2 * (P.d + 1); ++x) P.qext[x] = 0;
 }
 // end of sweep `it`: the scalar reductions of dmrgg.f90:961-967, the record of the sweep (after the quadrature), the exit
 // test of dmrgg.f90:1010-1019, and the preparation of the next sweep (rr = r snapshot of :325, pivotmax = pivotmin = -1)
 __global__ void k_sweep_log(DevPlan P, int maxrank) {
+    tl_stamp(P, 8);
     if (P.ctrl->ready) return;
     const int it = P.ctrl->it;
+    __shared__ unsigned long long s_ne;
+    __shared__ double s_amax, s_pmax, s_pmin;
+    if (threadIdx.x == 0) { s_ne = 0ULL; s_amax = P.st[0].amax; s_pmax = P.st[0].pivotmax; s_pmin = P.st[0].pivotmin; }
     for (int x = threadIdx.x; x <= P.d; x += blockDim.x) { int r = P.rk[x]; P.rklog[(i64)it * (P.d + 1) + x] = r; P.rks[x] = r; }
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    i64 ne = 0;
-    for (int v = 0; v < P.P; ++v) ne += P.st[v].neval;
-    SweepOut o;
-    o.val = P.sweep_out->val;
-    o.neval = ne; o.amax = P.st[0].amax; o.pivotmax = P.st[0].pivotmax; o.pivotmin = P.st[0].pivotmin;
-    o.t_ns = globaltimer_ns() - P.ctrl->t0_ns;
-    o.valid = 1; o.pad = 0;
-    P.slog[it] = o;
-    for (int v = 0; v < P.P; ++v) {
+    for (int v = threadIdx.x; v < P.P; v += blockDim.x) {
+        atomicAdd(&s_ne, (unsigned long long)P.st[v].neval);
         P.st[v].pivotmax_prev = P.st[v].pivotmax;        // dmrgg.f90:961
         P.st[v].pivotmax = -1.0; P.st[v].pivotmin = -1.0; // dmrgg.f90:326-327 of the next sweep
     }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const i64 ne = (i64)s_ne;
+    SweepOut o;
+    o.val = P.sweep_out->val;
+    o.neval = ne; o.amax = s_amax; o.pivotmax = s_pmax; o.pivotmin = s_pmin;
+    o.t_ns = globaltimer_ns() - P.ctrl->t0_ns;
+    o.valid = 1; o.pad = 0;
+    P.slog[it] = o;
     P.ctrl->nsweeps = it;
     int ready = 0;
     if (maxrank > 0) ready = (it + 1 >= maxrank);
@@ -998,6 +1125,7 @@ __global__ void k_sweep_log(DevPlan P, int maxrank) {
 // ----------------------------------------------------------------------------
 template <int KIND>
 __global__ void k_exchange_corner(DevPlan P) {
+    tl_stamp(P, 9);
     if (P.ctrl->ready) return;
     extern __shared__ double smem[];
     __shared__ Partial shp[32];
@@ -1008,12 +1136,26 @@ __global__ void k_exchange_corner(DevPlan P) {
     const double* A = stage_aux<KIND>(P, smem);
     const int nc = P.n[c];
     double* argc = P.arg + P.coreOff[c];
+    // the d-1 fixed positions of the corner fiber, staged once (one round trip instead of a pointer chase per evaluation)
+    double* XF = smem + P.auxsm; double* WF = XF + P.d;
+    {
+        const int* Lt = P.Lidx + P.offL[c - 1]; const int* Rt = P.Ridx + P.offR[c];
+        const bool hasw = (P.kind == KIND_ISING);
+        const int nwoff = P.n[1];
+        for (int pos = threadIdx.x; pos < P.d - 1; pos += blockDim.x) {
+            const int idx = (pos < c - 1) ? Lt[(i64)pos * P.Rmax + (rc1 - 1)] : Rt[(i64)(pos - (c - 1)) * P.Rmax + (rc - 1)];
+            XF[pos] = P.par[idx - 1]; WF[pos] = hasw ? P.par[nwoff + idx - 1] : 0.0;
+        }
+        __syncthreads();
+    }
     Partial best = amax_init();
     for (int j = threadIdx.x; j < nc; j += blockDim.x) {
-        PointSrc s;
-        s.L = P.Lidx + P.offL[c - 1]; s.nl = c - 1; s.i = rc1; s.j = j + 1; s.k = 0; s.hask = 0;
-        s.R = P.Ridx + P.offR[c]; s.q = rc; s.Rmax = P.Rmax;
-        double f = eval_src<KIND>(P, s, A);
+        StagedVals sv;
+        sv.XL = XF; sv.WL = WF; sv.nl = c - 1; sv.rl = 1; sv.i = 1;
+        sv.xj = P.par[j]; sv.wj = (P.kind == KIND_ISING) ? P.par[P.n[1] + j] : 0.0;
+        sv.hask = 0; sv.xk = 0.0; sv.wk = 0.0;
+        sv.XR = XF + (c - 1); sv.WR = WF + (c - 1); sv.rr = 1; sv.q = 1;
+        double f = eval_point<KIND>(P, sv, A);
         argc[(rc1 - 1) + (i64)P.Rmax * (j + (i64)nc * (rc - 1))] = f;
         amax_take(best, f, j);
     }
@@ -1028,6 +1170,7 @@ __global__ void k_exchange_corner(DevPlan P) {
     }
 }
 __global__ void k_exchange_extend(DevPlan P) {
+    tl_stamp(P, 10);
     if (P.ctrl->ready) return;
     const int b = first_boundary(P) + blockIdx.y;
     const int c = P.own[b + 1];
@@ -1078,6 +1221,7 @@ __global__ void k_exchange_extend(DevPlan P) {
 // ----------------------------------------------------------------------------
 // ttqq(p)(i,k) = sum_j arg(p)(i,j,k) * w_p(j), accumulated from 0 in ascending j (dgemv 'n', beta = 0)
 __global__ void k_quad_contract(DevPlan P, int use_weights) {
+    tl_stamp(P, 11);
     const int p = P.c_lo + blockIdx.y;
     const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
     const double* a = P.arg + P.coreOff[p];
@@ -1095,6 +1239,7 @@ __global__ void k_quad_contract(DevPlan P, int use_weights) {
 // dtt_lua on the contracted train: core p is an r0 x r1 matrix with leading dimension Rmax.
 // One CTA per core: d2_luar over columns (thread per column), then d2_lual over rows (thread per row).
 __global__ void k_quad_lua(DevPlan P) {
+    tl_stamp(P, 12);
     if (P.ctrl->ready) return;
     const int p = P.c_lo + blockIdx.x;
     const int r0 = P.rk[p - 1], r1 = P.rk[p];
@@ -1136,6 +1281,7 @@ __device__ __forceinline__ void mat_mul(const double* A, int m, int kdim, const 
     }
 }
 __global__ void k_quad_chain(DevPlan P) {
+    tl_stamp(P, 13);
     const int v = P.v0 + blockIdx.x;
     const int first = P.own[v];
     int last = P.own[v + 1] - 1;
@@ -1157,6 +1303,7 @@ __global__ void k_quad_chain(DevPlan P) {
     }
 }
 __global__ void k_quad_tree(DevPlan P) {
+    tl_stamp(P, 14);
     const i64 msz = (i64)P.Rmax * P.Rmax;
     for (int q = 1; q < P.P; q *= 2) {
         for (int me = 0; me < P.P; me += 2 * q) {
@@ -1180,7 +1327,8 @@ __global__ void k_quad_tree(DevPlan P) {
 }
 
 // finalisation: dtt_lua on the real cores, in place (dmrgg.f90:1248-1257)
-__global__ void k_lua_r(DevPlan P) {   // d2_luar(n*r1, r0, inv(p-1)): thread per column (j,k)
+__global__ void k_lua_r(DevPlan P) {
+    tl_stamp(P, 15);   // d2_luar(n*r1, r0, inv(p-1)): thread per column (j,k)
     const int p = P.c_lo + blockIdx.y;
     const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
     if (r0 < 2) return;
@@ -1197,7 +1345,8 @@ __global__ void k_lua_r(DevPlan P) {   // d2_luar(n*r1, r0, inv(p-1)): thread pe
         }
     }
 }
-__global__ void k_lua_l(DevPlan P) {   // d2_lual(r0*n, r1, inv(p)): thread per row (i,j); cores 1..d-1
+__global__ void k_lua_l(DevPlan P) {
+    tl_stamp(P, 16);   // d2_lual(r0*n, r1, inv(p)): thread per row (i,j); cores 1..d-1
     const int p = P.c_lo + blockIdx.y;
     if (p >= P.d) return;
     const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
@@ -1218,6 +1367,7 @@ __global__ void k_lua_l(DevPlan P) {   // d2_lual(r0*n, r1, inv(p)): thread per 
 }
 // padded -> packed copy of one core for ttc_core()
 __global__ void k_pack_core(DevPlan P, int p, double* out) {
+    tl_stamp(P, 17);
     const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
     const double* a = P.arg + P.coreOff[p];
     const i64 tot = (i64)r0 * n * r1;
@@ -1232,6 +1382,7 @@ __global__ void k_pack_core(DevPlan P, int p, double* out) {
 // ----------------------------------------------------------------------------
 template <int KIND>
 __global__ void k_init_search(DevPlan P, int nn, int snum, double* b) {
+    tl_stamp(P, 18);
     extern __shared__ double smem[];
     const double* A = stage_aux<KIND>(P, smem);
     for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < nn * snum; x += gridDim.x * blockDim.x) {
@@ -1242,6 +1393,7 @@ __global__ void k_init_search(DevPlan P, int nn, int snum, double* b) {
 // fiber of core p through the initial cross: arg(p)(1,j,1) = f(ind0 with position p := j); tables hold pivot 1 already
 template <int KIND>
 __global__ void k_init_cross(DevPlan P) {
+    tl_stamp(P, 19);
     extern __shared__ double smem[];
     const int p = blockIdx.y + 1;
     const double* A = stage_aux<KIND>(P, smem);
@@ -1270,6 +1422,19 @@ constexpr unsigned FULLMASK = 0xffffffffu;
 template <class GF>
 __device__ __forceinline__ void warp_luar(double (&y)[MAXRPL], int r, GF g) {
     const int lane = threadIdx.x & 31;
+    if (r <= 32) {          // one row per lane: no slot selection on the chain, coefficient loads issued ahead of it
+        double y0 = y[0], tmp0 = 0.0;
+        const bool in = lane < r;
+#pragma unroll 4
+        for (int u = 0; u + 1 < r; ++u) {
+            const double gsu = (in && lane > u) ? g(lane, u) : 0.0;
+            const double yu = __shfl_sync(FULLMASK, y0, u);
+            if (in && lane > u) tmp0 = tmp0 + yu * gsu;
+            if (lane == u + 1) y0 = y0 + (-tmp0);
+        }
+        y[0] = y0;
+        return;
+    }
     double tmp[MAXRPL];
 #pragma unroll
     for (int t = 0; t < MAXRPL; ++t) tmp[t] = 0.0;
@@ -1292,6 +1457,21 @@ __device__ __forceinline__ void warp_luar(double (&y)[MAXRPL], int r, GF g) {
 template <class GF, class DF>
 __device__ __forceinline__ void warp_lual(double (&y)[MAXRPL], int r, GF g, DF dinv) {
     const int lane = threadIdx.x & 31;
+    if (r <= 32) {
+        double y0 = y[0];
+        const bool in = lane < r;
+        const double di = in ? dinv(lane) : 0.0;
+        if (r > 0 && lane == 0) y0 = di * y0;
+#pragma unroll 4
+        for (int u = 0; u + 1 < r; ++u) {
+            const double gcu = (in && lane > u) ? g(lane, u) : 0.0;
+            const double yu = __shfl_sync(FULLMASK, y0, u);
+            if (in && lane > u) y0 = y0 + (-gcu) * yu;
+            if (lane == u + 1) y0 = di * y0;
+        }
+        y[0] = y0;
+        return;
+    }
     if (r > 0 && lane == 0) y[0] = dinv(0) * y[0];
     for (int u = 0; u + 1 < r; ++u) {
         double yu = 0.0;
@@ -1329,6 +1509,7 @@ __device__ __forceinline__ void stage_lual(const double* g, int r, double* T, do
 // ttqq(p)(i,k) = sum_j arg(p)(i,j,k)*w(j): CTA (k, p) stages the slice arg(p)(:,:,k) chunk by chunk with all threads
 // (deep memory-level parallelism), then r0 threads run the ordered sums out of shared memory.
 __global__ void k_quad_contract_sm(DevPlan P, int use_weights, int chunk_doubles) {
+    tl_stamp(P, 20);
     extern __shared__ double smem[];
     const int p = P.c_lo + blockIdx.y, k = blockIdx.x;
     const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
@@ -1352,6 +1533,7 @@ __global__ void k_quad_contract_sm(DevPlan P, int use_weights, int chunk_doubles
 // dtt_lua on the contracted cores: one CTA per core, matrix and both packed LUs staged in shared memory,
 // one warp per column (d2_luar) then one warp per row (d2_lual).  Requires r <= 32*MAXRPL.
 __global__ void k_quad_lua_sm(DevPlan P) {
+    tl_stamp(P, 21);
     extern __shared__ double smem[];
     if (P.ctrl->ready) return;
     const int p = P.c_lo + blockIdx.x;
@@ -1402,6 +1584,7 @@ __device__ __forceinline__ void mat_load_sm(const double* g, int m, int n, int l
 }
 // chain product per virtual rank (dmrgg.f90:1323-1345): CTA v, three shared buffers of Rmax^2
 __global__ void k_quad_chain_sm(DevPlan P) {
+    tl_stamp(P, 22);
     extern __shared__ double smem[];
     const int v = P.v0 + blockIdx.x;
     const int first = P.own[v];
@@ -1427,6 +1610,7 @@ __global__ void k_quad_chain_sm(DevPlan P) {
 }
 // binary tree over virtual ranks (dmrgg.f90:1355-1405): level `q`, CTA per receiving rank; launched once per level
 __global__ void k_quad_tree_sm(DevPlan P, int q, int last_level) {
+    tl_stamp(P, 23);
     extern __shared__ double smem[];
     const int me = blockIdx.x * 2 * q, her = me + q;
     const int ld = P.Rmax;
@@ -1445,6 +1629,154 @@ __global__ void k_quad_tree_sm(DevPlan P, int q, int last_level) {
         for (int e = threadIdx.x; e < m * n; e += blockDim.x) { int j = e / m, i = e - j * m; out[i + (i64)ld * j] = C[i + ld * j]; }
         if (last_level && me == 0 && threadIdx.x == 0) P.sweep_out->val = C[0];
     }
+}
+
+// ----------------------------------------------------------------------------
+// Incremental per-sweep quadrature (dmrgg.f90:975-993: ttqq = arg x weights, dtt_lua(ttqq), dtt_quad(ttqq)).
+// A sweep appends at most one row and one column to every contracted core; every entry of the contracted,
+// luar'd and lual'd core is a fixed sequence of operations on data that never changes once written (the raw
+// fibers and the packed LUs only grow), so the old entries are bit-identical to a recomputation and only the
+// new row i = e0 and the new column k = e1 are evaluated: O((r0 + r1) * (n + r)) instead of O(r0 * r1 * (n + r)).
+//   Y = after d2_luar(inv(p-1)) on every column, Z = after d2_lual(inv(p)) on every row (Z = Y for the last core).
+// One CTA per own core; qext[p] = extents already done.  Needs r <= 32*MAXRPL.
+// ----------------------------------------------------------------------------
+__global__ void k_quad_inc(DevPlan P, int use_weights, int stage_doubles) {
+    tl_stamp(P, 34);
+    if (P.ctrl->ready) return;
+    extern __shared__ double smem[];
+    const int p = P.c_lo + blockIdx.x;
+    const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
+    const int e0 = P.qext[2 * p], e1 = P.qext[2 * p + 1];
+    if (e0 == r0 && e1 == r1) return;
+    if (r0 - e0 > 1 || r1 - e1 > 1 || r0 < e0 || r1 < e1) { if (threadIdx.x == 0) P.ctrl->error = 2; return; }
+    const bool grow_row = r0 > e0, grow_col = r1 > e1;
+    const double* a = P.arg + P.coreOff[p];
+    const double* w = P.quadw + P.quadOff[p];
+    double* Y = P.ttqy + (i64)p * P.Rmax * P.Rmax;
+    double* Z = P.ttqq + (i64)p * P.Rmax * P.Rmax;
+    const double* gl = P.inv + (i64)(p - 1) * P.Rmax * P.Rmax;
+    const double* gr = P.inv + (i64)p * P.Rmax * P.Rmax;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int ld = P.Rmax, R = P.Rmax;
+    // shared: TL[R*R] luar table of inv(p-1) | TR[R*R] lual table of inv(p) | DI[R] | rawcol[R] | rawrow[R] |
+    //         YS[R*R] old Y (ld e0) | ZS[R*R] old Z (ld e0) | stage[...]
+    double* TL = smem; double* TR = TL + R * R; double* DI = TR + R * R; double* rawcol = DI + R; double* rawrow = rawcol + R;
+    double* YS = rawrow + R; double* ZS = YS + R * R; double* stg = ZS + R * R;
+    stage_luar(gl, r0, TL);
+    if (p < P.d) stage_lual(gr, r1, TR, DI);
+    for (int k = wid; k < e1; k += nw)
+        for (int u = lane; u < e0; u += 32) { YS[u + e0 * k] = Y[u + ld * k]; ZS[u + e0 * k] = Z[u + ld * k]; }
+    tl_mark0(P, 60);
+    // 1. raw contractions of the new column (all rows) and of the new row (all columns), dgemv 'n' order of
+    //    dmrgg.f90:986-991: y = 0; y = y + w(j) * a(., j, .) for ascending j.  One thread per entry (the sum is a
+    //    sequential chain by definition); the operands are staged chunk by chunk by the whole CTA with
+    //    independent loads in flight.
+    const int ncol = grow_col ? r0 : 0, nrow = grow_row ? r1 : 0;
+    int JC = (stage_doubles - 8) / (ncol + nrow + 1) - 1;
+    if (JC > n) JC = n;
+    const int half = blockDim.x >> 1;
+    const bool col_thread = (int)threadIdx.x < ncol, row_thread = (int)threadIdx.x >= half && (int)threadIdx.x - half < nrow;
+    double y = 0.0;
+    for (int j0 = 0; j0 < n; j0 += JC) {
+        const int jc = min(JC, n - j0);
+        double* WS = stg; double* Sc = WS + jc; double* Sr = Sc + ncol * jc;      // WS[jj], Sc[i + ncol*jj], Sr[k*(jc+1) + jj]
+        for (int jj = threadIdx.x; jj < jc; jj += blockDim.x) WS[jj] = use_weights ? w[j0 + jj] : 1.0;
+        const double* ac = a + (i64)R * n * e1 + (i64)R * j0;
+        constexpr int MB = 8;                                            // loads in flight per thread
+        for (int i0 = 0; i0 < ncol; i0 += 32) {
+            const int i = min(i0 + lane, ncol - 1);
+            for (int jb = wid; jb < jc; jb += MB * nw) {
+                double vv[MB];
+#pragma unroll
+                for (int u = 0; u < MB; ++u) vv[u] = ac[i + (i64)R * min(jb + u * nw, jc - 1)];
+#pragma unroll
+                for (int u = 0; u < MB; ++u) { const int jj = jb + u * nw; if (jj < jc && i0 + lane < ncol) Sc[i + ncol * jj] = vv[u]; }
+            }
+        }
+        const double* ar = a + e0 + (i64)R * j0;
+        for (int k = wid; k < nrow; k += nw) {
+            const double* ark = ar + (i64)R * n * k;
+            double* srk = Sr + k * (jc + 1);
+            for (int jb = lane; jb < jc; jb += MB * 32) {
+                double vv[MB];
+#pragma unroll
+                for (int u = 0; u < MB; ++u) vv[u] = ark[(i64)R * min(jb + u * 32, jc - 1)];
+#pragma unroll
+                for (int u = 0; u < MB; ++u) { const int jj = jb + u * 32; if (jj < jc) srk[jj] = vv[u]; }
+            }
+        }
+        __syncthreads();
+        tl_mark0(P, 61);
+        if (col_thread) {
+            const double* sc = Sc + threadIdx.x;
+            if (use_weights) {
+#pragma unroll 8
+                for (int jj = 0; jj < jc; ++jj) y = y + WS[jj] * sc[ncol * jj];
+            } else {
+#pragma unroll 8
+                for (int jj = 0; jj < jc; ++jj) y = y + sc[ncol * jj];
+            }
+        } else if (row_thread) {
+            const double* sr = Sr + (threadIdx.x - half) * (jc + 1);
+            if (use_weights) {
+#pragma unroll 8
+                for (int jj = 0; jj < jc; ++jj) y = y + WS[jj] * sr[jj];
+            } else {
+#pragma unroll 8
+                for (int jj = 0; jj < jc; ++jj) y = y + sr[jj];
+            }
+        }
+        __syncthreads();
+        tl_mark0(P, 62);
+    }
+    if (col_thread) rawcol[threadIdx.x] = y;
+    if (row_thread) rawrow[threadIdx.x - half] = y;
+    __syncthreads();
+    // 2. d2_luar: new column as a wavefront chain (warp 0); new row element of every old column (the other warps)
+    if (grow_col && wid == 0) {
+        double yy[MAXRPL];
+#pragma unroll
+        for (int t = 0; t < MAXRPL; ++t) { int sidx = lane + 32 * t; yy[t] = (sidx < r0) ? rawcol[sidx] : 0.0; }
+        warp_luar(yy, r0, GSm{TL, r0});
+#pragma unroll
+        for (int t = 0; t < MAXRPL; ++t) { int sidx = lane + 32 * t; if (sidx < r0) Y[sidx + ld * e1] = yy[t]; }
+    }
+    if (grow_row && wid >= 1) {
+        for (int k = (int)threadIdx.x - 32; k < e1; k += blockDim.x - 32) {
+            double tmp = 0.0;
+            const double* yk = YS + e0 * k;
+#pragma unroll 8
+            for (int u = 0; u < e0; ++u) tmp = tmp + yk[u] * TL[u * r0 + e0];
+            Y[e0 + ld * k] = (e0 > 0) ? rawrow[k] + (-tmp) : rawrow[k];
+        }
+    }
+    __syncthreads();
+    tl_mark0(P, 63);
+    // 3. d2_lual (not for the last core): new row as a wavefront chain; new column element of every old row
+    if (p < P.d) {
+        if (grow_row && wid == 0) {
+            double yy[MAXRPL];
+#pragma unroll
+            for (int t = 0; t < MAXRPL; ++t) { int c = lane + 32 * t; yy[t] = (c < r1) ? Y[e0 + ld * c] : 0.0; }
+            warp_lual(yy, r1, GSm{TR, r1}, DSm{DI});
+#pragma unroll
+            for (int t = 0; t < MAXRPL; ++t) { int c = lane + 32 * t; if (c < r1) Z[e0 + ld * c] = yy[t]; }
+        }
+        if (grow_col && wid >= 1) {
+            for (int i = (int)threadIdx.x - 32; i < e0; i += blockDim.x - 32) {
+                double val = Y[i + ld * e1];
+#pragma unroll 8
+                for (int u = 0; u < e1; ++u) val = val + (-TR[u * r1 + e1]) * ZS[i + e0 * u];
+                val = DI[e1] * val;
+                Z[i + ld * e1] = val;
+            }
+        }
+    } else {
+        if (grow_col) for (int i = threadIdx.x; i < r0; i += blockDim.x) Z[i + ld * e1] = Y[i + ld * e1];
+        if (grow_row) for (int k = threadIdx.x; k < r1; k += blockDim.x) Z[e0 + ld * k] = Y[e0 + ld * k];
+    }
+    if (threadIdx.x == 0) { P.qext[2 * p] = r0; P.qext[2 * p + 1] = r1; }
+    tl_mark0(P, 64);
 }
 
 // ----------------------------------------------------------------------------
@@ -1487,6 +1819,7 @@ __device__ __forceinline__ void run_ext_lual(const ExtJob& J, double* sm) {
 }
 // neighbour factors after an accepted pivot (dmrgg.f90:715-749)
 __global__ void k_update_nbr_w(DevPlan P, int dir, int pp) {
+    tl_stamp(P, 24);
     extern __shared__ double smem[];
     if (P.ctrl->ready) return;
     const int v = P.v0 + blockIdx.y;
@@ -1511,6 +1844,7 @@ __global__ void k_update_nbr_w(DevPlan P, int dir, int pp) {
 }
 // factor extensions of the neighbour exchange (dmrgg.f90:939-951, dmrggmp.f90:616-626)
 __global__ void k_exchange_extend_w(DevPlan P) {
+    tl_stamp(P, 25);
     extern __shared__ double smem[];
     if (P.ctrl->ready) return;
     const int b = first_boundary(P) + blockIdx.y;
@@ -1536,6 +1870,7 @@ __global__ void k_exchange_extend_w(DevPlan P) {
 }
 // finalisation with wavefronts: d2_luar over the n*r1 columns, then d2_lual over the r0*n rows of every core
 __global__ void k_lua_r_w(DevPlan P) {
+    tl_stamp(P, 26);
     extern __shared__ double smem[];
     const int p = P.c_lo + blockIdx.y;
     const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
@@ -1547,6 +1882,7 @@ __global__ void k_lua_r_w(DevPlan P) {
     run_ext_luar(J, smem);
 }
 __global__ void k_lua_l_w(DevPlan P) {
+    tl_stamp(P, 27);
     extern __shared__ double smem[];
     const int p = P.c_lo + blockIdx.y;
     if (p >= P.d) return;
@@ -1573,6 +1909,7 @@ __global__ void k_lua_l_w(DevPlan P) {
 // factors of the initial cross (dmrgg.f90:234-248): inv(p)(1) = pivot, col(p) = arg(p)/pivot (d2_lual, r = 1),
 // row(p) = arg(p) (d2_luar with r = 1 is the identity).  blockIdx.y = core - 1.
 __global__ void k_init_factors(DevPlan P) {
+    tl_stamp(P, 28);
     const int p = blockIdx.y + 1;
     const int n = P.n[p];
     const double* a = P.arg + P.coreOff[p];
@@ -1610,6 +1947,7 @@ __host__ __device__ __forceinline__ int mb2_slot_doubles(int Rmax) { return Rmax
 
 // grid: nv + 2 CTAs.  CTA b < nv: mailbox slot of virtual rank v0+b.  CTA nv: slab for the left process.  CTA nv+1: right.
 __global__ void k_mp_pack1(DevPlan P) {
+    tl_stamp(P, 29);
     if (P.ctrl->ready) return;
     const int it = P.ctrl->it;
     const int b = blockIdx.x;
@@ -1644,6 +1982,7 @@ __global__ void k_mp_pack1(DevPlan P) {
 // grid: P CTAs, CTA v handles foreign virtual rank v: state + visit records, then the replay of its accepted pivots
 // (the index-set half of k_accept) in visit order.
 __global__ void k_mp_unpack1(DevPlan P) {
+    tl_stamp(P, 30);
     if (P.ctrl->ready) return;
     const int v = blockIdx.x;
     if (own_vrank(P, v)) return;
@@ -1680,6 +2019,7 @@ __global__ void k_mp_unpack1(DevPlan P) {
 // grid: (NB, 2).  y = 0: what the left process sent (new row of core own[v0] + inv of its last bond);
 // y = 1: what the right process sent (new column slab of core own[v0+nv]).  Runs after k_mp_unpack1 (ranks replayed).
 __global__ void k_mp_unpack1b(DevPlan P) {
+    tl_stamp(P, 31);
     if (P.ctrl->ready) return;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     if (blockIdx.y == 0) {
@@ -1704,6 +2044,7 @@ __global__ void k_mp_unpack1b(DevPlan P) {
 // phase 2 (after the corner evaluations and the per-rank quadrature chains): chain products, amax, neval, error flag
 // final != 0: the collective ttc_quad after the run (not gated by the ready flag; only the chain products travel)
 __global__ void k_mp_pack2(DevPlan P, int final) {
+    tl_stamp(P, 32);
     if (!final && P.ctrl->ready) return;
     const int b = blockIdx.x, v = P.v0 + b;
     const int msz = P.Rmax * P.Rmax;
@@ -1718,6 +2059,7 @@ __global__ void k_mp_pack2(DevPlan P, int final) {
     }
 }
 __global__ void k_mp_unpack2(DevPlan P, int final) {
+    tl_stamp(P, 33);
     if (!final && P.ctrl->ready) return;
     const int v = blockIdx.x;
     if (own_vrank(P, v)) return;
@@ -1734,4 +2076,5 @@ __global__ void k_mp_unpack2(DevPlan P, int final) {
     }
 }
 
+static const char* const tl_names[] = {"k_lot", "k_fiber", "k_superblock", "k_accept", "k_update_main", "k_update_nbr", "k_allreduce", "k_run_begin", "k_sweep_log", "k_exchange_corner", "k_exchange_extend", "k_quad_contract", "k_quad_lua", "k_quad_chain", "k_quad_tree", "k_lua_r", "k_lua_l", "k_pack_core", "k_init_search", "k_init_cross", "k_quad_contract_sm", "k_quad_lua_sm", "k_quad_chain_sm", "k_quad_tree_sm", "k_update_nbr_w", "k_exchange_extend_w", "k_lua_r_w", "k_lua_l_w", "k_init_factors", "k_mp_pack1", "k_mp_unpack1", "k_mp_unpack1b", "k_mp_pack2", "k_mp_unpack2", "k_quad_inc"};
 }  // namespace ttc

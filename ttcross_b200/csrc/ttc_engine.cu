@@ -12,6 +12,7 @@
 // =============================================================================
 #include "../../include/ttcross_b200.h"
 #include "ttc_device.cuh"
+#include "ttc_visit.cuh"
 #include "ttc_nccl.hpp"
 
 #include <algorithm>
@@ -86,8 +87,8 @@ std::string fmt_e(double v, int w, int dgt) {
 
 struct PivRec { int it, vrank, bond, ii, jj, kk, qq, upd; double pivot; };
 
-enum KClass { KC_LOT = 0, KC_FIBER, KC_REDUCE, KC_SUPERBLOCK, KC_ACCEPT, KC_UPDATE, KC_NBR, KC_EXCHANGE, KC_QUAD, KC_INIT, KC_FINAL, KC_MISC, KC_COUNT };
-const char* kclass_names[KC_COUNT] = {"lottery_eval", "fiber_eval_residual", "argmax_reduce", "superblock", "accept", "rank1_update",
+enum KClass { KC_VISITS = 0, KC_LOT, KC_FIBER, KC_REDUCE, KC_SUPERBLOCK, KC_ACCEPT, KC_UPDATE, KC_NBR, KC_EXCHANGE, KC_QUAD, KC_INIT, KC_FINAL, KC_MISC, KC_COUNT };
+const char* kclass_names[KC_COUNT] = {"bond_visits_cluster", "lottery_eval", "fiber_eval_residual", "argmax_reduce", "superblock", "accept", "rank1_update",
                                       "neighbour_factors", "exchange", "quadrature", "init", "finalise", "misc"};
 
 }  // namespace
@@ -129,10 +130,13 @@ struct ttc_handle {
     int no_graph = 0;
     bool use_wave = true;                // warp-wavefront / shared-memory support kernels (needs Rmax <= 32*MAXRPL)
     size_t sm_contract = 0, sm_lua = 0, sm_mat3 = 0, sm_ext = 0, sm_lot = 0, sm_fiber = 0, sm_sb = 0;
-    int force_sync = 0, force_host_lottery = 0, force_simple = 0;
+    int force_sync = 0, force_host_lottery = 0, force_simple = 0, force_split = 0;
+    size_t sm_qinc = 0; int qinc_stage = 0;
+    int cluster_size = 8, cluster_threads = 512; size_t sm_visit = 0; bool cluster_ok = false;
     int nsm = 148;
     // core blocks over processes (one per GPU): NCCL communicator of ttc_comm_init, this process's rank
     NcclComm comm = nullptr; int nproc = 1, prank = 0;
+    int timeline = 0; unsigned long long* tlog_d = nullptr; int* tlog_n_d = nullptr;
     size_t mb1_bytes = 0, mb2_count = 0, nbl_send = 0, nbl_recv = 0;   // message sizes per process / neighbour
 
     std::vector<int> setup_sig;
@@ -420,6 +424,7 @@ int setup_device(ttc_handle* h, int maxrank) {
     TRY(dev_alloc(h, &dpart, (size_t)P * 2 * GMAX));
     TRY(dev_alloc(h, &dst, (size_t)P)); TRY(dev_alloc(h, &dout, (size_t)P)); TRY(dev_alloc(h, &dsw, 1));
     TRY(dev_alloc(h, &dttqq, (size_t)(d + 1) * Rmax * Rmax));
+    { double* dttqy; int* dqext; TRY(dev_alloc(h, &dttqy, (size_t)(d + 1) * Rmax * Rmax)); TRY(dev_alloc(h, &dqext, (size_t)2 * (d + 2))); h->plan.ttqy = dttqy; h->plan.qext = dqext; }
     TRY(dev_alloc(h, &dch, (size_t)(P + 1) * Rmax * Rmax)); TRY(dev_alloc(h, &dch2, (size_t)(P + 1) * Rmax * Rmax));
 #undef TRY
     D.n = dn; D.own = down; D.par = dpar; D.aux = daux; D.Lidx = dL; D.Ridx = dR; D.offL = doffL; D.offR = doffR;
@@ -481,6 +486,13 @@ int setup_device(ttc_handle* h, int maxrank) {
         h->sm_mat3 = 3 * R * R * sizeof(double);
         h->sm_ext = (R * R + R) * sizeof(double);
         if (h->sm_lua > 200 * 1024) h->use_wave = false;
+        {   // k_quad_inc: two packed-LU tables + a staging area for the new row and column (as much as fits in ~96 KB)
+            const size_t fixed = (4 * R * R + 3 * R) * sizeof(double);
+            size_t stage = std::min<size_t>((size_t)(2 * R + 1) * (h->nmax + 1) + 64, (64 * 1024) / sizeof(double));
+            if (fixed + stage * sizeof(double) > 200 * 1024) h->use_wave = false;
+            h->qinc_stage = (int)stage; h->sm_qinc = fixed + stage * sizeof(double);
+            if (h->use_wave) cudaFuncSetAttribute(k_quad_inc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_qinc);
+        }
         if (h->use_wave) {
             cudaFuncSetAttribute(k_quad_contract_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_contract);
             cudaFuncSetAttribute(k_quad_lua_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_lua);
@@ -492,6 +504,24 @@ int setup_device(ttc_handle* h, int maxrank) {
             cudaFuncSetAttribute(k_lua_l_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_ext);
         }
     }
+    // cluster kernel of the bond visits (ttc_visit.cuh): needs the staged evaluation inputs and the wavefront updates
+    {
+        if (const char* e = std::getenv("TTC_CLUSTER_SIZE")) h->cluster_size = std::atoi(e);
+        if (const char* e = std::getenv("TTC_CLUSTER_THREADS")) h->cluster_threads = std::atoi(e);
+        if (h->kind == TTC_MVN && !std::getenv("TTC_CLUSTER_THREADS")) h->cluster_threads = 256;
+        h->sm_visit = ((size_t)D.auxsm + Rmax + (size_t)Rmax * Rmax + Rmax + D.stage_max) * sizeof(double) + (size_t)(4 * Rmax + 8) * sizeof(int);
+        h->cluster_ok = D.stage && h->use_wave && h->sm_visit <= 200 * 1024 && h->cluster_size >= 1 && h->cluster_size <= MAXCS && h->cluster_threads >= 32 &&
+                        h->cluster_threads <= VISIT_MAXTHREADS && h->cluster_threads % 32 == 0 &&
+                        !std::getenv("TTC_NO_CLUSTER");
+        if (h->cluster_ok) {
+            cudaError_t ce = cudaSuccess;
+            KIND_SWITCH(h->kind,
+                ce = cudaFuncSetAttribute(k_visits<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_visit);
+                if (ce == cudaSuccess && h->cluster_size > 8) ce = cudaFuncSetAttribute(k_visits<K>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            );
+            if (ce != cudaSuccess) { (void)cudaGetLastError(); h->cluster_ok = false; }
+        }
+    }
     // opt in to more than 48 KB of dynamic shared memory where the staging areas need it
     {
         const int bl = (int)h->sm_lot, bf = (int)h->sm_fiber, bs = (int)h->sm_sb, ba = (int)aux_smem(h);
@@ -501,7 +531,8 @@ int setup_device(ttc_handle* h, int maxrank) {
                                   cudaFuncSetAttribute(k_fiber<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf); }
             if (bs > 48 * 1024) { cudaFuncSetAttribute(k_superblock<K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs);
                                   cudaFuncSetAttribute(k_superblock<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs); }
-            if (ba > 48 * 1024) { cudaFuncSetAttribute(k_exchange_corner<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba);
+            if (ba + 16 * h->d > 48 * 1024) cudaFuncSetAttribute(k_exchange_corner<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba + 16 * h->d);
+            if (ba > 48 * 1024) {
                                   cudaFuncSetAttribute(k_init_search<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba);
                                   cudaFuncSetAttribute(k_init_cross<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba); }
         );
@@ -607,8 +638,13 @@ int launch_quad(ttc_handle* h, Launcher& L, bool with_lua, bool use_weights, int
         L(KC_QUAD, [&] { k_quad_tree<<<1, 256, 0, s>>>(D); });
         return 0;
     }
-    L(KC_QUAD, [&] { k_quad_contract_sm<<<dim3(R, ncore), 256, h->sm_contract, s>>>(D, use_weights ? 1 : 0, (int)(h->sm_contract / sizeof(double))); });
-    if (with_lua) L(KC_QUAD, [&] { k_quad_lua_sm<<<ncore, 512, h->sm_lua, s>>>(D); });
+    if (with_lua && !h->force_split) {
+        // per-sweep path: only the new row / column of every contracted core (k_quad_inc)
+        L(KC_QUAD, [&] { k_quad_inc<<<ncore, 256, h->sm_qinc, s>>>(D, use_weights ? 1 : 0, h->qinc_stage); });
+    } else {
+        L(KC_QUAD, [&] { k_quad_contract_sm<<<dim3(R, ncore), 256, h->sm_contract, s>>>(D, use_weights ? 1 : 0, (int)(h->sm_contract / sizeof(double))); });
+        if (with_lua) L(KC_QUAD, [&] { k_quad_lua_sm<<<ncore, 512, h->sm_lua, s>>>(D); });
+    }
     L(KC_QUAD, [&] { k_quad_chain_sm<<<D.nv, 512, h->sm_mat3, s>>>(D); });
     if (h->nproc > 1) { int e = mp_phase2(h, L, final); if (e) return e; }
     for (int q = 1; q < h->P; q *= 2) {
@@ -666,6 +702,11 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     char line[512];
 
     D.piv = h->piv;
+    if (h->timeline) {
+        if (!h->tlog_d) { CUDA_TRY(h, cudaMalloc((void**)&h->tlog_d, 3 * 65536 * sizeof(unsigned long long))); CUDA_TRY(h, cudaMalloc((void**)&h->tlog_n_d, sizeof(int))); }
+        CUDA_TRY(h, cudaMemsetAsync(h->tlog_n_d, 0, sizeof(int), s));
+        D.tlog = h->tlog_d; D.tlog_n = h->tlog_n_d; D.tlog_cap = 65536;
+    } else { D.tlog = nullptr; D.tlog_n = nullptr; D.tlog_cap = 0; }
     CUDA_TRY(h, cudaEventRecord(h->ev0, s));
     L(KC_MISC, [&] { k_run_begin<<<1, 32, 0, s>>>(D, h->seed, accuracy >= 0 ? 1 : 0, accuracy); });
 
@@ -730,6 +771,8 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     // ---- initial cross fibers and factors (dmrgg.f90:220-248)
     KIND_SWITCH(h->kind, L(KC_INIT, [&] { k_init_cross<K><<<dim3(cdiv(h->nmax, TB), d), TB, smA, s>>>(D); }));
     L(KC_INIT, [&] { k_init_factors<<<dim3(cdiv(h->nmax, 256), d), 256, 0, s>>>(D); });
+    if (has_quad && h->use_wave && !h->force_split)      // contracted cores of the rank-1 train: extents (1,1) for the incremental quadrature
+        L(KC_INIT, [&] { k_quad_inc<<<D.c_hi - D.c_lo + 1, 256, h->sm_qinc, s>>>(D, 1, h->qinc_stage); });
     // fibers back to the host for the scalar bookkeeping of the '0::' line
     std::vector<std::vector<double>> fib(d + 1);
     for (int p = 1; p <= d; ++p) fib[p].resize(h->n[p]);
@@ -869,14 +912,32 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         }
         return 0;
     };
+    // one cluster per virtual rank runs the whole visit list of the sweep (ttc_visit.cuh) when the lottery is on the device
+    const bool use_cluster = h->cluster_ok && !sync_mode && dev_lot && h->piv >= 0 && !h->force_split;
     auto enqueue_sweep = [&](int dir, int rb) -> int {
         if (sync_mode) h->rks_h = h->rk_h;
-        for (int pp = 1; pp <= maxnb; ++pp) { int e = enqueue_visit(dir, pp, rb); if (e) return e; }
+        if (use_cluster) {
+            cudaLaunchConfig_t cfg;
+            std::memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3(h->cluster_size, NV, 1);
+            cfg.blockDim = dim3(h->cluster_threads, 1, 1);
+            cfg.dynamicSmemBytes = h->sm_visit;
+            cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = h->cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaError_t ce = cudaSuccess;
+            KIND_SWITCH(h->kind, L(KC_VISITS, [&] { ce = cudaLaunchKernelEx(&cfg, k_visits<K>, D, dir, small_element, small_pivot, multi ? 0 : 1); }));
+            CUDA_TRY(h, ce);
+        } else {
+            for (int pp = 1; pp <= maxnb; ++pp) { int e = enqueue_visit(dir, pp, rb); if (e) return e; }
+        }
         if (P > 1) {
             if (multi) { int e = mp_phase1(h, L); if (e) return e; }
             const int nbnd = boundary_count(D);
-            L(KC_EXCHANGE, [&] { k_allreduce<<<1, 32, 0, s>>>(D); });
-            KIND_SWITCH(h->kind, L(KC_EXCHANGE, [&] { k_exchange_corner<K><<<dim3(1, nbnd), TB, smA, s>>>(D); }));
+            if (multi || !use_cluster) L(KC_EXCHANGE, [&] { k_allreduce<<<1, 32, 0, s>>>(D); });
+            KIND_SWITCH(h->kind, L(KC_EXCHANGE, [&] { k_exchange_corner<K><<<dim3(1, nbnd), TB, smA + 2 * (size_t)d * sizeof(double), s>>>(D); }));
             if (h->use_wave) L(KC_EXCHANGE, [&] { k_exchange_extend_w<<<dim3(cdiv(h->nmax, 8), nbnd, 2), 256, h->sm_ext, s>>>(D); });
             else L(KC_EXCHANGE, [&] { k_exchange_extend<<<dim3(cdiv(2 * h->nmax, 64), nbnd), 64, 0, s>>>(D); });
         }
@@ -894,7 +955,8 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     const bool use_graph = !sync_mode && !h->profile && !h->no_graph && (!multi || std::getenv("TTC_MP_GRAPH") != nullptr);
     if (use_graph) {
         std::vector<long long> gsig = {(long long)h->piv, (long long)has_quad, (long long)maxrank, (long long)h->use_wave, (long long)dev_lot,
-                                       (long long)h->setup_serial};
+                                       (long long)h->setup_serial, (long long)h->timeline, (long long)use_cluster,
+                                       (long long)h->cluster_size, (long long)h->cluster_threads};
         if (gsig != h->graph_sig) {
             for (int gdir = 0; gdir < 2; ++gdir) {
                 if (h->gexec[gdir]) { cudaGraphExecDestroy(h->gexec[gdir]); h->gexec[gdir] = nullptr; }
@@ -970,6 +1032,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     // ---- read the logs back and rebuild the reference's report
     Ctrl ctrl;
     CUDA_TRY(h, cudaMemcpy(&ctrl, D.ctrl, sizeof ctrl, cudaMemcpyDeviceToHost));
+    if (ctrl.error == 2) { h->err = "internal: the incremental quadrature saw a rank grow by more than one in a sweep"; return TTC_ERR_STATE; }
     if (ctrl.error) { h->err = "rank capacity exceeded (pass maxrank)"; return TTC_ERR_RANK; }
     it = ctrl.nsweeps;
     {
@@ -1063,6 +1126,7 @@ void ttc_destroy(ttc_handle* h) {
     if (h->stream || !h->allocs.empty()) { cudaSetDevice(h->device); free_device(h); }
     if (h->comm) { cudaSetDevice(h->device); nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->flush_d) cudaFree(h->flush_d);
+    if (h->tlog_d) { cudaFree(h->tlog_d); cudaFree(h->tlog_n_d); }
     delete h;
 }
 
@@ -1095,11 +1159,29 @@ int ttc_set_seed(ttc_handle* h, unsigned long long seed) { if (!h) return TTC_ER
 int ttc_set_uniform_callback(ttc_handle* h, ttc_uniform_cb cb, void* ctx) { if (!h) return TTC_ERR_ARG; h->ucb = cb; h->ucb_ctx = ctx; return TTC_OK; }
 int ttc_set_verbose(ttc_handle* h, int v) { if (!h) return TTC_ERR_ARG; h->verbose = v; return TTC_OK; }
 int ttc_set_lottery_mode(ttc_handle* h, int mode) {
-    if (!h || mode < 0 || mode > 3) return TTC_ERR_ARG;
+    if (!h || mode < 0 || mode > 4) return TTC_ERR_ARG;
     h->force_host_lottery = (mode == 1); h->force_sync = (mode == 1 || mode == 2);
     h->force_simple = (mode == 3);      // 3: the plain (non-wavefront) support kernels, asynchronous
+    h->force_split = (mode == 4);       // 4: one kernel per step of a bond visit instead of the cluster kernel
     h->setup_sig.clear();
     return TTC_OK;
+}
+int ttc_set_timeline(ttc_handle* h, int on) { if (!h) return TTC_ERR_ARG; h->timeline = on; return TTC_OK; }
+long ttc_timeline(const ttc_handle* h, long cap, int* ids, unsigned long long* t_ns, const char** names, int names_cap) {
+    if (!h || !h->tlog_d) return 0;
+    int n = 0;
+    cudaMemcpy(&n, h->tlog_n_d, sizeof n, cudaMemcpyDeviceToHost);
+    n = std::min(n, 65536);
+    std::vector<unsigned long long> buf(3 * (size_t)n);
+    if (n) cudaMemcpy(buf.data(), h->tlog_d, buf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    for (long i = 0; i < std::min<long>(n, cap); ++i) {
+        if (ids) ids[i] = (int)buf[3 * i];
+        if (t_ns) t_ns[i] = buf[3 * i + 1];
+        if (t_ns && cap >= 2 * (long)n) t_ns[n + i] = buf[3 * i + 2];      // SM cycle counters after the timestamps
+    }
+    const int nn = (int)(sizeof(tl_names) / sizeof(tl_names[0]));
+    for (int i = 0; names && i < std::min(nn, names_cap); ++i) names[i] = tl_names[i];
+    return n;
 }
 int ttc_set_profile(ttc_handle* h, int on) { if (!h) return TTC_ERR_ARG; h->profile = on; return TTC_OK; }
 

@@ -1,0 +1,482 @@
+// =============================================================================
+// ttc_visit.cuh — one thread-block CLUSTER per virtual rank runs all bond visits of a sweep.
+//
+// A bond visit of the rook search (dmrgg.f90:410-758) is a chain of 6-7 tiny dependent steps
+// (lottery -> up to 2*piv cross fibers -> accept -> rank-1 update), each a few thousand integrand
+// evaluations followed by a first-index argmax.  As separate kernels every step pays a launch, a
+// grid ramp, a chain of dependent global loads for the geometry, and a last-CTA reduction through
+// HBM (measured on B200: ~10 us per fiber step, ~100 us per visit).  Here the whole visit list of a
+// virtual rank lives in ONE kernel: the cluster's CTAs split every fiber, argmax partials are
+// exchanged through distributed shared memory, and the steps are separated by the hardware
+// cluster barrier.  Scalar state (pivot candidate, amax, neval, RNG position) is replicated in
+// every CTA's shared memory and advanced identically from the same reduced partials.
+//
+// Arithmetic, summation orders and tie-breaks are those of ttc_device.cuh (bit-identical results).
+// Data that other CTAs of the cluster may have written earlier in the same kernel (ranks, index
+// tables, packed LUs, factor cores, fiber buffers) is read with ld.global.cg (L2) so no SM ever
+// sees a stale L1 line; visibility is ordered by __threadfence + barrier.cluster (release/acquire).
+// =============================================================================
+#pragma once
+#include "ttc_device.cuh"
+#include <cooperative_groups.h>
+
+namespace ttc {
+namespace cg = cooperative_groups;
+
+constexpr int MAXCS = 16;     // largest cluster the hardware allows (non-portable size)
+
+struct VisitShared {
+    Partial xpart[2][2][MAXCS];   // [phase parity][raw|res][CTA rank]; only CTA 0's copy is used
+    Partial red[2];
+    Partial shp[32];
+    LotSeg seg[2][MAXSEG];
+    int ns[2], nz[2];
+    VState S;
+    int r0, r1, r2;
+};
+
+// ---- L2 (cache-global) variants of the residual / staging helpers of ttc_device.cuh
+__device__ __forceinline__ double resid_axpy_cg(double f, const double* base, i64 stride, const double* xs, int r) {
+    double res = f;
+    int s0 = 0;
+    for (; s0 + RU <= r; s0 += RU) {
+        double a[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) a[u] = __ldcg(base + (s0 + u) * stride);
+#pragma unroll
+        for (int u = 0; u < RU; ++u) res = res + (-xs[s0 + u]) * a[u];
+    }
+    for (; s0 < r; ++s0) res = res + (-xs[s0]) * __ldcg(base + s0 * stride);
+    return res;
+}
+__device__ __forceinline__ double resid_dot_cg(double f, const double* base, i64 stride, const double* xs, int r) {
+    double t = 0.0;
+    int s0 = 0;
+    for (; s0 + RU <= r; s0 += RU) {
+        double a[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) a[u] = __ldcg(base + (s0 + u) * stride);
+#pragma unroll
+        for (int u = 0; u < RU; ++u) t = t + a[u] * xs[s0 + u];
+    }
+    for (; s0 < r; ++s0) t = t + __ldcg(base + s0 * stride) * xs[s0];
+    return f + (-t);
+}
+__device__ __forceinline__ double resid_ddot2_cg(double f, const double* c, i64 cs, const double* r, i64 rs, int r1) {
+    double t = 0.0;
+    int s0 = 0;
+    for (; s0 + RU <= r1; s0 += RU) {
+        double a[RU], b[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) { a[u] = __ldcg(c + (s0 + u) * cs); b[u] = __ldcg(r + (s0 + u) * rs); }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) t = t + a[u] * b[u];
+    }
+    for (; s0 < r1; ++s0) t = t + __ldcg(c + s0 * cs) * __ldcg(r + s0 * rs);
+    return f - t;
+}
+// residuals with the first RP factor values loaded BEFORE the evaluation (their L2 round trip hides behind it)
+constexpr int RP = 16;
+struct Pref { double a[RP]; };
+__device__ __forceinline__ void pref_load(Pref& pf, const double* base, i64 stride, int r) {
+#pragma unroll
+    for (int u = 0; u < RP; ++u) pf.a[u] = __ldcg(base + min(u, r - 1) * stride);   // clamped, never predicated: all in flight at once
+}
+__device__ __forceinline__ double resid_axpy_pf(double f, const Pref& pf, const double* base, i64 stride, const double* xs, int r) {
+    double res = f;
+#pragma unroll
+    for (int u = 0; u < RP; ++u) if (u < r) res = res + (-xs[u]) * pf.a[u];
+    for (int s0 = RP; s0 < r; s0 += RP) {
+        double a[RP];
+#pragma unroll
+        for (int u = 0; u < RP; ++u) a[u] = __ldcg(base + min(s0 + u, r - 1) * stride);
+#pragma unroll
+        for (int u = 0; u < RP; ++u) if (s0 + u < r) res = res + (-xs[s0 + u]) * a[u];
+    }
+    return res;
+}
+__device__ __forceinline__ double resid_dot_pf(double f, const Pref& pf, const double* base, i64 stride, const double* xs, int r) {
+    double t = 0.0;
+#pragma unroll
+    for (int u = 0; u < RP; ++u) if (u < r) t = t + pf.a[u] * xs[u];
+    for (int s0 = RP; s0 < r; s0 += RP) {
+        double a[RP];
+#pragma unroll
+        for (int u = 0; u < RP; ++u) a[u] = __ldcg(base + min(s0 + u, r - 1) * stride);
+#pragma unroll
+        for (int u = 0; u < RP; ++u) if (s0 + u < r) t = t + a[u] * xs[s0 + u];
+    }
+    return f + (-t);
+}
+// stage_bond of ttc_device.cuh with the index tables read through L2 (they grow during the kernel)
+__device__ __forceinline__ Stage stage_bond_cg(const DevPlan& P, double* sm, int pl, int rl, int c1, int c2, int pr, int rr) {
+    Stage S;
+    const int n1 = P.n[c1], n2 = c2 ? P.n[c2] : 0;
+    const int nl = pl, nr = P.d - pr;
+    const bool hasw = (P.kind == KIND_ISING);
+    const int nwoff = P.n[1];
+    double* NX = sm; double* NW = NX + n1; double* NX2 = NW + n1; double* NW2 = NX2 + n2;
+    double* XL = NW2 + n2; double* WL = XL + nl * rl; double* XR = WL + nl * rl; double* WR = XR + nr * rr;
+    for (int x = threadIdx.x; x < n1; x += blockDim.x) { NX[x] = P.par[x]; NW[x] = hasw ? P.par[nwoff + x] : 0.0; }
+    for (int x = threadIdx.x; x < n2; x += blockDim.x) { NX2[x] = P.par[x]; NW2[x] = hasw ? P.par[nwoff + x] : 0.0; }
+    const int* L = P.Lidx + P.offL[pl];
+    for (int x = threadIdx.x; x < nl * rl; x += blockDim.x) {
+        int pos = x / rl, t = x - pos * rl;
+        int idx = __ldcg(L + (i64)pos * P.Rmax + t);
+        XL[x] = P.par[idx - 1]; WL[x] = hasw ? P.par[nwoff + idx - 1] : 0.0;
+    }
+    const int* R = P.Ridx + P.offR[pr];
+    for (int x = threadIdx.x; x < nr * rr; x += blockDim.x) {
+        int pos = x / rr, t = x - pos * rr;
+        int idx = __ldcg(R + (i64)pos * P.Rmax + t);
+        XR[x] = P.par[idx - 1]; WR[x] = hasw ? P.par[nwoff + idx - 1] : 0.0;
+    }
+    __syncthreads();
+    S.NX = NX; S.NW = NW; S.NX2 = NX2; S.NW2 = NW2; S.XL = XL; S.WL = WL; S.XR = XR; S.WR = WR;
+    S.nl = nl; S.rl = rl; S.nr = nr; S.rr = rr; S.hask = c2 ? 1 : 0;
+    return S;
+}
+__device__ __forceinline__ void stage_luar_cg(const double* g, int r, double* T) {
+    for (int x = threadIdx.x; x < r * r; x += blockDim.x) { int s = x / r, u = x - s * r; if (u < s) T[u * r + s] = __ldcg(g + (i64)s * s + u); }
+}
+__device__ __forceinline__ void stage_lual_cg(const double* g, int r, double* T, double* dinv) {
+    for (int x = threadIdx.x; x < r * r; x += blockDim.x) { int c = x / r, u = x - c * r; if (u < c) T[u * r + c] = __ldcg(g + (i64)(c + 1) * (c + 1) - (c + 1) + u); }
+    for (int c = threadIdx.x; c < r; c += blockDim.x) dinv[c] = 1.0 / __ldcg(g + (i64)(c + 1) * (c + 1) - 1);
+}
+
+// first-index argmax over the whole cluster; every thread of every CTA returns with the folded (raw, res).
+// One cluster barrier per call: the exchange area is double-buffered by call parity.
+__device__ __forceinline__ void cluster_fold(cg::cluster_group& cl, VisitShared& sh, int& phase, Partial& raw, Partial& res) {
+    raw = amax_block(raw, sh.shp);
+    res = amax_block(res, sh.shp);
+    const int buf = phase & 1;
+    ++phase;
+    const int cs = (int)cl.num_blocks();
+    VisitShared* lead = cl.map_shared_rank(&sh, 0);
+    if (threadIdx.x == 0) {
+        lead->xpart[buf][0][cl.block_rank()] = raw;
+        lead->xpart[buf][1][cl.block_rank()] = res;
+    }
+    cl.sync();                  // barrier.cluster arrive.release / wait.acquire: the fiber stores above are visible to the cluster
+    if (threadIdx.x < 32) {
+        Partial a = amax_init(), b = amax_init();
+        if ((int)threadIdx.x < cs) { a = lead->xpart[buf][0][threadIdx.x]; b = lead->xpart[buf][1][threadIdx.x]; }
+        a = amax_warp(a);
+        b = amax_warp(b);
+        if (threadIdx.x == 0) { sh.red[0] = a; sh.red[1] = b; }
+    }
+    __syncthreads();
+    raw = sh.red[0];
+    res = sh.red[1];
+}
+
+// ----------------------------------------------------------------------------
+// all bond visits of one sweep direction for the virtual ranks of this process (pivoting >= 0).
+// grid (CS, nv), cluster (CS, 1, 1).  dynamic smem: A[auxsm] | xs[Rmax] | ext[Rmax^2 + Rmax] | stage[stage_max] | ints[4*Rmax + 8]
+// fold_allreduce != 0: the last cluster to finish performs the MAX reduction of dmrgg.f90:852-870 (single process only).
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void tl_mark(const DevPlan& P, int id) {     // diagnostic: phase stamps of the first cluster
+    if (P.tlog && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        int k = atomicAdd(P.tlog_n, 1);
+        if (k < P.tlog_cap) { P.tlog[3 * k] = (unsigned long long)id; P.tlog[3 * k + 1] = t; P.tlog[3 * k + 2] = (unsigned long long)clock64(); }
+    }
+}
+constexpr int VISIT_MAXTHREADS = 512;
+template <int KIND>
+__global__ void __launch_bounds__(VISIT_MAXTHREADS, 1) k_visits(DevPlan P, int dir, double small_element, double small_pivot, int fold_allreduce) {
+    tl_stamp(P, 40);
+    if (__ldcg(&P.ctrl->ready)) return;          // uniform over the grid: written only by k_sweep_log
+    cg::cluster_group cl = cg::this_cluster();
+    extern __shared__ double smem[];
+    __shared__ VisitShared sh;
+    const int crank = (int)cl.block_rank(), cs = (int)cl.num_blocks();
+    const int v = P.v0 + blockIdx.y;
+    const int lo = P.own[v], hi = P.own[v + 1], nb = hi - lo;
+    const int it = P.ctrl->it;
+    const int gtid = crank * blockDim.x + threadIdx.x, gthreads = cs * blockDim.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const double* A = stage_aux<KIND>(P, smem);
+    double* xs = smem + P.auxsm;
+    double* ext = xs + P.Rmax;
+    double* stg = ext + (i64)P.Rmax * P.Rmax + P.Rmax;
+    int* ibuf = (int*)(stg + P.stage_max);
+    if (threadIdx.x == 0) sh.S = P.st[v];
+    int phase = 0;
+    double* fa_c = P.acol1 + (i64)v * P.Rmax * P.nmax; double* fb_c = P.bcol1 + (i64)v * P.Rmax * P.nmax;
+    double* fa_r = P.arow1 + (i64)v * P.Rmax * P.nmax; double* fb_r = P.brow1 + (i64)v * P.Rmax * P.nmax;
+
+    for (int pp = 1; pp <= nb; ++pp) {
+        const int p = (dir == 1) ? lo + pp - 1 : hi - pp;
+        if (threadIdx.x == 0) {
+            sh.r0 = (p - 1 >= lo) ? __ldcg(P.rk + p - 1) : P.rks[p - 1];
+            sh.r1 = __ldcg(P.rk + p);
+            sh.r2 = (p + 1 <= hi - 1) ? __ldcg(P.rk + p + 1) : P.rks[p + 1];
+        }
+        __syncthreads();
+        const int r0 = sh.r0, r1 = sh.r1, r2 = sh.r2, n1 = P.n[p], n2 = P.n[p + 1];
+        const Stage S = stage_bond_cg(P, stg, p - 1, r0, p, p + 1, p + 1, r2);
+        tl_mark(P, 41);
+        const double* colp = P.col + P.coreOff[p];
+        const double* rowp = P.rowT + P.coreOff[p + 1];
+        const i64 cs_ = (i64)P.Rmax * n1;        // stride of s in col(i,j,s)
+        const i64 rs_ = (i64)n2 * P.Rmax;        // stride of s in rowT(s,k,q)
+        const int ccount = r0 * n1, rcount = n2 * r2;
+
+        // ---- lottery candidates (dmrgg.f90:425-490)
+        {
+            const int nlot = r0 + n1 + n2 + r2;
+            int* tmp = ibuf; int* zc = ibuf + 2 * P.Rmax; int* zr = ibuf + 3 * P.Rmax;
+            const int* vip_p = P.vip + (i64)p * P.Rmax * 4;
+            const int m = ccount, n = rcount;
+            lot_zeros2(vip_p, r1, r0, n2, tmp, zc, zr, sh.nz);
+            if (threadIdx.x == 0) sh.ns[0] = build_segments(m - sh.nz[0], sh.seg[0]);
+            if (threadIdx.x == 32) sh.ns[1] = build_segments(n - sh.nz[1], sh.seg[1]);
+            __syncthreads();
+            tl_mark(P, 42);
+            const unsigned long long k0 = sh.S.rng_k, seed = P.ctrl->seed;
+            Partial braw = amax_init(), bres = amax_init();
+            // a lane pair shares one candidate: the even lane draws its column cell, the odd lane its row cell (the two
+            // bisections are the long serial part of a candidate), then the even lane evaluates
+            for (int x0 = 0; x0 < nlot; x0 += gthreads / 2) {
+                const int x = x0 + (gtid >> 1);
+                const int side = gtid & 1;
+                const bool live = x < nlot;
+                int cell = 1;
+                if (live) {
+                    const double uu = stream_uniform(seed, v, k0 + (unsigned long long)(side ? nlot + x : x));
+                    cell = side ? lot_draw(sh.seg[1], sh.ns[1], n - sh.nz[1], n, zr, sh.nz[1], uu)
+                                : lot_draw(sh.seg[0], sh.ns[0], m - sh.nz[0], m, zc, sh.nz[0], uu);
+                }
+                const int w = __shfl_down_sync(FULLMASK, cell, 1);
+                if (!live || side) continue;
+                const int c = cell;
+                const int i = (c - 1) % r0 + 1, j = (c - 1) / r0 + 1, k = (w - 1) % n2 + 1, q = (w - 1) / n2 + 1;
+                StagedVals sv = S.point(i, j, k, q);
+                const double f = eval_point<KIND>(P, sv, A);
+                const double res = resid_ddot2_cg(f, colp + (i - 1) + (i64)P.Rmax * (j - 1), cs_, rowp + (k - 1) + (i64)n2 * (q - 1), rs_, r1);
+                amax_take(braw, f, x);
+                amax_take(bres, res, x);
+            }
+ tl_mark(P, 43);
+            cluster_fold(cl, sh, phase, braw, bres);
+            tl_mark(P, 44);
+            if (threadIdx.x == 0) {
+                VState& St = sh.S;
+                St.amax = fmax(St.amax, braw.absv);
+                const int x = (int)bres.idx;         // the winner's cell is a pure function of its draw number
+                const double uc = stream_uniform(seed, v, k0 + (unsigned long long)x);
+                const double ur = stream_uniform(seed, v, k0 + (unsigned long long)(nlot + x));
+                const int c = lot_draw(sh.seg[0], sh.ns[0], m - sh.nz[0], m, zc, sh.nz[0], uc);
+                const int w = lot_draw(sh.seg[1], sh.ns[1], n - sh.nz[1], n, zr, sh.nz[1], ur);
+                St.ii = (c - 1) % r0 + 1; St.jj = (c - 1) / r0 + 1; St.kk = (w - 1) % n2 + 1; St.qq = (w - 1) / n2 + 1;
+                St.pivot = bres.val;
+                St.done = 0; St.havecol = 0; St.haverow = 0; St.crs = 0; St.upd = 0;
+                St.neval += nlot;
+                St.rng_k += 2ULL * (unsigned long long)nlot;
+            }
+            __syncthreads();
+        }
+
+        // ---- cross fibers: piv = 0 one column + one row (dmrgg.f90:492-513), piv >= 1 the rook loop (:515-582)
+        const int nfib = (P.piv == 0) ? 2 : 2 * P.piv;
+        int isrow = (P.piv == 0) ? 0 : ((dir == 2) ? 1 : 0);
+        for (int c = 0; c < nfib; ++c, isrow ^= 1) {
+            if (sh.S.done) break;                                   // uniform over the cluster
+            const int ii = sh.S.ii, jj = sh.S.jj, kk = sh.S.kk, qq = sh.S.qq;
+            __syncthreads();                                        // xs of the previous fiber no longer read
+            for (int s = threadIdx.x; s < r1; s += blockDim.x)
+                xs[s] = isrow ? __ldcg(colp + (ii - 1) + (i64)P.Rmax * (jj - 1) + s * cs_) : __ldcg(rowp + (kk - 1) + (i64)n2 * (qq - 1) + s * rs_);
+            __syncthreads();
+            tl_mark(P, 50);
+            const int count = isrow ? rcount : ccount;
+            double* fa = isrow ? fa_r : fa_c;
+            double* fb = isrow ? fb_r : fb_c;
+            Partial braw = amax_init(), bres = amax_init();
+            for (int e = gtid; e < count; e += gthreads) {
+                double f, res;
+                Pref pf;
+                if (!isrow) {
+                    const int j = e / r0 + 1, i = e % r0 + 1;
+                    const double* base = colp + (i - 1) + (i64)P.Rmax * (j - 1);
+                    pref_load(pf, base, cs_, r1);
+                    StagedVals sv = S.point(i, j, kk, qq);
+                    f = eval_point<KIND>(P, sv, A);
+                    res = resid_axpy_pf(f, pf, base, cs_, xs, r1);
+                } else {
+                    const int q = e / n2 + 1, k = e % n2 + 1;
+                    const double* base = rowp + (k - 1) + (i64)n2 * (q - 1);
+                    pref_load(pf, base, rs_, r1);
+                    StagedVals sv = S.point(ii, jj, k, q);
+                    f = eval_point<KIND>(P, sv, A);
+                    res = resid_dot_pf(f, pf, base, rs_, xs, r1);
+                }
+                fa[e] = f;
+                fb[e] = res;
+                amax_take(braw, f, e);
+                amax_take(bres, res, e);
+            }
+            tl_mark(P, 45);
+            cluster_fold(cl, sh, phase, braw, bres);
+            tl_mark(P, 46);
+            if (threadIdx.x == 0) {                                 // dmrgg.f90:527-547, 560-580
+                VState& St = sh.S;
+                St.neval += count;
+                if (P.piv == 0) {
+                    St.havecol = 1; St.haverow = 1;
+                    if (c == 1) St.done = 1;
+                } else {
+                    St.amax = fmax(St.amax, braw.absv);
+                    if (isrow) St.haverow = 1; else St.havecol = 1;
+                    St.crs += 1;
+                    int done = St.havecol && St.haverow && (St.crs >= 2 * P.piv);
+                    if (!done) {
+                        const int e = (int)bres.idx;
+                        if (!isrow) {
+                            const int j = e / r0 + 1, i = e % r0 + 1;
+                            done = St.havecol && St.haverow && (i == St.ii && j == St.jj);
+                            St.ii = i; St.jj = j;
+                        } else {
+                            const int q = e / n2 + 1, k = e % n2 + 1;
+                            done = St.havecol && St.haverow && (k == St.kk && q == St.qq);
+                            St.kk = k; St.qq = q;
+                        }
+                        St.pivot = bres.val;
+                    }
+                    St.done = done;
+                }
+            }
+            __syncthreads();
+        }
+
+        tl_mark(P, 47);
+        // ---- accept test and index-set update (dmrgg.f90:598-660); every CTA takes the same decision
+        const int ii = sh.S.ii, jj = sh.S.jj, kk = sh.S.kk, qq = sh.S.qq;
+        const double pivot = sh.S.pivot;
+        const double ap = fabs(pivot);
+        int upd = (ap > small_element * sh.S.amax) && (ap > small_pivot * sh.S.pivotmax_prev);
+        if (upd && r1 >= P.Rmax) { upd = 0; if (crank == 0 && threadIdx.x == 0) P.ctrl->error = 1; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            VState& St = sh.S;
+            St.upd = upd;
+            if (upd) {
+                St.pivotmax = (St.pivotmax < 0.0) ? ap : fmax(St.pivotmax, ap);
+                St.pivotmin = (St.pivotmin < 0.0) ? ap : fmin(St.pivotmin, ap);
+            }
+            if (crank == 0) {
+                VisitOut& O = P.vlog[((i64)(it - 1) * P.maxnb + (pp - 1)) * P.P + v];
+                O.active = 1; O.upd = upd; O.bond = p; O.ii = ii; O.jj = jj; O.kk = kk; O.qq = qq; O.pivot = pivot;
+            }
+        }
+        if (upd) {
+            const int t = r1;                                       // 0-based slot of the new pivot
+            if (crank == 0) {
+                if (threadIdx.x == 0) { int* vp = P.vip + ((i64)p * P.Rmax + t) * 4; vp[0] = ii; vp[1] = jj; vp[2] = kk; vp[3] = qq; }
+                int* Lp = P.Lidx + P.offL[p];
+                const int* Lm = P.Lidx + P.offL[p - 1];
+                for (int pos = threadIdx.x; pos < p; pos += blockDim.x)
+                    Lp[(i64)pos * P.Rmax + t] = (pos < p - 1) ? __ldcg(Lm + (i64)pos * P.Rmax + (ii - 1)) : jj;
+                int* Rp = P.Ridx + P.offR[p];
+                const int* Rn = P.Ridx + P.offR[p + 1];
+                for (int pos = threadIdx.x; pos < P.d - p; pos += blockDim.x)
+                    Rp[(i64)pos * P.Rmax + t] = (pos == 0) ? kk : __ldcg(Rn + (i64)(pos - 1) * P.Rmax + (qq - 1));
+                // packed LU: [ col(ii,jj,1:r) | row(1:r,kk,qq) | pivot ]
+                double* g = P.inv + (i64)p * P.Rmax * P.Rmax;
+                for (int s = threadIdx.x; s < r1; s += blockDim.x) {
+                    g[(i64)r1 * r1 + s] = __ldcg(colp + (ii - 1) + (i64)P.Rmax * (jj - 1) + s * cs_);
+                    g[(i64)r1 * r1 + r1 + s] = __ldcg(rowp + (kk - 1) + (i64)n2 * (qq - 1) + s * rs_);
+                }
+                if (threadIdx.x == 0) g[(i64)(r1 + 1) * (r1 + 1) - 1] = pivot;
+            }
+            // neighbour factors (dmrgg.f90:715-749): warps of the whole cluster run the chains as wavefronts
+            if (p > lo && r0 >= 1) {
+                stage_luar_cg(P.inv + (i64)(p - 1) * P.Rmax * P.Rmax, r0, ext);
+                __syncthreads();
+                double* dst = P.rowT + P.coreOff[p] + (i64)n1 * t;
+                const i64 de = (i64)n1 * P.Rmax;
+                for (int x = crank * nw + wid; x < n1; x += cs * nw) {
+                    double y[MAXRPL];
+#pragma unroll
+                    for (int u = 0; u < MAXRPL; ++u) { int sidx = lane + 32 * u; y[u] = (sidx < r0) ? __ldcg(fa_c + (i64)x * r0 + sidx) : 0.0; }
+                    warp_luar(y, r0, GSm{ext, r0});
+#pragma unroll
+                    for (int u = 0; u < MAXRPL; ++u) { int sidx = lane + 32 * u; if (sidx < r0) dst[x + sidx * de] = y[u]; }
+                }
+                __syncthreads();
+            }
+            if (p < hi - 1 && r2 >= 1) {
+                double* di = ext + r2 * r2;
+                stage_lual_cg(P.inv + (i64)(p + 1) * P.Rmax * P.Rmax, r2, ext, di);
+                __syncthreads();
+                double* dst = P.col + P.coreOff[p + 1] + t;
+                const i64 de = (i64)P.Rmax * n2;
+                for (int x = crank * nw + wid; x < n2; x += cs * nw) {
+                    double y[MAXRPL];
+#pragma unroll
+                    for (int u = 0; u < MAXRPL; ++u) { int c = lane + 32 * u; y[u] = (c < r2) ? __ldcg(fa_r + x + (i64)c * n2) : 0.0; }
+                    warp_lual(y, r2, GSm{ext, r2}, DSm{di});
+#pragma unroll
+                    for (int u = 0; u < MAXRPL; ++u) { int c = lane + 32 * u; if (c < r2) dst[(i64)x * P.Rmax + c * de] = y[u]; }
+                }
+                __syncthreads();
+            }
+            tl_mark(P, 48);
+            // rank-1 append (dmrgg.f90:663-713): the residuals of the last fibers ARE the lual/luar(from=r+1) eliminations
+            {
+                double* argp = P.arg + P.coreOff[p];
+                double* argn = P.arg + P.coreOff[p + 1];
+                double* colw = P.col + P.coreOff[p];
+                double* roww = P.rowT + P.coreOff[p + 1];
+                const double sc = 1.0 / pivot;
+                for (int e = gtid; e < ccount + rcount; e += gthreads) {
+                    if (e < ccount) {
+                        const int j = e / r0, i = e % r0;
+                        const i64 o = i + (i64)P.Rmax * (j + (i64)n1 * t);
+                        argp[o] = __ldcg(fa_c + e);
+                        colw[o] = sc * __ldcg(fb_c + e);
+                    } else {
+                        const int x = e - ccount;
+                        const int q = x / n2, k = x % n2;
+                        argn[t + (i64)P.Rmax * (k + (i64)n2 * q)] = __ldcg(fa_r + x);
+                        roww[k + (i64)n2 * (q + (i64)P.Rmax * t)] = __ldcg(fb_r + x);
+                    }
+                }
+            }
+            if (crank == 0 && threadIdx.x == 0) P.rk[p] = r1 + 1;
+        }
+        tl_mark(P, 49);
+        cl.sync();          // the next visit of this cluster (Gauss-Seidel, dmrgg.f90:329-331) sees everything written above
+    }
+    if (crank == 0) {
+        for (int pp = nb + threadIdx.x + 1; pp <= P.maxnb; pp += blockDim.x) {
+            VisitOut& O = P.vlog[((i64)(it - 1) * P.maxnb + (pp - 1)) * P.P + v];
+            O.active = 0; O.upd = 0;
+        }
+        if (threadIdx.x == 0) {
+            P.st[v] = sh.S;
+            if (fold_allreduce && P.P > 1) {
+                __threadfence();
+                const unsigned tk = atomicAdd(P.tickets + P.P, 1u);
+                if (tk == (unsigned)P.nv - 1) {
+                    P.tickets[P.P] = 0;
+                    __threadfence();
+                    volatile VState* st = P.st;
+                    double c1 = st[0].amax, c2 = st[0].pivotmax, c3 = (st[0].pivotmin > 0.0) ? -st[0].pivotmin : -999e9;
+                    for (int u = 1; u < P.P; ++u) {
+                        c1 = fmax(c1, st[u].amax); c2 = fmax(c2, st[u].pivotmax);
+                        const double pm = st[u].pivotmin;
+                        c3 = fmax(c3, (pm > 0.0) ? -pm : -999e9);
+                    }
+                    for (int u = 0; u < P.P; ++u) {
+                        st[u].amax = c1; st[u].pivotmax = c2;
+                        st[u].pivotmin = (-c3 == 999e9) ? -1.0 : -c3;
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace ttc
