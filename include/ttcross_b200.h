@@ -111,6 +111,11 @@ double ttc_stream_uniform(unsigned long long seed, int vrank, unsigned long long
  */
 int ttc_superblock_probe(ttc_handle* h, int bond, int store, int reps, long long* out_idx, double* out_val,
                          double* ms, long long* count);
+/* variant 0: the tiled kernel with the reference arithmetic (what ttc_dmrgg runs; same as ttc_superblock_probe);
+ * 1: the plain one-thread-per-element kernel (cross-check); 2: the tiled kernel with the K = r(p) residual update
+ * contracted into DFMA — NOT bit-exact, never used by ttc_dmrgg, measures the FP64 ceiling of the shape. */
+int ttc_superblock_probe_ex(ttc_handle* h, int bond, int store, int reps, int variant, long long* out_idx, double* out_val,
+                            double* ms, long long* count);
 /* Fiber kernel probe: column fiber (isrow=0) or row fiber (isrow=1) of bond p through pivot (ii,jj,kk,qq); returns
  * the fiber values (r(p-1)*n(p) or n(p+1)*r(p+1) doubles) and its residual. */
 int ttc_fiber_probe(ttc_handle* h, int bond, int isrow, int ii, int jj, int kk, int qq, double* fiber, double* resid,
@@ -123,6 +128,9 @@ long long ttc_launch_count(const ttc_handle* h);
 /* write `bytes` (> L2 size) of scratch HBM so the next timed run starts with a cold L2 (measurement hygiene) */
 int ttc_l2_flush(ttc_handle* h, long long bytes);
 double ttc_device_ms(const ttc_handle* h);
+/* measured FP64 ceiling of the device in TFLOP/s (roofline denominator of the evaluation / residual kernels):
+ * fma = 1 DFMA chains, fma = 0 separate DMUL + DADD chains (the reference arithmetic has no FMA contraction) */
+int ttc_fp64_peak(int device, int fma, double* tflops);
 /* per-kernel-class accounting of the last ttc_dmrgg: names[i] (static strings), launches, total ms (events, only when
  * profiling was enabled with ttc_set_profile(h, 1)) */
 int ttc_set_profile(ttc_handle* h, int on);

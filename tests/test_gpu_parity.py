@@ -97,3 +97,36 @@ def test_repeated_runs_reuse_buffers_and_agree():
     assert np.array_equal(g1.pivlog, g2.pivlog) and np.array_equal(g1.vals, g2.vals)
     for a, b in zip(c1, t.cores()):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("kind,index,n,R,P", [("c", 6, 20, 8, 1), ("c", 7, 12, 6, 2), ("d", 5, 12, 6, 1), ("e", 5, 10, 5, 1)])
+def test_superblock_kernels_agree(kind, index, n, R, P):
+    """The tiled superblock kernel (per-row / per-column partial recurrences, register-blocked residual) against the plain
+    one-thread-per-element kernel on the same device state: both argmaxes and both values bit for bit; the stored variant
+    too; the DFMA variant (not used by the sweep) within rounding."""
+    p = T.drivers.ising(kind, index, n)
+    t = p.make(); t.set_partition(P)
+    t.dmrgg(R, p.accuracy, 1)
+    for bond in range(1, p.d):
+        try:
+            a = t.superblock_probe(bond, variant=0)
+        except T.TTCrossError as e:
+            assert "another rank" in e.msg
+            continue
+        b = t.superblock_probe(bond, variant=1)
+        s = t.superblock_probe(bond, store=True, variant=0)
+        for key in ("argmax_a", "argmax_b", "a", "b", "count"):
+            assert a[key] == b[key] == s[key], (bond, key, a, b, s)
+        f = t.superblock_probe(bond, variant=2)
+        assert f["argmax_a"] == a["argmax_a"] and f["a"] == a["a"]
+        assert abs(f["b"] - a["b"]) <= 1e-12 * max(abs(a["a"]), 1e-300)
+
+
+def test_superblock_kernel_mvn_matches_plain():
+    p = T.drivers.mvn(4, 16)
+    t = p.make()
+    t.dmrgg(6, p.accuracy, 1)
+    for bond in range(1, p.d):
+        a, b = t.superblock_probe(bond, variant=0), t.superblock_probe(bond, variant=1)
+        for key in ("argmax_a", "argmax_b", "a", "b", "count"):
+            assert a[key] == b[key], (bond, key, a, b)

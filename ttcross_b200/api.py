@@ -73,6 +73,7 @@ def load_library(build_if_missing: bool = True):
     L.ttc_stream_uniform.restype = C.c_double
     L.ttc_stream_uniform.argtypes = [C.c_ulonglong, C.c_int, C.c_ulonglong]
     L.ttc_superblock_probe.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), _dp, _dp, C.POINTER(C.c_longlong)]
+    L.ttc_superblock_probe_ex.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), _dp, _dp, C.POINTER(C.c_longlong)]
     L.ttc_fiber_probe.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp]
     L.ttc_launch_count.restype = C.c_longlong
     L.ttc_launch_count.argtypes = [vp]
@@ -80,6 +81,7 @@ def load_library(build_if_missing: bool = True):
     L.ttc_device_ms.restype = C.c_double
     L.ttc_device_ms.argtypes = [vp]
     L.ttc_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_longlong), _dp]
+    L.ttc_fp64_peak.argtypes = [C.c_int, C.c_int, _dp]
     L.ttc_set_timeline.argtypes = [vp, C.c_int]
     L.ttc_timeline.restype = C.c_long
     L.ttc_timeline.argtypes = [vp, C.c_long, _ip, C.POINTER(C.c_ulonglong), C.POINTER(C.c_char_p), C.c_int]
@@ -115,6 +117,16 @@ class CrossResult:
     seconds: float
     device_ms: float
     launches: int
+
+
+def fp64_peak(device: int = 0, fma: bool = True) -> float:
+    """Measured FP64 ceiling of the device in TFLOP/s (DFMA chains, or separate DMUL + DADD when fma is False)."""
+    L = load_library()
+    v = C.c_double()
+    st = L.ttc_fp64_peak(device, int(fma), C.byref(v))
+    if st != 0:
+        raise TTCrossError(st, "ttc_fp64_peak failed (no CUDA device?)")
+    return v.value
 
 
 class TTCross:
@@ -258,12 +270,13 @@ class TTCross:
         return v.value
 
     # ---- probes
-    def superblock_probe(self, bond: int, store: bool = False, reps: int = 1):
+    def superblock_probe(self, bond: int, store: bool = False, reps: int = 1, variant: int = 0):
+        """variant 0: tiled kernel, reference arithmetic; 1: plain kernel; 2: tiled kernel with DFMA residual (not bit-exact)."""
         idx = (C.c_longlong * 2)()
         val = (C.c_double * 2)()
         ms = C.c_double()
         cnt = C.c_longlong()
-        self._check(self._L.ttc_superblock_probe(self.h, bond, int(store), reps, idx, val, C.byref(ms), C.byref(cnt)))
+        self._check(self._L.ttc_superblock_probe_ex(self.h, bond, int(store), reps, variant, idx, val, C.byref(ms), C.byref(cnt)))
         return {"argmax_a": idx[0], "argmax_b": idx[1], "a": val[0], "b": val[1], "ms": ms.value, "count": cnt.value}
 
     def fiber_probe(self, bond: int, isrow: bool, ii: int, jj: int, kk: int, qq: int, reps: int = 1):
@@ -297,7 +310,7 @@ class TTCross:
         special = {40: "k_visits", 100: "fold_done", 41: "v:staged", 42: "v:lot_setup", 43: "v:lot_eval", 44: "v:lot_fold",
                    45: "v:fiber_eval", 46: "v:fiber_fold", 47: "v:rook_done", 48: "v:nbr_done", 49: "v:append_done", 50: "f:xs_staged", 51: "f:pref_issued", 52: "f:eval_done",
                    53: "f:resid_done", 54: "f:stored", 34: "k_quad_inc", 60: "q:lu_staged", 61: "q:chunk_staged", 62: "q:chunk_summed",
-                   63: "q:luar_done", 64: "q:end"}
+                   63: "q:luar_done", 64: "q:end", 35: "k_superblock_t"}
         out = [(special.get(int(i), nm[i] if i < 64 else "?"), int(t)) for i, t in zip(ids[:n], ts[:n])]
         return sorted(out, key=lambda x: x[1])
 

@@ -13,6 +13,7 @@
 #include "../../include/ttcross_b200.h"
 #include "ttc_device.cuh"
 #include "ttc_visit.cuh"
+#include "ttc_superblock.cuh"
 #include "ttc_nccl.hpp"
 
 #include <algorithm>
@@ -132,6 +133,7 @@ struct ttc_handle {
     size_t sm_contract = 0, sm_lua = 0, sm_mat3 = 0, sm_ext = 0, sm_lot = 0, sm_fiber = 0, sm_sb = 0;
     int force_sync = 0, force_host_lottery = 0, force_simple = 0, force_split = 0;
     size_t sm_qinc = 0; int qinc_stage = 0;
+    size_t sm_sbt = 0; bool sbt_ok = false;      // tiled superblock kernel (ttc_superblock.cuh)
     int cluster_size = 8, cluster_threads = 512; size_t sm_visit = 0; bool cluster_ok = false;
     int nsm = 148;
     // core blocks over processes (one per GPU): NCCL communicator of ttc_comm_init, this process's rank
@@ -504,6 +506,21 @@ int setup_device(ttc_handle* h, int maxrank) {
             cudaFuncSetAttribute(k_lua_l_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_ext);
         }
     }
+    // tiled superblock kernel (ttc_superblock.cuh): column-factor slab + per-tile tables in shared memory
+    {
+        h->sm_sbt = ((size_t)D.auxsm + D.stage_max + sb_tile_doubles(Rmax, d)) * sizeof(double);
+        h->sbt_ok = D.stage && h->sm_sbt <= 200 * 1024 && !h->force_simple && !std::getenv("TTC_NO_TILED_SUPERBLOCK");
+        if (h->sbt_ok) {
+            cudaError_t ce = cudaSuccess;
+            const int bt = (int)h->sm_sbt;
+            KIND_SWITCH(h->kind,
+                ce = cudaFuncSetAttribute(k_superblock_t<K, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bt);
+                if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_superblock_t<K, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bt);
+                if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_superblock_t<K, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bt);
+            );
+            if (ce != cudaSuccess) { (void)cudaGetLastError(); h->sbt_ok = false; }
+        }
+    }
     // cluster kernel of the bond visits (ttc_visit.cuh): needs the staged evaluation inputs and the wavefront updates
     {
         if (const char* e = std::getenv("TTC_CLUSTER_SIZE")) h->cluster_size = std::atoi(e);
@@ -872,8 +889,14 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         }
         const int Gc = std::min(GMAX, cdiv(maxcol, TB)), Gr = std::min(GMAX, cdiv(maxrow, TB));
         if (h->piv == -1) {
-            const int Gs = (int)std::min<i64>(GMAX, std::max<i64>(1, (maxsb + TB - 1) / TB));
-            KIND_SWITCH(h->kind, L(KC_SUPERBLOCK, [&] { k_superblock<K, 0><<<dim3(Gs, NV), TB, smS, s>>>(D, dir, pp, 0, 0, nullptr, nullptr); }));
+            if (h->sbt_ok) {
+                const int nrb = cdiv(maxcol, SB_TM);
+                const int nsp = std::max(1, std::min({cdiv(2 * h->nsm, nrb * NV), cdiv(maxrow, SB_TN), GMAX / nrb}));
+                KIND_SWITCH(h->kind, L(KC_SUPERBLOCK, [&] { k_superblock_t<K, 0, 0><<<dim3(nrb, nsp, NV), SB_TM, h->sm_sbt, s>>>(D, dir, pp, 0, 0, nullptr, nullptr); }));
+            } else {
+                const int Gs = (int)std::min<i64>(GMAX, std::max<i64>(1, (maxsb + TB - 1) / TB));
+                KIND_SWITCH(h->kind, L(KC_SUPERBLOCK, [&] { k_superblock<K, 0><<<dim3(Gs, NV), TB, smS, s>>>(D, dir, pp, 0, 0, nullptr, nullptr); }));
+            }
             KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 0><<<dim3(Gc, NV), TB, smF, s>>>(D, dir, pp, 2); }));
             KIND_SWITCH(h->kind, L(KC_FIBER, [&] { k_fiber<K, 1><<<dim3(Gr, NV), TB, smF, s>>>(D, dir, pp, 2); }));
         } else {
@@ -1307,6 +1330,54 @@ void ttc_share(int first, int last, int nproc, int* own) {
 }
 double ttc_stream_uniform(unsigned long long seed, int vrank, unsigned long long k) { return stream_uniform(seed, vrank, k); }
 
+// FP64 pipe ceiling of this device, measured: 8 independent chains per thread, 16 warps per CTA, 2 CTAs per SM.
+// fma = 1: DFMA (2 flops per instruction); fma = 0: separate DMUL + DADD (the reference arithmetic).
+template <int FMA>
+__global__ void __launch_bounds__(512) k_fp64_peak(double* out, int iters, double seed) {
+    double a[8], b = seed, c = 1.0 - seed * 1e-9;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] = seed + u + threadIdx.x * 1e-6;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (FMA) a[u] = fma(a[u], c, b);
+                else { a[u] = a[u] * c; a[u] = a[u] + b; }
+            }
+        }
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) sum += a[u];
+    if (sum == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = sum;   // keeps the chains alive
+}
+int ttc_fp64_peak(int device, int fma, double* tflops) {
+    if (!tflops) return TTC_ERR_ARG;
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || device < 0 || device >= cnt) return TTC_ERR_CUDA;
+    cudaSetDevice(device);
+    int nsm = 0; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+    double* out = nullptr;
+    if (cudaMalloc((void**)&out, (size_t)nsm * 2 * 512 * sizeof(double)) != cudaSuccess) return TTC_ERR_CUDA;
+    const int iters = 20000;
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(a);
+        if (fma) k_fp64_peak<1><<<nsm * 2, 512>>>(out, iters, 0.5); else k_fp64_peak<0><<<nsm * 2, 512>>>(out, iters, 0.5);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0; cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+    if (cudaGetLastError() != cudaSuccess) return TTC_ERR_CUDA;
+    const double flops = (double)nsm * 2 * 512 * (double)iters * 64 * 2;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return TTC_OK;
+}
+
 int ttc_l2_flush(ttc_handle* h, long long bytes) {
     if (!h || bytes <= 0) return TTC_ERR_ARG;
     int st = check_device(h);
@@ -1341,8 +1412,14 @@ int ttc_profile(const ttc_handle* h, int cap, const char** names, long long* lau
     return KC_COUNT;
 }
 
+int ttc_superblock_probe_ex(ttc_handle* h, int bond, int store, int reps, int variant, long long* out_idx, double* out_val, double* ms, long long* count);
 int ttc_superblock_probe(ttc_handle* h, int bond, int store, int reps, long long* out_idx, double* out_val, double* ms, long long* count) {
-    if (!h || bond < 1 || bond > h->d - 1 || reps < 1) return TTC_ERR_ARG;
+    return ttc_superblock_probe_ex(h, bond, store, reps, 0, out_idx, out_val, ms, count);
+}
+// variant 0: tiled kernel, reference arithmetic (what ttc_dmrgg runs); 1: the plain one-thread-per-element kernel;
+// 2: tiled kernel with the residual update contracted into DFMA (not bit-exact; FP64 ceiling measurement only)
+int ttc_superblock_probe_ex(ttc_handle* h, int bond, int store, int reps, int variant, long long* out_idx, double* out_val, double* ms, long long* count) {
+    if (!h || bond < 1 || bond > h->d - 1 || reps < 1 || variant < 0 || variant > 2) return TTC_ERR_ARG;
     if (!h->ran) { h->err = "ttc_superblock_probe before ttc_dmrgg"; return TTC_ERR_STATE; }
     if (bond < h->own[h->plan.v0] || bond >= h->own[h->plan.v0 + h->plan.nv]) { h->err = "ttc_superblock_probe: bond belongs to another rank"; return TTC_ERR_STATE; }
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -1358,9 +1435,21 @@ int ttc_superblock_probe(ttc_handle* h, int bond, int store, int reps, long long
     // persistent-style grid: a few CTAs per SM, grid-stride over the superblock
     const int Gs = (int)std::min<i64>(GMAX, std::max<i64>(1, std::min<i64>((tot + TB - 1) / TB, (i64)h->nsm * (h->kind == TTC_MVN ? 8 : 6))));
     const size_t smA = aux_smem(h);
+    if (variant != 1 && !h->sbt_ok) { cudaFree(pout); if (a_out) cudaFree(a_out); h->err = "tiled superblock kernel unavailable for this shape"; return TTC_ERR_STATE; }
+    if (variant == 2 && store) { cudaFree(pout); if (a_out) cudaFree(a_out); h->err = "the DFMA variant has no stored form"; return TTC_ERR_ARG; }
+    const int m1 = h->rk_h[bond - 1] * h->n[bond], nc = h->n[bond + 1] * h->rk_h[bond + 1];
+    const int nrb = cdiv(m1, SB_TM);
+    const int nsp = std::max(1, std::min({cdiv(2 * h->nsm, nrb), cdiv(nc, SB_TN), GMAX / nrb}));
     auto launch = [&]() {
-        if (store) { KIND_SWITCH(h->kind, k_superblock<K, 1><<<Gs, TB, h->sm_sb, s>>>(D, 1, 1, bond, 0, a_out, pout)); }
-        else       { KIND_SWITCH(h->kind, k_superblock<K, 0><<<Gs, TB, h->sm_sb, s>>>(D, 1, 1, bond, 0, nullptr, pout)); }
+        if (variant == 1) {
+            if (store) { KIND_SWITCH(h->kind, k_superblock<K, 1><<<Gs, TB, h->sm_sb, s>>>(D, 1, 1, bond, 0, a_out, pout)); }
+            else       { KIND_SWITCH(h->kind, k_superblock<K, 0><<<Gs, TB, h->sm_sb, s>>>(D, 1, 1, bond, 0, nullptr, pout)); }
+        } else if (variant == 2) {
+            KIND_SWITCH(h->kind, k_superblock_t<K, 0, 1><<<dim3(nrb, nsp, 1), SB_TM, h->sm_sbt, s>>>(D, 1, 1, bond, 0, nullptr, pout));
+        } else {
+            if (store) { KIND_SWITCH(h->kind, k_superblock_t<K, 1, 0><<<dim3(nrb, nsp, 1), SB_TM, h->sm_sbt, s>>>(D, 1, 1, bond, 0, a_out, pout)); }
+            else       { KIND_SWITCH(h->kind, k_superblock_t<K, 0, 0><<<dim3(nrb, nsp, 1), SB_TM, h->sm_sbt, s>>>(D, 1, 1, bond, 0, nullptr, pout)); }
+        }
         h->launches += 1;
     };
     launch();   // warm-up
