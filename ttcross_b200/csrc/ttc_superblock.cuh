@@ -245,4 +245,27 @@ __global__ void __launch_bounds__(SB_TM) k_superblock_t(DevPlan P, int dir, int 
     }
 }
 
+// FP64 pipe ceiling of this device, measured: 8 independent chains per thread, 16 warps per CTA, 2 CTAs per SM.
+// fma = 1: DFMA (2 flops per instruction); fma = 0: separate DMUL + DADD (the reference arithmetic).
+template <int FMA>
+__global__ void __launch_bounds__(512) k_fp64_peak(double* out, int iters, double seed) {
+    double a[8], b = seed, c = 1.0 - seed * 1e-9;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] = seed + u + threadIdx.x * 1e-6;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (FMA) a[u] = fma(a[u], c, b);
+                else { a[u] = a[u] * c; a[u] = a[u] + b; }
+            }
+        }
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) sum += a[u];
+    if (sum == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = sum;   // keeps the chains alive
+}
+
 }  // namespace ttc
