@@ -7,7 +7,7 @@
 //
 // This is the one roofline-sized kernel of the path: 67.6 M evaluations and a 8224 x 8224 x 32 contraction
 // per bond visit at the C_10 shape.  Layout of the work:
-//   * a CTA owns TM = 256 consecutive rows (one per thread) and walks a range of columns in tiles of TN = 16;
+//   * a CTA owns TM = 256 consecutive rows (one per thread) and walks a range of columns in tiles of TN = 32;
 //   * the K x TM slab of the column factor stays in shared memory for the CTA's whole life; the K x TN slab of the row
 //     factor and the per-column integrand state are rebuilt per tile by a few threads;
 //   * every thread carries 8 columns at a time in registers: per step of the contraction one conflict-free shared load
@@ -27,7 +27,7 @@ namespace ttc {
 
 constexpr int SB_TM = 256;       // rows per CTA = threads per CTA
 constexpr int SB_CN = 8;         // columns a thread carries in registers
-constexpr int SB_TN = 16;        // columns per tile
+constexpr int SB_TN = 32;        // columns per tile
 constexpr int SB_MAXL = 8;       // left positions (+ the free mode) kept in registers on the fast Ising-C path
 
 __host__ __device__ __forceinline__ size_t sb_tile_doubles(int Rmax, int d) {
