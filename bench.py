@@ -218,24 +218,47 @@ def main():
     t.set_profile(False)
     tot_ms = sum(v[1] for v in prof.values())
     dom = max(prof.items(), key=lambda kv: kv[1][1])
-    # fiber kernel: per launch it reads the factor core (r*n*r(p) doubles) of every partition's bond and writes fiber+residual
+    # dominant kernel of the step: k_visits (ttc_visit.cuh) — one launch per sweep runs every bond visit of this GPU's
+    # partitions.  ALGORITHMIC bytes per launch (DESIGN.md "k_visits"): every lottery candidate reads 2*r(p) factor values,
+    # every fiber element reads r(p) factor values and writes fiber + residual (16 B), the rank-1 append re-reads and
+    # writes the last column and row fibers (32 B per element).  Ranks at sweep `it` are min(it, final rank) (one pivot per
+    # bond and sweep); all 2*piv rook steps are counted (upper bound), averaged over the sweeps of the step.
     ranks = g.ranks
     nn = int(prob.n[0])
-    fiber_bytes = 0.0
-    # algorithmic bytes per fiber launch at final ranks, averaged over column/row fibers of all partitions' bonds
-    per_bond = []
-    for p in range(1, prob.d):
-        r0, r1, r2 = int(ranks[p - 1]), int(ranks[p]), int(ranks[p + 1])
-        per_bond.append(8.0 * (r0 * nn * r1 + 2 * r0 * nn))       # column fiber: col core + acol1 + bcol1
-        per_bond.append(8.0 * (r1 * nn * r2 + 2 * nn * r2))       # row fiber
-    fiber_bytes = float(np.mean(per_bond)) * PARTITIONS / world       # partitions batched in one launch on this GPU
-    fl, fms = prof["fiber_eval_residual"]
-    fiber_avg_ms = fms / max(fl, 1)
-    achieved = fiber_bytes / (fiber_avg_ms * 1e-3) / 1e9
-    roofline = {"kernel": "k_fiber (column/row cross fiber + residual + argmax partials)", "bound": "hbm", "achieved": achieved,
-                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "share_of_step": fms / tot_ms if tot_ms else None, "avg_launch_us": 1e3 * fiber_avg_ms,
-                "note": "latency-bound by construction (<= 8224 evaluations per partition per launch, SURVEY F4); bytes at final ranks (upper bound)"}
+    own = T.multi.share(1, prob.d - 1, PARTITIONS)
+    v0, v1 = T.multi.block_of(PARTITIONS, world, rank)
+    my_bonds = list(range(int(own[v0]), int(own[v1])))
+    byt, flo = [], []
+    for it in range(1, int(g.nsweeps) + 1):
+        b = f = 0.0
+        for pb in my_bonds:
+            r0, r1, r2 = (min(it, int(ranks[q])) for q in (pb - 1, pb, pb + 1))
+            nlot, ncol, nrow = r0 + 2 * nn + r2, r0 * nn, nn * r2
+            ev = nlot + piv * (ncol + nrow)
+            b += nlot * 16.0 * r1 + piv * (ncol + nrow) * (8.0 * r1 + 16.0) + (ncol + nrow) * 32.0
+            f += ev * (5 * prob.d + 3 + 2 * r1)
+        byt.append(b)
+        flo.append(f)
+    dom_name = "bond_visits_cluster" if prof.get("bond_visits_cluster", (0, 0))[0] else "fiber_eval_residual"
+    fl, fms = prof[dom_name]
+    dom_avg_ms = fms / max(fl, 1)
+    per_launch_bytes = float(np.mean(byt)) * (1.0 if dom_name == "bond_visits_cluster" else 1.0 / (2 * piv + 1))
+    achieved = per_launch_bytes / (dom_avg_ms * 1e-3) / 1e9
+    ncu = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")) as fjs:
+            ncu = json.load(fjs)
+    except Exception:
+        pass
+    traffic = ncu.get("k_visits", {}).get("dram_bytes_per_launch") if dom_name == "bond_visits_cluster" else None
+    roofline = {"kernel": "k_visits (cluster per partition: lottery + rook fibers + residuals + argmax folds + rank-1 append)"
+                if dom_name == "bond_visits_cluster" else "k_fiber", "bound": "hbm", "achieved": achieved,
+                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": per_launch_bytes, "algorithmic_flops_per_launch": float(np.mean(flo)),
+                "share_of_step": fms / tot_ms if tot_ms else None, "avg_launch_us": 1e3 * dom_avg_ms,
+                "note": "latency-bound by construction (a sweep is ~6 dependent steps of <= 8224 evaluations per partition, SURVEY F4): "
+                        "the factors stay in the 126 MB L2 (ncu DRAM traffic per launch in `traffic`), so neither roofline binds; "
+                        "the roofline-sized kernel of the path is reported in roofline_superblock"}
 
     line = {
         "metric": "integrand_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -255,21 +278,36 @@ def main():
         "wall_s_timed_region": wall,
     }
 
-    # ---- superblock kernel (pivoting = -1 branch) at the workload's shape: the roofline-sized kernel of this path
+    # ---- superblock kernel (pivoting = -1 branch, dmrgg.f90:341-396) at the workload's shape: the roofline-sized kernel
     if not args.no_superblock and rank == 0 and world == 1:
         try:
             bond = prob.d // 2
-            sb = t.superblock_probe(bond, store=False, reps=3)
             r1 = int(ranks[bond])
-            flops = sb["count"] * (5 * prob.d + 3 + 2 * r1)
-            sbs = t.superblock_probe(bond, store=True, reps=3)
+            pk_fma, pk_nofma = T.fp64_peak(local_rank, True), T.fp64_peak(local_rank, False)
+            sb = t.superblock_probe(bond, store=False, reps=5, variant=0)
+            sbf = t.superblock_probe(bond, store=False, reps=5, variant=2)
+            sbs = t.superblock_probe(bond, store=True, reps=5, variant=0)
+            sbp = t.superblock_probe(bond, store=False, reps=2, variant=1)
+            flops = sb["count"] * (5 * prob.d + 3 + 2 * r1)          # 5d+3 per evaluation + 2 r(p) per residual element
+            def tf(ms):
+                return flops / (ms * 1e-3) / 1e12
             line["roofline_superblock"] = {
+                "kernel": "k_superblock_t (ttc_superblock.cuh): evaluate a(i,j,k,q), residual against col*row (K = r(p)), two first-index argmaxes",
                 "shape": [int(ranks[bond - 1]), nn, nn, int(ranks[bond + 1])], "K": r1, "elements": sb["count"],
-                "fused": {"ms": sb["ms"], "bound": "fp64", "achieved": flops / (sb["ms"] * 1e-3) / 1e12, "unit": "TFLOP/s",
-                          "peak": 37.2, "peak_source": "derived 148 SM x 64 FMA/clk x 2 x 1.965 GHz (not measured)",
-                          "frac": flops / (sb["ms"] * 1e-3) / 1e12 / 37.2, "evals_per_s": sb["count"] / (sb["ms"] * 1e-3)},
+                "algorithmic_flops_per_launch": flops,
+                "fp64_peak_measured_tflops": {"dfma": pk_fma, "dmul_dadd": pk_nofma,
+                                              "how": "ttc_fp64_peak: 8 independent chains per thread, 2 x 512 threads per SM, CUDA events"},
+                "fused": {"ms": sb["ms"], "bound": "fp64", "achieved": tf(sb["ms"]), "unit": "TFLOP/s", "peak": pk_nofma,
+                          "frac": tf(sb["ms"]) / pk_nofma, "frac_of_dfma_peak": tf(sb["ms"]) / pk_fma,
+                          "evals_per_s": sb["count"] / (sb["ms"] * 1e-3),
+                          "traffic": ncu.get("k_superblock_t", {}).get("dram_bytes_per_launch"),
+                          "note": "reference arithmetic (no FMA contraction): the DMUL+DADD ceiling is the bound; bit-identical to the oracle"},
+                "fused_dfma": {"ms": sbf["ms"], "achieved": tf(sbf["ms"]), "unit": "TFLOP/s", "peak": pk_fma, "frac": tf(sbf["ms"]) / pk_fma,
+                               "note": "residual contracted into DFMA: not bit-exact, never used by the sweep"},
                 "stored": {"ms": sbs["ms"], "bound": "hbm", "achieved": 8.0 * sbs["count"] / (sbs["ms"] * 1e-3) / 1e9, "unit": "GB/s",
-                           "peak": hbm_peak, "frac": 8.0 * sbs["count"] / (sbs["ms"] * 1e-3) / 1e9 / hbm_peak},
+                           "peak": hbm_peak, "frac": 8.0 * sbs["count"] / (sbs["ms"] * 1e-3) / 1e9 / hbm_peak,
+                           "note": "also writes a (8 B per element); still FP64-bound at this shape"},
+                "plain_kernel_ms": sbp["ms"],
             }
         except Exception as e:  # noqa: BLE001
             line["roofline_superblock"] = {"error": str(e)}

@@ -140,6 +140,13 @@ int ttc_set_timeline(ttc_handle* h, int on);
 long ttc_timeline(const ttc_handle* h, long cap, int* ids, unsigned long long* t_ns, const char** names, int names_cap);
 int ttc_profile(const ttc_handle* h, int cap, const char** names, long long* launches, double* ms);
 
+/* ---- tall-skinny Householder QR: ort0_d (lib/ort.f90:17-81 = LAPACK dgeqrf + dorgqr), SURVEY 8 row a21 ----------
+ * a: m x n column-major (leading dimension m) on the HOST; q: m x n orthonormal factor; r: n x n upper triangular with
+ * LAPACK's sign convention (zeros below the diagonal).  m < n follows the reference's early return (ort.f90:32-46).
+ * Not called by the sweep; it is the kernel of TT orthogonalisation (dtt_ort, lib/tt.f90:130-198).
+ * ms (may be NULL): device time of one factorisation, averaged over `reps` runs.  Failure message: ttc_last_error(NULL). */
+int ttc_qr_thin(int device, int m, int n, const double* a, double* q, double* r, int reps, double* ms);
+
 /* ---- multi-GPU: one process per GPU, core blocks partitioned over ranks ------
  * Replaces MPI_COMM_WORLD of the reference (lib/dmrgg.f90:86-95, 763-959, 1209-1246, 1355-1405).  The communicator id
  * is an NCCL unique id (128 bytes) created on rank 0 by ttc_comm_unique_id and broadcast by the caller (MPI_Bcast in a

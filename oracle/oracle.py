@@ -74,6 +74,7 @@ def lib():
         L.tto_idamax.argtypes = [C.c_long, dp]
         L.tto_d2_lual.argtypes = [C.c_long, C.c_int, dp, dp, C.c_int]
         L.tto_d2_luar.argtypes = [C.c_long, C.c_int, dp, dp, C.c_int]
+        L.tto_qr_thin.argtypes = [C.c_int, C.c_int, dp, dp, dp]
         L.tto_erank.restype = C.c_double
         L.tto_erank.argtypes = [C.c_int, ip, ip]
         L.tto_fmt_e.restype = C.c_int
@@ -347,3 +348,13 @@ def share(first: int, last: int, nproc: int) -> np.ndarray:
     own = np.zeros(nproc + 1, dtype=np.int32)
     lib().tto_share(first, last, nproc, _ip(own))
     return own
+
+
+def qr_thin(a):
+    """ort0_d (lib/ort.f90:17-81): thin Householder QR with LAPACK's conventions -> (q, r)."""
+    a = np.asfortranarray(a, dtype=np.float64)
+    m, n = a.shape
+    q = np.zeros((m, n), order="F")
+    r = np.zeros((n, n), order="F")
+    lib().tto_qr_thin(m, n, _dp(a), _dp(q), _dp(r))
+    return q, r

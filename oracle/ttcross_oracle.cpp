@@ -24,6 +24,7 @@
 //    share            lib/default.f90:80-97
 //    lgwt             lib/quad.f90:97-131
 //    dtt_rank (erank) lib/tt.f90:1228-1245
+//    ort0_d           lib/ort.f90:17-81 (LAPACK dgeqrf + dorgqr restated as dgeqr2 + dorg2r; pinned against numpy's LAPACK)
 //    integrands       test_crs_ising.f90:176-218, test_crs_stdnorm.f90:154-170,
 //                     lib/mvn_pdf.f90:63-83 + test_crs_mvn.f90:156-172
 //    BLAS semantics   netlib reference order (idamax first-max, sequential ddot,
@@ -1088,6 +1089,54 @@ void tto_d2_luar(long n, int r, const double* g, double* row, int from) { d2_lua
 double tto_erank(int d, const int* n, const int* r) {
     std::vector<int> nv(n, n + d), rv(r, r + d + 1);
     return erank(1, d, nv, rv);
+}
+// ort0_d (lib/ort.f90:17-81) = LAPACK dgeqrf + dorgqr.  LAPACK is a third-party dependency that the reference links
+// unpinned ("-llapack", Makefile:18) and that is absent from /root/reference; this restates its published unblocked
+// algorithm (netlib dgeqr2 / dlarfg / dlarf / dorg2r: beta = -sign(alpha) * norm, v(1) = 1, tau = (beta - alpha) / beta).
+// PINNED in tests/test_qr.py against numpy.linalg.qr, which calls the same LAPACK routines (dgeqrf + dorgqr).
+// a: m x n column-major (lda = m), overwritten?  no: inputs are copied.  q: m x n, r: n x n (zeros below the diagonal).
+void tto_qr_thin(int m, int n, const double* a, double* q, double* r) {
+    if (m < n) {     // ort.f90:32-46
+        for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) r[i + (size_t)n * j] = (i < m) ? a[i + (size_t)m * j] : 0.0;
+        for (int j = 0; j < n; ++j) for (int i = 0; i < m; ++i) q[i + (size_t)m * j] = (i == j) ? 1.0 : 0.0;
+        return;
+    }
+    std::vector<double> y(a, a + (size_t)m * n), tau(n, 0.0);
+    auto Y = [&](int i, int j) -> double& { return y[i + (size_t)m * j]; };
+    for (int k = 0; k < n; ++k) {                       // dgeqr2
+        double ssq = 0.0;
+        for (int i = k + 1; i < m; ++i) ssq += Y(i, k) * Y(i, k);
+        const double alpha = Y(k, k);
+        double beta = alpha; tau[k] = 0.0;
+        if (ssq != 0.0) {                               // dlarfg
+            beta = -std::copysign(std::sqrt(alpha * alpha + ssq), alpha);
+            tau[k] = (beta - alpha) / beta;
+            const double sc = 1.0 / (alpha - beta);
+            for (int i = k + 1; i < m; ++i) Y(i, k) *= sc;
+        }
+        for (int j = k + 1; j < n; ++j) {               // dlarf from the left, v(k) = 1
+            double w = Y(k, j);
+            for (int i = k + 1; i < m; ++i) w += Y(i, k) * Y(i, j);
+            Y(k, j) -= tau[k] * w;
+            for (int i = k + 1; i < m; ++i) Y(i, j) -= tau[k] * w * Y(i, k);
+        }
+        Y(k, k) = beta;
+    }
+    for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) r[i + (size_t)n * j] = (i <= j) ? Y(i, j) : 0.0;
+    for (int k = n - 1; k >= 0; --k) {                  // dorg2r
+        if (k < n - 1) {
+            for (int j = k + 1; j < n; ++j) {
+                double w = Y(k, j);
+                for (int i = k + 1; i < m; ++i) w += Y(i, k) * Y(i, j);
+                Y(k, j) -= tau[k] * w;
+                for (int i = k + 1; i < m; ++i) Y(i, j) -= tau[k] * w * Y(i, k);
+            }
+        }
+        for (int i = k + 1; i < m; ++i) Y(i, k) = -tau[k] * Y(i, k);
+        Y(k, k) = 1.0 - tau[k];
+        for (int i = 0; i < k; ++i) Y(i, k) = 0.0;
+    }
+    std::copy(y.begin(), y.end(), q);
 }
 int tto_fmt_e(double v, int w, int dgt, char* buf) { std::string s = fmt_e(v, w, dgt); std::memcpy(buf, s.c_str(), s.size() + 1); return (int)s.size(); }
 int tto_num_threads() {

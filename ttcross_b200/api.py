@@ -82,6 +82,7 @@ def load_library(build_if_missing: bool = True):
     L.ttc_device_ms.argtypes = [vp]
     L.ttc_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_longlong), _dp]
     L.ttc_fp64_peak.argtypes = [C.c_int, C.c_int, _dp]
+    L.ttc_qr_thin.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _dp]
     L.ttc_set_timeline.argtypes = [vp, C.c_int]
     L.ttc_timeline.restype = C.c_long
     L.ttc_timeline.argtypes = [vp, C.c_long, _ip, C.POINTER(C.c_ulonglong), C.POINTER(C.c_char_p), C.c_int]
@@ -127,6 +128,20 @@ def fp64_peak(device: int = 0, fma: bool = True) -> float:
     if st != 0:
         raise TTCrossError(st, "ttc_fp64_peak failed (no CUDA device?)")
     return v.value
+
+
+def qr_thin(a, device: int = 0, reps: int = 1):
+    """ort0_d (lib/ort.f90:17-81): thin QR of an m x n block on the GPU -> (q, r, ms)."""
+    L = load_library()
+    a = np.asfortranarray(a, dtype=np.float64)
+    m, n = a.shape
+    q = np.zeros((m, n), order="F")
+    r = np.zeros((n, n), order="F")
+    ms = C.c_double()
+    st = L.ttc_qr_thin(device, m, n, _d(a), _d(q), _d(r), reps, C.byref(ms))
+    if st != 0:
+        raise TTCrossError(st, L.ttc_last_error(None).decode())
+    return q, r, ms.value
 
 
 class TTCross:

@@ -14,6 +14,7 @@
 #include "ttc_device.cuh"
 #include "ttc_visit.cuh"
 #include "ttc_superblock.cuh"
+#include "ttc_qr.cuh"
 #include "ttc_nccl.hpp"
 
 #include <algorithm>
@@ -1353,6 +1354,58 @@ int ttc_fp64_peak(int device, int fma, double* tflops) {
     if (cudaGetLastError() != cudaSuccess) return TTC_ERR_CUDA;
     const double flops = (double)nsm * 2 * 512 * (double)iters * 64 * 2;
     *tflops = flops / (best * 1e-3) / 1e12;
+    return TTC_OK;
+}
+
+// ort0_d (lib/ort.f90:17-81): thin QR of an m x n block, host buffers in and out (column-major, leading dimension m).
+// q: m x n, r: n x n.  m < n follows the reference's early-return branch (:32-46).  ms: kernel time per run (CUDA events).
+int ttc_qr_thin(int device, int m, int n, const double* a, double* q, double* r, int reps, double* ms) {
+    if (!a || !q || !r || m < 1 || n < 1 || reps < 1) return TTC_ERR_ARG;
+    if (ms) *ms = 0.0;
+    if (m < n) {
+        for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) r[i + (size_t)n * j] = (i < m) ? a[i + (size_t)m * j] : 0.0;
+        for (int j = 0; j < n; ++j) for (int i = 0; i < m; ++i) q[i + (size_t)m * j] = (i == j) ? 1.0 : 0.0;
+        return TTC_OK;
+    }
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || device < 0 || device >= cnt) { g_create_err = "ttc_qr_thin: no CUDA device (there is no CPU fallback)"; return TTC_ERR_CUDA; }
+    cudaSetDevice(device);
+    int nsm = 0, coop = 0;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    if (!coop) { g_create_err = "ttc_qr_thin: device lacks cooperative launch"; return TTC_ERR_CUDA; }
+    int G = std::max(1, std::min(nsm, (m + 15) / 16));
+    int rpb = (m + G - 1) / G;
+    G = (m + rpb - 1) / rpb;
+    const size_t smem = ((size_t)rpb * n + n) * sizeof(double);
+    if (smem > 200 * 1024) { g_create_err = "ttc_qr_thin: the block does not fit the shared memory of one cooperative launch"; return TTC_ERR_ARG; }
+    cudaError_t e = cudaFuncSetAttribute(k_qr_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    double *da = nullptr, *dq = nullptr, *dr = nullptr, *dpart = nullptr, *dpw = nullptr, *dhead = nullptr;
+    auto cleanup = [&]() { cudaFree(da); cudaFree(dq); cudaFree(dr); cudaFree(dpart); cudaFree(dpw); cudaFree(dhead); };
+    if (e == cudaSuccess) e = cudaMalloc((void**)&da, (size_t)m * n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dq, (size_t)m * n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dr, (size_t)n * n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dpart, (size_t)G * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dpw, (size_t)2 * G * n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dhead, (size_t)(n + 2) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(da, a, (size_t)m * n * sizeof(double), cudaMemcpyHostToDevice);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    int lda = m;
+    void* args[] = {(void*)&da, (void*)&m, (void*)&n, (void*)&lda, (void*)&dq, (void*)&dr, (void*)&dpart, (void*)&dpw, (void*)&dhead, (void*)&rpb};
+    for (int rep = 0; rep <= reps && e == cudaSuccess; ++rep) {      // run 0 is the warm-up
+        if (rep == 1) cudaEventRecord(ev0);
+        e = cudaLaunchCooperativeKernel((void*)k_qr_panel, dim3(G), dim3(QR_THREADS), args, smem, nullptr);
+    }
+    cudaEventRecord(ev1);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(q, dq, (size_t)m * n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(r, dr, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost);
+    float t = 0; cudaEventElapsedTime(&t, ev0, ev1);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    cleanup();
+    if (e != cudaSuccess) { g_create_err = std::string("ttc_qr_thin: CUDA error: ") + cudaGetErrorString(e); return TTC_ERR_CUDA; }
+    if (ms) *ms = t / reps;
     return TTC_OK;
 }
 
