@@ -126,6 +126,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version banner there) go to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     dist = None
     if world > 1:
         import torch
@@ -329,7 +332,8 @@ def main():
         line["cpu_baseline"] = {"value": ne / dt, "unit": "evals/s", "cores": O.lib().tto_num_threads(), "kind": "port",
                                 "sample": f"{reps} full runs of the same workload and partition in {dt:.1f} s", "matches_gpu_bitwise": same}
     if rank == 0:
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 

@@ -176,7 +176,7 @@ __device__ __forceinline__ void cluster_fold(cg::cluster_group& cl, VisitShared&
 // fold_allreduce != 0: the last cluster to finish performs the MAX reduction of dmrgg.f90:852-870 (single process only).
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ void tl_mark(const DevPlan& P, int id) {     // diagnostic: phase stamps of the first cluster
-    if (P.tlog && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    if (P.tlog && blockIdx.x == 0 && blockIdx.y == gridDim.y / 2 && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         int k = atomicAdd(P.tlog_n, 1);
