@@ -967,7 +967,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         }
         if (has_quad) { int e = launch_quad(h, L, true, true); if (e) return e; }
         else if (multi) { int e = mp_phase2(h, L, 0); if (e) return e; }
-        L(KC_MISC, [&] { k_sweep_log<<<1, 128, 0, s>>>(D, maxrank); });
+        L(KC_MISC, [&] { k_sweep_log<<<1, 128, 0, s>>>(D, maxrank > 0 ? maxrank : Rmax); });   // no maxrank: the rank capacity ends the run
         return 0;
     };
 
@@ -976,29 +976,33 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     // In asynchronous mode a sweep is a fixed kernel sequence (sweep number, seed and thresholds live in device memory),
     // so it is captured once per direction into a CUDA graph and replayed: one graph launch per sweep instead of ~25
     // kernel launches.  Grids are sized for the rank capacity; surplus CTAs exit at once.
+    int graph_sweeps = 4;                 // even: every graph starts with a '>>' sweep
+    if (const char* e = std::getenv("TTC_GRAPH_SWEEPS")) graph_sweeps = std::max(2, 2 * (std::atoi(e) / 2));
     const bool use_graph = !sync_mode && !h->profile && !h->no_graph && (!multi || std::getenv("TTC_MP_GRAPH") != nullptr);
     if (use_graph) {
         std::vector<long long> gsig = {(long long)h->piv, (long long)has_quad, (long long)maxrank, (long long)h->use_wave, (long long)dev_lot,
                                        (long long)h->setup_serial, (long long)h->timeline, (long long)use_cluster,
                                        (long long)h->cluster_size, (long long)h->cluster_threads};
+        gsig.push_back(graph_sweeps);
         if (gsig != h->graph_sig) {
-            for (int gdir = 0; gdir < 2; ++gdir) {
-                if (h->gexec[gdir]) { cudaGraphExecDestroy(h->gexec[gdir]); h->gexec[gdir] = nullptr; }
-                cudaGraph_t g = nullptr;
-                CUDA_TRY(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-                long long l0 = h->launches;
-                long long kc0[KC_COUNT];
-                std::copy(h->kc_launch, h->kc_launch + KC_COUNT, kc0);
-                int e = enqueue_sweep(gdir == 0 ? 1 : 2, Rmax);
-                h->graph_nodes[gdir] = h->launches - l0;
-                h->launches = l0;
-                for (int c = 0; c < KC_COUNT; ++c) { h->graph_kc[gdir][c] = h->kc_launch[c] - kc0[c]; h->kc_launch[c] = kc0[c]; }
-                cudaError_t ce = cudaStreamEndCapture(s, &g);
-                if (e) return e;
-                CUDA_TRY(h, ce);
-                CUDA_TRY(h, cudaGraphInstantiate(&h->gexec[gdir], g, 0));
-                cudaGraphDestroy(g);
-            }
+            // ONE graph holds `graph_sweeps` consecutive sweeps ('>>', '<<', '>>', ...): fewer graph boundaries on the device.
+            // Sweeps past the exit condition are no-ops (the ready flag is tested by every kernel).
+            for (int gdir = 0; gdir < 2; ++gdir) if (h->gexec[gdir]) { cudaGraphExecDestroy(h->gexec[gdir]); h->gexec[gdir] = nullptr; }
+            cudaGraph_t g = nullptr;
+            CUDA_TRY(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            long long l0 = h->launches;
+            long long kc0[KC_COUNT];
+            std::copy(h->kc_launch, h->kc_launch + KC_COUNT, kc0);
+            int e = 0;
+            for (int q = 0; q < graph_sweeps && !e; ++q) e = enqueue_sweep(q % 2 == 0 ? 1 : 2, Rmax);
+            h->graph_nodes[0] = h->launches - l0;
+            h->launches = l0;
+            for (int c = 0; c < KC_COUNT; ++c) { h->graph_kc[0][c] = h->kc_launch[c] - kc0[c]; h->kc_launch[c] = kc0[c]; }
+            cudaError_t ce = cudaStreamEndCapture(s, &g);
+            if (e) return e;
+            CUDA_TRY(h, ce);
+            CUDA_TRY(h, cudaGraphInstantiate(&h->gexec[0], g, 0));
+            cudaGraphDestroy(g);
             h->graph_sig = gsig;
         }
     }
@@ -1008,10 +1012,10 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         if (!multi && *(volatile int*)h->ready_h) break;   // device already reached its exit condition
         int e = 0;
         if (use_graph) {
-            const int gdir = (it % 2 == 1) ? 0 : 1;     // graph 0: odd sweeps ('>>'), graph 1: even sweeps ('<<')
-            CUDA_TRY(h, cudaGraphLaunch(h->gexec[gdir], s));
-            h->launches += h->graph_nodes[gdir];
-            for (int c = 0; c < KC_COUNT; ++c) h->kc_launch[c] += h->graph_kc[gdir][c];
+            CUDA_TRY(h, cudaGraphLaunch(h->gexec[0], s));  // sweeps it .. it + graph_sweeps - 1
+            h->launches += h->graph_nodes[0];
+            for (int c = 0; c < KC_COUNT; ++c) h->kc_launch[c] += h->graph_kc[0][c];
+            it += graph_sweeps - 1;
         } else {
             cur_it = it;
             e = enqueue_sweep(2 - it % 2, std::min(it + 1, Rmax));
