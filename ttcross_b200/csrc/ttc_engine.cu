@@ -1108,6 +1108,10 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     h->neval = nevalall;
     h->seconds = timef();
     h->ran = true;
+    if (h->verbose && multi) {            // several processes run asynchronously: the sweep lines are printed once the run is over
+        std::fputs(h->text.c_str(), stdout);
+        std::fflush(stdout);
+    }
     return TTC_OK;
 }
 

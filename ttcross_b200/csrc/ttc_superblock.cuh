@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(SB_TM) k_superblock_t(DevPlan P, int dir, int 
             double res[SB_CN];
 #pragma unroll
             for (int c = 0; c < SB_CN; ++c) res[c] = f[c];
-#pragma unroll 4
+#pragma unroll 8
             for (int s = 0; s < K; ++s) {
                 const double cv = Ct[s * SB_TM + threadIdx.x];
                 const double2* rp = reinterpret_cast<const double2*>(Rt + s * SB_TN + cb);
@@ -193,10 +193,8 @@ __global__ void __launch_bounds__(SB_TM) k_superblock_t(DevPlan P, int dir, int 
                     if (kq < ncols) {
                         const i64 x = (i64)row + (i64)m1 * kq;
                         if (STORE) a_out[x] = f[c];
-                        Partial t1; t1.absv = fabs(f[c]); t1.val = f[c]; t1.idx = x;
-                        Partial t2; t2.absv = fabs(res[c]); t2.val = res[c]; t2.idx = x;
-                        amax_merge(braw, t1);
-                        amax_merge(bres, t2);
+                        amax_take(braw, f[c], x);        // this thread meets its elements in ascending linear index:
+                        amax_take(bres, res[c], x);      // strict '>' keeps the first maximum (idamax)
                     }
                 }
             }
