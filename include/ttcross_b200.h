@@ -123,6 +123,9 @@ int ttc_fiber_probe(ttc_handle* h, int bond, int isrow, int ii, int jj, int kk, 
 /* The device lottery's closed-form cumulative weights, executed on the host (test hook): cells[x] = the 1-based cell that
  * lottery2 (rnd.f90:105-126) picks for uniform u[x] among m cells of weight 1 except the listed zero-weight cells. */
 int ttc_lottery_closed_form(int m, const int* zeros_sorted_distinct, int nz, const double* u, int count, int* cells);
+/* the same draws by the table-free rule of the cluster kernel (one multiplication decides unless u lies within the
+ * rounding window of a boundary, where the boundary is formed by literal sequential addition) */
+int ttc_lottery_fast(int m, const int* zeros_sorted_distinct, int nz, const double* u, int count, int* cells);
 /* Counters: kernels launched by this handle since creation, device time of the last ttc_dmrgg (CUDA events, ms) */
 long long ttc_launch_count(const ttc_handle* h);
 /* write `bytes` (> L2 size) of scratch HBM so the next timed run starts with a cold L2 (measurement hygiene) */

@@ -148,3 +148,9 @@ def test_closed_form_lottery_matches_literal_loop():
         pts = np.zeros(2 * cnt, dtype=np.int32)
         O.lib().tto_lottery2(cnt, m, 1, O._dp(w), O._dp(np.ones(1)), O._dp(uu), O._ip(pts))
         assert np.array_equal(pts[:cnt], cells), f"trial {trial}: m={m} nz={nz}"
+        # the table-free rule of the cluster kernel (one multiplication, literal summation inside the rounding window)
+        L.ttc_lottery_fast.argtypes = L.ttc_lottery_closed_form.argtypes
+        cells2 = np.zeros(cnt, dtype=np.int32)
+        assert L.ttc_lottery_fast(m, zeros.ctypes.data_as(C.POINTER(C.c_int)), nz, u.ctypes.data_as(C.POINTER(C.c_double)),
+                                  cnt, cells2.ctypes.data_as(C.POINTER(C.c_int))) == 0
+        assert np.array_equal(pts[:cnt], cells2), f"trial {trial} (fast rule): m={m} nz={nz}"

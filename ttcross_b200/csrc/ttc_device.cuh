@@ -535,6 +535,31 @@ __host__ __device__ __noinline__ int lot_draw(const LotSeg* seg, int ns, int sco
     for (int z = 0; z < nz; ++z) { if (zeros[z] <= sidx) ++sidx; else break; }
     return sidx;
 }
+// The same draw WITHOUT the segment table (used by the cluster kernel): T[c] = c*delta up to the accumulated rounding of c
+// additions, |T[c] - c*delta| <= c * 2^-53 * T[c] < (c + 4) * 2^-52, so the comparison y < T[c] is decided by one
+// multiplication unless y lies inside that window (probability ~1e-9 per draw); only then T[c] is formed exactly as the
+// reference forms it, by c sequential additions (rnd.f90:118-119).
+__host__ __device__ __forceinline__ bool lot_lt(double y, int c, double delta) {      // y < T[c] ?
+    const double a = (double)c * delta;
+    const double tol = (double)(c + 4) * 2.220446049250313e-16;
+    if (y < a - tol) return true;
+    if (y >= a + tol) return false;
+    double T = 0.0;
+    for (int i = 0; i < c; ++i) T = T + delta;
+    return y < T;
+}
+__host__ __device__ __noinline__ int lot_draw_fast(int scol, int m, const int* zeros, int nz, double y) {
+    const double delta = 1.0 / (double)scol;
+    if (!lot_lt(y, scol, delta)) return m;              // x(n) <= y  ->  n = m+1, clamped to m (rnd.f90:122)
+    int lo = (int)(y * (double)scol) + 1;
+    if (lo < 1) lo = 1;
+    if (lo > scol) lo = scol;
+    while (lo < scol && !lot_lt(y, lo, delta)) ++lo;
+    while (lo > 1 && lot_lt(y, lo - 1, delta)) --lo;
+    int sidx = lo;
+    for (int z = 0; z < nz; ++z) { if (zeros[z] <= sidx) ++sidx; else break; }
+    return sidx;
+}
 // sorted distinct zero-weight cells (1-based) of one side of bond p; thread-parallel rank sort over the r1 pivots.
 // tmp, zeros: shared int[>= r1]; *nz: shared int.  side 0: (i,j) with stride r0; side 1: (k,q) with stride n2.
 __device__ __forceinline__ void lot_zeros(const int* vip_p, int r1, int side, int stride, int* tmp, int* zeros, int* nz) {

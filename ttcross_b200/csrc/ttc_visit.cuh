@@ -29,8 +29,7 @@ struct VisitShared {
     Partial xpart[2][2][MAXCS];   // [phase parity][raw|res][CTA rank]; only CTA 0's copy is used
     Partial red[2];
     Partial shp[32];
-    LotSeg seg[2][MAXSEG];
-    int ns[2], nz[2];
+    int nz[2];
     VState S;
     int r0, r1, r2;
 };
@@ -231,9 +230,6 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, 1) k_visits(DevPlan P, int d
             const int* vip_p = P.vip + (i64)p * P.Rmax * 4;
             const int m = ccount, n = rcount;
             lot_zeros2(vip_p, r1, r0, n2, tmp, zc, zr, sh.nz);
-            if (threadIdx.x == 0) sh.ns[0] = build_segments(m - sh.nz[0], sh.seg[0]);
-            if (threadIdx.x == 32) sh.ns[1] = build_segments(n - sh.nz[1], sh.seg[1]);
-            __syncthreads();
             tl_mark(P, 42);
             const unsigned long long k0 = sh.S.rng_k, seed = P.ctrl->seed;
             Partial braw = amax_init(), bres = amax_init();
@@ -246,8 +242,7 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, 1) k_visits(DevPlan P, int d
                 int cell = 1;
                 if (live) {
                     const double uu = stream_uniform(seed, v, k0 + (unsigned long long)(side ? nlot + x : x));
-                    cell = side ? lot_draw(sh.seg[1], sh.ns[1], n - sh.nz[1], n, zr, sh.nz[1], uu)
-                                : lot_draw(sh.seg[0], sh.ns[0], m - sh.nz[0], m, zc, sh.nz[0], uu);
+                    cell = side ? lot_draw_fast(n - sh.nz[1], n, zr, sh.nz[1], uu) : lot_draw_fast(m - sh.nz[0], m, zc, sh.nz[0], uu);
                 }
                 const int w = __shfl_down_sync(FULLMASK, cell, 1);
                 if (!live || side) continue;
@@ -268,8 +263,8 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, 1) k_visits(DevPlan P, int d
                 const int x = (int)bres.idx;         // the winner's cell is a pure function of its draw number
                 const double uc = stream_uniform(seed, v, k0 + (unsigned long long)x);
                 const double ur = stream_uniform(seed, v, k0 + (unsigned long long)(nlot + x));
-                const int c = lot_draw(sh.seg[0], sh.ns[0], m - sh.nz[0], m, zc, sh.nz[0], uc);
-                const int w = lot_draw(sh.seg[1], sh.ns[1], n - sh.nz[1], n, zr, sh.nz[1], ur);
+                const int c = lot_draw_fast(m - sh.nz[0], m, zc, sh.nz[0], uc);
+                const int w = lot_draw_fast(n - sh.nz[1], n, zr, sh.nz[1], ur);
                 St.ii = (c - 1) % r0 + 1; St.jj = (c - 1) / r0 + 1; St.kk = (w - 1) % n2 + 1; St.qq = (w - 1) / n2 + 1;
                 St.pivot = bres.val;
                 St.done = 0; St.havecol = 0; St.haverow = 0; St.crs = 0; St.upd = 0;
