@@ -13,8 +13,8 @@
 //
 // Arithmetic, summation orders and tie-breaks are those of ttc_device.cuh (bit-identical results).
 // Data that other CTAs of the cluster may have written earlier in the same kernel (ranks, index
-// tables, packed LUs, factor cores, fiber buffers) is read with ld.global.cg (L2) so no SM ever
-// sees a stale L1 line; visibility is ordered by __threadfence + barrier.cluster (release/acquire).
+// tables, packed LUs, factor cores, fiber buffers) is read only after a barrier.cluster, whose
+// release/acquire semantics (and L1 invalidation) make ordinary loads see it (see LDF below).
 // =============================================================================
 #pragma once
 #include "ttc_device.cuh"
@@ -34,6 +34,15 @@ struct VisitShared {
     int r0, r1, r2;
 };
 
+// Loads of data that other CTAs of the cluster may have written earlier in this kernel (ranks, index tables, packed LUs,
+// factor cores, fiber buffers).  Every such write is separated from its next read by barrier.cluster (cluster.sync):
+// arrive.release / wait.acquire at cluster scope orders them, and the hardware invalidates the SM's L1 at the barrier
+// (CCTL.IVALL), so ordinary cached loads are correct; -DTTC_STRONG_FACTOR_LOADS turns them into ld.global.cg.
+#ifdef TTC_STRONG_FACTOR_LOADS
+#define LDF(p) __ldcg(p)
+#else
+#define LDF(p) (*(p))
+#endif
 // ---- L2 (cache-global) variants of the residual / staging helpers of ttc_device.cuh
 __device__ __forceinline__ double resid_axpy_cg(double f, const double* base, i64 stride, const double* xs, int r) {
     double res = f;
@@ -41,11 +50,11 @@ __device__ __forceinline__ double resid_axpy_cg(double f, const double* base, i6
     for (; s0 + RU <= r; s0 += RU) {
         double a[RU];
 #pragma unroll
-        for (int u = 0; u < RU; ++u) a[u] = __ldcg(base + (s0 + u) * stride);
+        for (int u = 0; u < RU; ++u) a[u] = LDF(base + (s0 + u) * stride);
 #pragma unroll
         for (int u = 0; u < RU; ++u) res = res + (-xs[s0 + u]) * a[u];
     }
-    for (; s0 < r; ++s0) res = res + (-xs[s0]) * __ldcg(base + s0 * stride);
+    for (; s0 < r; ++s0) res = res + (-xs[s0]) * LDF(base + s0 * stride);
     return res;
 }
 __device__ __forceinline__ double resid_dot_cg(double f, const double* base, i64 stride, const double* xs, int r) {
@@ -54,11 +63,11 @@ __device__ __forceinline__ double resid_dot_cg(double f, const double* base, i64
     for (; s0 + RU <= r; s0 += RU) {
         double a[RU];
 #pragma unroll
-        for (int u = 0; u < RU; ++u) a[u] = __ldcg(base + (s0 + u) * stride);
+        for (int u = 0; u < RU; ++u) a[u] = LDF(base + (s0 + u) * stride);
 #pragma unroll
         for (int u = 0; u < RU; ++u) t = t + a[u] * xs[s0 + u];
     }
-    for (; s0 < r; ++s0) t = t + __ldcg(base + s0 * stride) * xs[s0];
+    for (; s0 < r; ++s0) t = t + LDF(base + s0 * stride) * xs[s0];
     return f + (-t);
 }
 __device__ __forceinline__ double resid_ddot2_cg(double f, const double* c, i64 cs, const double* r, i64 rs, int r1) {
@@ -67,11 +76,11 @@ __device__ __forceinline__ double resid_ddot2_cg(double f, const double* c, i64 
     for (; s0 + RU <= r1; s0 += RU) {
         double a[RU], b[RU];
 #pragma unroll
-        for (int u = 0; u < RU; ++u) { a[u] = __ldcg(c + (s0 + u) * cs); b[u] = __ldcg(r + (s0 + u) * rs); }
+        for (int u = 0; u < RU; ++u) { a[u] = LDF(c + (s0 + u) * cs); b[u] = LDF(r + (s0 + u) * rs); }
 #pragma unroll
         for (int u = 0; u < RU; ++u) t = t + a[u] * b[u];
     }
-    for (; s0 < r1; ++s0) t = t + __ldcg(c + s0 * cs) * __ldcg(r + s0 * rs);
+    for (; s0 < r1; ++s0) t = t + LDF(c + s0 * cs) * LDF(r + s0 * rs);
     return f - t;
 }
 // residuals with the first RP factor values loaded BEFORE the evaluation (their L2 round trip hides behind it)
@@ -79,7 +88,7 @@ constexpr int RP = 16;
 struct Pref { double a[RP]; };
 __device__ __forceinline__ void pref_load(Pref& pf, const double* base, i64 stride, int r) {
 #pragma unroll
-    for (int u = 0; u < RP; ++u) pf.a[u] = __ldcg(base + min(u, r - 1) * stride);   // clamped, never predicated: all in flight at once
+    for (int u = 0; u < RP; ++u) pf.a[u] = LDF(base + min(u, r - 1) * stride);   // clamped, never predicated: all in flight at once
 }
 __device__ __forceinline__ double resid_axpy_pf(double f, const Pref& pf, const double* base, i64 stride, const double* xs, int r) {
     double res = f;
@@ -88,7 +97,7 @@ __device__ __forceinline__ double resid_axpy_pf(double f, const Pref& pf, const 
     for (int s0 = RP; s0 < r; s0 += RP) {
         double a[RP];
 #pragma unroll
-        for (int u = 0; u < RP; ++u) a[u] = __ldcg(base + min(s0 + u, r - 1) * stride);
+        for (int u = 0; u < RP; ++u) a[u] = LDF(base + min(s0 + u, r - 1) * stride);
 #pragma unroll
         for (int u = 0; u < RP; ++u) if (s0 + u < r) res = res + (-xs[s0 + u]) * a[u];
     }
@@ -101,7 +110,7 @@ __device__ __forceinline__ double resid_dot_pf(double f, const Pref& pf, const d
     for (int s0 = RP; s0 < r; s0 += RP) {
         double a[RP];
 #pragma unroll
-        for (int u = 0; u < RP; ++u) a[u] = __ldcg(base + min(s0 + u, r - 1) * stride);
+        for (int u = 0; u < RP; ++u) a[u] = LDF(base + min(s0 + u, r - 1) * stride);
 #pragma unroll
         for (int u = 0; u < RP; ++u) if (s0 + u < r) t = t + a[u] * xs[s0 + u];
     }
@@ -121,13 +130,13 @@ __device__ __forceinline__ Stage stage_bond_cg(const DevPlan& P, double* sm, int
     const int* L = P.Lidx + P.offL[pl];
     for (int x = threadIdx.x; x < nl * rl; x += blockDim.x) {
         int pos = x / rl, t = x - pos * rl;
-        int idx = __ldcg(L + (i64)pos * P.Rmax + t);
+        int idx = LDF(L + (i64)pos * P.Rmax + t);
         XL[x] = P.par[idx - 1]; WL[x] = hasw ? P.par[nwoff + idx - 1] : 0.0;
     }
     const int* R = P.Ridx + P.offR[pr];
     for (int x = threadIdx.x; x < nr * rr; x += blockDim.x) {
         int pos = x / rr, t = x - pos * rr;
-        int idx = __ldcg(R + (i64)pos * P.Rmax + t);
+        int idx = LDF(R + (i64)pos * P.Rmax + t);
         XR[x] = P.par[idx - 1]; WR[x] = hasw ? P.par[nwoff + idx - 1] : 0.0;
     }
     __syncthreads();
@@ -136,11 +145,11 @@ __device__ __forceinline__ Stage stage_bond_cg(const DevPlan& P, double* sm, int
     return S;
 }
 __device__ __forceinline__ void stage_luar_cg(const double* g, int r, double* T) {
-    for (int x = threadIdx.x; x < r * r; x += blockDim.x) { int s = x / r, u = x - s * r; if (u < s) T[u * r + s] = __ldcg(g + (i64)s * s + u); }
+    for (int x = threadIdx.x; x < r * r; x += blockDim.x) { int s = x / r, u = x - s * r; if (u < s) T[u * r + s] = LDF(g + (i64)s * s + u); }
 }
 __device__ __forceinline__ void stage_lual_cg(const double* g, int r, double* T, double* dinv) {
-    for (int x = threadIdx.x; x < r * r; x += blockDim.x) { int c = x / r, u = x - c * r; if (u < c) T[u * r + c] = __ldcg(g + (i64)(c + 1) * (c + 1) - (c + 1) + u); }
-    for (int c = threadIdx.x; c < r; c += blockDim.x) dinv[c] = 1.0 / __ldcg(g + (i64)(c + 1) * (c + 1) - 1);
+    for (int x = threadIdx.x; x < r * r; x += blockDim.x) { int c = x / r, u = x - c * r; if (u < c) T[u * r + c] = LDF(g + (i64)(c + 1) * (c + 1) - (c + 1) + u); }
+    for (int c = threadIdx.x; c < r; c += blockDim.x) dinv[c] = 1.0 / LDF(g + (i64)(c + 1) * (c + 1) - 1);
 }
 
 // first-index argmax over the whole cluster; every thread of every CTA returns with the folded (raw, res).
@@ -186,7 +195,7 @@ constexpr int VISIT_MAXTHREADS = 512;
 template <int KIND>
 __global__ void __launch_bounds__(VISIT_MAXTHREADS, 1) k_visits(DevPlan P, int dir, double small_element, double small_pivot, int fold_allreduce) {
     tl_stamp(P, 40);
-    if (__ldcg(&P.ctrl->ready)) return;          // uniform over the grid: written only by k_sweep_log
+    if (LDF(&P.ctrl->ready)) return;          // uniform over the grid: written only by k_sweep_log
     cg::cluster_group cl = cg::this_cluster();
     extern __shared__ double smem[];
     __shared__ VisitShared sh;
@@ -209,9 +218,9 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, 1) k_visits(DevPlan P, int d
     for (int pp = 1; pp <= nb; ++pp) {
         const int p = (dir == 1) ? lo + pp - 1 : hi - pp;
         if (threadIdx.x == 0) {
-            sh.r0 = (p - 1 >= lo) ? __ldcg(P.rk + p - 1) : P.rks[p - 1];
-            sh.r1 = __ldcg(P.rk + p);
-            sh.r2 = (p + 1 <= hi - 1) ? __ldcg(P.rk + p + 1) : P.rks[p + 1];
+            sh.r0 = (p - 1 >= lo) ? LDF(P.rk + p - 1) : P.rks[p - 1];
+            sh.r1 = LDF(P.rk + p);
+            sh.r2 = (p + 1 <= hi - 1) ? LDF(P.rk + p + 1) : P.rks[p + 1];
         }
         __syncthreads();
         const int r0 = sh.r0, r1 = sh.r1, r2 = sh.r2, n1 = P.n[p], n2 = P.n[p + 1];
@@ -282,7 +291,7 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, 1) k_visits(DevPlan P, int d
             const int ii = sh.S.ii, jj = sh.S.jj, kk = sh.S.kk, qq = sh.S.qq;
             __syncthreads();                                        // xs of the previous fiber no longer read
             for (int s = threadIdx.x; s < r1; s += blockDim.x)
-                xs[s] = isrow ? __ldcg(colp + (ii - 1) + (i64)P.Rmax * (jj - 1) + s * cs_) : __ldcg(rowp + (kk - 1) + (i64)n2 * (qq - 1) + s * rs_);
+                xs[s] = isrow ? LDF(colp + (ii - 1) + (i64)P.Rmax * (jj - 1) + s * cs_) : LDF(rowp + (kk - 1) + (i64)n2 * (qq - 1) + s * rs_);
             __syncthreads();
             tl_mark(P, 50);
             const int count = isrow ? rcount : ccount;
@@ -372,16 +381,16 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, 1) k_visits(DevPlan P, int d
                 int* Lp = P.Lidx + P.offL[p];
                 const int* Lm = P.Lidx + P.offL[p - 1];
                 for (int pos = threadIdx.x; pos < p; pos += blockDim.x)
-                    Lp[(i64)pos * P.Rmax + t] = (pos < p - 1) ? __ldcg(Lm + (i64)pos * P.Rmax + (ii - 1)) : jj;
+                    Lp[(i64)pos * P.Rmax + t] = (pos < p - 1) ? LDF(Lm + (i64)pos * P.Rmax + (ii - 1)) : jj;
                 int* Rp = P.Ridx + P.offR[p];
                 const int* Rn = P.Ridx + P.offR[p + 1];
                 for (int pos = threadIdx.x; pos < P.d - p; pos += blockDim.x)
-                    Rp[(i64)pos * P.Rmax + t] = (pos == 0) ? kk : __ldcg(Rn + (i64)(pos - 1) * P.Rmax + (qq - 1));
+                    Rp[(i64)pos * P.Rmax + t] = (pos == 0) ? kk : LDF(Rn + (i64)(pos - 1) * P.Rmax + (qq - 1));
                 // packed LU: [ col(ii,jj,1:r) | row(1:r,kk,qq) | pivot ]
                 double* g = P.inv + (i64)p * P.Rmax * P.Rmax;
                 for (int s = threadIdx.x; s < r1; s += blockDim.x) {
-                    g[(i64)r1 * r1 + s] = __ldcg(colp + (ii - 1) + (i64)P.Rmax * (jj - 1) + s * cs_);
-                    g[(i64)r1 * r1 + r1 + s] = __ldcg(rowp + (kk - 1) + (i64)n2 * (qq - 1) + s * rs_);
+                    g[(i64)r1 * r1 + s] = LDF(colp + (ii - 1) + (i64)P.Rmax * (jj - 1) + s * cs_);
+                    g[(i64)r1 * r1 + r1 + s] = LDF(rowp + (kk - 1) + (i64)n2 * (qq - 1) + s * rs_);
                 }
                 if (threadIdx.x == 0) g[(i64)(r1 + 1) * (r1 + 1) - 1] = pivot;
             }
@@ -394,7 +403,7 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, 1) k_visits(DevPlan P, int d
                 for (int x = crank * nw + wid; x < n1; x += cs * nw) {
                     double y[MAXRPL];
 #pragma unroll
-                    for (int u = 0; u < MAXRPL; ++u) { int sidx = lane + 32 * u; y[u] = (sidx < r0) ? __ldcg(fa_c + (i64)x * r0 + sidx) : 0.0; }
+                    for (int u = 0; u < MAXRPL; ++u) { int sidx = lane + 32 * u; y[u] = (sidx < r0) ? LDF(fa_c + (i64)x * r0 + sidx) : 0.0; }
                     warp_luar(y, r0, GSm{ext, r0});
 #pragma unroll
                     for (int u = 0; u < MAXRPL; ++u) { int sidx = lane + 32 * u; if (sidx < r0) dst[x + sidx * de] = y[u]; }
@@ -410,7 +419,7 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, 1) k_visits(DevPlan P, int d
                 for (int x = crank * nw + wid; x < n2; x += cs * nw) {
                     double y[MAXRPL];
 #pragma unroll
-                    for (int u = 0; u < MAXRPL; ++u) { int c = lane + 32 * u; y[u] = (c < r2) ? __ldcg(fa_r + x + (i64)c * n2) : 0.0; }
+                    for (int u = 0; u < MAXRPL; ++u) { int c = lane + 32 * u; y[u] = (c < r2) ? LDF(fa_r + x + (i64)c * n2) : 0.0; }
                     warp_lual(y, r2, GSm{ext, r2}, DSm{di});
 #pragma unroll
                     for (int u = 0; u < MAXRPL; ++u) { int c = lane + 32 * u; if (c < r2) dst[(i64)x * P.Rmax + c * de] = y[u]; }
@@ -429,13 +438,13 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, 1) k_visits(DevPlan P, int d
                     if (e < ccount) {
                         const int j = e / r0, i = e % r0;
                         const i64 o = i + (i64)P.Rmax * (j + (i64)n1 * t);
-                        argp[o] = __ldcg(fa_c + e);
-                        colw[o] = sc * __ldcg(fb_c + e);
+                        argp[o] = LDF(fa_c + e);
+                        colw[o] = sc * LDF(fb_c + e);
                     } else {
                         const int x = e - ccount;
                         const int q = x / n2, k = x % n2;
-                        argn[t + (i64)P.Rmax * (k + (i64)n2 * q)] = __ldcg(fa_r + x);
-                        roww[k + (i64)n2 * (q + (i64)P.Rmax * t)] = __ldcg(fb_r + x);
+                        argn[t + (i64)P.Rmax * (k + (i64)n2 * q)] = LDF(fa_r + x);
+                        roww[k + (i64)n2 * (q + (i64)P.Rmax * t)] = LDF(fb_r + x);
                     }
                 }
             }
