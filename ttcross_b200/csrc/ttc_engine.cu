@@ -292,6 +292,7 @@ inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
         default:          { constexpr int K = KIND_MVN;     __VA_ARGS__; } break; \
     }
 
+static int QINC_THREADS = std::getenv("TTC_QINC_THREADS") ? std::atoi(std::getenv("TTC_QINC_THREADS")) : 1024;   // k_quad_inc: staging is latency-bound, more loads in flight
 int threads_for(const ttc_handle* h) { return h->kind == TTC_MVN ? 64 : 256; }
 size_t aux_smem(const ttc_handle* h) { return (size_t)h->plan.auxsm * sizeof(double); }
 
@@ -492,7 +493,7 @@ int setup_device(ttc_handle* h, int maxrank) {
         if (h->sm_lua > 200 * 1024) h->use_wave = false;
         {   // k_quad_inc: two packed-LU tables + a staging area for the new row and column (as much as fits in ~96 KB)
             const size_t fixed = (4 * R * R + 3 * R) * sizeof(double);
-            size_t stage = std::min<size_t>((size_t)(2 * R + 1) * (h->nmax + 1) + 64, (64 * 1024) / sizeof(double));
+            size_t stage = std::min<size_t>((size_t)(2 * R + 1) * (h->nmax + 1) + 64, fixed < 136 * 1024 ? (200 * 1024 - fixed) / sizeof(double) - 16 : (64 * 1024) / sizeof(double));
             if (fixed + stage * sizeof(double) > 200 * 1024) h->use_wave = false;
             h->qinc_stage = (int)stage; h->sm_qinc = fixed + stage * sizeof(double);
             if (h->use_wave) cudaFuncSetAttribute(k_quad_inc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_qinc);
@@ -674,7 +675,7 @@ int launch_quad(ttc_handle* h, Launcher& L, bool with_lua, bool use_weights, int
     }
     if (with_lua && !h->force_split) {
         // per-sweep path: only the new row / column of every contracted core (k_quad_inc)
-        L(KC_QUAD, [&] { k_quad_inc<<<ncore, 256, h->sm_qinc, s>>>(D, use_weights ? 1 : 0, h->qinc_stage); });
+        L(KC_QUAD, [&] { k_quad_inc<<<ncore, QINC_THREADS, h->sm_qinc, s>>>(D, use_weights ? 1 : 0, h->qinc_stage); });
     } else {
         L(KC_QUAD, [&] { k_quad_contract_sm<<<dim3(R, ncore), 256, h->sm_contract, s>>>(D, use_weights ? 1 : 0, (int)(h->sm_contract / sizeof(double))); });
         if (with_lua) L(KC_QUAD, [&] { k_quad_lua_sm<<<ncore, 512, h->sm_lua, s>>>(D); });
@@ -806,7 +807,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     KIND_SWITCH(h->kind, L(KC_INIT, [&] { k_init_cross<K><<<dim3(cdiv(h->nmax, TB), d), TB, smA, s>>>(D); }));
     L(KC_INIT, [&] { k_init_factors<<<dim3(cdiv(h->nmax, 256), d), 256, 0, s>>>(D); });
     if (has_quad && h->use_wave && !h->force_split)      // contracted cores of the rank-1 train: extents (1,1) for the incremental quadrature
-        L(KC_INIT, [&] { k_quad_inc<<<D.c_hi - D.c_lo + 1, 256, h->sm_qinc, s>>>(D, 1, h->qinc_stage); });
+        L(KC_INIT, [&] { k_quad_inc<<<D.c_hi - D.c_lo + 1, QINC_THREADS, h->sm_qinc, s>>>(D, 1, h->qinc_stage); });
     // fibers back to the host for the scalar bookkeeping of the '0::' line
     std::vector<std::vector<double>> fib(d + 1);
     for (int p = 1; p <= d; ++p) fib[p].resize(h->n[p]);
