@@ -376,7 +376,9 @@ int setup_device(ttc_handle* h, int maxrank) {
     D.auxsm = 0;
     if (h->kind == TTC_MVN) {
         size_t need = (size_t)d * d * sizeof(double) + (size_t)Rmax * sizeof(double);
-        if (need <= 100 * 1024) D.auxsm = d * d;
+        // the d x d matrix goes to shared memory only while it is small: at d = 64 (32 KB) it would halve the CTAs per SM,
+        // and every thread reads the same element at the same time anyway (one broadcast L1 hit)
+        if (need <= 100 * 1024 && (size_t)d * d * sizeof(double) <= 8 * 1024 && !(std::getenv("TTC_MVN_AUX_GLOBAL"))) D.auxsm = d * d;
     }
     // shared-memory staging of node/weight values (left + right tables of a bond visit hold d-2 positions in total)
     {
@@ -526,11 +528,16 @@ int setup_device(ttc_handle* h, int maxrank) {
     }
     // cluster kernel of the bond visits (ttc_visit.cuh): needs the staged evaluation inputs and the wavefront updates
     {
+        // measured on B200: clusters of 16 x 256 threads while all of them fit the chip at once (config B: 8 partitions, 3.5 ms
+        // against 3.8 ms with 8 x 512); with many partitions the portable 8-CTA clusters win (config E, 63 partitions: 59 ms
+        // against 100 ms with 16)
+        if (D.nv * 16 <= h->nsm) { h->cluster_size = 16; h->cluster_threads = 256; }
+        else { h->cluster_size = 8; h->cluster_threads = (h->kind == TTC_MVN) ? 256 : 512; }
         if (const char* e = std::getenv("TTC_CLUSTER_SIZE")) h->cluster_size = std::atoi(e);
         if (const char* e = std::getenv("TTC_CLUSTER_THREADS")) h->cluster_threads = std::atoi(e);
         h->sm_visit = ((size_t)D.auxsm + Rmax + (size_t)Rmax * Rmax + Rmax + D.stage_max) * sizeof(double) + (size_t)(4 * Rmax + 8) * sizeof(int);
         h->cluster_ok = D.stage && h->use_wave && h->sm_visit <= 200 * 1024 && h->cluster_size >= 1 && h->cluster_size <= MAXCS && h->cluster_threads >= 32 &&
-                        h->cluster_threads <= VISIT_MAXTHREADS && h->cluster_threads % 32 == 0 &&
+                        h->cluster_threads <= (h->kind == TTC_MVN ? 256 : VISIT_MAXTHREADS) && h->cluster_threads % 32 == 0 &&
                         !std::getenv("TTC_NO_CLUSTER");
         if (h->cluster_ok) {
             cudaError_t ce = cudaSuccess;
