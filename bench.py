@@ -334,6 +334,7 @@ def main():
     if rank == 0:
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
+    t.close()            # collective when a communicator is attached (peer windows are unmapped before they are freed)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -30,4 +30,5 @@ else:
     dev = ms[-1][0]
 if rank == 0:
     print(f"config {name} P={P} gpus={world}: device ms {dev:.3f} (runs {[round(m[0],2) for m in ms]}) neval {g.neval} evals/s {g.neval/dev*1e3:.3e} sweeps {g.nsweeps} val {g.vals[-1]!r} ranks {list(map(int,g.ranks))[:6]}...")
+t.close()
 if dist: dist.destroy_process_group()

@@ -57,6 +57,8 @@ struct Ctrl {                   // device-side control of the asynchronous sweep
     int nsweeps;                // sweeps actually performed
     unsigned long long t0_ns;
     int it;                     // current sweep (advanced by k_sweep_begin, so captured graphs carry no sweep number)
+    unsigned long long run_serial;   // ttc_dmrgg call number on this handle (sequence numbers of the peer-memory exchange)
+    unsigned long long quad_serial;  // collective ttc_quad call number
     int has_accuracy;
     double accuracy;
     unsigned long long seed;    // uniform stream seed
@@ -106,6 +108,11 @@ struct DevPlan {
     double* mb2_send; double* mb2_recv;                           // phase 2: per virtual rank [chain Rmax^2 | amax | neval | error | pad]
     double* nb_send_l; double* nb_recv_l;   // to/from the left neighbour process : send column slab [Rmax*nmax]; recv row [nmax*Rmax] | inv [Rmax^2]
     double* nb_send_r; double* nb_recv_r;   // to/from the right neighbour process: send row | inv; recv column slab
+    // peer-memory exchange (one process per GPU, CUDA IPC): the four receive areas above live in ONE window per process;
+    // peer_win[g] is rank g's window mapped into this process, the win_* are byte offsets inside a window.
+    // flags[(phase - 1) * nproc + src] (phase 1, 2, 3 = final quadrature) carry the sequence number of the last push of `src`.
+    char** peer_win; unsigned long long* win_flags;
+    long long win_mb1, win_mb2, win_nbl, win_nbr, win_flg;
     double* ttqy;          // [(d+1)][Rmax*Rmax] contracted cores after d2_luar (incremental per-sweep quadrature, k_quad_inc)
     int* qext;             // [(d+1)][2] extents of ttqy/ttqq already computed
     // diagnostic timeline (ttc_set_timeline): every kernel stamps %globaltimer when its first CTA starts
@@ -1095,9 +1102,10 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__global__ void k_run_begin(DevPlan P, unsigned long long seed, int has_accuracy, double accuracy) {
+__global__ void k_run_begin(DevPlan P, unsigned long long seed, int has_accuracy, double accuracy, unsigned long long run_serial) {
     tl_stamp(P, 7);
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    P.ctrl->run_serial = run_serial;
     P.ctrl->ready = 0; P.ctrl->strike = 0; P.ctrl->error = 0; P.ctrl->nsweeps = 0; P.ctrl->it = 1;
     P.ctrl->seed = seed; P.ctrl->has_accuracy = has_accuracy; P.ctrl->accuracy = accuracy;
     P.ctrl->t0_ns = globaltimer_ns();
@@ -2004,11 +2012,91 @@ __global__ void k_mp_pack1(DevPlan P) {
         for (int x = threadIdx.x; x < n * P.Rmax; x += blockDim.x) P.nb_send_r[x] = a[(i64)P.Rmax * x];
     }
 }
+// ----------------------------------------------------------------------------
+// Peer-memory exchange: the pack kernels' send buffers are STORED straight into the other ranks' windows over NVLink
+// (mapped with CUDA IPC), followed by a system-scope fence and one sequence-number store per destination; the unpack
+// kernels spin on their own window's flags.  One process drives one GPU, so every spinning kernel has its producer
+// running on another GPU; a bounded spin turns a lost peer into an error instead of a hang.
+//   phase 1: mailbox slot block of this rank -> every rank; column slab -> left neighbour's nb_recv_r area; row | inv ->
+//            right neighbour's nb_recv_l area.          phase 2 / 3: chain-product block -> every rank.
+// grid: nproc + 2 CTAs (phase 1), nproc CTAs (phase 2/3).
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mp_seq(const DevPlan& P, int phase) {
+    if (phase == 3) return P.ctrl->quad_serial + 1ULL;
+    return P.ctrl->run_serial * 65536ULL + (unsigned long long)P.ctrl->it;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void k_mp_push(DevPlan P, int phase, long long mb1_words, long long mb2_doubles, long long slab, long long rowinv) {
+    if (phase != 3 && P.ctrl->ready) return;
+    __shared__ int s_last;
+    const int g = blockIdx.x;
+    if (g < P.nproc) {
+        if (phase == 1) {
+            unsigned long long* dst = (unsigned long long*)(P.peer_win[g] + P.win_mb1) + (long long)P.prank * mb1_words;
+            for (long long x = threadIdx.x; x < mb1_words; x += blockDim.x) dst[x] = P.mb1_send[x];
+        } else {
+            double* dst = (double*)(P.peer_win[g] + P.win_mb2) + (long long)P.prank * mb2_doubles;
+            for (long long x = threadIdx.x; x < mb2_doubles; x += blockDim.x) dst[x] = P.mb2_send[x];
+        }
+    } else if (g == P.nproc) {
+        if (P.prank > 0) {      // our new column slab of the shared core: the left rank receives it "from the right"
+            double* dst = (double*)(P.peer_win[P.prank - 1] + P.win_nbr);
+            for (long long x = threadIdx.x; x < slab; x += blockDim.x) dst[x] = P.nb_send_l[x];
+        }
+    } else {
+        if (P.prank < P.nproc - 1) {   // our new row | inv: the right rank receives it "from the left"
+            double* dst = (double*)(P.peer_win[P.prank + 1] + P.win_nbl);
+            for (long long x = threadIdx.x; x < rowinv; x += blockDim.x) dst[x] = P.nb_send_r[x];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(P.tickets + P.P, 1u);
+        s_last = (t == gridDim.x - 1);
+        if (s_last) P.tickets[P.P] = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    const unsigned long long seq = mp_seq(P, phase);
+    for (int q = threadIdx.x; q < P.nproc; q += blockDim.x)
+        st_release_sys((unsigned long long*)(P.peer_win[q] + P.win_flg) + (long long)(phase - 1) * P.nproc + P.prank, seq);
+    if (phase == 3 && threadIdx.x == 0) P.ctrl->quad_serial = seq;
+}
+// every consumer CTA calls this first: wait until all ranks' pushes of this phase have landed in the local window
+__device__ __forceinline__ void mp_wait(const DevPlan& P, int phase) {
+    if (!P.peer_win) return;                        // NCCL transport: the stream orders the receive
+    if (threadIdx.x == 0) {
+        // phase 3 is consumed after this rank's own push already advanced quad_serial
+        const unsigned long long seq = (phase == 3) ? P.ctrl->quad_serial : mp_seq(P, phase);
+        unsigned long long t0 = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (int q = 0; q < P.nproc; ++q) {
+            const unsigned long long* f = P.win_flags + (long long)(phase - 1) * P.nproc + q;
+            while (ld_acquire_sys(f) < seq) {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 4000000000ULL) { P.ctrl->error = 3; break; }     // 4 s: a peer is gone
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+}
 // grid: P CTAs, CTA v handles foreign virtual rank v: state + visit records, then the replay of its accepted pivots
 // (the index-set half of k_accept) in visit order.
 __global__ void k_mp_unpack1(DevPlan P) {
     tl_stamp(P, 30);
     if (P.ctrl->ready) return;
+    mp_wait(P, 1);
     const int v = blockIdx.x;
     if (own_vrank(P, v)) return;
     const int it = P.ctrl->it;
@@ -2086,6 +2174,7 @@ __global__ void k_mp_pack2(DevPlan P, int final) {
 __global__ void k_mp_unpack2(DevPlan P, int final) {
     tl_stamp(P, 33);
     if (!final && P.ctrl->ready) return;
+    mp_wait(P, final ? 3 : 2);
     const int v = blockIdx.x;
     if (own_vrank(P, v)) return;
     int g = 0;

@@ -142,6 +142,9 @@ struct ttc_handle {
     NcclComm comm = nullptr; int nproc = 1, prank = 0;
     int timeline = 0; unsigned long long* tlog_d = nullptr; int* tlog_n_d = nullptr;
     size_t mb1_bytes = 0, mb2_count = 0, nbl_send = 0, nbl_recv = 0;   // message sizes per process / neighbour
+    // peer-memory transport (CUDA IPC windows); p2p = false -> NCCL send/recv/all-gather
+    bool p2p = false; char* win = nullptr; size_t win_bytes = 0; std::vector<char*> peer_ptrs; char** peer_win_d = nullptr;
+    unsigned long long mp_run = 0;
 
     std::vector<int> setup_sig;
     std::vector<double> quad_or_ones() const {
@@ -240,9 +243,73 @@ int dev_upload(ttc_handle* h, T** p, const std::vector<T>& v) {
     return 0;
 }
 
+// all ranks reach this point (tiny NCCL all-gather + stream synchronisation)
+int comm_barrier(ttc_handle* h) {
+    if (!h->comm || !h->stream) return 0;
+    int* d = nullptr;
+    if (cudaMalloc((void**)&d, sizeof(int) * (h->nproc + 1)) != cudaSuccess) return TTC_ERR_CUDA;
+    int e = nccl_api().AllGather(d + h->nproc, d, 1, NCCL_INT8, h->comm, h->stream);
+    cudaError_t ce = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    return (e || ce != cudaSuccess) ? TTC_ERR_COMM : 0;
+}
+// unmap the peers' windows, wait until every rank has done so, free our own
+void window_teardown(ttc_handle* h) {
+    if (!h->win) return;
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int g = 0; g < (int)h->peer_ptrs.size(); ++g)
+        if (g != h->prank && h->peer_ptrs[g]) cudaIpcCloseMemHandle(h->peer_ptrs[g]);
+    h->peer_ptrs.clear();
+    comm_barrier(h);
+    cudaFree(h->win); h->win = nullptr; h->win_bytes = 0;
+    if (h->peer_win_d) { cudaFree(h->peer_win_d); h->peer_win_d = nullptr; }
+    h->p2p = false;
+}
+// one window per rank: mb1_recv | mb2_recv | nb_recv_l | nb_recv_r | flags; IPC handles travel by NCCL all-gather
+int window_setup(ttc_handle* h, size_t w1, size_t w2, size_t slab, size_t rowinv) {
+    DevPlan& D = h->plan;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o1 = 0, o2 = o1 + al(w1 * h->nproc * 8), o3 = o2 + al(w2 * h->nproc * 8), o4 = o3 + al(rowinv * 8),
+                 o5 = o4 + al(slab * 8), tot = o5 + al(3 * (size_t)h->nproc * 8);
+    CUDA_TRY(h, cudaMalloc((void**)&h->win, tot));
+    h->win_bytes = tot;
+    CUDA_TRY(h, cudaMemsetAsync(h->win, 0, tot, h->stream));
+    D.win_mb1 = (long long)o1; D.win_mb2 = (long long)o2; D.win_nbl = (long long)o3; D.win_nbr = (long long)o4; D.win_flg = (long long)o5;
+    D.mb1_recv = (unsigned long long*)(h->win + o1); D.mb2_recv = (double*)(h->win + o2);
+    D.nb_recv_l = (double*)(h->win + o3); D.nb_recv_r = (double*)(h->win + o4);
+    D.win_flags = (unsigned long long*)(h->win + o5);
+    cudaIpcMemHandle_t mine;
+    CUDA_TRY(h, cudaIpcGetMemHandle(&mine, h->win));
+    char* dh = nullptr;
+    CUDA_TRY(h, cudaMalloc((void**)&dh, sizeof(mine) * h->nproc));
+    CUDA_TRY(h, cudaMemcpyAsync(dh + sizeof(mine) * h->prank, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+    int e = nccl_api().AllGather(dh + sizeof(mine) * h->prank, dh, sizeof(mine), NCCL_INT8, h->comm, h->stream);
+    std::vector<cudaIpcMemHandle_t> all(h->nproc);
+    cudaError_t ce = cudaMemcpyAsync(all.data(), dh, sizeof(mine) * h->nproc, cudaMemcpyDeviceToHost, h->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+    cudaFree(dh);
+    if (e) { h->err = "window_setup: NCCL all-gather of the IPC handles failed"; return TTC_ERR_COMM; }
+    CUDA_TRY(h, ce);
+    h->peer_ptrs.assign(h->nproc, nullptr);
+    for (int g = 0; g < h->nproc; ++g) {
+        if (g == h->prank) { h->peer_ptrs[g] = h->win; continue; }
+        void* q = nullptr;
+        cudaError_t oe = cudaIpcOpenMemHandle(&q, all[g], cudaIpcMemLazyEnablePeerAccess);
+        if (oe != cudaSuccess) { (void)cudaGetLastError(); h->err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(oe); return TTC_ERR_COMM; }
+        h->peer_ptrs[g] = (char*)q;
+    }
+    CUDA_TRY(h, cudaMalloc((void**)&h->peer_win_d, sizeof(char*) * h->nproc));
+    CUDA_TRY(h, cudaMemcpyAsync(h->peer_win_d, h->peer_ptrs.data(), sizeof(char*) * h->nproc, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    D.peer_win = h->peer_win_d;
+    h->p2p = true;
+    return 0;
+}
+
 void free_device(ttc_handle* h) {
     h->setup_sig.clear();
     if (h->stream) cudaStreamSynchronize(h->stream);
+    window_teardown(h);
     for (int g = 0; g < 2; ++g) if (h->gexec[g]) { cudaGraphExecDestroy(h->gexec[g]); h->gexec[g] = nullptr; }
     h->graph_sig.clear();
     {
@@ -475,12 +542,18 @@ int setup_device(ttc_handle* h, int maxrank) {
             const size_t slab = (size_t)Rmax * h->nmax, rowinv = slab + (size_t)Rmax * Rmax;
             unsigned long long *s1, *r1; double *s2, *r2, *sl, *rl, *sr, *rr;
             s1 = nullptr; r1 = nullptr; s2 = r2 = sl = rl = sr = rr = nullptr;
-            if ((s1 = nullptr, dev_alloc(h, &s1, w1)) || dev_alloc(h, &r1, w1 * h->nproc) || dev_alloc(h, &s2, w2) ||
-                dev_alloc(h, &r2, w2 * h->nproc) || dev_alloc(h, &sl, slab) || dev_alloc(h, &rl, rowinv) ||
-                dev_alloc(h, &sr, rowinv) || dev_alloc(h, &rr, slab)) return TTC_ERR_CUDA;
-            D.mb1_send = s1; D.mb1_recv = r1; D.mb2_send = s2; D.mb2_recv = r2;
-            D.nb_send_l = sl; D.nb_recv_l = rl; D.nb_send_r = sr; D.nb_recv_r = rr;
+            if (dev_alloc(h, &s1, w1) || dev_alloc(h, &s2, w2) || dev_alloc(h, &sl, slab) || dev_alloc(h, &sr, rowinv)) return TTC_ERR_CUDA;
+            D.mb1_send = s1; D.mb2_send = s2; D.nb_send_l = sl; D.nb_send_r = sr;
             h->mb1_bytes = w1 * 8; h->mb2_count = w2; h->nbl_send = slab; h->nbl_recv = rowinv;
+            D.peer_win = nullptr; D.win_flags = nullptr;
+            int pe = std::getenv("TTC_MP_NCCL") ? TTC_ERR_COMM : window_setup(h, w1, w2, slab, rowinv);   // peer-memory windows (CUDA IPC)...
+            if (pe) {                                                                                    // ...or NCCL receive buffers
+                if (h->win) { cudaFree(h->win); h->win = nullptr; }
+                h->p2p = false; D.peer_win = nullptr; D.win_flags = nullptr;
+                if (!std::getenv("TTC_MP_NCCL") && std::getenv("TTC_MP_P2P_REQUIRED")) return pe;
+                if (dev_alloc(h, &r1, w1 * h->nproc) || dev_alloc(h, &r2, w2 * h->nproc) || dev_alloc(h, &rl, rowinv) || dev_alloc(h, &rr, slab)) return TTC_ERR_CUDA;
+                D.mb1_recv = r1; D.mb2_recv = r2; D.nb_recv_l = rl; D.nb_recv_r = rr;
+            }
         }
     }
 
@@ -637,6 +710,12 @@ int mp_phase1(ttc_handle* h, Launcher& L) {
     cudaStream_t s = h->stream;
     NcclApi& N = nccl_api();
     L(KC_EXCHANGE, [&] { k_mp_pack1<<<D.nv + 2, 256, 0, s>>>(D); });
+    if (h->p2p) {     // stores into the peers' windows + flags; the unpack kernels wait on the flags
+        L(KC_EXCHANGE, [&] { k_mp_push<<<h->nproc + 2, 512, 0, s>>>(D, 1, (long long)(h->mb1_bytes / 8), (long long)h->mb2_count, (long long)h->nbl_send, (long long)h->nbl_recv); });
+        L(KC_EXCHANGE, [&] { k_mp_unpack1<<<D.P, 128, 0, s>>>(D); });
+        L(KC_EXCHANGE, [&] { k_mp_unpack1b<<<dim3(8, 2), 256, 0, s>>>(D); });
+        return 0;
+    }
     NCCL_TRY(h, N.GroupStart());
     int e = N.AllGather(D.mb1_send, D.mb1_recv, h->mb1_bytes, NCCL_INT8, h->comm, s);
     if (!e && h->prank > 0) {
@@ -659,6 +738,11 @@ int mp_phase2(ttc_handle* h, Launcher& L, int final) {
     cudaStream_t s = h->stream;
     NcclApi& N = nccl_api();
     L(KC_EXCHANGE, [&] { k_mp_pack2<<<D.nv, 256, 0, s>>>(D, final); });
+    if (h->p2p) {
+        L(KC_EXCHANGE, [&] { k_mp_push<<<h->nproc, 512, 0, s>>>(D, final ? 3 : 2, (long long)(h->mb1_bytes / 8), (long long)h->mb2_count, (long long)h->nbl_send, (long long)h->nbl_recv); });
+        L(KC_EXCHANGE, [&] { k_mp_unpack2<<<D.P, 256, 0, s>>>(D, final); });
+        return 0;
+    }
     NCCL_TRY(h, N.AllGather(D.mb2_send, D.mb2_recv, h->mb2_count, NCCL_FLOAT64, h->comm, s));
     L(KC_EXCHANGE, [&] { k_mp_unpack2<<<D.P, 256, 0, s>>>(D, final); });
     return 0;
@@ -750,7 +834,8 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         D.tlog = h->tlog_d; D.tlog_n = h->tlog_n_d; D.tlog_cap = 65536;
     } else { D.tlog = nullptr; D.tlog_n = nullptr; D.tlog_cap = 0; }
     CUDA_TRY(h, cudaEventRecord(h->ev0, s));
-    L(KC_MISC, [&] { k_run_begin<<<1, 32, 0, s>>>(D, h->seed, accuracy >= 0 ? 1 : 0, accuracy); });
+    h->mp_run += 1;
+    L(KC_MISC, [&] { k_run_begin<<<1, 32, 0, s>>>(D, h->seed, accuracy >= 0 ? 1 : 0, accuracy, h->mp_run); });
 
     // ---- initial cross search (dmrgg.f90:150-217)
     const int snum = std::max(8, P);
@@ -1002,7 +1087,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     // kernel launches.  Grids are sized for the rank capacity; surplus CTAs exit at once.
     int graph_sweeps = 4;                 // even: every graph starts with a '>>' sweep
     if (const char* e = std::getenv("TTC_GRAPH_SWEEPS")) graph_sweeps = std::max(2, 2 * (std::atoi(e) / 2));
-    const bool use_graph = !sync_mode && !h->profile && !h->no_graph && (!multi || std::getenv("TTC_MP_GRAPH") != nullptr);
+    const bool use_graph = !sync_mode && !h->profile && !h->no_graph && (!multi || h->p2p || std::getenv("TTC_MP_GRAPH") != nullptr);
     if (use_graph) {
         std::vector<long long> gsig = {(long long)h->piv, (long long)has_quad, (long long)maxrank, (long long)h->use_wave, (long long)dev_lot,
                                        (long long)h->setup_serial, (long long)h->timeline, (long long)use_cluster,
@@ -1084,6 +1169,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     // ---- read the logs back and rebuild the reference's report
     Ctrl ctrl;
     CUDA_TRY(h, cudaMemcpy(&ctrl, D.ctrl, sizeof ctrl, cudaMemcpyDeviceToHost));
+    if (ctrl.error == 3) { h->err = "multi-GPU exchange timed out waiting for a peer rank"; return TTC_ERR_COMM; }
     if (ctrl.error == 2) { h->err = "internal: the incremental quadrature saw a rank grow by more than one in a sweep"; return TTC_ERR_STATE; }
     if (ctrl.error) { h->err = "rank capacity exceeded (pass maxrank)"; return TTC_ERR_RANK; }
     it = ctrl.nsweeps;
@@ -1180,6 +1266,7 @@ int ttc_create(ttc_handle** out, int kind, int d, const int* n, const double* pa
 void ttc_destroy(ttc_handle* h) {
     if (!h) return;
     if (h->stream || !h->allocs.empty()) { cudaSetDevice(h->device); free_device(h); }
+    if (h->win) { cudaSetDevice(h->device); window_teardown(h); }
     if (h->comm) { cudaSetDevice(h->device); nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->flush_d) cudaFree(h->flush_d);
     if (h->tlog_d) { cudaFree(h->tlog_d); cudaFree(h->tlog_n_d); }
