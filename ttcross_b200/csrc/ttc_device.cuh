@@ -1979,47 +1979,13 @@ __host__ __device__ __forceinline__ int mb1_slot_words(int maxnb) { return maxnb
 __host__ __device__ __forceinline__ int mb2_slot_doubles(int Rmax) { return Rmax * Rmax + 4; }
 
 // grid: nv + 2 CTAs.  CTA b < nv: mailbox slot of virtual rank v0+b.  CTA nv: slab for the left process.  CTA nv+1: right.
-__global__ void k_mp_pack1(DevPlan P) {
-    tl_stamp(P, 29);
-    if (P.ctrl->ready) return;
-    const int it = P.ctrl->it;
-    const int b = blockIdx.x;
-    if (b < P.nv) {
-        const int v = P.v0 + b;
-        unsigned long long* slot = P.mb1_send + (i64)b * mb1_slot_words(P.maxnb);
-        for (int x = threadIdx.x; x < P.maxnb * VO_WORDS; x += blockDim.x) {
-            const int pp = x / VO_WORDS, w = x - pp * VO_WORDS;
-            slot[x] = ((const unsigned long long*)&P.vlog[((i64)(it - 1) * P.maxnb + pp) * P.P + v])[w];
-        }
-        for (int x = threadIdx.x; x < VS_WORDS; x += blockDim.x)
-            slot[P.maxnb * VO_WORDS + x] = ((const unsigned long long*)&P.st[v])[x];
-    } else if (b == P.nv) {
-        if (P.v0 == 0) return;
-        const int c = P.own[P.v0];                       // shared with the left process; our bond c
-        if (!(P.rk[c] > P.rks[c])) return;
-        const int n = P.n[c];
-        const double* slab = P.arg + P.coreOff[c] + (i64)P.Rmax * n * P.rks[c];   // new slice, contiguous
-        for (int x = threadIdx.x; x < P.Rmax * n; x += blockDim.x) P.nb_send_l[x] = slab[x];
-    } else {
-        if (P.v0 + P.nv >= P.P) return;
-        const int c = P.own[P.v0 + P.nv];                // shared with the right process; our bond c-1
-        const int n = P.n[c];
-        const double* g = P.inv + (i64)(c - 1) * P.Rmax * P.Rmax;
-        double* ginv = P.nb_send_r + (i64)P.nmax * P.Rmax;
-        for (int x = threadIdx.x; x < P.Rmax * P.Rmax; x += blockDim.x) ginv[x] = g[x];
-        if (!(P.rk[c - 1] > P.rks[c - 1])) return;
-        const double* a = P.arg + P.coreOff[c] + P.rks[c - 1];                    // new row t, stride Rmax
-        for (int x = threadIdx.x; x < n * P.Rmax; x += blockDim.x) P.nb_send_r[x] = a[(i64)P.Rmax * x];
-    }
-}
 // ----------------------------------------------------------------------------
-// Peer-memory exchange: the pack kernels' send buffers are STORED straight into the other ranks' windows over NVLink
-// (mapped with CUDA IPC), followed by a system-scope fence and one sequence-number store per destination; the unpack
-// kernels spin on their own window's flags.  One process drives one GPU, so every spinning kernel has its producer
-// running on another GPU; a bounded spin turns a lost peer into an error instead of a hang.
-//   phase 1: mailbox slot block of this rank -> every rank; column slab -> left neighbour's nb_recv_r area; row | inv ->
-//            right neighbour's nb_recv_l area.          phase 2 / 3: chain-product block -> every rank.
-// grid: nproc + 2 CTAs (phase 1), nproc CTAs (phase 2/3).
+// Peer-memory exchange: the pack kernels STORE straight into the other ranks' windows over NVLink (mapped with CUDA
+// IPC), followed by a system-scope fence and one sequence-number store per destination; the unpack kernels spin on
+// their own window's flags.  One process drives one GPU, so every spinning kernel has its producer running on another
+// GPU; a bounded spin turns a lost peer into an error instead of a hang.
+//   phase 1: mailbox slots of this rank's partitions -> every rank; column slab -> left neighbour's nb_recv_r area;
+//            row | inv -> right neighbour's nb_recv_l area.          phase 2 / 3: chain-product slots -> every rank.
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long mp_seq(const DevPlan& P, int phase) {
     if (phase == 3) return P.ctrl->quad_serial + 1ULL;
@@ -2033,29 +1999,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__global__ void k_mp_push(DevPlan P, int phase, long long mb1_words, long long mb2_doubles, long long slab, long long rowinv) {
-    if (phase != 3 && P.ctrl->ready) return;
+// epilogue of a packing kernel (every thread of every CTA calls it): once the whole grid's stores are fenced, the last CTA
+// stores this phase's sequence number into every rank's flag slot for this source
+__device__ __forceinline__ void mp_publish(const DevPlan& P, int phase) {
     __shared__ int s_last;
-    const int g = blockIdx.x;
-    if (g < P.nproc) {
-        if (phase == 1) {
-            unsigned long long* dst = (unsigned long long*)(P.peer_win[g] + P.win_mb1) + (long long)P.prank * mb1_words;
-            for (long long x = threadIdx.x; x < mb1_words; x += blockDim.x) dst[x] = P.mb1_send[x];
-        } else {
-            double* dst = (double*)(P.peer_win[g] + P.win_mb2) + (long long)P.prank * mb2_doubles;
-            for (long long x = threadIdx.x; x < mb2_doubles; x += blockDim.x) dst[x] = P.mb2_send[x];
-        }
-    } else if (g == P.nproc) {
-        if (P.prank > 0) {      // our new column slab of the shared core: the left rank receives it "from the right"
-            double* dst = (double*)(P.peer_win[P.prank - 1] + P.win_nbr);
-            for (long long x = threadIdx.x; x < slab; x += blockDim.x) dst[x] = P.nb_send_l[x];
-        }
-    } else {
-        if (P.prank < P.nproc - 1) {   // our new row | inv: the right rank receives it "from the left"
-            double* dst = (double*)(P.peer_win[P.prank + 1] + P.win_nbl);
-            for (long long x = threadIdx.x; x < rowinv; x += blockDim.x) dst[x] = P.nb_send_r[x];
-        }
-    }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -2070,6 +2017,51 @@ __global__ void k_mp_push(DevPlan P, int phase, long long mb1_words, long long m
     for (int q = threadIdx.x; q < P.nproc; q += blockDim.x)
         st_release_sys((unsigned long long*)(P.peer_win[q] + P.win_flg) + (long long)(phase - 1) * P.nproc + P.prank, seq);
     if (phase == 3 && threadIdx.x == 0) P.ctrl->quad_serial = seq;
+}
+__global__ void k_mp_pack1(DevPlan P) {
+    tl_stamp(P, 29);
+    if (P.ctrl->ready) return;
+    const int it = P.ctrl->it;
+    const int b = blockIdx.x;
+    const bool p2p = P.peer_win != nullptr;
+    const int sw = mb1_slot_words(P.maxnb);
+    if (b < P.nv) {
+        const int v = P.v0 + b;
+        for (int g = 0; g < (p2p ? P.nproc : 1); ++g) {
+            unsigned long long* slot = p2p ? (unsigned long long*)(P.peer_win[g] + P.win_mb1) + ((i64)P.prank * P.vper + b) * sw
+                                           : P.mb1_send + (i64)b * sw;
+            for (int x = threadIdx.x; x < P.maxnb * VO_WORDS; x += blockDim.x) {
+                const int pp = x / VO_WORDS, w = x - pp * VO_WORDS;
+                slot[x] = ((const unsigned long long*)&P.vlog[((i64)(it - 1) * P.maxnb + pp) * P.P + v])[w];
+            }
+            for (int x = threadIdx.x; x < VS_WORDS; x += blockDim.x)
+                slot[P.maxnb * VO_WORDS + x] = ((const unsigned long long*)&P.st[v])[x];
+        }
+    } else if (b == P.nv) {
+        if (P.v0 > 0) {
+            const int c = P.own[P.v0];                       // shared with the left process; our bond c
+            if (P.rk[c] > P.rks[c]) {
+                const int n = P.n[c];
+                const double* slab = P.arg + P.coreOff[c] + (i64)P.Rmax * n * P.rks[c];   // new slice, contiguous
+                double* dst = p2p ? (double*)(P.peer_win[P.prank - 1] + P.win_nbr) : P.nb_send_l;   // the left rank receives "from the right"
+                for (int x = threadIdx.x; x < P.Rmax * n; x += blockDim.x) dst[x] = slab[x];
+            }
+        }
+    } else {
+        if (P.v0 + P.nv < P.P) {
+            const int c = P.own[P.v0 + P.nv];                // shared with the right process; our bond c-1
+            const int n = P.n[c];
+            const double* g = P.inv + (i64)(c - 1) * P.Rmax * P.Rmax;
+            double* dst = p2p ? (double*)(P.peer_win[P.prank + 1] + P.win_nbl) : P.nb_send_r;       // the right rank receives "from the left"
+            double* ginv = dst + (i64)P.nmax * P.Rmax;
+            for (int x = threadIdx.x; x < P.Rmax * P.Rmax; x += blockDim.x) ginv[x] = g[x];
+            if (P.rk[c - 1] > P.rks[c - 1]) {
+                const double* a = P.arg + P.coreOff[c] + P.rks[c - 1];                    // new row t, stride Rmax
+                for (int x = threadIdx.x; x < n * P.Rmax; x += blockDim.x) dst[x] = a[(i64)P.Rmax * x];
+            }
+        }
+    }
+    if (p2p) mp_publish(P, 1);
 }
 // every consumer CTA calls this first: wait until all ranks' pushes of this phase have landed in the local window
 __device__ __forceinline__ void mp_wait(const DevPlan& P, int phase) {
@@ -2135,6 +2127,17 @@ __global__ void k_mp_unpack1b(DevPlan P) {
     tl_stamp(P, 31);
     if (P.ctrl->ready) return;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && P.P > 1) {
+        // MPI_ALLREDUCE(MAX) of (amax, pivotmax, -pivotmin) (dmrgg.f90:852-870) over the gathered states (k_allreduce)
+        double c1 = P.st[0].amax, c2 = P.st[0].pivotmax, c3 = (P.st[0].pivotmin > 0.0) ? -P.st[0].pivotmin : -999e9;
+        for (int v = 1; v < P.P; ++v) {
+            c1 = fmax(c1, P.st[v].amax); c2 = fmax(c2, P.st[v].pivotmax);
+            c3 = fmax(c3, (P.st[v].pivotmin > 0.0) ? -P.st[v].pivotmin : -999e9);
+        }
+        for (int v = 0; v < P.P; ++v) {
+            P.st[v].amax = c1; P.st[v].pivotmax = c2; P.st[v].pivotmin = (-c3 == 999e9) ? -1.0 : -c3;
+        }
+    }
     if (blockIdx.y == 0) {
         if (P.v0 == 0) return;
         const int c = P.own[P.v0];
@@ -2161,15 +2164,20 @@ __global__ void k_mp_pack2(DevPlan P, int final) {
     if (!final && P.ctrl->ready) return;
     const int b = blockIdx.x, v = P.v0 + b;
     const int msz = P.Rmax * P.Rmax;
-    double* slot = P.mb2_send + (i64)b * mb2_slot_doubles(P.Rmax);
+    const bool p2p = P.peer_win != nullptr;
     const double* ch = P.chain + (i64)v * msz;
-    for (int x = threadIdx.x; x < msz; x += blockDim.x) slot[x] = ch[x];
-    if (threadIdx.x == 0) {
-        slot[msz] = P.st[v].amax;
-        slot[msz + 1] = __longlong_as_double(P.st[v].neval);
-        slot[msz + 2] = __longlong_as_double((long long)P.ctrl->error);
-        slot[msz + 3] = 0.0;
+    for (int g = 0; g < (p2p ? P.nproc : 1); ++g) {
+        double* slot = p2p ? (double*)(P.peer_win[g] + P.win_mb2) + ((i64)P.prank * P.vper + b) * mb2_slot_doubles(P.Rmax)
+                           : P.mb2_send + (i64)b * mb2_slot_doubles(P.Rmax);
+        for (int x = threadIdx.x; x < msz; x += blockDim.x) slot[x] = ch[x];
+        if (threadIdx.x == 0) {
+            slot[msz] = P.st[v].amax;
+            slot[msz + 1] = __longlong_as_double(P.st[v].neval);
+            slot[msz + 2] = __longlong_as_double((long long)P.ctrl->error);
+            slot[msz + 3] = 0.0;
+        }
     }
+    if (p2p) mp_publish(P, final ? 3 : 2);
 }
 __global__ void k_mp_unpack2(DevPlan P, int final) {
     tl_stamp(P, 33);

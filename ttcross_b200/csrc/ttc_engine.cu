@@ -711,7 +711,6 @@ int mp_phase1(ttc_handle* h, Launcher& L) {
     NcclApi& N = nccl_api();
     L(KC_EXCHANGE, [&] { k_mp_pack1<<<D.nv + 2, 256, 0, s>>>(D); });
     if (h->p2p) {     // stores into the peers' windows + flags; the unpack kernels wait on the flags
-        L(KC_EXCHANGE, [&] { k_mp_push<<<h->nproc + 2, 512, 0, s>>>(D, 1, (long long)(h->mb1_bytes / 8), (long long)h->mb2_count, (long long)h->nbl_send, (long long)h->nbl_recv); });
         L(KC_EXCHANGE, [&] { k_mp_unpack1<<<D.P, 128, 0, s>>>(D); });
         L(KC_EXCHANGE, [&] { k_mp_unpack1b<<<dim3(8, 2), 256, 0, s>>>(D); });
         return 0;
@@ -739,7 +738,6 @@ int mp_phase2(ttc_handle* h, Launcher& L, int final) {
     NcclApi& N = nccl_api();
     L(KC_EXCHANGE, [&] { k_mp_pack2<<<D.nv, 256, 0, s>>>(D, final); });
     if (h->p2p) {
-        L(KC_EXCHANGE, [&] { k_mp_push<<<h->nproc, 512, 0, s>>>(D, final ? 3 : 2, (long long)(h->mb1_bytes / 8), (long long)h->mb2_count, (long long)h->nbl_send, (long long)h->nbl_recv); });
         L(KC_EXCHANGE, [&] { k_mp_unpack2<<<D.P, 256, 0, s>>>(D, final); });
         return 0;
     }
@@ -1069,7 +1067,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         if (P > 1) {
             if (multi) { int e = mp_phase1(h, L); if (e) return e; }
             const int nbnd = boundary_count(D);
-            if (multi || !use_cluster) L(KC_EXCHANGE, [&] { k_allreduce<<<1, 32, 0, s>>>(D); });
+            if (!multi && !use_cluster) L(KC_EXCHANGE, [&] { k_allreduce<<<1, 32, 0, s>>>(D); });   // (several processes: folded into k_mp_unpack1b)
             KIND_SWITCH(h->kind, L(KC_EXCHANGE, [&] { k_exchange_corner<K><<<dim3(1, nbnd), TB, smA + 2 * (size_t)d * sizeof(double), s>>>(D); }));
             if (h->use_wave) L(KC_EXCHANGE, [&] { k_exchange_extend_w<<<dim3(cdiv(h->nmax, 8), nbnd, 2), 256, h->sm_ext, s>>>(D); });
             else L(KC_EXCHANGE, [&] { k_exchange_extend<<<dim3(cdiv(2 * h->nmax, 64), nbnd), 64, 0, s>>>(D); });
