@@ -35,30 +35,38 @@ def main():
     lines = []
     for arg in sys.argv[1:]:
         name, path = arg.split("=", 1)
-        hdr, units, rows = load(path)
-        n = len(rows)
-        avg = lambda m: sum(col(hdr, units, r, m) or 0.0 for r in rows) / n
-        stalls = {h.split("issue_stalled_")[1].split("_per_issue")[0]: sum(float(r[i] or 0) for r in rows) / n
-                  for i, h in enumerate(hdr) if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("per_issue_active.ratio")}
-        top = sorted(stalls.items(), key=lambda kv: -kv[1])[:5]
-        e = {
-            "kernel": rows[0][hdr.index("Kernel Name")], "launches_captured": n, "report": os.path.basename(path),
-            "duration_us": avg("gpu__time_duration.sum"),
-            "dram_bytes_per_launch": avg("dram__bytes_read.sum") + avg("dram__bytes_write.sum"),
-            "dram_read_bytes": avg("dram__bytes_read.sum"), "dram_write_bytes": avg("dram__bytes_write.sum"),
-            "fp64_pipe_pct_of_peak_active": avg("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
-            "fp64_pipe_pct_of_peak_elapsed": avg("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed"),
-            "issue_active_pct": avg("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-            "warps_active_pct": avg("sm__warps_active.avg.pct_of_peak_sustained_active"),
-            "registers_per_thread": avg("launch__registers_per_thread"),
-            "shared_mem_per_block_bytes": avg("launch__shared_mem_per_block_allocated"),
-            "warp_instructions": avg("smsp__inst_executed.sum"),
-            "top_stalls_per_issue": {k: round(v, 3) for k, v in top},
-        }
-        summary[name] = e
-        lines.append(f"{name:16s} {e['duration_us']:9.1f} us  dram {e['dram_bytes_per_launch'] / 1e6:8.3f} MB/launch  fp64 pipe "
-                     f"{e['fp64_pipe_pct_of_peak_active']:5.1f}% (active) {e['fp64_pipe_pct_of_peak_elapsed']:5.1f}% (elapsed)  issue "
-                     f"{e['issue_active_pct']:5.1f}%  warps {e['warps_active_pct']:5.1f}%  regs {e['registers_per_thread']:.0f}  stalls {e['top_stalls_per_issue']}")
+        hdr, units, allrows = load(path)
+        kn = hdr.index("Kernel Name")
+        if name == "*":          # one entry per kernel found in the report, keyed by its short name
+            groups = {}
+            for r in allrows:
+                groups.setdefault(r[kn].replace("void ", "").split("(")[0].split("<")[0], []).append(r)
+        else:
+            groups = {name: allrows}
+        for name, rows in groups.items():
+          n = len(rows)
+          avg = lambda m: sum(col(hdr, units, r, m) or 0.0 for r in rows) / n
+          stalls = {h.split("issue_stalled_")[1].split("_per_issue")[0]: sum(float(r[i] or 0) for r in rows) / n
+                    for i, h in enumerate(hdr) if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("per_issue_active.ratio")}
+          top = sorted(stalls.items(), key=lambda kv: -kv[1])[:5]
+          e = {
+              "kernel": rows[0][hdr.index("Kernel Name")], "launches_captured": n, "report": os.path.basename(path),
+              "duration_us": avg("gpu__time_duration.sum"),
+              "dram_bytes_per_launch": avg("dram__bytes_read.sum") + avg("dram__bytes_write.sum"),
+              "dram_read_bytes": avg("dram__bytes_read.sum"), "dram_write_bytes": avg("dram__bytes_write.sum"),
+              "fp64_pipe_pct_of_peak_active": avg("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+              "fp64_pipe_pct_of_peak_elapsed": avg("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+              "issue_active_pct": avg("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+              "warps_active_pct": avg("sm__warps_active.avg.pct_of_peak_sustained_active"),
+              "registers_per_thread": avg("launch__registers_per_thread"),
+              "shared_mem_per_block_bytes": avg("launch__shared_mem_per_block_allocated"),
+              "warp_instructions": avg("smsp__inst_executed.sum"),
+              "top_stalls_per_issue": {k: round(v, 3) for k, v in top},
+          }
+          summary[name] = e
+          lines.append(f"{name:16s} {e['duration_us']:9.1f} us  dram {e['dram_bytes_per_launch'] / 1e6:8.3f} MB/launch  fp64 pipe "
+                       f"{e['fp64_pipe_pct_of_peak_active']:5.1f}% (active) {e['fp64_pipe_pct_of_peak_elapsed']:5.1f}% (elapsed)  issue "
+                       f"{e['issue_active_pct']:5.1f}%  warps {e['warps_active_pct']:5.1f}%  regs {e['registers_per_thread']:.0f}  stalls {e['top_stalls_per_issue']}")
     here = os.path.dirname(os.path.abspath(__file__))
     old = {}
     p = os.path.join(here, "r01_ncu_summary.json")
