@@ -621,7 +621,7 @@ int setup_device(ttc_handle* h, int maxrank) {
             if (ce != cudaSuccess) { (void)cudaGetLastError(); h->cluster_ok = false; }
             // clusters of 16 are a non-portable size: ask the driver whether one fits, else fall back to the portable 8 x 512
             auto fits = [&](int cs, int tb) {
-                cudaLaunchConfig_t cfg; std::memset(&cfg, 0, sizeof cfg);
+                cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3(cs, 1, 1); cfg.blockDim = dim3(tb, 1, 1); cfg.dynamicSmemBytes = h->sm_visit;
                 cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
                 at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1048,8 +1048,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     auto enqueue_sweep = [&](int dir, int rb) -> int {
         if (sync_mode) h->rks_h = h->rk_h;
         if (use_cluster) {
-            cudaLaunchConfig_t cfg;
-            std::memset(&cfg, 0, sizeof cfg);
+            cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(h->cluster_size, NV, 1);
             cfg.blockDim = dim3(h->cluster_threads, 1, 1);
             cfg.dynamicSmemBytes = h->sm_visit;
@@ -1114,7 +1113,6 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         }
     }
     tr.lap("graph_capture");
-    int enq = 0;
     for (it = 1; it <= last_sweep; ++it) {
         if (!multi && *(volatile int*)h->ready_h) break;   // device already reached its exit condition
         int e = 0;
@@ -1128,7 +1126,6 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
             e = enqueue_sweep(2 - it % 2, std::min(it + 1, Rmax));
         }
         if (e) return e;
-        enq = it;
         CUDA_TRY(h, cudaMemcpyAsync(h->ready_h, &D.ctrl->ready, sizeof(int), cudaMemcpyDeviceToHost, s));
         if (sync_mode) {
             CUDA_TRY(h, cudaStreamSynchronize(s));
@@ -1148,7 +1145,6 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
             }
         }
     }
-    (void)enq;
 
     // ---- finalise (dmrgg.f90:1028-1029); not gated by the ready flag.  Each process finalises the cores it owns.
     const int ncore_own = D.c_hi - D.c_lo + 1;
