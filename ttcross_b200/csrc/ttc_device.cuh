@@ -206,7 +206,7 @@ struct GlobalVals {
         for (int pos = 1; pos <= m; ++pos) {
             const int idx = s(pos) - 1;
             xv[pos - 1] = par[idx];
-            wv[pos - 1] = needw ? par[nw + idx] : 0.0;
+            if (needw) wv[pos - 1] = par[nw + idx];
         }
     }
 };
@@ -231,12 +231,21 @@ struct StagedVals {
     // all m positions at once: three branch-free runs of independent shared-memory loads
     __device__ __forceinline__ void gather(int m, double* xv, double* wv, bool needw) const {
         const double* xl = XL + (i - 1); const double* wl = WL + (i - 1);
-        for (int pos = 0; pos < nl; ++pos) { xv[pos] = xl[pos * rl]; wv[pos] = needw ? wl[pos * rl] : 0.0; }
-        xv[nl] = xj; wv[nl] = wj;
-        int o = nl + 1;
-        if (hask) { xv[o] = xk; wv[o] = wk; ++o; }
-        const double* xr = XR + (q - 1); const double* wr = WR + (q - 1);
-        for (int t = 0; o + t < m; ++t) { xv[o + t] = xr[t * rr]; wv[o + t] = needw ? wr[t * rr] : 0.0; }
+        if (needw) {
+            for (int pos = 0; pos < nl; ++pos) { xv[pos] = xl[pos * rl]; wv[pos] = wl[pos * rl]; }
+            xv[nl] = xj; wv[nl] = wj;
+            int o = nl + 1;
+            if (hask) { xv[o] = xk; wv[o] = wk; ++o; }
+            const double* xr = XR + (q - 1); const double* wr = WR + (q - 1);
+            for (int t = 0; o + t < m; ++t) { xv[o + t] = xr[t * rr]; wv[o + t] = wr[t * rr]; }
+        } else {        // node values only (stdnorm, MVN): wv is not touched and may be null
+            for (int pos = 0; pos < nl; ++pos) xv[pos] = xl[pos * rl];
+            xv[nl] = xj;
+            int o = nl + 1;
+            if (hask) { xv[o] = xk; ++o; }
+            const double* xr = XR + (q - 1);
+            for (int t = 0; o + t < m; ++t) xv[o + t] = xr[t * rr];
+        }
     }
 };
 
@@ -314,8 +323,8 @@ template <class V>
 __device__ __noinline__ double eval_stdnorm(const DevPlan& P, const V& v) {
     double sum = 0.0;
     if (P.d <= MAXD_LOCAL) {
-        double x[MAXD_LOCAL], wq[MAXD_LOCAL];
-        v.gather(P.d, x, wq, false);
+        double x[MAXD_LOCAL];
+        v.gather(P.d, x, nullptr, false);
         for (int i = 0; i < P.d; ++i) sum = sum + x[i] * x[i];
         return exp(-sum);
     }
@@ -330,8 +339,8 @@ __device__ __noinline__ double eval_mvn(const DevPlan& P, const V& v, const doub
     const double denom = P.aux[m + (i64)m * m];
     double e = 0.0;
     if (m <= MAXD_LOCAL) {
-        double diff[MAXD_LOCAL], wq[MAXD_LOCAL];
-        v.gather(m, diff, wq, false);
+        double diff[MAXD_LOCAL];
+        v.gather(m, diff, nullptr, false);
         for (int i = 0; i < m; ++i) diff[i] = diff[i] - mu[i];
         for (int i = 0; i < m; ++i) {
             const double di = diff[i];
