@@ -1487,7 +1487,11 @@ int ttc_qr_thin(int device, int m, int n, const double* a, double* q, double* r,
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
     if (!coop) { g_create_err = "ttc_qr_thin: device lacks cooperative launch"; return TTC_ERR_CUDA; }
-    int G = std::max(1, std::min(nsm, (m + 15) / 16));
+    // CTAs: every column costs two grid barriers and a reduction over the CTAs' partials, so fewer, fatter CTAs win until the
+    // row slab no longer fits in shared memory (rows per CTA target: TTC_QR_ROWS, default 128, measured)
+    const int rows_target = std::getenv("TTC_QR_ROWS") ? std::max(16, std::atoi(std::getenv("TTC_QR_ROWS"))) : 128;
+    int G = std::max(1, std::min(nsm, (m + rows_target - 1) / rows_target));
+    while (G < nsm && ((size_t)((m + G - 1) / G) * n + n) * sizeof(double) > 200 * 1024) ++G;
     int rpb = (m + G - 1) / G;
     G = (m + rpb - 1) / rpb;
     const size_t smem = ((size_t)rpb * n + n) * sizeof(double);
