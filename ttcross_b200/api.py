@@ -31,8 +31,8 @@ def load_library(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if build_if_missing and _build.needs_build() and os.path.exists(_build.NVCC):
+    path = os.environ.get("TTC_LIB_PATH", _build.LIB)      # (kernel-tuning experiments load alternative builds)
+    if build_if_missing and path == _build.LIB and _build.needs_build() and os.path.exists(_build.NVCC):
         _build.build()
     if not os.path.exists(path):
         raise TTCrossError(-1, f"{path} is missing: run `python -m ttcross_b200.build` (nvcc, sm_100a); there is no CPU fallback")

@@ -999,7 +999,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         if (h->piv == -1) {
             if (h->sbt_ok) {
                 const int nrb = cdiv(maxcol, SB_TM);
-                const int nsp = std::max(1, std::min({(2 * h->nsm) / std::max(1, nrb * NV), cdiv(maxrow, SB_TN), GMAX / nrb}));   // whole waves: <= 2 CTAs per SM
+                const int nsp = std::max(1, std::min({(SB_MINB * h->nsm) / std::max(1, nrb * NV), cdiv(maxrow, SB_TN), GMAX / nrb}));   // whole waves: SB_MINB CTAs per SM
                 KIND_SWITCH(h->kind, L(KC_SUPERBLOCK, [&] { k_superblock_t<K, 0, 0><<<dim3(nrb, nsp, NV), SB_TM, h->sm_sbt, s>>>(D, dir, pp, 0, 0, nullptr, nullptr); }));
             } else {
                 const int Gs = (int)std::min<i64>(GMAX, std::max<i64>(1, (maxsb + TB - 1) / TB));
@@ -1594,7 +1594,7 @@ int ttc_superblock_probe_ex(ttc_handle* h, int bond, int store, int reps, int va
     if (variant == 2 && store) { cudaFree(pout); if (a_out) cudaFree(a_out); h->err = "the DFMA variant has no stored form"; return TTC_ERR_ARG; }
     const int m1 = h->rk_h[bond - 1] * h->n[bond], nc = h->n[bond + 1] * h->rk_h[bond + 1];
     const int nrb = cdiv(m1, SB_TM);
-    const int nsp = std::max(1, std::min({(2 * h->nsm) / std::max(1, nrb), cdiv(nc, SB_TN), GMAX / nrb}));   // whole waves: <= 2 CTAs per SM
+    const int nsp = std::max(1, std::min({(SB_MINB * h->nsm) / std::max(1, nrb), cdiv(nc, SB_TN), GMAX / nrb}));   // whole waves: SB_MINB CTAs per SM
     auto launch = [&]() {
         if (variant == 1) {
             if (store) { KIND_SWITCH(h->kind, k_superblock<K, 1><<<Gs, TB, h->sm_sb, s>>>(D, 1, 1, bond, 0, a_out, pout)); }

@@ -25,9 +25,22 @@
 
 namespace ttc {
 
-constexpr int SB_TM = 256;       // rows per CTA = threads per CTA
-constexpr int SB_CN = 8;         // columns a thread carries in registers
-constexpr int SB_TN = 32;        // columns per tile
+#ifndef TTC_SB_TM
+#define TTC_SB_TM 256
+#endif
+#ifndef TTC_SB_CN
+#define TTC_SB_CN 8
+#endif
+#ifndef TTC_SB_TN
+#define TTC_SB_TN 32
+#endif
+#ifndef TTC_SB_MINB
+#define TTC_SB_MINB 2
+#endif
+constexpr int SB_TM = TTC_SB_TM;     // rows per CTA = threads per CTA
+constexpr int SB_CN = TTC_SB_CN;     // columns a thread carries in registers
+constexpr int SB_TN = TTC_SB_TN;     // columns per tile
+constexpr int SB_MINB = TTC_SB_MINB; // CTAs per SM the register allocation aims at
 constexpr int SB_MAXL = 8;       // left positions (+ the free mode) kept in registers on the fast Ising-C path
 
 __host__ __device__ __forceinline__ size_t sb_tile_doubles(int Rmax, int d) {
@@ -36,7 +49,7 @@ __host__ __device__ __forceinline__ size_t sb_tile_doubles(int Rmax, int d) {
 }
 
 template <int KIND, int STORE, int FMA>
-__global__ void __launch_bounds__(SB_TM) k_superblock_t(DevPlan P, int dir, int pp, int fixed_bond, int fixed_v, double* a_out, Partial* probe_out) {
+__global__ void __launch_bounds__(SB_TM, SB_MINB) k_superblock_t(DevPlan P, int dir, int pp, int fixed_bond, int fixed_v, double* a_out, Partial* probe_out) {
     tl_stamp(P, 35);
     extern __shared__ double smem[];
     __shared__ Partial shp[32];
