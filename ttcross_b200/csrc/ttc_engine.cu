@@ -605,12 +605,12 @@ int setup_device(ttc_handle* h, int maxrank) {
         // against 3.8 ms with 8 x 512); with many partitions the portable 8-CTA clusters win (config E, 63 partitions: 59 ms
         // against 100 ms with 16)
         if (D.nv * 16 <= h->nsm) { h->cluster_size = 16; h->cluster_threads = 256; }
-        else { h->cluster_size = 8; h->cluster_threads = (h->kind == TTC_MVN) ? 256 : 512; }
+        else { h->cluster_size = 8; h->cluster_threads = 256; }
         if (const char* e = std::getenv("TTC_CLUSTER_SIZE")) h->cluster_size = std::atoi(e);
         if (const char* e = std::getenv("TTC_CLUSTER_THREADS")) h->cluster_threads = std::atoi(e);
         h->sm_visit = ((size_t)D.auxsm + Rmax + (size_t)Rmax * Rmax + Rmax + D.stage_max) * sizeof(double) + (size_t)(4 * Rmax + 8) * sizeof(int);
         h->cluster_ok = D.stage && h->use_wave && h->sm_visit <= 200 * 1024 && h->cluster_size >= 1 && h->cluster_size <= MAXCS && h->cluster_threads >= 32 &&
-                        h->cluster_threads <= (h->kind == TTC_MVN ? 256 : VISIT_MAXTHREADS) && h->cluster_threads % 32 == 0 &&
+                        h->cluster_threads <= VISIT_MAXTHREADS && h->cluster_threads % 32 == 0 &&
                         !std::getenv("TTC_NO_CLUSTER");
         if (h->cluster_ok) {
             cudaError_t ce = cudaSuccess;
@@ -632,8 +632,8 @@ int setup_device(ttc_handle* h, int maxrank) {
                 return ncl >= 1;
             };
             if (h->cluster_ok && !fits(h->cluster_size, h->cluster_threads)) {
-                h->cluster_size = 8; h->cluster_threads = 512;
-                if (!fits(8, 512)) h->cluster_ok = false;
+                h->cluster_size = 8; h->cluster_threads = 256;
+                if (!fits(8, 256)) h->cluster_ok = false;
             }
         }
     }

@@ -191,11 +191,11 @@ __device__ __forceinline__ void tl_mark(const DevPlan& P, int id) {     // diagn
         if (k < P.tlog_cap) { P.tlog[3 * k] = (unsigned long long)id; P.tlog[3 * k + 1] = t; P.tlog[3 * k + 2] = (unsigned long long)clock64(); }
     }
 }
-constexpr int VISIT_MAXTHREADS = 512;
+constexpr int VISIT_MAXTHREADS = 256;
 // MVN evaluations are one long dependent DADD chain each (3 d^2 operations, one accumulator, mvn_pdf.f90:74-80): they need
 // many resident warps, not registers -> 256 threads x 4 CTAs per SM (64 registers); the other integrands keep 128 registers.
 template <int KIND>
-__global__ void __launch_bounds__(KIND == KIND_MVN ? 256 : VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 1) k_visits(DevPlan P, int dir, double small_element, double small_pivot, int fold_allreduce) {
+__global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_visits(DevPlan P, int dir, double small_element, double small_pivot, int fold_allreduce) {
     tl_stamp(P, 40);
     if (LDF(&P.ctrl->ready)) return;          // uniform over the grid: written only by k_sweep_log
     cg::cluster_group cl = cg::this_cluster();
