@@ -130,3 +130,27 @@ def test_superblock_kernel_mvn_matches_plain():
         a, b = t.superblock_probe(bond, variant=0), t.superblock_probe(bond, variant=1)
         for key in ("argmax_a", "argmax_b", "a", "b", "count"):
             assert a[key] == b[key], (bond, key, a, b)
+
+
+def test_uniform_callback_feeds_the_host_lottery():
+    """ttc_set_uniform_callback: the caller supplies the uniforms (what a Fortran driver would do with random_number).  Fed with
+    the library's own stream it must reproduce the device-lottery run bit for bit; fed with another stream it must differ."""
+    p = T.drivers.ising("c", 6, 32)
+    t0 = p.make(); t0.set_partition(2); t0.set_seed(9)
+    g0 = t0.dmrgg(10, p.accuracy, 2)
+    L = T.load_library()
+    pos = {}
+
+    def stream(vrank, count):
+        k0 = pos.get(vrank, 0)
+        pos[vrank] = k0 + count
+        return [L.ttc_stream_uniform(9, vrank, k0 + i) for i in range(count)]
+    t1 = p.make(); t1.set_partition(2); t1.set_uniform_source(stream)
+    g1 = t1.dmrgg(10, p.accuracy, 2)
+    assert np.array_equal(g0.pivlog, g1.pivlog) and np.array_equal(g0.pivots, g1.pivots) and np.array_equal(g0.vals, g1.vals)
+    assert g0.neval == g1.neval and sum(pos.values()) > 0
+    rng = np.random.default_rng(0)
+    t2 = p.make(); t2.set_partition(2); t2.set_uniform_source(lambda v, c: rng.random(c))
+    g2 = t2.dmrgg(10, p.accuracy, 2)
+    assert g2.neval != g0.neval or not np.array_equal(g0.pivlog, g2.pivlog)     # another stream: other candidates (the rook search may still meet the same pivots)
+    assert abs(g2.vals[-1] / g0.vals[-1] - 1) < 1e-6

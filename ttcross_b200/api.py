@@ -17,6 +17,8 @@ ISING, STDNORM, MVN = 1, 4, 5
 
 _lib = None
 _dp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+# void cb(void* ctx, int vrank, int count, double* out): `count` uniforms in [0,1) for virtual rank `vrank`
+UNIFORM_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, _dp)
 
 
 class TTCrossError(RuntimeError):
@@ -50,6 +52,7 @@ def load_library(build_if_missing: bool = True):
     L.ttc_set_tru.argtypes = [vp, C.c_int, C.c_double]
     L.ttc_set_seed.argtypes = [vp, C.c_ulonglong]
     L.ttc_set_verbose.argtypes = [vp, C.c_int]
+    L.ttc_set_uniform_callback.argtypes = [vp, UNIFORM_CB, C.c_void_p]
     L.ttc_set_lottery_mode.argtypes = [vp, C.c_int]
     L.ttc_set_profile.argtypes = [vp, C.c_int]
     L.ttc_dmrgg.argtypes = [vp, C.c_int, C.c_double, C.c_int]
@@ -204,6 +207,21 @@ class TTCross:
 
     def set_seed(self, seed: int):
         self._check(self._L.ttc_set_seed(self.h, seed))
+
+    def set_uniform_source(self, fn):
+        """fn(vrank, count) -> array of `count` uniforms in [0,1): replaces the built-in stream (the reference's unseeded
+        random_number, rnd.f90:120); implies the host lottery, one call per bond visit and virtual rank.  None removes it."""
+        if fn is None:
+            self._ucb = None
+            self._check(self._L.ttc_set_uniform_callback(self.h, UNIFORM_CB(0), None))
+            return
+
+        def _cb(ctx, vrank, count, out):
+            vals = np.asarray(fn(int(vrank), int(count)), dtype=np.float64)
+            for i in range(count):
+                out[i] = vals[i]
+        self._ucb = UNIFORM_CB(_cb)            # keep the trampoline alive
+        self._check(self._L.ttc_set_uniform_callback(self.h, self._ucb, None))
 
     def set_lottery_mode(self, mode: int):
         self._check(self._L.ttc_set_lottery_mode(self.h, mode))
