@@ -149,6 +149,10 @@ int ttc_profile(const ttc_handle* h, int cap, const char** names, long long* lau
  * Not called by the sweep; it is the kernel of TT orthogonalisation (dtt_ort, lib/tt.f90:130-198).
  * ms (may be NULL): device time of one factorisation, averaged over `reps` runs.  Failure message: ttc_last_error(NULL). */
 int ttc_qr_thin(int device, int m, int n, const double* a, double* q, double* r, int reps, double* ms);
+/* dtt_ort (lib/tt.f90:130-198): orthogonalise the train of the last ttc_dmrgg from the left, in place on the device (QR of
+ * every unfolding, R normalised and pushed into the next core, norms equalised over the cores).  Afterwards ttc_core /
+ * ttc_cores / ttc_quad see the orthogonalised train.  First row of SURVEY 8(f); single process only. */
+int ttc_ort(ttc_handle* h);
 
 /* ---- multi-GPU: one process per GPU, core blocks partitioned over ranks ------
  * Replaces MPI_COMM_WORLD of the reference (lib/dmrgg.f90:86-95, 763-959, 1209-1246, 1355-1405).  The communicator id

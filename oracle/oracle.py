@@ -75,6 +75,8 @@ def lib():
         L.tto_d2_lual.argtypes = [C.c_long, C.c_int, dp, dp, C.c_int]
         L.tto_d2_luar.argtypes = [C.c_long, C.c_int, dp, dp, C.c_int]
         L.tto_qr_thin.argtypes = [C.c_int, C.c_int, dp, dp, dp]
+        L.tto_tt_ort.argtypes = [C.c_int, ip, ip, dp]
+        L.tto_tt_ort.restype = C.c_int
         L.tto_erank.restype = C.c_double
         L.tto_erank.argtypes = [C.c_int, ip, ip]
         L.tto_fmt_e.restype = C.c_int
@@ -358,3 +360,19 @@ def qr_thin(a):
     r = np.zeros((n, n), order="F")
     lib().tto_qr_thin(m, n, _dp(a), _dp(q), _dp(r))
     return q, r
+
+
+def tt_ort(cores):
+    """dtt_ort (lib/tt.f90:130-198) on a list of cores (r0 x n x r1 arrays) -> new list of cores."""
+    d = len(cores)
+    n = np.array([c.shape[1] for c in cores], dtype=np.int32)
+    r = np.array([cores[0].shape[0]] + [c.shape[2] for c in cores], dtype=np.int32)
+    flat = np.concatenate([np.asarray(c, dtype=np.float64).reshape(-1, order="F") for c in cores])
+    st = lib().tto_tt_ort(d, _ip(n), _ip(r), _dp(flat))
+    if st != 0:
+        raise ValueError("tt_ort: an unfolding has fewer rows than columns")
+    out, off = [], 0
+    for c in cores:
+        out.append(flat[off:off + c.size].reshape(c.shape, order="F").copy())
+        off += c.size
+    return out

@@ -25,6 +25,7 @@
 //    lgwt             lib/quad.f90:97-131
 //    dtt_rank (erank) lib/tt.f90:1228-1245
 //    ort0_d           lib/ort.f90:17-81 (LAPACK dgeqrf + dorgqr restated as dgeqr2 + dorg2r; pinned against numpy's LAPACK)
+//    dtt_ort          lib/tt.f90:130-198 (first row of SURVEY 8(f))
 //    integrands       test_crs_ising.f90:176-218, test_crs_stdnorm.f90:154-170,
 //                     lib/mvn_pdf.f90:63-83 + test_crs_mvn.f90:156-172
 //    BLAS semantics   netlib reference order (idamax first-max, sequential ddot,
@@ -1137,6 +1138,42 @@ void tto_qr_thin(int m, int n, const double* a, double* q, double* r) {
         for (int i = 0; i < k; ++i) Y(i, k) = 0.0;
     }
     std::copy(y.begin(), y.end(), q);
+}
+// dtt_ort (lib/tt.f90:130-198): orthogonalise a train from the left.  cores: the d cores concatenated, core k is
+// r(k-1) x n(k) x r(k) column-major; overwritten.  Only the rank-preserving case r(k) <= r(k-1) n(k) (every cross result).
+// dgeqrf/dorgqr = tto_qr_thin above; dnrm2 as a plain root of the sum of squares; dgemm 'n','n' in reference order.
+int tto_tt_ort(int d, const int* n, const int* r, double* cores) {
+    std::vector<size_t> off(d + 1, 0);
+    for (int k = 0; k < d; ++k) off[k + 1] = off[k] + (size_t)r[k] * n[k] * r[k + 1];
+    double lognrm = 0.0;
+    for (int k = 0; k + 1 < d; ++k) {
+        const int mm = r[k] * n[k], nn = r[k + 1];
+        const long kk = (long)n[k + 1] * r[k + 2];
+        if (mm < nn) return 1;
+        std::vector<double> q((size_t)mm * nn), mat((size_t)nn * nn);
+        tto_qr_thin(mm, nn, cores + off[k], q.data(), mat.data());
+        double ss = 0.0;
+        for (double x : mat) ss += x * x;
+        const double nrm = std::sqrt(ss);
+        if (nrm != 0.0) { const double sc = 1.0 / nrm; for (double& x : mat) x = sc * x; lognrm = lognrm + std::log(nrm); }
+        std::copy(q.begin(), q.end(), cores + off[k]);
+        std::vector<double> u((size_t)nn * kk, 0.0);
+        const double* b = cores + off[k + 1];
+        for (long c = 0; c < kk; ++c)
+            for (int l = 0; l < nn; ++l) { const double t = b[l + (size_t)nn * c]; for (int i = 0; i < nn; ++i) u[i + (size_t)nn * c] += t * mat[i + (size_t)nn * l]; }
+        std::copy(u.begin(), u.end(), cores + off[k + 1]);
+    }
+    {
+        double* last = cores + off[d - 1];
+        const size_t cnt = off[d] - off[d - 1];
+        double ss = 0.0;
+        for (size_t x = 0; x < cnt; ++x) ss += last[x] * last[x];
+        const double nrm = std::sqrt(ss);
+        if (nrm != 0.0) { const double sc = 1.0 / nrm; for (size_t x = 0; x < cnt; ++x) last[x] = sc * last[x]; lognrm = lognrm + std::log(nrm); }
+    }
+    const double nrm = std::exp(lognrm / d);
+    for (size_t x = 0; x < off[d]; ++x) cores[x] = nrm * cores[x];
+    return 0;
 }
 int tto_fmt_e(double v, int w, int dgt, char* buf) { std::string s = fmt_e(v, w, dgt); std::memcpy(buf, s.c_str(), s.size() + 1); return (int)s.size(); }
 int tto_num_threads() {

@@ -85,6 +85,7 @@ def load_library(build_if_missing: bool = True):
     L.ttc_device_ms.argtypes = [vp]
     L.ttc_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_longlong), _dp]
     L.ttc_fp64_peak.argtypes = [C.c_int, C.c_int, _dp]
+    L.ttc_ort.argtypes = [vp]
     L.ttc_qr_thin.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _dp]
     L.ttc_set_timeline.argtypes = [vp, C.c_int]
     L.ttc_timeline.restype = C.c_long
@@ -295,6 +296,10 @@ class TTCross:
             out.append(buf[off:off + sz].reshape((int(self.ranks[k - 1]), int(self.n[k - 1]), int(self.ranks[k])), order="F"))
             off += sz
         return out
+
+    # ---- dtt_ort (lib/tt.f90:130-198)
+    def ort(self):
+        self._check(self._L.ttc_ort(self.h))
 
     # ---- dtt_quad
     def quad(self) -> float:

@@ -1470,6 +1470,94 @@ int ttc_fp64_peak(int device, int fma, double* tflops) {
     return TTC_OK;
 }
 
+// cooperative launch of k_qr_panel on device buffers (m >= n); scratch: part[G], partw[2*G*n], head[n+2]
+struct QrScratch { double* part = nullptr; double* pw = nullptr; double* head = nullptr; size_t cap_g = 0, cap_n = 0;
+    void release() { cudaFree(part); cudaFree(pw); cudaFree(head); part = pw = head = nullptr; cap_g = cap_n = 0; } };
+int qr_geometry(int nsm, int m, int n, int& G, int& rpb, size_t& smem) {
+    const int rows_target = std::getenv("TTC_QR_ROWS") ? std::max(16, std::atoi(std::getenv("TTC_QR_ROWS"))) : 128;
+    G = std::max(1, std::min(nsm, (m + rows_target - 1) / rows_target));
+    while (G < nsm && ((size_t)((m + G - 1) / G) * n + n) * sizeof(double) > 200 * 1024) ++G;
+    rpb = (m + G - 1) / G;
+    G = (m + rpb - 1) / rpb;
+    smem = ((size_t)rpb * n + n) * sizeof(double);
+    return smem <= 200 * 1024 ? 0 : TTC_ERR_ARG;
+}
+cudaError_t qr_launch(cudaStream_t s, int nsm, const double* da, int m, int n, double* dq, double* dr, QrScratch& sc) {
+    int G, rpb; size_t smem;
+    if (qr_geometry(nsm, m, n, G, rpb, smem)) return cudaErrorInvalidValue;
+    if ((size_t)G > sc.cap_g || (size_t)n > sc.cap_n) {
+        sc.release();
+        cudaError_t e = cudaMalloc((void**)&sc.part, (size_t)nsm * sizeof(double));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&sc.pw, (size_t)2 * nsm * std::max(n, 128) * sizeof(double));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&sc.head, (size_t)(std::max(n, 128) + 2) * sizeof(double));
+        if (e != cudaSuccess) return e;
+        sc.cap_g = nsm; sc.cap_n = std::max(n, 128);
+    }
+    cudaError_t e = cudaFuncSetAttribute(k_qr_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int lda = m;
+    void* args[] = {(void*)&da, (void*)&m, (void*)&n, (void*)&lda, (void*)&dq, (void*)&dr, (void*)&sc.part, (void*)&sc.pw, (void*)&sc.head, (void*)&rpb};
+    return cudaLaunchCooperativeKernel((void*)k_qr_panel, dim3(G), dim3(QR_THREADS), args, smem, s);
+}
+
+// dtt_ort (lib/tt.f90:130-198): orthogonalise the train of the last ttc_dmrgg from the left, in place on the device.
+// Afterwards ttc_core / ttc_cores / ttc_quad see the orthogonalised train (ranks are unchanged: a cross result has
+// r(k) <= r(k-1) n(k), the only case handled).  Single process only.
+int ttc_ort(ttc_handle* h) {
+    if (!h) return TTC_ERR_ARG;
+    if (!h->ran) { h->err = "ttc_ort before ttc_dmrgg"; return TTC_ERR_STATE; }
+    if (h->nproc > 1) { h->err = "ttc_ort: not collective yet (run it on a single-process handle)"; return TTC_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+    if (!coop) { h->err = "ttc_ort: device lacks cooperative launch"; return TTC_ERR_CUDA; }
+    const int d = h->d, R = h->Rmax;
+    cudaStream_t s = h->stream;
+    const DevPlan& D = h->plan;
+    size_t maxel = 0;
+    for (int k = 1; k <= d; ++k) {
+        maxel = std::max(maxel, (size_t)h->rk_h[k - 1] * h->n[k] * h->rk_h[k]);
+        if (k < d && (long long)h->rk_h[k - 1] * h->n[k] < h->rk_h[k]) { h->err = "ttc_ort: an unfolding with fewer rows than columns is not supported"; return TTC_ERR_ARG; }
+    }
+    double *ua = nullptr, *uq = nullptr, *ur = nullptr, *acc = nullptr;
+    QrScratch sc;
+    auto cleanup = [&]() { cudaFree(ua); cudaFree(uq); cudaFree(ur); cudaFree(acc); sc.release(); };
+    cudaError_t e = cudaMalloc((void**)&ua, maxel * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&uq, maxel * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ur, (size_t)R * R * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&acc, 4 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemsetAsync(acc, 0, 4 * sizeof(double), s);
+    std::vector<i64> coreOff(d + 2, 0);
+    { i64 a = 0; for (int p = 1; p <= d; ++p) { coreOff[p] = a; a += (i64)R * h->n[p] * R; } }
+    for (int k = 1; k < d && e == cudaSuccess; ++k) {
+        const int r0 = h->rk_h[k - 1], nk = h->n[k], r1 = h->rk_h[k];
+        const int mm = r0 * nk, nn = r1;
+        const i64 kk = (i64)h->n[k + 1] * h->rk_h[k + 1];
+        k_pack_core<<<std::min(1024, cdiv((i64)mm * nn, 256)), 256, 0, s>>>(D, k, ua);                 // unfolding mm x nn
+        e = qr_launch(s, h->nsm, ua, mm, nn, uq, ur, sc);
+        if (e != cudaSuccess) break;
+        k_ort_rnorm<<<1, 256, 0, s>>>(ur, nn, acc);
+        k_ort_store_q<<<std::min(1024, cdiv((i64)mm * nn, 256)), 256, 0, s>>>(uq, D.arg + coreOff[k], r0, nk, r1, R);
+        k_pack_core<<<std::min(1024, cdiv((i64)nn * kk, 256)), 256, 0, s>>>(D, k + 1, ua);             // nn x kk copy of core k+1
+        k_ort_apply_r<<<std::min(2048, cdiv((i64)nn * kk, 256)), 256, 0, s>>>(ur, ua, D.arg + coreOff[k + 1], nn, kk, R);
+        h->launches += 6;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) {
+        const i64 cols = (i64)h->n[d] * h->rk_h[d];
+        k_ort_lastnorm<<<1, 256, 0, s>>>(D.arg + coreOff[d], h->rk_h[d - 1], cols, R, acc);
+        for (int k = 1; k <= d; ++k) {
+            const i64 ck = (i64)h->n[k] * h->rk_h[k];
+            k_ort_scale<<<std::min(1024, cdiv((i64)h->rk_h[k - 1] * ck, 256)), 256, 0, s>>>(D.arg + coreOff[k], h->rk_h[k - 1], ck, R, acc, d, k == d ? 1 : 0);
+        }
+        h->launches += d + 1;
+        e = cudaStreamSynchronize(s);
+    }
+    cleanup();
+    if (e != cudaSuccess) { h->err = std::string("ttc_ort: CUDA error: ") + cudaGetErrorString(e); return TTC_ERR_CUDA; }
+    return TTC_OK;
+}
+
 // ort0_d (lib/ort.f90:17-81): thin QR of an m x n block, host buffers in and out (column-major, leading dimension m).
 // q: m x n, r: n x n.  m < n follows the reference's early-return branch (:32-46).  ms: kernel time per run (CUDA events).
 int ttc_qr_thin(int device, int m, int n, const double* a, double* q, double* r, int reps, double* ms) {
@@ -1487,32 +1575,20 @@ int ttc_qr_thin(int device, int m, int n, const double* a, double* q, double* r,
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
     if (!coop) { g_create_err = "ttc_qr_thin: device lacks cooperative launch"; return TTC_ERR_CUDA; }
-    // CTAs: every column costs two grid barriers and a reduction over the CTAs' partials, so fewer, fatter CTAs win until the
-    // row slab no longer fits in shared memory (rows per CTA target: TTC_QR_ROWS, default 128, measured)
-    const int rows_target = std::getenv("TTC_QR_ROWS") ? std::max(16, std::atoi(std::getenv("TTC_QR_ROWS"))) : 128;
-    int G = std::max(1, std::min(nsm, (m + rows_target - 1) / rows_target));
-    while (G < nsm && ((size_t)((m + G - 1) / G) * n + n) * sizeof(double) > 200 * 1024) ++G;
-    int rpb = (m + G - 1) / G;
-    G = (m + rpb - 1) / rpb;
-    const size_t smem = ((size_t)rpb * n + n) * sizeof(double);
-    if (smem > 200 * 1024) { g_create_err = "ttc_qr_thin: the block does not fit the shared memory of one cooperative launch"; return TTC_ERR_ARG; }
-    cudaError_t e = cudaFuncSetAttribute(k_qr_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    double *da = nullptr, *dq = nullptr, *dr = nullptr, *dpart = nullptr, *dpw = nullptr, *dhead = nullptr;
-    auto cleanup = [&]() { cudaFree(da); cudaFree(dq); cudaFree(dr); cudaFree(dpart); cudaFree(dpw); cudaFree(dhead); };
-    if (e == cudaSuccess) e = cudaMalloc((void**)&da, (size_t)m * n * sizeof(double));
+    int G, rpb; size_t smem;
+    if (qr_geometry(nsm, m, n, G, rpb, smem)) { g_create_err = "ttc_qr_thin: the block does not fit the shared memory of one cooperative launch"; return TTC_ERR_ARG; }
+    double *da = nullptr, *dq = nullptr, *dr = nullptr;
+    QrScratch sc;
+    auto cleanup = [&]() { cudaFree(da); cudaFree(dq); cudaFree(dr); sc.release(); };
+    cudaError_t e = cudaMalloc((void**)&da, (size_t)m * n * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc((void**)&dq, (size_t)m * n * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc((void**)&dr, (size_t)n * n * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&dpart, (size_t)G * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&dpw, (size_t)2 * G * n * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&dhead, (size_t)(n + 2) * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpy(da, a, (size_t)m * n * sizeof(double), cudaMemcpyHostToDevice);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEventCreate(&ev0); cudaEventCreate(&ev1);
-    int lda = m;
-    void* args[] = {(void*)&da, (void*)&m, (void*)&n, (void*)&lda, (void*)&dq, (void*)&dr, (void*)&dpart, (void*)&dpw, (void*)&dhead, (void*)&rpb};
     for (int rep = 0; rep <= reps && e == cudaSuccess; ++rep) {      // run 0 is the warm-up
         if (rep == 1) cudaEventRecord(ev0);
-        e = cudaLaunchCooperativeKernel((void*)k_qr_panel, dim3(G), dim3(QR_THREADS), args, smem, nullptr);
+        e = qr_launch(nullptr, nsm, da, m, n, dq, dr, sc);
     }
     cudaEventRecord(ev1);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();

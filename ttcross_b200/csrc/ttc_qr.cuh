@@ -150,4 +150,65 @@ __global__ void __launch_bounds__(QR_THREADS) k_qr_panel(const double* __restric
     for (int e = threadIdx.x; e < rows * n; e += blockDim.x) { const int j = e / rows, i = e - j * rows; q[(size_t)(row0 + i) + (size_t)m * j] = S[e]; }
 }
 
+// ----------------------------------------------------------------------------
+// Support kernels of dtt_ort (lib/tt.f90:130-198): left-to-right orthogonalisation of the train.  Per core k:
+//   QR of the (r(k-1) n(k)) x r(k) unfolding (k_qr_panel) -> R / ||R||_F, lognrm += log ||R||_F  (k_ort_rnorm)
+//   core k <- Q (k_ort_store_q);  core k+1 <- R * core k+1 (k_ort_apply_r, dgemm 'n','n' order, beta = 0)
+// and at the end the last core is normalised and every core is scaled by exp(lognrm / d) (k_ort_finish).
+// Cores live in the sweep's padded layout: element (i,j,s) at i + ld*(j + n*s).
+// ----------------------------------------------------------------------------
+// acc[0] = running lognrm, acc[1] = norm of this R (for the record)
+__global__ void k_ort_rnorm(double* r, int n, double* acc) {
+    __shared__ double sh[33];
+    double ss = 0.0;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) ss += r[e] * r[e];
+    const double nrm = sqrt(qr_block_sum(ss, sh));
+    if (nrm != 0.0) {
+        const double sc = 1.0 / nrm;                     // dscal(mn*nn, 1.d0/nrm, mat, 1)
+        for (int e = threadIdx.x; e < n * n; e += blockDim.x) r[e] = sc * r[e];
+        if (threadIdx.x == 0) acc[0] = acc[0] + log(nrm);
+    }
+    if (threadIdx.x == 0) acc[1] = nrm;
+}
+// core(i + ld*(j + n*s)) <- q(e + mm*s), e = i + r0*j
+__global__ void k_ort_store_q(const double* q, double* core, int r0, int n, int r1, int ld) {
+    const long long mm = (long long)r0 * n, tot = mm * r1;
+    for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < tot; x += (long long)gridDim.x * blockDim.x) {
+        const long long s = x / mm, e = x - s * mm;
+        const int j = (int)(e / r0), i = (int)(e - (long long)j * r0);
+        core[i + (long long)ld * (j + (long long)n * s)] = q[x];
+    }
+}
+// next(i + ld*c) <- sum_l r(i + nn*l) * u(l + nn*c), l ascending from 0 (reference dgemm, beta = 0); u = packed copy of next
+__global__ void k_ort_apply_r(const double* r, const double* u, double* next, int nn, long long kk, int ld) {
+    const long long tot = (long long)nn * kk;
+    for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < tot; x += (long long)gridDim.x * blockDim.x) {
+        const long long c = x / nn; const int i = (int)(x - c * nn);
+        double t = 0.0;
+        for (int l = 0; l < nn; ++l) t = t + u[l + (long long)nn * c] * r[i + (long long)nn * l];
+        next[i + (long long)ld * c] = t;
+    }
+}
+// norm of the (padded) last core into acc[2]; one CTA
+__global__ void k_ort_lastnorm(const double* core, int r0, long long cols, int ld, double* acc) {
+    __shared__ double sh[33];
+    double ss = 0.0;
+    const long long tot = (long long)r0 * cols;
+    for (long long x = threadIdx.x; x < tot; x += blockDim.x) { const long long c = x / r0; const int i = (int)(x - c * r0); const double v = core[i + (long long)ld * c]; ss += v * v; }
+    const double nrm = sqrt(qr_block_sum(ss, sh));
+    if (threadIdx.x == 0) { acc[2] = nrm; if (nrm != 0.0) acc[0] = acc[0] + log(nrm); }
+}
+// scale one core by `pre` (1/||last|| for the last core, 1 otherwise) and by exp(acc[0] / d)
+__global__ void k_ort_scale(double* core, int r0, long long cols, int ld, const double* acc, int d, int is_last) {
+    const double nrm = exp(acc[0] / (double)d);
+    const double pre = (is_last && acc[2] != 0.0) ? 1.0 / acc[2] : 1.0;
+    const long long tot = (long long)r0 * cols;
+    for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < tot; x += (long long)gridDim.x * blockDim.x) {
+        const long long c = x / r0; const int i = (int)(x - c * r0);
+        double v = core[i + (long long)ld * c];
+        if (is_last) v = pre * v;
+        core[i + (long long)ld * c] = nrm * v;
+    }
+}
+
 }  // namespace ttc
