@@ -1123,9 +1123,8 @@ __global__ void k_run_begin(DevPlan P, unsigned long long seed, int has_accuracy
 }
 // end of sweep `it`: the scalar reductions of dmrgg.f90:961-967, the record of the sweep (after the quadrature), the exit
 // test of dmrgg.f90:1010-1019, and the preparation of the next sweep (rr = r snapshot of :325, pivotmax = pivotmin = -1)
-__global__ void k_sweep_log(DevPlan P, int maxrank) {
-    tl_stamp(P, 8);
-    if (P.ctrl->ready) return;
+// (block-cooperative body: every thread of ONE CTA calls it; also run by the last quadrature kernel of a sweep)
+__device__ __forceinline__ void sweep_log_body(const DevPlan& P, int maxrank) {
     const int it = P.ctrl->it;
     __shared__ unsigned long long s_ne;
     __shared__ double s_amax, s_pmax, s_pmin;
@@ -1157,6 +1156,11 @@ __global__ void k_sweep_log(DevPlan P, int maxrank) {
     P.ctrl->it = it + 1;
     __threadfence();
     P.ctrl->ready = ready;
+}
+__global__ void k_sweep_log(DevPlan P, int maxrank) {
+    tl_stamp(P, 8);
+    if (P.ctrl->ready) return;
+    sweep_log_body(P, maxrank);
 }
 
 // ----------------------------------------------------------------------------
@@ -1625,7 +1629,7 @@ __device__ __forceinline__ void mat_load_sm(const double* g, int m, int n, int l
     for (int e = threadIdx.x; e < m * n; e += blockDim.x) { int j = e / m, i = e - j * m; S[i + ld * j] = g[i + (i64)ldg * j]; }
 }
 // chain product per virtual rank (dmrgg.f90:1323-1345): CTA v, three shared buffers of Rmax^2
-__global__ void k_quad_chain_sm(DevPlan P) {
+__global__ void k_quad_chain_sm(DevPlan P, int log_maxrank) {
     tl_stamp(P, 22);
     extern __shared__ double smem[];
     const int v = P.v0 + blockIdx.x;
@@ -1649,9 +1653,10 @@ __global__ void k_quad_chain_sm(DevPlan P) {
     const int nl = P.rk[last];
     for (int e = threadIdx.x; e < m * nl; e += blockDim.x) { int j = e / m, i = e - j * m; out[i + (i64)ld * j] = cur[i + ld * j]; }
     if (P.P == 1 && threadIdx.x == 0) P.sweep_out->val = cur[0];
+    if (P.P == 1 && log_maxrank > 0 && !P.ctrl->ready) { __syncthreads(); sweep_log_body(P, log_maxrank); }   // single partition: this is the sweep's last kernel
 }
 // binary tree over virtual ranks (dmrgg.f90:1355-1405): level `q`, CTA per receiving rank; launched once per level
-__global__ void k_quad_tree_sm(DevPlan P, int q, int last_level) {
+__global__ void k_quad_tree_sm(DevPlan P, int q, int last_level, int log_maxrank) {
     tl_stamp(P, 23);
     extern __shared__ double smem[];
     const int me = blockIdx.x * 2 * q, her = me + q;
@@ -1671,6 +1676,8 @@ __global__ void k_quad_tree_sm(DevPlan P, int q, int last_level) {
         for (int e = threadIdx.x; e < m * n; e += blockDim.x) { int j = e / m, i = e - j * m; out[i + (i64)ld * j] = C[i + ld * j]; }
         if (last_level && me == 0 && threadIdx.x == 0) P.sweep_out->val = C[0];
     }
+    // the root of the tree is the sweep's last kernel: it also writes the sweep record and takes the exit decision
+    if (last_level && me == 0 && log_maxrank > 0 && !P.ctrl->ready) { __syncthreads(); sweep_log_body(P, log_maxrank); }
 }
 
 // ----------------------------------------------------------------------------

@@ -749,7 +749,9 @@ int mp_phase2(ttc_handle* h, Launcher& L, int final) {
 // quadrature of the current cores -> sweep_out->val.  with_lua: the per-sweep path of dmrgg.f90:975-993.
 // Several processes: each contracts its own cores and chains its own virtual ranks; the chain products are
 // all-gathered (phase 2) and every process runs the reference's binary tree (dmrgg.f90:1355-1405) on all of them.
-int launch_quad(ttc_handle* h, Launcher& L, bool with_lua, bool use_weights, int final = 0) {
+// log_maxrank > 0: the last kernel also runs the end-of-sweep bookkeeping (k_sweep_log's body); returns 1 in *logged then.
+int launch_quad(ttc_handle* h, Launcher& L, bool with_lua, bool use_weights, int final = 0, int log_maxrank = 0, bool* logged = nullptr) {
+    if (logged) *logged = false;
     const DevPlan& D = h->plan;
     cudaStream_t s = h->stream;
     const int R = h->Rmax;
@@ -769,11 +771,12 @@ int launch_quad(ttc_handle* h, Launcher& L, bool with_lua, bool use_weights, int
         L(KC_QUAD, [&] { k_quad_contract_sm<<<dim3(R, ncore), 256, h->sm_contract, s>>>(D, use_weights ? 1 : 0, (int)(h->sm_contract / sizeof(double))); });
         if (with_lua) L(KC_QUAD, [&] { k_quad_lua_sm<<<ncore, 512, h->sm_lua, s>>>(D); });
     }
-    L(KC_QUAD, [&] { k_quad_chain_sm<<<D.nv, 512, h->sm_mat3, s>>>(D); });
+    L(KC_QUAD, [&] { k_quad_chain_sm<<<D.nv, 512, h->sm_mat3, s>>>(D, log_maxrank); });
+    if (logged && log_maxrank > 0) *logged = true;
     if (h->nproc > 1) { int e = mp_phase2(h, L, final); if (e) return e; }
     for (int q = 1; q < h->P; q *= 2) {
         const int last = (2 * q >= h->P) ? 1 : 0;
-        L(KC_QUAD, [&] { k_quad_tree_sm<<<cdiv(h->P, 2 * q), 512, h->sm_mat3, s>>>(D, q, last); });
+        L(KC_QUAD, [&] { k_quad_tree_sm<<<cdiv(h->P, 2 * q), 512, h->sm_mat3, s>>>(D, q, last, log_maxrank); });
     }
     return 0;
 }
@@ -1071,9 +1074,11 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
             if (h->use_wave) L(KC_EXCHANGE, [&] { k_exchange_extend_w<<<dim3(cdiv(h->nmax, 8), nbnd, 2), 256, h->sm_ext, s>>>(D); });
             else L(KC_EXCHANGE, [&] { k_exchange_extend<<<dim3(cdiv(2 * h->nmax, 64), nbnd), 64, 0, s>>>(D); });
         }
-        if (has_quad) { int e = launch_quad(h, L, true, true); if (e) return e; }
+        const int eff_maxrank = maxrank > 0 ? maxrank : Rmax;        // no maxrank: the rank capacity ends the run
+        bool logged = false;
+        if (has_quad) { int e = launch_quad(h, L, true, true, 0, h->force_split ? 0 : eff_maxrank, &logged); if (e) return e; }
         else if (multi) { int e = mp_phase2(h, L, 0); if (e) return e; }
-        L(KC_MISC, [&] { k_sweep_log<<<1, 128, 0, s>>>(D, maxrank > 0 ? maxrank : Rmax); });   // no maxrank: the rank capacity ends the run
+        if (!logged) L(KC_MISC, [&] { k_sweep_log<<<1, 128, 0, s>>>(D, eff_maxrank); });
         return 0;
     };
 
