@@ -154,6 +154,16 @@ int ttc_qr_thin(int device, int m, int n, const double* a, double* q, double* r,
  * ttc_cores / ttc_quad see the orthogonalised train.  First row of SURVEY 8(f); single process only. */
 int ttc_ort(ttc_handle* h);
 
+/* ---- TT files in the reference's stream format: dtt_write / dtt_read (lib/ttio.f90:10-17, 29-108, 196-296) ----------
+ * 128-byte header 'TT      ' | ver | inf | comment | i(8), then l, m, n(l:m), r(l-1:m) as int32 and the cores as float64,
+ * little-endian without record markers — files are interchangeable with the reference's.  Host-only helpers
+ * (n: d mode sizes, r: d+1 ranks, cores concatenated column-major) and ttc_write for the train a handle holds.
+ * Failure message: ttc_last_error(NULL) (ttc_write: ttc_last_error(h)). */
+int ttc_tt_write(const char* path, int l, int m, const int* n, const int* r, const double* cores);
+int ttc_tt_read_header(const char* path, int* l, int* m, int* n, int* r, int cap, long long* ncore);
+int ttc_tt_read_cores(const char* path, double* cores, long long cap);
+int ttc_write(ttc_handle* h, const char* path);
+
 /* ---- multi-GPU: one process per GPU, core blocks partitioned over ranks ------
  * Replaces MPI_COMM_WORLD of the reference (lib/dmrgg.f90:86-95, 763-959, 1209-1246, 1355-1405).  The communicator id
  * is an NCCL unique id (128 bytes) created on rank 0 by ttc_comm_unique_id and broadcast by the caller (MPI_Bcast in a

@@ -86,6 +86,10 @@ def load_library(build_if_missing: bool = True):
     L.ttc_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_longlong), _dp]
     L.ttc_fp64_peak.argtypes = [C.c_int, C.c_int, _dp]
     L.ttc_ort.argtypes = [vp]
+    L.ttc_write.argtypes = [vp, C.c_char_p]
+    L.ttc_tt_write.argtypes = [C.c_char_p, C.c_int, C.c_int, _ip, _ip, _dp]
+    L.ttc_tt_read_header.argtypes = [C.c_char_p, _ip, _ip, _ip, _ip, C.c_int, C.POINTER(C.c_longlong)]
+    L.ttc_tt_read_cores.argtypes = [C.c_char_p, _dp, C.c_longlong]
     L.ttc_qr_thin.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _dp]
     L.ttc_set_timeline.argtypes = [vp, C.c_int]
     L.ttc_timeline.restype = C.c_long
@@ -146,6 +150,42 @@ def qr_thin(a, device: int = 0, reps: int = 1):
     if st != 0:
         raise TTCrossError(st, L.ttc_last_error(None).decode())
     return q, r, ms.value
+
+
+def tt_write(path: str, cores, l: int = 1):
+    """dtt_write (lib/ttio.f90:29-108): a list of cores (r0 x n x r1 arrays) to a TT file in the reference's stream format."""
+    L = load_library()
+    d = len(cores)
+    n = np.array([c.shape[1] for c in cores], dtype=np.int32)
+    r = np.array([cores[0].shape[0]] + [c.shape[2] for c in cores], dtype=np.int32)
+    flat = np.concatenate([np.asarray(c, dtype=np.float64).reshape(-1, order="F") for c in cores])
+    st = L.ttc_tt_write(path.encode(), l, l + d - 1, _i(n), _i(r), _d(flat))
+    if st != 0:
+        raise TTCrossError(st, L.ttc_last_error(None).decode())
+
+
+def tt_read(path: str):
+    """dtt_read (lib/ttio.f90:196-296) -> (l, list of cores)."""
+    L = load_library()
+    l, m, tot = C.c_int(), C.c_int(), C.c_longlong()
+    st = L.ttc_tt_read_header(path.encode(), C.byref(l), C.byref(m), None, None, 0, C.byref(tot))
+    if st != 0:
+        raise TTCrossError(st, L.ttc_last_error(None).decode())
+    d = m.value - l.value + 1
+    n = np.zeros(d, dtype=np.int32)
+    r = np.zeros(d + 1, dtype=np.int32)
+    st = L.ttc_tt_read_header(path.encode(), C.byref(l), C.byref(m), _i(n), _i(r), d, C.byref(tot))
+    flat = np.zeros(tot.value)
+    if st == 0:
+        st = L.ttc_tt_read_cores(path.encode(), _d(flat), flat.size)
+    if st != 0:
+        raise TTCrossError(st, L.ttc_last_error(None).decode())
+    cores, off = [], 0
+    for k in range(d):
+        sz = int(r[k]) * int(n[k]) * int(r[k + 1])
+        cores.append(flat[off:off + sz].reshape((int(r[k]), int(n[k]), int(r[k + 1])), order="F"))
+        off += sz
+    return l.value, cores
 
 
 class TTCross:
@@ -296,6 +336,10 @@ class TTCross:
             out.append(buf[off:off + sz].reshape((int(self.ranks[k - 1]), int(self.n[k - 1]), int(self.ranks[k])), order="F"))
             off += sz
         return out
+
+    def write(self, path: str):
+        """dtt_write (lib/ttio.f90:29-108) of the train this handle holds."""
+        self._check(self._L.ttc_write(self.h, path.encode()))
 
     # ---- dtt_ort (lib/tt.f90:130-198)
     def ort(self):

@@ -1607,6 +1607,92 @@ int ttc_qr_thin(int device, int m, int n, const double* a, double* q, double* r,
     return TTC_OK;
 }
 
+// ---- TT files in the reference's stream format (lib/ttio.f90:10-17 header, :29-108 dtt_write, :196-296 dtt_read) ----
+// layout (little-endian, no record markers): 'TT      ' | ver(2) = 1,0 | inf(4) = tt_size,0,0,0 | comment(64) | i(8) with
+// i(1) = l, i(2) = m  [128 bytes]  | l, m | n(l:m) | r(l-1:m)  [int32]  | all cores concatenated [float64]
+namespace {
+struct TtHead { char txt[8]; int32_t ver[2]; int32_t inf[4]; char comment[64]; int32_t i[8]; };
+static_assert(sizeof(TtHead) == 128, "tthead of ttio.f90 is 128 bytes");
+}
+int ttc_tt_write(const char* path, int l, int m, const int* n, const int* r, const double* cores) {
+    if (!path || !n || !r || !cores || m < l || l < 1) { g_create_err = "ttc_tt_write: bad arguments"; return TTC_ERR_ARG; }
+    const int d = m - l + 1;
+    size_t tot = 0;
+    for (int k = 0; k < d; ++k) tot += (size_t)r[k] * n[k] * r[k + 1];
+    FILE* f = std::fopen(path, "wb");
+    if (!f) { g_create_err = std::string("dtt_write: error opening file: ") + path; return TTC_ERR_ARG; }
+    TtHead hd;
+    std::memcpy(hd.txt, "TT      ", 8);
+    hd.ver[0] = 1; hd.ver[1] = 0;
+    hd.inf[0] = 2048; hd.inf[1] = hd.inf[2] = hd.inf[3] = 0;      // tt_size (lib/tt.f90:16)
+    std::memset(hd.comment, ' ', sizeof hd.comment);
+    std::memset(hd.i, 0, sizeof hd.i);
+    hd.i[0] = l; hd.i[1] = m;
+    std::vector<int32_t> ints;
+    ints.push_back(l); ints.push_back(m);
+    for (int k = 0; k < d; ++k) ints.push_back(n[k]);
+    for (int k = 0; k <= d; ++k) ints.push_back(r[k]);
+    bool ok = std::fwrite(&hd, sizeof hd, 1, f) == 1 && std::fwrite(ints.data(), sizeof(int32_t), ints.size(), f) == ints.size() &&
+              std::fwrite(cores, sizeof(double), tot, f) == tot;
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) { g_create_err = "dtt_write: error writing file"; return TTC_ERR_ARG; }
+    return TTC_OK;
+}
+// header of a TT file: l, m, then n(l:m) and r(l-1:m) if the caller's arrays hold cap / cap + 1 entries; *ncore = doubles of the cores
+int ttc_tt_read_header(const char* path, int* l, int* m, int* n, int* r, int cap, long long* ncore) {
+    if (!path || !l || !m) { g_create_err = "ttc_tt_read_header: bad arguments"; return TTC_ERR_ARG; }
+    FILE* f = std::fopen(path, "rb");
+    if (!f) { g_create_err = std::string("dtt_read: file not exist: ") + path; return TTC_ERR_ARG; }
+    TtHead hd; int32_t lm[2];
+    bool ok = std::fread(&hd, sizeof hd, 1, f) == 1;
+    if (ok && !(hd.txt[0] == 'T' && hd.txt[1] == 'T')) { std::fclose(f); g_create_err = "dtt_read: not TT header in file"; return TTC_ERR_ARG; }
+    if (ok && hd.ver[0] != 1) { std::fclose(f); g_create_err = "dtt_read: not correct version of TT file"; return TTC_ERR_ARG; }
+    ok = ok && std::fread(lm, sizeof(int32_t), 2, f) == 2;
+    if (!ok || lm[1] < lm[0] || lm[0] < 1 || lm[1] - lm[0] + 1 > 2048) { std::fclose(f); g_create_err = "dtt_read: error reading header / lm"; return TTC_ERR_ARG; }
+    *l = lm[0]; *m = lm[1];
+    const int d = lm[1] - lm[0] + 1;
+    std::vector<int32_t> ints(2 * (size_t)d + 1);
+    ok = std::fread(ints.data(), sizeof(int32_t), ints.size(), f) == ints.size();
+    std::fclose(f);
+    if (!ok) { g_create_err = "dtt_read: error reading nr"; return TTC_ERR_ARG; }
+    long long tot = 0;
+    for (int k = 0; k < d; ++k) tot += (long long)ints[d + k] * ints[k] * ints[d + k + 1];
+    if (ncore) *ncore = tot;
+    if (n && r) {
+        if (cap < d) { g_create_err = "ttc_tt_read_header: arrays too small"; return TTC_ERR_ARG; }
+        for (int k = 0; k < d; ++k) n[k] = ints[k];
+        for (int k = 0; k <= d; ++k) r[k] = ints[d + k];
+    }
+    return TTC_OK;
+}
+int ttc_tt_read_cores(const char* path, double* cores, long long cap) {
+    int l, m; long long tot = 0;
+    int st = ttc_tt_read_header(path, &l, &m, nullptr, nullptr, 0, &tot);
+    if (st) return st;
+    if (!cores || cap < tot) { g_create_err = "ttc_tt_read_cores: output buffer too small"; return TTC_ERR_ARG; }
+    FILE* f = std::fopen(path, "rb");
+    if (!f) { g_create_err = "dtt_read: error opening file"; return TTC_ERR_ARG; }
+    const long off = (long)sizeof(TtHead) + 4L * (2 + 2 * (m - l + 1) + 1);
+    bool ok = std::fseek(f, off, SEEK_SET) == 0 && std::fread(cores, sizeof(double), (size_t)tot, f) == (size_t)tot;
+    std::fclose(f);
+    if (!ok) { g_create_err = "dtt_read: error reading cores"; return TTC_ERR_ARG; }
+    return TTC_OK;
+}
+// dtt_write(arg, fnam) for the train held by the handle (the cores this rank holds)
+int ttc_write(ttc_handle* h, const char* path) {
+    if (!h || !path) return TTC_ERR_ARG;
+    if (!h->ran) { h->err = "ttc_write before ttc_dmrgg"; return TTC_ERR_STATE; }
+    if (h->nproc > 1) { h->err = "ttc_write: gather the cores first (each rank holds its own block)"; return TTC_ERR_STATE; }
+    size_t tot = 0;
+    for (int k = 1; k <= h->d; ++k) tot += (size_t)h->rk_h[k - 1] * h->n[k] * h->rk_h[k];
+    std::vector<double> buf(tot);
+    int st = ttc_cores(h, buf.data(), (long long)tot);
+    if (st) return st;
+    st = ttc_tt_write(path, 1, h->d, h->n.data() + 1, h->rk_h.data(), buf.data());
+    if (st) h->err = g_create_err;
+    return st;
+}
+
 int ttc_l2_flush(ttc_handle* h, long long bytes) {
     if (!h || bytes <= 0) return TTC_ERR_ARG;
     int st = check_device(h);
