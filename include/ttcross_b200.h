@@ -154,6 +154,11 @@ int ttc_qr_thin(int device, int m, int n, const double* a, double* q, double* r,
  * ttc_cores / ttc_quad see the orthogonalised train.  First row of SURVEY 8(f); single process only. */
 int ttc_ort(ttc_handle* h);
 
+/* ztt_quad (lib/dmrgg.f90:1418-1523): quadrature of the train against `nsets` COMPLEX rank-1 weight tensors in one launch
+ * (test_crs_chf.f90:153-168 and test_crs_pdf.f90:128-190 loop over 32 frequencies).  wre / wim: [nsets][n(1)+...+n(d)],
+ * out_re / out_im: [nsets]; single-rank chain order of the reference.  SURVEY 8(f) rank 2; single process only. */
+int ttc_quad_complex(ttc_handle* h, int nsets, const double* wre, const double* wim, double* out_re, double* out_im);
+
 /* ---- TT files in the reference's stream format: dtt_write / dtt_read (lib/ttio.f90:10-17, 29-108, 196-296) ----------
  * 128-byte header 'TT      ' | ver | inf | comment | i(8), then l, m, n(l:m), r(l-1:m) as int32 and the cores as float64,
  * little-endian without record markers — files are interchangeable with the reference's.  Host-only helpers

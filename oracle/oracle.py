@@ -75,6 +75,7 @@ def lib():
         L.tto_d2_lual.argtypes = [C.c_long, C.c_int, dp, dp, C.c_int]
         L.tto_d2_luar.argtypes = [C.c_long, C.c_int, dp, dp, C.c_int]
         L.tto_qr_thin.argtypes = [C.c_int, C.c_int, dp, dp, dp]
+        L.tto_quad_complex.argtypes = [C.c_int, ip, ip, dp, dp, dp, dp]
         L.tto_tt_ort.argtypes = [C.c_int, ip, ip, dp]
         L.tto_tt_ort.restype = C.c_int
         L.tto_erank.restype = C.c_double
@@ -376,3 +377,16 @@ def tt_ort(cores):
         out.append(flat[off:off + c.size].reshape(c.shape, order="F").copy())
         off += c.size
     return out
+
+
+def quad_complex(cores, weights):
+    """ztt_quad (lib/dmrgg.f90:1418-1523) of real cores against complex rank-1 weights [sum n] -> complex."""
+    d = len(cores)
+    n = np.array([c.shape[1] for c in cores], dtype=np.int32)
+    r = np.array([cores[0].shape[0]] + [c.shape[2] for c in cores], dtype=np.int32)
+    flat = np.concatenate([np.asarray(c, dtype=np.float64).reshape(-1, order="F") for c in cores])
+    w = np.ascontiguousarray(weights, dtype=np.complex128)
+    wre, wim = np.ascontiguousarray(w.real), np.ascontiguousarray(w.imag)
+    out = np.zeros(2)
+    lib().tto_quad_complex(d, _ip(n), _ip(r), _dp(flat), _dp(wre), _dp(wim), _dp(out))
+    return complex(out[0], out[1])

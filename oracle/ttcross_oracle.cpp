@@ -1175,6 +1175,27 @@ int tto_tt_ort(int d, const int* n, const int* r, double* cores) {
     for (size_t x = 0; x < off[d]; ++x) cores[x] = nrm * cores[x];
     return 0;
 }
+// ztt_quad (lib/dmrgg.f90:1418-1523), one rank: cores real (the drivers give the complex train zero imaginary parts),
+// weights complex.  zgemv 'n' per slice (:1469-1471), zgemm 'n','n' chain (:1481-1483), reference BLAS orders.
+void tto_quad_complex(int d, const int* n, const int* r, const double* cores, const double* wre, const double* wim, double* out) {
+    std::vector<double> pre(1, 1.0), pim(1, 0.0);
+    size_t off = 0, woff = 0;
+    for (int p = 0; p < d; ++p) {
+        const int r0 = r[p], r1 = r[p + 1], np_ = n[p];
+        std::vector<double> nre(r1, 0.0), nim(r1, 0.0);
+        for (int k = 0; k < r1; ++k) {
+            std::vector<double> cre(r0, 0.0), cim(r0, 0.0);
+            for (int j = 0; j < np_; ++j)
+                for (int i = 0; i < r0; ++i) { const double v = cores[off + i + (size_t)r0 * (j + (size_t)np_ * k)]; cre[i] = cre[i] + wre[woff + j] * v; cim[i] = cim[i] + wim[woff + j] * v; }
+            double are = 0.0, aim = 0.0;
+            for (int l = 0; l < r0; ++l) { are = are + (cre[l] * pre[l] - cim[l] * pim[l]); aim = aim + (cre[l] * pim[l] + cim[l] * pre[l]); }
+            nre[k] = are; nim[k] = aim;
+        }
+        pre.swap(nre); pim.swap(nim);
+        off += (size_t)r0 * np_ * r1; woff += np_;
+    }
+    out[0] = pre[0]; out[1] = pim[0];
+}
 int tto_fmt_e(double v, int w, int dgt, char* buf) { std::string s = fmt_e(v, w, dgt); std::memcpy(buf, s.c_str(), s.size() + 1); return (int)s.size(); }
 int tto_num_threads() {
 #ifdef _OPENMP

@@ -86,6 +86,7 @@ def load_library(build_if_missing: bool = True):
     L.ttc_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_longlong), _dp]
     L.ttc_fp64_peak.argtypes = [C.c_int, C.c_int, _dp]
     L.ttc_ort.argtypes = [vp]
+    L.ttc_quad_complex.argtypes = [vp, C.c_int, _dp, _dp, _dp, _dp]
     L.ttc_write.argtypes = [vp, C.c_char_p]
     L.ttc_tt_write.argtypes = [C.c_char_p, C.c_int, C.c_int, _ip, _ip, _dp]
     L.ttc_tt_read_header.argtypes = [C.c_char_p, _ip, _ip, _ip, _ip, C.c_int, C.POINTER(C.c_longlong)]
@@ -336,6 +337,18 @@ class TTCross:
             out.append(buf[off:off + sz].reshape((int(self.ranks[k - 1]), int(self.n[k - 1]), int(self.ranks[k])), order="F"))
             off += sz
         return out
+
+    def quad_complex(self, weights) -> np.ndarray:
+        """ztt_quad (lib/dmrgg.f90:1418-1523) for several complex rank-1 weight tensors at once.
+        weights: complex array [nsets, n(1)+...+n(d)] -> complex array [nsets]."""
+        w = np.ascontiguousarray(weights, dtype=np.complex128)
+        if w.ndim == 1:
+            w = w[None, :]
+        assert w.shape[1] == int(self.n.sum())
+        wre, wim = np.ascontiguousarray(w.real), np.ascontiguousarray(w.imag)
+        ore, oim = np.zeros(w.shape[0]), np.zeros(w.shape[0])
+        self._check(self._L.ttc_quad_complex(self.h, w.shape[0], _d(wre), _d(wim), _d(ore), _d(oim)))
+        return ore + 1j * oim
 
     def write(self, path: str):
         """dtt_write (lib/ttio.f90:29-108) of the train this handle holds."""

@@ -15,6 +15,7 @@
 #include "ttc_visit.cuh"
 #include "ttc_superblock.cuh"
 #include "ttc_qr.cuh"
+#include "ttc_post.cuh"
 #include "ttc_nccl.hpp"
 
 #include <algorithm>
@@ -1604,6 +1605,36 @@ int ttc_qr_thin(int device, int m, int n, const double* a, double* q, double* r,
     cleanup();
     if (e != cudaSuccess) { g_create_err = std::string("ttc_qr_thin: CUDA error: ") + cudaGetErrorString(e); return TTC_ERR_CUDA; }
     if (ms) *ms = t / reps;
+    return TTC_OK;
+}
+
+// ztt_quad (lib/dmrgg.f90:1418-1523) for `nsets` complex rank-1 weight tensors at once (test_crs_chf.f90:153-168 loops over
+// 32 of them).  wre / wim: [nsets][n(1)+...+n(d)]; out_re / out_im: [nsets].  Host buffers; single process only.
+int ttc_quad_complex(ttc_handle* h, int nsets, const double* wre, const double* wim, double* out_re, double* out_im) {
+    if (!h || nsets < 1 || !wre || !wim || !out_re || !out_im) return TTC_ERR_ARG;
+    if (!h->ran) { h->err = "ttc_quad_complex before ttc_dmrgg"; return TTC_ERR_STATE; }
+    if (h->nproc > 1) { h->err = "ttc_quad_complex: not collective yet (run it on a single-process handle)"; return TTC_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    size_t wlen = 0;
+    for (int p = 1; p <= h->d; ++p) wlen += h->n[p];
+    double *dw = nullptr, *dout = nullptr;
+    const size_t wtot = (size_t)nsets * wlen;
+    cudaError_t e = cudaMalloc((void**)&dw, 2 * wtot * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dout, 2 * (size_t)nsets * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dw, wre, wtot * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dw + wtot, wim, wtot * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        const size_t smem = (4 * (size_t)h->Rmax + 2 * (size_t)h->nmax) * sizeof(double);
+        k_zquad<<<nsets, 256, smem, h->stream>>>(h->plan, nsets, dw, dw + wtot, dout, dout + nsets, (long long)wlen);
+        h->launches += 1;
+        e = cudaGetLastError();
+    }
+    std::vector<double> out(2 * (size_t)nsets);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out.data(), dout, out.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dw); cudaFree(dout);
+    if (e != cudaSuccess) { h->err = std::string("ttc_quad_complex: CUDA error: ") + cudaGetErrorString(e); return TTC_ERR_CUDA; }
+    for (int q = 0; q < nsets; ++q) { out_re[q] = out[q]; out_im[q] = out[nsets + q]; }
     return TTC_OK;
 }
 
