@@ -159,6 +159,13 @@ int ttc_ort(ttc_handle* h);
  * out_re / out_im: [nsets]; single-rank chain order of the reference.  SURVEY 8(f) rank 2; single process only. */
 int ttc_quad_complex(ttc_handle* h, int nsets, const double* wre, const double* wim, double* out_re, double* out_im);
 
+/* dtt_ijk (lib/tt.f90:630-652) for `count` multi-indices at once: ind [count][d] (1-based), values [count]. */
+int ttc_values(ttc_handle* h, long long count, const int* ind, double* values);
+/* dtt_accchk (lib/dmrgg.f90:1081-1166): the train against the integrand at nlot random entries (indices int(u*n)+1 from
+ * ttc_stream_uniform(seed, 0x7fffffff, sample*d + position)).  out[0..3] = einf, efro, ainf, afro; pivot[d] (may be
+ * NULL) = multi-index of the largest error.  SURVEY 8(f) rank 4 (the checker half); single process only. */
+int ttc_accchk(ttc_handle* h, long long nlot, unsigned long long seed, double* out, int* pivot);
+
 /* ---- TT files in the reference's stream format: dtt_write / dtt_read (lib/ttio.f90:10-17, 29-108, 196-296) ----------
  * 128-byte header 'TT      ' | ver | inf | comment | i(8), then l, m, n(l:m), r(l-1:m) as int32 and the cores as float64,
  * little-endian without record markers — files are interchangeable with the reference's.  Host-only helpers

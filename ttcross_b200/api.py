@@ -86,6 +86,8 @@ def load_library(build_if_missing: bool = True):
     L.ttc_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_longlong), _dp]
     L.ttc_fp64_peak.argtypes = [C.c_int, C.c_int, _dp]
     L.ttc_ort.argtypes = [vp]
+    L.ttc_values.argtypes = [vp, C.c_longlong, _ip, _dp]
+    L.ttc_accchk.argtypes = [vp, C.c_longlong, C.c_ulonglong, _dp, _ip]
     L.ttc_quad_complex.argtypes = [vp, C.c_int, _dp, _dp, _dp, _dp]
     L.ttc_write.argtypes = [vp, C.c_char_p]
     L.ttc_tt_write.argtypes = [C.c_char_p, C.c_int, C.c_int, _ip, _ip, _dp]
@@ -349,6 +351,23 @@ class TTCross:
         ore, oim = np.zeros(w.shape[0]), np.zeros(w.shape[0])
         self._check(self._L.ttc_quad_complex(self.h, w.shape[0], _d(wre), _d(wim), _d(ore), _d(oim)))
         return ore + 1j * oim
+
+    def values(self, ind) -> np.ndarray:
+        """dtt_ijk (lib/tt.f90:630-652) at many multi-indices: ind int array [count, d], 1-based."""
+        a = np.ascontiguousarray(ind, dtype=np.int32)
+        if a.ndim == 1:
+            a = a[None, :]
+        assert a.shape[1] == self.d
+        out = np.zeros(a.shape[0])
+        self._check(self._L.ttc_values(self.h, a.shape[0], _i(a), _d(out)))
+        return out
+
+    def accchk(self, nlot: int, seed: int = 1):
+        """dtt_accchk (lib/dmrgg.f90:1081-1166) -> dict(einf, efro, ainf, afro, pivot)."""
+        out = np.zeros(4)
+        piv = np.zeros(self.d, dtype=np.int32)
+        self._check(self._L.ttc_accchk(self.h, nlot, seed, _d(out), _i(piv)))
+        return {"einf": out[0], "efro": out[1], "ainf": out[2], "afro": out[3], "pivot": piv}
 
     def write(self, path: str):
         """dtt_write (lib/ttio.f90:29-108) of the train this handle holds."""

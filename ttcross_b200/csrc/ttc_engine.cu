@@ -1638,6 +1638,73 @@ int ttc_quad_complex(ttc_handle* h, int nsets, const double* wre, const double* 
     return TTC_OK;
 }
 
+// dtt_ijk (lib/tt.f90:630-652) for `count` multi-indices at once: ind [count][d], 1-based; values [count].  Host buffers.
+int ttc_values(ttc_handle* h, long long count, const int* ind, double* values) {
+    if (!h || count < 1 || !ind || !values) return TTC_ERR_ARG;
+    if (!h->ran) { h->err = "ttc_values before ttc_dmrgg"; return TTC_ERR_STATE; }
+    if (h->nproc > 1) { h->err = "ttc_values: not collective yet (run it on a single-process handle)"; return TTC_ERR_STATE; }
+    for (long long x = 0; x < count * h->d; ++x)
+        if (ind[x] < 1 || ind[x] > h->n[1 + x % h->d]) { h->err = "ttc_values: index out of range"; return TTC_ERR_ARG; }   // dtt_ijk returns -3
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int* di = nullptr; double* dv = nullptr;
+    cudaError_t e = cudaMalloc((void**)&di, (size_t)count * h->d * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dv, (size_t)count * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(di, ind, (size_t)count * h->d * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        const int nw = 8;
+        const size_t smem = (size_t)nw * 2 * h->Rmax * sizeof(double);
+        const int grid = (int)std::min<long long>((count + nw - 1) / nw, (long long)h->nsm * 8);
+        k_tt_values<<<grid, 32 * nw, smem, h->stream>>>(h->plan, count, di, dv);
+        h->launches += 1;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(values, dv, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(di); cudaFree(dv);
+    if (e != cudaSuccess) { h->err = std::string("ttc_values: CUDA error: ") + cudaGetErrorString(e); return TTC_ERR_CUDA; }
+    return TTC_OK;
+}
+// dtt_accchk (lib/dmrgg.f90:1081-1166): Monte-Carlo accuracy check of the train against the integrand at nlot random entries.
+// out[0..3] = einf, efro, ainf, afro; pivot (d ints, may be NULL) = the multi-index of the largest error.
+int ttc_accchk(ttc_handle* h, long long nlot, unsigned long long seed, double* out, int* pivot) {
+    if (!h || nlot < 1 || !out) return TTC_ERR_ARG;
+    if (!h->ran) { h->err = "ttc_accchk before ttc_dmrgg"; return TTC_ERR_STATE; }
+    if (h->nproc > 1) { h->err = "ttc_accchk: not collective yet (run it on a single-process handle)"; return TTC_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int nw = 8;
+    const int grid = (int)std::min<long long>((nlot + nw - 1) / nw, (long long)h->nsm * 4);
+    double* dpart = nullptr; long long* darg = nullptr;
+    cudaError_t e = cudaMalloc((void**)&dpart, (size_t)grid * 4 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&darg, (size_t)grid * sizeof(long long));
+    const size_t smem = aux_smem(h) + (size_t)nw * (2 * h->Rmax + h->d) * sizeof(double);
+    if (e == cudaSuccess) {
+        KIND_SWITCH(h->kind,
+            if (smem > 48 * 1024) cudaFuncSetAttribute(k_accchk<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_accchk<K><<<grid, 32 * nw, smem, h->stream>>>(h->plan, nlot, seed, dpart, darg));
+        h->launches += 1;
+        e = cudaGetLastError();
+    }
+    std::vector<double> part((size_t)grid * 4); std::vector<long long> argp(grid);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(part.data(), dpart, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(argp.data(), darg, argp.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dpart); cudaFree(darg);
+    if (e != cudaSuccess) { h->err = std::string("ttc_accchk: CUDA error: ") + cudaGetErrorString(e); return TTC_ERR_CUDA; }
+    double einf = -1.0, efro = 0.0, ainf = 0.0, afro = 0.0; long long ex = 0;
+    for (int g = 0; g < grid; ++g) {
+        if (einf < part[4 * g] || (einf == part[4 * g] && argp[g] < ex)) { einf = part[4 * g]; ex = argp[g]; }
+        efro += part[4 * g + 1]; ainf = std::max(ainf, part[4 * g + 2]); afro += part[4 * g + 3];
+    }
+    out[0] = std::max(einf, 0.0); out[1] = std::sqrt(efro); out[2] = ainf; out[3] = std::sqrt(afro);
+    if (pivot)
+        for (int p = 0; p < h->d; ++p) {
+            const double u = stream_uniform(seed, 0x7fffffff, (unsigned long long)ex * h->d + p);
+            int v = (int)(u * h->n[p + 1]) + 1; if (v > h->n[p + 1]) v = h->n[p + 1];
+            pivot[p] = v;
+        }
+    return TTC_OK;
+}
+
 // ---- TT files in the reference's stream format (lib/ttio.f90:10-17 header, :29-108 dtt_write, :196-296 dtt_read) ----
 // layout (little-endian, no record markers): 'TT      ' | ver(2) = 1,0 | inf(4) = tt_size,0,0,0 | comment(64) | i(8) with
 // i(1) = l, i(2) = m  [128 bytes]  | l, m | n(l:m) | r(l-1:m)  [int32]  | all cores concatenated [float64]

@@ -62,4 +62,89 @@ __global__ void k_zquad(DevPlan P, int nsets, const double* __restrict__ wre, co
     if (threadIdx.x == 0) { out_re[set] = pre[0]; out_im[set] = pim[0]; }
 }
 
+// ----------------------------------------------------------------------------
+// dtt_ijk (lib/tt.f90:630-652): one element of the train, x = core_d(:, i_d, 1); for p = d-1 .. 1: x = core_p(:, i_p, :) x.
+// One warp per multi-index, the running vector in shared memory (two buffers of Rmax doubles per warp); rows of the slice
+// across lanes (coalesced), the sum over the column index sequential from zero (the order of an inlined matmul).
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ double tt_value_warp(const DevPlan& P, const int* ind, double* xa, double* xb) {
+    const int lane = threadIdx.x & 31;
+    const int d = P.d, R = P.Rmax;
+    {
+        const int r0 = P.rk[d - 1], n = P.n[d];
+        const double* a = P.arg + P.coreOff[d] + (i64)R * (ind[d - 1] - 1);
+        for (int i = lane; i < r0; i += 32) xa[i] = a[i];
+        (void)n;
+    }
+    __syncwarp();
+    for (int p = d - 1; p >= 1; --p) {
+        const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
+        const double* a = P.arg + P.coreOff[p] + (i64)R * (ind[p - 1] - 1);      // y(i,k) = a[i + R*n*k]
+        for (int i = lane; i < r0; i += 32) {
+            double z = 0.0;
+#pragma unroll 4
+            for (int k = 0; k < r1; ++k) z = z + a[i + (i64)R * n * k] * xa[k];
+            xb[i] = z;
+        }
+        __syncwarp();
+        double* t = xa; xa = xb; xb = t;
+    }
+    return xa[0];
+}
+// values[x] = train(ind[x][0..d-1]) for `count` multi-indices (1-based); dynamic smem: 2*Rmax doubles per warp
+__global__ void k_tt_values(DevPlan P, long long count, const int* __restrict__ ind, double* __restrict__ values) {
+    extern __shared__ double smem[];
+    const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = threadIdx.x & 31;
+    double* xa = smem + (size_t)wid * 2 * P.Rmax; double* xb = xa + P.Rmax;
+    for (long long x = (long long)blockIdx.x * nw + wid; x < count; x += (long long)gridDim.x * nw) {
+        const double v = tt_value_warp(P, ind + x * P.d, xa, xb);
+        if (lane == 0) values[x] = v;
+        __syncwarp();
+    }
+}
+// dtt_accchk (lib/dmrgg.f90:1081-1166): nlot random multi-indices ind(p) = int(u*n(p)) + 1 (irnd, rnd.f90:84-90) from the
+// built-in uniform stream; a = integrand, b = train; per-CTA partials of  max|a-b| (+ sample number),  sum (a-b)^2,
+// max a,  sum a^2  in `part` [gridDim.x][4] + sample numbers [gridDim.x]; the host folds them in CTA order.
+template <int KIND>
+__global__ void k_accchk(DevPlan P, long long nlot, unsigned long long seed, double* part, long long* argpart) {
+    extern __shared__ double smem[];
+    __shared__ double s_e[32], s_f[32], s_a[32], s_g[32];
+    __shared__ long long s_x[32];
+    const double* A = stage_aux<KIND>(P, smem);
+    const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = threadIdx.x & 31;
+    double* xa = smem + P.auxsm + (size_t)wid * (2 * P.Rmax + P.d); double* xb = xa + P.Rmax;
+    int* ind = (int*)(xb + P.Rmax);
+    double einf = -1.0, efro = 0.0, ainf = 0.0, afro = 0.0; long long ex = 0;
+    for (long long x = (long long)blockIdx.x * nw + wid; x < nlot; x += (long long)gridDim.x * nw) {
+        for (int p = lane; p < P.d; p += 32) {
+            const double u = stream_uniform(seed, 0x7fffffff, (unsigned long long)x * P.d + p);
+            int v = (int)(u * P.n[p + 1]) + 1;
+            if (v > P.n[p + 1]) v = P.n[p + 1];
+            ind[p] = v;
+        }
+        __syncwarp();
+        const double b = tt_value_warp(P, ind, xa, xb);
+        if (lane == 0) {
+            struct Idx { const int* v; __device__ __forceinline__ int operator()(int pos) const { return v[pos - 1]; } } src{ind};
+            const double a = eval_src<KIND>(P, src, A);
+            const double e = fabs(a - b);
+            if (einf < e) { einf = e; ex = x; }
+            efro = efro + (a - b) * (a - b);
+            ainf = fmax(ainf, a);                          // dmax1(ainf, aval): not the absolute value, as in the reference
+            afro = afro + a * a;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) { s_e[wid] = einf; s_f[wid] = efro; s_a[wid] = ainf; s_g[wid] = afro; s_x[wid] = ex; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < nw; ++w) {
+            if (s_e[0] < s_e[w] || (s_e[0] == s_e[w] && s_x[w] < s_x[0])) { s_e[0] = s_e[w]; s_x[0] = s_x[w]; }
+            s_f[0] += s_f[w]; s_a[0] = fmax(s_a[0], s_a[w]); s_g[0] += s_g[w];
+        }
+        part[4 * blockIdx.x] = s_e[0]; part[4 * blockIdx.x + 1] = s_f[0]; part[4 * blockIdx.x + 2] = s_a[0]; part[4 * blockIdx.x + 3] = s_g[0];
+        argpart[blockIdx.x] = s_x[0];
+    }
+}
+
 }  // namespace ttc
