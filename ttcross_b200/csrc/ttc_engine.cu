@@ -1415,6 +1415,9 @@ int ttc_quad(ttc_handle* h, double* val) {
     if (!h->ran) { h->err = "ttc_quad before ttc_dmrgg"; return TTC_ERR_STATE; }
     CUDA_TRY(h, cudaSetDevice(h->device));
     Launcher L(h);
+    // peer windows: the last sweep's phase-2 slots of a slower rank must have been consumed before anybody overwrites them
+    // with the final chain products (inside the sweeps phase 1 plays that role); ttc_quad is rare, a barrier is cheap
+    if (h->nproc > 1 && h->p2p) { int st = comm_barrier(h); if (st) { h->err = "ttc_quad: barrier failed"; return st; } }
     { int st = launch_quad(h, L, false, !h->quad.empty(), 1); if (st) return st; }   // collective when there are several processes
     CUDA_TRY(h, cudaMemcpyAsync(h->sweep_h, h->plan.sweep_out, sizeof(SweepOut), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
