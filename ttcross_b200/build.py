@@ -16,7 +16,7 @@ FLAGS = [
     "-fmad=false",                 # reference arithmetic has no FMA contraction
     "-Xcompiler", "-fPIC", "-shared",
     "-ccbin", "/usr/bin/g++",
-    "-cudart", "shared", "-ldl",
+    "-cudart", "shared", "-ldl", "-Xcompiler", "-pthread",
 ]
 
 

@@ -28,6 +28,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace ttc;
@@ -1374,9 +1375,30 @@ int ttc_cores(ttc_handle* h, double* out, long long cap) {
         h->launches += 1;
         off += cnt;
     }
-    CUDA_TRY(h, cudaMemcpyAsync(h->stage_h, h->pack_d, tot * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    // device -> pinned staging in four slices; each slice is copied to the caller's (pageable) buffer by its own host
+    // thread as soon as its DMA has finished, so DMA and host copies overlap and the host copy runs at memory bandwidth
+    const size_t bytes = tot * sizeof(double);
+    const int nsl = bytes >= ((size_t)2 << 20) ? 4 : 1;
+    cudaEvent_t evs[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t b0[5];
+    for (int q = 0; q <= nsl; ++q) b0[q] = (bytes * q / nsl) & ~(size_t)63;
+    b0[nsl] = bytes;
+    for (int q = 0; q < nsl; ++q) {
+        CUDA_TRY(h, cudaMemcpyAsync((char*)h->stage_h + b0[q], (const char*)h->pack_d + b0[q], b0[q + 1] - b0[q], cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&evs[q], cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventRecord(evs[q], h->stream));
+    }
+    {
+        std::vector<std::thread> th;
+        char* dst = (char*)out; const char* src = (const char*)h->stage_h;
+        for (int q = 1; q < nsl; ++q)
+            th.emplace_back([=]() { cudaEventSynchronize(evs[q]); std::memcpy(dst + b0[q], src + b0[q], b0[q + 1] - b0[q]); });
+        cudaEventSynchronize(evs[0]);
+        std::memcpy(dst, src, b0[1] - b0[0]);
+        for (auto& t : th) t.join();
+    }
+    for (int q = 0; q < nsl; ++q) cudaEventDestroy(evs[q]);
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    std::memcpy(out, h->stage_h, tot * sizeof(double));
     return TTC_OK;
 }
 long long ttc_neval(const ttc_handle* h) { return h ? h->neval : 0; }
