@@ -28,7 +28,9 @@ typedef struct ttc_handle ttc_handle;
 enum {
     TTC_ISING = 1,   /* test_crs_ising.f90:176-218; C/D/E selected by par(2n+1) = 1/2/3 like the reference */
     TTC_STDNORM = 4, /* test_crs_stdnorm.f90:154-170 */
-    TTC_MVN = 5      /* lib/mvn_pdf.f90:63-83 via test_crs_mvn.f90:156-172; aux = mu(d) | inv_cov(d,d) | denom */
+    TTC_MVN = 5,     /* lib/mvn_pdf.f90:63-83 via test_crs_mvn.f90:156-172; aux = mu(d) | inv_cov(d,d) | denom */
+    TTC_COSCOEF = 6  /* lib/coefficients.f90:33-65 (COS-method coefficients of a Gaussian density, test_crs_coscoeff.f90:186);
+                        aux = mu(d) | sigma(d,d) column-major | lower | upper; par is ignored (may be NULL); d <= 24 */
 };
 
 enum ttc_status {

@@ -21,7 +21,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libttcross_oracle.so")
 
-ISING, STDNORM, MVN = 1, 4, 5
+ISING, STDNORM, MVN, COSCOEF = 1, 4, 5, 6
 EPS = 2.220446049250313e-16
 
 
@@ -390,3 +390,14 @@ def quad_complex(cores, weights):
     out = np.zeros(2)
     lib().tto_quad_complex(d, _ip(n), _ip(r), _dp(flat), _dp(wre), _dp(wim), _dp(out))
     return complex(out[0], out[1])
+
+
+def coscoef_setup(d: int, n: int) -> Setup:
+    """test_crs_coscoeff.f90:70-186 (no par, no quad in the dtt_dmrgg call)."""
+    x0 = math.log(100.0)
+    sig = np.full(d, 0.4)
+    mean = x0 + (0.0 - 0.5 * sig ** 2) * 1.0
+    cov = np.where(np.eye(d, dtype=bool), np.outer(sig, sig) * 1.0, (np.outer(sig, 0.5 * sig)) * 1.0)
+    aux = np.concatenate([mean, np.asfortranarray(cov).ravel(order="F"), [0.525170185988090843, 8.52517018598809173]])
+    return Setup(COSCOEF, d, np.full(d, n, dtype=np.int32), np.arange(n, dtype=np.float64), aux, np.ones(d * n), 500 * EPS, 0.0,
+                 f"coscoeff d={d} n={n}")

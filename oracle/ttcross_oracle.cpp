@@ -26,6 +26,7 @@
 //    dtt_rank (erank) lib/tt.f90:1228-1245
 //    ort0_d           lib/ort.f90:17-81 (LAPACK dgeqrf + dorgqr restated as dgeqr2 + dorg2r; pinned against numpy's LAPACK)
 //    dtt_ort          lib/tt.f90:130-198 (first row of SURVEY 8(f))
+//    COS coefficient  lib/coefficients.f90:33-65, lib/funcs.f90:8-26, lib/s_vectors.f90:7-29
 //    integrands       test_crs_ising.f90:176-218, test_crs_stdnorm.f90:154-170,
 //                     lib/mvn_pdf.f90:63-83 + test_crs_mvn.f90:156-172
 //    BLAS semantics   netlib reference order (idamax first-max, sequential ddot,
@@ -261,8 +262,45 @@ double f_mvn(int m, const int* ind, const int*, const double* par, const double*
         for (int j = 0; j < m; ++j) e = e + diff[i] * A[i + (i64)j * m] * diff[j];
     return std::exp(-0.5 * e) / denom;
 }
+// lib/coefficients.f90:33-65 (calc_coefficient) with lib/funcs.f90:8-26 (gaussian_chf_nd) and lib/s_vectors.f90:7-29.
+// aux = mu(d) | sigma(d,d) column-major | lower | upper.  x**n: libgcc __powidf2; matmul(sigma, t): column by column from 0;
+// cexp(z) = exp(re z) (cos(im z), sin(im z)); complex product (a+bi)(c+di) -> real part ac - bd.
+static double powi_gcc(double x, int m) {
+    unsigned int n = m < 0 ? (unsigned)(-m) : (unsigned)m;
+    double y = (n % 2) ? x : 1.0;
+    while (n >>= 1) { x = x * x; if (n % 2) y = y * x; }
+    return m < 0 ? 1.0 / y : y;
+}
+double f_coscoef(int m, const int* ind, const double* aux) {
+    const double* mu = aux; const double* sg = aux + m;
+    const double lower = aux[m + (i64)m * m], upper = aux[m + (i64)m * m + 1];
+    const double pi = 3.14159265358979323846;
+    const double oob = 1 / (upper - lower);
+    const double factor = 2.0 * powi_gcc(oob, m);
+    std::vector<double> t(m), y(m);
+    double real_sum = 0.0;
+    const unsigned ns = 1u << (m - 1);
+    for (unsigned i = 0; i < ns; ++i) {
+        for (int j = 0; j < m; ++j) {
+            const int sj = (j == 0) ? 1 : (((i >> (j - 1)) & 1u) ? -1 : 1);
+            t[j] = (((pi * (double)sj) * (double)(ind[j] - 1)) * oob);
+        }
+        double dot_mu = 0.0, st = 0.0;
+        for (int j = 0; j < m; ++j) { dot_mu = dot_mu + t[j] * mu[j]; st = st + t[j]; }
+        for (int a = 0; a < m; ++a) y[a] = 0.0;
+        for (int b = 0; b < m; ++b) for (int a = 0; a < m; ++a) y[a] = y[a] + sg[a + (i64)b * m] * t[b];
+        double quad = 0.0;
+        for (int a = 0; a < m; ++a) quad = quad + y[a] * t[a];
+        const double E = std::exp(-0.5 * quad);
+        const double c2 = std::cos(dot_mu), s2 = std::sin(dot_mu);
+        const double c1 = std::cos(-lower * st), s1 = std::sin(-lower * st);
+        real_sum = real_sum + (c1 * (E * c2) - s1 * (E * s2));
+    }
+    return factor * real_sum;
+}
 double fun(const Problem& P, const int* ind) {
     switch (P.kind) {
+        case 6: return f_coscoef(P.d, ind, P.aux.data());
         case ISING: return f_ising(P.d, ind, P.n.data(), P.par.data());
         case STDNORM: return f_stdnorm(P.d, ind, P.n.data(), P.par.data());
         case MVN: return f_mvn(P.d, ind, P.n.data(), P.par.data(), P.aux.data());

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import build as _build
 
-ISING, STDNORM, MVN = 1, 4, 5
+ISING, STDNORM, MVN, COSCOEF = 1, 4, 5, 6
 
 _lib = None
 _dp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_int)

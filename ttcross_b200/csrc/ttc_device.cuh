@@ -25,7 +25,7 @@ namespace ttc {
 
 typedef long long i64;
 
-enum { KIND_ISING = 1, KIND_STDNORM = 4, KIND_MVN = 5 };
+enum { KIND_ISING = 1, KIND_STDNORM = 4, KIND_MVN = 5, KIND_COSCOEF = 6 };
 constexpr int MAXD_LOCAL = 64;     // integrands gather node values into registers/local memory up to this d
 constexpr int GMAX = 1024;         // max CTAs per virtual rank in any reducing kernel
 
@@ -355,6 +355,50 @@ __device__ __noinline__ double eval_mvn(const DevPlan& P, const V& v, const doub
     return exp(-0.5 * e) / denom;
 }
 
+// COS-method coefficient of a Gaussian density (lib/coefficients.f90:33-65 with lib/funcs.f90:8-26, lib/s_vectors.f90:7-29):
+//   f = 2/(b-a)^d * sum over the 2^(d-1) sign vectors s (s_1 = 1) of Re[ exp(-i a sum(t)) * exp(i t.mu - t.Sigma.t / 2) ],
+//   t_j = pi s_j (ind_j - 1) / (b - a).   aux = mu(d) | Sigma(d,d) column-major | a | b;  the "node" of mode index k is k - 1.
+// x ** n with an integer n is libgcc's __powidf2 (square and multiply), matmul(Sigma, t) accumulates column by column.
+__host__ __device__ __forceinline__ double powi_gcc(double x, int m) {
+    unsigned int n = m < 0 ? (unsigned)(-m) : (unsigned)m;
+    double y = (n % 2) ? x : 1.0;
+    while (n >>= 1) { x = x * x; if (n % 2) y = y * x; }
+    return m < 0 ? 1.0 / y : y;
+}
+constexpr int COS_MAXD = 24;
+template <class V>
+__device__ __noinline__ double eval_coscoef(const DevPlan& P, const V& v) {
+    const int m = P.d;
+    if (m > COS_MAXD) return nan("");
+    const double* mu = P.aux; const double* sg = P.aux + m;
+    const double lower = P.aux[m + (i64)m * m], upper = P.aux[m + (i64)m * m + 1];
+    const double pi = 3.14159265358979323846;
+    double k[COS_MAXD], t[COS_MAXD], y[COS_MAXD];
+    v.gather(m, k, y, false);
+    const double oob = 1 / (upper - lower);
+    const double factor = 2.0 * powi_gcc(oob, m);
+    double real_sum = 0.0;
+    const unsigned ns = 1u << (m - 1);
+    for (unsigned i = 0; i < ns; ++i) {
+        for (int j = 0; j < m; ++j) {
+            const int sj = (j == 0) ? 1 : (((i >> (j - 1)) & 1u) ? -1 : 1);
+            t[j] = (((pi * (double)sj) * k[j]) * oob);
+        }
+        double dot_mu = 0.0, st = 0.0;
+        for (int j = 0; j < m; ++j) { dot_mu = dot_mu + t[j] * mu[j]; st = st + t[j]; }
+        for (int a = 0; a < m; ++a) y[a] = 0.0;
+        for (int b = 0; b < m; ++b) for (int a = 0; a < m; ++a) y[a] = y[a] + sg[a + (i64)b * m] * t[b];
+        double quad = 0.0;
+        for (int a = 0; a < m; ++a) quad = quad + y[a] * t[a];
+        const double E = exp(-0.5 * quad);
+        double s2, c2, s1, c1;
+        sincos(dot_mu, &s2, &c2);
+        sincos(-lower * st, &s1, &c1);
+        real_sum = real_sum + (c1 * (E * c2) - s1 * (E * s2));
+    }
+    return factor * real_sum;
+}
+
 // Stage the MVN matrix into shared memory when it fits; returns the pointer the integrand should read.
 template <int KIND>
 __device__ __forceinline__ const double* stage_aux(const DevPlan& P, double* smem) {
@@ -372,6 +416,7 @@ template <int KIND, class V>
 __device__ __forceinline__ double eval_point(const DevPlan& P, const V& v, const double* A) {
     if (KIND == KIND_ISING) return eval_ising(P, v);
     if (KIND == KIND_STDNORM) return eval_stdnorm(P, v);
+    if (KIND == KIND_COSCOEF) return eval_coscoef(P, v);
     return eval_mvn(P, v, A);
 }
 template <int KIND, class Src>

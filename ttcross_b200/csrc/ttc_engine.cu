@@ -358,6 +358,7 @@ inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
     switch (kind) {                                                              \
         case TTC_ISING:   { constexpr int K = KIND_ISING;   __VA_ARGS__; } break; \
         case TTC_STDNORM: { constexpr int K = KIND_STDNORM; __VA_ARGS__; } break; \
+        case TTC_COSCOEF: { constexpr int K = KIND_COSCOEF; __VA_ARGS__; } break; \
         default:          { constexpr int K = KIND_MVN;     __VA_ARGS__; } break; \
     }
 
@@ -1238,7 +1239,16 @@ int ttc_version(void) { return 100; }
 int ttc_create(ttc_handle** out, int kind, int d, const int* n, const double* par, long npar, const double* aux, long naux) {
     if (!out) { g_create_err = "ttc_create: out is NULL"; return TTC_ERR_ARG; }
     *out = nullptr;
-    if (kind != TTC_ISING && kind != TTC_STDNORM && kind != TTC_MVN) { g_create_err = "ttc_create: unknown integrand kind"; return TTC_ERR_ARG; }
+    if (kind != TTC_ISING && kind != TTC_STDNORM && kind != TTC_MVN && kind != TTC_COSCOEF) { g_create_err = "ttc_create: unknown integrand kind"; return TTC_ERR_ARG; }
+    std::vector<double> cospar;
+    if (kind == TTC_COSCOEF) {      // calc_coefficient reads ind(j) - 1, not par: the "node" of mode index k is k - 1
+        if (d < 2 || !n) { g_create_err = "ttc_create: need d >= 2 and n"; return TTC_ERR_ARG; }
+        if (d > COS_MAXD) { g_create_err = "ttc_create: the COS coefficient sums 2^(d-1) sign vectors; d is limited to 24"; return TTC_ERR_ARG; }
+        if (!aux || naux < (long)d + (long)d * d + 2) { g_create_err = "ttc_create: COS aux must hold mu(d) | sigma(d,d) | lower | upper"; return TTC_ERR_ARG; }
+        int nm = 1; for (int i = 0; i < d; ++i) nm = std::max(nm, n[i]);
+        cospar.resize(nm); for (int i = 0; i < nm; ++i) cospar[i] = (double)i;
+        par = cospar.data(); npar = nm;
+    }
     if (d < 2 || !n || !par || npar <= 0) { g_create_err = "ttc_create: need d >= 2, n and par"; return TTC_ERR_ARG; }
     for (int i = 0; i < d; ++i) if (n[i] < 1) { g_create_err = "ttc_create: mode sizes must be positive"; return TTC_ERR_ARG; }
     if (kind == TTC_ISING) {

@@ -153,3 +153,16 @@ def mvn(d: int, n: int) -> Problem:
     aux = np.concatenate([mu, np.asfortranarray(inv).ravel(order="F"), [denom]])
     return Problem(api.MVN, d, np.full(d, n, dtype=np.int32), np.concatenate([x, w]), aux, np.tile(w, d), 500 * EPS, 1.0,
                    f"test_crs_mvn {d} {n}")
+
+
+def coscoef(d: int, n: int) -> Problem:
+    """test_crs_coscoeff.f90:70-186: COS-method coefficient tensor of a d-variate Gaussian (X_0 = ln 100, sigma = 0.4,
+    corr = 0.5, rate = 0, T = 1) on [a, b]; dtt_dmrgg is called WITHOUT par and WITHOUT quad there."""
+    x0 = math.log(100.0)
+    sig = np.full(d, 0.4)
+    mean = x0 + (0.0 - 0.5 * sig ** 2) * 1.0
+    cov = np.where(np.eye(d, dtype=bool), np.outer(sig, sig) * 1.0, (np.outer(sig, 0.5 * sig)) * 1.0)
+    lower, upper = 0.525170185988090843, 8.52517018598809173
+    aux = np.concatenate([mean, np.asfortranarray(cov).ravel(order="F"), [lower, upper]])
+    return Problem(api.COSCOEF, d, np.full(d, n, dtype=np.int32), np.arange(n, dtype=np.float64), aux, np.ones(d * n), 500 * EPS, 0.0,
+                   f"test_crs_coscoeff {d} {n}")
