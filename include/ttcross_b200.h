@@ -155,6 +155,10 @@ int ttc_qr_thin(int device, int m, int n, const double* a, double* q, double* r,
  * every unfolding, R normalised and pushed into the next core, norms equalised over the cores).  Afterwards ttc_core /
  * ttc_cores / ttc_quad see the orthogonalised train.  First row of SURVEY 8(f); single process only. */
 int ttc_ort(ttc_handle* h);
+/* dtt_svd (lib/tt.f90:307-368): TT rounding on the device — ttc_ort, then right to left an SVD of every unfolding truncated by
+ * chop(tol, rmax) of lib/mat.f90:433-455 (tol < 0 / rmax <= 0: absent).  Ranks shrink; ttc_ranks / ttc_core / ttc_quad see
+ * the rounded train.  Single process only; ranks up to 64. */
+int ttc_svd(ttc_handle* h, double tol, int rmax);
 
 /* ztt_quad (lib/dmrgg.f90:1418-1523): quadrature of the train against `nsets` COMPLEX rank-1 weight tensors in one launch
  * (test_crs_chf.f90:153-168 and test_crs_pdf.f90:128-190 loop over 32 frequencies).  wre / wim: [nsets][n(1)+...+n(d)],

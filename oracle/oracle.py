@@ -76,6 +76,8 @@ def lib():
         L.tto_d2_luar.argtypes = [C.c_long, C.c_int, dp, dp, C.c_int]
         L.tto_qr_thin.argtypes = [C.c_int, C.c_int, dp, dp, dp]
         L.tto_quad_complex.argtypes = [C.c_int, ip, ip, dp, dp, dp, dp]
+        L.tto_tt_svd.argtypes = [C.c_int, ip, ip, dp, C.c_double, C.c_int]
+        L.tto_tt_svd.restype = C.c_int
         L.tto_tt_ort.argtypes = [C.c_int, ip, ip, dp]
         L.tto_tt_ort.restype = C.c_int
         L.tto_erank.restype = C.c_double
@@ -401,3 +403,20 @@ def coscoef_setup(d: int, n: int) -> Setup:
     aux = np.concatenate([mean, np.asfortranarray(cov).ravel(order="F"), [0.525170185988090843, 8.52517018598809173]])
     return Setup(COSCOEF, d, np.full(d, n, dtype=np.int32), np.arange(n, dtype=np.float64), aux, np.ones(d * n), 500 * EPS, 0.0,
                  f"coscoeff d={d} n={n}")
+
+
+def tt_svd(cores, tol=-1.0, rmax=0):
+    """dtt_svd (lib/tt.f90:307-368): TT rounding -> new list of cores with the truncated ranks."""
+    d = len(cores)
+    n = np.array([c.shape[1] for c in cores], dtype=np.int32)
+    r = np.array([cores[0].shape[0]] + [c.shape[2] for c in cores], dtype=np.int32)
+    flat = np.concatenate([np.asarray(c, dtype=np.float64).reshape(-1, order="F") for c in cores])
+    st = lib().tto_tt_svd(d, _ip(n), _ip(r), _dp(flat), float(tol), int(rmax))
+    if st != 0:
+        raise ValueError("tt_svd: unsupported shape")
+    out, off = [], 0
+    for k in range(d):
+        sz = int(r[k]) * int(n[k]) * int(r[k + 1])
+        out.append(flat[off:off + sz].reshape((int(r[k]), int(n[k]), int(r[k + 1])), order="F").copy())
+        off += sz
+    return out

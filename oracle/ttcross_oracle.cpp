@@ -25,7 +25,7 @@
 //    lgwt             lib/quad.f90:97-131
 //    dtt_rank (erank) lib/tt.f90:1228-1245
 //    ort0_d           lib/ort.f90:17-81 (LAPACK dgeqrf + dorgqr restated as dgeqr2 + dorg2r; pinned against numpy's LAPACK)
-//    dtt_ort          lib/tt.f90:130-198 (first row of SURVEY 8(f))
+//    dtt_ort, dtt_svd lib/tt.f90:130-198, 307-368 with chop of lib/mat.f90:433-455 (first row of SURVEY 8(f))
 //    COS coefficient  lib/coefficients.f90:33-65, lib/funcs.f90:8-26, lib/s_vectors.f90:7-29
 //    integrands       test_crs_ising.f90:176-218, test_crs_stdnorm.f90:154-170,
 //                     lib/mvn_pdf.f90:63-83 + test_crs_mvn.f90:156-172
@@ -1233,6 +1233,75 @@ void tto_quad_complex(int d, const int* n, const int* r, const double* cores, co
         off += (size_t)r0 * np_ * r1; woff += np_;
     }
     out[0] = pre[0]; out[1] = pim[0];
+}
+// dtt_svd (lib/tt.f90:307-368) with d_svd / chop (lib/mat.f90:340-385, 433-455).  LAPACK dgesvd is an unpinned third-party
+// dependency of the reference; its published contract (M = U diag(s) V^T, s descending) is restated with a one-sided Jacobi
+// SVD.  PINNED in tests/test_tt_svd.py against numpy.linalg.svd (LAPACK) through ranks and the rounded tensor.
+// r: ranks in/out (d+1); cores in/out (compacted to the new ranks); tol < 0 / rmax <= 0: absent.
+static void jacobi_svd_rows(int mm, long nn, std::vector<double>& M /*mm x nn col-major*/, std::vector<double>& U, std::vector<double>& sv, std::vector<double>& V) {
+    // work on A = M^T (nn x mm): A J = B (orthogonal columns) => M = J diag-normalised...: M^T = B J^T, so M = J B^T = (J) (S Vr) with U = J
+    std::vector<double> A((size_t)nn * mm), J((size_t)mm * mm, 0.0);
+    for (long c = 0; c < nn; ++c) for (int i = 0; i < mm; ++i) A[c + (size_t)nn * i] = M[i + (size_t)mm * c];
+    for (int i = 0; i < mm; ++i) J[i + (size_t)mm * i] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        bool rot = false;
+        for (int p = 0; p < mm - 1; ++p)
+            for (int q = p + 1; q < mm; ++q) {
+                double a = 0, b = 0, g = 0;
+                for (long c = 0; c < nn; ++c) { const double x = A[c + (size_t)nn * p], y = A[c + (size_t)nn * q]; a += x * x; b += y * y; g += x * y; }
+                if (g == 0.0 || std::fabs(g) <= 1e-15 * std::sqrt(a * b)) continue;
+                rot = true;
+                const double zeta = (b - a) / (2.0 * g), t = std::copysign(1.0, zeta) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+                const double cs = 1.0 / std::sqrt(1.0 + t * t), sn = cs * t;
+                for (long c = 0; c < nn; ++c) { const double x = A[c + (size_t)nn * p], y = A[c + (size_t)nn * q]; A[c + (size_t)nn * p] = cs * x - sn * y; A[c + (size_t)nn * q] = sn * x + cs * y; }
+                for (int i = 0; i < mm; ++i) { const double x = J[i + (size_t)mm * p], y = J[i + (size_t)mm * q]; J[i + (size_t)mm * p] = cs * x - sn * y; J[i + (size_t)mm * q] = sn * x + cs * y; }
+            }
+        if (!rot) break;
+    }
+    std::vector<double> nrm(mm); std::vector<int> ord(mm);
+    for (int j = 0; j < mm; ++j) { double a = 0; for (long c = 0; c < nn; ++c) a += A[c + (size_t)nn * j] * A[c + (size_t)nn * j]; nrm[j] = std::sqrt(a); ord[j] = j; }
+    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return nrm[x] > nrm[y]; });
+    U.assign((size_t)mm * mm, 0.0); V.assign((size_t)mm * nn, 0.0); sv.assign(mm, 0.0);
+    for (int jo = 0; jo < mm; ++jo) {
+        const int j = ord[jo]; sv[jo] = nrm[j];
+        for (int i = 0; i < mm; ++i) U[i + (size_t)mm * jo] = J[i + (size_t)mm * j];
+        for (long c = 0; c < nn; ++c) V[jo + (size_t)mm * c] = nrm[j] > 0 ? A[c + (size_t)nn * j] / nrm[j] : 0.0;     // V(jo, c): rows of V^T... stored mm x nn
+    }
+}
+int tto_tt_ort(int d, const int* n, const int* r, double* cores);
+int tto_tt_svd(int d, const int* n, int* r, double* cores, double tol, int rmax) {
+    if (tto_tt_ort(d, n, r, cores)) return 1;
+    std::vector<std::vector<double>> c(d);
+    { size_t off = 0; for (int k = 0; k < d; ++k) { const size_t sz = (size_t)r[k] * n[k] * r[k + 1]; c[k].assign(cores + off, cores + off + sz); off += sz; } }
+    double lognrm = 0.0;
+    for (int k = d - 1; k >= 1; --k) {
+        const int mm = r[k]; const long nn = (long)n[k] * r[k + 1], kk = (long)r[k - 1] * n[k - 1];
+        std::vector<double> U, sv, V;
+        jacobi_svd_rows(mm, nn, c[k], U, sv, V);
+        // chop (mat.f90:433-455)
+        int rr = mm; double er2 = 0.0;
+        if (rmax > 0 && rmax < rr) { for (int i = rmax; i < rr; ++i) er2 += sv[i] * sv[i]; rr = rmax; }
+        if (tol >= 0) {
+            double ss = 0; for (double x : sv) ss += x * x;
+            const double nrm = std::sqrt(ss), bound = tol * tol * nrm * nrm;
+            double er = er2 + sv[rr - 1] * sv[rr - 1];
+            while (er < bound && rr > 1) { er2 = er; rr = rr - 1; er = er + sv[rr - 1] * sv[rr - 1]; }
+        }
+        double ss = 0; for (int j = 0; j < rr; ++j) ss += sv[j] * sv[j];
+        const double nrm = std::sqrt(ss);
+        std::vector<double> sn(sv.begin(), sv.begin() + rr);
+        if (nrm != 0.0) { for (double& x : sn) x = (1.0 / nrm) * x; lognrm = lognrm + std::log(nrm); }
+        std::vector<double> left((size_t)kk * rr, 0.0), right((size_t)rr * nn);
+        for (int j = 0; j < rr; ++j)
+            for (int l = 0; l < mm; ++l) { const double t = U[l + (size_t)mm * j] * sn[j]; for (long x = 0; x < kk; ++x) left[x + (size_t)kk * j] += t * c[k - 1][x + (size_t)kk * l]; }
+        for (long cc = 0; cc < nn; ++cc) for (int i = 0; i < rr; ++i) right[i + (size_t)rr * cc] = V[i + (size_t)mm * cc];
+        c[k - 1].swap(left); c[k].swap(right); r[k] = rr;
+    }
+    { double ss = 0; for (double x : c[0]) ss += x * x; const double nrm = std::sqrt(ss); if (nrm != 0.0) { for (double& x : c[0]) x = (1.0 / nrm) * x; lognrm = lognrm + std::log(nrm); } }
+    const double sc = std::exp(lognrm / d);
+    size_t off = 0;
+    for (int k = 0; k < d; ++k) { for (double x : c[k]) cores[off++] = sc * x; }
+    return 0;
 }
 int tto_fmt_e(double v, int w, int dgt, char* buf) { std::string s = fmt_e(v, w, dgt); std::memcpy(buf, s.c_str(), s.size() + 1); return (int)s.size(); }
 int tto_num_threads() {

@@ -86,6 +86,7 @@ def load_library(build_if_missing: bool = True):
     L.ttc_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_longlong), _dp]
     L.ttc_fp64_peak.argtypes = [C.c_int, C.c_int, _dp]
     L.ttc_ort.argtypes = [vp]
+    L.ttc_svd.argtypes = [vp, C.c_double, C.c_int]
     L.ttc_values.argtypes = [vp, C.c_longlong, _ip, _dp]
     L.ttc_accchk.argtypes = [vp, C.c_longlong, C.c_ulonglong, _dp, _ip]
     L.ttc_quad_complex.argtypes = [vp, C.c_int, _dp, _dp, _dp, _dp]
@@ -376,6 +377,13 @@ class TTCross:
     # ---- dtt_ort (lib/tt.f90:130-198)
     def ort(self):
         self._check(self._L.ttc_ort(self.h))
+
+    def svd(self, tol: float = -1.0, rmax: int = 0):
+        """dtt_svd (lib/tt.f90:307-368): TT rounding; afterwards self.ranks / core() / quad() see the rounded train."""
+        self._check(self._L.ttc_svd(self.h, tol, rmax))
+        r = np.zeros(self.d + 1, dtype=np.int32)
+        self._check(self._L.ttc_ranks(self.h, _i(r)))
+        self.ranks = r
 
     # ---- dtt_quad
     def quad(self) -> float:

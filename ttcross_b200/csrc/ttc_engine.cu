@@ -1599,6 +1599,95 @@ int ttc_ort(ttc_handle* h) {
     return TTC_OK;
 }
 
+// chop (lib/mat.f90:433-455): number of singular values kept for relative accuracy tol and rank cap rmax
+static int chop_ref(const std::vector<double>& sv, bool has_tol, double tol, bool has_rmax, int rmax) {
+    int r = (int)sv.size(); double er2 = 0.0;
+    if (has_rmax && rmax < r) { for (int i = rmax; i < r; ++i) er2 += sv[i] * sv[i]; r = rmax; }
+    if (has_tol) {
+        double ss = 0.0; for (double x : sv) ss += x * x;
+        const double nrm = std::sqrt(ss), bound = tol * tol * nrm * nrm;
+        double er = er2 + sv[r - 1] * sv[r - 1];
+        while (er < bound && r > 1) { er2 = er; r = r - 1; er = er + sv[r - 1] * sv[r - 1]; }
+    }
+    return r;
+}
+// dtt_svd (lib/tt.f90:307-368): TT rounding of the train of the last ttc_dmrgg on the device: ttc_ort, then right to left an SVD
+// of every unfolding (QR of the transpose + one-sided Jacobi on the small factor), truncated by mat.f90's chop(tol, rmax);
+// U S goes into the core on the left, norms are equalised like in dtt_ort.  tol < 0 / rmax <= 0: absent.  Ranks shrink:
+// ttc_ranks / ttc_core / ttc_quad see the rounded train.  Single process only; needs r <= 64.
+int ttc_svd(ttc_handle* h, double tol, int rmax) {
+    if (!h) return TTC_ERR_ARG;
+    if (!h->ran) { h->err = "ttc_svd before ttc_dmrgg"; return TTC_ERR_STATE; }
+    if (h->nproc > 1) { h->err = "ttc_svd: not collective yet (run it on a single-process handle)"; return TTC_ERR_STATE; }
+    for (int k = 0; k <= h->d; ++k) if (h->rk_h[k] > 64) { h->err = "ttc_svd: ranks above 64 are not supported"; return TTC_ERR_ARG; }
+    int st = ttc_ort(h);
+    if (st) return st;
+    const int d = h->d, R = h->Rmax;
+    cudaStream_t s = h->stream;
+    const DevPlan& D = h->plan;
+    size_t maxel = 0;
+    for (int k = 1; k <= d; ++k) maxel = std::max(maxel, (size_t)h->rk_h[k - 1] * h->n[k] * h->rk_h[k]);
+    double *T = nullptr, *Q = nullptr, *Rm = nullptr, *U = nullptr, *W = nullptr, *sv = nullptr, *tmp = nullptr, *acc = nullptr;
+    QrScratch sc;
+    auto cleanup = [&]() { cudaFree(T); cudaFree(Q); cudaFree(Rm); cudaFree(U); cudaFree(W); cudaFree(sv); cudaFree(tmp); cudaFree(acc); sc.release(); };
+    cudaError_t e = cudaMalloc((void**)&T, maxel * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&Q, maxel * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&tmp, maxel * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&Rm, (size_t)R * R * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&U, (size_t)R * R * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&W, (size_t)R * R * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&sv, 2 * (size_t)R * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&acc, 4 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemsetAsync(acc, 0, 4 * sizeof(double), s);
+    std::vector<i64> coreOff(d + 2, 0);
+    { i64 a = 0; for (int p = 1; p <= d; ++p) { coreOff[p] = a; a += (i64)R * h->n[p] * R; } }
+    double lognrm = 0.0;
+    for (int k = d; k >= 2 && e == cudaSuccess; --k) {
+        const int mm = h->rk_h[k - 1];
+        const i64 nn = (i64)h->n[k] * h->rk_h[k], kk0 = (i64)h->rk_h[k - 2] * h->n[k - 1];
+        if (nn < mm) { cleanup(); h->err = "ttc_svd: an unfolding with more rows than columns is not supported"; return TTC_ERR_ARG; }
+        k_svd_pack_t<<<std::min(2048, cdiv((i64)mm * nn, 256)), 256, 0, s>>>(D.arg + coreOff[k], mm, nn, R, T);
+        e = qr_launch(s, h->nsm, T, (int)nn, mm, Q, Rm, sc);
+        if (e != cudaSuccess) break;
+        const size_t smem = (2 * (size_t)mm * mm + 2 * (size_t)mm) * sizeof(double) + (2 * (size_t)mm + 4) * sizeof(int);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_svd_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_svd_small<<<1, 32 * std::max(1, std::min(32, (mm + 1) / 2)), smem, s>>>(Rm, mm, U, sv, W);
+        std::vector<double> svh(mm);
+        e = cudaMemcpyAsync(svh.data(), sv, mm * sizeof(double), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) break;
+        const int rr = chop_ref(svh, tol >= 0, tol, rmax > 0, rmax);
+        double ss = 0.0; for (int j = 0; j < rr; ++j) ss += svh[j] * svh[j];
+        const double nrm = std::sqrt(ss);                              // dnrm2(rr, s, 1) over the kept values (tt.f90:333)
+        std::vector<double> sn(svh.begin(), svh.begin() + rr);
+        if (nrm != 0.0) { const double sc1 = 1.0 / nrm; for (double& x : sn) x = sc1 * x; lognrm = lognrm + std::log(nrm); }
+        e = cudaMemcpyAsync(sv + R, sn.data(), rr * sizeof(double), cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) break;
+        k_svd_apply_left<<<std::min(2048, cdiv(kk0 * rr, 256)), 256, 0, s>>>(D.arg + coreOff[k - 1], kk0, h->n[k - 1], R, U, sv + R, mm, rr, tmp);
+        k_svd_store_left<<<std::min(2048, cdiv(kk0 * rr, 256)), 256, 0, s>>>(tmp, D.arg + coreOff[k - 1], kk0, h->n[k - 1], R, rr);
+        k_svd_apply_right<<<std::min(2048, cdiv(nn * rr, 256)), 256, 0, s>>>(Q, nn, W, mm, rr, D.arg + coreOff[k], R);
+        h->rk_h[k - 1] = rr;
+        e = cudaMemcpyAsync(D.rk + (k - 1), &h->rk_h[k - 1], sizeof(int), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);            // (sn and rk_h are host temporaries of this iteration)
+        h->launches += 6;
+    }
+    if (e == cudaSuccess) {
+        // first core normalised, then every core scaled by exp(lognrm / d) (tt.f90:354-364)
+        e = cudaMemcpyAsync(acc, &lognrm, sizeof(double), cudaMemcpyHostToDevice, s);
+        const i64 c1 = (i64)h->n[1] * h->rk_h[1];
+        k_ort_lastnorm<<<1, 256, 0, s>>>(D.arg + coreOff[1], h->rk_h[0], c1, R, acc);
+        for (int k = 1; k <= d; ++k) {
+            const i64 ck = (i64)h->n[k] * h->rk_h[k];
+            k_ort_scale<<<std::min(1024, cdiv((i64)h->rk_h[k - 1] * ck, 256)), 256, 0, s>>>(D.arg + coreOff[k], h->rk_h[k - 1], ck, R, acc, d, k == 1 ? 1 : 0);
+        }
+        h->launches += d + 1;
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    }
+    cleanup();
+    if (e != cudaSuccess) { h->err = std::string("ttc_svd: CUDA error: ") + cudaGetErrorString(e); return TTC_ERR_CUDA; }
+    return TTC_OK;
+}
+
 // ort0_d (lib/ort.f90:17-81): thin QR of an m x n block, host buffers in and out (column-major, leading dimension m).
 // q: m x n, r: n x n.  m < n follows the reference's early-return branch (:32-46).  ms: kernel time per run (CUDA events).
 int ttc_qr_thin(int device, int m, int n, const double* a, double* q, double* r, int reps, double* ms) {

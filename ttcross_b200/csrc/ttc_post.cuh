@@ -147,4 +147,118 @@ __global__ void k_accchk(DevPlan P, long long nlot, unsigned long long seed, dou
     }
 }
 
+// ----------------------------------------------------------------------------
+// dtt_svd (lib/tt.f90:307-368): TT rounding.  After dtt_ort the unfolding M = core_k viewed as r(k-1) x (n(k) r(k)) is
+// short and fat; its SVD is taken as  M^T = Q R  (tall-skinny QR, k_qr_panel)  and  R^T = U S W^T  (one-sided Jacobi on the
+// small r x r matrix inside one CTA, below), so  M = U S (Q W)^T.  The truncation rule is mat.f90's `chop` (host, the r
+// singular values), U S goes into core k-1 and the kept rows of (Q W)^T become core k.
+// ----------------------------------------------------------------------------
+// T(jk + nn*i) = core(i + ld*jk): the transposed unfolding, contiguous
+__global__ void k_svd_pack_t(const double* core, int mm, long long nn, int ld, double* T) {
+    const long long tot = (long long)mm * nn;
+    for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < tot; x += (long long)gridDim.x * blockDim.x) {
+        const long long jk = x / mm; const int i = (int)(x - jk * mm);
+        T[jk + nn * i] = core[i + (long long)ld * jk];
+    }
+}
+// One-sided Jacobi SVD of A = R^T (m x m, R upper triangular from the QR, leading dimension m): A J = B with orthogonal
+// columns, B = U S, W = J.  One CTA; a warp per column pair, pairs of a round from the round-robin (tournament) schedule.
+// Output: U (m x m), s (m, descending), W (m x m), all column-major with leading dimension m.
+// dynamic smem: 2*m*m doubles (A, W) + 2*m doubles (norms, scratch) + 2*m ints (perm, order)
+__global__ void k_svd_small(const double* __restrict__ R, int m, double* U, double* sv, double* Wout) {
+    extern __shared__ double smem[];
+    double* A = smem; double* W = A + (size_t)m * m; double* nrm = W + (size_t)m * m; double* tmp = nrm + m;
+    int* perm = (int*)(tmp + m); int* ord = perm + m + 1;
+    __shared__ int s_rot;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) { const int j = e / m, i = e - j * m; A[e] = R[j + (size_t)m * i]; W[e] = (i == j) ? 1.0 : 0.0; }   // A = R^T
+    const int me = m + (m & 1);                       // even number of players (a dummy sits out)
+    for (int e = threadIdx.x; e < me; e += blockDim.x) perm[e] = e;
+    __syncthreads();
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        if (threadIdx.x == 0) s_rot = 0;
+        __syncthreads();
+        for (int round = 0; round < me - 1; ++round) {
+            for (int pr = wid; pr < me / 2; pr += nw) {
+                int p = perm[pr], q = perm[me - 1 - pr];
+                if (p >= m || q >= m) continue;
+                if (p > q) { const int t = p; p = q; q = t; }
+                double a = 0.0, b = 0.0, g = 0.0;
+                for (int i = lane; i < m; i += 32) { const double x = A[i + m * p], y = A[i + m * q]; a += x * x; b += y * y; g += x * y; }
+                for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); g += __shfl_xor_sync(0xffffffffu, g, o); }
+                if (fabs(g) > 1e-15 * sqrt(a * b) && g != 0.0) {
+                    const double zeta = (b - a) / (2.0 * g);
+                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+                    for (int i = lane; i < m; i += 32) {
+                        const double x = A[i + m * p], y = A[i + m * q];
+                        A[i + m * p] = c * x - sn * y; A[i + m * q] = sn * x + c * y;
+                        const double wx = W[i + m * p], wy = W[i + m * q];
+                        W[i + m * p] = c * wx - sn * wy; W[i + m * q] = sn * wx + c * wy;
+                    }
+                    if (lane == 0) s_rot = 1;
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) { const int last = perm[me - 1]; for (int e = me - 1; e > 1; --e) perm[e] = perm[e - 1]; perm[1] = last; }
+            __syncthreads();
+        }
+        if (!s_rot) break;
+        __syncthreads();
+    }
+    // singular values = column norms, descending order, U = normalised columns
+    for (int j = wid; j < m; j += nw) {
+        double a = 0.0;
+        for (int i = lane; i < m; i += 32) { const double x = A[i + m * j]; a += x * x; }
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) nrm[j] = sqrt(a);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {        // rank of column j in the descending order (ties by index)
+        int rnk = 0;
+        for (int u = 0; u < m; ++u) rnk += (nrm[u] > nrm[j]) || (nrm[u] == nrm[j] && u < j);
+        ord[rnk] = j;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+        const int jo = e / m, i = e - jo * m, j = ord[jo];
+        const double sj = nrm[j];
+        U[e] = (sj > 0.0) ? A[i + m * j] / sj : ((i == jo) ? 1.0 : 0.0);
+        Wout[e] = W[i + m * j];
+    }
+    for (int jo = threadIdx.x; jo < m; jo += blockDim.x) sv[jo] = nrm[ord[jo]];
+}
+// tmp(x + kk*j) = sum_l prevcore(x, l) * U(l, j) * s(j), x < kk, j < rr  (dgemm 'n','n' of tt.f90:342 with U scaled first, :338-340)
+__global__ void k_svd_apply_left(const double* prev, long long kk0, int nprev, int ldp, const double* U, const double* sn, int mm, int rr, double* tmp) {
+    // prev is the padded core k-1: element (i, j, l) at i + ldp*(j + nprev*l); x = i + r(k-2)*j enumerates its rows
+    const long long tot = kk0 * rr;
+    const int r2 = (int)(kk0 / nprev);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(e / kk0); const long long x = e - (long long)j * kk0;
+        const int jj = (int)(x / r2), i = (int)(x - (long long)jj * r2);
+        double t = 0.0;
+        for (int l = 0; l < mm; ++l) t = t + (U[l + (size_t)mm * j] * sn[j]) * prev[i + (long long)ldp * (jj + (long long)nprev * l)];
+        tmp[e] = t;
+    }
+}
+__global__ void k_svd_store_left(const double* tmp, double* prev, long long kk0, int nprev, int ldp, int rr) {
+    const long long tot = kk0 * rr;
+    const int r2 = (int)(kk0 / nprev);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(e / kk0); const long long x = e - (long long)j * kk0;
+        const int jj = (int)(x / r2), i = (int)(x - (long long)jj * r2);
+        prev[i + (long long)ldp * (jj + (long long)nprev * j)] = tmp[e];
+    }
+}
+// core_k(i + ld*jk) = V(i, jk) = sum_j W(j, i) * Q(jk, j), i < rr  (the kept rows of (Q W)^T)
+__global__ void k_svd_apply_right(const double* Q, long long nn, const double* W, int mm, int rr, double* core, int ld) {
+    const long long tot = nn * rr;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+        const long long jk = e / rr; const int i = (int)(e - jk * rr);
+        double t = 0.0;
+        for (int j = 0; j < mm; ++j) t = t + W[j + (size_t)mm * i] * Q[jk + nn * j];
+        core[i + (long long)ld * jk] = t;
+    }
+}
+
 }  // namespace ttc
