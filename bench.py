@@ -7,7 +7,8 @@ rook depth 2).  The bonds are cut into P = 8 partitions (the reference's MPI par
 the partition, not of the GPU count) which are mapped block-wise onto the N GPUs.
 
 metric : integrand evaluations per second = neval / device time of the step (max over ranks)
-e2e    : the same through the C-ABI with HOST buffers: create (par upload) + sweep + copy-out of all cores + integral
+e2e    : the same through the C-ABI with HOST buffers: par + quad upload + sweep + copy-out of all cores + integral every step
+         (handle created once; `cold_ms_per_step` adds ttc_create / ttc_destroy)
 --impl reference : the CPU oracle (restatement of the reference; the Fortran reference cannot be built here) on all host
                    threads, same workload, same partition.
 """
@@ -177,30 +178,37 @@ def main():
         ms_step = float(x.item())
     value = g.neval / (ms_step * 1e-3)
 
-    # ---- e2e arm: host buffers in, host buffers out, every step
-    e2e_t = []
+    # ---- e2e arm: host buffers in, host buffers out, every step.  The handle (device plan, captured graphs, pinned staging)
+    # is created once, like the reference's mpi_init + allocation of `tt`; every step ships par + quad from host memory
+    # (ttc_set_par / ttc_set_quad -> uploaded by the next ttc_dmrgg), runs the cross, copies every core back and reads the
+    # integral.  `cold_ms_per_step` is the same with ttc_create / ttc_destroy inside the timed region as well.
+    e2e_t, cold_t = [], []
+    host_out = np.empty(sum(int(g.ranks[k]) * int(prob.n[k]) * int(g.ranks[k + 1]) for k in range(prob.d)))   # caller-owned, like arg%u(k)%p
     h2d = prob.par.nbytes + prob.quad.nbytes + prob.n.nbytes
     d2h = 0
     for it in range(args.steps + 1):
         barrier()
         t0 = time.perf_counter()
-        if world == 1:
-            te = prob.make(device=local_rank)           # ttc_create + par/quad upload from host buffers
-            te.set_partition(PARTITIONS)
-        else:
-            te = t                                       # the communicator is set up once (like mpi_init); inputs travel every step
-            te.set_par(prob.par)
-            te.set_quad(prob.quad)
-        ge = te.dmrgg(R, prob.accuracy, piv)
-        cores = te.cores()                               # device -> host: every core this rank holds
-        val = te.quad()
+        t.set_par(prob.par)
+        t.set_quad(prob.quad)
+        ge = t.dmrgg(R, prob.accuracy, piv)
+        cores = t.cores(out=host_out)                    # device -> host: every core this rank holds
+        val = t.quad()
         barrier()
         dt = time.perf_counter() - t0
         d2h = sum(c.nbytes for c in cores) + 8 + ge.pivlog.nbytes
-        if world == 1:
-            te.close()
         if it > 0:
             e2e_t.append(dt)
+    if world == 1:
+        for it in range(3):
+            t0 = time.perf_counter()
+            te = prob.make(device=local_rank)            # ttc_create + first upload
+            te.set_partition(PARTITIONS)
+            te.dmrgg(R, prob.accuracy, piv)
+            te.cores(); te.quad()
+            te.close()
+            if it > 0:
+                cold_t.append(time.perf_counter() - t0)
     e2e_mean = float(np.mean(e2e_t))
     if dist is not None:
         import torch
@@ -273,7 +281,8 @@ def main():
                    "sweeps": int(g.nsweeps), "final_ranks": [int(x) for x in g.ranks], "l2": "flushed between timed steps (256 MiB write)",
                    "integral": float(g.vals[-1])},
         "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * e2e_mean},
+                "ms_per_step": 1e3 * e2e_mean, "cold_ms_per_step": (1e3 * float(np.mean(cold_t)) if cold_t else None),
+                "handle": "reused across steps (ttc_set_par + ttc_set_quad ship the inputs every step)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

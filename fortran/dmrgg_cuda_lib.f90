@@ -10,7 +10,7 @@
 !   val = dtt_quad(tt, qq)  ->  val = dtt_quad_cuda(tt)
 !
 ! A host `external fun` cannot run on the GPU, so the integrand is named by its family
-! (TTC_ISING / TTC_STDNORM / TTC_MVN) and `par` is the same opaque blob the reference
+! (TTC_ISING / TTC_STDNORM / TTC_MVN / TTC_COSCOEF) and `par` is the same opaque blob the reference
 ! hands to `fun` (test_crs_ising.f90:63-69).  Everything else keeps its meaning; the
 ! callee wipes `arg` to the result exactly like the reference (dmrgg.f90:96-100) and the
 ! caller frees it with dealloc(tt).
@@ -25,9 +25,10 @@ module dmrgg_cuda_lib
     implicit none
     private
     public :: dtt_dmrgg_cuda, dtt_quad_cuda, dmrgg_cuda_comm_init, dmrgg_cuda_finalize
-    public :: TTC_ISING, TTC_STDNORM, TTC_MVN
+    public :: ztt_quad_cuda, dtt_ort_cuda, dtt_svd_cuda, dtt_ijk_cuda, dtt_accchk_cuda, dtt_write_cuda
+    public :: TTC_ISING, TTC_STDNORM, TTC_MVN, TTC_COSCOEF
 
-    integer(c_int), parameter :: TTC_ISING = 1, TTC_STDNORM = 4, TTC_MVN = 5
+    integer(c_int), parameter :: TTC_ISING = 1, TTC_STDNORM = 4, TTC_MVN = 5, TTC_COSCOEF = 6
     type(c_ptr), save :: handle = c_null_ptr          ! one live problem, like the module state of the reference
     logical, save :: comm_wanted = .false.
     integer, save :: comm_size = 1, comm_rank = 0
@@ -62,6 +63,19 @@ module dmrgg_cuda_lib
         integer(c_int) function ttc_comm_init(h, nranks, rank, id) bind(C, name='ttc_comm_init')
             import; type(c_ptr), value :: h; integer(c_int), value :: nranks, rank; character(kind=c_char), intent(in) :: id(128)
         end function
+        integer(c_int) function ttc_quad_complex(h, nsets, wre, wim, ore, oim) bind(C, name='ttc_quad_complex')
+            import; type(c_ptr), value :: h; integer(c_int), value :: nsets
+            real(c_double), intent(in) :: wre(*), wim(*); real(c_double), intent(out) :: ore(*), oim(*)
+        end function
+        integer(c_int) function ttc_ort(h) bind(C, name='ttc_ort'); import; type(c_ptr), value :: h; end function
+        integer(c_int) function ttc_svd(h, tol, rmax) bind(C, name='ttc_svd'); import; type(c_ptr), value :: h; real(c_double), value :: tol; integer(c_int), value :: rmax; end function
+        integer(c_int) function ttc_values(h, count, ind, values) bind(C, name='ttc_values')
+            import; type(c_ptr), value :: h; integer(c_long_long), value :: count; integer(c_int), intent(in) :: ind(*); real(c_double), intent(out) :: values(*)
+        end function
+        integer(c_int) function ttc_accchk(h, nlot, seed, out4, pivot) bind(C, name='ttc_accchk')
+            import; type(c_ptr), value :: h; integer(c_long_long), value :: nlot, seed; real(c_double), intent(out) :: out4(4); type(c_ptr), value :: pivot
+        end function
+        integer(c_int) function ttc_write(h, path) bind(C, name='ttc_write'); import; type(c_ptr), value :: h; character(kind=c_char), intent(in) :: path(*); end function
     end interface
 
 contains
@@ -179,6 +193,84 @@ contains
         call check(ttc_quad(handle, v), 'dtt_quad')
         val = v
     end function
+
+    ! reads ranks and cores of the handle's train back into the caller's type(dtt) (after ort / svd changed them)
+    subroutine fetch_train(arg)
+        type(dtt), intent(inout) :: arg
+        integer :: l, m, d, k, first, last
+        integer(c_int), allocatable :: rr(:)
+        l = arg%l; m = arg%m; d = m - l + 1
+        allocate (rr(0:d))
+        call check(ttc_ranks(handle, rr), 'ttc_ranks')
+        arg%r(l - 1:m) = rr(0:d)
+        call alloc(arg)
+        call check(ttc_core_range(handle, first, last), 'ttc_core_range')
+        do k = first, last
+            call check(ttc_core(handle, int(k, c_int), arg%u(l + k - 1)%p), 'ttc_core')
+        end do
+    end subroutine
+
+    ! ztt_quad(tt_z, qq) (dmrgg.f90:1418-1523) for nsets rank-1 complex weight sets at once; w(:, s) holds the
+    ! n(1)+...+n(d) weights of set s.  test_crs_chf.f90:153-168 becomes one call with nsets = 32.
+    subroutine ztt_quad_cuda(nsets, w, ans)
+        integer, intent(in) :: nsets
+        double complex, intent(in) :: w(:, :)
+        double complex, intent(out) :: ans(nsets)
+        real(c_double), allocatable :: wre(:), wim(:), ore(:), oim(:)
+        if (.not. c_associated(handle)) then; write (*, *) 'ztt_quad_cuda: no cross has been computed'; stop; end if
+        allocate (wre(size(w)), wim(size(w)), ore(nsets), oim(nsets))
+        wre = reshape(dble(w), [size(w)]); wim = reshape(dimag(w), [size(w)])
+        call check(ttc_quad_complex(handle, int(nsets, c_int), wre, wim, ore, oim), 'ztt_quad')
+        ans = dcmplx(ore, oim)
+    end subroutine
+
+    ! call ort(tt) = dtt_ort (tt.f90:130-198) on the train of the last dtt_dmrgg_cuda; arg receives the orthogonalised cores
+    subroutine dtt_ort_cuda(arg)
+        type(dtt), intent(inout) :: arg
+        call check(ttc_ort(handle), 'dtt_ort')
+        call fetch_train(arg)
+    end subroutine
+
+    ! call svd(tt, tol, rmax) = dtt_svd (tt.f90:307-368); arg receives the rounded train (ranks shrink)
+    subroutine dtt_svd_cuda(arg, tol, rmax)
+        type(dtt), intent(inout) :: arg
+        double precision, intent(in) :: tol
+        integer, intent(in), optional :: rmax
+        integer :: mr
+        mr = 0; if (present(rmax)) mr = rmax
+        call check(ttc_svd(handle, tol, int(mr, c_int)), 'dtt_svd')
+        call dealloc(arg)
+        call fetch_train(arg)
+    end subroutine
+
+    ! dtt_ijk(tt, ind) (tt.f90:630-660) for count multi-indices at once; ind(d, count), 1-based like the reference
+    subroutine dtt_ijk_cuda(count, ind, values)
+        integer, intent(in) :: count
+        integer, intent(in) :: ind(:, :)
+        double precision, intent(out) :: values(count)
+        integer(c_int), allocatable :: flat(:)
+        allocate (flat(size(ind)))
+        flat = reshape(ind, [size(ind)])
+        call check(ttc_values(handle, int(count, c_long_long), flat, values), 'dtt_ijk')
+    end subroutine
+
+    ! dtt_accchk(nlot, tt, einf, efro, ainf, afro, fun, par, pivot) (dmrgg.f90:1081-1160) with a seeded index stream
+    subroutine dtt_accchk_cuda(nlot, einf, efro, ainf, afro, seed)
+        integer, intent(in) :: nlot
+        double precision, intent(out) :: einf, efro, ainf, afro
+        integer(kind=8), intent(in), optional :: seed
+        real(c_double) :: out4(4)
+        integer(c_long_long) :: sd
+        sd = 1; if (present(seed)) sd = seed
+        call check(ttc_accchk(handle, int(nlot, c_long_long), sd, out4, c_null_ptr), 'dtt_accchk')
+        einf = out4(1); efro = out4(2); ainf = out4(3); afro = out4(4)
+    end subroutine
+
+    ! call write(tt, fnam) = dtt_write (ttio.f90:29-108): same file, byte for byte
+    subroutine dtt_write_cuda(fnam)
+        character(len=*), intent(in) :: fnam
+        call check(ttc_write(handle, trim(fnam)//c_null_char), 'dtt_write')
+    end subroutine
 
     subroutine dmrgg_cuda_finalize()
         if (c_associated(handle)) call ttc_destroy(handle)

@@ -329,11 +329,16 @@ class TTCross:
         self._check(self._L.ttc_core(self.h, k, _d(a)))
         return a
 
-    def cores(self):
-        """The cores this rank holds (all of them on a single GPU), in core order."""
+    def cores(self, out=None):
+        """The cores this rank holds (all of them on a single GPU), in core order.  `out`: optional caller-owned flat float64
+        buffer (>= the total size) the cores are written into, the returned arrays are views of it."""
         lo, hi = self.core_range()
         sizes = [int(self.ranks[k - 1]) * int(self.n[k - 1]) * int(self.ranks[k]) for k in range(lo, hi + 1)]
-        buf = np.empty(sum(sizes))
+        if out is None:
+            buf = np.empty(sum(sizes))
+        else:
+            assert out.dtype == np.float64 and out.ndim == 1 and out.flags.c_contiguous and out.size >= sum(sizes)
+            buf = out[:sum(sizes)]
         self._check(self._L.ttc_cores(self.h, _d(buf), buf.size))
         out, off = [], 0
         for k, sz in zip(range(lo, hi + 1), sizes):

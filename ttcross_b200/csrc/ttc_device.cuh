@@ -62,6 +62,8 @@ struct Ctrl {                   // device-side control of the asynchronous sweep
     int has_accuracy;
     double accuracy;
     unsigned long long seed;    // uniform stream seed
+    int itq;                    // overlapped quadrature (second stream): sweeps whose quadrature value has been recorded
+    int pad_itq;
 };
 // exact restatement of lottery2's cumulative weights (rnd.f90:115-125) for 0/1 weights, see build_segments()
 struct LotSeg { long long M; long long k; int c0; int J; int E; int pad; };
@@ -80,6 +82,8 @@ struct DevPlan {
     int* Lidx; int* Ridx; const i64* offL; const i64* offR;
     int* vip;              // [(d+1)][Rmax][4]
     int* rk; int* rks;     // ranks now / at sweep start, index 0..d
+    const int* rkq;        // ranks the quadrature kernels read: rk, or the snapshot rks when the quadrature of sweep s runs beside
+                           // the bond visits of sweep s+1 (second stream; everything it reads below those ranks never changes)
     double* arg; double* col; double* rowT; const i64* coreOff;   // coreOff[p], p = 1..d
     double* inv;           // [(d+1)][Rmax*Rmax]
     double* acol1; double* bcol1; double* arow1; double* brow1;   // [P][Rmax*nmax]
@@ -1160,7 +1164,7 @@ __global__ void k_run_begin(DevPlan P, unsigned long long seed, int has_accuracy
     tl_stamp(P, 7);
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     P.ctrl->run_serial = run_serial;
-    P.ctrl->ready = 0; P.ctrl->strike = 0; P.ctrl->error = 0; P.ctrl->nsweeps = 0; P.ctrl->it = 1;
+    P.ctrl->ready = 0; P.ctrl->strike = 0; P.ctrl->error = 0; P.ctrl->nsweeps = 0; P.ctrl->it = 1; P.ctrl->itq = 0;
     P.ctrl->seed = seed; P.ctrl->has_accuracy = has_accuracy; P.ctrl->accuracy = accuracy;
     P.ctrl->t0_ns = globaltimer_ns();
     for (int v = 0; v <= P.P; ++v) P.tickets[v] = 0;
@@ -1169,7 +1173,7 @@ __global__ void k_run_begin(DevPlan P, unsigned long long seed, int has_accuracy
 // end of sweep `it`: the scalar reductions of dmrgg.f90:961-967, the record of the sweep (after the quadrature), the exit
 // test of dmrgg.f90:1010-1019, and the preparation of the next sweep (rr = r snapshot of :325, pivotmax = pivotmin = -1)
 // (block-cooperative body: every thread of ONE CTA calls it; also run by the last quadrature kernel of a sweep)
-__device__ __forceinline__ void sweep_log_body(const DevPlan& P, int maxrank) {
+__device__ __forceinline__ void sweep_log_body(const DevPlan& P, int maxrank, bool with_val = true) {
     const int it = P.ctrl->it;
     __shared__ unsigned long long s_ne;
     __shared__ double s_amax, s_pmax, s_pmin;
@@ -1185,11 +1189,11 @@ __device__ __forceinline__ void sweep_log_body(const DevPlan& P, int maxrank) {
     if (threadIdx.x != 0) return;
     const i64 ne = (i64)s_ne;
     SweepOut o;
-    o.val = P.sweep_out->val;
     o.neval = ne; o.amax = s_amax; o.pivotmax = s_pmax; o.pivotmin = s_pmin;
     o.t_ns = globaltimer_ns() - P.ctrl->t0_ns;
-    o.valid = 1; o.pad = 0;
-    P.slog[it] = o;
+    if (with_val) P.slog[it].val = P.sweep_out->val;     // (overlapped quadrature: quad_record() fills val later)
+    P.slog[it].neval = o.neval; P.slog[it].amax = o.amax; P.slog[it].pivotmax = o.pivotmax; P.slog[it].pivotmin = o.pivotmin;
+    P.slog[it].t_ns = o.t_ns; P.slog[it].valid = 1; P.slog[it].pad = 0;
     P.ctrl->nsweeps = it;
     int ready = 0;
     if (maxrank > 0) ready = (it + 1 >= maxrank);
@@ -1202,10 +1206,23 @@ __device__ __forceinline__ void sweep_log_body(const DevPlan& P, int maxrank) {
     __threadfence();
     P.ctrl->ready = ready;
 }
-__global__ void k_sweep_log(DevPlan P, int maxrank) {
+__global__ void k_sweep_log(DevPlan P, int maxrank, int with_val) {
     tl_stamp(P, 8);
     if (P.ctrl->ready) return;
-    sweep_log_body(P, maxrank);
+    sweep_log_body(P, maxrank, with_val != 0);
+}
+// Overlapped quadrature (log_maxrank < 0 in the quadrature kernels): the exit test of dmrgg.f90:1010-1019 does not use the
+// quadrature value, so k_sweep_log(with_val = 0) closes sweep s right after the exchange and the quadrature of sweep s
+// runs on a second stream beside the bond visits of sweep s+1, reading the rank snapshot rks (P.rkq).  ctrl->it - 1 sweeps
+// are closed, ctrl->itq of them have their value recorded; the next k_sweep_log waits for the quadrature (event), so both
+// counters are stable while a quadrature group runs.
+__device__ __forceinline__ bool quad_pending(const DevPlan& P) { return P.ctrl->itq < P.ctrl->it - 1; }
+__device__ __forceinline__ void quad_record(const DevPlan& P, double val) {    // one thread of the group's last kernel
+    if (!quad_pending(P)) return;
+    const int sw = P.ctrl->itq + 1;
+    P.slog[sw].val = val;
+    __threadfence();
+    P.ctrl->itq = sw;
 }
 
 // ----------------------------------------------------------------------------
@@ -1684,20 +1701,20 @@ __global__ void k_quad_chain_sm(DevPlan P, int log_maxrank) {
     const int ld = P.Rmax;
     const i64 msz = (i64)ld * ld;
     double* cur = smem; double* nxt = smem + msz; double* B = smem + 2 * msz;
-    const int m = P.rk[first - 1];
-    mat_load_sm(P.ttqq + (i64)first * msz, m, P.rk[first], ld, cur, ld);
+    const int m = P.rkq[first - 1];
+    mat_load_sm(P.ttqq + (i64)first * msz, m, P.rkq[first], ld, cur, ld);
     __syncthreads();
     for (int p = first + 1; p <= last; ++p) {
-        mat_load_sm(P.ttqq + (i64)p * msz, P.rk[p - 1], P.rk[p], ld, B, ld);
+        mat_load_sm(P.ttqq + (i64)p * msz, P.rkq[p - 1], P.rkq[p], ld, B, ld);
         __syncthreads();
-        mat_mul_sm(cur, m, P.rk[p - 1], B, P.rk[p], nxt, ld);
+        mat_mul_sm(cur, m, P.rkq[p - 1], B, P.rkq[p], nxt, ld);
         __syncthreads();
         double* t = cur; cur = nxt; nxt = t;
     }
     double* out = P.chain + (i64)v * msz;
-    const int nl = P.rk[last];
+    const int nl = P.rkq[last];
     for (int e = threadIdx.x; e < m * nl; e += blockDim.x) { int j = e / m, i = e - j * m; out[i + (i64)ld * j] = cur[i + ld * j]; }
-    if (P.P == 1 && threadIdx.x == 0) P.sweep_out->val = cur[0];
+    if (P.P == 1 && threadIdx.x == 0) { P.sweep_out->val = cur[0]; if (log_maxrank < 0) quad_record(P, cur[0]); }
     if (P.P == 1 && log_maxrank > 0 && !P.ctrl->ready) { __syncthreads(); sweep_log_body(P, log_maxrank); }   // single partition: this is the sweep's last kernel
 }
 // binary tree over virtual ranks (dmrgg.f90:1355-1405): level `q`, CTA per receiving rank; launched once per level
@@ -1710,8 +1727,8 @@ __global__ void k_quad_tree_sm(DevPlan P, int q, int last_level, int log_maxrank
     if (her < P.P) {
         double* A = smem; double* B = smem + msz; double* C = smem + 2 * msz;
         int herend = her + q; if (herend > P.P) herend = P.P;
-        const int m = P.rk[P.own[me] - 1], kd = P.rk[P.own[her] - 1];
-        const int n = (herend == P.P) ? P.rk[P.d] : P.rk[P.own[herend] - 1];
+        const int m = P.rkq[P.own[me] - 1], kd = P.rkq[P.own[her] - 1];
+        const int n = (herend == P.P) ? P.rkq[P.d] : P.rkq[P.own[herend] - 1];
         mat_load_sm(P.chain + (i64)me * msz, m, kd, ld, A, ld);
         mat_load_sm(P.chain + (i64)her * msz, kd, n, ld, B, ld);
         __syncthreads();
@@ -1719,7 +1736,7 @@ __global__ void k_quad_tree_sm(DevPlan P, int q, int last_level, int log_maxrank
         __syncthreads();
         double* out = P.chain + (i64)me * msz;
         for (int e = threadIdx.x; e < m * n; e += blockDim.x) { int j = e / m, i = e - j * m; out[i + (i64)ld * j] = C[i + ld * j]; }
-        if (last_level && me == 0 && threadIdx.x == 0) P.sweep_out->val = C[0];
+        if (last_level && me == 0 && threadIdx.x == 0) { P.sweep_out->val = C[0]; if (log_maxrank < 0) quad_record(P, C[0]); }
     }
     // the root of the tree is the sweep's last kernel: it also writes the sweep record and takes the exit decision
     if (last_level && me == 0 && log_maxrank > 0 && !P.ctrl->ready) { __syncthreads(); sweep_log_body(P, log_maxrank); }
@@ -1734,12 +1751,12 @@ __global__ void k_quad_tree_sm(DevPlan P, int q, int last_level, int log_maxrank
 //   Y = after d2_luar(inv(p-1)) on every column, Z = after d2_lual(inv(p)) on every row (Z = Y for the last core).
 // One CTA per own core; qext[p] = extents already done.  Needs r <= 32*MAXRPL.
 // ----------------------------------------------------------------------------
-__global__ void k_quad_inc(DevPlan P, int use_weights, int stage_doubles) {
+__global__ void k_quad_inc(DevPlan P, int use_weights, int stage_doubles, int ovl) {
     tl_stamp(P, 34);
-    if (P.ctrl->ready) return;
+    if (ovl ? !quad_pending(P) : (P.ctrl->ready != 0)) return;
     extern __shared__ double smem[];
     const int p = P.c_lo + blockIdx.x;
-    const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
+    const int r0 = P.rkq[p - 1], r1 = P.rkq[p], n = P.n[p];
     const int e0 = P.qext[2 * p], e1 = P.qext[2 * p + 1];
     if (e0 == r0 && e1 == r1) return;
     if (r0 - e0 > 1 || r1 - e1 > 1 || r0 < e0 || r1 < e1) { if (threadIdx.x == 0) P.ctrl->error = 2; return; }

@@ -120,6 +120,8 @@ struct ttc_handle {
     std::vector<std::pair<void*, size_t>> host_blocks;
     double* stage_h = nullptr; size_t stage_cap = 0;   // pinned staging for result copy-out
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_q = nullptr;                   // overlapped per-sweep quadrature (lower priority than `stream`)
+    std::vector<cudaEvent_t> ev_fork, ev_join;         // main -> quadrature stream / back, one pair per sweep of a graph
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int* lot_h = nullptr; VisitOut* out_h = nullptr; SweepOut* sweep_h = nullptr;   // pinned
     double* pack_d = nullptr; size_t pack_cap = 0;
@@ -325,6 +327,10 @@ void free_device(ttc_handle* h) {
     h->pack_d = nullptr; h->pack_cap = 0;
     if (h->ev0) { cudaEventDestroy(h->ev0); h->ev0 = nullptr; }
     if (h->ev1) { cudaEventDestroy(h->ev1); h->ev1 = nullptr; }
+    for (cudaEvent_t e : h->ev_fork) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_join) cudaEventDestroy(e);
+    h->ev_fork.clear(); h->ev_join.clear();
+    if (h->stream_q) { cudaStreamDestroy(h->stream_q); h->stream_q = nullptr; }
     if (h->stream) { cudaStreamDestroy(h->stream); h->stream = nullptr; }
 }
 
@@ -424,7 +430,13 @@ int setup_device(ttc_handle* h, int maxrank) {
     int st = check_device(h);
     if (st) return st;
     CUDA_TRY(h, cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, h->device));   // (cudaGetDeviceProperties costs milliseconds)
-    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    {
+        // the sweep stream outranks the quadrature stream: when both have CTAs to place, the bond-visit clusters go first
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_TRY(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_TRY(h, cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
+        CUDA_TRY(h, cudaStreamCreateWithPriority(&h->stream_q, cudaStreamNonBlocking, prio_lo));
+    }
     CUDA_TRY(h, cudaEventCreate(&h->ev0));
     CUDA_TRY(h, cudaEventCreate(&h->ev1));
 
@@ -505,7 +517,7 @@ int setup_device(ttc_handle* h, int maxrank) {
     TRY(dev_alloc(h, &dch, (size_t)(P + 1) * Rmax * Rmax)); TRY(dev_alloc(h, &dch2, (size_t)(P + 1) * Rmax * Rmax));
 #undef TRY
     D.n = dn; D.own = down; D.par = dpar; D.aux = daux; D.Lidx = dL; D.Ridx = dR; D.offL = doffL; D.offR = doffR;
-    D.vip = dvip; D.rk = drk; D.rks = drks; D.arg = darg; D.col = dcol; D.rowT = drow; D.coreOff = dcoreOff; D.inv = dinv;
+    D.vip = dvip; D.rk = drk; D.rks = drks; D.rkq = drk; D.arg = darg; D.col = dcol; D.rowT = drow; D.coreOff = dcoreOff; D.inv = dinv;
     D.acol1 = da1; D.bcol1 = db1; D.arow1 = da2; D.brow1 = db2; D.lot = dlot; D.lraw = dlraw; D.lres = dlres;
     D.part = dpart; D.st = dst; D.out = dout; D.quadw = dquad; D.quadOff = dquadOff; D.ttqq = dttqq; D.chain = dch;
     D.chain2 = dch2; D.sweep_out = dsw;
@@ -753,10 +765,14 @@ int mp_phase2(ttc_handle* h, Launcher& L, int final) {
 // Several processes: each contracts its own cores and chains its own virtual ranks; the chain products are
 // all-gathered (phase 2) and every process runs the reference's binary tree (dmrgg.f90:1355-1405) on all of them.
 // log_maxrank > 0: the last kernel also runs the end-of-sweep bookkeeping (k_sweep_log's body); returns 1 in *logged then.
-int launch_quad(ttc_handle* h, Launcher& L, bool with_lua, bool use_weights, int final = 0, int log_maxrank = 0, bool* logged = nullptr) {
+// log_maxrank < 0: overlapped mode (second stream `qs`, rank snapshot, value recorded by quad_record; see k_sweep_log).
+int launch_quad(ttc_handle* h, Launcher& L, bool with_lua, bool use_weights, int final = 0, int log_maxrank = 0, bool* logged = nullptr,
+                cudaStream_t qs = nullptr) {
     if (logged) *logged = false;
-    const DevPlan& D = h->plan;
-    cudaStream_t s = h->stream;
+    DevPlan D = h->plan;
+    cudaStream_t s = qs ? qs : h->stream;
+    const int ovl = log_maxrank < 0 ? 1 : 0;
+    if (ovl) D.rkq = D.rks;
     const int R = h->Rmax;
     const int ncore = D.c_hi - D.c_lo + 1;
     if (!h->use_wave) {
@@ -769,7 +785,7 @@ int launch_quad(ttc_handle* h, Launcher& L, bool with_lua, bool use_weights, int
     }
     if (with_lua && !h->force_split) {
         // per-sweep path: only the new row / column of every contracted core (k_quad_inc)
-        L(KC_QUAD, [&] { k_quad_inc<<<ncore, QINC_THREADS, h->sm_qinc, s>>>(D, use_weights ? 1 : 0, h->qinc_stage); });
+        L(KC_QUAD, [&] { k_quad_inc<<<ncore, QINC_THREADS, h->sm_qinc, s>>>(D, use_weights ? 1 : 0, h->qinc_stage, ovl); });
     } else {
         L(KC_QUAD, [&] { k_quad_contract_sm<<<dim3(R, ncore), 256, h->sm_contract, s>>>(D, use_weights ? 1 : 0, (int)(h->sm_contract / sizeof(double))); });
         if (with_lua) L(KC_QUAD, [&] { k_quad_lua_sm<<<ncore, 512, h->sm_lua, s>>>(D); });
@@ -903,7 +919,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     KIND_SWITCH(h->kind, L(KC_INIT, [&] { k_init_cross<K><<<dim3(cdiv(h->nmax, TB), d), TB, smA, s>>>(D); }));
     L(KC_INIT, [&] { k_init_factors<<<dim3(cdiv(h->nmax, 256), d), 256, 0, s>>>(D); });
     if (has_quad && h->use_wave && !h->force_split)      // contracted cores of the rank-1 train: extents (1,1) for the incremental quadrature
-        L(KC_INIT, [&] { k_quad_inc<<<D.c_hi - D.c_lo + 1, QINC_THREADS, h->sm_qinc, s>>>(D, 1, h->qinc_stage); });
+        L(KC_INIT, [&] { k_quad_inc<<<D.c_hi - D.c_lo + 1, QINC_THREADS, h->sm_qinc, s>>>(D, 1, h->qinc_stage, 0); });
     // fibers back to the host for the scalar bookkeeping of the '0::' line
     std::vector<std::vector<double>> fib(d + 1);
     for (int p = 1; p <= d; ++p) fib[p].resize(h->n[p]);
@@ -1051,6 +1067,18 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     };
     // one cluster per virtual rank runs the whole visit list of the sweep (ttc_visit.cuh) when the lottery is on the device
     const bool use_cluster = h->cluster_ok && !sync_mode && dev_lot && h->piv >= 0 && !h->force_split;
+    // per-sweep quadrature beside the next sweep's bond visits (second stream); TTC_NO_QUAD_OVERLAP=1 keeps it in line
+    // Only when the bond-visit clusters of all partitions fit on the device at once and leave SMs over: with several waves
+    // of clusters (config E: 63 partitions) the quadrature CTAs get in the way of cluster placement and the sweep slows down.
+    bool overlap = has_quad && !multi && !sync_mode && dev_lot && h->use_wave && !h->force_split && !h->profile &&
+                   (!use_cluster || NV * h->cluster_size < h->nsm);
+    if (const char* e = std::getenv("TTC_QUAD_OVERLAP")) overlap = overlap && std::atoi(e) != 0;      // 0: keep the quadrature in line
+    bool q_pending = false; cudaEvent_t q_last = nullptr; int q_slot = 0;
+    auto quad_rejoin = [&]() -> int {       // the sweep stream waits for the last quadrature (end of a graph / of the run)
+        if (q_pending) CUDA_TRY(h, cudaStreamWaitEvent(s, q_last, 0));
+        q_pending = false;
+        return 0;
+    };
     auto enqueue_sweep = [&](int dir, int rb) -> int {
         if (sync_mode) h->rks_h = h->rk_h;
         if (use_cluster) {
@@ -1078,10 +1106,23 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
             else L(KC_EXCHANGE, [&] { k_exchange_extend<<<dim3(cdiv(2 * h->nmax, 64), nbnd), 64, 0, s>>>(D); });
         }
         const int eff_maxrank = maxrank > 0 ? maxrank : Rmax;        // no maxrank: the rank capacity ends the run
+        if (overlap) {
+            // close the sweep now (the exit test needs no quadrature value) and let its quadrature run on the second stream
+            // beside the next sweep's bond visits; the close overwrites the rank snapshot the previous quadrature reads
+            const size_t slot = (size_t)q_slot++ % h->ev_fork.size();
+            if (q_pending) CUDA_TRY(h, cudaStreamWaitEvent(s, q_last, 0));
+            L(KC_MISC, [&] { k_sweep_log<<<1, 128, 0, s>>>(D, eff_maxrank, 0); });
+            CUDA_TRY(h, cudaEventRecord(h->ev_fork[slot], s));
+            CUDA_TRY(h, cudaStreamWaitEvent(h->stream_q, h->ev_fork[slot], 0));
+            { int e = launch_quad(h, L, true, true, 0, -1, nullptr, h->stream_q); if (e) return e; }
+            CUDA_TRY(h, cudaEventRecord(h->ev_join[slot], h->stream_q));
+            q_last = h->ev_join[slot]; q_pending = true;
+            return 0;
+        }
         bool logged = false;
         if (has_quad) { int e = launch_quad(h, L, true, true, 0, h->force_split ? 0 : eff_maxrank, &logged); if (e) return e; }
         else if (multi) { int e = mp_phase2(h, L, 0); if (e) return e; }
-        if (!logged) L(KC_MISC, [&] { k_sweep_log<<<1, 128, 0, s>>>(D, eff_maxrank); });
+        if (!logged) L(KC_MISC, [&] { k_sweep_log<<<1, 128, 0, s>>>(D, eff_maxrank, 1); });
         return 0;
     };
 
@@ -1090,14 +1131,30 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     // In asynchronous mode a sweep is a fixed kernel sequence (sweep number, seed and thresholds live in device memory),
     // so it is captured once per direction into a CUDA graph and replayed: one graph launch per sweep instead of ~25
     // kernel launches.  Grids are sized for the rank capacity; surplus CTAs exit at once.
-    int graph_sweeps = 4;                 // even: every graph starts with a '>>' sweep
+    // sweeps per graph: even (every graph starts with a '>>' sweep), at most 16, and chosen so that the expected number of
+    // sweeps (maxrank - 1 when the rank bound ends the run) leaves as few no-op sweeps as possible at the end.  The overlapped
+    // quadrature rejoins at the end of a graph, so longer graphs also expose fewer quadratures.
+    int graph_sweeps;
+    {
+        const int S = std::max(2, (maxrank > 0 ? maxrank : Rmax) - 1);
+        const int ng = cdiv(S, 16);
+        graph_sweeps = 2 * cdiv(cdiv(S, ng), 2);
+    }
     if (const char* e = std::getenv("TTC_GRAPH_SWEEPS")) graph_sweeps = std::max(2, 2 * (std::atoi(e) / 2));
+    if (overlap)
+        while ((int)h->ev_fork.size() < std::max(graph_sweeps, 2)) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            CUDA_TRY(h, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+            CUDA_TRY(h, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+            h->ev_fork.push_back(a); h->ev_join.push_back(b);
+        }
     const bool use_graph = !sync_mode && !h->profile && !h->no_graph && (!multi || h->p2p || std::getenv("TTC_MP_GRAPH") != nullptr);
     if (use_graph) {
         std::vector<long long> gsig = {(long long)h->piv, (long long)has_quad, (long long)maxrank, (long long)h->use_wave, (long long)dev_lot,
                                        (long long)h->setup_serial, (long long)h->timeline, (long long)use_cluster,
                                        (long long)h->cluster_size, (long long)h->cluster_threads};
         gsig.push_back(graph_sweeps);
+        gsig.push_back((long long)overlap);
         if (gsig != h->graph_sig) {
             // ONE graph holds `graph_sweeps` consecutive sweeps ('>>', '<<', '>>', ...): fewer graph boundaries on the device.
             // Sweeps past the exit condition are no-ops (the ready flag is tested by every kernel).
@@ -1109,6 +1166,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
             std::copy(h->kc_launch, h->kc_launch + KC_COUNT, kc0);
             int e = 0;
             for (int q = 0; q < graph_sweeps && !e; ++q) e = enqueue_sweep(q % 2 == 0 ? 1 : 2, Rmax);
+            if (!e) e = quad_rejoin();
             h->graph_nodes[0] = h->launches - l0;
             h->launches = l0;
             for (int c = 0; c < KC_COUNT; ++c) { h->graph_kc[0][c] = h->kc_launch[c] - kc0[c]; h->kc_launch[c] = kc0[c]; }
@@ -1154,6 +1212,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         }
     }
 
+    { int e = quad_rejoin(); if (e) return e; }      // (eager mode; a graph rejoins at its end) the finalisation rewrites the cores
     // ---- finalise (dmrgg.f90:1028-1029); not gated by the ready flag.  Each process finalises the cores it owns.
     const int ncore_own = D.c_hi - D.c_lo + 1;
     if (h->use_wave) {

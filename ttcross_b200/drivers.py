@@ -166,3 +166,32 @@ def coscoef(d: int, n: int) -> Problem:
     aux = np.concatenate([mean, np.asfortranarray(cov).ravel(order="F"), [lower, upper]])
     return Problem(api.COSCOEF, d, np.full(d, n, dtype=np.int32), np.arange(n, dtype=np.float64), aux, np.ones(d * n), 500 * EPS, 0.0,
                    f"test_crs_coscoeff {d} {n}")
+
+
+def chf_weights(p: Problem, nfreq: int = 32, span: float = 300.0) -> np.ndarray:
+    """Complex rank-1 weight sets of test_crs_chf.f90:153-166 / test_crs_pdf.f90:153-166: set k weighs every mode with
+    w_q * exp(i * omega_k * exp(x_q) / d), omega_k = k*pi/span; shape [nfreq, d*n] as ttc_quad_complex takes it."""
+    nq = int(p.n[0])
+    x, w = p.par[:nq], p.par[nq:2 * nq]
+    return np.array([np.tile(w * np.exp(1j * (k * math.pi / span) * np.exp(x) / p.d), p.d) for k in range(nfreq)])
+
+
+def cos_approximate(xs, phis, lower_bound: float, upper_bound: float, n_terms=None) -> np.ndarray:
+    """lib/cos_approx.f90:90-127 (cos_approximate_array): COS-method density from characteristic-function values,
+    sum_k' coeff_k cos(omega_k (x - a)), coeff_k = 2/(b-a) Re(phi_k exp(-i omega_k a)), first term halved.  Host-side
+    post-processing of the 32 values ttc_quad_complex returns (test_crs_pdf.f90:171-183)."""
+    xs = np.asarray(xs, dtype=np.float64)
+    phis = np.asarray(phis, dtype=np.complex128)
+    n = len(phis) if n_terms is None else int(n_terms)
+    if n > len(phis):                                   # the reference prints an error and returns zeros (:107-111)
+        print(" Error: n_terms exceeds the size of phis.")
+        return np.zeros_like(xs)
+    out = np.zeros_like(xs)
+    pi_over_bound = 3.1415926535897932384626433832795 / (upper_bound - lower_bound)
+    for k in range(n):
+        omega = k * pi_over_bound
+        coeff = 2.0 / (upper_bound - lower_bound) * (phis[k] * np.exp(-1j * omega * lower_bound)).real
+        if k == 0:
+            coeff = coeff / 2.0
+        out = out + coeff * np.cos(omega * (xs - lower_bound))
+    return out

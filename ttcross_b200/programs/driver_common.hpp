@@ -80,4 +80,46 @@ inline int run_and_report(ttc_handle* h, int maxrank, double acc, int piv, doubl
     return 0;
 }
 
+// Gauss-Jordan with partial pivoting (the reference calls LAPACK dgetrf/dgetri; any correct inverse is input data)
+inline void inv_det(std::vector<double> a, int n, std::vector<double>& inv, double& det) {
+    std::vector<double> m((size_t)n * 2 * n, 0.0);
+    auto M = [&](int i, int j) -> double& { return m[(size_t)i * 2 * n + j]; };
+    for (int i = 0; i < n; ++i) { for (int j = 0; j < n; ++j) M(i, j) = a[(size_t)i * n + j]; M(i, n + i) = 1.0; }
+    det = 1.0;
+    for (int k = 0; k < n; ++k) {
+        int piv = k;
+        for (int i = k + 1; i < n; ++i) if (std::fabs(M(i, k)) > std::fabs(M(piv, k))) piv = i;
+        if (piv != k) { for (int j = 0; j < 2 * n; ++j) std::swap(M(k, j), M(piv, j)); det = -det; }
+        det = det * M(k, k);
+        double pk = M(k, k);
+        for (int j = 0; j < 2 * n; ++j) M(k, j) = M(k, j) / pk;
+        for (int i = 0; i < n; ++i) {
+            if (i == k || M(i, k) == 0.0) continue;
+            double f = M(i, k);
+            for (int j = 0; j < 2 * n; ++j) M(i, j) = M(i, j) - f * M(k, j);
+        }
+    }
+    inv.assign((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) inv[i + (size_t)j * n] = M(i, n + j);   // column-major
+}
+inline double powi(double x, int m) {   // libgcc __powidf2 (what gfortran emits for real**integer)
+    unsigned n = m < 0 ? -m : m;
+    double y = (n % 2) ? x : 1.0;
+    while (n >>= 1) { x = x * x; if (n % 2) y *= x; }
+    return m < 0 ? 1.0 / y : y;
+}
+
+// aux blob of the MVN integrand = module state of lib/mvn_pdf.f90:4-11 after mvn_init(n, r, T) (mvn_pdf.f90:15-60)
+inline std::vector<double> mvn_aux(int d, double rr, double T) {
+    const double sigma = 0.4, corr = 0.5;
+    std::vector<double> cov((size_t)d * d), inv;
+    for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) cov[(size_t)i * d + j] = ((i == j) ? sigma * sigma : sigma * corr * sigma) * T;
+    double det;
+    inv_det(cov, d, inv, det);
+    std::vector<double> aux(d, std::log(100.0) + (rr - 0.5 * (sigma * sigma)) * T);
+    aux.insert(aux.end(), inv.begin(), inv.end());
+    aux.push_back(std::sqrt(powi(2.0 * 3.141592653589793, d) * det));
+    return aux;
+}
+
 }  // namespace drv
