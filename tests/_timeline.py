@@ -16,7 +16,7 @@ tot=sum(sum(v) for v in agg.values())
 for k,v in sorted(agg.items(), key=lambda kv:-sum(kv[1])): print(f"{k:24s} n={len(v):5d} total={sum(v):9.1f} us avg={np.mean(v):7.2f} med={np.median(v):7.2f} share={100*sum(v)/tot:5.1f}%")
 # one late sweep in detail
 names=[a for a,_ in tl]
-idx=[i for i,a in enumerate(names) if a=='k_sweep_log']
+idx=[i for i,a in enumerate(names) if a=='k_visits']
 i0,i1=idx[-3],idx[-2]
 t0=tl[i0][1]
 ck=t.timeline_clocks

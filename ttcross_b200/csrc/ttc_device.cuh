@@ -82,8 +82,10 @@ struct DevPlan {
     int* Lidx; int* Ridx; const i64* offL; const i64* offR;
     int* vip;              // [(d+1)][Rmax][4]
     int* rk; int* rks;     // ranks now / at sweep start, index 0..d
-    const int* rkq;        // ranks the quadrature kernels read: rk, or the snapshot rks when the quadrature of sweep s runs beside
-                           // the bond visits of sweep s+1 (second stream; everything it reads below those ranks never changes)
+    int* qsnap;            // [2][d+1] rank snapshots for the overlapped quadrature: the close of sweep s writes buffer s & 1, the
+                           // quadrature of sweep s (second stream, beside the bond visits of sweep s+1) reads it; everything
+                           // the quadrature reads below those ranks never changes once written
+    unsigned int* btick;   // arrival counter of k_exchange_fused (its last CTA closes the sweep)
     double* arg; double* col; double* rowT; const i64* coreOff;   // coreOff[p], p = 1..d
     double* inv;           // [(d+1)][Rmax*Rmax]
     double* acol1; double* bcol1; double* arow1; double* brow1;   // [P][Rmax*nmax]
@@ -1178,7 +1180,10 @@ __device__ __forceinline__ void sweep_log_body(const DevPlan& P, int maxrank, bo
     __shared__ unsigned long long s_ne;
     __shared__ double s_amax, s_pmax, s_pmin;
     if (threadIdx.x == 0) { s_ne = 0ULL; s_amax = P.st[0].amax; s_pmax = P.st[0].pivotmax; s_pmin = P.st[0].pivotmin; }
-    for (int x = threadIdx.x; x <= P.d; x += blockDim.x) { int r = P.rk[x]; P.rklog[(i64)it * (P.d + 1) + x] = r; P.rks[x] = r; }
+    for (int x = threadIdx.x; x <= P.d; x += blockDim.x) {
+        int r = P.rk[x];
+        P.rklog[(i64)it * (P.d + 1) + x] = r; P.rks[x] = r; P.qsnap[(it & 1) * (P.d + 1) + x] = r;
+    }
     __syncthreads();
     for (int v = threadIdx.x; v < P.P; v += blockDim.x) {
         atomicAdd(&s_ne, (unsigned long long)P.st[v].neval);
@@ -1213,10 +1218,13 @@ __global__ void k_sweep_log(DevPlan P, int maxrank, int with_val) {
 }
 // Overlapped quadrature (log_maxrank < 0 in the quadrature kernels): the exit test of dmrgg.f90:1010-1019 does not use the
 // quadrature value, so k_sweep_log(with_val = 0) closes sweep s right after the exchange and the quadrature of sweep s
-// runs on a second stream beside the bond visits of sweep s+1, reading the rank snapshot rks (P.rkq).  ctrl->it - 1 sweeps
-// are closed, ctrl->itq of them have their value recorded; the next k_sweep_log waits for the quadrature (event), so both
-// counters are stable while a quadrature group runs.
-__device__ __forceinline__ bool quad_pending(const DevPlan& P) { return P.ctrl->itq < P.ctrl->it - 1; }
+// runs on a second stream beside the bond visits of sweep s+1, reading the rank snapshot qsnap[s & 1].  ctrl->it - 1
+// sweeps are closed, ctrl->itq of them have their value recorded (itq changes only at the end of a quadrature group; the
+// close of sweep s+2 waits for the quadrature of sweep s by an event, so its snapshot buffer is not overwritten early).
+__device__ __forceinline__ bool quad_pending(const DevPlan& P) { return P.ctrl->itq < *(volatile int*)&P.ctrl->it - 1; }
+__device__ __forceinline__ const int* quad_ranks(const DevPlan& P, int ovl) {
+    return ovl ? P.qsnap + ((P.ctrl->itq + 1) & 1) * (P.d + 1) : P.rk;
+}
 __device__ __forceinline__ void quad_record(const DevPlan& P, double val) {    // one thread of the group's last kernel
     if (!quad_pending(P)) return;
     const int sw = P.ctrl->itq + 1;
@@ -1699,20 +1707,21 @@ __global__ void k_quad_chain_sm(DevPlan P, int log_maxrank) {
     int last = P.own[v + 1] - 1;
     if (v == P.P - 1) last = P.d;
     const int ld = P.Rmax;
+    const int* rq = quad_ranks(P, log_maxrank < 0);
     const i64 msz = (i64)ld * ld;
     double* cur = smem; double* nxt = smem + msz; double* B = smem + 2 * msz;
-    const int m = P.rkq[first - 1];
-    mat_load_sm(P.ttqq + (i64)first * msz, m, P.rkq[first], ld, cur, ld);
+    const int m = rq[first - 1];
+    mat_load_sm(P.ttqq + (i64)first * msz, m, rq[first], ld, cur, ld);
     __syncthreads();
     for (int p = first + 1; p <= last; ++p) {
-        mat_load_sm(P.ttqq + (i64)p * msz, P.rkq[p - 1], P.rkq[p], ld, B, ld);
+        mat_load_sm(P.ttqq + (i64)p * msz, rq[p - 1], rq[p], ld, B, ld);
         __syncthreads();
-        mat_mul_sm(cur, m, P.rkq[p - 1], B, P.rkq[p], nxt, ld);
+        mat_mul_sm(cur, m, rq[p - 1], B, rq[p], nxt, ld);
         __syncthreads();
         double* t = cur; cur = nxt; nxt = t;
     }
     double* out = P.chain + (i64)v * msz;
-    const int nl = P.rkq[last];
+    const int nl = rq[last];
     for (int e = threadIdx.x; e < m * nl; e += blockDim.x) { int j = e / m, i = e - j * m; out[i + (i64)ld * j] = cur[i + ld * j]; }
     if (P.P == 1 && threadIdx.x == 0) { P.sweep_out->val = cur[0]; if (log_maxrank < 0) quad_record(P, cur[0]); }
     if (P.P == 1 && log_maxrank > 0 && !P.ctrl->ready) { __syncthreads(); sweep_log_body(P, log_maxrank); }   // single partition: this is the sweep's last kernel
@@ -1723,12 +1732,13 @@ __global__ void k_quad_tree_sm(DevPlan P, int q, int last_level, int log_maxrank
     extern __shared__ double smem[];
     const int me = blockIdx.x * 2 * q, her = me + q;
     const int ld = P.Rmax;
+    const int* rq = quad_ranks(P, log_maxrank < 0);
     const i64 msz = (i64)ld * ld;
     if (her < P.P) {
         double* A = smem; double* B = smem + msz; double* C = smem + 2 * msz;
         int herend = her + q; if (herend > P.P) herend = P.P;
-        const int m = P.rkq[P.own[me] - 1], kd = P.rkq[P.own[her] - 1];
-        const int n = (herend == P.P) ? P.rkq[P.d] : P.rkq[P.own[herend] - 1];
+        const int m = rq[P.own[me] - 1], kd = rq[P.own[her] - 1];
+        const int n = (herend == P.P) ? rq[P.d] : rq[P.own[herend] - 1];
         mat_load_sm(P.chain + (i64)me * msz, m, kd, ld, A, ld);
         mat_load_sm(P.chain + (i64)her * msz, kd, n, ld, B, ld);
         __syncthreads();
@@ -1756,7 +1766,8 @@ __global__ void k_quad_inc(DevPlan P, int use_weights, int stage_doubles, int ov
     if (ovl ? !quad_pending(P) : (P.ctrl->ready != 0)) return;
     extern __shared__ double smem[];
     const int p = P.c_lo + blockIdx.x;
-    const int r0 = P.rkq[p - 1], r1 = P.rkq[p], n = P.n[p];
+    const int* rq = quad_ranks(P, ovl);
+    const int r0 = rq[p - 1], r1 = rq[p], n = P.n[p];
     const int e0 = P.qext[2 * p], e1 = P.qext[2 * p + 1];
     if (e0 == r0 && e1 == r1) return;
     if (r0 - e0 > 1 || r1 - e1 > 1 || r0 < e0 || r1 < e1) { if (threadIdx.x == 0) P.ctrl->error = 2; return; }

@@ -136,6 +136,7 @@ struct ttc_handle {
     int no_graph = 0;
     bool use_wave = true;                // warp-wavefront / shared-memory support kernels (needs Rmax <= 32*MAXRPL)
     size_t sm_contract = 0, sm_lua = 0, sm_mat3 = 0, sm_ext = 0, sm_lot = 0, sm_fiber = 0, sm_sb = 0;
+    size_t sm_xf = 0; bool xf_ok = false;             // k_exchange_fused: aux | 2 d | two staged LU tables
     int force_sync = 0, force_host_lottery = 0, force_simple = 0, force_split = 0;
     size_t sm_qinc = 0; int qinc_stage = 0;
     size_t sm_sbt = 0; bool sbt_ok = false;      // tiled superblock kernel (ttc_superblock.cuh)
@@ -517,7 +518,7 @@ int setup_device(ttc_handle* h, int maxrank) {
     TRY(dev_alloc(h, &dch, (size_t)(P + 1) * Rmax * Rmax)); TRY(dev_alloc(h, &dch2, (size_t)(P + 1) * Rmax * Rmax));
 #undef TRY
     D.n = dn; D.own = down; D.par = dpar; D.aux = daux; D.Lidx = dL; D.Ridx = dR; D.offL = doffL; D.offR = doffR;
-    D.vip = dvip; D.rk = drk; D.rks = drks; D.rkq = drk; D.arg = darg; D.col = dcol; D.rowT = drow; D.coreOff = dcoreOff; D.inv = dinv;
+    D.vip = dvip; D.rk = drk; D.rks = drks; D.arg = darg; D.col = dcol; D.rowT = drow; D.coreOff = dcoreOff; D.inv = dinv;
     D.acol1 = da1; D.bcol1 = db1; D.arow1 = da2; D.brow1 = db2; D.lot = dlot; D.lraw = dlraw; D.lres = dlres;
     D.part = dpart; D.st = dst; D.out = dout; D.quadw = dquad; D.quadOff = dquadOff; D.ttqq = dttqq; D.chain = dch;
     D.chain2 = dch2; D.sweep_out = dsw;
@@ -552,6 +553,10 @@ int setup_device(ttc_handle* h, int maxrank) {
         D.ctrl = dctrl; D.vlog = dvlog; D.slog = dslog; D.rklog = drklog;
         unsigned int* dtick; s1 = dev_alloc(h, &dtick, (size_t)P + 1); if (s1) return s1;
         D.tickets = dtick;
+        unsigned int* dbt; int* dqs;
+        s1 = dev_alloc(h, &dbt, 2); if (s1) return s1;
+        s1 = dev_alloc(h, &dqs, (size_t)2 * (d + 2)); if (s1) return s1;
+        D.btick = dbt; D.qsnap = dqs;
         if (h->nproc > 1) {
             const size_t w1 = (size_t)mb1_slot_words(maxnb0) * D.vper, w2 = (size_t)mb2_slot_doubles(Rmax) * D.vper;
             const size_t slab = (size_t)Rmax * h->nmax, rowinv = slab + (size_t)Rmax * Rmax;
@@ -662,6 +667,11 @@ int setup_device(ttc_handle* h, int maxrank) {
             if (bs > 48 * 1024) { cudaFuncSetAttribute(k_superblock<K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs);
                                   cudaFuncSetAttribute(k_superblock<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs); }
             if (ba + 16 * h->d > 48 * 1024) cudaFuncSetAttribute(k_exchange_corner<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba + 16 * h->d);
+            {
+                h->sm_xf = (size_t)ba + ((size_t)2 * h->d + (size_t)2 * h->Rmax * h->Rmax + h->Rmax) * sizeof(double);
+                h->xf_ok = h->sm_xf <= (size_t)200 * 1024 &&
+                           cudaFuncSetAttribute(k_exchange_fused<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_xf) == cudaSuccess;
+            }
             if (ba > 48 * 1024) {
                                   cudaFuncSetAttribute(k_init_search<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba);
                                   cudaFuncSetAttribute(k_init_cross<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba); }
@@ -769,10 +779,9 @@ int mp_phase2(ttc_handle* h, Launcher& L, int final) {
 int launch_quad(ttc_handle* h, Launcher& L, bool with_lua, bool use_weights, int final = 0, int log_maxrank = 0, bool* logged = nullptr,
                 cudaStream_t qs = nullptr) {
     if (logged) *logged = false;
-    DevPlan D = h->plan;
+    const DevPlan& D = h->plan;
     cudaStream_t s = qs ? qs : h->stream;
     const int ovl = log_maxrank < 0 ? 1 : 0;
-    if (ovl) D.rkq = D.rks;
     const int R = h->Rmax;
     const int ncore = D.c_hi - D.c_lo + 1;
     if (!h->use_wave) {
@@ -1074,13 +1083,28 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
                    (!use_cluster || NV * h->cluster_size < h->nsm);
     if (const char* e = std::getenv("TTC_QUAD_OVERLAP")) overlap = overlap && std::atoi(e) != 0;      // 0: keep the quadrature in line
     bool q_pending = false; cudaEvent_t q_last = nullptr; int q_slot = 0;
+    cudaEvent_t q_prev = nullptr;           // fused sweep: the join event of the quadrature before the last one
     auto quad_rejoin = [&]() -> int {       // the sweep stream waits for the last quadrature (end of a graph / of the run)
         if (q_pending) CUDA_TRY(h, cudaStreamWaitEvent(s, q_last, 0));
-        q_pending = false;
+        q_pending = false; q_prev = nullptr;
         return 0;
     };
+    // fused sweep (single process): the close of the sweep runs in the sweep's last kernel -- k_exchange_fused (corner +
+    // extensions + close in one launch), or k_visits itself with one partition; the quadrature then always runs in its
+    // overlapped form (own sweep counter, rank snapshot), on the second stream when `overlap`, else in line.
+    // The fused exchange spends one warp per mode index: it pays when its grid is about one wave (config E with 62
+    // boundaries and a 12k-flop integrand is better off with the separate corner kernel).  TTC_FUSED_SWEEP=0 disables.
+    bool fused = use_cluster && !multi && h->use_wave && (P == 1 || (h->xf_ok && cdiv(2 * h->nmax, 8) * (P - 1) <= 4 * h->nsm));
+    if (const char* e = std::getenv("TTC_FUSED_SWEEP")) fused = fused && std::atoi(e) != 0;
+    if (const char* e = std::getenv("TTC_FUSED_SWEEP")) fused = fused && std::atoi(e) != 0;
+    const int eff_maxrank = maxrank > 0 ? maxrank : Rmax;        // no maxrank: the rank capacity ends the run
     auto enqueue_sweep = [&](int dir, int rb) -> int {
         if (sync_mode) h->rks_h = h->rk_h;
+        if (fused && overlap && q_prev) {
+            // the close inside this sweep's kernel overwrites the rank snapshot buffer the quadrature of two sweeps ago read
+            CUDA_TRY(h, cudaStreamWaitEvent(s, q_prev, 0));
+            q_prev = nullptr;
+        }
         if (use_cluster) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(h->cluster_size, NV, 1);
@@ -1092,10 +1116,26 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
             at[0].val.clusterDim.x = h->cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             cudaError_t ce = cudaSuccess;
-            KIND_SWITCH(h->kind, L(KC_VISITS, [&] { ce = cudaLaunchKernelEx(&cfg, k_visits<K>, D, dir, small_element, small_pivot, multi ? 0 : 1); }));
+            KIND_SWITCH(h->kind, L(KC_VISITS, [&] { ce = cudaLaunchKernelEx(&cfg, k_visits<K>, D, dir, small_element, small_pivot, multi ? 0 : 1, (fused && P == 1) ? eff_maxrank : 0); }));
             CUDA_TRY(h, ce);
         } else {
             for (int pp = 1; pp <= maxnb; ++pp) { int e = enqueue_visit(dir, pp, rb); if (e) return e; }
+        }
+        if (fused) {
+            if (P > 1) {
+                const int nbnd = boundary_count(D);
+                KIND_SWITCH(h->kind, L(KC_EXCHANGE, [&] { k_exchange_fused<K><<<dim3(cdiv(2 * h->nmax, 8), nbnd), 256, h->sm_xf, s>>>(D, eff_maxrank); }));
+            }
+            if (!has_quad) return 0;
+            if (!overlap) return launch_quad(h, L, true, true, 0, -1, nullptr, nullptr);
+            const size_t slot = (size_t)q_slot++ % h->ev_fork.size();
+            CUDA_TRY(h, cudaEventRecord(h->ev_fork[slot], s));
+            CUDA_TRY(h, cudaStreamWaitEvent(h->stream_q, h->ev_fork[slot], 0));
+            { int e = launch_quad(h, L, true, true, 0, -1, nullptr, h->stream_q); if (e) return e; }
+            CUDA_TRY(h, cudaEventRecord(h->ev_join[slot], h->stream_q));
+            q_prev = q_pending ? q_last : nullptr;
+            q_last = h->ev_join[slot]; q_pending = true;
+            return 0;
         }
         if (P > 1) {
             if (multi) { int e = mp_phase1(h, L); if (e) return e; }
@@ -1105,7 +1145,6 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
             if (h->use_wave) L(KC_EXCHANGE, [&] { k_exchange_extend_w<<<dim3(cdiv(h->nmax, 8), nbnd, 2), 256, h->sm_ext, s>>>(D); });
             else L(KC_EXCHANGE, [&] { k_exchange_extend<<<dim3(cdiv(2 * h->nmax, 64), nbnd), 64, 0, s>>>(D); });
         }
-        const int eff_maxrank = maxrank > 0 ? maxrank : Rmax;        // no maxrank: the rank capacity ends the run
         if (overlap) {
             // close the sweep now (the exit test needs no quadrature value) and let its quadrature run on the second stream
             // beside the next sweep's bond visits; the close overwrites the rank snapshot the previous quadrature reads
@@ -1155,6 +1194,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
                                        (long long)h->cluster_size, (long long)h->cluster_threads};
         gsig.push_back(graph_sweeps);
         gsig.push_back((long long)overlap);
+        gsig.push_back((long long)fused);
         if (gsig != h->graph_sig) {
             // ONE graph holds `graph_sweeps` consecutive sweeps ('>>', '<<', '>>', ...): fewer graph boundaries on the device.
             // Sweeps past the exit condition are no-ops (the ready flag is tested by every kernel).

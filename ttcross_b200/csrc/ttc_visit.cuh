@@ -179,9 +179,158 @@ __device__ __forceinline__ void cluster_fold(cg::cluster_group& cl, VisitShared&
 }
 
 // ----------------------------------------------------------------------------
+// Close of a sweep inside the sweep's last kernel (single process).  The exit test of dmrgg.f90:1010-1019 needs no
+// quadrature value, so the last CTA / cluster to finish (arrival counter) runs k_sweep_log's body right away: one launch
+// less on the critical path.  Values other CTAs produced in this kernel are read through volatile / ld.global.cg.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void sweep_close_fused(const DevPlan& P, int maxrank) {
+    volatile VState* st = P.st;
+    const int it = P.ctrl->it;
+    __shared__ unsigned long long s_ne;
+    __shared__ double s_amax, s_pmax, s_pmin;
+    if (threadIdx.x == 0) { s_ne = 0ULL; s_amax = st[0].amax; s_pmax = st[0].pivotmax; s_pmin = st[0].pivotmin; }
+    for (int x = threadIdx.x; x <= P.d; x += blockDim.x) {
+        const int r = __ldcg(P.rk + x);
+        P.rklog[(i64)it * (P.d + 1) + x] = r; P.rks[x] = r; P.qsnap[(it & 1) * (P.d + 1) + x] = r;
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < P.P; v += blockDim.x) {          // one thread per virtual rank: independent L2 round trips
+        atomicAdd(&s_ne, (unsigned long long)st[v].neval);
+        st[v].pivotmax_prev = st[v].pivotmax;            // dmrgg.f90:961
+        st[v].pivotmax = -1.0; st[v].pivotmin = -1.0;    // dmrgg.f90:326-327 of the next sweep
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    P.slog[it].neval = (i64)s_ne; P.slog[it].amax = s_amax; P.slog[it].pivotmax = s_pmax; P.slog[it].pivotmin = s_pmin;
+    P.slog[it].t_ns = globaltimer_ns() - P.ctrl->t0_ns; P.slog[it].valid = 1; P.slog[it].pad = 0;
+    P.ctrl->nsweeps = it;
+    int ready = 0;
+    if (maxrank > 0) ready = (it + 1 >= maxrank);
+    if (P.ctrl->has_accuracy) {
+        if (s_pmax <= P.ctrl->accuracy * s_amax) P.ctrl->strike += 1; else P.ctrl->strike = 0;
+        ready = ready || (P.ctrl->strike >= 3);
+    }
+    if (P.ctrl->error) ready = 1;
+    P.ctrl->it = it + 1;
+    __threadfence();
+    P.ctrl->ready = ready;
+}
+
+// ----------------------------------------------------------------------------
+// Post-sweep exchange of a single process in ONE kernel (k_exchange_corner + k_exchange_extend_w + k_sweep_log).
+// Boundary b, shared core c = own[b+1]: the LEFT chain of mode index x (row(c)(:, x, rc), d2_luar with inv(c-1)) and the
+// RIGHT chain of x (col(c)(rc1, x, :), d2_lual with inv(c)) each need exactly one element of the corner fiber, the one
+// at x -- so the warp that owns x evaluates it itself and no CTA waits for another one (dmrgg.f90:872-958,
+// dmrggmp.f90:572-629).  grid (ceil(2 nmax / warps per CTA), boundaries); the last CTA closes the sweep (close_maxrank > 0).
+// dynamic smem: A[auxsm] | XF[d] WF[d] | TL[Rmax^2] | TR[Rmax^2 + Rmax]
+// ----------------------------------------------------------------------------
+template <int KIND>
+__global__ void k_exchange_fused(DevPlan P, int close_maxrank) {
+    tl_stamp(P, 9);
+    if (P.ctrl->ready) return;
+    extern __shared__ double smem[];
+    __shared__ Partial shp[32];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int b = blockIdx.y;
+    const int c = P.own[b + 1];
+    const int rc1 = P.rk[c - 1], rc1s = P.rks[c - 1], rc = P.rk[c], rcs = P.rks[c];
+    const int nc = P.n[c];
+    const bool corner = (rc1 > rc1s) && (rc > rcs), left = rc > rcs, right = rc1 > rc1s;
+    if (left || right) {
+        const double* A = stage_aux<KIND>(P, smem);
+        double* XF = smem + P.auxsm; double* WF = XF + P.d;
+        double* TL = WF + P.d; double* TR = TL + (i64)P.Rmax * P.Rmax; double* DI = TR + (i64)P.Rmax * P.Rmax;
+        double* argc = P.arg + P.coreOff[c];
+        const bool hasw = (P.kind == KIND_ISING);
+        const int nwoff = P.n[1];
+        if (corner) {
+            const int* Lt = P.Lidx + P.offL[c - 1]; const int* Rt = P.Ridx + P.offR[c];
+            for (int pos = threadIdx.x; pos < P.d - 1; pos += blockDim.x) {
+                const int idx = (pos < c - 1) ? Lt[(i64)pos * P.Rmax + (rc1 - 1)] : Rt[(i64)(pos - (c - 1)) * P.Rmax + (rc - 1)];
+                XF[pos] = P.par[idx - 1]; WF[pos] = hasw ? P.par[nwoff + idx - 1] : 0.0;
+            }
+        }
+        if (left) stage_luar(P.inv + (i64)(c - 1) * P.Rmax * P.Rmax, rc1, TL);
+        if (right) stage_lual(P.inv + (i64)c * P.Rmax * P.Rmax, rc, TR, DI);
+        __syncthreads();
+        const int job = blockIdx.x * nw + wid;                      // one warp per (mode index, side): both sides evaluate the
+        const int x = job >> 1, side = job & 1;                     // corner element (cheap), side 0 stores and counts it
+        Partial best = amax_init();
+        if (x < nc) {
+            double f = 0.0;
+            if (corner) {                                           // lane 0 evaluates and stores, the warp gets the value
+                if (lane == 0) {
+                    StagedVals sv;
+                    sv.XL = XF; sv.WL = WF; sv.nl = c - 1; sv.rl = 1; sv.i = 1;
+                    sv.xj = P.par[x]; sv.wj = hasw ? P.par[nwoff + x] : 0.0;
+                    sv.hask = 0; sv.xk = 0.0; sv.wk = 0.0;
+                    sv.XR = XF + (c - 1); sv.WR = WF + (c - 1); sv.rr = 1; sv.q = 1;
+                    f = eval_point<KIND>(P, sv, A);
+                    if (side == 0) { argc[(rc1 - 1) + (i64)P.Rmax * (x + (i64)nc * (rc - 1))] = f; amax_take(best, f, x); }
+                }
+                f = __shfl_sync(FULLMASK, f, 0);
+            }
+            if (left && side == 0) {
+                // LEFT receiver (virtual rank b): row(c)(:, x, rc) = d2_luar(rc1, inv(c-1)) of arg(c)(:, x, rc)
+                const double* src = argc + (i64)P.Rmax * (x + (i64)nc * (rc - 1));
+                double* dst = P.rowT + P.coreOff[c] + (i64)nc * (rc - 1) + x;
+                const i64 de = (i64)nc * P.Rmax;
+                double y[MAXRPL];
+#pragma unroll
+                for (int u = 0; u < MAXRPL; ++u) {
+                    const int sidx = lane + 32 * u;
+                    y[u] = (sidx < rc1) ? ((corner && sidx == rc1 - 1) ? f : src[sidx]) : 0.0;
+                }
+                warp_luar(y, rc1, GSm{TL, rc1});
+#pragma unroll
+                for (int u = 0; u < MAXRPL; ++u) { const int sidx = lane + 32 * u; if (sidx < rc1) dst[sidx * de] = y[u]; }
+            }
+            if (right && side == 1) {
+                // RIGHT receiver (virtual rank b+1): col(c)(rc1, x, :) = d2_lual(rc, inv(c)) of arg(c)(rc1, x, :)
+                const i64 se = (i64)P.Rmax * nc;
+                const double* src = argc + (rc1 - 1) + (i64)P.Rmax * x;
+                double* dst = P.col + P.coreOff[c] + (rc1 - 1) + (i64)P.Rmax * x;
+                double y[MAXRPL];
+#pragma unroll
+                for (int u = 0; u < MAXRPL; ++u) {
+                    const int cc = lane + 32 * u;
+                    y[u] = (cc < rc) ? ((corner && cc == rc - 1) ? f : src[cc * se]) : 0.0;
+                }
+                warp_lual(y, rc, GSm{TR, rc}, DSm{DI});
+#pragma unroll
+                for (int u = 0; u < MAXRPL; ++u) { const int cc = lane + 32 * u; if (cc < rc) dst[cc * se] = y[u]; }
+            }
+        }
+        if (corner) {
+            best = amax_block(best, shp);
+            if (threadIdx.x == 0) {
+                // both virtual ranks of the boundary saw the fiber (amax >= 0: the bit pattern orders like the value); each counts it
+                for (int v = b; v <= b + 1; ++v) {
+                    atomicMax((long long*)&P.st[v].amax, __double_as_longlong(best.absv));
+                    if (blockIdx.x == 0) atomicAdd((unsigned long long*)&P.st[v].neval, (unsigned long long)nc);
+                }
+            }
+        }
+    }
+    if (close_maxrank <= 0) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        const unsigned tk = atomicAdd(P.btick, 1u);
+        s_last = (tk == total - 1);
+        if (s_last) { P.btick[0] = 0; __threadfence(); }
+    }
+    __syncthreads();
+    if (s_last) sweep_close_fused(P, close_maxrank);
+}
+
+// ----------------------------------------------------------------------------
 // all bond visits of one sweep direction for the virtual ranks of this process (pivoting >= 0).
 // grid (CS, nv), cluster (CS, 1, 1).  dynamic smem: A[auxsm] | xs[Rmax] | ext[Rmax^2 + Rmax] | stage[stage_max] | ints[4*Rmax + 8]
 // fold_allreduce != 0: the last cluster to finish performs the MAX reduction of dmrgg.f90:852-870 (single process only).
+// close_maxrank > 0 (single partition only): the cluster also closes the sweep (sweep_close_fused).
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ void tl_mark(const DevPlan& P, int id) {     // diagnostic: phase stamps of the first cluster
     if (P.tlog && blockIdx.x == 0 && blockIdx.y == gridDim.y / 2 && threadIdx.x == 0) {
@@ -195,7 +344,7 @@ constexpr int VISIT_MAXTHREADS = 256;
 // MVN evaluations are one long dependent DADD chain each (3 d^2 operations, one accumulator, mvn_pdf.f90:74-80): they need
 // many resident warps, not registers -> 256 threads x 4 CTAs per SM (64 registers); the other integrands keep 128 registers.
 template <int KIND>
-__global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_visits(DevPlan P, int dir, double small_element, double small_pivot, int fold_allreduce) {
+__global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_visits(DevPlan P, int dir, double small_element, double small_pivot, int fold_allreduce, int close_maxrank) {
     tl_stamp(P, 40);
     if (LDF(&P.ctrl->ready)) return;          // uniform over the grid: written only by k_sweep_log
     cg::cluster_group cl = cg::this_cluster();
@@ -460,6 +609,25 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_
             VisitOut& O = P.vlog[((i64)(it - 1) * P.maxnb + (pp - 1)) * P.P + v];
             O.active = 0; O.upd = 0;
         }
+    }
+    if (close_maxrank > 0) {
+        // ---- single partition: this cluster is the whole sweep; close it here (no exchange, no reduction)
+        if (crank == 0 && threadIdx.x == 0) P.st[v] = sh.S;
+        __threadfence();
+        cl.sync();
+        if (crank == 0) {
+            if (threadIdx.x == 0) {
+                __threadfence();
+                const unsigned tk = atomicAdd(P.tickets + P.P, 1u);
+                sh.nz[1] = (tk == (unsigned)P.nv - 1);
+                if (sh.nz[1]) { P.tickets[P.P] = 0; __threadfence(); }
+            }
+            __syncthreads();
+            if (sh.nz[1]) sweep_close_fused(P, close_maxrank);
+        }
+        return;
+    }
+    if (crank == 0) {
         if (threadIdx.x == 0) {
             P.st[v] = sh.S;
             if (fold_allreduce && P.P > 1) {
