@@ -1,12 +1,17 @@
 import sys; sys.path.insert(0,'/root/repo')
 import numpy as np, collections
 import ttcross_b200 as T
-p = T.drivers.ising('c',10,256)
-t=p.make(); t.set_partition(int(sys.argv[1]) if len(sys.argv)>1 else 8)
-for i in range(3): g=t.dmrgg(32,p.accuracy,2)
+import os
+cfg = os.environ.get('TTC_TL_CFG', 'B')
+if cfg == 'E':
+    p = T.drivers.mvn(64, 128); R, piv, P0 = 32, 1, 63
+else:
+    p = T.drivers.ising('c',10,256); R, piv, P0 = 32, 2, 8
+t=p.make(); t.set_partition(int(sys.argv[1]) if len(sys.argv)>1 else P0)
+for i in range(3): g=t.dmrgg(R,p.accuracy,piv)
 print("device ms", g.device_ms, "sweeps", g.nsweeps)
 t.set_timeline(True)
-g=t.dmrgg(32,p.accuracy,2)
+g=t.dmrgg(R,p.accuracy,piv)
 tl=t.timeline()
 print("timeline device ms", g.device_ms, "stamps", len(tl))
 # intervals: time from this stamp to the next stamp, attributed to this kernel

@@ -361,6 +361,48 @@ __device__ __noinline__ double eval_mvn(const DevPlan& P, const V& v, const doub
     return exp(-0.5 * e) / denom;
 }
 
+// The same arithmetic with diff[] held in REGISTERS for the inner loop.  eval_mvn above keeps diff[] in local memory: at
+// d = 64 that is 512 B per thread, the resident threads' copies (256 KB per SM) do not fit the L1 next to the staged
+// matrix, and every one of the d*d terms re-reads diff[j] from L2 (timeline of config E: 300 us per evaluation).  Here the
+// inner loop over j is fully unrolled over M >= d slots in blocks of 8 (d a multiple of 8), so the only memory operand of
+// a term is the matrix entry, which all lanes share.  Needs ~2 M + 40 registers: kernels that call it must not cap the
+// register count below that (k_visits<MVN> is compiled for one CTA per SM).  Same operations in the same order.
+template <int M, class V>
+__device__ __noinline__ double eval_mvn_reg(const DevPlan& P, const V& v, const double* __restrict__ A /*d*d*/) {
+    const int m = P.d;                                   // a multiple of 8, M - 16 < m <= M
+    const double* mu = P.aux;
+    const double denom = P.aux[m + (i64)m * m];
+    double x[MAXD_LOCAL];
+    v.gather(m, x, nullptr, false);
+    double dr[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) dr[j] = (j < m) ? x[j] - mu[j] : 0.0;
+    double e = 0.0;
+    for (int i = 0; i < m; ++i) {
+        const double di = x[i] - mu[i];
+        const double* Ai = A + i;
+#pragma unroll
+        for (int jb = 0; jb < M; jb += 8) {
+            if (jb < m) {                                // whole blocks of 8: the matrix entries load ahead of the chain
+                double a[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a[u] = Ai[(i64)(jb + u) * m];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) e = e + di * a[u] * dr[jb + u];
+            }
+        }
+    }
+    return exp(-0.5 * e) / denom;
+}
+template <class V>
+__device__ __forceinline__ double eval_mvn_fast(const DevPlan& P, const V& v, const double* A) {
+    const int m = P.d;
+    if (m <= 16 || m > 64 || (m & 7)) return eval_mvn(P, v, A);     // small d: the local copy stays in L1
+    if (m <= 32) return eval_mvn_reg<32>(P, v, A);
+    if (m <= 48) return eval_mvn_reg<48>(P, v, A);
+    return eval_mvn_reg<64>(P, v, A);
+}
+
 // COS-method coefficient of a Gaussian density (lib/coefficients.f90:33-65 with lib/funcs.f90:8-26, lib/s_vectors.f90:7-29):
 //   f = 2/(b-a)^d * sum over the 2^(d-1) sign vectors s (s_1 = 1) of Re[ exp(-i a sum(t)) * exp(i t.mu - t.Sigma.t / 2) ],
 //   t_j = pi s_j (ind_j - 1) / (b - a).   aux = mu(d) | Sigma(d,d) column-major | a | b;  the "node" of mode index k is k - 1.
@@ -424,6 +466,12 @@ __device__ __forceinline__ double eval_point(const DevPlan& P, const V& v, const
     if (KIND == KIND_STDNORM) return eval_stdnorm(P, v);
     if (KIND == KIND_COSCOEF) return eval_coscoef(P, v);
     return eval_mvn(P, v, A);
+}
+// for kernels without a tight register cap (see eval_mvn_reg)
+template <int KIND, class V>
+__device__ __forceinline__ double eval_point_wide(const DevPlan& P, const V& v, const double* A) {
+    if (KIND == KIND_MVN) return eval_mvn_fast(P, v, A);
+    return eval_point<KIND>(P, v, A);
 }
 template <int KIND, class Src>
 __device__ __forceinline__ double eval_src(const DevPlan& P, const Src& s, const double* A) {
@@ -1271,7 +1319,7 @@ __global__ void k_exchange_corner(DevPlan P) {
         sv.xj = P.par[j]; sv.wj = (P.kind == KIND_ISING) ? P.par[P.n[1] + j] : 0.0;
         sv.hask = 0; sv.xk = 0.0; sv.wk = 0.0;
         sv.XR = XF + (c - 1); sv.WR = WF + (c - 1); sv.rr = 1; sv.q = 1;
-        double f = eval_point<KIND>(P, sv, A);
+        double f = eval_point_wide<KIND>(P, sv, A);
         argc[(rc1 - 1) + (i64)P.Rmax * (j + (i64)nc * (rc - 1))] = f;
         amax_take(best, f, j);
     }

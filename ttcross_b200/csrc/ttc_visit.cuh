@@ -266,7 +266,7 @@ __global__ void k_exchange_fused(DevPlan P, int close_maxrank) {
                     sv.xj = P.par[x]; sv.wj = hasw ? P.par[nwoff + x] : 0.0;
                     sv.hask = 0; sv.xk = 0.0; sv.wk = 0.0;
                     sv.XR = XF + (c - 1); sv.WR = WF + (c - 1); sv.rr = 1; sv.q = 1;
-                    f = eval_point<KIND>(P, sv, A);
+                    f = eval_point_wide<KIND>(P, sv, A);
                     if (side == 0) { argc[(rc1 - 1) + (i64)P.Rmax * (x + (i64)nc * (rc - 1))] = f; amax_take(best, f, x); }
                 }
                 f = __shfl_sync(FULLMASK, f, 0);
@@ -341,8 +341,11 @@ __device__ __forceinline__ void tl_mark(const DevPlan& P, int id) {     // diagn
     }
 }
 constexpr int VISIT_MAXTHREADS = 256;
-// MVN evaluations are one long dependent DADD chain each (3 d^2 operations, one accumulator, mvn_pdf.f90:74-80): they need
-// many resident warps, not registers -> 256 threads x 4 CTAs per SM (64 registers); the other integrands keep 128 registers.
+// MVN evaluations are one long dependent DADD chain each (3 d^2 operations, one accumulator, mvn_pdf.f90:74-80): what
+// hides the FP64 latency (~60 cycles per dependent DADD, measured) is resident warps, not registers -> 64 registers per
+// thread.  (Measured on config E: the register-resident eval_mvn_reg makes one evaluation 2.3x faster, 133 us instead of
+// 300 us, but needs 255 registers = one CTA per SM, and 63 clusters then run in four waves instead of two: 86 ms
+// instead of 59 ms.  It is used where a single evaluation is the critical path: the corner fibers of the exchange.)
 template <int KIND>
 __global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_visits(DevPlan P, int dir, double small_element, double small_pivot, int fold_allreduce, int close_maxrank) {
     tl_stamp(P, 40);
