@@ -10,8 +10,11 @@
 //  ships no golden vectors for them and cannot be compiled in the build
 //  container (no Fortran, MPI, BLAS).  The oracle is pinned only by the
 //  reference's analytic integral values (test_crs_ising.f90:71-100,
-//  test_crs_stdnorm.f90:83, test_crs_mvn.f90:83) and by brute-force tensor
-//  checks in tests/.
+//  test_crs_stdnorm.f90:83, test_crs_mvn.f90:83), by the one known-answer table
+//  the reference ships (get_reference_val, test_crs_chf.f90:232-271: 32 complex
+//  characteristic-function values of the MVN cross + ztt_quad pipeline at DIM = 4,
+//  reproduced to < 8e-5 absolute = the table's own resolution, tests/test_chf.py)
+//  and by brute-force tensor checks in tests/.
 //
 //  What is restated (reference file:line):
 //    dtt_dmrgg        lib/dmrgg.f90:11-1050      (main routine)
