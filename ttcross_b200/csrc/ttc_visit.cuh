@@ -26,9 +26,12 @@ namespace cg = cooperative_groups;
 constexpr int MAXCS = 16;     // largest cluster the hardware allows (non-portable size)
 
 struct VisitShared {
-    Partial xpart[2][2][MAXCS];   // [phase parity][raw|res][CTA rank]; only CTA 0's copy is used
-    Partial red[2];
+    Partial xres[2][MAXCS];       // [fold parity][CTA rank]: every CTA receives every CTA's residual partial (pushed)
+    double xraw[2][MAXCS];        // same for the largest |f|
+    Partial red;
+    double redraw;
     Partial shp[32];
+    double shr[32];
     int nz[2];
     VState S;
     int r0, r1, r2;
@@ -152,30 +155,46 @@ __device__ __forceinline__ void stage_lual_cg(const double* g, int r, double* T,
     for (int c = threadIdx.x; c < r; c += blockDim.x) dinv[c] = 1.0 / LDF(g + (i64)(c + 1) * (c + 1) - 1);
 }
 
-// first-index argmax over the whole cluster; every thread of every CTA returns with the folded (raw, res).
-// One cluster barrier per call: the exchange area is double-buffered by call parity.
-__device__ __forceinline__ void cluster_fold(cg::cluster_group& cl, VisitShared& sh, int& phase, Partial& raw, Partial& res) {
-    raw = amax_block(raw, sh.shp);
-    res = amax_block(res, sh.shp);
+// Fold over the whole cluster: the first-index argmax of the residuals (idamax) and the largest |f| (only its magnitude
+// is used: amax).  Every thread of every CTA returns with the folded values.  Each CTA PUSHES its partial into every
+// CTA's shared memory before the one cluster barrier of the call, so nobody reads remote memory after it; the exchange
+// area is double-buffered by call parity (a CTA two folds ahead would have had to pass the barrier in between).
+__device__ __forceinline__ void cluster_fold(cg::cluster_group& cl, VisitShared& sh, int& phase, double& rawmax, Partial& res) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    res = amax_warp(res);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rawmax = fmax(rawmax, __shfl_down_sync(FULLMASK, rawmax, o));
+    if (lane == 0) { sh.shp[w] = res; sh.shr[w] = rawmax; }
+    __syncthreads();
     const int buf = phase & 1;
     ++phase;
-    const int cs = (int)cl.num_blocks();
-    VisitShared* lead = cl.map_shared_rank(&sh, 0);
-    if (threadIdx.x == 0) {
-        lead->xpart[buf][0][cl.block_rank()] = raw;
-        lead->xpart[buf][1][cl.block_rank()] = res;
-    }
-    cl.sync();                  // barrier.cluster arrive.release / wait.acquire: the fiber stores above are visible to the cluster
-    if (threadIdx.x < 32) {
-        Partial a = amax_init(), b = amax_init();
-        if ((int)threadIdx.x < cs) { a = lead->xpart[buf][0][threadIdx.x]; b = lead->xpart[buf][1][threadIdx.x]; }
+    const int cs = (int)cl.num_blocks(), me = (int)cl.block_rank();
+    if (w == 0) {
+        Partial a = (lane < nw) ? sh.shp[lane] : amax_init();
+        double r = (lane < nw) ? sh.shr[lane] : -1.0;
         a = amax_warp(a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_down_sync(FULLMASK, r, o));
+        a.absv = __shfl_sync(FULLMASK, a.absv, 0); a.val = __shfl_sync(FULLMASK, a.val, 0); a.idx = __shfl_sync(FULLMASK, a.idx, 0);
+        r = __shfl_sync(FULLMASK, r, 0);
+        if (lane < cs) {
+            VisitShared* dst = cl.map_shared_rank(&sh, lane);
+            dst->xres[buf][me] = a;
+            dst->xraw[buf][me] = r;
+        }
+    }
+    cl.sync();                  // barrier.cluster arrive.release / wait.acquire: the pushes and the fiber stores are visible
+    if (w == 0) {
+        Partial b = (lane < cs) ? sh.xres[buf][lane] : amax_init();
+        double r = (lane < cs) ? sh.xraw[buf][lane] : -1.0;
         b = amax_warp(b);
-        if (threadIdx.x == 0) { sh.red[0] = a; sh.red[1] = b; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_down_sync(FULLMASK, r, o));
+        if (lane == 0) { sh.red = b; sh.redraw = r; }
     }
     __syncthreads();
-    raw = sh.red[0];
-    res = sh.red[1];
+    res = sh.red;
+    rawmax = sh.redraw;
 }
 
 // ----------------------------------------------------------------------------
@@ -395,7 +414,8 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_
             lot_zeros2(vip_p, r1, r0, n2, tmp, zc, zr, sh.nz);
             tl_mark(P, 42);
             const unsigned long long k0 = sh.S.rng_k, seed = P.ctrl->seed;
-            Partial braw = amax_init(), bres = amax_init();
+            Partial bres = amax_init();
+            double braw = -1.0;                  // largest |f| (NaN never wins: fmax drops it, like the strict '>' of idamax)
             // a lane pair shares one candidate: the even lane draws its column cell, the odd lane its row cell (the two
             // bisections are the long serial part of a candidate), then the even lane evaluates
             for (int x0 = 0; x0 < nlot; x0 += gthreads / 2) {
@@ -414,15 +434,15 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_
                 StagedVals sv = S.point(i, j, k, q);
                 const double f = eval_point<KIND>(P, sv, A);
                 const double res = resid_ddot2_cg(f, colp + (i - 1) + (i64)P.Rmax * (j - 1), cs_, rowp + (k - 1) + (i64)n2 * (q - 1), rs_, r1);
-                amax_take(braw, f, x);
+                braw = fmax(braw, fabs(f));
                 amax_take(bres, res, x);
             }
- tl_mark(P, 43);
+            tl_mark(P, 43);
             cluster_fold(cl, sh, phase, braw, bres);
             tl_mark(P, 44);
             if (threadIdx.x == 0) {
                 VState& St = sh.S;
-                St.amax = fmax(St.amax, braw.absv);
+                St.amax = fmax(St.amax, braw);
                 const int x = (int)bres.idx;         // the winner's cell is a pure function of its draw number
                 const double uc = stream_uniform(seed, v, k0 + (unsigned long long)x);
                 const double ur = stream_uniform(seed, v, k0 + (unsigned long long)(nlot + x));
@@ -451,7 +471,8 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_
             const int count = isrow ? rcount : ccount;
             double* fa = isrow ? fa_r : fa_c;
             double* fb = isrow ? fb_r : fb_c;
-            Partial braw = amax_init(), bres = amax_init();
+            Partial bres = amax_init();
+            double braw = -1.0;
             for (int e = gtid; e < count; e += gthreads) {
                 double f, res;
                 Pref pf;
@@ -472,7 +493,7 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_
                 }
                 fa[e] = f;
                 fb[e] = res;
-                amax_take(braw, f, e);
+                braw = fmax(braw, fabs(f));
                 amax_take(bres, res, e);
             }
             tl_mark(P, 45);
@@ -485,7 +506,7 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_
                     St.havecol = 1; St.haverow = 1;
                     if (c == 1) St.done = 1;
                 } else {
-                    St.amax = fmax(St.amax, braw.absv);
+                    St.amax = fmax(St.amax, braw);
                     if (isrow) St.haverow = 1; else St.havecol = 1;
                     St.crs += 1;
                     int done = St.havecol && St.haverow && (St.crs >= 2 * P.piv);
