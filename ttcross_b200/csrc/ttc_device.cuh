@@ -671,9 +671,12 @@ __host__ __device__ __noinline__ int lot_draw_fast(int scol, int m, const int* z
     if (lo > scol) lo = scol;
     while (lo < scol && !lot_lt(y, lo, delta)) ++lo;
     while (lo > 1 && lot_lt(y, lo - 1, delta)) --lo;
-    int sidx = lo;
-    for (int z = 0; z < nz; ++z) { if (zeros[z] <= sidx) ++sidx; else break; }
-    return sidx;
+    // the lo-th cell of non-zero weight = lo + (number of zero cells before it).  Walking the sorted distinct zeros
+    // (`if (zeros[z] <= sidx) ++sidx; else break;`) takes zero z exactly when zeros[z] - z <= lo, and zeros[z] - z never
+    // decreases, so the walk equals this count -- with independent loads instead of a dependent chain.
+    int k = 0;
+    for (int z = 0; z < nz; ++z) k += (zeros[z] - z <= lo) ? 1 : 0;
+    return lo + k;
 }
 // sorted distinct zero-weight cells (1-based) of one side of bond p; thread-parallel rank sort over the r1 pivots.
 // tmp, zeros: shared int[>= r1]; *nz: shared int.  side 0: (i,j) with stride r0; side 1: (k,q) with stride n2.

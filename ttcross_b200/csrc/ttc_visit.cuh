@@ -414,6 +414,7 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_
             lot_zeros2(vip_p, r1, r0, n2, tmp, zc, zr, sh.nz);
             tl_mark(P, 42);
             const unsigned long long k0 = sh.S.rng_k, seed = P.ctrl->seed;
+            const bool packed = m < (1 << 20) && n < (1 << 20) && nlot < (1 << 22);
             Partial bres = amax_init();
             double braw = -1.0;                  // largest |f| (NaN never wins: fmax drops it, like the strict '>' of idamax)
             // a lane pair shares one candidate: the even lane draws its column cell, the odd lane its row cell (the two
@@ -428,14 +429,18 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_
                     cell = side ? lot_draw_fast(n - sh.nz[1], n, zr, sh.nz[1], uu) : lot_draw_fast(m - sh.nz[0], m, zc, sh.nz[0], uu);
                 }
                 const int w = __shfl_down_sync(FULLMASK, cell, 1);
+                tl_mark(P, 55);
                 if (!live || side) continue;
                 const int c = cell;
                 const int i = (c - 1) % r0 + 1, j = (c - 1) / r0 + 1, k = (w - 1) % n2 + 1, q = (w - 1) / n2 + 1;
                 StagedVals sv = S.point(i, j, k, q);
                 const double f = eval_point<KIND>(P, sv, A);
+                tl_mark(P, 56);
                 const double res = resid_ddot2_cg(f, colp + (i - 1) + (i64)P.Rmax * (j - 1), cs_, rowp + (k - 1) + (i64)n2 * (q - 1), rs_, r1);
                 braw = fmax(braw, fabs(f));
-                amax_take(bres, res, x);
+                // the winner's cells ride along below the draw number (the draw number stays the major key of the
+                // first-index tie-break), so nobody has to redraw them after the fold
+                amax_take(bres, res, packed ? (((i64)x << 40) | ((i64)c << 20) | (i64)w) : (i64)x);
             }
             tl_mark(P, 43);
             cluster_fold(cl, sh, phase, braw, bres);
@@ -443,11 +448,15 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_
             if (threadIdx.x == 0) {
                 VState& St = sh.S;
                 St.amax = fmax(St.amax, braw);
-                const int x = (int)bres.idx;         // the winner's cell is a pure function of its draw number
-                const double uc = stream_uniform(seed, v, k0 + (unsigned long long)x);
-                const double ur = stream_uniform(seed, v, k0 + (unsigned long long)(nlot + x));
-                const int c = lot_draw_fast(m - sh.nz[0], m, zc, sh.nz[0], uc);
-                const int w = lot_draw_fast(n - sh.nz[1], n, zr, sh.nz[1], ur);
+                int c, w;
+                if (packed) { c = (int)((bres.idx >> 20) & 0xfffff); w = (int)(bres.idx & 0xfffff); }
+                else {                               // the winner's cell is a pure function of its draw number
+                    const int x = (int)bres.idx;
+                    const double uc = stream_uniform(seed, v, k0 + (unsigned long long)x);
+                    const double ur = stream_uniform(seed, v, k0 + (unsigned long long)(nlot + x));
+                    c = lot_draw_fast(m - sh.nz[0], m, zc, sh.nz[0], uc);
+                    w = lot_draw_fast(n - sh.nz[1], n, zr, sh.nz[1], ur);
+                }
                 St.ii = (c - 1) % r0 + 1; St.jj = (c - 1) / r0 + 1; St.kk = (w - 1) % n2 + 1; St.qq = (w - 1) / n2 + 1;
                 St.pivot = bres.val;
                 St.done = 0; St.havecol = 0; St.haverow = 0; St.crs = 0; St.upd = 0;
