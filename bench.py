@@ -39,42 +39,55 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region."""
+    """nvidia-smi clocks + throttle reasons of ONE GPU, polled every 50 ms from before the warm-up until after the timed
+    regions; stop() keeps the samples whose host time stamp falls inside the timed regions."""
 
-    def __init__(self):
+    def __init__(self, gpu_index=0):
         self.rows = []
         self.proc = None
+        self.gpu = gpu_index
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "--query-gpu=index,clocks.sm,clocks.max.sm,clocks_event_reasons.active,"
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=index,clocks.sm,clocks.max.sm,clocks_event_reasons.active,"
                  "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
                  "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self, gpu_index=0):
+    def wait_first(self, timeout=5.0):
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
-        rows = [r for r in self.rows if len(r) >= 8 and r[0] == str(gpu_index)]
+        rows = [(ts, r) for ts, r in self.rows if len(r) >= 8]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[1]) for r in rows)
+        inside = [r for ts, r in rows if t_begin is not None and t_begin - 0.05 <= ts <= t_end + 0.05]
+        window = "timed regions"
+        if not inside:                       # (a timed region shorter than the polling period: take the neighbours)
+            inside = [r for ts, r in rows]
+            window = "whole run (no sample fell inside the timed regions)"
+        sm = sorted(float(r[1]) for r in inside)
         reasons = set()
-        for r in rows:
+        for r in inside:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons), "samples": len(rows)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(inside[0][2]), "reasons": sorted(reasons), "samples": len(inside),
+                "window": window}
 
 
 def reference_arm(args):
@@ -155,12 +168,16 @@ def main():
         # the P = 8 core blocks are mapped block-wise onto the N ranks; the library's own NCCL communicator carries the
         # per-sweep exchange (pivot tape + boundary fibers + quadrature chains); torch.distributed only hands over its id
         T.multi.attach(t, dist)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                    # polling runs from before the warm-up: nvidia-smi needs a moment to start
     for _ in range(max(args.warmup, 3)):
         g = t.dmrgg(R, prob.accuracy, piv)
+    if rank == 0:
+        sampler.wait_first()
     launches0 = t.launch_count()
-    sampler = ClockSampler()
-    sampler.start()
     barrier()
+    t_timed_begin = time.perf_counter()
     dev_ms = []
     wall0 = time.perf_counter()
     for _ in range(args.steps):
@@ -220,7 +237,7 @@ def main():
         d2h = int(y[1].item())                           # all ranks' copies
         h2d *= world
     e2e_val = g.neval / e2e_mean
-    clocks = sampler.stop(local_rank)
+    clocks = sampler.stop(t_timed_begin, time.perf_counter()) if rank == 0 else None
 
     # ---- roofline of the dominant kernel: per-class device times from a profiled pass (events around every launch)
     t.set_profile(True)                                  # collective like every ttc_dmrgg call when world > 1
