@@ -219,7 +219,7 @@ contains
         real(c_double), allocatable :: wre(:), wim(:), ore(:), oim(:)
         if (.not. c_associated(handle)) then; write (*, *) 'ztt_quad_cuda: no cross has been computed'; stop; end if
         allocate (wre(size(w)), wim(size(w)), ore(nsets), oim(nsets))
-        wre = reshape(dble(w), [size(w)]); wim = reshape(dimag(w), [size(w)])
+        wre = reshape(dble(w), [size(w)]); wim = reshape(aimag(w), [size(w)])
         call check(ttc_quad_complex(handle, int(nsets, c_int), wre, wim, ore, oim), 'ztt_quad')
         ans = dcmplx(ore, oim)
     end subroutine
