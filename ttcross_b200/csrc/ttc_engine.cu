@@ -1096,7 +1096,6 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     // boundaries and a 12k-flop integrand is better off with the separate corner kernel).  TTC_FUSED_SWEEP=0 disables.
     bool fused = use_cluster && !multi && h->use_wave && (P == 1 || (h->xf_ok && cdiv(2 * h->nmax, 8) * (P - 1) <= 4 * h->nsm));
     if (const char* e = std::getenv("TTC_FUSED_SWEEP")) fused = fused && std::atoi(e) != 0;
-    if (const char* e = std::getenv("TTC_FUSED_SWEEP")) fused = fused && std::atoi(e) != 0;
     const int eff_maxrank = maxrank > 0 ? maxrank : Rmax;        // no maxrank: the rank capacity ends the run
     auto enqueue_sweep = [&](int dir, int rb) -> int {
         if (sync_mode) h->rks_h = h->rk_h;
