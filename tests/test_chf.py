@@ -94,3 +94,25 @@ def test_chf_program_prints_reference_layout(tmp_path):
     assert np.abs(got - _table()).max() < TOL
     digits = [float(x) for x in re.findall(r"correct digits:\s*(\S+)", out)]
     assert len(digits) == 32 and min(digits[:6]) > 4.0               # the leading frequencies carry >4 digits of the table
+
+
+@pytest.mark.gpu
+def test_pdf_program_writes_the_cos_density(tmp_path):
+    """test_crs_pdf.f90: chf pipeline + cos_approximate_array on 200 points of [0, 300], two es25.17 columns."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "ttcross_b200", "programs")])
+    out = tmp_path / "pdf.txt"
+    env = dict(os.environ, TTC_PDF_OUT=str(out), TTC_SEED="1", TTC_QUIET="1")
+    r = subprocess.run([os.path.join(ROOT, "ttcross_b200", "programs", "bin", "test_crs_pdf"), "4", "64", "20", "1"],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "Phi values computed." in r.stdout and "Writing PDF output to:" in r.stdout, r.stdout + r.stderr
+    rows = np.loadtxt(out)
+    assert rows.shape == (200, 2) and rows[0, 0] == 0.0 and rows[-1, 0] == 300.0
+    # the same pipeline through the Python mirror
+    p = T.drivers.mvn(4, 64)
+    t = p.make(use_quad=False, use_tru=False); t.set_seed(1)
+    t.dmrgg(20, p.accuracy, 1)
+    phis = t.quad_complex(T.drivers.chf_weights(p))
+    want = T.drivers.cos_approximate(rows[:, 0], phis, 0.0, 300.0, n_terms=32)
+    np.testing.assert_allclose(rows[:, 1], want, rtol=1e-9, atol=1e-13)
+    dx = rows[1, 0] - rows[0, 0]
+    assert abs(float(np.sum(0.5 * (rows[1:, 1] + rows[:-1, 1])) * dx) - 1.0) < 1e-4      # a density

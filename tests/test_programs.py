@@ -22,7 +22,7 @@ def _build():
 def test_programs_build_and_fail_loudly_without_gpu(has_gpu):
     T.load_library()
     _build()
-    for prog in ("test_crs_ising", "test_crs_mvn", "test_crs_stdnorm", "test_crs_chf"):
+    for prog in ("test_crs_ising", "test_crs_mvn", "test_crs_stdnorm", "test_crs_chf", "test_crs_pdf"):
         assert os.access(os.path.join(BIN, prog), os.X_OK)
     if not has_gpu:
         r = subprocess.run([os.path.join(BIN, "test_crs_ising"), "c", "4", "8", "4", "1"], capture_output=True, text=True, timeout=120)

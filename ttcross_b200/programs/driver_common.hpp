@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <chrono>
+#include <complex>
 
 #include "../../include/ttcross_b200.h"
 
@@ -120,6 +121,23 @@ inline std::vector<double> mvn_aux(int d, double rr, double T) {
     aux.insert(aux.end(), inv.begin(), inv.end());
     aux.push_back(std::sqrt(powi(2.0 * 3.141592653589793, d) * det));
     return aux;
+}
+
+// cos_approximate_array (lib/cos_approx.f90:90-127): pdf(x) = sum_k' coeff_k cos(omega_k (x - a)), omega_k = k pi / (b - a),
+// coeff_k = 2 / (b - a) Re(phi_k exp(-i omega_k a)), the k = 0 term halved; n_terms > size(phis) prints the reference's
+// error line and returns zeros (:107-111)
+inline void cos_approximate_array(const std::vector<double>& xs, const std::vector<std::complex<double>>& phis, double lower_bound,
+                                  double upper_bound, int n_terms, std::vector<double>& pdf_vals) {
+    pdf_vals.assign(xs.size(), 0.0);
+    if (n_terms > (int)phis.size()) { std::printf(" Error: n_terms exceeds the size of phis.\n"); return; }
+    const double pi = 3.1415926535897932384626433832795;
+    const double pi_over_bound = pi / (upper_bound - lower_bound);
+    for (int k = 0; k < n_terms; ++k) {
+        const double omega = k * pi_over_bound;
+        double coeff = 2.0 / (upper_bound - lower_bound) * (phis[k] * std::exp(-1.0 * std::complex<double>(0.0, 1.0) * omega * lower_bound)).real();
+        if (k == 0) coeff = coeff / 2.0;
+        for (size_t i = 0; i < xs.size(); ++i) pdf_vals[i] = pdf_vals[i] + coeff * std::cos(omega * (xs[i] - lower_bound));
+    }
 }
 
 }  // namespace drv
