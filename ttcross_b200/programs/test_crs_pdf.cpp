@@ -2,7 +2,8 @@
 // without quad/tru, :128-129; 32 complex quadratures, :153-168 -- one batched ttc_quad_complex launch here), then the COS
 // series of the density of mean_j exp(X_j) on 200 points of [0, 300] (cos_approximate_array, lib/cos_approx.f90:90-127)
 // written as two es25.17 columns (:186-199).  Output file: ./out/tt-cross-pdf.txt like the reference, or $TTC_PDF_OUT.
-// The reference then shells out to its matplotlib scripts (:206-214); this twin stops at the file.
+// The reference then shells out to its matplotlib scripts (:206-214); this twin stops at the file.  With $TTC_TT_OUT set it
+// also stores the train like test_crs_store.f90:136 does (in the reference's TT stream format instead of HDF5).
 #include "driver_common.hpp"
 #include <complex>
 
@@ -49,6 +50,11 @@ int main(int argc, char** argv) {
     }
     st = ttc_quad_complex(h, K, wre.data(), wim.data(), ore.data(), oim.data());
     if (st) drv::die(h, st, "ttc_quad_complex");
+    if (const char* tt_out = std::getenv("TTC_TT_OUT")) {      // test_crs_store.f90:136 saves the train (HDF5 there; the TT stream
+        st = ttc_write(h, tt_out);                              // format of lib/ttio.f90 here -- no HDF5 library in this build)
+        if (st) drv::die(h, st, "ttc_write");
+        std::printf("   Train written to: %s\n", tt_out);
+    }
     ttc_destroy(h);
     std::printf("   Phi values computed.\n");
     std::vector<std::complex<double>> phis(K);
