@@ -154,3 +154,18 @@ def test_closed_form_lottery_matches_literal_loop():
         assert L.ttc_lottery_fast(m, zeros.ctypes.data_as(C.POINTER(C.c_int)), nz, u.ctypes.data_as(C.POINTER(C.c_double)),
                                   cnt, cells2.ctypes.data_as(C.POINTER(C.c_int))) == 0
         assert np.array_equal(pts[:cnt], cells2), f"trial {trial} (fast rule): m={m} nz={nz}"
+
+
+def test_ragged_mode_sizes_are_rejected_for_the_ising_family():
+    """type(dtt) carries one mode size per core (tt.f90:18-26) but the drivers always use one quadrature for all modes; the
+    Ising integrand here is built on that (weights live at par[n(1) + ind]): unequal sizes are an argument error with a
+    message, not a silent misread.  (The nodes-only integrands accept them.)  No GPU needed: ttc_create validates first."""
+    import numpy as np
+    import pytest
+    import ttcross_b200 as T
+    p = T.drivers.ising("c", 7, 16)
+    p.n = np.array([17, 12, 17, 10, 14, 17], dtype=np.int32)
+    p.quad = np.full(int(p.n.sum()), p.quad[0])
+    with pytest.raises(T.api.TTCrossError) as e:
+        p.make()
+    assert "equal mode sizes" in str(e.value)

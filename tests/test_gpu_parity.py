@@ -187,3 +187,4 @@ def test_no_quadrature_run_with_partitions():
     p = T.drivers.ising("c", 8, 24)
     t, g, o = run_both(p, 10, 2, P=4, use_quad=False, use_tru=False)
     assert_parity(t, g, o, exact=True)
+
