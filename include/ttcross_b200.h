@@ -75,6 +75,15 @@ int ttc_set_uniform_callback(ttc_handle* h, ttc_uniform_cb cb, void* ctx);
  * that runs a virtual rank's whole visit list.  All modes produce identical results; modes 1-4 exist to prove that. */
 int ttc_set_lottery_mode(ttc_handle* h, int mode);
 int ttc_set_verbose(ttc_handle* h, int verbose);                    /* 1: print the reference's per-sweep lines on stdout */
+/* exp of the exp-based integrands (stdnorm: test_crs_stdnorm.f90:168, MVN: lib/mvn_pdf.f90:81).  0 (default): the platform's
+ * exp, like the reference's libm call.  1: the deterministic + - * routine of include/ttc_detexp.h ("parity mode"): the CPU
+ * oracle has the same switch, and with it GPU and CPU runs of these integrands agree bit for bit (CUDA's and glibc's exp
+ * differ in the last ulp, which decides near-tied pivots of symmetric integrands). */
+int ttc_set_exp_mode(ttc_handle* h, int mode);
+/* 1 if the last ttc_dmrgg ended on its accuracy criterion (three consecutive sweeps with pivotmax <= accuracy * amax,
+ * dmrgg.f90:1013-1017), 0 if it ended on the rank bound: maxrank when given, else the capacity of 64 that stands in for
+ * "no maxrank" (the reference would keep growing; here the run stops and this flag says it did not converge). */
+int ttc_converged(const ttc_handle* h);
 
 /* ---- the sweep: dtt_dmrgg (lib/dmrgg.f90:11) -------------------------------
  *   maxrank   <= 0 : absent          accuracy  < 0 : absent

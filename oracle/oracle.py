@@ -86,6 +86,7 @@ def lib():
         L.tto_fmt_e.argtypes = [C.c_double, C.c_int, C.c_int, C.c_char_p]
         L.tto_num_threads.restype = C.c_int
         L.tto_set_num_threads.argtypes = [C.c_int]
+        L.tto_set_exp_mode.argtypes = [C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -292,6 +293,10 @@ class Oracle:
                 self.h = None
         except Exception:
             pass
+
+    def set_exp_mode(self, mode: int):
+        """1: exp through include/ttc_detexp.h, the deterministic routine the product uses in its parity mode."""
+        lib().tto_set_exp_mode(self.h, mode)
 
     def integrand(self, ind) -> float:
         a = np.ascontiguousarray(ind, dtype=np.int32)

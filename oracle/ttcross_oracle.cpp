@@ -56,6 +56,7 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#include "../include/ttc_detexp.h"   // the deterministic exp both sides use in parity mode (a product header; the product never includes oracle/)
 
 namespace {
 
@@ -211,7 +212,9 @@ struct Problem {
     std::vector<int> n;         // n[0..d-1]
     std::vector<double> par;
     std::vector<double> aux;    // MVN: mu(d) | inv_cov(d,d) column-major | denom
+    int exp_mode = 0;           // 1: exp through include/ttc_detexp.h (parity mode; the product has the same switch)
 };
+inline double prob_exp(int mode, double x) { return mode ? ttc_det_exp(x) : std::exp(x); }
 
 // test_crs_ising.f90:176-218
 double f_ising(int m, const int* ind, const int* n, const double* par) {
@@ -250,20 +253,20 @@ double f_ising(int m, const int* ind, const int* n, const double* par) {
     return f;
 }
 // test_crs_stdnorm.f90:154-170
-double f_stdnorm(int m, const int* ind, const int*, const double* par) {
+double f_stdnorm(int m, const int* ind, const int*, const double* par, int exp_mode) {
     double s = 0.0;
     for (int i = 0; i < m; ++i) { double x = par[ind[i] - 1]; s = s + x * x; }
-    return std::exp(-s);
+    return prob_exp(exp_mode, -s);
 }
 // lib/mvn_pdf.f90:63-83 through test_crs_mvn.f90:156-172
-double f_mvn(int m, const int* ind, const int*, const double* par, const double* aux) {
+double f_mvn(int m, const int* ind, const int*, const double* par, const double* aux, int exp_mode) {
     const double* mu = aux; const double* A = aux + m; double denom = aux[m + (i64)m * m];
     std::vector<double> diff(m);
     for (int i = 0; i < m; ++i) diff[i] = par[ind[i] - 1] - mu[i];
     double e = 0.0;
     for (int i = 0; i < m; ++i)
         for (int j = 0; j < m; ++j) e = e + diff[i] * A[i + (i64)j * m] * diff[j];
-    return std::exp(-0.5 * e) / denom;
+    return prob_exp(exp_mode, -0.5 * e) / denom;
 }
 // lib/coefficients.f90:33-65 (calc_coefficient) with lib/funcs.f90:8-26 (gaussian_chf_nd) and lib/s_vectors.f90:7-29.
 // aux = mu(d) | sigma(d,d) column-major | lower | upper.  x**n: libgcc __powidf2; matmul(sigma, t): column by column from 0;
@@ -305,8 +308,8 @@ double fun(const Problem& P, const int* ind) {
     switch (P.kind) {
         case 6: return f_coscoef(P.d, ind, P.aux.data());
         case ISING: return f_ising(P.d, ind, P.n.data(), P.par.data());
-        case STDNORM: return f_stdnorm(P.d, ind, P.n.data(), P.par.data());
-        case MVN: return f_mvn(P.d, ind, P.n.data(), P.par.data(), P.aux.data());
+        case STDNORM: return f_stdnorm(P.d, ind, P.n.data(), P.par.data(), P.exp_mode);
+        case MVN: return f_mvn(P.d, ind, P.n.data(), P.par.data(), P.aux.data(), P.exp_mode);
     }
     std::abort();
 }
@@ -1066,6 +1069,7 @@ void* tto_create(int kind, int d, const int* n, const double* par, long npar, co
     return O;
 }
 void tto_destroy(void* h) { delete (Oracle*)h; }
+void tto_set_exp_mode(void* h, int mode) { ((Oracle*)h)->prob.exp_mode = mode; }
 
 // quad: concatenated weight vectors sum(n) doubles, or NULL.  own: P+1 ints or NULL.
 int tto_run(void* h, int maxrank, double accuracy, int piv, int P, const int* own, const double* quad,

@@ -22,13 +22,14 @@ for k,v in sorted(agg.items(), key=lambda kv:-sum(kv[1])): print(f"{k:24s} n={le
 # one late sweep in detail
 names=[a for a,_ in tl]
 idx=[i for i,a in enumerate(names) if a=='k_visits']
+if len(idx) < 3: idx=[i for i,a in enumerate(names) if a=='v:staged']     # persistent kernel: one launch, sweeps start at 'v:staged'
 i0,i1=idx[-3],idx[-2]
 t0=tl[i0][1]
 ck=t.timeline_clocks
 prev=None
 for a,ta in tl[i0:i1+1]:
     extra=''
-    if prev is not None and a.startswith(('v:','f:','q:')) and prev[0].startswith(('v:','f:','q:','k_visits','k_quad_inc')):
+    if prev is not None and a.startswith(('v:','f:','q:','s:','l:')) and prev[0].startswith(('v:','f:','q:','s:','l:','k_visits','k_quad_inc')):
         dc=ck[ta]-ck[prev[1]]; dt=ta-prev[1]
         if dt>0 and 0<dc<10**7: extra=f"  dcycles={dc} -> {dc/dt*1e3:.0f} MHz"
     print(f"  {(ta-t0)/1e3:8.2f} us  {a}{extra}")

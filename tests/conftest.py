@@ -30,3 +30,14 @@ def _has_gpu() -> bool:
 @pytest.fixture(scope="session")
 def has_gpu():
     return _has_gpu()
+
+
+def pytest_collection_modifyitems(config, items):
+    """Without a CUDA device the `gpu` tests cannot run (the product has no CPU fallback): skip them instead of reporting
+    a hundred TTC_ERR_CUDA failures that would bury a real CPU-side regression."""
+    if _has_gpu():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

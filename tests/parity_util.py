@@ -12,13 +12,16 @@ def to_oracle_setup(p: "T.drivers.Problem") -> "O.Setup":
     return O.Setup(p.kind, p.d, p.n, p.par, p.aux, p.quad, p.accuracy, p.tru, p.label)
 
 
-def run_both(p, maxrank, piv, P=1, own=None, seed=1, accuracy=None, use_quad=True, use_tru=True):
+def run_both(p, maxrank, piv, P=1, own=None, seed=1, accuracy=None, use_quad=True, use_tru=True, exp_mode=0):
     acc = p.accuracy if accuracy is None else accuracy
     t = p.make(use_quad=use_quad, use_tru=use_tru)
     t.set_partition(P, own)
     t.set_seed(seed)
+    t.set_exp_mode(exp_mode)          # 1: both sides evaluate exp through include/ttc_detexp.h (parity mode)
     g = t.dmrgg(maxrank, acc, piv)
-    o = O.Oracle(to_oracle_setup(p)).run(maxrank=maxrank, piv=piv, P=P, own=own, accuracy=acc, use_quad=use_quad,
+    orc = O.Oracle(to_oracle_setup(p))
+    orc.set_exp_mode(exp_mode)
+    o = orc.run(maxrank=maxrank, piv=piv, P=P, own=own, accuracy=acc, use_quad=use_quad,
                                          use_tru=use_tru, seed=seed)
     return t, g, o
 

@@ -58,6 +58,30 @@ def test_mvn_config_E_full_size(P):
     assert np.array_equal(g.pivlog, g2.pivlog) and np.array_equal(g.pivots, g2.pivots) and np.array_equal(g.vals, g2.vals)
 
 
+@pytest.mark.parametrize("P", [8, 63])
+def test_mvn_config_E_parity_mode_bit_exact(P):
+    """Config E with the SAME exp on both sides (ttc_set_exp_mode(1) / the oracle's switch: the + - * routine of
+    include/ttc_detexp.h): pivot tape, ranks, neval, per-sweep values, final integral and every core are bit-identical to
+    the end of the run.  This is the proof that the divergences of the default mode (test above) come from the last ulp
+    of the platform exp and from nothing else in the arithmetic of lib/mvn_pdf.f90:63-83 or of the sweep."""
+    p = T.drivers.mvn(64, 128)
+    t, g, o = run_both(p, 32, 1, P=P, exp_mode=1)
+    assert_parity(t, g, o, exact=True)
+
+
+@pytest.mark.parametrize("d,n,R,P", [(8, 32, 10, 1), (12, 24, 8, 3), (16, 16, 6, 5)])
+def test_mvn_parity_mode_bit_exact(d, n, R, P):
+    p = T.drivers.mvn(d, n)
+    t, g, o = run_both(p, R, 1, P=P, exp_mode=1)
+    assert_parity(t, g, o, exact=True)
+
+
+def test_stdnorm_parity_mode_bit_exact():
+    p = T.drivers.stdnorm(8, 33)
+    t, g, o = run_both(p, 8, 2, P=2, exp_mode=1)
+    assert_parity(t, g, o, exact=True)
+
+
 def _parity_or_documented_tie(g, o, rtol):
     """Identical tapes, or identical up to a record where the two sides chose different candidates whose residuals agree to
     1e-8 (a mathematical tie of the permutation-symmetric MVN decided by the last ulp of exp()); values compared up to there."""

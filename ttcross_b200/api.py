@@ -54,6 +54,8 @@ def load_library(build_if_missing: bool = True):
     L.ttc_set_verbose.argtypes = [vp, C.c_int]
     L.ttc_set_uniform_callback.argtypes = [vp, UNIFORM_CB, C.c_void_p]
     L.ttc_set_lottery_mode.argtypes = [vp, C.c_int]
+    L.ttc_set_exp_mode.argtypes = [vp, C.c_int]
+    L.ttc_converged.argtypes = [vp]
     L.ttc_set_profile.argtypes = [vp, C.c_int]
     L.ttc_dmrgg.argtypes = [vp, C.c_int, C.c_double, C.c_int]
     L.ttc_ranks.argtypes = [vp, _ip]
@@ -271,6 +273,14 @@ class TTCross:
     def set_lottery_mode(self, mode: int):
         self._check(self._L.ttc_set_lottery_mode(self.h, mode))
 
+    def set_exp_mode(self, mode: int):
+        """0: platform exp (default); 1: deterministic exp shared with the test oracle (parity mode)."""
+        self._check(self._L.ttc_set_exp_mode(self.h, mode))
+
+    @property
+    def converged(self) -> bool:
+        return bool(self._L.ttc_converged(self.h))
+
     def set_verbose(self, v: bool):
         self._check(self._L.ttc_set_verbose(self.h, int(v)))
 
@@ -437,7 +447,8 @@ class TTCross:
         special = {40: "k_visits", 100: "fold_done", 41: "v:staged", 42: "v:lot_setup", 43: "v:lot_eval", 44: "v:lot_fold",
                    45: "v:fiber_eval", 46: "v:fiber_fold", 47: "v:rook_done", 48: "v:nbr_done", 49: "v:append_done", 50: "f:xs_staged", 51: "f:pref_issued", 52: "f:eval_done",
                    53: "f:resid_done", 54: "f:stored", 55: "l:drawn", 56: "l:evaluated", 34: "k_quad_inc", 60: "q:lu_staged", 61: "q:chunk_staged", 62: "q:chunk_summed",
-                   63: "q:luar_done", 64: "q:end", 35: "k_superblock_t"}
+                   63: "q:luar_done", 64: "q:end", 35: "k_superblock_t", 36: "k_sweeps", 70: "s:announced", 71: "s:nbr_ready",
+                   72: "s:exchanged", 73: "s:all_ready", 74: "s:closed"}
         out = [(special.get(int(i), nm[i] if i < 64 else "?"), int(t)) for i, t in zip(ids[:n], ts[:n])]
         return sorted(out, key=lambda x: x[1])
 

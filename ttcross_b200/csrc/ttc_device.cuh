@@ -20,12 +20,14 @@
 #include <stdint.h>
 #include <string.h>
 #include <math.h>
+#include "../../include/ttc_detexp.h"
 
 namespace ttc {
 
 typedef long long i64;
 
-enum { KIND_ISING = 1, KIND_STDNORM = 4, KIND_MVN = 5, KIND_COSCOEF = 6 };
+enum { KIND_ISING = 1, KIND_STDNORM = 4, KIND_MVN = 5, KIND_COSCOEF = 6,
+       KIND_ISINGC = 7 };   // compile-time tag of the bond-visit kernels for Ising with id = 1 (P.kind stays KIND_ISING)
 constexpr int MAXD_LOCAL = 64;     // integrands gather node values into registers/local memory up to this d
 constexpr int GMAX = 1024;         // max CTAs per virtual rank in any reducing kernel
 
@@ -123,7 +125,11 @@ struct DevPlan {
     int* qext;             // [(d+1)][2] extents of ttqy/ttqq already computed
     // diagnostic timeline (ttc_set_timeline): every kernel stamps %globaltimer when its first CTA starts
     unsigned long long* tlog; int* tlog_n; int tlog_cap;
+    // persistent sweep kernel (ttc_sweep.cuh): one mailbox per partition (inside the peer window when there are several processes)
+    struct SweepMail* mail; long long win_mail;
+    int exp_mode;          // 0: platform exp; 1: the deterministic exp of include/ttc_detexp.h (parity mode, ttc_set_exp_mode)
 };
+__device__ __forceinline__ double plan_exp(const DevPlan& P, double x) { return P.exp_mode ? ttc_det_exp(x) : exp(x); }
 __device__ __forceinline__ void tl_stamp(const DevPlan& P, int id) {
     if (P.tlog && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
         unsigned long long t;
@@ -332,10 +338,10 @@ __device__ __noinline__ double eval_stdnorm(const DevPlan& P, const V& v) {
         double x[MAXD_LOCAL];
         v.gather(P.d, x, nullptr, false);
         for (int i = 0; i < P.d; ++i) sum = sum + x[i] * x[i];
-        return exp(-sum);
+        return plan_exp(P, -sum);
     }
     for (int i = 1; i <= P.d; ++i) { double x = v.x(i); sum = sum + x * x; }
-    return exp(-sum);
+    return plan_exp(P, -sum);
 }
 // lib/mvn_pdf.f90:63-83 (through test_crs_mvn.f90:156-172); A = inv_cov column-major, staged by the caller
 template <class V>
@@ -358,7 +364,7 @@ __device__ __noinline__ double eval_mvn(const DevPlan& P, const V& v, const doub
             for (int j = 0; j < m; ++j) e = e + di * A[i + (i64)j * m] * (v.x(j + 1) - mu[j]);
         }
     }
-    return exp(-0.5 * e) / denom;
+    return plan_exp(P, -0.5 * e) / denom;
 }
 
 // The same arithmetic with diff[] held in REGISTERS for the inner loop.  eval_mvn above keeps diff[] in local memory: at
@@ -392,7 +398,7 @@ __device__ __noinline__ double eval_mvn_reg(const DevPlan& P, const V& v, const 
             }
         }
     }
-    return exp(-0.5 * e) / denom;
+    return plan_exp(P, -0.5 * e) / denom;
 }
 template <class V>
 __device__ __forceinline__ double eval_mvn_fast(const DevPlan& P, const V& v, const double* A) {
@@ -462,7 +468,7 @@ __device__ __forceinline__ const double* stage_aux(const DevPlan& P, double* sme
 }
 template <int KIND, class V>
 __device__ __forceinline__ double eval_point(const DevPlan& P, const V& v, const double* A) {
-    if (KIND == KIND_ISING) return eval_ising(P, v);
+    if (KIND == KIND_ISING || KIND == KIND_ISINGC) return eval_ising(P, v);
     if (KIND == KIND_STDNORM) return eval_stdnorm(P, v);
     if (KIND == KIND_COSCOEF) return eval_coscoef(P, v);
     return eval_mvn(P, v, A);
@@ -2338,5 +2344,5 @@ __global__ void k_mp_unpack2(DevPlan P, int final) {
     }
 }
 
-static const char* const tl_names[] = {"k_lot", "k_fiber", "k_superblock", "k_accept", "k_update_main", "k_update_nbr", "k_allreduce", "k_run_begin", "k_sweep_log", "k_exchange_corner", "k_exchange_extend", "k_quad_contract", "k_quad_lua", "k_quad_chain", "k_quad_tree", "k_lua_r", "k_lua_l", "k_pack_core", "k_init_search", "k_init_cross", "k_quad_contract_sm", "k_quad_lua_sm", "k_quad_chain_sm", "k_quad_tree_sm", "k_update_nbr_w", "k_exchange_extend_w", "k_lua_r_w", "k_lua_l_w", "k_init_factors", "k_mp_pack1", "k_mp_unpack1", "k_mp_unpack1b", "k_mp_pack2", "k_mp_unpack2", "k_quad_inc"};
+static const char* const tl_names[] = {"k_lot", "k_fiber", "k_superblock", "k_accept", "k_update_main", "k_update_nbr", "k_allreduce", "k_run_begin", "k_sweep_log", "k_exchange_corner", "k_exchange_extend", "k_quad_contract", "k_quad_lua", "k_quad_chain", "k_quad_tree", "k_lua_r", "k_lua_l", "k_pack_core", "k_init_search", "k_init_cross", "k_quad_contract_sm", "k_quad_lua_sm", "k_quad_chain_sm", "k_quad_tree_sm", "k_update_nbr_w", "k_exchange_extend_w", "k_lua_r_w", "k_lua_l_w", "k_init_factors", "k_mp_pack1", "k_mp_unpack1", "k_mp_unpack1b", "k_mp_pack2", "k_mp_unpack2", "k_quad_inc", "k_sweeps"};
 }  // namespace ttc

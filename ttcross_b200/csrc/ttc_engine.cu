@@ -13,6 +13,7 @@
 #include "../../include/ttcross_b200.h"
 #include "ttc_device.cuh"
 #include "ttc_visit.cuh"
+#include "ttc_sweep.cuh"
 #include "ttc_superblock.cuh"
 #include "ttc_qr.cuh"
 #include "ttc_post.cuh"
@@ -107,6 +108,7 @@ struct ttc_handle {
     int P = 1; std::vector<int> own; bool own_given = false;
     u64 seed = 1; ttc_uniform_cb ucb = nullptr; void* ucb_ctx = nullptr;
     int verbose = 0, device = 0, profile = 0;
+    int alloc_device = -1;              // the device the current blocks / streams / windows live on (device may be changed between runs)
     std::string err;
 
     // run parameters / state
@@ -138,10 +140,14 @@ struct ttc_handle {
     size_t sm_contract = 0, sm_lua = 0, sm_mat3 = 0, sm_ext = 0, sm_lot = 0, sm_fiber = 0, sm_sb = 0;
     size_t sm_xf = 0; bool xf_ok = false;             // k_exchange_fused: aux | 2 d | two staged LU tables
     int force_sync = 0, force_host_lottery = 0, force_simple = 0, force_split = 0;
+    int exp_mode = 0;                   // 1: deterministic exp (include/ttc_detexp.h)
+    int converged = 0;                  // the last run ended on the accuracy criterion
     size_t sm_qinc = 0; int qinc_stage = 0;
     size_t sm_sbt = 0; bool sbt_ok = false;      // tiled superblock kernel (ttc_superblock.cuh)
     int cluster_size = 16, cluster_threads = 256;   // measured best on B200 (16 x 256 beats the portable 8 x 512 by 7 %)
     size_t sm_visit = 0; bool cluster_ok = false;
+    bool persist_ok = false;                       // the persistent sweep kernel (ttc_sweep.cuh) fits the device in one cooperative wave
+    double* chainS = nullptr;                      // [maxsweeps][P + 1][Rmax^2] chain products of the per-sweep quadrature after the loop
     int nsm = 148;
     // core blocks over processes (one per GPU): NCCL communicator of ttc_comm_init, this process's rank
     NcclComm comm = nullptr; int nproc = 1, prank = 0;
@@ -313,15 +319,18 @@ int window_setup(ttc_handle* h, size_t w1, size_t w2, size_t slab, size_t rowinv
 
 void free_device(ttc_handle* h) {
     h->setup_sig.clear();
+    // everything below belongs to the device the state was built on, which ttc_set_device may since have left behind
+    const int adev = h->alloc_device >= 0 ? h->alloc_device : h->device;
+    if (h->alloc_device >= 0) cudaSetDevice(adev);
     if (h->stream) cudaStreamSynchronize(h->stream);
     window_teardown(h);
     for (int g = 0; g < 2; ++g) if (h->gexec[g]) { cudaGraphExecDestroy(h->gexec[g]); h->gexec[g] = nullptr; }
     h->graph_sig.clear();
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
-        for (size_t i = 0; i < h->allocs.size(); ++i) g_pool.put_dev(h->device, h->alloc_bytes[i], h->allocs[i]);
+        for (size_t i = 0; i < h->allocs.size(); ++i) g_pool.put_dev(adev, h->alloc_bytes[i], h->allocs[i]);
         for (auto& hb : h->host_blocks) g_pool.put_host(hb.second, hb.first);
-        if (h->pack_d) { g_pool.put_dev(h->device, h->pack_cap * sizeof(double), h->pack_d); }
+        if (h->pack_d) { g_pool.put_dev(adev, h->pack_cap * sizeof(double), h->pack_d); }
     }
     h->allocs.clear(); h->alloc_bytes.clear(); h->host_blocks.clear();
     h->lot_h = nullptr; h->out_h = nullptr; h->sweep_h = nullptr; h->ready_h = nullptr; h->stage_h = nullptr; h->stage_cap = 0;
@@ -333,6 +342,7 @@ void free_device(ttc_handle* h) {
     h->ev_fork.clear(); h->ev_join.clear();
     if (h->stream_q) { cudaStreamDestroy(h->stream_q); h->stream_q = nullptr; }
     if (h->stream) { cudaStreamDestroy(h->stream); h->stream = nullptr; }
+    h->alloc_device = -1;
 }
 
 // kernel launch with accounting; in profile mode each launch is bracketed by events (serialising, diagnostic only)
@@ -369,6 +379,11 @@ inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
         default:          { constexpr int K = KIND_MVN;     __VA_ARGS__; } break; \
     }
 
+// the bond-visit kernels (k_visits, k_sweeps) have a dedicated instance for Ising C (streaming evaluation, ttc_visit.cuh)
+#define VISIT_KIND_SWITCH(h, ...)                                                                                     \
+    if ((h)->kind == TTC_ISING && (h)->ising_id == 1) { constexpr int K = KIND_ISINGC; __VA_ARGS__; }                 \
+    else KIND_SWITCH((h)->kind, __VA_ARGS__)
+
 static int QINC_THREADS = std::getenv("TTC_QINC_THREADS") ? std::atoi(std::getenv("TTC_QINC_THREADS")) : 1024;   // k_quad_inc: staging is latency-bound, more loads in flight
 int threads_for(const ttc_handle* h) { return h->kind == TTC_MVN ? 64 : 256; }
 size_t aux_smem(const ttc_handle* h) { return (size_t)h->plan.auxsm * sizeof(double); }
@@ -376,10 +391,11 @@ size_t aux_smem(const ttc_handle* h) { return (size_t)h->plan.auxsm * sizeof(dou
 int ensure_pack(ttc_handle* h, size_t cnt) {
     std::lock_guard<std::mutex> lk(g_pool_mu);
     if (cnt > h->pack_cap) {
-        if (h->pack_d) g_pool.put_dev(h->device, h->pack_cap * sizeof(double), h->pack_d);
+        const int adev = h->alloc_device >= 0 ? h->alloc_device : h->device;
+        if (h->pack_d) g_pool.put_dev(adev, h->pack_cap * sizeof(double), h->pack_d);
         h->pack_d = nullptr; h->pack_cap = 0;
         void* q = nullptr;
-        CUDA_TRY(h, g_pool.get_dev(h->device, cnt * sizeof(double), &q));
+        CUDA_TRY(h, g_pool.get_dev(adev, cnt * sizeof(double), &q));
         h->pack_d = (double*)q; h->pack_cap = cnt;
     }
     if (cnt > h->stage_cap) {
@@ -430,6 +446,7 @@ int setup_device(ttc_handle* h, int maxrank) {
     h->setup_serial += 1;
     int st = check_device(h);
     if (st) return st;
+    h->alloc_device = h->device;
     CUDA_TRY(h, cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, h->device));   // (cudaGetDeviceProperties costs milliseconds)
     {
         // the sweep stream outranks the quadrature stream: when both have CTAs to place, the bond-visit clusters go first
@@ -628,13 +645,13 @@ int setup_device(ttc_handle* h, int maxrank) {
         else { h->cluster_size = 8; h->cluster_threads = 256; }
         if (const char* e = std::getenv("TTC_CLUSTER_SIZE")) h->cluster_size = std::atoi(e);
         if (const char* e = std::getenv("TTC_CLUSTER_THREADS")) h->cluster_threads = std::atoi(e);
-        h->sm_visit = ((size_t)D.auxsm + Rmax + (size_t)Rmax * Rmax + Rmax + D.stage_max) * sizeof(double) + (size_t)(4 * Rmax + 8) * sizeof(int);
+        h->sm_visit = ((size_t)D.auxsm + 5 * (size_t)Rmax + (size_t)Rmax * Rmax + Rmax + D.stage_max) * sizeof(double) + (size_t)(4 * Rmax + 8) * sizeof(int);
         h->cluster_ok = D.stage && h->use_wave && h->sm_visit <= 200 * 1024 && h->cluster_size >= 1 && h->cluster_size <= MAXCS && h->cluster_threads >= 32 &&
                         h->cluster_threads <= VISIT_MAXTHREADS && h->cluster_threads % 32 == 0 &&
                         !std::getenv("TTC_NO_CLUSTER");
         if (h->cluster_ok) {
             cudaError_t ce = cudaSuccess;
-            KIND_SWITCH(h->kind,
+            VISIT_KIND_SWITCH(h,
                 ce = cudaFuncSetAttribute(k_visits<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_visit);
                 if (ce == cudaSuccess && h->cluster_size > 8) ce = cudaFuncSetAttribute(k_visits<K>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             );
@@ -647,7 +664,7 @@ int setup_device(ttc_handle* h, int maxrank) {
                 at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 cfg.attrs = at; cfg.numAttrs = 1;
                 int ncl = 0; cudaError_t e2 = cudaSuccess;
-                KIND_SWITCH(h->kind, e2 = cudaOccupancyMaxActiveClusters(&ncl, k_visits<K>, &cfg));
+                VISIT_KIND_SWITCH(h, e2 = cudaOccupancyMaxActiveClusters(&ncl, k_visits<K>, &cfg));
                 if (e2 != cudaSuccess) { (void)cudaGetLastError(); return false; }
                 return ncl >= 1;
             };
@@ -655,6 +672,39 @@ int setup_device(ttc_handle* h, int maxrank) {
                 h->cluster_size = 8; h->cluster_threads = 256;
                 if (!fits(8, 256)) h->cluster_ok = false;
             }
+        }
+    }
+    // persistent sweep kernel: same cluster shape and shared memory; every cluster must be resident at once (cooperative launch)
+    {
+        SweepMail* dmail = nullptr;
+        { int s1 = dev_alloc(h, &dmail, (size_t)P); if (s1) return s1; }
+        D.mail = dmail; D.win_mail = 0;
+        h->persist_ok = false;
+        if (h->cluster_ok && !std::getenv("TTC_NO_PERSISTENT")) {
+            cudaError_t ce = cudaSuccess;
+            VISIT_KIND_SWITCH(h,
+                ce = cudaFuncSetAttribute(k_sweeps<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_visit);
+                if (ce == cudaSuccess && h->cluster_size > 8) ce = cudaFuncSetAttribute(k_sweeps<K>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            );
+            if (ce == cudaSuccess) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(h->cluster_size, D.nv, 1); cfg.blockDim = dim3(h->cluster_threads, 1, 1); cfg.dynamicSmemBytes = h->sm_visit;
+                cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = h->cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                int ncl = 0;
+                VISIT_KIND_SWITCH(h, ce = cudaOccupancyMaxActiveClusters(&ncl, k_sweeps<K>, &cfg));
+                h->persist_ok = (ce == cudaSuccess) && ncl >= D.nv && P <= 64;
+            }
+            if (ce != cudaSuccess) (void)cudaGetLastError();
+        }
+        if (h->persist_ok) {
+            double* dcs = nullptr;
+            int s1 = dev_alloc(h, &dcs, (size_t)Rmax * (P + 1) * Rmax * Rmax, false); if (s1) return s1;
+            h->chainS = dcs;
+            cudaFuncSetAttribute(k_quad_lua_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_lua);
+            cudaFuncSetAttribute(k_quad_chain_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_mat3);
+            cudaFuncSetAttribute(k_quad_tree_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_mat3);
         }
     }
     // opt in to more than 48 KB of dynamic shared memory where the staging areas need it
@@ -857,6 +907,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     char line[512];
 
     D.piv = h->piv;
+    D.exp_mode = h->exp_mode;
     if (h->timeline) {
         if (!h->tlog_d) { CUDA_TRY(h, cudaMalloc((void**)&h->tlog_d, 3 * 65536 * sizeof(unsigned long long))); CUDA_TRY(h, cudaMalloc((void**)&h->tlog_n_d, sizeof(int))); }
         CUDA_TRY(h, cudaMemsetAsync(h->tlog_n_d, 0, sizeof(int), s));
@@ -924,10 +975,14 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     h->rng_k.assign(P, 0);
 
     tr.lap("init_search+tables");
+    // the whole sweep loop as one persistent cooperative kernel (ttc_sweep.cuh) whenever the cluster kernel applies and every
+    // cluster of this process is resident at once; TTC_NO_PERSISTENT=1 keeps the per-sweep schedule (graphs of k_visits + ...)
+    const bool persistent = h->persist_ok && h->cluster_ok && h->nproc == 1 && !h->ucb && !h->verbose && !h->force_sync && !h->force_host_lottery &&
+                            h->piv >= 0 && !h->force_split && !h->profile && h->use_wave;
     // ---- initial cross fibers and factors (dmrgg.f90:220-248)
     KIND_SWITCH(h->kind, L(KC_INIT, [&] { k_init_cross<K><<<dim3(cdiv(h->nmax, TB), d), TB, smA, s>>>(D); }));
     L(KC_INIT, [&] { k_init_factors<<<dim3(cdiv(h->nmax, 256), d), 256, 0, s>>>(D); });
-    if (has_quad && h->use_wave && !h->force_split)      // contracted cores of the rank-1 train: extents (1,1) for the incremental quadrature
+    if (has_quad && h->use_wave && !h->force_split && !persistent)      // contracted cores of the rank-1 train: extents (1,1) for the incremental quadrature
         L(KC_INIT, [&] { k_quad_inc<<<D.c_hi - D.c_lo + 1, QINC_THREADS, h->sm_qinc, s>>>(D, 1, h->qinc_stage, 0); });
     // fibers back to the host for the scalar bookkeeping of the '0::' line
     std::vector<std::vector<double>> fib(d + 1);
@@ -1115,7 +1170,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
             at[0].val.clusterDim.x = h->cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             cudaError_t ce = cudaSuccess;
-            KIND_SWITCH(h->kind, L(KC_VISITS, [&] { ce = cudaLaunchKernelEx(&cfg, k_visits<K>, D, dir, small_element, small_pivot, multi ? 0 : 1, (fused && P == 1) ? eff_maxrank : 0); }));
+            VISIT_KIND_SWITCH(h, L(KC_VISITS, [&] { ce = cudaLaunchKernelEx(&cfg, k_visits<K>, D, dir, small_element, small_pivot, multi ? 0 : 1, (fused && P == 1) ? eff_maxrank : 0); }));
             CUDA_TRY(h, ce);
         } else {
             for (int pp = 1; pp <= maxnb; ++pp) { int e = enqueue_visit(dir, pp, rb); if (e) return e; }
@@ -1186,7 +1241,30 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
             CUDA_TRY(h, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
             h->ev_fork.push_back(a); h->ev_join.push_back(b);
         }
-    const bool use_graph = !sync_mode && !h->profile && !h->no_graph && (!multi || h->p2p || std::getenv("TTC_MP_GRAPH") != nullptr);
+    const bool use_graph = !persistent && !sync_mode && !h->profile && !h->no_graph && (!multi || h->p2p || std::getenv("TTC_MP_GRAPH") != nullptr);
+    if (persistent) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(h->cluster_size, NV, 1);
+        cfg.blockDim = dim3(h->cluster_threads, 1, 1);
+        cfg.dynamicSmemBytes = h->sm_visit;
+        cfg.stream = s;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = h->cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
+        cfg.attrs = at; cfg.numAttrs = 2;
+        cudaError_t ce = cudaSuccess;
+        VISIT_KIND_SWITCH(h, L(KC_VISITS, [&] { ce = cudaLaunchKernelEx(&cfg, k_sweeps<K>, D, last_sweep, eff_maxrank, small_element, small_pivot); }));
+        CUDA_TRY(h, ce);
+        if (has_quad) {
+            // per-sweep quadrature values of ALL sweeps at once (they feed the printed lines only, dmrgg.f90:975-1008)
+            const int R = h->Rmax, ncore = D.c_hi - D.c_lo + 1;
+            L(KC_QUAD, [&] { k_quad_contract_sm<<<dim3(R, ncore), 256, h->sm_contract, s>>>(D, 1, (int)(h->sm_contract / sizeof(double))); });
+            L(KC_QUAD, [&] { k_quad_lua_all<<<ncore, 512, h->sm_lua, s>>>(D); });
+            L(KC_QUAD, [&] { k_quad_chain_all<<<dim3(NV, last_sweep), 512, h->sm_mat3, s>>>(D, h->chainS); });
+            L(KC_QUAD, [&] { k_quad_tree_all<<<last_sweep, 512, h->sm_mat3, s>>>(D, h->chainS); });
+        }
+    }
     if (use_graph) {
         std::vector<long long> gsig = {(long long)h->piv, (long long)has_quad, (long long)maxrank, (long long)h->use_wave, (long long)dev_lot,
                                        (long long)h->setup_serial, (long long)h->timeline, (long long)use_cluster,
@@ -1194,6 +1272,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         gsig.push_back(graph_sweeps);
         gsig.push_back((long long)overlap);
         gsig.push_back((long long)fused);
+        gsig.push_back((long long)h->exp_mode);
         if (gsig != h->graph_sig) {
             // ONE graph holds `graph_sweeps` consecutive sweeps ('>>', '<<', '>>', ...): fewer graph boundaries on the device.
             // Sweeps past the exit condition are no-ops (the ready flag is tested by every kernel).
@@ -1218,7 +1297,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         }
     }
     tr.lap("graph_capture");
-    for (it = 1; it <= last_sweep; ++it) {
+    for (it = 1; !persistent && it <= last_sweep; ++it) {
         if (!multi && *(volatile int*)h->ready_h) break;   // device already reached its exit condition
         int e = 0;
         if (use_graph) {
@@ -1273,6 +1352,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     if (ctrl.error == 2) { h->err = "internal: the incremental quadrature saw a rank grow by more than one in a sweep"; return TTC_ERR_STATE; }
     if (ctrl.error) { h->err = "rank capacity exceeded (pass maxrank)"; return TTC_ERR_RANK; }
     it = ctrl.nsweeps;
+    h->converged = (ctrl.has_accuracy && ctrl.strike >= 3) ? 1 : 0;
     {
         std::vector<SweepOut> slog(it + 1);
         std::vector<int> rklog((size_t)(it + 1) * (d + 1));
@@ -1374,7 +1454,7 @@ int ttc_create(ttc_handle** out, int kind, int d, const int* n, const double* pa
 
 void ttc_destroy(ttc_handle* h) {
     if (!h) return;
-    if (h->stream || !h->allocs.empty()) { cudaSetDevice(h->device); free_device(h); }
+    if (h->stream || !h->allocs.empty()) free_device(h);      // (switches to the device the blocks were allocated on)
     if (h->win) { cudaSetDevice(h->device); window_teardown(h); }
     if (h->comm) { cudaSetDevice(h->device); nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->flush_d) cudaFree(h->flush_d);
@@ -1384,7 +1464,18 @@ void ttc_destroy(ttc_handle* h) {
 
 const char* ttc_last_error(const ttc_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 
-int ttc_set_device(ttc_handle* h, int dev) { if (!h) return TTC_ERR_ARG; h->device = dev; return TTC_OK; }
+int ttc_set_device(ttc_handle* h, int dev) {
+    if (!h) return TTC_ERR_ARG;
+    if (dev == h->device) return TTC_OK;
+    if (h->comm) { h->err = "ttc_set_device: the communicator of ttc_comm_init is bound to the current device"; return TTC_ERR_STATE; }
+    // device state of an earlier run lives on the old device: release it there (free_device switches to the device the
+    // blocks were allocated on), so that nothing of GPU A is ever handed to a kernel on GPU B
+    if (h->stream || !h->allocs.empty()) { free_device(h); h->ran = false; }
+    if (h->flush_d) { cudaFree(h->flush_d); h->flush_d = nullptr; h->flush_cap = 0; }
+    if (h->tlog_d) { cudaFree(h->tlog_d); cudaFree(h->tlog_n_d); h->tlog_d = nullptr; h->tlog_n_d = nullptr; }
+    h->device = dev;
+    return TTC_OK;
+}
 int ttc_set_partition(ttc_handle* h, int nparts, const int* own) {
     if (!h || nparts < 1) return TTC_ERR_ARG;
     h->P = nparts;
@@ -1410,6 +1501,8 @@ int ttc_set_tru(ttc_handle* h, int present, double tru) { if (!h) return TTC_ERR
 int ttc_set_seed(ttc_handle* h, unsigned long long seed) { if (!h) return TTC_ERR_ARG; h->seed = seed; return TTC_OK; }
 int ttc_set_uniform_callback(ttc_handle* h, ttc_uniform_cb cb, void* ctx) { if (!h) return TTC_ERR_ARG; h->ucb = cb; h->ucb_ctx = ctx; return TTC_OK; }
 int ttc_set_verbose(ttc_handle* h, int v) { if (!h) return TTC_ERR_ARG; h->verbose = v; return TTC_OK; }
+int ttc_set_exp_mode(ttc_handle* h, int mode) { if (!h || mode < 0 || mode > 1) return TTC_ERR_ARG; h->exp_mode = mode; return TTC_OK; }
+int ttc_converged(const ttc_handle* h) { return h ? h->converged : 0; }
 int ttc_set_lottery_mode(ttc_handle* h, int mode) {
     if (!h || mode < 0 || mode > 4) return TTC_ERR_ARG;
     h->force_host_lottery = (mode == 1); h->force_sync = (mode == 1 || mode == 2);

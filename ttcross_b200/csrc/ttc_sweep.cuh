@@ -1,0 +1,500 @@
+// =============================================================================
+// ttc_sweep.cuh — the WHOLE sweep loop of dtt_dmrgg (dmrgg.f90:314-1020) as ONE persistent kernel.
+//
+// One thread-block cluster per partition (virtual rank) lives across all sweeps.  Per sweep a cluster
+//   1. runs the bond visits of its partition (visit_list, ttc_visit.cuh: lottery -> rook fibers -> accept -> rank-1 append),
+//   2. announces them (flag1) and waits for its two NEIGHBOURS only,
+//   3. does its half of the post-sweep exchange on both of its boundaries (dmrgg.f90:872-958, dmrggmp.f90:572-629): the
+//      left member of a boundary appends the new column of row(c) (d2_luar with inv(c-1)), the right member the new row
+//      of col(c) (d2_lual with inv(c)); both evaluate the corner fiber when both adjacent bonds grew,
+//   4. publishes its scalars (flag2), waits for everybody's, and takes the MAX allreduce (:852-870), the sweep record and
+//      the exit test (:1010-1019) -- every cluster computes the same decision from the same records.
+// Nothing returns to the host between sweeps and nothing is re-launched: the launch gaps, the per-launch re-staging of the
+// control state and the separate exchange / close kernels of the per-sweep schedule are gone.  The per-sweep quadrature
+// values (dmrgg.f90:975-993) do not feed the exit test; they are computed after the loop for all sweeps at once
+// (k_quad_chain_all / k_quad_tree_all below) from the rank log: every entry of a contracted, luar'd and lual'd core is a
+// fixed operation sequence on data that never changes once written, so the value of sweep s is the chain over the
+// leading r_s x r_s blocks of the FINAL contracted cores, bit for bit.
+//
+// The clusters wait on one another (flags in global memory), so the kernel is launched cooperatively (co-residency
+// guaranteed by the driver); with several processes (one per GPU) the flags and the boundary slabs live in the peer
+// windows (CUDA IPC) and the same kernel pushes them over NVLink.
+// =============================================================================
+#pragma once
+#include "ttc_visit.cuh"
+
+namespace ttc {
+
+struct SweepRec {                      // what a partition tells the others at the end of a sweep
+    double amax1, pivotmax, pivotmin;  // after the bond visits: inputs of the MAX allreduce (dmrgg.f90:852-870)
+    double amax2;                      // after the corner fibers (rank 0's goes into the sweep record and the exit test)
+    long long neval;                   // after the corner fibers
+    int error, pad;
+};
+struct SweepMail {                     // one per partition in every process's window; records double-buffered by sweep parity
+    unsigned long long flag1;          // sequence number of the last sweep whose bond visits (and pushes) are complete
+    unsigned long long flag2;          // ... whose exchange is complete (rec valid)
+    int upd1[2][2];                    // [parity][first bond, last bond] updated in that sweep (valid with flag1)
+    SweepRec rec[2];                   // (valid with flag2)
+    unsigned long long pad[16];
+};
+static_assert(sizeof(SweepMail) == 256, "SweepMail is 256 bytes");
+
+struct SweepLocal {                    // per-CTA replica of the cluster's loop state (advanced identically in every CTA)
+    int rkL, rkR;                      // current ranks of the foreign bonds lo-1 and hi
+    int updL, updR;                    // did the neighbour's adjacent bond grow in this sweep
+    int strike, ready, corner, pad;
+    double amax1;
+    double r_amax1[64], r_pmax[64], r_pmin[64], r_amax2[64];
+    long long r_neval[64];
+    int r_err[64];
+};
+
+template <bool SYS>
+__device__ __forceinline__ void st_release(unsigned long long* p, unsigned long long v) {
+    if (SYS) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    else asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+template <bool SYS>
+__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p) {
+    unsigned long long v;
+    if (SYS) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// bounded spin: a lost partner becomes ctrl->error = 3 (TTC_ERR_COMM) instead of a hang
+__device__ __forceinline__ void sweep_wait(const DevPlan& P, const unsigned long long* flag, unsigned long long seq, bool sys) {
+    unsigned long long t0 = 0;
+    int spins = 0;
+    while ((sys ? ld_acquire<true>(flag) : ld_acquire<false>(flag)) < seq) {
+        if (++spins < 64) continue;
+        spins = 0;
+        const unsigned long long t1 = globaltimer_ns();
+        if (t0 == 0) t0 = t1;
+        else if (t1 - t0 > 4000000000ULL) { P.ctrl->error = 3; break; }
+    }
+}
+
+// ----------------------------------------------------------------------------
+// NXI independent d2_luar / d2_lual recurrences of rank r <= 32 in one warp, interleaved: a recurrence is r dependent steps
+// of (broadcast, multiply, add) -- about 50 cycles each and nothing to overlap inside one chain -- so a warp that owns
+// several mode indices runs them side by side.  Same operations in the same order as warp_luar / warp_lual per chain.
+// ----------------------------------------------------------------------------
+constexpr int XCH = 6;
+__device__ __forceinline__ void warp_luar_multi(double (&y)[XCH], int nx, int r, const double* T) {
+    const int lane = threadIdx.x & 31;
+    const bool in = lane < r;
+    double tmp[XCH];
+#pragma unroll
+    for (int v = 0; v < XCH; ++v) tmp[v] = 0.0;
+#pragma unroll 2
+    for (int u = 0; u + 1 < r; ++u) {
+        const double gsu = (in && lane > u) ? T[u * r + lane] : 0.0;
+#pragma unroll
+        for (int v = 0; v < XCH; ++v) {
+            if (v < nx) {
+                const double yu = __shfl_sync(FULLMASK, y[v], u);
+                if (in && lane > u) tmp[v] = tmp[v] + yu * gsu;
+                if (lane == u + 1) y[v] = y[v] + (-tmp[v]);
+            }
+        }
+    }
+}
+__device__ __forceinline__ void warp_lual_multi(double (&y)[XCH], int nx, int r, const double* T, const double* DI) {
+    const int lane = threadIdx.x & 31;
+    const bool in = lane < r;
+    const double di = in ? DI[lane] : 0.0;
+    if (r > 0 && lane == 0) {
+#pragma unroll
+        for (int v = 0; v < XCH; ++v) y[v] = di * y[v];
+    }
+#pragma unroll 2
+    for (int u = 0; u + 1 < r; ++u) {
+        const double gcu = (in && lane > u) ? T[u * r + lane] : 0.0;
+#pragma unroll
+        for (int v = 0; v < XCH; ++v) {
+            if (v < nx) {
+                const double yu = __shfl_sync(FULLMASK, y[v], u);
+                if (in && lane > u) y[v] = y[v] + (-gcu) * yu;
+                if (lane == u + 1) y[v] = di * y[v];
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------
+// This partition's half of the post-sweep exchange (dmrgg.f90:872-958, dmrggmp.f90:572-629) on its two boundaries.
+// Core c is shared by the two members of a boundary; rc1 / rc are the ranks of the bonds c-1 / c AFTER the sweep.
+//   side 1 (left boundary, c = lo): this partition is the RIGHT member (owns bond c, inv(c), col(c)); if bond c-1 grew, the
+//           new row arg(c)(rc1, x, :) arrived and col(c)(rc1, x, :) = d2_lual(rc, inv(c)) of it is appended (dmrggmp.f90:597-626);
+//   side 0 (right boundary, c = hi): the LEFT member (owns bond c-1, inv(c-1), row(c)); if bond c grew, the new slice
+//           arg(c)(:, x, rc) arrived and row(c)(:, x, rc) = d2_luar(rc1, inv(c-1)) of it is appended (dmrgg.f90:913-951).
+// When both bonds of a boundary grew, the corner fiber arg(c)(rc1, x, rc), x = 1..n(c), is evaluated by BOTH members (each
+// counts it, like the reference).  When both boundaries have work the CTAs of the cluster split into two halves; a CTA
+// first evaluates the corner values of exactly the mode indices its own warps own (one thread each), then its warps run
+// their recurrences interleaved.  Returns the largest |corner value| seen by this thread (-1: none).
+// smem: ext = staged LU table (+ diagonal), stg = XF[d] | WF[d] | F[corner values of this CTA].
+// ----------------------------------------------------------------------------
+struct BoundaryJob { int work, side, c, rc1, rc, corner; };
+template <int KIND>
+__device__ __forceinline__ double exchange_boundaries(const DevPlan& P, cg::cluster_group& cl, const VisitCtx& C, const BoundaryJob& JA, const BoundaryJob& JB) {
+    if (!JA.work && !JB.work) return -1.0;
+    const int crank = (int)cl.block_rank(), cs = (int)cl.num_blocks();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    // which boundary this CTA serves, and its position among the CTAs that serve it
+    const bool both = JA.work && JB.work && cs >= 2;
+    const int halfA = cs / 2;
+    const bool mineB = both ? (crank >= halfA) : (JB.work != 0);
+    const BoundaryJob J = mineB ? JB : JA;
+    const int nside = both ? (mineB ? cs - halfA : halfA) : cs;
+    const int csub = both ? (mineB ? crank - halfA : crank) : crank;
+    const bool second_pass = JA.work && JB.work && cs < 2;       // (a one-CTA cluster serves both boundaries in turn)
+    double cmax = -1.0;
+    for (int pass = 0; pass < (second_pass ? 2 : 1); ++pass) {
+        const BoundaryJob Jp = second_pass ? (pass == 0 ? JA : JB) : J;
+        const int side = Jp.side, c = Jp.c, rc1 = Jp.rc1, rc = Jp.rc;
+        const bool corner = Jp.corner != 0;
+        const int nc = P.n[c];
+        double* XF = C.stg; double* WF = XF + P.d; double* F = WF + P.d;
+        double* T = C.ext; double* DI = T + (i64)P.Rmax * P.Rmax;
+        double* argc = P.arg + P.coreOff[c];
+        const bool hasw = (P.kind == KIND_ISING);
+        const int nwoff = P.n[1];
+        // the mode indices of this CTA: warp w owns x = first(w) .. first(w) + cnt(w) - 1 (contiguous, balanced over all warps)
+        const int W = nside * nw, base = nc / W, rem = nc % W;
+        const int gw0 = csub * nw;                                 // first global warp of this CTA
+        const int cta_first = gw0 * base + min(gw0, rem);
+        const int cta_cnt = nw * base + max(0, min(rem - gw0, nw));
+        __syncthreads();                                           // ext / stg are free (previous users done)
+        if (corner) {
+            const int* Lt = P.Lidx + P.offL[c - 1]; const int* Rt = P.Ridx + P.offR[c];
+            for (int pos = threadIdx.x; pos < P.d - 1; pos += blockDim.x) {
+                const int idx = (pos < c - 1) ? __ldcg(Lt + (i64)pos * P.Rmax + (rc1 - 1)) : __ldcg(Rt + (i64)(pos - (c - 1)) * P.Rmax + (rc - 1));
+                XF[pos] = P.par[idx - 1]; WF[pos] = hasw ? P.par[nwoff + idx - 1] : 0.0;
+            }
+        }
+        if (side == 0) stage_luar_cg(P.inv + (i64)(c - 1) * P.Rmax * P.Rmax, rc1, T);
+        else stage_lual_cg(P.inv + (i64)c * P.Rmax * P.Rmax, rc, T, DI);
+        __syncthreads();
+        if (corner) {
+            for (int t = threadIdx.x; t < cta_cnt; t += blockDim.x) {
+                const int x = cta_first + t;
+                StagedVals sv;
+                sv.XL = XF; sv.WL = WF; sv.nl = c - 1; sv.rl = 1; sv.i = 1;
+                sv.xj = P.par[x]; sv.wj = hasw ? P.par[nwoff + x] : 0.0;
+                sv.hask = 0; sv.xk = 0.0; sv.wk = 0.0;
+                sv.XR = XF + (c - 1); sv.WR = WF + (c - 1); sv.rr = 1; sv.q = 1;
+                const double f = eval_point_wide<KIND>(P, sv, C.A);
+                argc[(rc1 - 1) + (i64)P.Rmax * (x + (i64)nc * (rc - 1))] = f;     // (both members store the same value)
+                F[t] = f;
+                cmax = fmax(cmax, fabs(f));
+            }
+            __syncthreads();
+        }
+        const int gw = gw0 + wid;
+        const int wfirst = gw * base + min(gw, rem), wcnt = base + (gw < rem ? 1 : 0);
+        const int rr_ = side == 0 ? rc1 : rc;                      // rank of the recurrence
+        if (rr_ <= 32) {
+            for (int k0 = 0; k0 < wcnt; k0 += XCH) {
+                const int nx = min(XCH, wcnt - k0);
+                double y[XCH];
+#pragma unroll
+                for (int v = 0; v < XCH; ++v) {
+                    y[v] = 0.0;
+                    if (v < nx && lane < rr_) {
+                        const int x = wfirst + k0 + v;
+                        if (corner && lane == rr_ - 1) y[v] = F[x - cta_first];
+                        else if (side == 0) y[v] = __ldcg(argc + (i64)P.Rmax * (x + (i64)nc * (rc - 1)) + lane);
+                        else y[v] = __ldcg(argc + (rc1 - 1) + (i64)P.Rmax * x + lane * ((i64)P.Rmax * nc));
+                    }
+                }
+                if (side == 0) warp_luar_multi(y, nx, rr_, T); else warp_lual_multi(y, nx, rr_, T, DI);
+#pragma unroll
+                for (int v = 0; v < XCH; ++v) {
+                    if (v < nx && lane < rr_) {
+                        const int x = wfirst + k0 + v;
+                        if (side == 0) P.rowT[P.coreOff[c] + (i64)nc * (rc - 1) + x + lane * ((i64)nc * P.Rmax)] = y[v];
+                        else P.col[P.coreOff[c] + (rc1 - 1) + (i64)P.Rmax * x + lane * ((i64)P.Rmax * nc)] = y[v];
+                    }
+                }
+            }
+        } else {
+            for (int k = 0; k < wcnt; ++k) {
+                const int x = wfirst + k;
+                const double f = corner ? F[x - cta_first] : 0.0;
+                double y[MAXRPL];
+                if (side == 0) {
+                    const double* src = argc + (i64)P.Rmax * (x + (i64)nc * (rc - 1));
+                    double* dst = P.rowT + P.coreOff[c] + (i64)nc * (rc - 1) + x;
+                    const i64 de = (i64)nc * P.Rmax;
+#pragma unroll
+                    for (int u = 0; u < MAXRPL; ++u) {
+                        const int sidx = lane + 32 * u;
+                        y[u] = (sidx < rc1) ? ((corner && sidx == rc1 - 1) ? f : __ldcg(src + sidx)) : 0.0;
+                    }
+                    warp_luar(y, rc1, GSm{T, rc1});
+#pragma unroll
+                    for (int u = 0; u < MAXRPL; ++u) { const int sidx = lane + 32 * u; if (sidx < rc1) dst[sidx * de] = y[u]; }
+                } else {
+                    const i64 se = (i64)P.Rmax * nc;
+                    const double* src = argc + (rc1 - 1) + (i64)P.Rmax * x;
+                    double* dst = P.col + P.coreOff[c] + (rc1 - 1) + (i64)P.Rmax * x;
+#pragma unroll
+                    for (int u = 0; u < MAXRPL; ++u) {
+                        const int cc = lane + 32 * u;
+                        y[u] = (cc < rc) ? ((corner && cc == rc - 1) ? f : __ldcg(src + cc * se)) : 0.0;
+                    }
+                    warp_lual(y, rc, GSm{T, rc}, DSm{DI});
+#pragma unroll
+                    for (int u = 0; u < MAXRPL; ++u) { const int cc = lane + 32 * u; if (cc < rc) dst[cc * se] = y[u]; }
+                }
+            }
+        }
+    }
+    return cmax;
+}
+
+// ----------------------------------------------------------------------------
+// grid (CS, nv), cluster (CS, 1, 1), cooperative.  Dynamic shared memory as k_visits.
+// ----------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 1)
+k_sweeps(DevPlan P, int it_last, int maxrank, double small_element, double small_pivot) {
+    tl_stamp(P, 36);
+    cg::cluster_group cl = cg::this_cluster();
+    extern __shared__ double smem[];
+    __shared__ VisitShared sh;
+    __shared__ SweepLocal sl;
+    const int crank = (int)cl.block_rank();
+    VisitCtx C;
+    C.sh = &sh;
+    C.v = P.v0 + blockIdx.y;
+    C.lo = P.own[C.v]; C.hi = P.own[C.v + 1];
+    C.A = stage_aux<KIND>(P, smem);
+    C.xs = smem + P.auxsm;
+    C.pre = C.xs + P.Rmax;
+    C.ext = C.pre + 4 * (i64)P.Rmax;
+    C.stg = C.ext + (i64)P.Rmax * P.Rmax + P.Rmax;
+    C.ibuf = (int*)(C.stg + P.stage_max);
+    C.phase = 0;
+    const int v = C.v, lo = C.lo, hi = C.hi;
+    const bool multi = P.nproc > 1;
+    SweepMail* mail = P.mail;
+    const unsigned long long seq0 = P.ctrl->run_serial * 65536ULL;
+    if (threadIdx.x == 0) {
+        sh.S = P.st[v];
+        sl.rkL = P.rk[lo - 1]; sl.rkR = P.rk[hi];
+        sl.strike = 0; sl.ready = 0;
+    }
+    __syncthreads();
+    int it = 1;
+    for (; it <= it_last; ++it) {
+        const int dir = 2 - (it & 1);                  // dmrgg.f90:317
+        const int par = it & 1;
+        const unsigned long long seq = seq0 + (unsigned long long)it;
+        C.rkL = sl.rkL; C.rkR = sl.rkR;
+        visit_list<KIND>(P, cl, C, it, dir, small_element, small_pivot);      // ends with a cluster barrier
+
+        // ---- announce the bond visits: everything this cluster wrote is ordered before the flag (the cluster barrier
+        // synchronises the writers with this thread, the release is cumulative)
+        if (crank == 0 && threadIdx.x == 0) {
+            sl.amax1 = sh.S.amax;
+            mail[v].upd1[par][0] = C.upd_first; mail[v].upd1[par][1] = C.upd_last;
+            __threadfence();
+            if (multi) st_release<true>(&mail[v].flag1, seq); else st_release<false>(&mail[v].flag1, seq);
+        }
+        if (threadIdx.x == 0) sl.amax1 = sh.S.amax;
+        tl_mark(P, 70);
+        // ---- wait for the two neighbours (each CTA polls for itself: no extra cluster barrier)
+        if (threadIdx.x < 2) {
+            const int u = threadIdx.x == 0 ? v - 1 : v + 1;
+            int upd = 0;
+            if (u >= 0 && u < P.P) {
+                sweep_wait(P, &mail[u].flag1, seq, multi);
+                upd = *(volatile int*)&mail[u].upd1[par][threadIdx.x == 0 ? 1 : 0];
+            }
+            if (threadIdx.x == 0) sl.updL = upd; else sl.updR = upd;
+        }
+        __syncthreads();
+        tl_mark(P, 71);
+        // ---- this partition's half of the exchange on its two boundaries
+        const int updL = sl.updL, updR = sl.updR;
+        int ncorner = 0;
+        BoundaryJob JA = {0, 1, lo, 0, 0, 0}, JB = {0, 0, hi, 0, 0, 0};
+        if (v > 0) {                                    // RIGHT member of boundary v-1: core lo
+            JA.work = updL; JA.rc1 = sl.rkL + updL; JA.rc = LDF(P.rk + lo); JA.corner = updL && C.upd_first;
+            if (JA.corner) ncorner += P.n[lo];
+        }
+        if (v < P.P - 1) {                              // LEFT member of boundary v: core hi
+            JB.work = updR; JB.rc1 = LDF(P.rk + hi - 1); JB.rc = sl.rkR + updR; JB.corner = C.upd_last && updR;
+            if (JB.corner) ncorner += P.n[hi];
+        }
+        double cmax = exchange_boundaries<KIND>(P, cl, C, JA, JB);
+        if (ncorner) {                                  // uniform over the cluster
+            Partial dummy = amax_init();
+            cluster_fold(cl, sh, C.phase, cmax, dummy);
+            if (threadIdx.x == 0) { sh.S.amax = fmax(sh.S.amax, cmax); sh.S.neval += ncorner; }
+        } else {
+            cl.sync();                                  // the appended factor entries are read by other CTAs in the next sweep
+        }
+        tl_mark(P, 72);
+        // ---- publish the scalars, wait for everybody's
+        if (crank == 0 && threadIdx.x == 0) {
+            SweepRec& R = mail[v].rec[par];
+            R.amax1 = sl.amax1; R.pivotmax = sh.S.pivotmax; R.pivotmin = sh.S.pivotmin;
+            R.amax2 = sh.S.amax; R.neval = sh.S.neval; R.error = *(volatile int*)&P.ctrl->error; R.pad = 0;
+            __threadfence();
+            if (multi) st_release<true>(&mail[v].flag2, seq); else st_release<false>(&mail[v].flag2, seq);
+        }
+        for (int u = threadIdx.x; u < P.P; u += blockDim.x) {
+            sweep_wait(P, &mail[u].flag2, seq, multi);
+            const volatile SweepRec& R = mail[u].rec[par];
+            sl.r_amax1[u & 63] = R.amax1; sl.r_pmax[u & 63] = R.pivotmax; sl.r_pmin[u & 63] = R.pivotmin;
+            sl.r_amax2[u & 63] = R.amax2; sl.r_neval[u & 63] = R.neval; sl.r_err[u & 63] = R.error;
+        }
+        __syncthreads();
+        tl_mark(P, 73);
+        // ---- MAX allreduce (dmrgg.f90:852-870), sweep record (:961-1008), exit test (:1010-1019); identical in every CTA
+        if (threadIdx.x == 0) {
+            double c1 = sl.r_amax1[0], c2 = sl.r_pmax[0], c3 = (sl.r_pmin[0] > 0.0) ? -sl.r_pmin[0] : -999e9;
+            long long ne = sl.r_neval[0];
+            int err = sl.r_err[0];
+            for (int u = 1; u < P.P; ++u) {
+                c1 = fmax(c1, sl.r_amax1[u]); c2 = fmax(c2, sl.r_pmax[u]);
+                c3 = fmax(c3, (sl.r_pmin[u] > 0.0) ? -sl.r_pmin[u] : -999e9);
+                ne += sl.r_neval[u]; err |= sl.r_err[u];
+            }
+            VState& St = sh.S;
+            St.amax = fmax(c1, St.amax);                 // the allreduced value, then this partition's corner fibers
+            const double s_pmax = c2, s_pmin = (-c3 == 999e9) ? -1.0 : -c3;
+            const double s_amax = fmax(c1, sl.r_amax2[0]);     // st[0].amax after the exchange
+            St.pivotmax_prev = s_pmax;                   // dmrgg.f90:961
+            St.pivotmax = -1.0; St.pivotmin = -1.0;      // dmrgg.f90:326-327 of the next sweep
+            int ready = 0;
+            if (maxrank > 0) ready = (it + 1 >= maxrank);
+            if (P.ctrl->has_accuracy) {
+                if (s_pmax <= P.ctrl->accuracy * s_amax) sl.strike += 1; else sl.strike = 0;
+                ready = ready || (sl.strike >= 3);
+            }
+            if (err) ready = 1;
+            sl.ready = ready;
+            sl.rkL += updL; sl.rkR += updR;
+            if (crank == 0) {
+                for (int x = lo; x <= hi - 1; ++x) { const int r = LDF(P.rk + x); P.rklog[(i64)it * (P.d + 1) + x] = r; P.rks[x] = r; }
+                if (v == 0) P.rklog[(i64)it * (P.d + 1)] = 1;
+                if (v == P.P - 1) P.rklog[(i64)it * (P.d + 1) + P.d] = 1;
+                if (v == P.v0) {                         // one record per process
+                    SweepOut& O = P.slog[it];
+                    O.neval = ne; O.amax = s_amax; O.pivotmax = s_pmax; O.pivotmin = s_pmin;
+                    O.t_ns = globaltimer_ns() - P.ctrl->t0_ns; O.valid = 1; O.pad = 0;
+                    if (err && !P.ctrl->error) P.ctrl->error = err;
+                }
+            }
+        }
+        __syncthreads();
+        tl_mark(P, 74);
+        if (sl.ready) break;
+    }
+    if (it > it_last) it = it_last;
+    if (crank == 0 && threadIdx.x == 0) {
+        P.st[v] = sh.S;
+        if (v == P.v0) { P.ctrl->nsweeps = it; P.ctrl->it = it + 1; P.ctrl->strike = sl.strike; P.ctrl->ready = 1; }
+        if (multi) { P.rk[lo - 1] = sl.rkL; P.rk[hi] = sl.rkR; }      // (one process: the owners' own entries are the truth)
+    }
+}
+
+// ----------------------------------------------------------------------------
+// Per-sweep quadrature values after the loop.  The contracted cores ttqq have been formed and dtt_lua'd at the FINAL
+// ranks (k_quad_contract_sm, k_quad_lua_all); sweep s uses their leading rklog[s] blocks.
+// k_quad_chain_all: grid (nv, S): chain product of partition v0 + x at sweep y + 1 -> chainS[(sweep - 1) * (P + 1) + v]
+// k_quad_tree_all : grid (S): the reference's binary tree over partitions (dmrgg.f90:1355-1405) -> slog[sweep].val
+// dynamic smem: 3 Rmax^2 doubles.
+// ----------------------------------------------------------------------------
+__global__ void k_quad_lua_all(DevPlan P) {
+    extern __shared__ double smem[];
+    const int p = P.c_lo + blockIdx.x;
+    const int r0 = P.rk[p - 1], r1 = P.rk[p];
+    double* M = smem; double* TL = M + r0 * r1; double* TR = TL + r0 * r0; double* DI = TR + r1 * r1;
+    double* gm = P.ttqq + (i64)p * P.Rmax * P.Rmax;
+    for (int x = threadIdx.x; x < r0 * r1; x += blockDim.x) { int k = x / r0, i = x - k * r0; M[x] = gm[i + (i64)P.Rmax * k]; }
+    stage_luar(P.inv + (i64)(p - 1) * P.Rmax * P.Rmax, r0, TL);
+    if (p < P.d) stage_lual(P.inv + (i64)p * P.Rmax * P.Rmax, r1, TR, DI);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int k = wid; k < r1; k += nw) {
+        double y[MAXRPL];
+#pragma unroll
+        for (int t = 0; t < MAXRPL; ++t) { int sidx = lane + 32 * t; y[t] = (sidx < r0) ? M[sidx + r0 * k] : 0.0; }
+        warp_luar(y, r0, GSm{TL, r0});
+#pragma unroll
+        for (int t = 0; t < MAXRPL; ++t) { int sidx = lane + 32 * t; if (sidx < r0) M[sidx + r0 * k] = y[t]; }
+    }
+    __syncthreads();
+    if (p < P.d) {
+        for (int i = wid; i < r0; i += nw) {
+            double y[MAXRPL];
+#pragma unroll
+            for (int t = 0; t < MAXRPL; ++t) { int c = lane + 32 * t; y[t] = (c < r1) ? M[i + r0 * c] : 0.0; }
+            warp_lual(y, r1, GSm{TR, r1}, DSm{DI});
+#pragma unroll
+            for (int t = 0; t < MAXRPL; ++t) { int c = lane + 32 * t; if (c < r1) M[i + r0 * c] = y[t]; }
+        }
+        __syncthreads();
+    }
+    for (int x = threadIdx.x; x < r0 * r1; x += blockDim.x) { int k = x / r0, i = x - k * r0; gm[i + (i64)P.Rmax * k] = M[x]; }
+}
+__global__ void k_quad_chain_all(DevPlan P, double* chainS) {
+    extern __shared__ double smem[];
+    const int v = P.v0 + blockIdx.x, sw = blockIdx.y + 1;
+    if (sw > P.ctrl->nsweeps) return;
+    const int first = P.own[v];
+    int last = P.own[v + 1] - 1;
+    if (v == P.P - 1) last = P.d;
+    const int ld = P.Rmax;
+    const int* rq = P.rklog + (i64)sw * (P.d + 1);
+    const i64 msz = (i64)ld * ld;
+    double* cur = smem; double* nxt = smem + msz; double* B = smem + 2 * msz;
+    const int m = rq[first - 1];
+    mat_load_sm(P.ttqq + (i64)first * msz, m, rq[first], ld, cur, ld);
+    __syncthreads();
+    for (int p = first + 1; p <= last; ++p) {
+        mat_load_sm(P.ttqq + (i64)p * msz, rq[p - 1], rq[p], ld, B, ld);
+        __syncthreads();
+        mat_mul_sm(cur, m, rq[p - 1], B, rq[p], nxt, ld);
+        __syncthreads();
+        double* t = cur; cur = nxt; nxt = t;
+    }
+    double* out = chainS + ((i64)(sw - 1) * (P.P + 1) + v) * msz;
+    const int nl = rq[last];
+    for (int e = threadIdx.x; e < m * nl; e += blockDim.x) { int j = e / m, i = e - j * m; out[i + (i64)ld * j] = cur[i + ld * j]; }
+    if (P.P == 1 && threadIdx.x == 0) P.slog[sw].val = cur[0];
+}
+__global__ void k_quad_tree_all(DevPlan P, double* chainS) {
+    extern __shared__ double smem[];
+    const int sw = blockIdx.x + 1;
+    if (sw > P.ctrl->nsweeps || P.P == 1) return;
+    const int ld = P.Rmax;
+    const int* rq = P.rklog + (i64)sw * (P.d + 1);
+    const i64 msz = (i64)ld * ld;
+    double* ch = chainS + (i64)(sw - 1) * (P.P + 1) * msz;
+    double* A = smem; double* B = smem + msz; double* Cm = smem + 2 * msz;
+    for (int q = 1; q < P.P; q *= 2) {
+        for (int me = 0; me + q < P.P; me += 2 * q) {
+            const int her = me + q;
+            int herend = her + q; if (herend > P.P) herend = P.P;
+            const int m = rq[P.own[me] - 1], kd = rq[P.own[her] - 1];
+            const int n = (herend == P.P) ? rq[P.d] : rq[P.own[herend] - 1];
+            mat_load_sm(ch + (i64)me * msz, m, kd, ld, A, ld);
+            mat_load_sm(ch + (i64)her * msz, kd, n, ld, B, ld);
+            __syncthreads();
+            mat_mul_sm(A, m, kd, B, n, Cm, ld);
+            __syncthreads();
+            double* out = ch + (i64)me * msz;
+            for (int e = threadIdx.x; e < m * n; e += blockDim.x) { int j = e / m, i = e - j * m; out[i + (i64)ld * j] = Cm[i + ld * j]; }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) P.slog[sw].val = ch[0];
+}
+
+}  // namespace ttc

@@ -359,45 +359,143 @@ __device__ __forceinline__ void tl_mark(const DevPlan& P, int id) {     // diagn
         if (k < P.tlog_cap) { P.tlog[3 * k] = (unsigned long long)id; P.tlog[3 * k + 1] = t; P.tlog[3 * k + 2] = (unsigned long long)clock64(); }
     }
 }
-constexpr int VISIT_MAXTHREADS = 256;
-// MVN evaluations are one long dependent DADD chain each (3 d^2 operations, one accumulator, mvn_pdf.f90:74-80): what
-// hides the FP64 latency (~60 cycles per dependent DADD, measured) is resident warps, not registers -> 64 registers per
-// thread.  (Measured on config E: the register-resident eval_mvn_reg makes one evaluation 2.3x faster, 133 us instead of
-// 300 us, but needs 255 registers = one CTA per SM, and 63 clusters then run in four waves instead of two: 86 ms
-// instead of 59 ms.  It is used where a single evaluation is the critical path: the corner fibers of the exchange.)
+
+// ----------------------------------------------------------------------------
+// Streaming evaluation of the Ising C integrand (test_crs_ising.f90:186-217, id = 1) at the points of a bond visit.
+// The reference runs two independent recurrences over the positions -- the prefix sums w (positions 1..m ascending) and
+// the suffix sums v (m..1 descending) -- then f = 2 / (v * w) and the product of the m weights in position order.
+// At a bond visit a point is (left pivot i | j | k | right pivot q): the first p-1 prefix steps depend on i only and the
+// first m-p-1 suffix steps on q only, so they are taken ONCE per pivot and visit (tables PW*, SV* in shared memory,
+// ising_c_prepare) and every evaluation continues them: the same operations on the same operands in the same order
+// (bit-identical), read straight from the staged tables -- no per-thread local array, no call, and the dependent chain
+// of an evaluation is max(p+1, m-p+1) multiplications instead of 2m.
+// ----------------------------------------------------------------------------
+struct IsingCTab {
+    const double *XL, *WL, *XR, *WR, *NX, *NW, *NX2, *NW2;
+    const double *PWK, *PWW, *SVK, *SVV;
+    int nl, rl, nr, rr;
+};
+// pre: shared double[4 * Rmax]; every thread of the CTA calls it (ends with a block barrier)
+__device__ __forceinline__ IsingCTab ising_c_prepare(const Stage& S, double* pre, int Rmax) {
+    IsingCTab T;
+    T.XL = S.XL; T.WL = S.WL; T.XR = S.XR; T.WR = S.WR; T.NX = S.NX; T.NW = S.NW; T.NX2 = S.NX2; T.NW2 = S.NW2;
+    T.nl = S.nl; T.rl = S.rl; T.nr = S.nr; T.rr = S.rr;
+    double* PWK = pre; double* PWW = pre + Rmax; double* SVK = pre + 2 * Rmax; double* SVV = pre + 3 * Rmax;
+    for (int t = threadIdx.x; t < S.rl + S.rr; t += blockDim.x) {
+        if (t < S.rl) {
+            double wk = 1.0, w = 1.0;
+            const double* xl = S.XL + t;
+            for (int pos = 0; pos < S.nl; ++pos) { wk = wk * xl[pos * S.rl]; w = w + wk; }
+            PWK[t] = wk; PWW[t] = w;
+        } else {
+            const int q = t - S.rl;
+            double vk = 1.0, vv = 1.0;
+            const double* xr = S.XR + q;
+            for (int pos = S.nr - 1; pos >= 0; --pos) { vk = vk * xr[pos * S.rr]; vv = vv + vk; }
+            SVK[q] = vk; SVV[q] = vv;
+        }
+    }
+    T.PWK = PWK; T.PWW = PWW; T.SVK = SVK; T.SVV = SVV;
+    __syncthreads();
+    return T;
+}
+__device__ __forceinline__ double ising_c_eval(const IsingCTab& T, int i, int j, int k, int q) {     // 1-based
+    const double xj = T.NX[j - 1], xk = T.NX2[k - 1];
+    const double* xl = T.XL + (i - 1); const double* xr = T.XR + (q - 1);
+    double wk = T.PWK[i - 1], w = T.PWW[i - 1];
+    double vk = T.SVK[q - 1], vv = T.SVV[q - 1];
+    wk = wk * xj; w = w + wk;
+    vk = vk * xk; vv = vv + vk;
+    wk = wk * xk; w = w + wk;
+    vk = vk * xj; vv = vv + vk;
+#pragma unroll 4
+    for (int t = 0; t < T.nr; ++t) { wk = wk * xr[t * T.rr]; w = w + wk; }
+#pragma unroll 4
+    for (int t = T.nl - 1; t >= 0; --t) { vk = vk * xl[t * T.rl]; vv = vv + vk; }
+    const double b = 1.0 / (vv * w);
+    double f = 2 * b;
+    const double* wl = T.WL + (i - 1); const double* wr = T.WR + (q - 1);
+#pragma unroll 4
+    for (int t = 0; t < T.nl; ++t) f = f * wl[t * T.rl];
+    f = f * T.NW[j - 1];
+    f = f * T.NW2[k - 1];
+#pragma unroll 4
+    for (int t = 0; t < T.nr; ++t) f = f * wr[t * T.rr];
+    return f;
+}
+// residuals with ALL factor values of the first 32 terms in flight before the evaluation starts (one L2 round trip per
+// element instead of one per batch); same operations in the same order as resid_axpy / resid_dot / resid_ddot2
+constexpr int RPF = 32;
+struct PrefF { double a[RPF]; };
+__device__ __forceinline__ void pref_loadf(PrefF& pf, const double* base, i64 stride, int r) {
+#pragma unroll
+    for (int u = 0; u < RPF; ++u) pf.a[u] = LDF(base + min(u, r - 1) * stride);   // clamped, never predicated
+}
+__device__ __forceinline__ double resid_axpy_pff(double f, const PrefF& pf, const double* base, i64 stride, const double* xs, int r) {
+    double res = f;
+#pragma unroll
+    for (int u = 0; u < RPF; ++u) if (u < r) res = res + (-xs[u]) * pf.a[u];
+    for (int s0 = RPF; s0 < r; s0 += RP) {
+        double a[RP];
+#pragma unroll
+        for (int u = 0; u < RP; ++u) a[u] = LDF(base + min(s0 + u, r - 1) * stride);
+#pragma unroll
+        for (int u = 0; u < RP; ++u) if (s0 + u < r) res = res + (-xs[s0 + u]) * a[u];
+    }
+    return res;
+}
+__device__ __forceinline__ double resid_dot_pff(double f, const PrefF& pf, const double* base, i64 stride, const double* xs, int r) {
+    double t = 0.0;
+#pragma unroll
+    for (int u = 0; u < RPF; ++u) if (u < r) t = t + pf.a[u] * xs[u];
+    for (int s0 = RPF; s0 < r; s0 += RP) {
+        double a[RP];
+#pragma unroll
+        for (int u = 0; u < RP; ++u) a[u] = LDF(base + min(s0 + u, r - 1) * stride);
+#pragma unroll
+        for (int u = 0; u < RP; ++u) if (s0 + u < r) t = t + a[u] * xs[s0 + u];
+    }
+    return f + (-t);
+}
+
+// Everything a cluster needs to run the bond visits of one sweep: the cluster's shared exchange area, the carved-up dynamic
+// shared memory, and the partition's geometry.  rkL / rkR are the sweep-start ranks of the two foreign bonds next to the
+// partition (lo-1 and hi): the per-sweep kernel reads them from the snapshot P.rks, the persistent kernel (ttc_sweep.cuh)
+// tracks them itself.
+struct VisitCtx {
+    VisitShared* sh;
+    const double* A; double* xs; double* pre; double* ext; double* stg; int* ibuf;   // pre: 4 Rmax doubles (ising_c_prepare)
+    int v, lo, hi, rkL, rkR;
+    int phase;                 // parity counter of cluster_fold
+    int upd_first, upd_last;   // out: was the partition's first / last bond updated in this sweep (uniform over the cluster)
+};
 template <int KIND>
-__global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_visits(DevPlan P, int dir, double small_element, double small_pivot, int fold_allreduce, int close_maxrank) {
-    tl_stamp(P, 40);
-    if (LDF(&P.ctrl->ready)) return;          // uniform over the grid: written only by k_sweep_log
-    cg::cluster_group cl = cg::this_cluster();
-    extern __shared__ double smem[];
-    __shared__ VisitShared sh;
+__device__ __forceinline__ void visit_list(const DevPlan& P, cg::cluster_group& cl, VisitCtx& C, int it, int dir, double small_element, double small_pivot) {
+    VisitShared& sh = *C.sh;
     const int crank = (int)cl.block_rank(), cs = (int)cl.num_blocks();
-    const int v = P.v0 + blockIdx.y;
-    const int lo = P.own[v], hi = P.own[v + 1], nb = hi - lo;
-    const int it = P.ctrl->it;
+    const int v = C.v, lo = C.lo, hi = C.hi, nb = hi - lo;
     const int gtid = crank * blockDim.x + threadIdx.x, gthreads = cs * blockDim.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const double* A = stage_aux<KIND>(P, smem);
-    double* xs = smem + P.auxsm;
-    double* ext = xs + P.Rmax;
-    double* stg = ext + (i64)P.Rmax * P.Rmax + P.Rmax;
-    int* ibuf = (int*)(stg + P.stage_max);
-    if (threadIdx.x == 0) sh.S = P.st[v];
-    int phase = 0;
+    const double* A = C.A;
+    double* xs = C.xs; double* ext = C.ext; double* stg = C.stg; int* ibuf = C.ibuf;
+    int& phase = C.phase;
     double* fa_c = P.acol1 + (i64)v * P.Rmax * P.nmax; double* fb_c = P.bcol1 + (i64)v * P.Rmax * P.nmax;
     double* fa_r = P.arow1 + (i64)v * P.Rmax * P.nmax; double* fb_r = P.brow1 + (i64)v * P.Rmax * P.nmax;
+    C.upd_first = 0; C.upd_last = 0;
 
     for (int pp = 1; pp <= nb; ++pp) {
         const int p = (dir == 1) ? lo + pp - 1 : hi - pp;
         if (threadIdx.x == 0) {
-            sh.r0 = (p - 1 >= lo) ? LDF(P.rk + p - 1) : P.rks[p - 1];
+            sh.r0 = (p - 1 >= lo) ? LDF(P.rk + p - 1) : C.rkL;
             sh.r1 = LDF(P.rk + p);
-            sh.r2 = (p + 1 <= hi - 1) ? LDF(P.rk + p + 1) : P.rks[p + 1];
+            sh.r2 = (p + 1 <= hi - 1) ? LDF(P.rk + p + 1) : C.rkR;
         }
         __syncthreads();
         const int r0 = sh.r0, r1 = sh.r1, r2 = sh.r2, n1 = P.n[p], n2 = P.n[p + 1];
         const Stage S = stage_bond_cg(P, stg, p - 1, r0, p, p + 1, p + 1, r2);
+        constexpr bool fastc = (KIND == KIND_ISINGC);                      // streaming evaluation of Ising C
+        IsingCTab TC;
+        if (fastc) TC = ising_c_prepare(S, C.pre, P.Rmax);
         tl_mark(P, 41);
         const double* colp = P.col + P.coreOff[p];
         const double* rowp = P.rowT + P.coreOff[p + 1];
@@ -433,8 +531,9 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_
                 if (!live || side) continue;
                 const int c = cell;
                 const int i = (c - 1) % r0 + 1, j = (c - 1) / r0 + 1, k = (w - 1) % n2 + 1, q = (w - 1) / n2 + 1;
-                StagedVals sv = S.point(i, j, k, q);
-                const double f = eval_point<KIND>(P, sv, A);
+                double f;
+                if (fastc) f = ising_c_eval(TC, i, j, k, q);
+                else { StagedVals sv = S.point(i, j, k, q); f = eval_point<KIND>(P, sv, A); }
                 tl_mark(P, 56);
                 const double res = resid_ddot2_cg(f, colp + (i - 1) + (i64)P.Rmax * (j - 1), cs_, rowp + (k - 1) + (i64)n2 * (q - 1), rs_, r1);
                 braw = fmax(braw, fabs(f));
@@ -484,6 +583,22 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_
             double braw = -1.0;
             for (int e = gtid; e < count; e += gthreads) {
                 double f, res;
+                if (fastc) {
+                    PrefF pf;
+                    if (!isrow) {
+                        const int j = e / r0 + 1, i = e % r0 + 1;
+                        const double* base = colp + (i - 1) + (i64)P.Rmax * (j - 1);
+                        pref_loadf(pf, base, cs_, r1);
+                        f = ising_c_eval(TC, i, j, kk, qq);
+                        res = resid_axpy_pff(f, pf, base, cs_, xs, r1);
+                    } else {
+                        const int q = e / n2 + 1, k = e % n2 + 1;
+                        const double* base = rowp + (k - 1) + (i64)n2 * (q - 1);
+                        pref_loadf(pf, base, rs_, r1);
+                        f = ising_c_eval(TC, ii, jj, k, q);
+                        res = resid_dot_pff(f, pf, base, rs_, xs, r1);
+                    }
+                } else {
                 Pref pf;
                 if (!isrow) {
                     const int j = e / r0 + 1, i = e % r0 + 1;
@@ -499,6 +614,7 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_
                     StagedVals sv = S.point(ii, jj, k, q);
                     f = eval_point<KIND>(P, sv, A);
                     res = resid_dot_pf(f, pf, base, rs_, xs, r1);
+                }
                 }
                 fa[e] = f;
                 fb[e] = res;
@@ -633,6 +749,8 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_
                 }
             }
             if (crank == 0 && threadIdx.x == 0) P.rk[p] = r1 + 1;
+            if (p == lo) C.upd_first = 1;
+            if (p == hi - 1) C.upd_last = 1;
         }
         tl_mark(P, 49);
         cl.sync();          // the next visit of this cluster (Gauss-Seidel, dmrgg.f90:329-331) sees everything written above
@@ -643,6 +761,38 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_
             O.active = 0; O.upd = 0;
         }
     }
+}
+
+constexpr int VISIT_MAXTHREADS = 256;
+// MVN evaluations are one long dependent DADD chain each (3 d^2 operations, one accumulator, mvn_pdf.f90:74-80): what
+// hides the latency is resident warps, not registers -> 64 registers per thread.  (Measured on config E: the
+// register-resident eval_mvn_reg makes one evaluation 2.3x faster, 133 us instead of 300 us, but needs 255 registers =
+// one CTA per SM, and 63 clusters then run in four waves instead of two: 86 ms instead of 59 ms.  It is used where a
+// single evaluation is the critical path: the corner fibers of the exchange.)
+template <int KIND>
+__global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 2) k_visits(DevPlan P, int dir, double small_element, double small_pivot, int fold_allreduce, int close_maxrank) {
+    tl_stamp(P, 40);
+    if (LDF(&P.ctrl->ready)) return;          // uniform over the grid: written only by k_sweep_log
+    cg::cluster_group cl = cg::this_cluster();
+    extern __shared__ double smem[];
+    __shared__ VisitShared sh;
+    const int crank = (int)cl.block_rank();
+    VisitCtx C;
+    C.sh = &sh;
+    C.v = P.v0 + blockIdx.y;
+    C.lo = P.own[C.v]; C.hi = P.own[C.v + 1];
+    C.rkL = P.rks[C.lo - 1]; C.rkR = P.rks[C.hi];
+    C.A = stage_aux<KIND>(P, smem);
+    C.xs = smem + P.auxsm;
+    C.pre = C.xs + P.Rmax;
+    C.ext = C.pre + 4 * (i64)P.Rmax;
+    C.stg = C.ext + (i64)P.Rmax * P.Rmax + P.Rmax;
+    C.ibuf = (int*)(C.stg + P.stage_max);
+    C.phase = 0;
+    const int v = C.v;
+    const int it = P.ctrl->it;
+    if (threadIdx.x == 0) sh.S = P.st[v];
+    visit_list<KIND>(P, cl, C, it, dir, small_element, small_pivot);
     if (close_maxrank > 0) {
         // ---- single partition: this cluster is the whole sweep; close it here (no exchange, no reduction)
         if (crank == 0 && threadIdx.x == 0) P.st[v] = sh.S;
