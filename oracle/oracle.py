@@ -87,6 +87,7 @@ def lib():
         L.tto_num_threads.restype = C.c_int
         L.tto_set_num_threads.argtypes = [C.c_int]
         L.tto_set_exp_mode.argtypes = [C.c_void_p, C.c_int]
+        L.tto_set_rank_concurrency.argtypes = [C.c_int]
         _lib = L
     return _lib
 

@@ -59,6 +59,8 @@
 #include "../include/ttc_detexp.h"   // the deterministic exp both sides use in parity mode (a product header; the product never includes oracle/)
 
 namespace {
+double g_visit_seconds = 0;      // time spent in the bond visits (the part the ranks run concurrently), for tto_visit_seconds
+int g_rank_concurrency = 1;     // tto_set_rank_concurrency: 0 runs the virtual ranks one after another
 
 using i64 = long long;
 using u64 = unsigned long long;
@@ -644,6 +646,16 @@ int run(Oracle& O, const RunArgs& A) {
         res.pivotmaxs.push_back(-1); res.eranks.push_back(report_erank()); res.times.push_back(t2);
     }
 
+    // thread budget: ranks side by side, the rest of the threads inside each rank (nested teams)
+    int outer_nt = 1, inner_nt = 1;
+#ifdef _OPENMP
+    {
+        const int T = omp_get_max_threads();
+        outer_nt = g_rank_concurrency ? std::max(1, std::min(nproc, T)) : 1;
+        inner_nt = std::max(1, T / outer_nt);
+        if (outer_nt > 1 && inner_nt > 1) omp_set_max_active_levels(2);
+    }
+#endif
     // ---- main loop (dmrgg.f90:309-1020)
     int it = 0, strike = 0;
     bool ready = false;
@@ -654,6 +666,13 @@ int run(Oracle& O, const RunArgs& A) {
         int dir = 2 - it % 2;
         const char* sdir = dir == 1 ? ">>" : "<<";
 
+        // The virtual ranks of a sweep are independent (Jacobi: each works on its own Rank object with the index sets of the
+        // sweep start, dmrgg.f90:325-331) and the reference runs them as concurrent MPI ranks, each with its own OpenMP team
+        // (README.md:20-21).  Same here: `outer` ranks at a time, `inner_nt` threads for a rank's evaluation loops.  The pivot
+        // records are merged in rank order afterwards, so the result does not depend on the thread count.
+        std::vector<std::vector<PivRec>> plog(nproc);
+        const auto tv0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(outer_nt) if (outer_nt > 1)
         for (int me = 0; me < nproc; ++me) {
             Rank& K = R[me];
             std::vector<int>& r = K.r;
@@ -673,7 +692,7 @@ int run(Oracle& O, const RunArgs& A) {
                     // full pivoting (dmrgg.f90:341-408)
                     const i64 tot = (i64)r0 * n1 * n2 * r2;
                     std::vector<double> a(tot), b(tot);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(inner_nt)
                     for (i64 x = 1; x <= tot; ++x) {
                         i64 i = x - 1;
                         i64 q = i / ((i64)r0 * n1 * n2); i = i % ((i64)r0 * n1 * n2);
@@ -718,7 +737,7 @@ int run(Oracle& O, const RunArgs& A) {
                         lot[2 * nlot + x] = (w - 1) % n2 + 1;  // k
                         lot[3 * nlot + x] = (w - 1) / n2 + 1;  // q
                     }
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(inner_nt)
                     for (int x = 0; x < nlot; ++x)
                         b[x] = dmrgg_fun(prob, lot[x], lot[nlot + x], lot[2 * nlot + x], lot[3 * nlot + x], p, l, m, K.vip);
                     K.nevalloc += nlot;
@@ -734,12 +753,12 @@ int run(Oracle& O, const RunArgs& A) {
 
                     bool done = false, havecol = false, haverow = false;
                     if (piv == 0) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(inner_nt)
                         for (int ij = 0; ij < r0 * n1; ++ij) {
                             int j = ij / r0 + 1, i = ij % r0 + 1;
                             acol1[ij] = dmrgg_fun(prob, i, j, kk, qq, p, l, m, K.vip);
                         }
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(inner_nt)
                         for (int kq = 0; kq < n2 * r2; ++kq) {
                             int q = kq / n2 + 1, k = kq % n2 + 1;
                             arow1[kq] = dmrgg_fun(prob, ii, jj, k, q, p, l, m, K.vip);
@@ -751,7 +770,7 @@ int run(Oracle& O, const RunArgs& A) {
                     bool skipcol = (dir == 2);
                     while (!done) {
                         if (!skipcol) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(inner_nt)
                             for (int ij = 0; ij < r0 * n1; ++ij) {
                                 int j = ij / r0 + 1, i = ij % r0 + 1;
                                 acol1[ij] = dmrgg_fun(prob, i, j, kk, qq, p, l, m, K.vip);
@@ -773,7 +792,7 @@ int run(Oracle& O, const RunArgs& A) {
                         }
                         skipcol = false;
                         if (!done) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(inner_nt)
                             for (int kq = 0; kq < n2 * r2; ++kq) {
                                 int q = kq / n2 + 1, k = kq % n2 + 1;
                                 arow1[kq] = dmrgg_fun(prob, ii, jj, k, q, p, l, m, K.vip);
@@ -799,7 +818,7 @@ int run(Oracle& O, const RunArgs& A) {
                 // accept test + update (dmrgg.f90:598-758)
                 K.tape[p] = {-1, -1, -1, -1};
                 K.upd[p] = (std::fabs(pivot) > small_element * K.amax) && (std::fabs(pivot) > small_pivot * K.pivotmax_prev);
-                res.pivlog.push_back({it, me, p, ii, jj, kk, qq, (int)K.upd[p], pivot});
+                plog[me].push_back({it, me, p, ii, jj, kk, qq, (int)K.upd[p], pivot});
 
                 if (K.upd[p]) {
                     K.tape[p] = {ii, jj, kk, qq};
@@ -864,6 +883,8 @@ int run(Oracle& O, const RunArgs& A) {
                 }
             }  // own bonds
         }      // ranks
+        for (int me = 0; me < nproc; ++me) res.pivlog.insert(res.pivlog.end(), plog[me].begin(), plog[me].end());
+        g_visit_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - tv0).count();
 
         if (nproc > 1) {
             // ---- tape propagation (dmrgg.f90:763-850), sendrecv semantics
@@ -905,6 +926,7 @@ int run(Oracle& O, const RunArgs& A) {
                         msg[me].assign(src, src + cnt);
                     }
                 }
+#pragma omp parallel for schedule(dynamic, 1) num_threads(outer_nt) if (outer_nt > 1)     // receivers are independent (the messages are pre-exchange copies)
                 for (int me = 0; me < nproc - 1; ++me) {
                     Rank& K = R[me]; const std::vector<int>& r = K.r; const std::vector<int>& rr = K.rr;
                     int p = own[me + 1] - 1;
@@ -919,7 +941,7 @@ int run(Oracle& O, const RunArgs& A) {
                     K.arg[p + 1] = na;
                     if (K.upd[p]) {
                         int ii = K.vip[p][r[p] - 1][0], jj = K.vip[p][r[p] - 1][1];
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(inner_nt)
                         for (int k = 1; k <= N(p + 1); ++k)
                             K.arg[p + 1].at(r[p], k, r[p + 1]) = dmrgg_fun(prob, ii, jj, k, r[p + 1], p, l, m, K.vip);
                         for (int k = 1; k <= N(p + 1); ++k) K.amax = std::max(K.amax, std::fabs(K.arg[p + 1].at(r[p], k, r[p + 1])));
@@ -945,6 +967,7 @@ int run(Oracle& O, const RunArgs& A) {
                         for (size_t x = 0; x < cnt; ++x) msg[me][x] = src[x * (size_t)K.r[q]];
                     }
                 }
+#pragma omp parallel for schedule(dynamic, 1) num_threads(outer_nt) if (outer_nt > 1)
                 for (int me = 1; me < nproc; ++me) {
                     Rank& K = R[me]; const std::vector<int>& r = K.r; const std::vector<int>& rr = K.rr;
                     int p = own[me];
@@ -960,7 +983,7 @@ int run(Oracle& O, const RunArgs& A) {
                     K.arg[p] = na;
                     if (K.upd[p]) {
                         int kk = K.vip[p][r[p] - 1][2], qq = K.vip[p][r[p] - 1][3];
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(inner_nt)
                         for (int j = 1; j <= N(p); ++j)
                             K.arg[p].at(r[p - 1], j, r[p]) = dmrgg_fun(prob, r[p - 1], j, kk, qq, p, l, m, K.vip);
                         for (int j = 1; j <= N(p); ++j) K.amax = std::max(K.amax, std::fabs(K.arg[p].at(r[p - 1], j, r[p])));
@@ -991,6 +1014,7 @@ int run(Oracle& O, const RunArgs& A) {
         if (has_quad) {
             std::vector<std::vector<Core>> ttqq(nproc, std::vector<Core>(m + 1));
             std::vector<std::vector<Core>*> ptr(nproc);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(outer_nt) if (outer_nt > 1)     // every rank contracts its own cores
             for (int me = 0; me < nproc; ++me) {
                 Rank& K = R[me];
                 int first = own[me], last = own[me + 1] - 1; if (me == nproc - 1) last = m;
@@ -1069,6 +1093,8 @@ void* tto_create(int kind, int d, const int* n, const double* par, long npar, co
     return O;
 }
 void tto_destroy(void* h) { delete (Oracle*)h; }
+void tto_set_rank_concurrency(int on) { g_rank_concurrency = on; }
+double tto_visit_seconds(int reset) { double v = g_visit_seconds; if (reset) g_visit_seconds = 0; return v; }
 void tto_set_exp_mode(void* h, int mode) { ((Oracle*)h)->prob.exp_mode = mode; }
 
 // quad: concatenated weight vectors sum(n) doubles, or NULL.  own: P+1 ints or NULL.

@@ -127,6 +127,17 @@ struct DevPlan {
     unsigned long long* tlog; int* tlog_n; int tlog_cap;
     // persistent sweep kernel (ttc_sweep.cuh): one mailbox per partition (inside the peer window when there are several processes)
     struct SweepMail* mail; long long win_mail;
+    // several processes: what the neighbour processes push after their bond visits (double-buffered by sweep parity), and the
+    // log / chain-product areas every process pushes into every window.  All are byte offsets inside a window.
+    //   slab_l[par]: from the LEFT  process: new row of the shared core [nmax * Rmax] | L-table column [d ints] | packed-LU row [2 Rmax + 1]
+    //   slab_r[par]: from the RIGHT process: new slice of the shared core [Rmax * nmax] | R-table column [d ints]
+    long long win_sl, win_sr, slab_l_bytes, slab_r_bytes, win_vlog, win_rklog, win_chs;
+    double* chainS;        // [maxsweeps][P + 1][Rmax^2] chain products of the per-sweep quadrature after the loop
+    // VALUE tables of the persistent kernel: node value (and Ising weight) of every entry of Lidx / Ridx, same row structure with
+    // an even leading dimension RT (16-byte rows), so that the evaluation inputs of a bond visit are plain contiguous blocks
+    // that the TMA copies into shared memory (cp.async.bulk) instead of a gather through the index tables; parT = nodes | weights,
+    // each padded to NT (even) entries.  Null when the persistent kernel is not in use.
+    double* XLg; double* WLg; double* XRg; double* WRg; const double* parT; int RT, NT;
     int exp_mode;          // 0: platform exp; 1: the deterministic exp of include/ttc_detexp.h (parity mode, ttc_set_exp_mode)
 };
 __device__ __forceinline__ double plan_exp(const DevPlan& P, double x) { return P.exp_mode ? ttc_det_exp(x) : exp(x); }

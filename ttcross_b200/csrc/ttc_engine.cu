@@ -277,11 +277,15 @@ void window_teardown(ttc_handle* h) {
     h->p2p = false;
 }
 // one window per rank: mb1_recv | mb2_recv | nb_recv_l | nb_recv_r | flags; IPC handles travel by NCCL all-gather
-int window_setup(ttc_handle* h, size_t w1, size_t w2, size_t slab, size_t rowinv) {
+int window_setup(ttc_handle* h, size_t w1, size_t w2, size_t slab, size_t rowinv, size_t vlog_bytes, size_t rklog_bytes, size_t chs_bytes) {
     DevPlan& D = h->plan;
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t o1 = 0, o2 = o1 + al(w1 * h->nproc * 8), o3 = o2 + al(w2 * h->nproc * 8), o4 = o3 + al(rowinv * 8),
-                 o5 = o4 + al(slab * 8), tot = o5 + al(3 * (size_t)h->nproc * 8);
+                 o5 = o4 + al(slab * 8), o6 = o5 + al(3 * (size_t)h->nproc * 8);
+    // persistent sweep kernel (ttc_sweep.cuh): mailboxes | 2 slabs from the left | 2 slabs from the right | visit log | rank log | chain products
+    const size_t sl_b = al(((size_t)h->nmax * h->Rmax + h->d + 2 * (size_t)h->Rmax + 2) * 8), sr_b = al(((size_t)h->Rmax * h->nmax + h->d) * 8);
+    const size_t o7 = o6 + al((size_t)h->P * sizeof(SweepMail)), o8 = o7 + 2 * sl_b, o9 = o8 + 2 * sr_b, o10 = o9 + al(vlog_bytes),
+                 o11 = o10 + al(rklog_bytes), tot = o11 + al(chs_bytes);
     CUDA_TRY(h, cudaMalloc((void**)&h->win, tot));
     h->win_bytes = tot;
     CUDA_TRY(h, cudaMemsetAsync(h->win, 0, tot, h->stream));
@@ -289,6 +293,10 @@ int window_setup(ttc_handle* h, size_t w1, size_t w2, size_t slab, size_t rowinv
     D.mb1_recv = (unsigned long long*)(h->win + o1); D.mb2_recv = (double*)(h->win + o2);
     D.nb_recv_l = (double*)(h->win + o3); D.nb_recv_r = (double*)(h->win + o4);
     D.win_flags = (unsigned long long*)(h->win + o5);
+    D.win_mail = (long long)o6; D.win_sl = (long long)o7; D.win_sr = (long long)o8; D.slab_l_bytes = (long long)sl_b; D.slab_r_bytes = (long long)sr_b;
+    D.win_vlog = (long long)o9; D.win_rklog = (long long)o10; D.win_chs = (long long)o11;
+    D.mail = (SweepMail*)(h->win + o6);
+    D.vlog = (VisitOut*)(h->win + o9); D.rklog = (int*)(h->win + o10); D.chainS = (double*)(h->win + o11);
     cudaIpcMemHandle_t mine;
     CUDA_TRY(h, cudaIpcGetMemHandle(&mine, h->win));
     char* dh = nullptr;
@@ -434,6 +442,12 @@ int setup_device(ttc_handle* h, int maxrank) {
         h->plan.piv = h->piv;
         if (h->par_dirty) {
             CUDA_TRY(h, cudaMemcpyAsync(const_cast<double*>(h->plan.par), h->par.data(), h->par.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            if (h->plan.parT) {             // the padded copy the TMA staging reads
+                const int NT = h->plan.NT;
+                CUDA_TRY(h, cudaMemcpyAsync(const_cast<double*>(h->plan.parT), h->par.data(), std::min<size_t>(h->nmax, h->par.size()) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+                if (h->kind == TTC_ISING)
+                    CUDA_TRY(h, cudaMemcpyAsync(const_cast<double*>(h->plan.parT) + NT, h->par.data() + h->n[1], (size_t)h->nmax * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            }
             h->par_dirty = false;
         }
         CUDA_TRY(h, cudaMemcpyAsync(const_cast<double*>(h->plan.quadw), h->quad_or_ones().data(), h->quad_or_ones().size() * sizeof(double),
@@ -482,7 +496,8 @@ int setup_device(ttc_handle* h, int maxrank) {
     }
     // shared-memory staging of node/weight values (left + right tables of a bond visit hold d-2 positions in total)
     {
-        const size_t stage_d = 4 * (size_t)h->nmax + 2 * (size_t)std::max(0, d - 2) * Rmax;
+        // (sized for the TMA layout of the persistent kernel: vectors padded to an even length NT, table rows to an even RT)
+        const size_t stage_d = 4 * (size_t)((h->nmax + 1) & ~1) + 2 * (size_t)std::max(0, d - 2) * ((Rmax + 1) & ~1);
         const size_t need = ((size_t)D.auxsm + Rmax + stage_d) * sizeof(double) + (size_t)(3 * Rmax + 8) * sizeof(int);
         D.stage = (need <= 200 * 1024 && !h->force_simple) ? 1 : 0;
         D.stage_max = D.stage ? (int)stage_d : 0;
@@ -583,7 +598,11 @@ int setup_device(ttc_handle* h, int maxrank) {
             D.mb1_send = s1; D.mb2_send = s2; D.nb_send_l = sl; D.nb_send_r = sr;
             h->mb1_bytes = w1 * 8; h->mb2_count = w2; h->nbl_send = slab; h->nbl_recv = rowinv;
             D.peer_win = nullptr; D.win_flags = nullptr;
-            int pe = std::getenv("TTC_MP_NCCL") ? TTC_ERR_COMM : window_setup(h, w1, w2, slab, rowinv);   // peer-memory windows (CUDA IPC)...
+            VisitOut* vlog_plain = D.vlog; int* rklog_plain = D.rklog;
+            int pe = std::getenv("TTC_MP_NCCL") ? TTC_ERR_COMM
+                                                : window_setup(h, w1, w2, slab, rowinv, (size_t)Rmax * maxnb0 * P * sizeof(VisitOut), (size_t)(Rmax + 1) * (d + 1) * sizeof(int),
+                                                               (size_t)Rmax * (P + 1) * Rmax * Rmax * sizeof(double));   // peer-memory windows (CUDA IPC)...
+            if (pe) { D.vlog = vlog_plain; D.rklog = rklog_plain; D.chainS = nullptr; D.mail = nullptr; }
             if (pe) {                                                                                    // ...or NCCL receive buffers
                 if (h->win) { cudaFree(h->win); h->win = nullptr; }
                 h->p2p = false; D.peer_win = nullptr; D.win_flags = nullptr;
@@ -645,7 +664,7 @@ int setup_device(ttc_handle* h, int maxrank) {
         else { h->cluster_size = 8; h->cluster_threads = 256; }
         if (const char* e = std::getenv("TTC_CLUSTER_SIZE")) h->cluster_size = std::atoi(e);
         if (const char* e = std::getenv("TTC_CLUSTER_THREADS")) h->cluster_threads = std::atoi(e);
-        h->sm_visit = ((size_t)D.auxsm + 5 * (size_t)Rmax + (size_t)Rmax * Rmax + Rmax + D.stage_max) * sizeof(double) + (size_t)(4 * Rmax + 8) * sizeof(int);
+        h->sm_visit = ((size_t)D.auxsm + 5 * (size_t)Rmax + (size_t)Rmax * Rmax + Rmax + D.stage_max + 2) * sizeof(double) + (size_t)(4 * Rmax + 8) * sizeof(int);
         h->cluster_ok = D.stage && h->use_wave && h->sm_visit <= 200 * 1024 && h->cluster_size >= 1 && h->cluster_size <= MAXCS && h->cluster_threads >= 32 &&
                         h->cluster_threads <= VISIT_MAXTHREADS && h->cluster_threads % 32 == 0 &&
                         !std::getenv("TTC_NO_CLUSTER");
@@ -676,11 +695,13 @@ int setup_device(ttc_handle* h, int maxrank) {
     }
     // persistent sweep kernel: same cluster shape and shared memory; every cluster must be resident at once (cooperative launch)
     {
-        SweepMail* dmail = nullptr;
-        { int s1 = dev_alloc(h, &dmail, (size_t)P); if (s1) return s1; }
-        D.mail = dmail; D.win_mail = 0;
+        if (!h->p2p) {                 // one process (or the NCCL transport, which keeps the per-sweep schedule): plain allocations
+            SweepMail* dmail = nullptr;
+            { int s1 = dev_alloc(h, &dmail, (size_t)P); if (s1) return s1; }
+            D.mail = dmail; D.win_mail = 0; D.chainS = nullptr;
+        }
         h->persist_ok = false;
-        if (h->cluster_ok && !std::getenv("TTC_NO_PERSISTENT")) {
+        if (h->cluster_ok && (h->nproc == 1 || h->p2p) && !std::getenv("TTC_NO_PERSISTENT")) {
             cudaError_t ce = cudaSuccess;
             VISIT_KIND_SWITCH(h,
                 ce = cudaFuncSetAttribute(k_sweeps<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_visit);
@@ -699,9 +720,22 @@ int setup_device(ttc_handle* h, int maxrank) {
             if (ce != cudaSuccess) (void)cudaGetLastError();
         }
         if (h->persist_ok) {
-            double* dcs = nullptr;
-            int s1 = dev_alloc(h, &dcs, (size_t)Rmax * (P + 1) * Rmax * Rmax, false); if (s1) return s1;
-            h->chainS = dcs;
+            if (!h->p2p) {
+                double* dcs = nullptr;
+                int s1 = dev_alloc(h, &dcs, (size_t)Rmax * (P + 1) * Rmax * Rmax, false); if (s1) return s1;
+                D.chainS = dcs;
+            }
+            h->chainS = D.chainS;
+            // value tables + padded node / weight vectors for the TMA staging (ttc_visit.cuh)
+            D.RT = (Rmax + 1) & ~1; D.NT = (h->nmax + 1) & ~1;
+            const size_t tl = (size_t)(accL / Rmax) * D.RT + 2, tr = (size_t)(accR / Rmax) * D.RT + 2;
+            double *xl = nullptr, *wl = nullptr, *xr = nullptr, *wr = nullptr, *pt = nullptr;
+            if (dev_alloc(h, &xl, tl) || dev_alloc(h, &wl, tl) || dev_alloc(h, &xr, tr) || dev_alloc(h, &wr, tr)) return TTC_ERR_CUDA;
+            std::vector<double> ptv(2 * (size_t)D.NT, 0.0);
+            for (int x = 0; x < h->nmax && x < (int)h->par.size(); ++x) ptv[x] = h->par[x];
+            if (h->kind == TTC_ISING) for (int x = 0; x < h->nmax; ++x) ptv[D.NT + x] = h->par[h->n[1] + x];
+            if (dev_upload(h, &pt, ptv)) return TTC_ERR_CUDA;
+            D.XLg = xl; D.WLg = wl; D.XRg = xr; D.WRg = wr; D.parT = pt;
             cudaFuncSetAttribute(k_quad_lua_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_lua);
             cudaFuncSetAttribute(k_quad_chain_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_mat3);
             cudaFuncSetAttribute(k_quad_tree_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_mat3);
@@ -977,7 +1011,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     tr.lap("init_search+tables");
     // the whole sweep loop as one persistent cooperative kernel (ttc_sweep.cuh) whenever the cluster kernel applies and every
     // cluster of this process is resident at once; TTC_NO_PERSISTENT=1 keeps the per-sweep schedule (graphs of k_visits + ...)
-    const bool persistent = h->persist_ok && h->cluster_ok && h->nproc == 1 && !h->ucb && !h->verbose && !h->force_sync && !h->force_host_lottery &&
+    const bool persistent = h->persist_ok && h->cluster_ok && (h->nproc == 1 || h->p2p) && !h->ucb && !h->verbose && !h->force_sync && !h->force_host_lottery &&
                             h->piv >= 0 && !h->force_split && !h->profile && h->use_wave;
     // ---- initial cross fibers and factors (dmrgg.f90:220-248)
     KIND_SWITCH(h->kind, L(KC_INIT, [&] { k_init_cross<K><<<dim3(cdiv(h->nmax, TB), d), TB, smA, s>>>(D); }));

@@ -62,6 +62,13 @@ __device__ __forceinline__ unsigned long long ld_acquire(const unsigned long lon
     else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+template <class T>
+__device__ __forceinline__ T* peer_ptr(const DevPlan& P, int g, long long off) { return (T*)(P.peer_win[g] + off); }
+__device__ __forceinline__ int proc_of(const DevPlan& P, int v) {        // the process that runs partition v (block map)
+    int g = 0;
+    while (g + 1 < P.nproc && proc_v0(P.P, P.nproc, g + 1) <= v) ++g;
+    return g;
+}
 // bounded spin: a lost partner becomes ctrl->error = 3 (TTC_ERR_COMM) instead of a hang
 __device__ __forceinline__ void sweep_wait(const DevPlan& P, const unsigned long long* flag, unsigned long long seq, bool sys) {
     unsigned long long t0 = 0;
@@ -262,9 +269,10 @@ __global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 1)
 k_sweeps(DevPlan P, int it_last, int maxrank, double small_element, double small_pivot) {
     tl_stamp(P, 36);
     cg::cluster_group cl = cg::this_cluster();
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     __shared__ VisitShared sh;
     __shared__ SweepLocal sl;
+    __shared__ __align__(8) unsigned long long tma_bar;
     const int crank = (int)cl.block_rank();
     VisitCtx C;
     C.sh = &sh;
@@ -275,8 +283,10 @@ k_sweeps(DevPlan P, int it_last, int maxrank, double small_element, double small
     C.pre = C.xs + P.Rmax;
     C.ext = C.pre + 4 * (i64)P.Rmax;
     C.stg = C.ext + (i64)P.Rmax * P.Rmax + P.Rmax;
+    C.stg = (double*)(((unsigned long long)C.stg + 15ULL) & ~15ULL);          // TMA destinations are 16-byte aligned
     C.ibuf = (int*)(C.stg + P.stage_max);
     C.phase = 0;
+    C.bar = &tma_bar; C.bar_parity = 0;
     const int v = C.v, lo = C.lo, hi = C.hi;
     const bool multi = P.nproc > 1;
     SweepMail* mail = P.mail;
@@ -285,23 +295,84 @@ k_sweeps(DevPlan P, int it_last, int maxrank, double small_element, double small
         sh.S = P.st[v];
         sl.rkL = P.rk[lo - 1]; sl.rkR = P.rk[hi];
         sl.strike = 0; sl.ready = 0;
+        mbar_init(&tma_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    // value tables of the bonds this partition reads (lo-1 .. hi) from the index tables of the initial cross; neighbours
+    // write the same values into the bonds they share
+    {
+        const bool hasw = (P.kind == KIND_ISING);
+        const int nwoff = P.n[1];
+        const int gtid = crank * blockDim.x + threadIdx.x, gthreads = (int)cl.num_blocks() * blockDim.x;
+        for (int b = lo - 1; b <= hi; ++b) {
+            const int rb = P.rk[b];
+            const int* Lt = P.Lidx + P.offL[b]; const int* Rt = P.Ridx + P.offR[b];
+            const i64 oL = P.offL[b] / P.Rmax * P.RT, oR = P.offR[b] / P.Rmax * P.RT;
+            for (int x = gtid; x < b * rb; x += gthreads) {
+                const int pos = x / rb, t = x - pos * rb, idx = Lt[(i64)pos * P.Rmax + t];
+                P.XLg[oL + (i64)pos * P.RT + t] = P.par[idx - 1]; if (hasw) P.WLg[oL + (i64)pos * P.RT + t] = P.par[nwoff + idx - 1];
+            }
+            for (int x = gtid; x < (P.d - b) * rb; x += gthreads) {
+                const int pos = x / rb, t = x - pos * rb, idx = Rt[(i64)pos * P.Rmax + t];
+                P.XRg[oR + (i64)pos * P.RT + t] = P.par[idx - 1]; if (hasw) P.WRg[oR + (i64)pos * P.RT + t] = P.par[nwoff + idx - 1];
+            }
+        }
+        fence_proxy_async();
+        __threadfence();
+    }
+    cl.sync();
     int it = 1;
     for (; it <= it_last; ++it) {
         const int dir = 2 - (it & 1);                  // dmrgg.f90:317
         const int par = it & 1;
         const unsigned long long seq = seq0 + (unsigned long long)it;
         C.rkL = sl.rkL; C.rkR = sl.rkR;
-        visit_list<KIND>(P, cl, C, it, dir, small_element, small_pivot);      // ends with a cluster barrier
+        visit_list<KIND, true>(P, cl, C, it, dir, small_element, small_pivot);      // ends with a cluster barrier
 
+        // ---- several processes: the first / last partition of a process pushes what its foreign neighbour needs straight into
+        // that process's window over NVLink (the tape of dmrgg.f90:763-850 reduced to the one table column the neighbour will
+        // dereference, and the blocks of :872-958 / dmrggmp.f90:572-629), then fences at system scope
+        const bool edgeL = multi && v == P.v0 && P.prank > 0, edgeR = multi && v == P.v0 + P.nv - 1 && P.prank < P.nproc - 1;
+        if (edgeL || edgeR) {
+            const int gtid = crank * blockDim.x + threadIdx.x, gthreads = (int)cl.num_blocks() * blockDim.x;
+            if (edgeL && C.upd_first) {               // to the LEFT process: new slice of core lo, new column of the R table of bond lo
+                const int c = lo, n = P.n[c], rc = LDF(P.rk + c);
+                char* dstw = P.peer_win[P.prank - 1] + P.win_sr + (long long)par * P.slab_r_bytes;
+                double* dst = (double*)dstw;
+                const double* slab = P.arg + P.coreOff[c] + (i64)P.Rmax * n * (rc - 1);
+                for (int x = gtid; x < P.Rmax * n; x += gthreads) dst[x] = LDF(slab + x);
+                int* dcol = (int*)(dst + (i64)P.Rmax * P.nmax);
+                const int* Rt = P.Ridx + P.offR[c];
+                for (int pos = gtid; pos < P.d - c; pos += gthreads) dcol[pos] = LDF(Rt + (i64)pos * P.Rmax + (rc - 1));
+            }
+            if (edgeR && C.upd_last) {                // to the RIGHT process: new row of core hi, L-table column and packed-LU row of bond hi-1
+                const int c = hi, n = P.n[c], rc1 = LDF(P.rk + c - 1), rq = sl.rkR;
+                char* dstw = P.peer_win[P.prank + 1] + P.win_sl + (long long)par * P.slab_l_bytes;
+                double* dst = (double*)dstw;
+                const double* a = P.arg + P.coreOff[c] + (rc1 - 1);
+                for (int x = gtid; x < n * rq; x += gthreads) dst[x] = LDF(a + (i64)P.Rmax * x);
+                int* dcol = (int*)(dst + (i64)P.nmax * P.Rmax);
+                const int* Lt = P.Lidx + P.offL[c - 1];
+                for (int pos = gtid; pos < c - 1; pos += gthreads) dcol[pos] = LDF(Lt + (i64)pos * P.Rmax + (rc1 - 1));
+                double* dlu = dst + (i64)P.nmax * P.Rmax + P.d;
+                const double* g = P.inv + (i64)(c - 1) * P.Rmax * P.Rmax + (i64)(rc1 - 1) * (rc1 - 1);
+                for (int x = gtid; x < 2 * (rc1 - 1) + 1; x += gthreads) dlu[x] = LDF(g + x);
+            }
+            __threadfence_system();
+            cl.sync();
+        }
         // ---- announce the bond visits: everything this cluster wrote is ordered before the flag (the cluster barrier
         // synchronises the writers with this thread, the release is cumulative)
-        if (crank == 0 && threadIdx.x == 0) {
-            sl.amax1 = sh.S.amax;
-            mail[v].upd1[par][0] = C.upd_first; mail[v].upd1[par][1] = C.upd_last;
-            __threadfence();
-            if (multi) st_release<true>(&mail[v].flag1, seq); else st_release<false>(&mail[v].flag1, seq);
+        if (crank == 0 && threadIdx.x < 3) {
+            // thread 0: this process's window; 1 / 2: the left / right process's window when the neighbour partition lives there
+            const int g = threadIdx.x == 0 ? P.prank : (threadIdx.x == 1 ? P.prank - 1 : P.prank + 1);
+            const bool go = threadIdx.x == 0 || (threadIdx.x == 1 ? edgeL : edgeR);
+            if (go) {
+                SweepMail* mb = (multi ? peer_ptr<SweepMail>(P, g, P.win_mail) : mail) + v;
+                mb->upd1[par][0] = C.upd_first; mb->upd1[par][1] = C.upd_last;
+                if (multi) { __threadfence_system(); st_release<true>(&mb->flag1, seq); }
+                else { __threadfence(); st_release<false>(&mb->flag1, seq); }
+            }
         }
         if (threadIdx.x == 0) sl.amax1 = sh.S.amax;
         tl_mark(P, 70);
@@ -317,8 +388,46 @@ k_sweeps(DevPlan P, int it_last, int maxrank, double small_element, double small
         }
         __syncthreads();
         tl_mark(P, 71);
-        // ---- this partition's half of the exchange on its two boundaries
         const int updL = sl.updL, updR = sl.updR;
+        if ((edgeL && updL) || (edgeR && updR)) {       // drop what the foreign neighbour pushed into place (uniform over the cluster)
+            const int gtid = crank * blockDim.x + threadIdx.x, gthreads = (int)cl.num_blocks() * blockDim.x;
+            if (edgeL && updL) {                        // from the LEFT process: new row of core lo | L column of bond lo-1 | packed-LU row of inv(lo-1)
+                const int c = lo, n = P.n[c], t = sl.rkL, rq = LDF(P.rk + c) - C.upd_first;      // the sender saw bond c at its sweep-start rank
+                const double* src = (const double*)((const char*)P.mail + (P.win_sl - P.win_mail) + (long long)par * P.slab_l_bytes);
+                double* a = P.arg + P.coreOff[c] + t;
+                for (int x = gtid; x < n * rq; x += gthreads) a[(i64)P.Rmax * x] = __ldcg(src + x);
+                const int* scol = (const int*)(src + (i64)P.nmax * P.Rmax);
+                int* Lt = P.Lidx + P.offL[c - 1];
+                const bool hasw = (P.kind == KIND_ISING); const int nwoff = P.n[1];
+                const i64 oL = P.offL[c - 1] / P.Rmax * P.RT;
+                for (int pos = gtid; pos < c - 1; pos += gthreads) {
+                    const int idx = __ldcg(scol + pos);
+                    Lt[(i64)pos * P.Rmax + t] = idx;
+                    P.XLg[oL + (i64)pos * P.RT + t] = P.par[idx - 1]; if (hasw) P.WLg[oL + (i64)pos * P.RT + t] = P.par[nwoff + idx - 1];
+                }
+                const double* slu = src + (i64)P.nmax * P.Rmax + P.d;
+                double* g = P.inv + (i64)(c - 1) * P.Rmax * P.Rmax + (i64)t * t;
+                for (int x = gtid; x < 2 * t + 1; x += gthreads) g[x] = __ldcg(slu + x);
+            }
+            if (edgeR && updR) {                        // from the RIGHT process: new slice of core hi | R column of bond hi
+                const int c = hi, n = P.n[c], t = sl.rkR, ri = LDF(P.rk + c - 1) - C.upd_last;   // the sender saw bond c-1 at its sweep-start rank
+                const double* src = (const double*)((const char*)P.mail + (P.win_sr - P.win_mail) + (long long)par * P.slab_r_bytes);
+                double* slab = P.arg + P.coreOff[c] + (i64)P.Rmax * n * t;
+                for (int x = gtid; x < P.Rmax * n; x += gthreads) { if (x % P.Rmax < ri) slab[x] = __ldcg(src + x); }
+                const int* scol = (const int*)(src + (i64)P.Rmax * P.nmax);
+                int* Rt = P.Ridx + P.offR[c];
+                const bool hasw = (P.kind == KIND_ISING); const int nwoff = P.n[1];
+                const i64 oR = P.offR[c] / P.Rmax * P.RT;
+                for (int pos = gtid; pos < P.d - c; pos += gthreads) {
+                    const int idx = __ldcg(scol + pos);
+                    Rt[(i64)pos * P.Rmax + t] = idx;
+                    P.XRg[oR + (i64)pos * P.RT + t] = P.par[idx - 1]; if (hasw) P.WRg[oR + (i64)pos * P.RT + t] = P.par[nwoff + idx - 1];
+                }
+            }
+            fence_proxy_async();
+            cl.sync();
+        }
+        // ---- this partition's half of the exchange on its two boundaries
         int ncorner = 0;
         BoundaryJob JA = {0, 1, lo, 0, 0, 0}, JB = {0, 0, hi, 0, 0, 0};
         if (v > 0) {                                    // RIGHT member of boundary v-1: core lo
@@ -339,12 +448,13 @@ k_sweeps(DevPlan P, int it_last, int maxrank, double small_element, double small
         }
         tl_mark(P, 72);
         // ---- publish the scalars, wait for everybody's
-        if (crank == 0 && threadIdx.x == 0) {
-            SweepRec& R = mail[v].rec[par];
+        if (crank == 0 && threadIdx.x < P.nproc) {     // one thread per destination window
+            SweepMail* mb = (multi ? peer_ptr<SweepMail>(P, threadIdx.x, P.win_mail) : mail) + v;
+            SweepRec& R = mb->rec[par];
             R.amax1 = sl.amax1; R.pivotmax = sh.S.pivotmax; R.pivotmin = sh.S.pivotmin;
             R.amax2 = sh.S.amax; R.neval = sh.S.neval; R.error = *(volatile int*)&P.ctrl->error; R.pad = 0;
-            __threadfence();
-            if (multi) st_release<true>(&mail[v].flag2, seq); else st_release<false>(&mail[v].flag2, seq);
+            if (multi) { __threadfence_system(); st_release<true>(&mb->flag2, seq); }
+            else { __threadfence(); st_release<false>(&mb->flag2, seq); }
         }
         for (int u = threadIdx.x; u < P.P; u += blockDim.x) {
             sweep_wait(P, &mail[u].flag2, seq, multi);
@@ -399,7 +509,35 @@ k_sweeps(DevPlan P, int it_last, int maxrank, double small_element, double small
     if (crank == 0 && threadIdx.x == 0) {
         P.st[v] = sh.S;
         if (v == P.v0) { P.ctrl->nsweeps = it; P.ctrl->it = it + 1; P.ctrl->strike = sl.strike; P.ctrl->ready = 1; }
-        if (multi) { P.rk[lo - 1] = sl.rkL; P.rk[hi] = sl.rkR; }      // (one process: the owners' own entries are the truth)
+    }
+    if (multi) {
+        // every process ends with the complete pivot tape and rank log (the reference's tape reaches every rank, dmrgg.f90:763-850):
+        // each partition pushes its records of all sweeps into every other window, then a last flag round
+        if (crank == 0) {
+            for (int g = 0; g < P.nproc; ++g) {
+                if (g == P.prank) continue;
+                VisitOut* dv = peer_ptr<VisitOut>(P, g, P.win_vlog);
+                int* dr = peer_ptr<int>(P, g, P.win_rklog);
+                const int nrec = it * P.maxnb;
+                for (int x = threadIdx.x; x < nrec * (int)(sizeof(VisitOut) / 8); x += blockDim.x) {
+                    const int rec = x / (int)(sizeof(VisitOut) / 8), w = x - rec * (int)(sizeof(VisitOut) / 8);
+                    const i64 idx = (i64)rec * P.P + v;
+                    ((unsigned long long*)(dv + idx))[w] = ((const unsigned long long*)(P.vlog + idx))[w];
+                }
+                const int nbo = hi - lo + (v == 0 ? 1 : 0) + (v == P.P - 1 ? 1 : 0), b0 = (v == 0) ? 0 : lo;
+                for (int x = threadIdx.x; x < it * nbo; x += blockDim.x) {
+                    const int sw = x / nbo + 1, bx = b0 + (x - (sw - 1) * nbo);
+                    dr[(i64)sw * (P.d + 1) + bx] = P.rklog[(i64)sw * (P.d + 1) + bx];
+                }
+            }
+            __threadfence_system();
+            __syncthreads();
+            const unsigned long long seqf = seq0 + 65535ULL;
+            if (threadIdx.x < P.nproc) st_release<true>(&peer_ptr<SweepMail>(P, threadIdx.x, P.win_mail)[v].flag1, seqf);
+            for (int u = threadIdx.x; u < P.P; u += blockDim.x) sweep_wait(P, &mail[u].flag1, seqf, true);
+            __syncthreads();
+            if (v == P.v0) for (int x = threadIdx.x; x <= P.d; x += blockDim.x) { const int r = __ldcg(P.rklog + (i64)it * (P.d + 1) + x); P.rk[x] = r; P.rks[x] = r; }
+        }
     }
 }
 
@@ -443,35 +581,59 @@ __global__ void k_quad_lua_all(DevPlan P) {
     }
     for (int x = threadIdx.x; x < r0 * r1; x += blockDim.x) { int k = x / r0, i = x - k * r0; gm[i + (i64)P.Rmax * k] = M[x]; }
 }
+// epilogue of a kernel whose results other processes wait for (every thread of every CTA calls it): once the whole grid's
+// peer stores are fenced, the last CTA stores this phase's sequence number into every process's flag slot (cf. mp_publish)
+__device__ __forceinline__ void mp_publish_grid(const DevPlan& P, int phase) {
+    __shared__ int s_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(P.tickets + P.P, 1u);
+        s_last = (t == gridDim.x * gridDim.y * gridDim.z - 1);
+        if (s_last) P.tickets[P.P] = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    const unsigned long long seq = mp_seq(P, phase);
+    for (int q = threadIdx.x; q < P.nproc; q += blockDim.x)
+        st_release_sys((unsigned long long*)(P.peer_win[q] + P.win_flg) + (long long)(phase - 1) * P.nproc + P.prank, seq);
+}
 __global__ void k_quad_chain_all(DevPlan P, double* chainS) {
     extern __shared__ double smem[];
     const int v = P.v0 + blockIdx.x, sw = blockIdx.y + 1;
-    if (sw > P.ctrl->nsweeps) return;
-    const int first = P.own[v];
-    int last = P.own[v + 1] - 1;
-    if (v == P.P - 1) last = P.d;
-    const int ld = P.Rmax;
-    const int* rq = P.rklog + (i64)sw * (P.d + 1);
-    const i64 msz = (i64)ld * ld;
-    double* cur = smem; double* nxt = smem + msz; double* B = smem + 2 * msz;
-    const int m = rq[first - 1];
-    mat_load_sm(P.ttqq + (i64)first * msz, m, rq[first], ld, cur, ld);
-    __syncthreads();
-    for (int p = first + 1; p <= last; ++p) {
-        mat_load_sm(P.ttqq + (i64)p * msz, rq[p - 1], rq[p], ld, B, ld);
+    if (sw <= P.ctrl->nsweeps) {
+        const int first = P.own[v];
+        int last = P.own[v + 1] - 1;
+        if (v == P.P - 1) last = P.d;
+        const int ld = P.Rmax;
+        const int* rq = P.rklog + (i64)sw * (P.d + 1);
+        const i64 msz = (i64)ld * ld;
+        double* cur = smem; double* nxt = smem + msz; double* B = smem + 2 * msz;
+        const int m = rq[first - 1];
+        mat_load_sm(P.ttqq + (i64)first * msz, m, rq[first], ld, cur, ld);
         __syncthreads();
-        mat_mul_sm(cur, m, rq[p - 1], B, rq[p], nxt, ld);
-        __syncthreads();
-        double* t = cur; cur = nxt; nxt = t;
+        for (int p = first + 1; p <= last; ++p) {
+            mat_load_sm(P.ttqq + (i64)p * msz, rq[p - 1], rq[p], ld, B, ld);
+            __syncthreads();
+            mat_mul_sm(cur, m, rq[p - 1], B, rq[p], nxt, ld);
+            __syncthreads();
+            double* t = cur; cur = nxt; nxt = t;
+        }
+        const i64 off = ((i64)(sw - 1) * (P.P + 1) + v) * msz;
+        const int nl = rq[last];
+        for (int g = 0; g < P.nproc; ++g) {          // the chain product goes to every process (each runs the tree, dmrgg.f90:1355-1405)
+            double* out = (P.nproc > 1 ? (double*)(P.peer_win[g] + P.win_chs) : chainS) + off;
+            for (int e = threadIdx.x; e < m * nl; e += blockDim.x) { int j = e / m, i = e - j * m; out[i + (i64)ld * j] = cur[i + ld * j]; }
+        }
+        if (P.P == 1 && threadIdx.x == 0) P.slog[sw].val = cur[0];
     }
-    double* out = chainS + ((i64)(sw - 1) * (P.P + 1) + v) * msz;
-    const int nl = rq[last];
-    for (int e = threadIdx.x; e < m * nl; e += blockDim.x) { int j = e / m, i = e - j * m; out[i + (i64)ld * j] = cur[i + ld * j]; }
-    if (P.P == 1 && threadIdx.x == 0) P.slog[sw].val = cur[0];
+    if (P.nproc > 1) mp_publish_grid(P, 2);
 }
 __global__ void k_quad_tree_all(DevPlan P, double* chainS) {
     extern __shared__ double smem[];
     const int sw = blockIdx.x + 1;
+    if (P.nproc > 1) mp_wait(P, 2);                  // every process's chain products have landed in this window
     if (sw > P.ctrl->nsweeps || P.P == 1) return;
     const int ld = P.Rmax;
     const int* rq = P.rklog + (i64)sw * (P.d + 1);

@@ -360,6 +360,57 @@ __device__ __forceinline__ void tl_mark(const DevPlan& P, int id) {     // diagn
     }
 }
 
+
+// ----------------------------------------------------------------------------
+// TMA staging (sm_100a): 1-D bulk copies global -> shared memory completing on an mbarrier (cp.async.bulk, SASS UBLKCP).
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok = 0;
+    while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Issue the staging of a bond visit (one thread): node / weight vectors of the two free modes and the value tables of the
+// left bond pl (pl rows) and the right bond pr (d - pr rows), whole padded rows.  Layout (doubles, all offsets even):
+//   NX[NT] NW[NT] NX2[NT] NW2[NT] XL[pl*RT] WL[pl*RT] XR[nr*RT] WR[nr*RT]
+__device__ __forceinline__ void stage_bond_tma_issue(const DevPlan& P, double* sm, int pl, int c1, int c2, int pr, unsigned long long* bar) {
+    const int RT = P.RT, NT = P.NT, nl = pl, nr = P.d - pr;
+    const bool hasw = (P.kind == KIND_ISING);
+    const int n1 = (P.n[c1] + 1) & ~1, n2 = (P.n[c2] + 1) & ~1;
+    const unsigned bl = (unsigned)(nl * RT * 8), br = (unsigned)(nr * RT * 8);
+    const unsigned total = (unsigned)(n1 * 8 + n2 * 8) * (hasw ? 2u : 1u) + (bl + br) * (hasw ? 2u : 1u);
+    double* NX = sm; double* NW = NX + NT; double* NX2 = NW + NT; double* NW2 = NX2 + NT;
+    double* XL = NW2 + NT; double* WL = XL + (i64)nl * RT; double* XR = WL + (i64)nl * RT; double* WR = XR + (i64)nr * RT;
+    const i64 oL = P.offL[pl] / P.Rmax * RT, oR = P.offR[pr] / P.Rmax * RT;
+    fence_proxy_async();                       // the staging area was last touched through the generic proxy
+    mbar_expect_tx(bar, total);
+    tma_load_1d(NX, P.parT, n1 * 8, bar);
+    tma_load_1d(NX2, P.parT, n2 * 8, bar);
+    if (hasw) { tma_load_1d(NW, P.parT + NT, n1 * 8, bar); tma_load_1d(NW2, P.parT + NT, n2 * 8, bar); }
+    if (bl) { tma_load_1d(XL, P.XLg + oL, bl, bar); if (hasw) tma_load_1d(WL, P.WLg + oL, bl, bar); }
+    if (br) { tma_load_1d(XR, P.XRg + oR, br, bar); if (hasw) tma_load_1d(WR, P.WRg + oR, br, bar); }
+}
+__device__ __forceinline__ Stage stage_bond_tma_view(const DevPlan& P, double* sm, int pl, int rl, int pr, int rr) {
+    Stage S;
+    const int RT = P.RT, NT = P.NT, nl = pl, nr = P.d - pr;
+    S.NX = sm; S.NW = sm + NT; S.NX2 = sm + 2 * NT; S.NW2 = sm + 3 * NT;
+    S.XL = sm + 4 * NT; S.WL = S.XL + (i64)nl * RT; S.XR = S.WL + (i64)nl * RT; S.WR = S.XR + (i64)nr * RT;
+    S.nl = nl; S.rl = RT; S.nr = nr; S.rr = RT; S.hask = 1;      // rl / rr are the row STRIDES of the tables
+    (void)rl; (void)rr;
+    return S;
+}
+
 // ----------------------------------------------------------------------------
 // Streaming evaluation of the Ising C integrand (test_crs_ising.f90:186-217, id = 1) at the points of a bond visit.
 // The reference runs two independent recurrences over the positions -- the prefix sums w (positions 1..m ascending) and
@@ -376,19 +427,19 @@ struct IsingCTab {
     int nl, rl, nr, rr;
 };
 // pre: shared double[4 * Rmax]; every thread of the CTA calls it (ends with a block barrier)
-__device__ __forceinline__ IsingCTab ising_c_prepare(const Stage& S, double* pre, int Rmax) {
+__device__ __forceinline__ IsingCTab ising_c_prepare(const Stage& S, int r0, int r2, double* pre, int Rmax) {
     IsingCTab T;
     T.XL = S.XL; T.WL = S.WL; T.XR = S.XR; T.WR = S.WR; T.NX = S.NX; T.NW = S.NW; T.NX2 = S.NX2; T.NW2 = S.NW2;
     T.nl = S.nl; T.rl = S.rl; T.nr = S.nr; T.rr = S.rr;
     double* PWK = pre; double* PWW = pre + Rmax; double* SVK = pre + 2 * Rmax; double* SVV = pre + 3 * Rmax;
-    for (int t = threadIdx.x; t < S.rl + S.rr; t += blockDim.x) {
-        if (t < S.rl) {
+    for (int t = threadIdx.x; t < r0 + r2; t += blockDim.x) {
+        if (t < r0) {
             double wk = 1.0, w = 1.0;
             const double* xl = S.XL + t;
             for (int pos = 0; pos < S.nl; ++pos) { wk = wk * xl[pos * S.rl]; w = w + wk; }
             PWK[t] = wk; PWW[t] = w;
         } else {
-            const int q = t - S.rl;
+            const int q = t - r0;
             double vk = 1.0, vv = 1.0;
             const double* xr = S.XR + q;
             for (int pos = S.nr - 1; pos >= 0; --pos) { vk = vk * xr[pos * S.rr]; vv = vv + vk; }
@@ -468,8 +519,9 @@ struct VisitCtx {
     int v, lo, hi, rkL, rkR;
     int phase;                 // parity counter of cluster_fold
     int upd_first, upd_last;   // out: was the partition's first / last bond updated in this sweep (uniform over the cluster)
+    unsigned long long* bar; unsigned bar_parity;     // TMA staging (persistent kernel): CTA-local mbarrier and its phase
 };
-template <int KIND>
+template <int KIND, bool TMA = false>
 __device__ __forceinline__ void visit_list(const DevPlan& P, cg::cluster_group& cl, VisitCtx& C, int it, int dir, double small_element, double small_pivot) {
     VisitShared& sh = *C.sh;
     const int crank = (int)cl.block_rank(), cs = (int)cl.num_blocks();
@@ -492,10 +544,16 @@ __device__ __forceinline__ void visit_list(const DevPlan& P, cg::cluster_group& 
         }
         __syncthreads();
         const int r0 = sh.r0, r1 = sh.r1, r2 = sh.r2, n1 = P.n[p], n2 = P.n[p + 1];
-        const Stage S = stage_bond_cg(P, stg, p - 1, r0, p, p + 1, p + 1, r2);
+        Stage S;
+        if (TMA) {
+            // the TMA fills the staging area (the previous visit's readers are past the cluster barrier that ended it)
+            if (threadIdx.x == 0) stage_bond_tma_issue(P, stg, p - 1, p, p + 1, p + 1, C.bar);
+            S = stage_bond_tma_view(P, stg, p - 1, r0, p + 1, r2);
+        } else {
+            S = stage_bond_cg(P, stg, p - 1, r0, p, p + 1, p + 1, r2);
+        }
         constexpr bool fastc = (KIND == KIND_ISINGC);                      // streaming evaluation of Ising C
         IsingCTab TC;
-        if (fastc) TC = ising_c_prepare(S, C.pre, P.Rmax);
         tl_mark(P, 41);
         const double* colp = P.col + P.coreOff[p];
         const double* rowp = P.rowT + P.coreOff[p + 1];
@@ -510,6 +568,8 @@ __device__ __forceinline__ void visit_list(const DevPlan& P, cg::cluster_group& 
             const int* vip_p = P.vip + (i64)p * P.Rmax * 4;
             const int m = ccount, n = rcount;
             lot_zeros2(vip_p, r1, r0, n2, tmp, zc, zr, sh.nz);
+            if (TMA) { mbar_wait(C.bar, C.bar_parity); C.bar_parity ^= 1u; }     // the staged tables have landed (copied beside the zero-cell setup)
+            if (fastc) TC = ising_c_prepare(S, r0, r2, C.pre, P.Rmax);
             tl_mark(P, 42);
             const unsigned long long k0 = sh.S.rng_k, seed = P.ctrl->seed;
             const bool packed = m < (1 << 20) && n < (1 << 20) && nlot < (1 << 22);
@@ -680,12 +740,22 @@ __device__ __forceinline__ void visit_list(const DevPlan& P, cg::cluster_group& 
                 if (threadIdx.x == 0) { int* vp = P.vip + ((i64)p * P.Rmax + t) * 4; vp[0] = ii; vp[1] = jj; vp[2] = kk; vp[3] = qq; }
                 int* Lp = P.Lidx + P.offL[p];
                 const int* Lm = P.Lidx + P.offL[p - 1];
-                for (int pos = threadIdx.x; pos < p; pos += blockDim.x)
-                    Lp[(i64)pos * P.Rmax + t] = (pos < p - 1) ? LDF(Lm + (i64)pos * P.Rmax + (ii - 1)) : jj;
+                const bool vt = P.XLg != nullptr, hasw_ = (P.kind == KIND_ISING);
+                const i64 oLp = P.offL[p] / P.Rmax * P.RT, oRp = P.offR[p] / P.Rmax * P.RT;
+                const int nwoff_ = P.n[1];
+                for (int pos = threadIdx.x; pos < p; pos += blockDim.x) {
+                    const int idx = (pos < p - 1) ? LDF(Lm + (i64)pos * P.Rmax + (ii - 1)) : jj;
+                    Lp[(i64)pos * P.Rmax + t] = idx;
+                    if (vt) { P.XLg[oLp + (i64)pos * P.RT + t] = P.par[idx - 1]; if (hasw_) P.WLg[oLp + (i64)pos * P.RT + t] = P.par[nwoff_ + idx - 1]; }
+                }
                 int* Rp = P.Ridx + P.offR[p];
                 const int* Rn = P.Ridx + P.offR[p + 1];
-                for (int pos = threadIdx.x; pos < P.d - p; pos += blockDim.x)
-                    Rp[(i64)pos * P.Rmax + t] = (pos == 0) ? kk : LDF(Rn + (i64)(pos - 1) * P.Rmax + (qq - 1));
+                for (int pos = threadIdx.x; pos < P.d - p; pos += blockDim.x) {
+                    const int idx = (pos == 0) ? kk : LDF(Rn + (i64)(pos - 1) * P.Rmax + (qq - 1));
+                    Rp[(i64)pos * P.Rmax + t] = idx;
+                    if (vt) { P.XRg[oRp + (i64)pos * P.RT + t] = P.par[idx - 1]; if (hasw_) P.WRg[oRp + (i64)pos * P.RT + t] = P.par[nwoff_ + idx - 1]; }
+                }
+                if (vt) fence_proxy_async();          // the TMA of later visits reads these tables through the async proxy
                 // packed LU: [ col(ii,jj,1:r) | row(1:r,kk,qq) | pivot ]
                 double* g = P.inv + (i64)p * P.Rmax * P.Rmax;
                 for (int s = threadIdx.x; s < r1; s += blockDim.x) {
