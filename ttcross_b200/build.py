@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libttcross_b200.so")
+LIB = os.environ.get("TTC_BUILD_OUT", os.path.join(HERE, "libttcross_b200.so"))
 SOURCES = ["ttc_engine.cu"]
 NVCC = os.environ.get("TTC_NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -17,7 +17,7 @@ FLAGS = [
     "-Xcompiler", "-fPIC", "-shared",
     "-ccbin", "/usr/bin/g++",
     "-cudart", "shared", "-ldl", "-Xcompiler", "-pthread",
-]
+] + os.environ.get("TTC_NVCC_EXTRA", "").split()
 
 
 def needs_build() -> bool:

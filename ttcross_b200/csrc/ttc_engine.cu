@@ -146,6 +146,7 @@ struct ttc_handle {
     size_t sm_sbt = 0; bool sbt_ok = false;      // tiled superblock kernel (ttc_superblock.cuh)
     int cluster_size = 16, cluster_threads = 256;   // measured best on B200 (16 x 256 beats the portable 8 x 512 by 7 %)
     size_t sm_visit = 0; bool cluster_ok = false;
+    int sweep_threads = 256;                       // CTA size of the persistent kernel (TTC_SWEEP_THREADS)
     bool persist_ok = false;                       // the persistent sweep kernel (ttc_sweep.cuh) fits the device in one cooperative wave
     double* chainS = nullptr;                      // [maxsweeps][P + 1][Rmax^2] chain products of the per-sweep quadrature after the loop
     int nsm = 148;
@@ -664,7 +665,8 @@ int setup_device(ttc_handle* h, int maxrank) {
         else { h->cluster_size = 8; h->cluster_threads = 256; }
         if (const char* e = std::getenv("TTC_CLUSTER_SIZE")) h->cluster_size = std::atoi(e);
         if (const char* e = std::getenv("TTC_CLUSTER_THREADS")) h->cluster_threads = std::atoi(e);
-        h->sm_visit = ((size_t)D.auxsm + 5 * (size_t)Rmax + (size_t)Rmax * Rmax + Rmax + D.stage_max + 2) * sizeof(double) + (size_t)(4 * Rmax + 8) * sizeof(int);
+        const size_t RE = std::max(Rmax, 32);       // (the exchange of the persistent kernel stages a 32 x 32 packed block)
+        h->sm_visit = ((size_t)D.auxsm + 5 * (size_t)Rmax + RE * RE + RE + D.stage_max + 2) * sizeof(double) + (size_t)(4 * Rmax + 8) * sizeof(int);
         h->cluster_ok = D.stage && h->use_wave && h->sm_visit <= 200 * 1024 && h->cluster_size >= 1 && h->cluster_size <= MAXCS && h->cluster_threads >= 32 &&
                         h->cluster_threads <= VISIT_MAXTHREADS && h->cluster_threads % 32 == 0 &&
                         !std::getenv("TTC_NO_CLUSTER");
@@ -701,6 +703,8 @@ int setup_device(ttc_handle* h, int maxrank) {
             D.mail = dmail; D.win_mail = 0; D.chainS = nullptr;
         }
         h->persist_ok = false;
+        h->sweep_threads = std::min(h->cluster_threads, SWEEP_MAXTHREADS);
+        if (const char* e = std::getenv("TTC_SWEEP_THREADS")) h->sweep_threads = std::max(32, std::min(SWEEP_MAXTHREADS, std::atoi(e) / 32 * 32));
         if (h->cluster_ok && (h->nproc == 1 || h->p2p) && !std::getenv("TTC_NO_PERSISTENT")) {
             cudaError_t ce = cudaSuccess;
             VISIT_KIND_SWITCH(h,
@@ -709,13 +713,14 @@ int setup_device(ttc_handle* h, int maxrank) {
             );
             if (ce == cudaSuccess) {
                 cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(h->cluster_size, D.nv, 1); cfg.blockDim = dim3(h->cluster_threads, 1, 1); cfg.dynamicSmemBytes = h->sm_visit;
+                cfg.gridDim = dim3(h->cluster_size, D.nv, 1); cfg.blockDim = dim3(h->sweep_threads, 1, 1); cfg.dynamicSmemBytes = h->sm_visit;
                 cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
                 at[0].val.clusterDim.x = h->cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 cfg.attrs = at; cfg.numAttrs = 1;
                 int ncl = 0;
                 VISIT_KIND_SWITCH(h, ce = cudaOccupancyMaxActiveClusters(&ncl, k_sweeps<K>, &cfg));
                 h->persist_ok = (ce == cudaSuccess) && ncl >= D.nv && P <= 64;
+                if (std::getenv("TTC_TRACE")) std::fprintf(stderr, "[ttc trace] persistent kernel: %d clusters of %d x %d threads resident at once (need %d), smem %zu B: %s\n", ncl, h->cluster_size, h->sweep_threads, D.nv, h->sm_visit, h->persist_ok ? "on" : "off");
             }
             if (ce != cudaSuccess) (void)cudaGetLastError();
         }
@@ -1279,7 +1284,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     if (persistent) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(h->cluster_size, NV, 1);
-        cfg.blockDim = dim3(h->cluster_threads, 1, 1);
+        cfg.blockDim = dim3(h->sweep_threads, 1, 1);
         cfg.dynamicSmemBytes = h->sm_visit;
         cfg.stream = s;
         cudaLaunchAttribute at[2];

@@ -87,46 +87,51 @@ __device__ __forceinline__ void sweep_wait(const DevPlan& P, const unsigned long
 // of (broadcast, multiply, add) -- about 50 cycles each and nothing to overlap inside one chain -- so a warp that owns
 // several mode indices runs them side by side.  Same operations in the same order as warp_luar / warp_lual per chain.
 // ----------------------------------------------------------------------------
-constexpr int XCH = 6;
-__device__ __forceinline__ void warp_luar_multi(double (&y)[XCH], int nx, int r, const double* T) {
-    const int lane = threadIdx.x & 31;
-    const bool in = lane < r;
-    double tmp[XCH];
+// d2_luar / d2_lual of ONE mode index per THREAD, rank <= RB, straight out of the packed LU block staged in shared memory
+// (every lane reads the same coefficient: a broadcast).  A recurrence is a chain of dependent steps, but only the LAST term of
+// row s waits for y(s-1); the r^2/2 other multiply-adds are independent of it, so with the rows fully unrolled in registers
+// the dependent path is 3 operations per row and the rest pipelines -- no shuffles, no idle lanes: 32 mode indices per warp
+// instead of one.  Same operations in the same order per row as lr.f90:124-154 (tmp from 0 in ascending u, then y - tmp; resp.
+// y + (-g) y(u) in ascending u, then the division by the pivot as a multiplication by its reciprocal, like warp_lual).
+// Rows >= r work on zeros and are discarded.  G: packed block (dmrgg.f90:650-660), DI[c] = 1 / pivot(c).
+// (The loops run over u OUTSIDE and the rows inside: consecutive instructions then belong to different rows and are
+// independent, which is what an in-order pipeline needs; every row still receives its terms in ascending u.)
+template <int RB>
+__device__ __forceinline__ void thread_luar(double (&y)[RB], const double* G) {
+    double tmp[RB];
 #pragma unroll
-    for (int v = 0; v < XCH; ++v) tmp[v] = 0.0;
-#pragma unroll 2
-    for (int u = 0; u + 1 < r; ++u) {
-        const double gsu = (in && lane > u) ? T[u * r + lane] : 0.0;
+    for (int s = 0; s < RB; ++s) tmp[s] = 0.0;
 #pragma unroll
-        for (int v = 0; v < XCH; ++v) {
-            if (v < nx) {
-                const double yu = __shfl_sync(FULLMASK, y[v], u);
-                if (in && lane > u) tmp[v] = tmp[v] + yu * gsu;
-                if (lane == u + 1) y[v] = y[v] + (-tmp[v]);
-            }
-        }
+    for (int u = 0; u + 1 < RB; ++u) {
+#pragma unroll
+        for (int s = u + 1; s < RB; ++s) tmp[s] = tmp[s] + y[u] * G[s * s + u];
+        y[u + 1] = y[u + 1] + (-tmp[u + 1]);
     }
 }
-__device__ __forceinline__ void warp_lual_multi(double (&y)[XCH], int nx, int r, const double* T, const double* DI) {
-    const int lane = threadIdx.x & 31;
-    const bool in = lane < r;
-    const double di = in ? DI[lane] : 0.0;
-    if (r > 0 && lane == 0) {
+template <int RB>
+__device__ __forceinline__ void thread_lual(double (&y)[RB], const double* G, const double* DI) {
+    y[0] = DI[0] * y[0];
 #pragma unroll
-        for (int v = 0; v < XCH; ++v) y[v] = di * y[v];
-    }
-#pragma unroll 2
-    for (int u = 0; u + 1 < r; ++u) {
-        const double gcu = (in && lane > u) ? T[u * r + lane] : 0.0;
+    for (int u = 0; u + 1 < RB; ++u) {
 #pragma unroll
-        for (int v = 0; v < XCH; ++v) {
-            if (v < nx) {
-                const double yu = __shfl_sync(FULLMASK, y[v], u);
-                if (in && lane > u) y[v] = y[v] + (-gcu) * yu;
-                if (lane == u + 1) y[v] = di * y[v];
-            }
-        }
+        for (int c = u + 1; c < RB; ++c) y[c] = y[c] + (-G[(c + 1) * (c + 1) - (c + 1) + u]) * y[u];
+        y[u + 1] = DI[u + 1] * y[u + 1];
     }
+}
+// (A loop version with the vector in a private shared-memory column was measured too: 19 us per boundary against 8 us for
+// the unrolled registers and 9 us for six interleaved warp wavefronts -- the store -> load round trips of the column
+// serialise it.)
+// one boundary job for the mode index x of this thread: load the right-hand side (the corner value replaces its last entry),
+// solve, store.  src / dst strides in doubles.
+template <int RB>
+__device__ __forceinline__ void thread_boundary(int side, int r, const double* src, i64 sstride, double* dst, i64 dstride, bool corner, double f,
+                                                const double* G, const double* DI) {
+    double y[RB];
+#pragma unroll
+    for (int u = 0; u < RB; ++u) y[u] = (u < r) ? ((corner && u == r - 1) ? f : __ldcg(src + u * sstride)) : 0.0;
+    if (side == 0) thread_luar<RB>(y, G); else thread_lual<RB>(y, G, DI);
+#pragma unroll
+    for (int u = 0; u < RB; ++u) if (u < r) dst[u * dstride] = y[u];
 }
 
 // ----------------------------------------------------------------------------
@@ -142,28 +147,33 @@ __device__ __forceinline__ void warp_lual_multi(double (&y)[XCH], int nx, int r,
 // their recurrences interleaved.  Returns the largest |corner value| seen by this thread (-1: none).
 // smem: ext = staged LU table (+ diagonal), stg = XF[d] | WF[d] | F[corner values of this CTA].
 // ----------------------------------------------------------------------------
-struct BoundaryJob { int work, side, c, rc1, rc, corner; };
+struct BoundaryJob { int exists, work, side, c, rc1, rc, corner; };   // exists: the partition has this boundary; work: something arrived
 template <int KIND>
-__device__ __forceinline__ double exchange_boundaries(const DevPlan& P, cg::cluster_group& cl, const VisitCtx& C, const BoundaryJob& JA, const BoundaryJob& JB) {
+__device__ __forceinline__ double exchange_boundaries(const DevPlan& P, cg::cluster_group& cl, const VisitCtx& C, const BoundaryJob& JA, const BoundaryJob& JB,
+                                                      int stage_only, int prestaged) {
     if (!JA.work && !JB.work) return -1.0;
     const int crank = (int)cl.block_rank(), cs = (int)cl.num_blocks();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    // which boundary this CTA serves, and its position among the CTAs that serve it
-    const bool both = JA.work && JB.work && cs >= 2;
+    // which boundary this CTA serves, and its position among the CTAs that serve it: a STATIC split (inner partitions: the
+    // first half of the cluster serves the left boundary, the rest the right one), so that a CTA can stage its packed LU --
+    // this partition's own data -- before the neighbour's flag arrives (prestaged != 0)
+    const bool both = JA.exists && JB.exists && cs >= 2;
     const int halfA = cs / 2;
-    const bool mineB = both ? (crank >= halfA) : (JB.work != 0);
+    const bool mineB = both ? (crank >= halfA) : (JB.exists != 0);
     const BoundaryJob J = mineB ? JB : JA;
     const int nside = both ? (mineB ? cs - halfA : halfA) : cs;
     const int csub = both ? (mineB ? crank - halfA : crank) : crank;
-    const bool second_pass = JA.work && JB.work && cs < 2;       // (a one-CTA cluster serves both boundaries in turn)
+    const bool second_pass = JA.exists && JB.exists && cs < 2;   // (a one-CTA cluster serves both boundaries in turn)
     double cmax = -1.0;
     for (int pass = 0; pass < (second_pass ? 2 : 1); ++pass) {
         const BoundaryJob Jp = second_pass ? (pass == 0 ? JA : JB) : J;
+        if (!Jp.work) continue;                                    // (uniform over the CTA)
         const int side = Jp.side, c = Jp.c, rc1 = Jp.rc1, rc = Jp.rc;
         const bool corner = Jp.corner != 0;
         const int nc = P.n[c];
         double* XF = C.stg; double* WF = XF + P.d; double* F = WF + P.d;
-        double* T = C.ext; double* DI = T + (i64)P.Rmax * P.Rmax;
+        const int RE = max(P.Rmax, 32);
+        double* T = C.ext; double* DI = T + (i64)RE * RE;
         double* argc = P.arg + P.coreOff[c];
         const bool hasw = (P.kind == KIND_ISING);
         const int nwoff = P.n[1];
@@ -175,14 +185,62 @@ __device__ __forceinline__ double exchange_boundaries(const DevPlan& P, cg::clus
         __syncthreads();                                           // ext / stg are free (previous users done)
         if (corner) {
             const int* Lt = P.Lidx + P.offL[c - 1]; const int* Rt = P.Ridx + P.offR[c];
+            const i64 oL = P.offL[c - 1] / P.Rmax * P.RT, oR = P.offR[c] / P.Rmax * P.RT;
             for (int pos = threadIdx.x; pos < P.d - 1; pos += blockDim.x) {
-                const int idx = (pos < c - 1) ? __ldcg(Lt + (i64)pos * P.Rmax + (rc1 - 1)) : __ldcg(Rt + (i64)(pos - (c - 1)) * P.Rmax + (rc - 1));
-                XF[pos] = P.par[idx - 1]; WF[pos] = hasw ? P.par[nwoff + idx - 1] : 0.0;
+                if (P.XLg) {                          // value tables: one round trip instead of index -> value
+                    const i64 o = (pos < c - 1) ? oL + (i64)pos * P.RT + (rc1 - 1) : oR + (i64)(pos - (c - 1)) * P.RT + (rc - 1);
+                    XF[pos] = __ldcg((pos < c - 1 ? P.XLg : P.XRg) + o); WF[pos] = hasw ? __ldcg((pos < c - 1 ? P.WLg : P.WRg) + o) : 0.0;
+                } else {
+                    const int idx = (pos < c - 1) ? __ldcg(Lt + (i64)pos * P.Rmax + (rc1 - 1)) : __ldcg(Rt + (i64)(pos - (c - 1)) * P.Rmax + (rc - 1));
+                    XF[pos] = P.par[idx - 1]; WF[pos] = hasw ? P.par[nwoff + idx - 1] : 0.0;
+                }
             }
         }
-        if (side == 0) stage_luar_cg(P.inv + (i64)(c - 1) * P.Rmax * P.Rmax, rc1, T);
-        else stage_lual_cg(P.inv + (i64)c * P.Rmax * P.Rmax, rc, T, DI);
+        const int rr_ = side == 0 ? rc1 : rc;                      // rank of the recurrence
+        const bool flat = rr_ <= 32;                               // thread-per-mode-index solves out of the packed block (ext holds >= 32 x 32 + 32)
+        if (!prestaged) {
+            if (flat) {
+                const double* g = P.inv + (i64)(side == 0 ? c - 1 : c) * P.Rmax * P.Rmax;
+                for (int x = threadIdx.x; x < rr_ * rr_; x += blockDim.x) T[x] = LDF(g + x);
+                for (int x = threadIdx.x; x < 32 * 32 - rr_ * rr_; x += blockDim.x) T[rr_ * rr_ + x] = 0.0;     // rows >= r of the unrolled solve
+                if (side == 1) for (int cc = threadIdx.x; cc < 32; cc += blockDim.x) DI[cc] = cc < rr_ ? 1.0 / LDF(g + (i64)(cc + 1) * (cc + 1) - 1) : 0.0;
+            } else if (side == 0) stage_luar_cg(P.inv + (i64)(c - 1) * P.Rmax * P.Rmax, rc1, T);
+            else stage_lual_cg(P.inv + (i64)c * P.Rmax * P.Rmax, rc, T, DI);
+        }
+        if (stage_only) continue;
         __syncthreads();
+        double* ST4 = F + P.nmax;                                   // prefix / suffix state of the fixed part of the corner fiber
+        if (KIND == KIND_ISINGC && corner) {
+            if (threadIdx.x == 0) ising_c_fixed(XF, c - 1, P.d - c, ST4);
+            __syncthreads();
+        }
+        tl_mark(P, 75);
+        if (flat) {
+            // one thread per mode index: corner value, solve, store
+            for (int t = threadIdx.x; t < cta_cnt; t += blockDim.x) {
+                const int x = cta_first + t;
+                double f = 0.0;
+                if (corner) {
+                    StagedVals sv;
+                    sv.XL = XF; sv.WL = WF; sv.nl = c - 1; sv.rl = 1; sv.i = 1;
+                    sv.xj = P.par[x]; sv.wj = hasw ? P.par[nwoff + x] : 0.0;
+                    sv.hask = 0; sv.xk = 0.0; sv.wk = 0.0;
+                    sv.XR = XF + (c - 1); sv.WR = WF + (c - 1); sv.rr = 1; sv.q = 1;
+                    if (KIND == KIND_ISINGC) f = ising_c_eval1(XF, WF, c - 1, P.d - c, ST4, sv.xj, sv.wj);
+                    else f = eval_point_wide<KIND>(P, sv, C.A);
+                    argc[(rc1 - 1) + (i64)P.Rmax * (x + (i64)nc * (rc - 1))] = f;     // (both members store the same value)
+                    cmax = fmax(cmax, fabs(f));
+                }
+                const double* src = side == 0 ? argc + (i64)P.Rmax * (x + (i64)nc * (rc - 1)) : argc + (rc1 - 1) + (i64)P.Rmax * x;
+                const i64 ss = side == 0 ? 1 : (i64)P.Rmax * nc;
+                double* dst = side == 0 ? P.rowT + P.coreOff[c] + (i64)nc * (rc - 1) + x : P.col + P.coreOff[c] + (rc1 - 1) + (i64)P.Rmax * x;
+                const i64 ds = side == 0 ? (i64)nc * P.Rmax : (i64)P.Rmax * nc;
+                if (rr_ <= 16) thread_boundary<16>(side, rr_, src, ss, dst, ds, corner, f, T, DI);
+                else thread_boundary<32>(side, rr_, src, ss, dst, ds, corner, f, T, DI);
+            }
+            tl_mark(P, 76);
+            continue;
+        }
         if (corner) {
             for (int t = threadIdx.x; t < cta_cnt; t += blockDim.x) {
                 const int x = cta_first + t;
@@ -198,34 +256,10 @@ __device__ __forceinline__ double exchange_boundaries(const DevPlan& P, cg::clus
             }
             __syncthreads();
         }
+        tl_mark(P, 76);
         const int gw = gw0 + wid;
         const int wfirst = gw * base + min(gw, rem), wcnt = base + (gw < rem ? 1 : 0);
-        const int rr_ = side == 0 ? rc1 : rc;                      // rank of the recurrence
-        if (rr_ <= 32) {
-            for (int k0 = 0; k0 < wcnt; k0 += XCH) {
-                const int nx = min(XCH, wcnt - k0);
-                double y[XCH];
-#pragma unroll
-                for (int v = 0; v < XCH; ++v) {
-                    y[v] = 0.0;
-                    if (v < nx && lane < rr_) {
-                        const int x = wfirst + k0 + v;
-                        if (corner && lane == rr_ - 1) y[v] = F[x - cta_first];
-                        else if (side == 0) y[v] = __ldcg(argc + (i64)P.Rmax * (x + (i64)nc * (rc - 1)) + lane);
-                        else y[v] = __ldcg(argc + (rc1 - 1) + (i64)P.Rmax * x + lane * ((i64)P.Rmax * nc));
-                    }
-                }
-                if (side == 0) warp_luar_multi(y, nx, rr_, T); else warp_lual_multi(y, nx, rr_, T, DI);
-#pragma unroll
-                for (int v = 0; v < XCH; ++v) {
-                    if (v < nx && lane < rr_) {
-                        const int x = wfirst + k0 + v;
-                        if (side == 0) P.rowT[P.coreOff[c] + (i64)nc * (rc - 1) + x + lane * ((i64)nc * P.Rmax)] = y[v];
-                        else P.col[P.coreOff[c] + (rc1 - 1) + (i64)P.Rmax * x + lane * ((i64)P.Rmax * nc)] = y[v];
-                    }
-                }
-            }
-        } else {
+        {
             for (int k = 0; k < wcnt; ++k) {
                 const int x = wfirst + k;
                 const double f = corner ? F[x - cta_first] : 0.0;
@@ -258,14 +292,22 @@ __device__ __forceinline__ double exchange_boundaries(const DevPlan& P, cg::clus
             }
         }
     }
+    tl_mark(P, 77);
     return cmax;
 }
 
 // ----------------------------------------------------------------------------
 // grid (CS, nv), cluster (CS, 1, 1), cooperative.  Dynamic shared memory as k_visits.
 // ----------------------------------------------------------------------------
+#ifndef TTC_SWEEP_MINB
+#define TTC_SWEEP_MINB 1
+#endif
+#ifndef TTC_SWEEP_MAXT
+#define TTC_SWEEP_MAXT VISIT_MAXTHREADS
+#endif
+constexpr int SWEEP_MAXTHREADS = TTC_SWEEP_MAXT;
 template <int KIND>
-__global__ void __launch_bounds__(VISIT_MAXTHREADS, KIND == KIND_MVN ? 4 : 1)
+__global__ void __launch_bounds__(SWEEP_MAXTHREADS, KIND == KIND_MVN ? 4 : TTC_SWEEP_MINB)
 k_sweeps(DevPlan P, int it_last, int maxrank, double small_element, double small_pivot) {
     tl_stamp(P, 36);
     cg::cluster_group cl = cg::this_cluster();
@@ -282,7 +324,7 @@ k_sweeps(DevPlan P, int it_last, int maxrank, double small_element, double small
     C.xs = smem + P.auxsm;
     C.pre = C.xs + P.Rmax;
     C.ext = C.pre + 4 * (i64)P.Rmax;
-    C.stg = C.ext + (i64)P.Rmax * P.Rmax + P.Rmax;
+    C.stg = C.ext + (i64)max(P.Rmax, 32) * max(P.Rmax, 32) + max(P.Rmax, 32);
     C.stg = (double*)(((unsigned long long)C.stg + 15ULL) & ~15ULL);          // TMA destinations are 16-byte aligned
     C.ibuf = (int*)(C.stg + P.stage_max);
     C.phase = 0;
@@ -376,6 +418,12 @@ k_sweeps(DevPlan P, int it_last, int maxrank, double small_element, double small
         }
         if (threadIdx.x == 0) sl.amax1 = sh.S.amax;
         tl_mark(P, 70);
+        // ---- while the flags travel: stage this CTA's packed LU for the exchange (own data: inv(lo) resp. inv(hi-1))
+        BoundaryJob JA = {v > 0, v > 0, 1, lo, 0, 0, 0}, JB = {v < P.P - 1, v < P.P - 1, 0, hi, 0, 0, 0};     // (work = exists while staging)
+        if (v > 0) JA.rc = LDF(P.rk + lo);
+        if (v < P.P - 1) JB.rc1 = LDF(P.rk + hi - 1);
+        const int prestaged = (int)cl.num_blocks() >= 2 ? 1 : 0;
+        if (prestaged) exchange_boundaries<KIND>(P, cl, C, JA, JB, 1, 0);
         // ---- wait for the two neighbours (each CTA polls for itself: no extra cluster barrier)
         if (threadIdx.x < 2) {
             const int u = threadIdx.x == 0 ? v - 1 : v + 1;
@@ -429,16 +477,15 @@ k_sweeps(DevPlan P, int it_last, int maxrank, double small_element, double small
         }
         // ---- this partition's half of the exchange on its two boundaries
         int ncorner = 0;
-        BoundaryJob JA = {0, 1, lo, 0, 0, 0}, JB = {0, 0, hi, 0, 0, 0};
         if (v > 0) {                                    // RIGHT member of boundary v-1: core lo
-            JA.work = updL; JA.rc1 = sl.rkL + updL; JA.rc = LDF(P.rk + lo); JA.corner = updL && C.upd_first;
+            JA.work = updL; JA.rc1 = sl.rkL + updL; JA.corner = updL && C.upd_first;
             if (JA.corner) ncorner += P.n[lo];
         }
         if (v < P.P - 1) {                              // LEFT member of boundary v: core hi
-            JB.work = updR; JB.rc1 = LDF(P.rk + hi - 1); JB.rc = sl.rkR + updR; JB.corner = C.upd_last && updR;
+            JB.work = updR; JB.rc = sl.rkR + updR; JB.corner = C.upd_last && updR;
             if (JB.corner) ncorner += P.n[hi];
         }
-        double cmax = exchange_boundaries<KIND>(P, cl, C, JA, JB);
+        double cmax = exchange_boundaries<KIND>(P, cl, C, JA, JB, 0, prestaged);
         if (ncorner) {                                  // uniform over the cluster
             Partial dummy = amax_init();
             cluster_fold(cl, sh, C.phase, cmax, dummy);

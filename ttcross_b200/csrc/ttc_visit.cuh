@@ -147,12 +147,24 @@ __device__ __forceinline__ Stage stage_bond_cg(const DevPlan& P, double* sm, int
     S.nl = nl; S.rl = rl; S.nr = nr; S.rr = rr; S.hask = c2 ? 1 : 0;
     return S;
 }
+// Packed LU -> transposed shared-memory table, one warp per row of the packed block with the rows of a warp in flight together
+// (the block is read once per use; a dependent load per loop trip would cost one L2 round trip each).
 __device__ __forceinline__ void stage_luar_cg(const double* g, int r, double* T) {
-    for (int x = threadIdx.x; x < r * r; x += blockDim.x) { int s = x / r, u = x - s * r; if (u < s) T[u * r + s] = LDF(g + (i64)s * s + u); }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll 4
+    for (int s = wid; s < r; s += nw)
+        for (int u = lane; u < s; u += 32) T[u * r + s] = LDF(g + (i64)s * s + u);
 }
 __device__ __forceinline__ void stage_lual_cg(const double* g, int r, double* T, double* dinv) {
-    for (int x = threadIdx.x; x < r * r; x += blockDim.x) { int c = x / r, u = x - c * r; if (u < c) T[u * r + c] = LDF(g + (i64)(c + 1) * (c + 1) - (c + 1) + u); }
-    for (int c = threadIdx.x; c < r; c += blockDim.x) dinv[c] = 1.0 / LDF(g + (i64)(c + 1) * (c + 1) - 1);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll 4
+    for (int c = wid; c < r; c += nw) {
+        const double* gc = g + (i64)(c + 1) * (c + 1) - (c + 1);
+        for (int u = lane; u <= c; u += 32) {
+            const double val = LDF(gc + u);
+            if (u < c) T[u * r + c] = val; else dinv[c] = 1.0 / val;
+        }
+    }
 }
 
 // Fold over the whole cluster: the first-index argmax of the residuals (idamax) and the largest |f| (only its magnitude
@@ -474,6 +486,32 @@ __device__ __forceinline__ double ising_c_eval(const IsingCTab& T, int i, int j,
     for (int t = 0; t < T.nr; ++t) f = f * wr[t * T.rr];
     return f;
 }
+// the same for a point with ONE free mode (the corner fiber of the exchange, dmrgg.f90:925-937): fixed left part XF[0..nl),
+// mode index j, fixed right part XF[nl..nl+nr); W* the weights.  pw / sv: prefix state after the left part, suffix state
+// after the right part (computed once per fiber by the caller with ising_c_fixed).
+__device__ __forceinline__ void ising_c_fixed(const double* XF, int nl, int nr, double* out4) {
+    double wk = 1.0, w = 1.0, vk = 1.0, vv = 1.0;
+    for (int t = 0; t < nl; ++t) { wk = wk * XF[t]; w = w + wk; }
+    for (int t = nr - 1; t >= 0; --t) { vk = vk * XF[nl + t]; vv = vv + vk; }
+    out4[0] = wk; out4[1] = w; out4[2] = vk; out4[3] = vv;
+}
+__device__ __forceinline__ double ising_c_eval1(const double* XF, const double* WF, int nl, int nr, const double* st4, double xj, double wj) {
+    double wk = st4[0], w = st4[1], vk = st4[2], vv = st4[3];
+    wk = wk * xj; w = w + wk;
+    vk = vk * xj; vv = vv + vk;
+#pragma unroll 4
+    for (int t = 0; t < nr; ++t) { wk = wk * XF[nl + t]; w = w + wk; }
+#pragma unroll 4
+    for (int t = nl - 1; t >= 0; --t) { vk = vk * XF[t]; vv = vv + vk; }
+    const double b = 1.0 / (vv * w);
+    double f = 2 * b;
+#pragma unroll 4
+    for (int t = 0; t < nl; ++t) f = f * WF[t];
+    f = f * wj;
+#pragma unroll 4
+    for (int t = 0; t < nr; ++t) f = f * WF[nl + t];
+    return f;
+}
 // residuals with ALL factor values of the first 32 terms in flight before the evaluation starts (one L2 round trip per
 // element instead of one per batch); same operations in the same order as resid_axpy / resid_dot / resid_ddot2
 constexpr int RPF = 32;
@@ -586,14 +624,49 @@ __device__ __forceinline__ void visit_list(const DevPlan& P, cg::cluster_group& 
                     const double uu = stream_uniform(seed, v, k0 + (unsigned long long)(side ? nlot + x : x));
                     cell = side ? lot_draw_fast(n - sh.nz[1], n, zr, sh.nz[1], uu) : lot_draw_fast(m - sh.nz[0], m, zc, sh.nz[0], uu);
                 }
+                if (fastc) {
+                    // streaming path: BOTH lanes of the pair know the candidate and split the factor loads of the residual
+                    // (each the halves [0,16) / [16,32) of every 32 terms), so the 2 r values are in flight in one L2 round
+                    // trip; the even lane then adds the products in the reference order, its partner's arriving by shuffle
+                    const int other = __shfl_xor_sync(FULLMASK, cell, 1);
+                    const int c = side ? other : cell, w = side ? cell : other;
+                    const int i = (c - 1) % r0 + 1, j = (c - 1) / r0 + 1, k = (w - 1) % n2 + 1, q = (w - 1) / n2 + 1;
+                    const double* cp = colp + (i - 1) + (i64)P.Rmax * (j - 1);
+                    const double* rp = rowp + (k - 1) + (i64)n2 * (q - 1);
+                    double la[16], lb[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) { const int sx = min(side * 16 + u, r1 - 1); la[u] = LDF(cp + sx * cs_); lb[u] = LDF(rp + sx * rs_); }
+                    tl_mark(P, 55);
+                    const double f = ising_c_eval(TC, i, j, k, q);
+                    tl_mark(P, 56);
+                    double tsum = 0.0;
+                    for (int s0 = 0; s0 < r1; s0 += 32) {
+                        if (s0 > 0) {
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) { const int sx = min(s0 + side * 16 + u, r1 - 1); la[u] = LDF(cp + sx * cs_); lb[u] = LDF(rp + sx * rs_); }
+                        }
+                        double pa[16];
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) pa[u] = la[u] * lb[u];
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) if (s0 + u < r1) tsum = tsum + pa[u];
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) { const double po = __shfl_down_sync(FULLMASK, pa[u], 1); if (s0 + 16 + u < r1) tsum = tsum + po; }
+                    }
+                    const double res = f - tsum;
+                    if (live && !side) {
+                        braw = fmax(braw, fabs(f));
+                        amax_take(bres, res, packed ? (((i64)x << 40) | ((i64)c << 20) | (i64)w) : (i64)x);
+                    }
+                    continue;
+                }
                 const int w = __shfl_down_sync(FULLMASK, cell, 1);
                 tl_mark(P, 55);
                 if (!live || side) continue;
                 const int c = cell;
                 const int i = (c - 1) % r0 + 1, j = (c - 1) / r0 + 1, k = (w - 1) % n2 + 1, q = (w - 1) / n2 + 1;
-                double f;
-                if (fastc) f = ising_c_eval(TC, i, j, k, q);
-                else { StagedVals sv = S.point(i, j, k, q); f = eval_point<KIND>(P, sv, A); }
+                StagedVals sv = S.point(i, j, k, q);
+                const double f = eval_point<KIND>(P, sv, A);
                 tl_mark(P, 56);
                 const double res = resid_ddot2_cg(f, colp + (i - 1) + (i64)P.Rmax * (j - 1), cs_, rowp + (k - 1) + (i64)n2 * (q - 1), rs_, r1);
                 braw = fmax(braw, fabs(f));
@@ -631,34 +704,46 @@ __device__ __forceinline__ void visit_list(const DevPlan& P, cg::cluster_group& 
         for (int c = 0; c < nfib; ++c, isrow ^= 1) {
             if (sh.S.done) break;                                   // uniform over the cluster
             const int ii = sh.S.ii, jj = sh.S.jj, kk = sh.S.kk, qq = sh.S.qq;
-            __syncthreads();                                        // xs of the previous fiber no longer read
-            for (int s = threadIdx.x; s < r1; s += blockDim.x)
-                xs[s] = isrow ? LDF(colp + (ii - 1) + (i64)P.Rmax * (jj - 1) + s * cs_) : LDF(rowp + (kk - 1) + (i64)n2 * (qq - 1) + s * rs_);
-            __syncthreads();
-            tl_mark(P, 50);
             const int count = isrow ? rcount : ccount;
             double* fa = isrow ? fa_r : fa_c;
             double* fb = isrow ? fb_r : fb_c;
             Partial bres = amax_init();
             double braw = -1.0;
-            for (int e = gtid; e < count; e += gthreads) {
-                double f, res;
-                if (fastc) {
-                    PrefF pf;
-                    if (!isrow) {
-                        const int j = e / r0 + 1, i = e % r0 + 1;
-                        const double* base = colp + (i - 1) + (i64)P.Rmax * (j - 1);
-                        pref_loadf(pf, base, cs_, r1);
-                        f = ising_c_eval(TC, i, j, kk, qq);
-                        res = resid_axpy_pff(f, pf, base, cs_, xs, r1);
-                    } else {
-                        const int q = e / n2 + 1, k = e % n2 + 1;
-                        const double* base = rowp + (k - 1) + (i64)n2 * (q - 1);
-                        pref_loadf(pf, base, rs_, r1);
-                        f = ising_c_eval(TC, ii, jj, k, q);
-                        res = resid_dot_pff(f, pf, base, rs_, xs, r1);
+            // streaming path: the factor values of this thread's first element are requested BEFORE the staging of xs, so the
+            // two L2 round trips of a fiber step overlap
+            int e = gtid, a1 = 1, a2 = 1;
+            const i64 fstride = isrow ? rs_ : cs_;
+            const double* base = colp;
+            PrefF pff;
+            if (fastc && e < count) {
+                if (!isrow) { a2 = e / r0 + 1; a1 = e % r0 + 1; base = colp + (a1 - 1) + (i64)P.Rmax * (a2 - 1); }
+                else { a2 = e / n2 + 1; a1 = e % n2 + 1; base = rowp + (a1 - 1) + (i64)n2 * (a2 - 1); }
+                pref_loadf(pff, base, fstride, r1);
+            }
+            __syncthreads();                                        // xs of the previous fiber no longer read
+            for (int s = threadIdx.x; s < r1; s += blockDim.x)
+                xs[s] = isrow ? LDF(colp + (ii - 1) + (i64)P.Rmax * (jj - 1) + s * cs_) : LDF(rowp + (kk - 1) + (i64)n2 * (qq - 1) + s * rs_);
+            __syncthreads();
+            tl_mark(P, 50);
+            if (fastc) {
+                while (e < count) {
+                    double f, res;
+                    if (!isrow) { f = ising_c_eval(TC, a1, a2, kk, qq); res = resid_axpy_pff(f, pff, base, fstride, xs, r1); }
+                    else { f = ising_c_eval(TC, ii, jj, a1, a2); res = resid_dot_pff(f, pff, base, fstride, xs, r1); }
+                    fa[e] = f;
+                    fb[e] = res;
+                    braw = fmax(braw, fabs(f));
+                    amax_take(bres, res, e);
+                    e += gthreads;
+                    if (e < count) {
+                        if (!isrow) { a2 = e / r0 + 1; a1 = e % r0 + 1; base = colp + (a1 - 1) + (i64)P.Rmax * (a2 - 1); }
+                        else { a2 = e / n2 + 1; a1 = e % n2 + 1; base = rowp + (a1 - 1) + (i64)n2 * (a2 - 1); }
+                        pref_loadf(pff, base, fstride, r1);
                     }
-                } else {
+                }
+            } else {
+            for (e = gtid; e < count; e += gthreads) {
+                double f, res;
                 Pref pf;
                 if (!isrow) {
                     const int j = e / r0 + 1, i = e % r0 + 1;
@@ -675,11 +760,11 @@ __device__ __forceinline__ void visit_list(const DevPlan& P, cg::cluster_group& 
                     f = eval_point<KIND>(P, sv, A);
                     res = resid_dot_pf(f, pf, base, rs_, xs, r1);
                 }
-                }
                 fa[e] = f;
                 fb[e] = res;
                 braw = fmax(braw, fabs(f));
                 amax_take(bres, res, e);
+            }
             }
             tl_mark(P, 45);
             cluster_fold(cl, sh, phase, braw, bres);
@@ -736,31 +821,41 @@ __device__ __forceinline__ void visit_list(const DevPlan& P, cg::cluster_group& 
         }
         if (upd) {
             const int t = r1;                                       // 0-based slot of the new pivot
+            // the three appends are independent: three CTAs of the cluster take one each (all of them CTA 0 in a one-CTA cluster)
+            const bool vt = P.XLg != nullptr, hasw_ = (P.kind == KIND_ISING);
+            const int nwoff_ = P.n[1];
+            // node value / weight of mode index idx: from the staged vectors when it lies inside them (always for equal mode sizes)
+            auto nodev = [&](int idx) { return idx <= n1 ? S.NX[idx - 1] : P.par[idx - 1]; };
+            auto nodew = [&](int idx) { return idx <= n1 ? S.NW[idx - 1] : P.par[nwoff_ + idx - 1]; };
             if (crank == 0) {
                 if (threadIdx.x == 0) { int* vp = P.vip + ((i64)p * P.Rmax + t) * 4; vp[0] = ii; vp[1] = jj; vp[2] = kk; vp[3] = qq; }
                 int* Lp = P.Lidx + P.offL[p];
                 const int* Lm = P.Lidx + P.offL[p - 1];
-                const bool vt = P.XLg != nullptr, hasw_ = (P.kind == KIND_ISING);
-                const i64 oLp = P.offL[p] / P.Rmax * P.RT, oRp = P.offR[p] / P.Rmax * P.RT;
-                const int nwoff_ = P.n[1];
+                const i64 oLp = P.offL[p] / P.Rmax * P.RT;
                 for (int pos = threadIdx.x; pos < p; pos += blockDim.x) {
                     const int idx = (pos < p - 1) ? LDF(Lm + (i64)pos * P.Rmax + (ii - 1)) : jj;
                     Lp[(i64)pos * P.Rmax + t] = idx;
-                    if (vt) { P.XLg[oLp + (i64)pos * P.RT + t] = P.par[idx - 1]; if (hasw_) P.WLg[oLp + (i64)pos * P.RT + t] = P.par[nwoff_ + idx - 1]; }
+                    if (vt) { P.XLg[oLp + (i64)pos * P.RT + t] = nodev(idx); if (hasw_) P.WLg[oLp + (i64)pos * P.RT + t] = nodew(idx); }
                 }
+                if (vt) fence_proxy_async();          // the TMA of later visits reads these tables through the async proxy
+            }
+            if (crank == 1 % cs) {
                 int* Rp = P.Ridx + P.offR[p];
                 const int* Rn = P.Ridx + P.offR[p + 1];
+                const i64 oRp = P.offR[p] / P.Rmax * P.RT;
                 for (int pos = threadIdx.x; pos < P.d - p; pos += blockDim.x) {
                     const int idx = (pos == 0) ? kk : LDF(Rn + (i64)(pos - 1) * P.Rmax + (qq - 1));
                     Rp[(i64)pos * P.Rmax + t] = idx;
-                    if (vt) { P.XRg[oRp + (i64)pos * P.RT + t] = P.par[idx - 1]; if (hasw_) P.WRg[oRp + (i64)pos * P.RT + t] = P.par[nwoff_ + idx - 1]; }
+                    if (vt) { P.XRg[oRp + (i64)pos * P.RT + t] = nodev(idx); if (hasw_) P.WRg[oRp + (i64)pos * P.RT + t] = nodew(idx); }
                 }
-                if (vt) fence_proxy_async();          // the TMA of later visits reads these tables through the async proxy
+                if (vt) fence_proxy_async();
+            }
+            if (crank == 2 % cs) {
                 // packed LU: [ col(ii,jj,1:r) | row(1:r,kk,qq) | pivot ]
                 double* g = P.inv + (i64)p * P.Rmax * P.Rmax;
-                for (int s = threadIdx.x; s < r1; s += blockDim.x) {
-                    g[(i64)r1 * r1 + s] = LDF(colp + (ii - 1) + (i64)P.Rmax * (jj - 1) + s * cs_);
-                    g[(i64)r1 * r1 + r1 + s] = LDF(rowp + (kk - 1) + (i64)n2 * (qq - 1) + s * rs_);
+                for (int s = threadIdx.x; s < 2 * r1; s += blockDim.x) {
+                    const int s1 = s < r1 ? s : s - r1;
+                    g[(i64)r1 * r1 + s] = s < r1 ? LDF(colp + (ii - 1) + (i64)P.Rmax * (jj - 1) + s1 * cs_) : LDF(rowp + (kk - 1) + (i64)n2 * (qq - 1) + s1 * rs_);
                 }
                 if (threadIdx.x == 0) g[(i64)(r1 + 1) * (r1 + 1) - 1] = pivot;
             }
@@ -804,17 +899,34 @@ __device__ __forceinline__ void visit_list(const DevPlan& P, cg::cluster_group& 
                 double* colw = P.col + P.coreOff[p];
                 double* roww = P.rowT + P.coreOff[p + 1];
                 const double sc = 1.0 / pivot;
-                for (int e = gtid; e < ccount + rcount; e += gthreads) {
-                    if (e < ccount) {
-                        const int j = e / r0, i = e % r0;
-                        const i64 o = i + (i64)P.Rmax * (j + (i64)n1 * t);
-                        argp[o] = LDF(fa_c + e);
-                        colw[o] = sc * LDF(fb_c + e);
-                    } else {
-                        const int x = e - ccount;
-                        const int q = x / n2, k = x % n2;
-                        argn[t + (i64)P.Rmax * (k + (i64)n2 * q)] = LDF(fa_r + x);
-                        roww[k + (i64)n2 * (q + (i64)P.Rmax * t)] = LDF(fb_r + x);
+                // (the loads of a batch are all in flight before the first store: one L2 round trip per batch, not per element)
+                constexpr int AU = 4;
+                const int tot = ccount + rcount;
+                for (int e0 = gtid; e0 < tot; e0 += AU * gthreads) {
+                    double va[AU], vb[AU];
+#pragma unroll
+                    for (int u = 0; u < AU; ++u) {
+                        const int e = e0 + u * gthreads;
+                        const bool isc = e < ccount;
+                        const int x = isc ? e : e - ccount;
+                        va[u] = e < tot ? LDF((isc ? fa_c : fa_r) + x) : 0.0;
+                        vb[u] = e < tot ? LDF((isc ? fb_c : fb_r) + x) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < AU; ++u) {
+                        const int e = e0 + u * gthreads;
+                        if (e >= tot) continue;
+                        if (e < ccount) {
+                            const int j = e / r0, i = e % r0;
+                            const i64 o = i + (i64)P.Rmax * (j + (i64)n1 * t);
+                            argp[o] = va[u];
+                            colw[o] = sc * vb[u];
+                        } else {
+                            const int x = e - ccount;
+                            const int q = x / n2, k = x % n2;
+                            argn[t + (i64)P.Rmax * (k + (i64)n2 * q)] = va[u];
+                            roww[k + (i64)n2 * (q + (i64)P.Rmax * t)] = vb[u];
+                        }
                     }
                 }
             }
