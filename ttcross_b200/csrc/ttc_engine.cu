@@ -146,7 +146,7 @@ struct ttc_handle {
     size_t sm_sbt = 0; bool sbt_ok = false;      // tiled superblock kernel (ttc_superblock.cuh)
     int cluster_size = 16, cluster_threads = 256;   // measured best on B200 (16 x 256 beats the portable 8 x 512 by 7 %)
     size_t sm_visit = 0; bool cluster_ok = false;
-    int sweep_threads = 256;                       // CTA size of the persistent kernel (TTC_SWEEP_THREADS)
+    int sweep_threads = 256, sweep_cluster = 16;   // geometry of the persistent kernel (chosen in setup_device; TTC_SWEEP_THREADS / TTC_SWEEP_CLUSTER)
     bool persist_ok = false;                       // the persistent sweep kernel (ttc_sweep.cuh) fits the device in one cooperative wave
     double* chainS = nullptr;                      // [maxsweeps][P + 1][Rmax^2] chain products of the per-sweep quadrature after the loop
     int nsm = 148;
@@ -703,24 +703,38 @@ int setup_device(ttc_handle* h, int maxrank) {
             D.mail = dmail; D.win_mail = 0; D.chainS = nullptr;
         }
         h->persist_ok = false;
-        h->sweep_threads = std::min(h->cluster_threads, SWEEP_MAXTHREADS);
-        if (const char* e = std::getenv("TTC_SWEEP_THREADS")) h->sweep_threads = std::max(32, std::min(SWEEP_MAXTHREADS, std::atoi(e) / 32 * 32));
+        // geometry of the persistent kernel: every cluster of the process must be resident at once.  The kernel runs at one
+        // CTA of 256 threads per SM (255 registers: the factor prefetch of the fiber loop), and this B200 has seven GPCs of
+        // ~20 SMs and one of 8 (measured with cudaOccupancyMaxActiveClusters: 7 clusters of 12..16 CTAs at one CTA per SM, 15 of
+        // 8), so the candidates are tried from the most threads per partition downwards and the first that fits is taken:
+        // 16 x 256 (up to 7 partitions), 16 x 128 (two CTAs per SM where needed: 14), 8 x 256 (15), 8 x 128, 4 x 128 ...
+        h->sweep_threads = 0; h->sweep_cluster = 0;
         if (h->cluster_ok && (h->nproc == 1 || h->p2p) && !std::getenv("TTC_NO_PERSISTENT")) {
+            std::vector<std::pair<int, int>> cand = {{16, 256}, {16, 128}, {8, 256}, {8, 128}, {4, 128}, {2, 128}, {1, 128}};
+            if (std::getenv("TTC_SWEEP_THREADS") || std::getenv("TTC_SWEEP_CLUSTER")) {
+                const int cs = std::getenv("TTC_SWEEP_CLUSTER") ? std::atoi(std::getenv("TTC_SWEEP_CLUSTER")) : 16;
+                const int th = std::getenv("TTC_SWEEP_THREADS") ? std::atoi(std::getenv("TTC_SWEEP_THREADS")) : 256;
+                cand = {{std::max(1, std::min(MAXCS, cs)), std::max(32, std::min(SWEEP_MAXTHREADS, th / 32 * 32))}};
+            }
             cudaError_t ce = cudaSuccess;
             VISIT_KIND_SWITCH(h,
                 ce = cudaFuncSetAttribute(k_sweeps<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_visit);
-                if (ce == cudaSuccess && h->cluster_size > 8) ce = cudaFuncSetAttribute(k_sweeps<K>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+                if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_sweeps<K>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             );
-            if (ce == cudaSuccess) {
+            for (size_t ci = 0; ci < cand.size() && ce == cudaSuccess && !h->persist_ok; ++ci) {
+                const int cs = cand[ci].first, th = std::min(cand[ci].second, SWEEP_MAXTHREADS);
                 cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(h->cluster_size, D.nv, 1); cfg.blockDim = dim3(h->sweep_threads, 1, 1); cfg.dynamicSmemBytes = h->sm_visit;
+                cfg.gridDim = dim3(cs, D.nv, 1); cfg.blockDim = dim3(th, 1, 1); cfg.dynamicSmemBytes = h->sm_visit;
                 cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
-                at[0].val.clusterDim.x = h->cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 cfg.attrs = at; cfg.numAttrs = 1;
                 int ncl = 0;
-                VISIT_KIND_SWITCH(h, ce = cudaOccupancyMaxActiveClusters(&ncl, k_sweeps<K>, &cfg));
-                h->persist_ok = (ce == cudaSuccess) && ncl >= D.nv && P <= 64;
-                if (std::getenv("TTC_TRACE")) std::fprintf(stderr, "[ttc trace] persistent kernel: %d clusters of %d x %d threads resident at once (need %d), smem %zu B: %s\n", ncl, h->cluster_size, h->sweep_threads, D.nv, h->sm_visit, h->persist_ok ? "on" : "off");
+                cudaError_t c2 = cudaSuccess;
+                VISIT_KIND_SWITCH(h, c2 = cudaOccupancyMaxActiveClusters(&ncl, k_sweeps<K>, &cfg));
+                if (c2 != cudaSuccess) { (void)cudaGetLastError(); ncl = 0; }
+                h->persist_ok = ncl >= D.nv && P <= 64;
+                if (h->persist_ok) { h->sweep_cluster = cs; h->sweep_threads = th; }
+                if (std::getenv("TTC_TRACE")) std::fprintf(stderr, "[ttc trace] persistent kernel: %d clusters of %d x %d threads resident at once (need %d), smem %zu B: %s\n", ncl, cs, th, D.nv, h->sm_visit, h->persist_ok ? "on" : "off");
             }
             if (ce != cudaSuccess) (void)cudaGetLastError();
         }
@@ -1283,13 +1297,13 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     const bool use_graph = !persistent && !sync_mode && !h->profile && !h->no_graph && (!multi || h->p2p || std::getenv("TTC_MP_GRAPH") != nullptr);
     if (persistent) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(h->cluster_size, NV, 1);
+        cfg.gridDim = dim3(h->sweep_cluster, NV, 1);
         cfg.blockDim = dim3(h->sweep_threads, 1, 1);
         cfg.dynamicSmemBytes = h->sm_visit;
         cfg.stream = s;
         cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = h->cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[0].val.clusterDim.x = h->sweep_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
         cfg.attrs = at; cfg.numAttrs = 2;
         cudaError_t ce = cudaSuccess;
