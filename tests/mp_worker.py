@@ -4,7 +4,8 @@ Every rank runs the same problem with the same partition through the C-ABI; the 
 fibers and quadrature chains over NCCL.  Rank 0 compares tape / ranks / neval / values / gathered cores with the CPU
 oracle run at the SAME partition (results are a function of the partition, not of the GPU count).
 
-usage: mp_worker.py KIND INDEX N RANK PIV PARTS [mvn|ising|stdnorm]
+usage: mp_worker.py KIND INDEX N RANK PIV PARTS [mvn|ising|stdnorm] [EXP_MODE]
+(EXP_MODE 1: both sides evaluate exp through include/ttc_detexp.h, so the exp-based integrands are compared bit for bit too)
 """
 import os
 import sys
@@ -24,6 +25,7 @@ def main():
 
     kind, index, n, R, piv, parts = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
     family = sys.argv[7] if len(sys.argv) > 7 else "ising"
+    exp_mode = int(sys.argv[8]) if len(sys.argv) > 8 else 0
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")          # plumbing only: the unique id travels as a Python object
@@ -33,9 +35,10 @@ def main():
         p = T.drivers.mvn(index, n)
     else:
         p = T.drivers.stdnorm(index, n)
-    exact = family == "ising"
+    exact = family == "ising" or exp_mode == 1
     t = p.make(device=local)
     t.set_partition(parts)
+    t.set_exp_mode(exp_mode)
     T.multi.attach(t, dist)
     ok = True
     msg = ""
@@ -47,7 +50,9 @@ def main():
         exp_lo, exp_hi = T.multi.core_block(T.multi.share(1, p.d - 1, parts), parts, world, rank, p.d)
         assert (lo, hi) == (exp_lo, exp_hi), ((lo, hi), (exp_lo, exp_hi))
         if rank == 0:
-            o = O.Oracle(to_oracle_setup(p)).run(maxrank=R, piv=piv, P=parts, accuracy=p.accuracy, seed=1)
+            orc = O.Oracle(to_oracle_setup(p))
+            orc.set_exp_mode(exp_mode)
+            o = orc.run(maxrank=R, piv=piv, P=parts, accuracy=p.accuracy, seed=1)
             try:
                 assert np.array_equal(g.pivlog, o.pivlog), "pivot tape indices differ"
                 assert np.array_equal(g.ranks, o.ranks), (g.ranks, o.ranks)

@@ -71,7 +71,8 @@ def test_unique_id_handoff_over_gloo_world2(has_gpu):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cfg", ["c 6 16 8 1 2", "c 10 32 10 2 8", "c 10 32 10 2 3", "e 6 16 8 2 4", "c 8 12 6 -1 3", "x 6 16 6 1 2 mvn"])
+@pytest.mark.parametrize("cfg", ["c 6 16 8 1 2", "c 10 32 10 2 8", "c 10 32 10 2 3", "e 6 16 8 2 4", "c 8 12 6 -1 3", "x 6 16 6 1 2 mvn",
+                                 "x 12 16 6 1 5 mvn 1", "x 8 17 6 2 4 stdnorm 1"])
 def test_two_gpus_match_oracle_at_same_partition(cfg):
     import torch
     if torch.cuda.device_count() < 2:

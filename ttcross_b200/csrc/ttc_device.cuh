@@ -138,6 +138,7 @@ struct DevPlan {
     // that the TMA copies into shared memory (cp.async.bulk) instead of a gather through the index tables; parT = nodes | weights,
     // each padded to NT (even) entries.  Null when the persistent kernel is not in use.
     double* XLg; double* WLg; double* XRg; double* WRg; const double* parT; int RT, NT;
+    int auxsm_p;           // doubles of shared memory the PERSISTENT kernel reserves for the MVN matrix (>= auxsm)
     int exp_mode;          // 0: platform exp; 1: the deterministic exp of include/ttc_detexp.h (parity mode, ttc_set_exp_mode)
 };
 __device__ __forceinline__ double plan_exp(const DevPlan& P, double x) { return P.exp_mode ? ttc_det_exp(x) : exp(x); }

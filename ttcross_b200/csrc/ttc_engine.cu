@@ -145,7 +145,7 @@ struct ttc_handle {
     size_t sm_qinc = 0; int qinc_stage = 0;
     size_t sm_sbt = 0; bool sbt_ok = false;      // tiled superblock kernel (ttc_superblock.cuh)
     int cluster_size = 16, cluster_threads = 256;   // measured best on B200 (16 x 256 beats the portable 8 x 512 by 7 %)
-    size_t sm_visit = 0; bool cluster_ok = false;
+    size_t sm_visit = 0, sm_sweep = 0; bool cluster_ok = false;
     int sweep_threads = 256, sweep_cluster = 16;   // geometry of the persistent kernel (chosen in setup_device; TTC_SWEEP_THREADS / TTC_SWEEP_CLUSTER)
     bool persist_ok = false;                       // the persistent sweep kernel (ttc_sweep.cuh) fits the device in one cooperative wave
     double* chainS = nullptr;                      // [maxsweeps][P + 1][Rmax^2] chain products of the per-sweep quadrature after the loop
@@ -666,7 +666,11 @@ int setup_device(ttc_handle* h, int maxrank) {
         if (const char* e = std::getenv("TTC_CLUSTER_SIZE")) h->cluster_size = std::atoi(e);
         if (const char* e = std::getenv("TTC_CLUSTER_THREADS")) h->cluster_threads = std::atoi(e);
         const size_t RE = std::max(Rmax, 32);       // (the exchange of the persistent kernel stages a 32 x 32 packed block)
+        D.auxsm_p = D.auxsm;
+        if (h->kind == TTC_MVN && (size_t)d * d * sizeof(double) <= 64 * 1024) D.auxsm_p = (d * d + 1) & ~1;
         h->sm_visit = ((size_t)D.auxsm + 5 * (size_t)Rmax + RE * RE + RE + D.stage_max + 2) * sizeof(double) + (size_t)(4 * Rmax + 8) * sizeof(int);
+        h->sm_sweep = h->sm_visit + (size_t)(std::max(D.auxsm, D.auxsm_p) - D.auxsm) * sizeof(double);
+        if (h->sm_sweep > 200 * 1024) { D.auxsm_p = D.auxsm; h->sm_sweep = h->sm_visit; }
         h->cluster_ok = D.stage && h->use_wave && h->sm_visit <= 200 * 1024 && h->cluster_size >= 1 && h->cluster_size <= MAXCS && h->cluster_threads >= 32 &&
                         h->cluster_threads <= VISIT_MAXTHREADS && h->cluster_threads % 32 == 0 &&
                         !std::getenv("TTC_NO_CLUSTER");
@@ -718,13 +722,13 @@ int setup_device(ttc_handle* h, int maxrank) {
             }
             cudaError_t ce = cudaSuccess;
             VISIT_KIND_SWITCH(h,
-                ce = cudaFuncSetAttribute(k_sweeps<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_visit);
+                ce = cudaFuncSetAttribute(k_sweeps<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_sweep);
                 if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_sweeps<K>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             );
             for (size_t ci = 0; ci < cand.size() && ce == cudaSuccess && !h->persist_ok; ++ci) {
                 const int cs = cand[ci].first, th = std::min(cand[ci].second, SWEEP_MAXTHREADS);
                 cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(cs, D.nv, 1); cfg.blockDim = dim3(th, 1, 1); cfg.dynamicSmemBytes = h->sm_visit;
+                cfg.gridDim = dim3(cs, D.nv, 1); cfg.blockDim = dim3(th, 1, 1); cfg.dynamicSmemBytes = h->sm_sweep;
                 cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
                 at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 cfg.attrs = at; cfg.numAttrs = 1;
@@ -734,7 +738,7 @@ int setup_device(ttc_handle* h, int maxrank) {
                 if (c2 != cudaSuccess) { (void)cudaGetLastError(); ncl = 0; }
                 h->persist_ok = ncl >= D.nv && P <= 64;
                 if (h->persist_ok) { h->sweep_cluster = cs; h->sweep_threads = th; }
-                if (std::getenv("TTC_TRACE")) std::fprintf(stderr, "[ttc trace] persistent kernel: %d clusters of %d x %d threads resident at once (need %d), smem %zu B: %s\n", ncl, cs, th, D.nv, h->sm_visit, h->persist_ok ? "on" : "off");
+                if (std::getenv("TTC_TRACE")) std::fprintf(stderr, "[ttc trace] persistent kernel: %d clusters of %d x %d threads resident at once (need %d), smem %zu B: %s\n", ncl, cs, th, D.nv, h->sm_sweep, h->persist_ok ? "on" : "off");
             }
             if (ce != cudaSuccess) (void)cudaGetLastError();
         }
@@ -1299,7 +1303,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(h->sweep_cluster, NV, 1);
         cfg.blockDim = dim3(h->sweep_threads, 1, 1);
-        cfg.dynamicSmemBytes = h->sm_visit;
+        cfg.dynamicSmemBytes = h->sm_sweep;
         cfg.stream = s;
         cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;

@@ -307,7 +307,7 @@ __device__ __forceinline__ double exchange_boundaries(const DevPlan& P, cg::clus
 #endif
 constexpr int SWEEP_MAXTHREADS = TTC_SWEEP_MAXT;
 template <int KIND>
-__global__ void __launch_bounds__(SWEEP_MAXTHREADS, KIND == KIND_MVN ? 4 : TTC_SWEEP_MINB)
+__global__ void __launch_bounds__(SWEEP_MAXTHREADS, TTC_SWEEP_MINB)
 k_sweeps(DevPlan P, int it_last, int maxrank, double small_element, double small_pivot) {
     tl_stamp(P, 36);
     cg::cluster_group cl = cg::this_cluster();
@@ -320,8 +320,15 @@ k_sweeps(DevPlan P, int it_last, int maxrank, double small_element, double small
     C.sh = &sh;
     C.v = P.v0 + blockIdx.y;
     C.lo = P.own[C.v]; C.hi = P.own[C.v + 1];
-    C.A = stage_aux<KIND>(P, smem);
-    C.xs = smem + P.auxsm;
+    // MVN: the d x d matrix in shared memory whenever the host made room for it (auxsm_p; the per-sweep kernels keep it in
+    // global memory beyond 8 KB because they run 4 CTAs per SM)
+    const int auxd = KIND == KIND_MVN ? max(P.auxsm, P.auxsm_p) : 0;
+    if (KIND == KIND_MVN && auxd >= P.d * P.d) {
+        for (int x = threadIdx.x; x < P.d * P.d; x += blockDim.x) smem[x] = P.aux[P.d + x];
+        __syncthreads();
+        C.A = smem;
+    } else C.A = stage_aux<KIND>(P, smem);
+    C.xs = smem + auxd;
     C.pre = C.xs + P.Rmax;
     C.ext = C.pre + 4 * (i64)P.Rmax;
     C.stg = C.ext + (i64)max(P.Rmax, 32) * max(P.Rmax, 32) + max(P.Rmax, 32);
@@ -369,7 +376,7 @@ k_sweeps(DevPlan P, int it_last, int maxrank, double small_element, double small
         const int par = it & 1;
         const unsigned long long seq = seq0 + (unsigned long long)it;
         C.rkL = sl.rkL; C.rkR = sl.rkR;
-        visit_list<KIND, true>(P, cl, C, it, dir, small_element, small_pivot);      // ends with a cluster barrier
+        visit_list<KIND, true, true>(P, cl, C, it, dir, small_element, small_pivot);      // ends with a cluster barrier
 
         // ---- several processes: the first / last partition of a process pushes what its foreign neighbour needs straight into
         // that process's window over NVLink (the tape of dmrgg.f90:763-850 reduced to the one table column the neighbour will

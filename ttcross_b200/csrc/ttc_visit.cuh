@@ -559,7 +559,7 @@ struct VisitCtx {
     int upd_first, upd_last;   // out: was the partition's first / last bond updated in this sweep (uniform over the cluster)
     unsigned long long* bar; unsigned bar_parity;     // TMA staging (persistent kernel): CTA-local mbarrier and its phase
 };
-template <int KIND, bool TMA = false>
+template <int KIND, bool TMA = false, bool WIDE = false>
 __device__ __forceinline__ void visit_list(const DevPlan& P, cg::cluster_group& cl, VisitCtx& C, int it, int dir, double small_element, double small_pivot) {
     VisitShared& sh = *C.sh;
     const int crank = (int)cl.block_rank(), cs = (int)cl.num_blocks();
@@ -666,7 +666,7 @@ __device__ __forceinline__ void visit_list(const DevPlan& P, cg::cluster_group& 
                 const int c = cell;
                 const int i = (c - 1) % r0 + 1, j = (c - 1) / r0 + 1, k = (w - 1) % n2 + 1, q = (w - 1) / n2 + 1;
                 StagedVals sv = S.point(i, j, k, q);
-                const double f = eval_point<KIND>(P, sv, A);
+                const double f = WIDE ? eval_point_wide<KIND>(P, sv, A) : eval_point<KIND>(P, sv, A);
                 tl_mark(P, 56);
                 const double res = resid_ddot2_cg(f, colp + (i - 1) + (i64)P.Rmax * (j - 1), cs_, rowp + (k - 1) + (i64)n2 * (q - 1), rs_, r1);
                 braw = fmax(braw, fabs(f));
@@ -744,21 +744,37 @@ __device__ __forceinline__ void visit_list(const DevPlan& P, cg::cluster_group& 
             } else {
             for (e = gtid; e < count; e += gthreads) {
                 double f, res;
+                if (KIND == KIND_MVN) {
+                    // an MVN evaluation is a 3 d^2-long dependent chain (tens of microseconds): nothing to hide behind it, and the
+                    // register-resident evaluation wants every register -> factor values are loaded AFTER it, in batches
+                    if (!isrow) {
+                        const int j = e / r0 + 1, i = e % r0 + 1;
+                        StagedVals sv = S.point(i, j, kk, qq);
+                        f = WIDE ? eval_point_wide<KIND>(P, sv, A) : eval_point<KIND>(P, sv, A);
+                        res = resid_axpy_cg(f, colp + (i - 1) + (i64)P.Rmax * (j - 1), cs_, xs, r1);
+                    } else {
+                        const int q = e / n2 + 1, k = e % n2 + 1;
+                        StagedVals sv = S.point(ii, jj, k, q);
+                        f = WIDE ? eval_point_wide<KIND>(P, sv, A) : eval_point<KIND>(P, sv, A);
+                        res = resid_dot_cg(f, rowp + (k - 1) + (i64)n2 * (q - 1), rs_, xs, r1);
+                    }
+                } else {
                 Pref pf;
                 if (!isrow) {
                     const int j = e / r0 + 1, i = e % r0 + 1;
                     const double* base = colp + (i - 1) + (i64)P.Rmax * (j - 1);
                     pref_load(pf, base, cs_, r1);
                     StagedVals sv = S.point(i, j, kk, qq);
-                    f = eval_point<KIND>(P, sv, A);
+                    f = WIDE ? eval_point_wide<KIND>(P, sv, A) : eval_point<KIND>(P, sv, A);
                     res = resid_axpy_pf(f, pf, base, cs_, xs, r1);
                 } else {
                     const int q = e / n2 + 1, k = e % n2 + 1;
                     const double* base = rowp + (k - 1) + (i64)n2 * (q - 1);
                     pref_load(pf, base, rs_, r1);
                     StagedVals sv = S.point(ii, jj, k, q);
-                    f = eval_point<KIND>(P, sv, A);
+                    f = WIDE ? eval_point_wide<KIND>(P, sv, A) : eval_point<KIND>(P, sv, A);
                     res = resid_dot_pf(f, pf, base, rs_, xs, r1);
+                }
                 }
                 fa[e] = f;
                 fb[e] = res;
