@@ -25,8 +25,30 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = ("c", 10, 256, 32, 2)     # kind, index, N, RANK, PIV  (BASELINE.json configs[1])
-PARTITIONS = 8
+# BASELINE.json configs: name -> (family, driver arguments, RANK, PIV, partitions, label).  B is the headline (configs[1]).
+CONFIGS = {
+    "A": ("ising", ("c", 6, 64), 16, 1, 4, "test_crs_ising c 6 64 16 1"),
+    "B": ("ising", ("c", 10, 256), 32, 2, 8, "test_crs_ising c 10 256 32 2"),
+    "C": ("ising", ("d", 8, 256), 48, 2, 6, "test_crs_ising d 8 256 48 2"),
+    "D": ("ising", ("e", 6, 512), 64, 3, 4, "test_crs_ising e 6 512 64 3"),
+    "E": ("mvn", (64, 128), 32, 1, 63, "test_crs_mvn 64 128 32 (pivoting 1)"),
+}
+
+
+L2_NOTE = "GPU arm: L2 flushed between timed steps (256 MiB write); working set < 126 MB L2"
+
+
+def make_problem(T, name):
+    fam, a, R, piv, P, label = CONFIGS[name]
+    prob = T.drivers.ising(*a) if fam == "ising" else T.drivers.mvn(*a)
+    return prob, R, piv, P, label
+
+
+def flops_per_eval(fam, a, d):
+    """operations of one integrand evaluation (Ising C 5d+3; D/E add the d(d+1)/2 pair products; MVN 3d^2 + d)."""
+    if fam == "mvn":
+        return 3 * d * d + d
+    return 5 * d + 3 if a[0] == "c" else 5 * d + 3 + 5 * (d * (d + 1) // 2)
 
 
 def _peaks():
@@ -91,21 +113,26 @@ class ClockSampler:
 
 
 def reference_arm(args):
-    """CPU baseline: the oracle (a restatement of the reference, kind = "port") on all host threads."""
+    """CPU arm: the oracle (a restatement of the reference, kind = "port": the Fortran reference cannot be built -- there is no
+    gfortran / mpif90 / BLAS in the image or on the GPU box, profiles/r02_toolchain_probe.txt) with every host core: the
+    virtual ranks run concurrently like the reference's MPI ranks, each with an OpenMP team for its evaluation loops."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle as O
-    kind, index, n, R, piv = WORKLOAD
-    s = O.ising_setup(kind, index, n)
+    fam, a, R, piv, P, label = CONFIGS[args.config]
+    s = O.ising_setup(*a) if fam == "ising" else O.mvn_setup(*a)
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    O.lib().tto_set_num_threads(ncpu)          # explicit: torchrun exports OMP_NUM_THREADS=1 to its children
+    O.lib().tto_set_rank_concurrency(1)
     cores = O.lib().tto_num_threads()
     o = O.Oracle(s)
     for _ in range(args.warmup):
-        o.run(maxrank=R, piv=piv, P=PARTITIONS)
+        o.run(maxrank=R, piv=piv, P=P)
     t0 = time.perf_counter()
     neval = 0
     for _ in range(args.steps):
-        r = o.run(maxrank=R, piv=piv, P=PARTITIONS)
+        r = o.run(maxrank=R, piv=piv, P=P)
         neval += r.neval
     dt = time.perf_counter() - t0
     v = neval / dt
@@ -113,10 +140,10 @@ def reference_arm(args):
         "impl": "reference", "metric": "integrand_evals_per_s", "value": v, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "test_crs_ising c 10 256 32 2", "partitions": PARTITIONS, "neval_per_step": neval // args.steps},
+        "config": {"workload": label, "partitions": P, "neval_per_step": neval // args.steps, "l2": L2_NOTE},
         "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} full runs of the workload (CPU restatement of dtt_dmrgg, OpenMP over evaluations; "
-                                   "the Fortran reference cannot be built: no gfortran/MPI/BLAS)"},
+                         "sample": f"{args.steps} full runs of the workload (CPU restatement of dtt_dmrgg: {P} virtual ranks side by side, "
+                                   f"OpenMP inside each, {cores} threads in all; the Fortran reference cannot be built: no gfortran/MPI/BLAS)"},
         "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -130,6 +157,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-superblock", action="store_true")
+    ap.add_argument("--config", default="B", choices=sorted(CONFIGS), help="BASELINE.json configuration (B = the headline workload)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -151,8 +179,9 @@ def main():
         dist_mod.init_process_group("nccl")
         dist = dist_mod
 
-    kind, index, n, R, piv = WORKLOAD
-    prob = T.drivers.ising(kind, index, n)
+    fam, cargs, _, _, _, _ = CONFIGS[args.config]
+    prob, R, piv, PARTITIONS, label = make_problem(T, args.config)
+    PARTITIONS = max(PARTITIONS, world)
     hbm_peak, peak_src = _peaks()
 
     def barrier():
@@ -178,12 +207,14 @@ def main():
     launches0 = t.launch_count()
     barrier()
     t_timed_begin = time.perf_counter()
-    dev_ms = []
+    dev_ms, sweep_ms = [], []
     wall0 = time.perf_counter()
     for _ in range(args.steps):
         t.l2_flush()                       # cold L2 between timed iterations (working set < 126 MB L2)
         g = t.dmrgg(R, prob.accuracy, piv)
         dev_ms.append(g.device_ms)
+        sweep_ms.append(t.sweep_kernel()[1])           # CUDA events on the library's stream around the persistent kernel
+    persistent, _, sweep_cluster, sweep_threads = t.sweep_kernel()
     barrier()
     wall = time.perf_counter() - wall0
     launches = t.launch_count() - launches0
@@ -256,54 +287,87 @@ def main():
     own = T.multi.share(1, prob.d - 1, PARTITIONS)
     v0, v1 = T.multi.block_of(PARTITIONS, world, rank)
     my_bonds = list(range(int(own[v0]), int(own[v1])))
-    byt, flo = [], []
+    fpe = flops_per_eval(fam, cargs, prob.d)
+    byt, flo, evs = [], [], []
     for it in range(1, int(g.nsweeps) + 1):
         b = f = 0.0
+        e_ = 0
         for pb in my_bonds:
             r0, r1, r2 = (min(it, int(ranks[q])) for q in (pb - 1, pb, pb + 1))
             nlot, ncol, nrow = r0 + 2 * nn + r2, r0 * nn, nn * r2
-            ev = nlot + piv * (ncol + nrow)
-            b += nlot * 16.0 * r1 + piv * (ncol + nrow) * (8.0 * r1 + 16.0) + (ncol + nrow) * 32.0
-            f += ev * (5 * prob.d + 3 + 2 * r1)
+            ev = nlot + max(piv, 1) * (ncol + nrow)
+            b += nlot * 16.0 * r1 + max(piv, 1) * (ncol + nrow) * (8.0 * r1 + 16.0) + (ncol + nrow) * 32.0
+            f += ev * (fpe + 2 * r1)
+            e_ += ev
         byt.append(b)
         flo.append(f)
-    dom_name = "bond_visits_cluster" if prof.get("bond_visits_cluster", (0, 0))[0] else "fiber_eval_residual"
-    fl, fms = prof[dom_name]
-    dom_avg_ms = fms / max(fl, 1)
-    per_launch_bytes = float(np.mean(byt)) * (1.0 if dom_name == "bond_visits_cluster" else 1.0 / (2 * piv + 1))
-    achieved = per_launch_bytes / (dom_avg_ms * 1e-3) / 1e9
+        evs.append(e_)
     ncu = {}
+    for fn in ("r02_ncu_summary.json", "r01_ncu_summary.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as fjs:
+                ncu = json.load(fjs)
+            break
+        except Exception:
+            pass
+    pk_nofma_bench = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")) as fjs:
-            ncu = json.load(fjs)
+        pk_nofma_bench = T.fp64_peak(local_rank, False)
     except Exception:
         pass
-    traffic = ncu.get("k_visits", {}).get("dram_bytes_per_launch") if dom_name == "bond_visits_cluster" else None
-    roofline = {"kernel": "k_visits (cluster per partition: lottery + rook fibers + residuals + argmax folds + rank-1 append)"
-                if dom_name == "bond_visits_cluster" else "k_fiber", "bound": "hbm", "achieved": achieved,
-                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": per_launch_bytes, "algorithmic_flops_per_launch": float(np.mean(flo)),
-                "share_of_step": fms / tot_ms if tot_ms else None, "avg_launch_us": 1e3 * dom_avg_ms,
-                "note": "latency-bound by construction (a sweep is ~6 dependent steps of <= 8224 evaluations per partition, SURVEY F4): "
-                        "the factors stay in the 126 MB L2 (ncu DRAM traffic per launch in `traffic`), so neither roofline binds; "
-                        "the roofline-sized kernel of the path is reported in roofline_superblock"}
+    if persistent:
+        # dominant kernel = the persistent sweep kernel k_sweeps (ttc_sweep.cuh): ONE launch runs every sweep of the step
+        dom_ms = float(np.mean(sweep_ms))
+        per_launch_bytes, per_launch_flops = float(np.sum(byt)), float(np.sum(flo))
+        strict_bytes = 8.0 * float(np.sum(evs))
+        achieved = per_launch_bytes / (dom_ms * 1e-3) / 1e9
+        tflops = per_launch_flops / (dom_ms * 1e-3) / 1e12
+        roofline = {"kernel": f"k_sweeps (persistent cooperative kernel, {sweep_cluster} CTAs x {sweep_threads} threads per partition: all sweeps of the step -- "
+                              "TMA-staged pivot tables, lottery, rook fibers + residuals, cluster argmax folds, rank-1 append, neighbour exchange, exit test)",
+                    "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": ncu.get("k_sweeps", {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": per_launch_bytes,
+                    "algorithmic_bytes_per_launch_strict_8B_per_evaluation": strict_bytes, "frac_strict": strict_bytes / (dom_ms * 1e-3) / 1e9 / hbm_peak,
+                    "algorithmic_flops_per_launch": per_launch_flops, "achieved_tflops": tflops,
+                    "fp64_frac_of_dmul_dadd_peak": (tflops / pk_nofma_bench) if pk_nofma_bench else None,
+                    "share_of_step": dom_ms / ms_step if ms_step else None, "avg_launch_us": 1e3 * dom_ms, "launches_per_step": 1,
+                    "timing": "CUDA events recorded by the library on its own stream around the launch (ttc_sweep_kernel_ms), mean over the timed steps",
+                    "note": "latency-bound by construction: a sweep is a chain of ~6 dependent steps of <= r*n evaluations per partition, each ending in a "
+                            "cluster-wide first-index argmax (SURVEY F4); the factors stay in the 126 MB L2, so neither roofline binds -- the algorithmic "
+                            "bytes count the factor values every residual reads (8 r(p) + 16 B per fiber element), the strict figure 8 B per kept evaluation; "
+                            "the roofline-sized kernel of the path is reported in roofline_superblock"}
+    else:
+        dom_name = "bond_visits_cluster" if prof.get("bond_visits_cluster", (0, 0))[0] else "fiber_eval_residual"
+        fl, fms = prof[dom_name]
+        dom_avg_ms = fms / max(fl, 1)
+        per_launch_bytes = float(np.mean(byt)) * (1.0 if dom_name == "bond_visits_cluster" else 1.0 / (2 * max(piv, 1) + 1))
+        achieved = per_launch_bytes / (dom_avg_ms * 1e-3) / 1e9
+        roofline = {"kernel": "k_visits (cluster per partition, one launch per sweep)" if dom_name == "bond_visits_cluster" else "k_fiber",
+                    "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": ncu.get("k_visits", {}).get("dram_bytes_per_launch") if dom_name == "bond_visits_cluster" else None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch_bytes, "algorithmic_flops_per_launch": float(np.mean(flo)),
+                    "share_of_step": fms / tot_ms if tot_ms else None, "avg_launch_us": 1e3 * dom_avg_ms,
+                    "note": "per-sweep schedule (the persistent kernel did not fit this configuration): latency-bound, factors L2-resident"}
 
     line = {
         "metric": "integrand_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "test_crs_ising c 10 256 32 2", "partitions": PARTITIONS,
-                   "partition_map": f"{PARTITIONS} core blocks block-mapped onto {world} GPU(s); per-sweep exchange over the library's NCCL communicator" if world > 1 else f"{PARTITIONS} core blocks batched on one GPU",
-                   "neval_per_step": int(g.neval),
-                   "sweeps": int(g.nsweeps), "final_ranks": [int(x) for x in g.ranks], "l2": "flushed between timed steps (256 MiB write)",
-                   "integral": float(g.vals[-1])},
+        # (the same dict in both arms, so the driver's config comparison holds; what is specific to this run is in `details`)
+        "config": {"workload": label, "partitions": PARTITIONS, "neval_per_step": int(g.neval), "l2": L2_NOTE},
+        "details": {"partition_map": (f"{PARTITIONS} core blocks block-mapped onto {world} GPU(s); per-sweep exchange = stores into the neighbours' peer-memory "
+                                      "windows (CUDA IPC over NVLink) + release/acquire flags inside the persistent kernel; NCCL only hands out the window handles")
+                    if world > 1 else f"{PARTITIONS} core blocks, one cluster each, in one persistent kernel on one GPU",
+                    "schedule": "persistent kernel" if persistent else "per-sweep kernels (CUDA graph)",
+                    "sweeps": int(g.nsweeps), "final_ranks": [int(x) for x in g.ranks], "integral": float(g.vals[-1])},
         "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_mean, "cold_ms_per_step": (1e3 * float(np.mean(cold_t)) if cold_t else None),
                 "handle": "reused across steps (ttc_set_par + ttc_set_quad ship the inputs every step)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
-        "kernel_classes_ms": {k: {"launches": v[0], "ms": v[1]} for k, v in prof.items() if v[0]},
+        "per_sweep_schedule_kernel_classes_ms": {k: {"launches": v[0], "ms": v[1]} for k, v in prof.items() if v[0]},
+        "per_sweep_schedule_note": "diagnostic pass with an event pair around every launch; it runs the per-sweep schedule (k_visits + k_exchange_fused + ...), not the persistent kernel",
         "wall_s_timed_region": wall,
     }
 
@@ -317,7 +381,7 @@ def main():
             sbf = t.superblock_probe(bond, store=False, reps=5, variant=2)
             sbs = t.superblock_probe(bond, store=True, reps=5, variant=0)
             sbp = t.superblock_probe(bond, store=False, reps=2, variant=1)
-            flops = sb["count"] * (5 * prob.d + 3 + 2 * r1)          # 5d+3 per evaluation + 2 r(p) per residual element
+            flops = sb["count"] * (fpe + 2 * r1)          # operations of an evaluation + 2 r(p) per residual element
             def tf(ms):
                 return flops / (ms * 1e-3) / 1e12
             line["roofline_superblock"] = {
@@ -345,6 +409,9 @@ def main():
     if not args.no_cpu_baseline and rank == 0 and args.gpus == 1:
         from oracle import oracle as O
         s = O.Setup(prob.kind, prob.d, prob.n, prob.par, prob.aux, prob.quad, prob.accuracy, prob.tru)
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        O.lib().tto_set_num_threads(ncpu)
+        O.lib().tto_set_rank_concurrency(1)
         o = O.Oracle(s)
         t0 = time.perf_counter()
         reps = 0

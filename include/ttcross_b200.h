@@ -142,6 +142,10 @@ long long ttc_launch_count(const ttc_handle* h);
 /* write `bytes` (> L2 size) of scratch HBM so the next timed run starts with a cold L2 (measurement hygiene) */
 int ttc_l2_flush(ttc_handle* h, long long bytes);
 double ttc_device_ms(const ttc_handle* h);
+/* the persistent sweep kernel (ttc_sweep.cuh): device time of its single launch in the last ttc_dmrgg (0 when the per-sweep
+ * schedule ran), and its geometry (CTAs per cluster, threads per CTA); returns 1 when the last run used it. */
+double ttc_sweep_kernel_ms(const ttc_handle* h);
+int ttc_sweep_geometry(const ttc_handle* h, int* cluster, int* threads);
 /* measured FP64 ceiling of the device in TFLOP/s (roofline denominator of the evaluation / residual kernels):
  * fma = 1 DFMA chains, fma = 0 separate DMUL + DADD chains (the reference arithmetic has no FMA contraction) */
 int ttc_fp64_peak(int device, int fma, double* tflops);

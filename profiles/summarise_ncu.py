@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Condense `ncu --set full` captures (gpurun_out/*.ncu-rep) into profiles/r01_ncu_summary.json + a readable table.
+"""Condense `ncu --set full` captures (gpurun_out/*.ncu-rep) into profiles/r02_ncu_summary.json + a readable table.
 
 usage: python profiles/summarise_ncu.py NAME=path.ncu-rep [NAME=path.ncu-rep ...]
 Per kernel: launches captured, average duration, DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum),
@@ -69,12 +69,12 @@ def main():
                        f"{e['issue_active_pct']:5.1f}%  warps {e['warps_active_pct']:5.1f}%  regs {e['registers_per_thread']:.0f}  stalls {e['top_stalls_per_issue']}")
     here = os.path.dirname(os.path.abspath(__file__))
     old = {}
-    p = os.path.join(here, "r01_ncu_summary.json")
+    p = os.path.join(here, "r02_ncu_summary.json")
     if os.path.exists(p):
         old = json.load(open(p))
     old.update(summary)
     json.dump(old, open(p, "w"), indent=1)
-    open(os.path.join(here, "r01_ncu_summary.txt"), "a").write("\n".join(lines) + "\n")
+    open(os.path.join(here, "r02_ncu_summary.txt"), "a").write("\n".join(lines) + "\n")
     print("\n".join(lines))
 
 

@@ -20,6 +20,14 @@ for name, mk, R, piv, P in [("B", lambda: T.drivers.ising('c', 10, 256), 32, 2, 
             q = t.superblock_probe(bond, reps=1, variant=1)
             line += f"; plain {q['ms']:.3f} ms; same argmax {q['argmax_b'] == r['argmax_b'] and q['b'] == r['b']}"
         print(line, flush=True)
+        pkf = T.fp64_peak(0, True)
+        for var, nm in ((2, "DFMA residual"), (3, "DMMA residual (fast mode)")):
+            try:
+                f = t.superblock_probe(bond, reps=2, variant=var)
+                print(f"    {nm}: {f['ms']:.3f} ms, {fl/f['ms']/1e9:.2f} alg TFLOP/s = {100*fl/f['ms']/1e9/pkf:.0f}% of the DFMA peak {pkf:.1f}; "
+                      f"same residual argmax {f['argmax_b'] == r['argmax_b']}, value rel diff {abs(f['b']/r['b']-1):.1e}", flush=True)
+            except T.TTCrossError as e:
+                print("   ", nm, "unavailable:", e.msg)
     except T.TTCrossError as e:
         print(name, "probe failed:", e)
 p = T.drivers.ising('c', 10, 256)

@@ -126,6 +126,32 @@ def test_superblock_kernels_agree(kind, index, n, R, P):
         assert abs(f["b"] - a["b"]) <= 1e-12 * max(abs(a["a"]), 1e-300)
 
 
+@pytest.mark.parametrize("kind,index,n,R", [("c", 6, 20, 8), ("c", 7, 12, 4), ("d", 5, 12, 8)])
+def test_superblock_dmma_fast_mode_agrees(kind, index, n, R):
+    """Fast mode (ttc_superblock_probe variant 3): the residual through mma.sync.m8n8k4.f64 (DMMA).  Not bit-identical by
+    construction (FMA, tensor-core summation order); asserted: the evaluated maximum is the same element and value, the
+    residual argmax is the same element unless two candidates tie to rounding, and its value agrees to 1e-12 of |a|max."""
+    p = T.drivers.ising(kind, index, n)
+    t = p.make()
+    t.dmrgg(R, p.accuracy, 1)
+    for bond in range(1, p.d):
+        a = t.superblock_probe(bond, variant=0)
+        f = t.superblock_probe(bond, variant=3)
+        assert f["count"] == a["count"] and f["argmax_a"] == a["argmax_a"] and f["a"] == a["a"]
+        assert abs(f["b"] - a["b"]) <= 1e-12 * max(abs(a["a"]), 1e-300), (bond, a, f)
+        if f["argmax_b"] != a["argmax_b"]:
+            assert abs(abs(f["b"]) - abs(a["b"])) <= 1e-13 * max(abs(a["a"]), 1e-300)
+
+
+@pytest.mark.parametrize("P", [1, 2])
+def test_superblock_sweep_moderate_shape_bit_exact(P):
+    """A full pivoting = -1 run whose superblocks span many row blocks and column tiles of the tiled kernel (8 x 65 x 65 x 8 =
+    270 k elements per bond visit at full rank) against the oracle, bit for bit: tape, ranks, neval, values, cores."""
+    p = T.drivers.ising("c", 6, 64)
+    t, g, o = run_both(p, 8, -1, P=P)
+    assert_parity(t, g, o, exact=True)
+
+
 def test_superblock_kernel_mvn_matches_plain():
     p = T.drivers.mvn(4, 16)
     t = p.make()

@@ -85,6 +85,9 @@ def load_library(build_if_missing: bool = True):
     L.ttc_l2_flush.argtypes = [vp, C.c_longlong]
     L.ttc_device_ms.restype = C.c_double
     L.ttc_device_ms.argtypes = [vp]
+    L.ttc_sweep_kernel_ms.restype = C.c_double
+    L.ttc_sweep_kernel_ms.argtypes = [vp]
+    L.ttc_sweep_geometry.argtypes = [vp, _ip, _ip]
     L.ttc_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_longlong), _dp]
     L.ttc_fp64_peak.argtypes = [C.c_int, C.c_int, _dp]
     L.ttc_ort.argtypes = [vp]
@@ -273,6 +276,12 @@ class TTCross:
     def set_lottery_mode(self, mode: int):
         self._check(self._L.ttc_set_lottery_mode(self.h, mode))
 
+    def sweep_kernel(self):
+        """(used, ms, cluster size, threads per CTA) of the persistent sweep kernel in the last dmrgg call."""
+        cs, th = C.c_int(0), C.c_int(0)
+        used = self._L.ttc_sweep_geometry(self.h, C.byref(cs), C.byref(th))
+        return bool(used), float(self._L.ttc_sweep_kernel_ms(self.h)), cs.value, th.value
+
     def set_exp_mode(self, mode: int):
         """0: platform exp (default); 1: deterministic exp shared with the test oracle (parity mode)."""
         self._check(self._L.ttc_set_exp_mode(self.h, mode))
@@ -408,7 +417,8 @@ class TTCross:
 
     # ---- probes
     def superblock_probe(self, bond: int, store: bool = False, reps: int = 1, variant: int = 0):
-        """variant 0: tiled kernel, reference arithmetic; 1: plain kernel; 2: tiled kernel with DFMA residual (not bit-exact)."""
+        """variant 0: tiled kernel, reference arithmetic; 1: plain kernel; 2: tiled kernel with DFMA residual (not bit-exact);
+        3: fast mode, residual through the FP64 tensor-core path (mma.sync.m8n8k4.f64 / DMMA; not bit-exact)."""
         idx = (C.c_longlong * 2)()
         val = (C.c_double * 2)()
         ms = C.c_double()

@@ -125,6 +125,8 @@ struct ttc_handle {
     cudaStream_t stream_q = nullptr;                   // overlapped per-sweep quadrature (lower priority than `stream`)
     std::vector<cudaEvent_t> ev_fork, ev_join;         // main -> quadrature stream / back, one pair per sweep of a graph
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evs0 = nullptr, evs1 = nullptr;        // around the persistent sweep kernel
+    double sweep_ms = 0; int persistent_used = 0;
     int* lot_h = nullptr; VisitOut* out_h = nullptr; SweepOut* sweep_h = nullptr;   // pinned
     double* pack_d = nullptr; size_t pack_cap = 0;
     void* flush_d = nullptr; size_t flush_cap = 0;
@@ -143,7 +145,7 @@ struct ttc_handle {
     int exp_mode = 0;                   // 1: deterministic exp (include/ttc_detexp.h)
     int converged = 0;                  // the last run ended on the accuracy criterion
     size_t sm_qinc = 0; int qinc_stage = 0;
-    size_t sm_sbt = 0; bool sbt_ok = false;      // tiled superblock kernel (ttc_superblock.cuh)
+    size_t sm_sbt = 0, sm_sbm = 0; bool sbt_ok = false, sbm_ok = false;      // tiled superblock kernel (ttc_superblock.cuh)
     int cluster_size = 16, cluster_threads = 256;   // measured best on B200 (16 x 256 beats the portable 8 x 512 by 7 %)
     size_t sm_visit = 0, sm_sweep = 0; bool cluster_ok = false;
     int sweep_threads = 256, sweep_cluster = 16;   // geometry of the persistent kernel (chosen in setup_device; TTC_SWEEP_THREADS / TTC_SWEEP_CLUSTER)
@@ -346,6 +348,8 @@ void free_device(ttc_handle* h) {
     h->pack_d = nullptr; h->pack_cap = 0;
     if (h->ev0) { cudaEventDestroy(h->ev0); h->ev0 = nullptr; }
     if (h->ev1) { cudaEventDestroy(h->ev1); h->ev1 = nullptr; }
+    if (h->evs0) { cudaEventDestroy(h->evs0); h->evs0 = nullptr; }
+    if (h->evs1) { cudaEventDestroy(h->evs1); h->evs1 = nullptr; }
     for (cudaEvent_t e : h->ev_fork) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_join) cudaEventDestroy(e);
     h->ev_fork.clear(); h->ev_join.clear();
@@ -472,6 +476,8 @@ int setup_device(ttc_handle* h, int maxrank) {
     }
     CUDA_TRY(h, cudaEventCreate(&h->ev0));
     CUDA_TRY(h, cudaEventCreate(&h->ev1));
+    CUDA_TRY(h, cudaEventCreate(&h->evs0));
+    CUDA_TRY(h, cudaEventCreate(&h->evs1));
 
     const int d = h->d, P = h->P;
     h->Rmax = maxrank > 0 ? maxrank : 64;
@@ -644,6 +650,7 @@ int setup_device(ttc_handle* h, int maxrank) {
     // tiled superblock kernel (ttc_superblock.cuh): column-factor slab + per-tile tables in shared memory
     {
         h->sm_sbt = ((size_t)D.auxsm + D.stage_max + sb_tile_doubles(Rmax, d)) * sizeof(double);
+        h->sm_sbm = h->sm_sbt + sb_mma_doubles() * sizeof(double);      // DMMA fast mode: + the parked tile
         h->sbt_ok = D.stage && h->sm_sbt <= 200 * 1024 && !h->force_simple && !std::getenv("TTC_NO_TILED_SUPERBLOCK");
         if (h->sbt_ok) {
             cudaError_t ce = cudaSuccess;
@@ -652,6 +659,9 @@ int setup_device(ttc_handle* h, int maxrank) {
                 ce = cudaFuncSetAttribute(k_superblock_t<K, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bt);
                 if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_superblock_t<K, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bt);
                 if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_superblock_t<K, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bt);
+                h->sbm_ok = ce == cudaSuccess && h->sm_sbm <= 220 * 1024 && Rmax % 4 == 0 &&
+                            cudaFuncSetAttribute(k_superblock_t<K, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_sbm) == cudaSuccess;
+                (void)cudaGetLastError();
             );
             if (ce != cudaSuccess) { (void)cudaGetLastError(); h->sbt_ok = false; }
         }
@@ -1311,8 +1321,10 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
         cfg.attrs = at; cfg.numAttrs = 2;
         cudaError_t ce = cudaSuccess;
+        CUDA_TRY(h, cudaEventRecord(h->evs0, s));
         VISIT_KIND_SWITCH(h, L(KC_VISITS, [&] { ce = cudaLaunchKernelEx(&cfg, k_sweeps<K>, D, last_sweep, eff_maxrank, small_element, small_pivot); }));
         CUDA_TRY(h, ce);
+        CUDA_TRY(h, cudaEventRecord(h->evs1, s));
         if (has_quad) {
             // per-sweep quadrature values of ALL sweeps at once (they feed the printed lines only, dmrgg.f90:975-1008)
             const int R = h->Rmax, ncore = D.c_hi - D.c_lo + 1;
@@ -1452,6 +1464,9 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     h->nsweeps = it;
     float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     h->device_ms = ms;
+    h->persistent_used = persistent ? 1 : 0;
+    h->sweep_ms = 0;
+    if (persistent) { float sm = 0; cudaEventElapsedTime(&sm, h->evs0, h->evs1); h->sweep_ms = sm; }
     h->neval = nevalall;
     h->seconds = timef();
     h->ran = true;
@@ -2197,6 +2212,13 @@ int ttc_lottery_fast(int m, const int* zeros_sorted_distinct, int nz, const doub
 
 long long ttc_launch_count(const ttc_handle* h) { return h ? h->launches : 0; }
 double ttc_device_ms(const ttc_handle* h) { return h ? h->device_ms : 0; }
+double ttc_sweep_kernel_ms(const ttc_handle* h) { return h ? h->sweep_ms : 0; }
+int ttc_sweep_geometry(const ttc_handle* h, int* cluster, int* threads) {
+    if (!h) return 0;
+    if (cluster) *cluster = h->sweep_cluster;
+    if (threads) *threads = h->sweep_threads;
+    return h->persistent_used;
+}
 int ttc_profile(const ttc_handle* h, int cap, const char** names, long long* launches, double* ms) {
     if (!h) return 0;
     int c = std::min(cap, (int)KC_COUNT);
@@ -2211,7 +2233,7 @@ int ttc_superblock_probe(ttc_handle* h, int bond, int store, int reps, long long
 // variant 0: tiled kernel, reference arithmetic (what ttc_dmrgg runs); 1: the plain one-thread-per-element kernel;
 // 2: tiled kernel with the residual update contracted into DFMA (not bit-exact; FP64 ceiling measurement only)
 int ttc_superblock_probe_ex(ttc_handle* h, int bond, int store, int reps, int variant, long long* out_idx, double* out_val, double* ms, long long* count) {
-    if (!h || bond < 1 || bond > h->d - 1 || reps < 1 || variant < 0 || variant > 2) return TTC_ERR_ARG;
+    if (!h || bond < 1 || bond > h->d - 1 || reps < 1 || variant < 0 || variant > 3) return TTC_ERR_ARG;
     if (!h->ran) { h->err = "ttc_superblock_probe before ttc_dmrgg"; return TTC_ERR_STATE; }
     if (bond < h->own[h->plan.v0] || bond >= h->own[h->plan.v0 + h->plan.nv]) { h->err = "ttc_superblock_probe: bond belongs to another rank"; return TTC_ERR_STATE; }
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -2228,7 +2250,8 @@ int ttc_superblock_probe_ex(ttc_handle* h, int bond, int store, int reps, int va
     const int Gs = (int)std::min<i64>(GMAX, std::max<i64>(1, std::min<i64>((tot + TB - 1) / TB, (i64)h->nsm * (h->kind == TTC_MVN ? 8 : 6))));
     const size_t smA = aux_smem(h);
     if (variant != 1 && !h->sbt_ok) { cudaFree(pout); if (a_out) cudaFree(a_out); h->err = "tiled superblock kernel unavailable for this shape"; return TTC_ERR_STATE; }
-    if (variant == 2 && store) { cudaFree(pout); if (a_out) cudaFree(a_out); h->err = "the DFMA variant has no stored form"; return TTC_ERR_ARG; }
+    if (variant == 3 && !h->sbm_ok) { cudaFree(pout); if (a_out) cudaFree(a_out); h->err = "the DMMA superblock variant needs maxrank % 4 == 0 and its tile in shared memory"; return TTC_ERR_STATE; }
+    if (variant >= 2 && store) { cudaFree(pout); if (a_out) cudaFree(a_out); h->err = "the DFMA variant has no stored form"; return TTC_ERR_ARG; }
     const int m1 = h->rk_h[bond - 1] * h->n[bond], nc = h->n[bond + 1] * h->rk_h[bond + 1];
     const int nrb = cdiv(m1, SB_TM);
     const int nsp = std::max(1, std::min({(SB_MINB * h->nsm) / std::max(1, nrb), cdiv(nc, SB_TN), GMAX / nrb}));   // whole waves: SB_MINB CTAs per SM
@@ -2236,6 +2259,9 @@ int ttc_superblock_probe_ex(ttc_handle* h, int bond, int store, int reps, int va
         if (variant == 1) {
             if (store) { KIND_SWITCH(h->kind, k_superblock<K, 1><<<Gs, TB, h->sm_sb, s>>>(D, 1, 1, bond, 0, a_out, pout)); }
             else       { KIND_SWITCH(h->kind, k_superblock<K, 0><<<Gs, TB, h->sm_sb, s>>>(D, 1, 1, bond, 0, nullptr, pout)); }
+        } else if (variant == 3) {
+            const int nsp1 = std::max(1, std::min({h->nsm / std::max(1, nrb), cdiv(nc, SB_TN), GMAX / nrb}));      // one CTA per SM (the parked tile)
+            KIND_SWITCH(h->kind, k_superblock_t<K, 0, 2><<<dim3(nrb, nsp1, 1), SB_TM, h->sm_sbm, s>>>(D, 1, 1, bond, 0, nullptr, pout));
         } else if (variant == 2) {
             KIND_SWITCH(h->kind, k_superblock_t<K, 0, 1><<<dim3(nrb, nsp, 1), SB_TM, h->sm_sbt, s>>>(D, 1, 1, bond, 0, nullptr, pout));
         } else {

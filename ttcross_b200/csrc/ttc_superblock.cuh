@@ -47,9 +47,18 @@ __host__ __device__ __forceinline__ size_t sb_tile_doubles(int Rmax, int d) {
     // Ct[Rmax*TM] | Rt[Rmax*TN] | XK WK VK VV [4*TN] | XRt WRt [2*d*TN]
     return (size_t)Rmax * SB_TM + (size_t)Rmax * SB_TN + 4 * SB_TN + 2 * (size_t)d * SB_TN + 2;   // + alignment slack
 }
+// FMA = 2 (fast mode): the residual b = a - col * row goes through the FP64 tensor-core path (mma.sync.m8n8k4.f64, SASS DMMA).
+// The evaluated tile a (TM x TN) is parked in shared memory (Ft, column-major, padded), then every warp owns 32 rows x 32
+// columns = 4 x 4 fragments: accumulators start from a, 8 k-steps of 4 contract K = 32.  Not bit-identical to the reference
+// (FMA contraction, k summed in the tensor core's order): pivot agreement with parity mode is reported by the tests / bench.
+constexpr int SB_TMP = SB_TM + 2;                // padded leading dimension of Ft
+__host__ __device__ __forceinline__ size_t sb_mma_doubles() { return (size_t)SB_TN * SB_TMP; }
+__device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
 
 template <int KIND, int STORE, int FMA>
-__global__ void __launch_bounds__(SB_TM, SB_MINB) k_superblock_t(DevPlan P, int dir, int pp, int fixed_bond, int fixed_v, double* a_out, Partial* probe_out) {
+__global__ void __launch_bounds__(SB_TM, FMA == 2 ? 1 : SB_MINB) k_superblock_t(DevPlan P, int dir, int pp, int fixed_bond, int fixed_v, double* a_out, Partial* probe_out) {
     tl_stamp(P, 35);
     extern __shared__ double smem[];
     __shared__ Partial shp[32];
@@ -76,6 +85,8 @@ __global__ void __launch_bounds__(SB_TM, SB_MINB) k_superblock_t(DevPlan P, int 
     double* XK = Rt + (size_t)P.Rmax * SB_TN; double* WK = XK + SB_TN; double* VK = WK + SB_TN; double* VV = VK + SB_TN;
     double* XRt = VV + SB_TN;                          // XRt[t*TN + col]
     double* WRt = XRt + (size_t)P.d * SB_TN;
+    double* Ft = WRt + (size_t)P.d * SB_TN;            // (FMA = 2 only) evaluated tile, Ft[col * TMP + row]
+    const int K4 = (D.r1 + 3) & ~3;                    // K rounded up to the k-step of the DMMA (extra rows are zero)
     const double* colp = P.col + P.coreOff[D.p];
     const double* rowp = P.rowT + P.coreOff[D.p + 1];
     const i64 cs = (i64)P.Rmax * D.n1;
@@ -98,6 +109,7 @@ __global__ void __launch_bounds__(SB_TM, SB_MINB) k_superblock_t(DevPlan P, int 
 #pragma unroll
             for (int u = 0; u < 8; ++u) if (s0 + u < K) Ct[(s0 + u) * SB_TM + threadIdx.x] = t[u];
         }
+        if (FMA == 2) for (int s1 = K; s1 < K4; ++s1) Ct[s1 * SB_TM + threadIdx.x] = 0.0;
     }
     double xl[SB_MAXL], wl[SB_MAXL];
     double xj = 0.0, wj = 0.0, wk_row = 1.0, w_row = 1.0;
@@ -125,6 +137,7 @@ __global__ void __launch_bounds__(SB_TM, SB_MINB) k_superblock_t(DevPlan P, int 
             const int kq = min(c0 + c, ncols - 1);
             Rt[e] = rowp[kq + (i64)s * rs];               // (k-1) + n2*(q-1) = kq
         }
+        if (FMA == 2) for (int e = K * SB_TN + threadIdx.x; e < K4 * SB_TN; e += blockDim.x) Rt[e] = 0.0;
         if (fastc && threadIdx.x < SB_TN) {
             const int c = threadIdx.x;
             const int kq = min(c0 + c, ncols - 1);
@@ -180,6 +193,20 @@ __global__ void __launch_bounds__(SB_TM, SB_MINB) k_superblock_t(DevPlan P, int 
                     f[c] = eval_point<KIND>(P, sv, A);
                 }
             }
+            if (FMA == 2) {
+                // fast mode: park the evaluated values; the residual of the whole tile is taken by the warps below
+#pragma unroll
+                for (int c = 0; c < SB_CN; ++c) {
+                    Ft[(cb + c) * SB_TMP + threadIdx.x] = f[c];
+                    const int kq = c0 + cb + c;
+                    if (rvalid && kq < ncols) {
+                        const i64 x = (i64)row + (i64)m1 * kq;
+                        if (STORE) a_out[x] = f[c];
+                        amax_take(braw, f[c], x);
+                    }
+                }
+                continue;
+            }
             double res[SB_CN];
 #pragma unroll
             for (int c = 0; c < SB_CN; ++c) res[c] = f[c];
@@ -190,7 +217,7 @@ __global__ void __launch_bounds__(SB_TM, SB_MINB) k_superblock_t(DevPlan P, int 
 #pragma unroll
                 for (int c2 = 0; c2 < SB_CN / 2; ++c2) {
                     const double2 rv = rp[c2];
-                    if (FMA) {
+                    if (FMA == 1) {
                         res[2 * c2] = fma(-rv.x, cv, res[2 * c2]);
                         res[2 * c2 + 1] = fma(-rv.y, cv, res[2 * c2 + 1]);
                     } else {
@@ -211,6 +238,41 @@ __global__ void __launch_bounds__(SB_TM, SB_MINB) k_superblock_t(DevPlan P, int 
                     }
                 }
             }
+        }
+        if (FMA == 2) {
+            __syncthreads();                               // the tile is complete in Ft
+            const int lane = threadIdx.x & 31, wrow = (threadIdx.x >> 5) * 32, g = lane >> 2, tq = lane & 3;
+            double acc[4][4][2];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    acc[mi][ni][0] = Ft[(ni * 8 + 2 * tq) * SB_TMP + wrow + mi * 8 + g];
+                    acc[mi][ni][1] = Ft[(ni * 8 + 2 * tq + 1) * SB_TMP + wrow + mi * 8 + g];
+                }
+            for (int kk = 0; kk < K4; kk += 4) {
+                double af[4], bf[4];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) af[mi] = -Ct[(kk + tq) * SB_TM + wrow + mi * 8 + g];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) bf[ni] = Rt[(kk + tq) * SB_TN + ni * 8 + g];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) dmma_m8n8k4(acc[mi][ni], af[mi], bf[ni]);
+            }
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) {
+                        const int r_ = blockIdx.x * SB_TM + wrow + mi * 8 + g, kq = c0 + ni * 8 + 2 * tq + e;
+                        if (r_ < m1 && kq < ncols) {
+                            Partial cand; cand.absv = fabs(acc[mi][ni][e]); cand.val = acc[mi][ni][e]; cand.idx = (i64)r_ + (i64)m1 * kq;
+                            amax_merge(bres, cand);      // (fragment order is not index order: ties go to the smaller index explicitly)
+                        }
+                    }
         }
     }
     // ---- grid-wide first-index argmax: last CTA (of this virtual rank) folds the partials
