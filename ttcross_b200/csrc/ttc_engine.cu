@@ -151,6 +151,7 @@ struct ttc_handle {
     int sweep_threads = 256, sweep_cluster = 16;   // geometry of the persistent kernel (chosen in setup_device; TTC_SWEEP_THREADS / TTC_SWEEP_CLUSTER)
     bool persist_ok = false;                       // the persistent sweep kernel (ttc_sweep.cuh) fits the device in one cooperative wave
     double* chainS = nullptr;                      // [maxsweeps][P + 1][Rmax^2] chain products of the per-sweep quadrature after the loop
+    double* init_scal = nullptr; int* init_ind0 = nullptr;   // device-side initial cross (k_init_pick / k_init_state)
     int nsm = 148;
     // core blocks over processes (one per GPU): NCCL communicator of ttc_comm_init, this process's rank
     NcclComm comm = nullptr; int nproc = 1, prank = 0;
@@ -759,6 +760,7 @@ int setup_device(ttc_handle* h, int maxrank) {
                 D.chainS = dcs;
             }
             h->chainS = D.chainS;
+            { double* sc = nullptr; int* i0 = nullptr; if (dev_alloc(h, &sc, 4) || dev_alloc(h, &i0, (size_t)d + 4)) return TTC_ERR_CUDA; h->init_scal = sc; h->init_ind0 = i0; }
             // value tables + padded node / weight vectors for the TMA staging (ttc_visit.cuh)
             D.RT = (Rmax + 1) & ~1; D.NT = (h->nmax + 1) & ~1;
             const size_t tl = (size_t)(accL / Rmax) * D.RT + 2, tr = (size_t)(accR / Rmax) * D.RT + 2;
@@ -992,6 +994,26 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     shifts[P] = snum;
     double* db = h->initb;
     KIND_SWITCH(h->kind, L(KC_INIT, [&] { k_init_search<K><<<cdiv((i64)nn * snum, TB), TB, smA, s>>>(D, nn, snum, db); }));
+    // the whole sweep loop as one persistent cooperative kernel (ttc_sweep.cuh) whenever the cluster kernel applies and every
+    // cluster of this process is resident at once; TTC_NO_PERSISTENT=1 keeps the per-sweep schedule (graphs of k_visits + ...)
+    const bool persistent = h->persist_ok && h->cluster_ok && (h->nproc == 1 || h->p2p) && !h->ucb && !h->verbose && !h->force_sync && !h->force_host_lottery &&
+                            h->piv >= 0 && !h->force_split && !h->profile && h->use_wave;
+    double val = 0, val_prev = 0, t_init = 0;
+    i64 nevalall = 0;
+    auto push_series = [&](double v_, i64 ne, double am, double pm, double er, double t) {
+        h->s_val.push_back(v_); h->s_neval.push_back((double)ne); h->s_amax.push_back(am); h->s_pivotmax.push_back(pm);
+        h->s_erank.push_back(er); h->s_time.push_back(t);
+    };
+    if (persistent) {
+        // ---- initial cross entirely on the device (k_init_pick / k_init_state, ttc_sweep.cuh): no host round trip before the sweeps
+        L(KC_INIT, [&] { k_init_pick<<<1, 1024, 0, s>>>(D, nn, snum, db, h->init_scal, h->init_ind0); });
+        KIND_SWITCH(h->kind, L(KC_INIT, [&] { k_init_cross<K><<<dim3(cdiv(h->nmax, TB), d), TB, smA, s>>>(D); }));
+        L(KC_INIT, [&] { k_init_factors<<<dim3(cdiv(h->nmax, 256), d), 256, 0, s>>>(D); });
+        L(KC_INIT, [&] { k_init_state<<<1, 256, 0, s>>>(D, nn, snum, h->init_scal, h->init_ind0, has_quad ? 1 : 0); });
+        h->rk_h.assign(d + 2, 1); h->rks_h.assign(d + 2, 1);
+        h->rng_k.assign(P, 0);
+        t_init = timef();
+    } else {
     std::vector<double> b((size_t)nn * snum);
     CUDA_TRY(h, cudaMemcpyAsync(b.data(), db, b.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
@@ -1042,10 +1064,6 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     h->rng_k.assign(P, 0);
 
     tr.lap("init_search+tables");
-    // the whole sweep loop as one persistent cooperative kernel (ttc_sweep.cuh) whenever the cluster kernel applies and every
-    // cluster of this process is resident at once; TTC_NO_PERSISTENT=1 keeps the per-sweep schedule (graphs of k_visits + ...)
-    const bool persistent = h->persist_ok && h->cluster_ok && (h->nproc == 1 || h->p2p) && !h->ucb && !h->verbose && !h->force_sync && !h->force_host_lottery &&
-                            h->piv >= 0 && !h->force_split && !h->profile && h->use_wave;
     // ---- initial cross fibers and factors (dmrgg.f90:220-248)
     KIND_SWITCH(h->kind, L(KC_INIT, [&] { k_init_cross<K><<<dim3(cdiv(h->nmax, TB), d), TB, smA, s>>>(D); }));
     L(KC_INIT, [&] { k_init_factors<<<dim3(cdiv(h->nmax, 256), d), 256, 0, s>>>(D); });
@@ -1079,7 +1097,6 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         CUDA_TRY(h, cudaMemcpyAsync(D.st, sv.data(), sizeof(VState) * P, cudaMemcpyHostToDevice, s));
         CUDA_TRY(h, cudaStreamSynchronize(s));
     }
-    double val = 0, val_prev = 0;
     if (has_quad) {
         std::vector<double> part(P);
         std::vector<i64> qoff(d + 2, 0);
@@ -1095,11 +1112,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         for (int v = 1; v < P; ++v) val = val * part[v];
         val_prev = val;
     }
-    i64 nevalall = 0; for (int v = 0; v < P; ++v) nevalall += neval_v[v];
-    auto push_series = [&](double v_, i64 ne, double am, double pm, double er, double t) {
-        h->s_val.push_back(v_); h->s_neval.push_back((double)ne); h->s_amax.push_back(am); h->s_pivotmax.push_back(pm);
-        h->s_erank.push_back(er); h->s_time.push_back(t);
-    };
+    for (int v = 0; v < P; ++v) nevalall += neval_v[v];
     {
         double t2 = timef();
         double er = erank(d, h->n, h->rk_h);
@@ -1111,6 +1124,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         push_series(val, nevalall, amax_v[0], -1.0, er, t2);
     }
 
+    }
     // ---- main loop (dmrgg.f90:309-1020)
     // Two host modes.  ASYNC (default): the lottery runs on the device, so every sweep is enqueued without waiting;
     // the exit test lives in k_sweep_log and later sweeps turn into no-ops once it fires.  The host polls a
@@ -1430,6 +1444,19 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
             CUDA_TRY(h, cudaMemcpy(slog.data(), D.slog, slog.size() * sizeof(SweepOut), cudaMemcpyDeviceToHost));
             CUDA_TRY(h, cudaMemcpy(rklog.data(), D.rklog, rklog.size() * sizeof(int), cudaMemcpyDeviceToHost));
             CUDA_TRY(h, cudaMemcpy(vlog.data(), D.vlog, (size_t)it * maxnb * P * sizeof(VisitOut), cudaMemcpyDeviceToHost));
+        }
+        if (persistent) {
+            // the '0::' line of the initial cross (dmrgg.f90:250-300) from the record k_init_state left in slog[0]
+            std::vector<int> rk1(d + 2, 1);
+            const double er0 = erank(d, h->n, rk1);
+            SweepOut s0;
+            CUDA_TRY(h, cudaMemcpy(&s0, D.slog, sizeof s0, cudaMemcpyDeviceToHost));
+            std::snprintf(line, sizeof line, "%3d%2s rank%5.1f time: %s n_evals: %10lld", 0, "::", er0, fmt_e(t_init, 9, 3).c_str(), (long long)s0.neval);
+            std::string str0 = line;
+            if (has_quad) str0 += " val " + fmt_e(s0.val, 20, 14);
+            h->text += str0 + "\n";
+            push_series(has_quad ? s0.val : 0.0, s0.neval, s0.amax, -1.0, er0, t_init);
+            nevalall = s0.neval;
         }
         double vprev = h->s_val.empty() ? 0.0 : h->s_val[0];
         for (int sw = 1; sw <= it; ++sw) {

@@ -713,4 +713,92 @@ __global__ void k_quad_tree_all(DevPlan P, double* chainS) {
     if (threadIdx.x == 0) P.slog[sw].val = ch[0];
 }
 
+// ----------------------------------------------------------------------------
+// Device-side initial cross (dmrgg.f90:150-270) for the persistent schedule: no host round trip between the kernels.
+// k_init_pick : first-index argmax of |b| over the nn x snum diagonal search points (idamax + MAXLOC, :179-203), the
+//               initial multi-index ind0, pivot 1 of every bond (vip, ranks, index tables)                       <<<1, 1024>>>
+// k_init_state: after k_init_cross / k_init_factors: per-partition amax / neval (:193-232), the value of the rank-1 train
+//               (:250-270) and the '0::' record slog[0]                                                          <<<1, 256>>>
+// scal: [0] = gmax.
+// ----------------------------------------------------------------------------
+__global__ void k_init_pick(DevPlan P, int nn, int snum, const double* b, double* scal, int* ind0 /*[d + 2]*/) {
+    __shared__ Partial shp[32];
+    __shared__ int s_ind[MAXD_LOCAL * 8 + 2];
+    Partial best = amax_init();
+    for (int x = threadIdx.x; x < nn * snum; x += blockDim.x) amax_take(best, b[x], x);
+    best = amax_block(best, shp);
+    __shared__ long long s_x;
+    if (threadIdx.x == 0) { s_x = best.idx; scal[0] = best.absv; }
+    __syncthreads();
+    const int gilot = (int)s_x + 1;
+    const int sft = (gilot - 1) / nn, k = (gilot - 1) % nn + 1;
+    const int d = P.d, Rmax = P.Rmax;
+    for (int p = threadIdx.x; p <= d + 1; p += blockDim.x) {
+        const int v = (p >= 1 && p <= d) ? (k - 1 + sft * (p - 1)) % P.n[p] + 1 : 1;
+        ind0[p] = v;
+        if (p < (int)(sizeof(s_ind) / sizeof(int))) s_ind[p] = v;
+    }
+    __syncthreads();
+    auto I0 = [&](int p) { return p < (int)(sizeof(s_ind) / sizeof(int)) ? s_ind[p] : ((p >= 1 && p <= d) ? (k - 1 + sft * (p - 1)) % P.n[p] + 1 : 1); };
+    for (int p = threadIdx.x; p <= d; p += blockDim.x) {
+        int* t = P.vip + (i64)p * Rmax * 4;
+        t[0] = 1; t[3] = 1;
+        t[1] = (p >= 1 && p <= d - 1) ? I0(p) : 1;
+        t[2] = (p >= 1 && p <= d - 1) ? I0(p + 1) : 1;
+        P.rk[p] = 1; P.rks[p] = 1;
+    }
+    if (threadIdx.x == 0) { P.rk[d + 1] = 1; P.rks[d + 1] = 1; }
+    // pivot 1 of the flat tables: L(p)(pos, 0) = ind0(pos + 1), pos < p;  R(p)(pos, 0) = ind0(p + pos + 1), pos < d - p
+    for (int x = threadIdx.x; x < (d + 1) * d; x += blockDim.x) {
+        const int p = x / d, pos = x - p * d;
+        if (pos < p) P.Lidx[P.offL[p] + (i64)pos * Rmax] = I0(pos + 1);
+        if (pos < d - p) P.Ridx[P.offR[p] + (i64)pos * Rmax] = I0(p + pos + 1);
+    }
+}
+__global__ void k_init_state(DevPlan P, int nn, int snum, const double* scal, const int* ind0, int has_quad) {
+    __shared__ double s_dot[MAXD_LOCAL * 8 + 2], s_part[64];
+    const int d = P.d, NP = P.P;
+    const double gmax = scal[0];
+    // ddot(fiber(p), quad(p)) per core, sequential in j like the reference's ddot
+    for (int p = 1 + threadIdx.x; p <= d; p += blockDim.x) {
+        double t = 0.0;
+        if (has_quad && p < (int)(sizeof(s_dot) / sizeof(double))) {
+            const double* a = P.arg + P.coreOff[p]; const double* w = P.quadw + P.quadOff[p];
+            for (int j = 0; j < P.n[p]; ++j) t = t + a[(i64)P.Rmax * j] * w[j];
+            s_dot[p] = t;
+        }
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < NP; v += blockDim.x) {
+        const int s0 = (int)((double)snum * (double)v / NP), s1 = (v + 1 == NP) ? snum : (int)((double)snum * (double)(v + 1) / NP);
+        double am = gmax;
+        long long ne = (long long)nn * (s1 - s0);
+        for (int p = P.own[v]; p <= P.own[v + 1]; ++p) {
+            ne += P.n[p];
+            const double* a = P.arg + P.coreOff[p];
+            for (int j = 0; j < P.n[p]; ++j) am = fmax(am, fabs(a[(i64)P.Rmax * j]));
+        }
+        VState S;
+        S.ii = S.jj = S.kk = S.qq = 0; S.pivot = 0.0; S.done = S.havecol = S.haverow = S.crs = 0; S.upd = 0; S.pad0 = 0;
+        S.amax = am; S.pivotmax = -1.0; S.pivotmin = -1.0; S.pivotmax_prev = am; S.neval = ne; S.rng_k = 0ULL;
+        P.st[v] = S;
+        double x = 1.0;
+        if (has_quad) {
+            for (int p = P.own[v]; p <= P.own[v + 1] - 1; ++p) x = x * s_dot[p] / P.arg[P.coreOff[p] + (i64)P.Rmax * (ind0[p] - 1)];
+            if (v == NP - 1) x = x * s_dot[d];
+        }
+        if (v < 64) s_part[v] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double val = 0.0;
+        if (has_quad) { val = s_part[0]; for (int v = 1; v < NP; ++v) val = val * s_part[v]; }
+        long long ne = 0;
+        for (int v = 0; v < NP; ++v) ne += P.st[v].neval;
+        SweepOut& O = P.slog[0];
+        O.val = val; O.neval = ne; O.amax = P.st[0].amax; O.pivotmax = -1.0; O.pivotmin = -1.0; O.t_ns = 0; O.valid = 1; O.pad = 0;
+        for (int x = 0; x <= d; ++x) P.rklog[x] = 1;
+    }
+}
+
 }  // namespace ttc
