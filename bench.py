@@ -381,6 +381,10 @@ def main():
             sbf = t.superblock_probe(bond, store=False, reps=5, variant=2)
             sbs = t.superblock_probe(bond, store=True, reps=5, variant=0)
             sbp = t.superblock_probe(bond, store=False, reps=2, variant=1)
+            try:
+                sbm = t.superblock_probe(bond, store=False, reps=5, variant=3)
+            except Exception:
+                sbm = None
             flops = sb["count"] * (fpe + 2 * r1)          # operations of an evaluation + 2 r(p) per residual element
             def tf(ms):
                 return flops / (ms * 1e-3) / 1e12
@@ -401,6 +405,13 @@ def main():
                            "peak": hbm_peak, "frac": 8.0 * sbs["count"] / (sbs["ms"] * 1e-3) / 1e9 / hbm_peak,
                            "note": "also writes a (8 B per element); still FP64-bound at this shape"},
                 "plain_kernel_ms": sbp["ms"],
+                "fast_dmma": ({"ms": sbm["ms"], "achieved": tf(sbm["ms"]), "unit": "TFLOP/s", "peak": pk_fma, "frac": tf(sbm["ms"]) / pk_fma,
+                               "same_residual_argmax_as_parity_mode": bool(sbm["argmax_b"] == sb["argmax_b"]),
+                               "residual_value_rel_diff": abs(sbm["b"] / sb["b"] - 1.0) if sb["b"] else None,
+                               "note": "fast mode: residual through mma.sync.m8n8k4.f64 (SASS DMMA), evaluated tile parked in shared memory; measured SLOWER than "
+                                       "the vector path -- on B200 the FP64 tensor rate equals the DFMA rate (profiles/r02_ubench.txt: 37.06 vs 36.89 TFLOP/s) and "
+                                       "the kernel is bound by the evaluation's instruction mix, not by the contraction"} if sbm else None),
+                "other_shapes": "profiles/r02_superblock_shapes.txt (C, D, E: generic per-element evaluation, 10-12 % of the DMUL+DADD ceiling)",
             }
         except Exception as e:  # noqa: BLE001
             line["roofline_superblock"] = {"error": str(e)}

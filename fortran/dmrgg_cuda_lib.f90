@@ -68,6 +68,9 @@ module dmrgg_cuda_lib
             real(c_double), intent(in) :: wre(*), wim(*); real(c_double), intent(out) :: ore(*), oim(*)
         end function
         integer(c_int) function ttc_ort(h) bind(C, name='ttc_ort'); import; type(c_ptr), value :: h; end function
+        integer(c_size_t) function c_strlen(s) bind(C, name='strlen'); import; type(c_ptr), value :: s; end function
+        integer(c_int) function ttc_set_exp_mode(h, mode) bind(C, name='ttc_set_exp_mode'); import; type(c_ptr), value :: h; integer(c_int), value :: mode; end function
+        integer(c_int) function ttc_converged(h) bind(C, name='ttc_converged'); import; type(c_ptr), value :: h; end function
         integer(c_int) function ttc_svd(h, tol, rmax) bind(C, name='ttc_svd'); import; type(c_ptr), value :: h; real(c_double), value :: tol; integer(c_int), value :: rmax; end function
         integer(c_int) function ttc_values(h, count, ind, values) bind(C, name='ttc_values')
             import; type(c_ptr), value :: h; integer(c_long_long), value :: count; integer(c_int), intent(in) :: ind(*); real(c_double), intent(out) :: values(*)
@@ -85,32 +88,43 @@ contains
         integer(c_int), intent(in) :: st
         character(len=*), intent(in) :: what
         character(kind=c_char), pointer :: msg(:)
-        integer :: i
+        type(c_ptr) :: cmsg
+        integer :: i, n
         if (st == 0) return
-        call c_f_pointer(ttc_last_error(handle), msg, [512])
+        cmsg = ttc_last_error(handle)
         write (*, '(3a)', advance='no') what, ': '
-        do i = 1, 512
-            if (msg(i) == c_null_char) exit
-            write (*, '(a)', advance='no') msg(i)
-        end do
+        if (c_associated(cmsg)) then
+            n = int(c_strlen(cmsg))                       ! exactly the bytes of the C string, never past its terminator
+            if (n > 0) then
+                call c_f_pointer(cmsg, msg, [n])
+                do i = 1, n
+                    write (*, '(a)', advance='no') msg(i)
+                end do
+            end if
+        end if
         write (*, *)
         stop
     end subroutine
 
     ! Replaces mpi_init + MPI_COMM_WORLD of the reference drivers (test_crs_ising.f90:31-36): every MPI rank drives one GPU.
-    ! Rank 0 creates the NCCL id, MPI broadcasts it; the next dtt_dmrgg_cuda attaches the communicator.
+    ! Only records the geometry; the NCCL id is created per cross (fresh_comm_id below).
     subroutine dmrgg_cuda_comm_init(nproc, me)
-        include 'mpif.h'
         integer, intent(in) :: nproc, me
+        comm_wanted = .true.; comm_size = nproc; comm_rank = me
+    end subroutine
+
+    ! An NCCL unique id is single use: every dtt_dmrgg_cuda call creates a new handle and therefore a new communicator, so rank 0
+    ! makes a FRESH id and MPI broadcasts it right before ttc_comm_init (the call is collective like dtt_dmrgg itself).
+    subroutine fresh_comm_id()
+        include 'mpif.h'
         integer :: info
         integer(c_int) :: st
-        if (me == 0) then
+        if (comm_rank == 0) then
             st = ttc_comm_unique_id(comm_id)
-            if (st /= 0) then; write (*, *) 'dmrgg_cuda_comm_init: cannot create the NCCL id'; stop; end if
+            if (st /= 0) then; write (*, *) 'dtt_dmrgg_cuda: cannot create the NCCL id'; stop; end if
         end if
         call mpi_bcast(comm_id, 128, MPI_CHARACTER, 0, MPI_COMM_WORLD, info)
-        if (info /= 0) then; write (*, *) 'dmrgg_cuda_comm_init: mpi_bcast fail: ', info; stop; end if
-        comm_wanted = .true.; comm_size = nproc; comm_rank = me
+        if (info /= 0) then; write (*, *) 'dtt_dmrgg_cuda: mpi_bcast fail: ', info; stop; end if
     end subroutine
 
     subroutine dtt_dmrgg_cuda(arg, kind, par, npar, accuracy, maxrank, mybonds, pivoting, neval, quad, tru, aux, seed, device, verbose)
@@ -153,7 +167,10 @@ contains
         else if (comm_wanted) then
             call check(ttc_set_partition(handle, int(comm_size, c_int), c_null_ptr), 'ttc_set_partition')   ! share(), default.f90:80-97
         end if
-        if (comm_wanted) call check(ttc_comm_init(handle, int(comm_size, c_int), int(comm_rank, c_int), comm_id), 'ttc_comm_init')
+        if (comm_wanted) then
+            call fresh_comm_id()
+            call check(ttc_comm_init(handle, int(comm_size, c_int), int(comm_rank, c_int), comm_id), 'ttc_comm_init')
+        end if
         if (present(quad)) then                                       ! rank-1 weights as one dense vector n(1)+...+n(d)
             allocate (qw(sum(nn)))
             k = 0

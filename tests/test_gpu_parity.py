@@ -214,3 +214,20 @@ def test_no_quadrature_run_with_partitions():
     t, g, o = run_both(p, 10, 2, P=4, use_quad=False, use_tru=False)
     assert_parity(t, g, o, exact=True)
 
+
+
+@pytest.mark.parametrize("family,P,piv", [("stdnorm", 1, 2), ("stdnorm", 2, 1), ("mvn", 1, 1), ("mvn", 3, 1)])
+def test_ragged_mode_sizes_nodes_only_integrands(family, P, piv):
+    """type(dtt) carries one mode size per core (tt.f90:18-26).  No reference driver uses unequal sizes, but the engine
+    (dmrgg.f90) is written for them; the nodes-only integrands read node x(ind) of a common node vector, so core k simply uses
+    its first n(k) nodes.  GPU against the oracle at ragged n(k), with the same exp on both sides (parity mode), bit for bit."""
+    d = 6
+    n = np.array([13, 9, 16, 7, 12, 10], dtype=np.int32)
+    base = T.drivers.stdnorm(d, 16) if family == "stdnorm" else T.drivers.mvn(d, 16)
+    nmax = int(n.max())
+    assert base.n[0] >= nmax
+    w = base.quad[:int(base.n[0])]
+    quad = np.concatenate([w[:nk] for nk in n])
+    p = T.drivers.Problem(base.kind, d, n, base.par, base.aux, quad, base.accuracy, 0.0, f"ragged {family}")
+    t, g, o = run_both(p, 6, piv, P=P, exp_mode=1, use_tru=False)
+    assert_parity(t, g, o, exact=True)
