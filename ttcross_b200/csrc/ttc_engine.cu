@@ -1322,6 +1322,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
             CUDA_TRY(h, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
             h->ev_fork.push_back(a); h->ev_join.push_back(b);
         }
+    bool persist_quad_pending = false;
     const bool use_graph = !persistent && !sync_mode && !h->profile && !h->no_graph && (!multi || h->p2p || std::getenv("TTC_MP_GRAPH") != nullptr);
     if (persistent) {
         cudaLaunchConfig_t cfg = {};
@@ -1342,10 +1343,23 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         if (has_quad) {
             // per-sweep quadrature values of ALL sweeps at once (they feed the printed lines only, dmrgg.f90:975-1008)
             const int R = h->Rmax, ncore = D.c_hi - D.c_lo + 1;
+            // The contraction reads the raw cores, which the finalisation (dtt_lua below) rewrites in place: it stays on the sweep
+            // stream; the rest works on the contracted copies only and runs on the second stream beside the finalisation.
             L(KC_QUAD, [&] { k_quad_contract_sm<<<dim3(R, ncore), 256, h->sm_contract, s>>>(D, 1, (int)(h->sm_contract / sizeof(double))); });
-            L(KC_QUAD, [&] { k_quad_lua_all<<<ncore, 512, h->sm_lua, s>>>(D); });
-            L(KC_QUAD, [&] { k_quad_chain_all<<<dim3(NV, last_sweep), 512, h->sm_mat3, s>>>(D, h->chainS); });
-            L(KC_QUAD, [&] { k_quad_tree_all<<<last_sweep, 512, h->sm_mat3, s>>>(D, h->chainS); });
+            if (h->ev_fork.empty()) {
+                cudaEvent_t a = nullptr, b = nullptr;
+                CUDA_TRY(h, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+                CUDA_TRY(h, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+                h->ev_fork.push_back(a); h->ev_join.push_back(b);
+            }
+            cudaStream_t qs = h->stream_q;
+            CUDA_TRY(h, cudaEventRecord(h->ev_fork[0], s));
+            CUDA_TRY(h, cudaStreamWaitEvent(qs, h->ev_fork[0], 0));
+            L(KC_QUAD, [&] { k_quad_lua_all<<<ncore, 512, h->sm_lua, qs>>>(D); });
+            L(KC_QUAD, [&] { k_quad_chain_all<<<dim3(NV, last_sweep), 512, h->sm_mat3, qs>>>(D, h->chainS); });
+            L(KC_QUAD, [&] { k_quad_tree_all<<<last_sweep, 512, h->sm_mat3, qs>>>(D, h->chainS); });
+            CUDA_TRY(h, cudaEventRecord(h->ev_join[0], qs));
+            persist_quad_pending = true;
         }
     }
     if (use_graph) {
@@ -1423,6 +1437,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         L(KC_FINAL, [&] { k_lua_r<<<dim3(cdiv((i64)h->nmax * Rmax, 128), ncore_own), 128, 0, s>>>(D); });
         L(KC_FINAL, [&] { k_lua_l<<<dim3(cdiv((i64)h->nmax * Rmax, 128), ncore_own), 128, 0, s>>>(D); });
     }
+    if (persist_quad_pending) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_join[0], 0));      // the per-sweep values are part of the run
     CUDA_TRY(h, cudaEventRecord(h->ev1, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     CUDA_TRY(h, cudaGetLastError());
