@@ -87,6 +87,8 @@ int ttc_converged(const ttc_handle* h);
 
 /* ---- the sweep: dtt_dmrgg (lib/dmrgg.f90:11) -------------------------------
  *   maxrank   <= 0 : absent          accuracy  < 0 : absent
+ *   (absent maxrank: the rank capacity is 64 -- the run then ends at rank 64 at the latest; ttc_converged() tells whether the
+ *    accuracy criterion of dmrgg.f90:1013-1017 or that capacity ended it)
  *   pivoting  -1 full superblock, 0 one cross, >= 1 rook depth (reference default 3)
  */
 int ttc_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting);

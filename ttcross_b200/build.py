@@ -29,11 +29,24 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if force or needs_build():
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-        if verbose:
-            print(" ".join(cmd))
-        subprocess.check_call(cmd)
+    """Compile the library if a source is newer than it.  Several processes may arrive at once (one per GPU under torchrun):
+    an exclusive file lock serialises them, the compiler writes to a temporary name and the result is renamed into place, so
+    nobody ever loads a half-written library and only the first arrival compiles."""
+    if not (force or needs_build()):
+        return LIB
+    import fcntl
+    with open(LIB + ".lock", "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            if force or needs_build():
+                tmp = f"{LIB}.tmp{os.getpid()}"
+                cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+                if verbose:
+                    print(" ".join(cmd))
+                subprocess.check_call(cmd)
+                os.replace(tmp, LIB)
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
     return LIB
 
 

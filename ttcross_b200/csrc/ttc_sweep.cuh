@@ -43,8 +43,9 @@ static_assert(sizeof(SweepMail) == 256, "SweepMail is 256 bytes");
 struct SweepLocal {                    // per-CTA replica of the cluster's loop state (advanced identically in every CTA)
     int rkL, rkR;                      // current ranks of the foreign bonds lo-1 and hi
     int updL, updR;                    // did the neighbour's adjacent bond grow in this sweep
-    int strike, ready, corner, pad;
+    int strike, ready, corner, pending;   // pending: sweep whose close (allreduce, record, exit test) has not been taken yet
     double amax1;
+    VState saved;                          // the partition's state when `pending` ended (restored if the next sweep is abandoned)
     double r_amax1[64], r_pmax[64], r_pmin[64], r_amax2[64];
     long long r_neval[64];
     int r_err[64];
@@ -370,13 +371,73 @@ k_sweeps(DevPlan P, int it_last, int maxrank, double small_element, double small
         __threadfence();
     }
     cl.sync();
+    if (threadIdx.x == 0) sl.pending = 0;
+    // Close of sweep `cit` (MAX allreduce dmrgg.f90:852-870, sweep record :961-1008, exit test :1010-1019), identical in every
+    // CTA of every cluster.  It is taken LATE: inside the next sweep's first visit, right before its accept test (the visit's
+    // lottery and fibers touch nothing outside the cluster), so the wait for everybody's records hides behind them; `spec` says
+    // that such a visit is under way: if the exit test fires, the partition state goes back to the end of sweep `cit`.
+    auto close_sweep = [&](int cit, bool spec) {
+        for (int u = threadIdx.x; u < P.P; u += blockDim.x) {
+        sweep_wait(P, &mail[u].flag2, seq0 + (unsigned long long)cit, multi);
+        const volatile SweepRec& R = mail[u].rec[cit & 1];
+        sl.r_amax1[u & 63] = R.amax1; sl.r_pmax[u & 63] = R.pivotmax; sl.r_pmin[u & 63] = R.pivotmin;
+        sl.r_amax2[u & 63] = R.amax2; sl.r_neval[u & 63] = R.neval; sl.r_err[u & 63] = R.error;
+    }
+    __syncthreads();
+    tl_mark(P, 73);
+    // ---- MAX allreduce (dmrgg.f90:852-870), sweep record (:961-1008), exit test (:1010-1019); identical in every CTA
+    if (threadIdx.x == 0) {
+        double c1 = sl.r_amax1[0], c2 = sl.r_pmax[0], c3 = (sl.r_pmin[0] > 0.0) ? -sl.r_pmin[0] : -999e9;
+        long long ne = sl.r_neval[0];
+        int err = sl.r_err[0];
+        for (int u = 1; u < P.P; ++u) {
+            c1 = fmax(c1, sl.r_amax1[u]); c2 = fmax(c2, sl.r_pmax[u]);
+            c3 = fmax(c3, (sl.r_pmin[u] > 0.0) ? -sl.r_pmin[u] : -999e9);
+            ne += sl.r_neval[u]; err |= sl.r_err[u];
+        }
+        const double s_pmax = c2, s_pmin = (-c3 == 999e9) ? -1.0 : -c3;
+        const double s_amax = fmax(c1, sl.r_amax2[0]);     // st[0].amax after the exchange
+        int ready = 0;
+        if (maxrank > 0) ready = (cit + 1 >= maxrank);
+        if (P.ctrl->has_accuracy) {
+            if (s_pmax <= P.ctrl->accuracy * s_amax) sl.strike += 1; else sl.strike = 0;
+            ready = ready || (sl.strike >= 3);
+        }
+        if (err) ready = 1;
+        sl.ready = ready;
+        if (ready && spec) sh.S = sl.saved;          // the visit under way is abandoned
+        VState& St = sh.S;
+        St.amax = fmax(c1, St.amax);                 // the allreduced value, then this partition's corner fibers (and, speculatively, the next visit's)
+        St.pivotmax_prev = s_pmax;                   // dmrgg.f90:961
+        St.pivotmax = -1.0; St.pivotmin = -1.0;      // dmrgg.f90:326-327 of the next sweep
+        if (crank == 0) {
+            for (int x = lo; x <= hi - 1; ++x) { const int r = LDF(P.rk + x); P.rklog[(i64)cit * (P.d + 1) + x] = r; P.rks[x] = r; }
+            if (v == 0) P.rklog[(i64)cit * (P.d + 1)] = 1;
+            if (v == P.P - 1) P.rklog[(i64)cit * (P.d + 1) + P.d] = 1;
+            if (v == P.v0) {                         // one record per process
+                SweepOut& O = P.slog[cit];
+                O.neval = ne; O.amax = s_amax; O.pivotmax = s_pmax; O.pivotmin = s_pmin;
+                O.t_ns = globaltimer_ns() - P.ctrl->t0_ns; O.valid = 1; O.pad = 0;
+                if (err && !P.ctrl->error) P.ctrl->error = err;
+            }
+        }
+    }
+        __syncthreads();
+        tl_mark(P, 74);
+    };
     int it = 1;
     for (; it <= it_last; ++it) {
         const int dir = 2 - (it & 1);                  // dmrgg.f90:317
         const int par = it & 1;
         const unsigned long long seq = seq0 + (unsigned long long)it;
         C.rkL = sl.rkL; C.rkR = sl.rkR;
-        visit_list<KIND, true, true>(P, cl, C, it, dir, small_element, small_pivot);      // ends with a cluster barrier
+        auto hook = [&]() -> bool {
+            if (sl.pending == 0) return false;           // (first sweep: nothing to close)
+            close_sweep(it - 1, true);
+            if (threadIdx.x == 0) sl.pending = 0;
+            return sl.ready != 0;
+        };
+        if (visit_list<KIND, true, true>(P, cl, C, it, dir, small_element, small_pivot, hook)) { it -= 1; break; }      // ends with a cluster barrier
 
         // ---- several processes: the first / last partition of a process pushes what its foreign neighbour needs straight into
         // that process's window over NVLink (the tape of dmrgg.f90:763-850 reduced to the one table column the neighbour will
@@ -510,56 +571,10 @@ k_sweeps(DevPlan P, int it_last, int maxrank, double small_element, double small
             if (multi) { __threadfence_system(); st_release<true>(&mb->flag2, seq); }
             else { __threadfence(); st_release<false>(&mb->flag2, seq); }
         }
-        for (int u = threadIdx.x; u < P.P; u += blockDim.x) {
-            sweep_wait(P, &mail[u].flag2, seq, multi);
-            const volatile SweepRec& R = mail[u].rec[par];
-            sl.r_amax1[u & 63] = R.amax1; sl.r_pmax[u & 63] = R.pivotmax; sl.r_pmin[u & 63] = R.pivotmin;
-            sl.r_amax2[u & 63] = R.amax2; sl.r_neval[u & 63] = R.neval; sl.r_err[u & 63] = R.error;
-        }
+        if (threadIdx.x == 0) { sl.rkL += updL; sl.rkR += updR; sl.pending = it; sl.saved = sh.S; }
         __syncthreads();
-        tl_mark(P, 73);
-        // ---- MAX allreduce (dmrgg.f90:852-870), sweep record (:961-1008), exit test (:1010-1019); identical in every CTA
-        if (threadIdx.x == 0) {
-            double c1 = sl.r_amax1[0], c2 = sl.r_pmax[0], c3 = (sl.r_pmin[0] > 0.0) ? -sl.r_pmin[0] : -999e9;
-            long long ne = sl.r_neval[0];
-            int err = sl.r_err[0];
-            for (int u = 1; u < P.P; ++u) {
-                c1 = fmax(c1, sl.r_amax1[u]); c2 = fmax(c2, sl.r_pmax[u]);
-                c3 = fmax(c3, (sl.r_pmin[u] > 0.0) ? -sl.r_pmin[u] : -999e9);
-                ne += sl.r_neval[u]; err |= sl.r_err[u];
-            }
-            VState& St = sh.S;
-            St.amax = fmax(c1, St.amax);                 // the allreduced value, then this partition's corner fibers
-            const double s_pmax = c2, s_pmin = (-c3 == 999e9) ? -1.0 : -c3;
-            const double s_amax = fmax(c1, sl.r_amax2[0]);     // st[0].amax after the exchange
-            St.pivotmax_prev = s_pmax;                   // dmrgg.f90:961
-            St.pivotmax = -1.0; St.pivotmin = -1.0;      // dmrgg.f90:326-327 of the next sweep
-            int ready = 0;
-            if (maxrank > 0) ready = (it + 1 >= maxrank);
-            if (P.ctrl->has_accuracy) {
-                if (s_pmax <= P.ctrl->accuracy * s_amax) sl.strike += 1; else sl.strike = 0;
-                ready = ready || (sl.strike >= 3);
-            }
-            if (err) ready = 1;
-            sl.ready = ready;
-            sl.rkL += updL; sl.rkR += updR;
-            if (crank == 0) {
-                for (int x = lo; x <= hi - 1; ++x) { const int r = LDF(P.rk + x); P.rklog[(i64)it * (P.d + 1) + x] = r; P.rks[x] = r; }
-                if (v == 0) P.rklog[(i64)it * (P.d + 1)] = 1;
-                if (v == P.P - 1) P.rklog[(i64)it * (P.d + 1) + P.d] = 1;
-                if (v == P.v0) {                         // one record per process
-                    SweepOut& O = P.slog[it];
-                    O.neval = ne; O.amax = s_amax; O.pivotmax = s_pmax; O.pivotmin = s_pmin;
-                    O.t_ns = globaltimer_ns() - P.ctrl->t0_ns; O.valid = 1; O.pad = 0;
-                    if (err && !P.ctrl->error) P.ctrl->error = err;
-                }
-            }
-        }
-        __syncthreads();
-        tl_mark(P, 74);
-        if (sl.ready) break;
     }
-    if (it > it_last) it = it_last;
+    if (it > it_last) { it = it_last; if (sl.pending) close_sweep(it, false); }
     if (crank == 0 && threadIdx.x == 0) {
         P.st[v] = sh.S;
         if (v == P.v0) { P.ctrl->nsweeps = it; P.ctrl->it = it + 1; P.ctrl->strike = sl.strike; P.ctrl->ready = 1; }

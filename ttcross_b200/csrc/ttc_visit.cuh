@@ -559,8 +559,13 @@ struct VisitCtx {
     int upd_first, upd_last;   // out: was the partition's first / last bond updated in this sweep (uniform over the cluster)
     unsigned long long* bar; unsigned bar_parity;     // TMA staging (persistent kernel): CTA-local mbarrier and its phase
 };
-template <int KIND, bool TMA = false, bool WIDE = false>
-__device__ __forceinline__ void visit_list(const DevPlan& P, cg::cluster_group& cl, VisitCtx& C, int it, int dir, double small_element, double small_pivot) {
+// Hook called by every thread right before the accept test of the sweep's FIRST visit: the persistent kernel closes the
+// PREVIOUS sweep there (MAX allreduce, record, exit test), so the all-to-all wait for the other partitions' records overlaps
+// the lottery and the fibers of this visit, which have no side effects outside the cluster.  Returns true to abandon the sweep.
+struct NoVisitHook { __device__ __forceinline__ bool operator()() const { return false; } };
+template <int KIND, bool TMA = false, bool WIDE = false, class Hook = NoVisitHook>
+__device__ __forceinline__ bool visit_list(const DevPlan& P, cg::cluster_group& cl, VisitCtx& C, int it, int dir, double small_element, double small_pivot,
+                                           Hook hook = Hook()) {
     VisitShared& sh = *C.sh;
     const int crank = (int)cl.block_rank(), cs = (int)cl.num_blocks();
     const int v = C.v, lo = C.lo, hi = C.hi, nb = hi - lo;
@@ -816,6 +821,7 @@ __device__ __forceinline__ void visit_list(const DevPlan& P, cg::cluster_group& 
         }
 
         tl_mark(P, 47);
+        if (pp == 1 && hook()) return true;                         // (uniform over the cluster)
         // ---- accept test and index-set update (dmrgg.f90:598-660); every CTA takes the same decision
         const int ii = sh.S.ii, jj = sh.S.jj, kk = sh.S.kk, qq = sh.S.qq;
         const double pivot = sh.S.pivot;
@@ -959,6 +965,7 @@ __device__ __forceinline__ void visit_list(const DevPlan& P, cg::cluster_group& 
             O.active = 0; O.upd = 0;
         }
     }
+    return false;
 }
 
 constexpr int VISIT_MAXTHREADS = 256;
