@@ -127,6 +127,8 @@ struct ttc_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t evs0 = nullptr, evs1 = nullptr;        // around the persistent sweep kernel
     double sweep_ms = 0; int persistent_used = 0;
+    char* log_h = nullptr; size_t log_cap = 0;       // pinned mirror of ctrl | slog | rklog | vlog | rk (one synchronisation for all logs)
+    bool quad_cached = false; double quad_value = 0;   // dtt_quad of the finalised train, taken at the end of ttc_dmrgg (one process)
     int* lot_h = nullptr; VisitOut* out_h = nullptr; SweepOut* sweep_h = nullptr;   // pinned
     double* pack_d = nullptr; size_t pack_cap = 0;
     void* flush_d = nullptr; size_t flush_cap = 0;
@@ -346,6 +348,7 @@ void free_device(ttc_handle* h) {
     }
     h->allocs.clear(); h->alloc_bytes.clear(); h->host_blocks.clear();
     h->lot_h = nullptr; h->out_h = nullptr; h->sweep_h = nullptr; h->ready_h = nullptr; h->stage_h = nullptr; h->stage_cap = 0;
+    h->log_h = nullptr; h->log_cap = 0;
     h->pack_d = nullptr; h->pack_cap = 0;
     if (h->ev0) { cudaEventDestroy(h->ev0); h->ev0 = nullptr; }
     if (h->ev1) { cudaEventDestroy(h->ev1); h->ev1 = nullptr; }
@@ -1439,13 +1442,39 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     }
     if (persist_quad_pending) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_join[0], 0));      // the per-sweep values are part of the run
     CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    // Every reference driver follows dtt_dmrgg with dtt_quad of the finalised train (test_crs_ising.f90:158): with one process
+    // its few small kernels are enqueued right here (after the timed region of ttc_device_ms) and ttc_quad returns the value
+    // without another launch + synchronisation round.
+    h->quad_cached = false;
+    if (h->nproc == 1) {
+        int stq = launch_quad(h, L, false, !h->quad.empty(), 1);
+        if (stq) return stq;
+        CUDA_TRY(h, cudaMemcpyAsync(h->sweep_h, h->plan.sweep_out, sizeof(SweepOut), cudaMemcpyDeviceToHost, s));
+    }
+    // the logs travel with the same synchronisation: ctrl | slog | rklog | vlog | rk into one pinned block (capacity-sized)
+    const size_t lb_ctrl = 0, lb_slog = 256, lb_rklog = lb_slog + (((size_t)(Rmax + 1) * sizeof(SweepOut) + 63) & ~(size_t)63),
+                 lb_vlog = lb_rklog + (((size_t)(Rmax + 1) * (d + 1) * sizeof(int) + 63) & ~(size_t)63),
+                 lb_rk = lb_vlog + (((size_t)Rmax * maxnb * P * sizeof(VisitOut) + 63) & ~(size_t)63),
+                 lb_tot = lb_rk + (((size_t)(d + 2) * sizeof(int) + 63) & ~(size_t)63);
+    if (lb_tot > h->log_cap) {
+        void* q = nullptr;
+        { std::lock_guard<std::mutex> lk(g_pool_mu); CUDA_TRY(h, g_pool.get_host(lb_tot, &q)); }
+        h->host_blocks.push_back({q, lb_tot});
+        h->log_h = (char*)q; h->log_cap = lb_tot;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->log_h + lb_ctrl, D.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->log_h + lb_slog, D.slog, (size_t)(Rmax + 1) * sizeof(SweepOut), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->log_h + lb_rklog, D.rklog, (size_t)(Rmax + 1) * (d + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->log_h + lb_vlog, D.vlog, (size_t)Rmax * maxnb * P * sizeof(VisitOut), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->log_h + lb_rk, D.rk, (size_t)(d + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     CUDA_TRY(h, cudaGetLastError());
+    if (h->nproc == 1) { h->quad_value = h->sweep_h->val; h->quad_cached = true; }
 
     tr.lap("sweeps+finalise");
     // ---- read the logs back and rebuild the reference's report
     Ctrl ctrl;
-    CUDA_TRY(h, cudaMemcpy(&ctrl, D.ctrl, sizeof ctrl, cudaMemcpyDeviceToHost));
+    std::memcpy(&ctrl, h->log_h + lb_ctrl, sizeof ctrl);
     if (ctrl.error == 3) { h->err = "multi-GPU exchange timed out waiting for a peer rank"; return TTC_ERR_COMM; }
     if (ctrl.error == 2) { h->err = "internal: the incremental quadrature saw a rank grow by more than one in a sweep"; return TTC_ERR_STATE; }
     if (ctrl.error) { h->err = "rank capacity exceeded (pass maxrank)"; return TTC_ERR_RANK; }
@@ -1456,16 +1485,16 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         std::vector<int> rklog((size_t)(it + 1) * (d + 1));
         std::vector<VisitOut> vlog((size_t)std::max(it, 1) * maxnb * P);
         if (it > 0) {
-            CUDA_TRY(h, cudaMemcpy(slog.data(), D.slog, slog.size() * sizeof(SweepOut), cudaMemcpyDeviceToHost));
-            CUDA_TRY(h, cudaMemcpy(rklog.data(), D.rklog, rklog.size() * sizeof(int), cudaMemcpyDeviceToHost));
-            CUDA_TRY(h, cudaMemcpy(vlog.data(), D.vlog, (size_t)it * maxnb * P * sizeof(VisitOut), cudaMemcpyDeviceToHost));
+            std::memcpy(slog.data(), h->log_h + lb_slog, slog.size() * sizeof(SweepOut));
+            std::memcpy(rklog.data(), h->log_h + lb_rklog, rklog.size() * sizeof(int));
+            std::memcpy(vlog.data(), h->log_h + lb_vlog, (size_t)it * maxnb * P * sizeof(VisitOut));
         }
         if (persistent) {
             // the '0::' line of the initial cross (dmrgg.f90:250-300) from the record k_init_state left in slog[0]
             std::vector<int> rk1(d + 2, 1);
             const double er0 = erank(d, h->n, rk1);
             SweepOut s0;
-            CUDA_TRY(h, cudaMemcpy(&s0, D.slog, sizeof s0, cudaMemcpyDeviceToHost));
+            std::memcpy(&s0, h->log_h + lb_slog, sizeof s0);
             std::snprintf(line, sizeof line, "%3d%2s rank%5.1f time: %s n_evals: %10lld", 0, "::", er0, fmt_e(t_init, 9, 3).c_str(), (long long)s0.neval);
             std::string str0 = line;
             if (has_quad) str0 += " val " + fmt_e(s0.val, 20, 14);
@@ -1499,7 +1528,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
             nevalall = SO.neval;
         }
         std::vector<int> rkf(d + 2, 1);
-        CUDA_TRY(h, cudaMemcpy(rkf.data(), D.rk, (size_t)(d + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+        std::memcpy(rkf.data(), h->log_h + lb_rk, (size_t)(d + 1) * sizeof(int));
         h->rk_h = rkf;
     }
     tr.lap("logs");
@@ -1598,6 +1627,7 @@ int ttc_set_partition(ttc_handle* h, int nparts, const int* own) {
     return TTC_OK;
 }
 int ttc_set_quad(ttc_handle* h, const double* quad) {
+    if (h) h->quad_cached = false;
     if (!h) return TTC_ERR_ARG;
     h->quad.clear();
     if (quad) { size_t tot = 0; for (int p = 1; p <= h->d; ++p) tot += h->n[p]; h->quad.assign(quad, quad + tot); }
@@ -1750,6 +1780,7 @@ long ttc_text(const ttc_handle* h, char* buf, long cap) {
 int ttc_quad(ttc_handle* h, double* val) {
     if (!h || !val) return TTC_ERR_ARG;
     if (!h->ran) { h->err = "ttc_quad before ttc_dmrgg"; return TTC_ERR_STATE; }
+    if (h->quad_cached) { *val = h->quad_value; return TTC_OK; }
     CUDA_TRY(h, cudaSetDevice(h->device));
     Launcher L(h);
     // peer windows: the last sweep's phase-2 slots of a slower rank must have been consumed before anybody overwrites them
@@ -1851,6 +1882,7 @@ cudaError_t qr_launch(cudaStream_t s, int nsm, const double* da, int m, int n, d
 // r(k) <= r(k-1) n(k), the only case handled).  Single process only.
 int ttc_ort(ttc_handle* h) {
     if (!h) return TTC_ERR_ARG;
+    h->quad_cached = false;
     if (!h->ran) { h->err = "ttc_ort before ttc_dmrgg"; return TTC_ERR_STATE; }
     if (h->nproc > 1) { h->err = "ttc_ort: not collective yet (run it on a single-process handle)"; return TTC_ERR_STATE; }
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -1922,6 +1954,7 @@ static int chop_ref(const std::vector<double>& sv, bool has_tol, double tol, boo
 // ttc_ranks / ttc_core / ttc_quad see the rounded train.  Single process only; needs r <= 64.
 int ttc_svd(ttc_handle* h, double tol, int rmax) {
     if (!h) return TTC_ERR_ARG;
+    h->quad_cached = false;
     if (!h->ran) { h->err = "ttc_svd before ttc_dmrgg"; return TTC_ERR_STATE; }
     if (h->nproc > 1) { h->err = "ttc_svd: not collective yet (run it on a single-process handle)"; return TTC_ERR_STATE; }
     for (int k = 0; k <= h->d; ++k) if (h->rk_h[k] > 64) { h->err = "ttc_svd: ranks above 64 are not supported"; return TTC_ERR_ARG; }
