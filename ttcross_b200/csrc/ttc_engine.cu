@@ -182,6 +182,7 @@ struct ttc_handle {
 
 namespace {
 
+int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting);
 std::string g_create_err;
 
 #define NCCL_TRY(h, call)                                                                                   \
@@ -1341,6 +1342,14 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         cudaError_t ce = cudaSuccess;
         CUDA_TRY(h, cudaEventRecord(h->evs0, s));
         VISIT_KIND_SWITCH(h, L(KC_VISITS, [&] { ce = cudaLaunchKernelEx(&cfg, k_sweeps<K>, D, last_sweep, eff_maxrank, small_element, small_pivot); }));
+        if (ce != cudaSuccess && h->nproc == 1) {
+            // the driver refused the cooperative launch (e.g. another context holds SMs): not an error of the problem -- run the
+            // per-sweep schedule instead (the device state built so far is reused; the initial cross is redone on that path)
+            (void)cudaGetLastError();
+            if (std::getenv("TTC_TRACE")) std::fprintf(stderr, "[ttc trace] persistent kernel: cooperative launch refused (%s), per-sweep schedule instead\n", cudaGetErrorString(ce));
+            h->persist_ok = false;
+            return run_dmrgg(h, maxrank, accuracy, pivoting);
+        }
         CUDA_TRY(h, ce);
         CUDA_TRY(h, cudaEventRecord(h->evs1, s));
         if (has_quad) {
