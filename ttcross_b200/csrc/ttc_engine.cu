@@ -729,11 +729,13 @@ int setup_device(ttc_handle* h, int maxrank) {
         // 16 x 256 (up to 7 partitions), 16 x 128 (two CTAs per SM where needed: 14), 8 x 256 (15), 8 x 128, 4 x 128 ...
         h->sweep_threads = 0; h->sweep_cluster = 0;
         if (h->cluster_ok && (h->nproc == 1 || h->p2p) && !std::getenv("TTC_NO_PERSISTENT")) {
+            const int maxt = h->kind == TTC_MVN ? SWEEP_MAXTHREADS_MVN : SWEEP_MAXTHREADS;
             std::vector<std::pair<int, int>> cand = {{16, 256}, {16, 128}, {8, 256}, {8, 128}, {4, 128}, {2, 128}, {1, 128}};
+            if (h->kind == TTC_MVN) cand = {{16, 192}, {8, 192}, {4, 192}, {4, 128}, {2, 192}, {1, 192}};
             if (std::getenv("TTC_SWEEP_THREADS") || std::getenv("TTC_SWEEP_CLUSTER")) {
                 const int cs = std::getenv("TTC_SWEEP_CLUSTER") ? std::atoi(std::getenv("TTC_SWEEP_CLUSTER")) : 16;
                 const int th = std::getenv("TTC_SWEEP_THREADS") ? std::atoi(std::getenv("TTC_SWEEP_THREADS")) : 256;
-                cand = {{std::max(1, std::min(MAXCS, cs)), std::max(32, std::min(SWEEP_MAXTHREADS, th / 32 * 32))}};
+                cand = {{std::max(1, std::min(MAXCS, cs)), std::max(32, std::min(maxt, th / 32 * 32))}};
             }
             cudaError_t ce = cudaSuccess;
             VISIT_KIND_SWITCH(h,
@@ -741,7 +743,7 @@ int setup_device(ttc_handle* h, int maxrank) {
                 if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_sweeps<K>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             );
             for (size_t ci = 0; ci < cand.size() && ce == cudaSuccess && !h->persist_ok; ++ci) {
-                const int cs = cand[ci].first, th = std::min(cand[ci].second, SWEEP_MAXTHREADS);
+                const int cs = cand[ci].first, th = std::min(cand[ci].second, maxt);
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3(cs, D.nv, 1); cfg.blockDim = dim3(th, 1, 1); cfg.dynamicSmemBytes = h->sm_sweep;
                 cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
