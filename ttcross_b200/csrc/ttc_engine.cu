@@ -1860,7 +1860,8 @@ int ttc_fp64_peak(int device, int fma, double* tflops) {
 
 // cooperative launch of k_qr_panel on device buffers (m >= n); scratch: part[G], partw[2*G*n], head[n+2]
 struct QrScratch { double* part = nullptr; double* pw = nullptr; double* head = nullptr; size_t cap_g = 0, cap_n = 0;
-    void release() { cudaFree(part); cudaFree(pw); cudaFree(head); part = pw = head = nullptr; cap_g = cap_n = 0; } };
+    double* tsqr = nullptr; size_t cap_t = 0;                       // TSQR: sign vector | per level R factors (| Q blocks)
+    void release() { cudaFree(part); cudaFree(pw); cudaFree(head); cudaFree(tsqr); part = pw = head = tsqr = nullptr; cap_g = cap_n = cap_t = 0; } };
 int qr_geometry(int nsm, int m, int n, int& G, int& rpb, size_t& smem) {
     const int rows_target = std::getenv("TTC_QR_ROWS") ? std::max(16, std::atoi(std::getenv("TTC_QR_ROWS"))) : 128;
     G = std::max(1, std::min(nsm, (m + rows_target - 1) / rows_target));
@@ -1870,7 +1871,47 @@ int qr_geometry(int nsm, int m, int n, int& G, int& rpb, size_t& smem) {
     smem = ((size_t)rpb * n + n) * sizeof(double);
     return smem <= 200 * 1024 ? 0 : TTC_ERR_ARG;
 }
+// TSQR (ttc_qr.cuh): level-1 blocks of ~4n rows, a tree of stacked R factors with fan-in 4, the chain of Q slices applied to the
+// first-level blocks, LAPACK's signs by Householder reconstruction.  Applies to m >= 8n, n <= 64; TTC_NO_TSQR=1 keeps k_qr_panel.
+static bool tsqr_applicable(int m, int n) { return n >= 1 && n <= 64 && m >= 8 * n && !std::getenv("TTC_NO_TSQR"); }
+cudaError_t tsqr_launch(cudaStream_t s, const double* da, int m, int n, double* dq, double* dr, QrScratch& sc) {
+    const int G1 = (m + 4 * n - 1) / (4 * n);
+    std::vector<int> G = {G1};
+    while (G.back() > 1) G.push_back((G.back() + 3) / 4);
+    const int L = (int)G.size();                                  // levels 1 .. L (level L has one node)
+    if (L > 8) return cudaErrorInvalidValue;
+    size_t need = (size_t)n + 8;
+    for (int l = 0; l < L; ++l) need += (size_t)G[l] * n * n + (l >= 1 ? (size_t)G[l] * 4 * n * n : 0);
+    if (need > sc.cap_t) {
+        if (sc.tsqr) cudaFree(sc.tsqr);
+        sc.tsqr = nullptr; sc.cap_t = 0;
+        cudaError_t e = cudaMalloc((void**)&sc.tsqr, need * sizeof(double));
+        if (e != cudaSuccess) return e;
+        sc.cap_t = need;
+    }
+    std::vector<double*> Rl(L), Ql(L, nullptr);
+    double* p = sc.tsqr;
+    double* sgn = p; p += n + 8;
+    for (int l = 0; l < L; ++l) { Rl[l] = p; p += (size_t)G[l] * n * n; if (l >= 1) { Ql[l] = p; p += (size_t)G[l] * 4 * n * n; } }
+    const int rows1 = (m + G1 - 1) / G1 + 1;
+    const size_t sm_f = ((size_t)std::max(rows1, 4 * n) * n + n + 40) * sizeof(double);
+    const size_t sm_a = ((size_t)2 * n * n + (size_t)rows1 * n) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(k_tsqr_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tsqr_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a);
+    if (e != cudaSuccess) return e;
+    k_tsqr_factor<<<G1, TSQR_THREADS, sm_f, s>>>(da, 1, m, n, m, G1, 0, Rl[0], dq, m);
+    for (int l = 1; l < L; ++l) k_tsqr_factor<<<G[l], TSQR_THREADS, sm_f, s>>>(Rl[l - 1], l + 1, m, n, m, G1, G[l - 1], Rl[l], Ql[l], m);
+    TsqrLevels LV; LV.count = L - 1;
+    for (int l = 1; l < L; ++l) LV.q[l - 1] = Ql[l];
+    if (L > 1) k_tsqr_apply<<<G1, TSQR_THREADS, sm_a, s>>>(dq, m, n, m, G1, LV);
+    e = cudaMemcpyAsync(dr, Rl[L - 1], (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return e;
+    k_tsqr_sign<<<1, TSQR_THREADS, ((size_t)n * n + n) * sizeof(double), s>>>(dq, n, m, dr, sgn);
+    k_tsqr_scale<<<std::min(2048, (int)(((long long)m * n + 255) / 256)), 256, 0, s>>>(dq, m, n, m, sgn);
+    return cudaGetLastError();
+}
 cudaError_t qr_launch(cudaStream_t s, int nsm, const double* da, int m, int n, double* dq, double* dr, QrScratch& sc) {
+    if (tsqr_applicable(m, n)) return tsqr_launch(s, da, m, n, dq, dr, sc);
     int G, rpb; size_t smem;
     if (qr_geometry(nsm, m, n, G, rpb, smem)) return cudaErrorInvalidValue;
     if ((size_t)G > sc.cap_g || (size_t)n > sc.cap_n) {

@@ -150,6 +150,176 @@ __global__ void __launch_bounds__(QR_THREADS) k_qr_panel(const double* __restric
     for (int e = threadIdx.x; e < rows * n; e += blockDim.x) { const int j = e / rows, i = e - j * rows; q[(size_t)(row0 + i) + (size_t)m * j] = S[e]; }
 }
 
+// =============================================================================
+// TSQR (round 2): communication-avoiding QR for the tall-skinny case (m >= 4n, n <= 64) with LAPACK's result.
+//
+// k_qr_panel above runs the unblocked algorithm over the whole grid: two grid barriers per column (64 columns x 2 phases).
+// Here the rows are dealt out in blocks of ~4n; every block is factored INSIDE one CTA (shared memory, block barriers only),
+// the n x n R factors are stacked four at a time and factored again, level by level, until one R is left
+// (k_tsqr_factor, one launch per level); then every first-level block multiplies its explicit Q by the chain of n x n
+// slices of the upper levels' Q factors (k_tsqr_apply: Q = Q1 Q2 ... QL, a dense (rows x n)(n x n) product per block).
+//
+// A QR is unique up to the signs of R's rows.  LAPACK's signs (beta = -sign(alpha) |x| at every step of the UNBLOCKED
+// algorithm) depend on the history of that algorithm, but they can be recovered from any QR by "Householder
+// reconstruction" (Ballard, Demmel, Grigori, Jacquelin, Nguyen, Solomonik 2014): run an LU factorisation without pivoting on
+// the top n x n block of Q, choosing S_kk = -sgn(current diagonal entry) and subtracting S_kk from it before eliminating;
+// then R_H = S R and Q_H = Q S are the Householder (LAPACK) factors.  k_tsqr_sign does that in one CTA, k_tsqr_scale applies
+// S to the columns of Q.  Checked against numpy.linalg.qr (tests/test_qr.py, unchanged).
+// =============================================================================
+constexpr int TSQR_THREADS = 1024;     // 32 warps: with two trailing columns per warp a reflector is applied in one round for n <= 64
+
+// H(k) = I - tau v v^T (v(k) = 1, v(i) = S(i,k) below) applied to the trailing columns, TWO columns per warp at a time (they
+// share the loads of v); dot product and update of a column stay inside its warp
+__device__ __forceinline__ void cta_apply_reflector(double* S, int rows, int n, int k, double tk) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int j0 = k + 1 + wid; j0 < n; j0 += 2 * nw) {
+        const int j1 = j0 + nw;
+        const bool two = j1 < n;
+        const double* v = S + (size_t)rows * k;
+        double* c0 = S + (size_t)rows * j0; double* c1 = S + (size_t)rows * (two ? j1 : j0);
+        double w0 = 0.0, w1 = 0.0;
+        for (int i = k + 1 + lane; i < rows; i += 32) { const double vi = v[i]; w0 += vi * c0[i]; w1 += vi * c1[i]; }
+        for (int o = 16; o > 0; o >>= 1) { w0 += __shfl_xor_sync(0xffffffffu, w0, o); w1 += __shfl_xor_sync(0xffffffffu, w1, o); }
+        w0 += c0[k]; w1 += c1[k];
+        const double t0 = tk * w0, t1 = tk * w1;
+        for (int i = k + 1 + lane; i < rows; i += 32) { const double vi = v[i]; c0[i] -= t0 * vi; if (two) c1[i] -= t1 * vi; }
+        if (lane == 0) { c0[k] -= t0; if (two) c1[k] -= t1; }
+    }
+}
+// Householder QR of the rows x n block S (column-major, leading dimension rows, rows >= n) held in shared memory, by one CTA.
+// On return the upper triangle holds R, the columns below the diagonal the reflector vectors (v(k) = 1 implicit), tau[k] the
+// scalars.  One warp per trailing column: dot product and update of a column stay inside its warp, so a reflector costs two
+// block barriers.  sh: scratch >= 34 doubles.
+__device__ __forceinline__ void cta_house_qr(double* S, int rows, int n, double* tau, double* sh) {
+    for (int k = 0; k < n; ++k) {
+        double ss = 0.0;
+        for (int i = k + 1 + threadIdx.x; i < rows; i += blockDim.x) { const double x = S[i + rows * k]; ss += x * x; }
+        ss = qr_block_sum(ss, sh);
+        const double alpha = S[k + rows * k];
+        double beta = alpha, scale = 0.0, tk = 0.0;
+        if (ss != 0.0) {
+            beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+            tk = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+        }
+        __syncthreads();                                  // everybody has read alpha
+        for (int i = k + 1 + threadIdx.x; i < rows; i += blockDim.x) S[i + rows * k] *= scale;
+        if (threadIdx.x == 0) { S[k + rows * k] = beta; tau[k] = tk; }
+        __syncthreads();
+        cta_apply_reflector(S, rows, n, k, tk);
+        __syncthreads();
+    }
+}
+// dorg2r in place: the reflectors left by cta_house_qr become the explicit rows x n factor Q
+__device__ __forceinline__ void cta_house_formq(double* S, int rows, int n, const double* tau) {
+    for (int k = n - 1; k >= 0; --k) {
+        const double tk = tau[k];
+        cta_apply_reflector(S, rows, n, k, tk);
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+            double x = S[i + rows * k];
+            if (i > k) x = -tk * x; else if (i == k) x = 1.0 - tk; else x = 0.0;
+            S[i + rows * k] = x;
+        }
+        __syncthreads();
+    }
+}
+// One level of the tree.  Node b factors `cnt` stacked source blocks:
+//   level 1 : src = A (m x n, lda), block b = rows [b*m/G, (b+1)*m/G);                     Q block -> qout (ldq = m) at those rows
+//   level>1 : src = the previous level's R factors (n x n each, contiguous), node b stacks R[4b .. 4b+3];  Q block (cnt*n x n) -> qout + b*4n*n
+// rout + b*n*n receives the node's R (upper triangular, zeros below).  dynamic smem: (maxrows*n + n + 40) doubles.
+__global__ void __launch_bounds__(TSQR_THREADS) k_tsqr_factor(const double* __restrict__ src, int level, int m, int n, int lda, int G, int nsrc,
+                                                             double* __restrict__ rout, double* __restrict__ qout, int ldq) {
+    extern __shared__ double smem[];
+    const int b = blockIdx.x;
+    int rows, row0 = 0;
+    if (level == 1) { row0 = (int)((long long)b * m / G); rows = (int)((long long)(b + 1) * m / G) - row0; }
+    else { const int c0 = 4 * b; rows = min(4, nsrc - c0) * n; }
+    double* S = smem; double* tau = S + (size_t)rows * n; double* sh = tau + n;
+    if (level == 1) {
+        for (int e = threadIdx.x; e < rows * n; e += blockDim.x) { const int j = e / rows, i = e - j * rows; S[e] = src[(size_t)(row0 + i) + (size_t)lda * j]; }
+    } else {
+        for (int e = threadIdx.x; e < rows * n; e += blockDim.x) {
+            const int j = e / rows, i = e - j * rows, blk = i / n, ii = i - blk * n;
+            S[e] = src[((size_t)(4 * b + blk) * n + j) * n + ii];
+        }
+    }
+    __syncthreads();
+    cta_house_qr(S, rows, n, tau, sh);
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) { const int j = e / n, i = e - j * n; rout[(size_t)b * n * n + e] = (i <= j) ? S[i + rows * j] : 0.0; }
+    __syncthreads();
+    cta_house_formq(S, rows, n, tau);
+    if (level == 1) {
+        for (int e = threadIdx.x; e < rows * n; e += blockDim.x) { const int j = e / rows, i = e - j * rows; qout[(size_t)(row0 + i) + (size_t)ldq * j] = S[e]; }
+    } else {
+        double* qb = qout + (size_t)b * 4 * n * n;                 // (4n x n, leading dimension 4n)
+        for (int e = threadIdx.x; e < rows * n; e += blockDim.x) { const int j = e / rows, i = e - j * rows; qb[i + (size_t)4 * n * j] = S[e]; }
+    }
+}
+// Q(block b) <- Q1(block b) * Q2[slice] * Q3[slice] * ... (levels 2..L); qlev[l] = that level's Q blocks (4n x n each, ld 4n).
+struct TsqrLevels { const double* q[8]; int count; };
+__global__ void __launch_bounds__(TSQR_THREADS) k_tsqr_apply(double* __restrict__ q, int m, int n, int ldq, int G, TsqrLevels LV) {
+    extern __shared__ double smem[];
+    const int b = blockIdx.x;
+    const int row0 = (int)((long long)b * m / G), rows = (int)((long long)(b + 1) * m / G) - row0;
+    double* M = smem; double* T = M + n * n; double* QB = T + n * n;      // M, T: n x n (ld n); QB: rows x n
+    for (int e = threadIdx.x; e < rows * n; e += blockDim.x) { const int j = e / rows, i = e - j * rows; QB[e] = q[(size_t)(row0 + i) + (size_t)ldq * j]; }
+    int idx = b;
+    for (int l = 0; l < LV.count; ++l) {
+        const int node = idx / 4, slot = idx - 4 * node;
+        const double* ql = LV.q[l] + (size_t)node * 4 * n * n + (size_t)slot * n;        // rows slot*n .. of the 4n x n block
+        if (l == 0) {
+            for (int e = threadIdx.x; e < n * n; e += blockDim.x) { const int j = e / n, i = e - j * n; M[e] = ql[i + (size_t)4 * n * j]; }
+        } else {
+            for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+                const int j = e / n, i = e - j * n;
+                double t = 0.0;
+                for (int x = 0; x < n; ++x) t += M[i + n * x] * ql[x + (size_t)4 * n * j];
+                T[e] = t;
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < n * n; e += blockDim.x) M[e] = T[e];
+        }
+        __syncthreads();
+        idx = node;
+    }
+    if (LV.count == 0) return;
+    for (int e = threadIdx.x; e < rows * n; e += blockDim.x) {
+        const int j = e / rows, i = e - j * rows;
+        double t = 0.0;
+        for (int x = 0; x < n; ++x) t += QB[i + rows * x] * M[x + n * j];
+        q[(size_t)(row0 + i) + (size_t)ldq * j] = t;
+    }
+}
+// Householder reconstruction of LAPACK's signs: modified LU (no pivoting) of the top n x n block of Q; sgn[k] = S_kk; r <- S r.
+__global__ void __launch_bounds__(TSQR_THREADS) k_tsqr_sign(const double* __restrict__ q, int n, int ldq, double* __restrict__ r, double* __restrict__ sgn) {
+    extern __shared__ double smem[];
+    double* W = smem; double* S = W + n * n;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) { const int j = e / n, i = e - j * n; W[e] = q[(size_t)i + (size_t)ldq * j]; }
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+        if (threadIdx.x == 0) { const double sk = (W[k + n * k] >= 0.0) ? -1.0 : 1.0; S[k] = sk; W[k + n * k] -= sk; }
+        __syncthreads();
+        const double piv = W[k + n * k];
+        for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) W[i + n * k] /= piv;
+        __syncthreads();
+        for (int e = threadIdx.x; e < (n - k - 1) * (n - k - 1); e += blockDim.x) {
+            const int jj = e / (n - k - 1), ii = e - jj * (n - k - 1), i = k + 1 + ii, j = k + 1 + jj;
+            W[i + n * j] -= W[i + n * k] * W[k + n * j];
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) { const int i = e % n; r[e] = S[i] * r[e]; }
+    for (int k = threadIdx.x; k < n; k += blockDim.x) sgn[k] = S[k];
+}
+__global__ void k_tsqr_scale(double* __restrict__ q, int m, int n, int ldq, const double* __restrict__ sgn) {
+    const long long tot = (long long)m * n;
+    for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < tot; x += (long long)gridDim.x * blockDim.x) {
+        const long long j = x / m; const long long i = x - j * m;
+        if (sgn[j] < 0.0) q[i + (long long)ldq * j] = -q[i + (long long)ldq * j];
+    }
+}
+
 // ----------------------------------------------------------------------------
 // Support kernels of dtt_ort (lib/tt.f90:130-198): left-to-right orthogonalisation of the train.  Per core k:
 //   QR of the (r(k-1) n(k)) x r(k) unfolding (k_qr_panel) -> R / ||R||_F, lognrm += log ||R||_F  (k_ort_rnorm)
