@@ -170,7 +170,7 @@ constexpr int TSQR_THREADS = 1024;     // 32 warps: with two trailing columns pe
 
 // H(k) = I - tau v v^T (v(k) = 1, v(i) = S(i,k) below) applied to the trailing columns, TWO columns per warp at a time (they
 // share the loads of v); dot product and update of a column stay inside its warp
-__device__ __forceinline__ void cta_apply_reflector(double* S, int rows, int n, int k, double tk) {
+__device__ __forceinline__ void cta_apply_reflector(double* S, int rows, int n, int k, double tk, double* next_ss = nullptr) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int j0 = k + 1 + wid; j0 < n; j0 += 2 * nw) {
         const int j1 = j0 + nw;
@@ -182,8 +182,19 @@ __device__ __forceinline__ void cta_apply_reflector(double* S, int rows, int n, 
         for (int o = 16; o > 0; o >>= 1) { w0 += __shfl_xor_sync(0xffffffffu, w0, o); w1 += __shfl_xor_sync(0xffffffffu, w1, o); }
         w0 += c0[k]; w1 += c1[k];
         const double t0 = tk * w0, t1 = tk * w1;
-        for (int i = k + 1 + lane; i < rows; i += 32) { const double vi = v[i]; c0[i] -= t0 * vi; if (two) c1[i] -= t1 * vi; }
+        double ss = 0.0;                                   // (warp 0's first column is column k+1: its norm below row k+1 feeds the next reflector)
+        for (int i = k + 1 + lane; i < rows; i += 32) {
+            const double vi = v[i];
+            const double x = c0[i] - t0 * vi;
+            c0[i] = x;
+            if (i > k + 1) ss += x * x;
+            if (two) c1[i] -= t1 * vi;
+        }
         if (lane == 0) { c0[k] -= t0; if (two) c1[k] -= t1; }
+        if (next_ss && j0 == k + 1) {
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            if (lane == 0) *next_ss = ss;
+        }
     }
 }
 // Householder QR of the rows x n block S (column-major, leading dimension rows, rows >= n) held in shared memory, by one CTA.
@@ -192,9 +203,12 @@ __device__ __forceinline__ void cta_apply_reflector(double* S, int rows, int n, 
 // block barriers.  sh: scratch >= 34 doubles.
 __device__ __forceinline__ void cta_house_qr(double* S, int rows, int n, double* tau, double* sh) {
     for (int k = 0; k < n; ++k) {
-        double ss = 0.0;
-        for (int i = k + 1 + threadIdx.x; i < rows; i += blockDim.x) { const double x = S[i + rows * k]; ss += x * x; }
-        ss = qr_block_sum(ss, sh);
+        double ss;
+        if (k == 0) {
+            ss = 0.0;
+            for (int i = 1 + threadIdx.x; i < rows; i += blockDim.x) { const double x = S[i]; ss += x * x; }
+            ss = qr_block_sum(ss, sh);
+        } else ss = sh[33];                               // left by the warp that updated column k in the previous step
         const double alpha = S[k + rows * k];
         double beta = alpha, scale = 0.0, tk = 0.0;
         if (ss != 0.0) {
@@ -206,7 +220,7 @@ __device__ __forceinline__ void cta_house_qr(double* S, int rows, int n, double*
         for (int i = k + 1 + threadIdx.x; i < rows; i += blockDim.x) S[i + rows * k] *= scale;
         if (threadIdx.x == 0) { S[k + rows * k] = beta; tau[k] = tk; }
         __syncthreads();
-        cta_apply_reflector(S, rows, n, k, tk);
+        cta_apply_reflector(S, rows, n, k, tk, sh + 33);
         __syncthreads();
     }
 }
