@@ -1015,7 +1015,11 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         L(KC_INIT, [&] { k_init_pick<<<1, 1024, 0, s>>>(D, nn, snum, db, h->init_scal, h->init_ind0); });
         KIND_SWITCH(h->kind, L(KC_INIT, [&] { k_init_cross<K><<<dim3(cdiv(h->nmax, TB), d), TB, smA, s>>>(D); }));
         L(KC_INIT, [&] { k_init_factors<<<dim3(cdiv(h->nmax, 256), d), 256, 0, s>>>(D); });
-        L(KC_INIT, [&] { k_init_state<<<1, 256, 0, s>>>(D, nn, snum, h->init_scal, h->init_ind0, has_quad ? 1 : 0); });
+        {
+            const size_t smi = (size_t)d * h->nmax * sizeof(double);
+            if (smi > 48 * 1024) cudaFuncSetAttribute(k_init_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smi);
+            L(KC_INIT, [&] { k_init_state<<<1, 1024, smi, s>>>(D, nn, snum, h->init_scal, h->init_ind0, has_quad ? 1 : 0); });
+        }
         h->rk_h.assign(d + 2, 1); h->rks_h.assign(d + 2, 1);
         h->rng_k.assign(P, 0);
         t_init = timef();

@@ -774,15 +774,21 @@ __global__ void k_init_pick(DevPlan P, int nn, int snum, const double* b, double
     }
 }
 __global__ void k_init_state(DevPlan P, int nn, int snum, const double* scal, const int* ind0, int has_quad) {
+    extern __shared__ double fibs[];                      // fibs[(p-1) * nmax + j]: the initial fiber of every core, staged by all threads
     __shared__ double s_dot[MAXD_LOCAL * 8 + 2], s_part[64];
     const int d = P.d, NP = P.P;
     const double gmax = scal[0];
-    // ddot(fiber(p), quad(p)) per core, sequential in j like the reference's ddot
+    for (int x = threadIdx.x; x < d * P.nmax; x += blockDim.x) {
+        const int p = x / P.nmax + 1, j = x - (p - 1) * P.nmax;
+        fibs[x] = (j < P.n[p]) ? P.arg[P.coreOff[p] + (i64)P.Rmax * j] : 0.0;
+    }
+    __syncthreads();
+    // ddot(fiber(p), quad(p)) per core, sequential in j like the reference's ddot (out of shared memory: no load latency on the chain)
     for (int p = 1 + threadIdx.x; p <= d; p += blockDim.x) {
         double t = 0.0;
         if (has_quad && p < (int)(sizeof(s_dot) / sizeof(double))) {
-            const double* a = P.arg + P.coreOff[p]; const double* w = P.quadw + P.quadOff[p];
-            for (int j = 0; j < P.n[p]; ++j) t = t + a[(i64)P.Rmax * j] * w[j];
+            const double* a = fibs + (size_t)(p - 1) * P.nmax; const double* w = P.quadw + P.quadOff[p];
+            for (int j = 0; j < P.n[p]; ++j) t = t + a[j] * w[j];
             s_dot[p] = t;
         }
     }
@@ -793,8 +799,8 @@ __global__ void k_init_state(DevPlan P, int nn, int snum, const double* scal, co
         long long ne = (long long)nn * (s1 - s0);
         for (int p = P.own[v]; p <= P.own[v + 1]; ++p) {
             ne += P.n[p];
-            const double* a = P.arg + P.coreOff[p];
-            for (int j = 0; j < P.n[p]; ++j) am = fmax(am, fabs(a[(i64)P.Rmax * j]));
+            const double* a = fibs + (size_t)(p - 1) * P.nmax;
+            for (int j = 0; j < P.n[p]; ++j) am = fmax(am, fabs(a[j]));
         }
         VState S;
         S.ii = S.jj = S.kk = S.qq = 0; S.pivot = 0.0; S.done = S.havecol = S.haverow = S.crs = 0; S.upd = 0; S.pad0 = 0;
@@ -802,7 +808,7 @@ __global__ void k_init_state(DevPlan P, int nn, int snum, const double* scal, co
         P.st[v] = S;
         double x = 1.0;
         if (has_quad) {
-            for (int p = P.own[v]; p <= P.own[v + 1] - 1; ++p) x = x * s_dot[p] / P.arg[P.coreOff[p] + (i64)P.Rmax * (ind0[p] - 1)];
+            for (int p = P.own[v]; p <= P.own[v + 1] - 1; ++p) x = x * s_dot[p] / fibs[(size_t)(p - 1) * P.nmax + (ind0[p] - 1)];
             if (v == NP - 1) x = x * s_dot[d];
         }
         if (v < 64) s_part[v] = x;
