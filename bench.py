@@ -231,7 +231,11 @@ def main():
     # (ttc_set_par / ttc_set_quad -> uploaded by the next ttc_dmrgg), runs the cross, copies every core back and reads the
     # integral.  `cold_ms_per_step` is the same with ttc_create / ttc_destroy inside the timed region as well.
     e2e_t, cold_t = [], []
-    host_out = np.empty(sum(int(g.ranks[k]) * int(prob.n[k]) * int(g.ranks[k + 1]) for k in range(prob.d)))   # caller-owned, like arg%u(k)%p
+    # caller-owned result buffer, like arg%u(k)%p -- sized for maxrank and BOUND to the handle (ttc_bind_cores): the reference
+    # returns the cores inside the dtt_dmrgg call (`arg` is inout, lib/dmrgg.f90:11-26), so every ttc_dmrgg below ends with
+    # the device -> host transfer of the cores into this buffer
+    host_out = np.empty(t.cores_capacity(R))
+    t.bind_cores(host_out)
     h2d = prob.par.nbytes + prob.quad.nbytes + prob.n.nbytes
     d2h = 0
     for it in range(args.steps + 1):
@@ -247,6 +251,7 @@ def main():
         d2h = sum(c.nbytes for c in cores) + 8 + ge.pivlog.nbytes
         if it > 0:
             e2e_t.append(dt)
+    t.bind_cores(None)
     if world == 1:
         for it in range(3):
             t0 = time.perf_counter()
@@ -362,7 +367,7 @@ def main():
                     "sweeps": int(g.nsweeps), "final_ranks": [int(x) for x in g.ranks], "integral": float(g.vals[-1])},
         "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_mean, "cold_ms_per_step": (1e3 * float(np.mean(cold_t)) if cold_t else None),
-                "handle": "reused across steps (ttc_set_par + ttc_set_quad ship the inputs every step)"},
+                "handle": "reused across steps (ttc_set_par + ttc_set_quad ship the inputs every step; the cores land in a caller-owned host buffer bound with ttc_bind_cores, transferred inside every ttc_dmrgg)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

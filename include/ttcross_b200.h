@@ -97,6 +97,15 @@ int ttc_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting);
 int ttc_ranks(const ttc_handle* h, int* r);            /* r(0:d) -> arg%r */
 int ttc_core(ttc_handle* h, int k, double* out);       /* arg%u(k)%p : r(k-1)*n(k)*r(k) doubles, column-major, k = 1..d */
 int ttc_cores(ttc_handle* h, double* out, long long cap); /* all cores, concatenated in core order (cap = doubles available) */
+/* The reference returns the cores INSIDE the call: `arg` is an inout argument of dtt_dmrgg and holds the train on return
+ * (lib/dmrgg.f90:11-26, cores reallocated at :676-685).  ttc_bind_cores gives ttc_dmrgg the same shape: `out` (caller-owned,
+ * `cap` doubles, must stay valid until rebound or the handle is destroyed) is filled by every later ttc_dmrgg with this
+ * process's cores, concatenated as ttc_cores does, before ttc_dmrgg returns.  The library page-locks the buffer once
+ * (cudaHostRegister) so the device writes into it directly, and the transfer runs beside the host's log processing; a later
+ * ttc_cores(h, out, ...) with the same pointer returns at once.  A run whose cores exceed `cap` returns TTC_ERR_ARG (the
+ * results stay available through ttc_core / ttc_cores); cap = sum of maxrank * n(k) * maxrank always suffices.
+ * out == NULL removes the binding. */
+int ttc_bind_cores(ttc_handle* h, double* out, long long cap);
 long long ttc_neval(const ttc_handle* h);              /* neval= */
 int ttc_nsweeps(const ttc_handle* h);
 double ttc_seconds(const ttc_handle* h);               /* wall time of the last ttc_dmrgg call (timef difference) */

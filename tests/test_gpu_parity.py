@@ -231,3 +231,36 @@ def test_ragged_mode_sizes_nodes_only_integrands(family, P, piv):
     p = T.drivers.Problem(base.kind, d, n, base.par, base.aux, quad, base.accuracy, 0.0, f"ragged {family}")
     t, g, o = run_both(p, 6, piv, P=P, exp_mode=1, use_tru=False)
     assert_parity(t, g, o, exact=True)
+
+
+@pytest.mark.parametrize("kind,index,n,R,piv,P", [("c", 6, 64, 16, 1, 4), ("d", 6, 16, 8, 2, 1), ("c", 10, 32, 10, 2, 8)])
+def test_bound_cores_arrive_inside_dmrgg(kind, index, n, R, piv, P):
+    """ttc_bind_cores: the reference returns the train inside the call (`arg` inout, lib/dmrgg.f90:11-26).  The bound buffer
+    must hold, on return of dmrgg, exactly what ttc_cores delivers -- bit for bit, run after run, also after the handle has
+    run an unbound cross in between; a buffer that is too small is refused with the results still available."""
+    p = T.drivers.ising(kind, index, n)
+    t = p.make()
+    t.set_partition(P)
+    g0 = t.dmrgg(R, p.accuracy, piv)
+    ref = np.concatenate([c.ravel(order="F") for c in t.cores()])
+    buf = np.full(t.cores_capacity(R), np.nan)
+    t.bind_cores(buf)
+    for _ in range(2):
+        buf[:] = np.nan
+        g = t.dmrgg(R, p.accuracy, piv)
+        assert np.array_equal(g.ranks, g0.ranks)
+        assert np.array_equal(buf[:ref.size], ref)                  # delivered by dmrgg itself
+        assert np.all(np.isnan(buf[ref.size:]))                     # and nothing written past the cores
+        views = t.cores(out=buf)                                    # same pointer: views only
+        assert np.array_equal(np.concatenate([c.ravel(order="F") for c in views]), ref)
+    other = np.empty(ref.size)
+    assert np.array_equal(np.concatenate([c.ravel(order="F") for c in t.cores(out=other)]), ref)   # unbound buffer: the usual copy
+    small = np.zeros(max(1, ref.size // 2))
+    t.bind_cores(small)
+    with pytest.raises(T.TTCrossError):
+        t.dmrgg(R, p.accuracy, piv)
+    assert np.array_equal(np.concatenate([c.ravel(order="F") for c in t.cores()]), ref)
+    t.bind_cores(None)
+    t.dmrgg(R, p.accuracy, piv)
+    assert np.array_equal(np.concatenate([c.ravel(order="F") for c in t.cores()]), ref)
+    t.close()

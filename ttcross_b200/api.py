@@ -61,6 +61,7 @@ def load_library(build_if_missing: bool = True):
     L.ttc_ranks.argtypes = [vp, _ip]
     L.ttc_core.argtypes = [vp, C.c_int, _dp]
     L.ttc_cores.argtypes = [vp, _dp, C.c_longlong]
+    L.ttc_bind_cores.argtypes = [vp, C.c_void_p, C.c_longlong]
     L.ttc_neval.restype = C.c_longlong
     L.ttc_neval.argtypes = [vp]
     L.ttc_nsweeps.argtypes = [vp]
@@ -224,6 +225,7 @@ class TTCross:
         if getattr(self, "h", None):
             self._L.ttc_destroy(self.h)
             self.h = None
+            self._bound = None
 
     def __del__(self):
         try:
@@ -364,6 +366,22 @@ class TTCross:
             out.append(buf[off:off + sz].reshape((int(self.ranks[k - 1]), int(self.n[k - 1]), int(self.ranks[k])), order="F"))
             off += sz
         return out
+
+    def bind_cores(self, out):
+        """Bind a caller-owned flat float64 buffer that every later dmrgg() fills with this rank's cores before it returns --
+        the reference's `arg` is an inout argument of dtt_dmrgg (lib/dmrgg.f90:11-26).  `cores(out=<the same array>)` then
+        only builds the views.  `out=None` removes the binding.  The array is kept alive by the handle."""
+        if out is None:
+            self._check(self._L.ttc_bind_cores(self.h, None, 0))
+            self._bound = None
+            return
+        assert out.dtype == np.float64 and out.ndim == 1 and out.flags.c_contiguous
+        self._check(self._L.ttc_bind_cores(self.h, out.ctypes.data, out.size))
+        self._bound = out
+
+    def cores_capacity(self, maxrank: int) -> int:
+        """Doubles that always hold the cores of a run with the given maxrank (for bind_cores)."""
+        return sum((1 if k == 1 else maxrank) * int(self.n[k - 1]) * (1 if k == self.d else maxrank) for k in range(1, self.d + 1))
 
     def quad_complex(self, weights) -> np.ndarray:
         """ztt_quad (lib/dmrgg.f90:1418-1523) for several complex rank-1 weight tensors at once.

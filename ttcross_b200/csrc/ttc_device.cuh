@@ -1561,6 +1561,22 @@ __global__ void k_pack_core(DevPlan P, int p, double* out) {
         out[e] = a[i + (i64)P.Rmax * jk];
     }
 }
+// padded -> packed copy of EVERY core c_lo..c_hi this process owns, concatenated in core order (the layout of ttc_cores), with the
+// offsets taken from the device-side ranks: enqueued right behind the finalisation, before the host knows the ranks
+// (ttc_bind_cores).  grid (x, number of own cores).
+__global__ void k_pack_all(DevPlan P, double* out) {
+    const int p = P.c_lo + blockIdx.y;
+    i64 off = 0;
+    for (int k = P.c_lo; k < p; ++k) off += (i64)P.rk[k - 1] * P.n[k] * P.rk[k];
+    const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
+    const double* a = P.arg + P.coreOff[p];
+    const i64 tot = (i64)r0 * n * r1;
+    double* o = out + off;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (i64)gridDim.x * blockDim.x) {
+        int i = (int)(e % r0); i64 jk = e / r0;
+        o[e] = a[i + (i64)P.Rmax * jk];
+    }
+}
 
 // ----------------------------------------------------------------------------
 // initial cross (dmrgg.f90:150-232)

@@ -131,6 +131,8 @@ struct ttc_handle {
     bool quad_cached = false; double quad_value = 0;   // dtt_quad of the finalised train, taken at the end of ttc_dmrgg (one process)
     int* lot_h = nullptr; VisitOut* out_h = nullptr; SweepOut* sweep_h = nullptr;   // pinned
     double* pack_d = nullptr; size_t pack_cap = 0;
+    // ttc_bind_cores: a caller-owned host buffer every ttc_dmrgg fills with this process's cores before it returns
+    double* bind_out = nullptr; long long bind_cap = 0; bool bind_pinned = false, bind_filled = false; size_t bind_count = 0;
     void* flush_d = nullptr; size_t flush_cap = 0;
     double* initb = nullptr;
     int* ready_h = nullptr;              // pinned mirror of Ctrl::ready
@@ -406,7 +408,7 @@ static int QINC_THREADS = std::getenv("TTC_QINC_THREADS") ? std::atoi(std::geten
 int threads_for(const ttc_handle* h) { return h->kind == TTC_MVN ? 64 : 256; }
 size_t aux_smem(const ttc_handle* h) { return (size_t)h->plan.auxsm * sizeof(double); }
 
-int ensure_pack(ttc_handle* h, size_t cnt) {
+int ensure_pack(ttc_handle* h, size_t cnt, bool stage = true) {
     std::lock_guard<std::mutex> lk(g_pool_mu);
     if (cnt > h->pack_cap) {
         const int adev = h->alloc_device >= 0 ? h->alloc_device : h->device;
@@ -416,7 +418,7 @@ int ensure_pack(ttc_handle* h, size_t cnt) {
         CUDA_TRY(h, g_pool.get_dev(adev, cnt * sizeof(double), &q));
         h->pack_d = (double*)q; h->pack_cap = cnt;
     }
-    if (cnt > h->stage_cap) {
+    if (stage && cnt > h->stage_cap) {
         void* q = nullptr;
         CUDA_TRY(h, g_pool.get_host(cnt * sizeof(double), &q));
         h->host_blocks.push_back({q, cnt * sizeof(double)});
@@ -1466,6 +1468,17 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         if (stq) return stq;
         CUDA_TRY(h, cudaMemcpyAsync(h->sweep_h, h->plan.sweep_out, sizeof(SweepOut), cudaMemcpyDeviceToHost, s));
     }
+    // ttc_bind_cores: the packed copy of this process's cores is formed on the device right here, with offsets from the device-side
+    // ranks; its transfer into the caller's buffer starts as soon as the logs (which carry the ranks) have arrived, and runs
+    // beside the host's log processing below
+    h->bind_filled = false;
+    const bool bound = h->bind_out != nullptr;
+    if (bound) {
+        size_t capcnt = 0;
+        for (int k = D.c_lo; k <= D.c_hi; ++k) capcnt += (size_t)std::min<i64>(Rmax, k == 1 ? 1 : Rmax) * h->n[k] * std::min<i64>(Rmax, k == d ? 1 : Rmax);
+        { int st = ensure_pack(h, capcnt, !h->bind_pinned); if (st) return st; }
+        L(KC_FINAL, [&] { k_pack_all<<<dim3(std::min(256, cdiv((i64)Rmax * h->nmax * Rmax, 256)), ncore_own), 256, 0, s>>>(D, h->pack_d); });
+    }
     // the logs travel with the same synchronisation: ctrl | slog | rklog | vlog | rk into one pinned block (capacity-sized)
     const size_t lb_ctrl = 0, lb_slog = 256, lb_rklog = lb_slog + (((size_t)(Rmax + 1) * sizeof(SweepOut) + 63) & ~(size_t)63),
                  lb_vlog = lb_rklog + (((size_t)(Rmax + 1) * (d + 1) * sizeof(int) + 63) & ~(size_t)63),
@@ -1485,6 +1498,15 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     CUDA_TRY(h, cudaStreamSynchronize(s));
     CUDA_TRY(h, cudaGetLastError());
     if (h->nproc == 1) { h->quad_value = h->sweep_h->val; h->quad_cached = true; }
+    size_t bind_tot = 0;
+    bool bind_small = false;
+    if (bound) {
+        const int* rkd = (const int*)(h->log_h + lb_rk);
+        for (int k = D.c_lo; k <= D.c_hi; ++k) bind_tot += (size_t)rkd[k - 1] * h->n[k] * rkd[k];
+        bind_small = (long long)bind_tot > h->bind_cap;
+        if (!bind_small && bind_tot > 0)
+            CUDA_TRY(h, cudaMemcpyAsync(h->bind_pinned ? h->bind_out : h->stage_h, h->pack_d, bind_tot * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
 
     tr.lap("sweeps+finalise");
     // ---- read the logs back and rebuild the reference's report
@@ -1554,12 +1576,19 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     h->sweep_ms = 0;
     if (persistent) { float sm = 0; cudaEventElapsedTime(&sm, h->evs0, h->evs1); h->sweep_ms = sm; }
     h->neval = nevalall;
+    if (bound && !bind_small) {
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        if (!h->bind_pinned) std::memcpy(h->bind_out, h->stage_h, bind_tot * sizeof(double));
+        h->bind_filled = true; h->bind_count = bind_tot;
+        tr.lap("bound cores");
+    }
     h->seconds = timef();
     h->ran = true;
     if (h->verbose && multi) {            // several processes run asynchronously: the sweep lines are printed once the run is over
         std::fputs(h->text.c_str(), stdout);
         std::fflush(stdout);
     }
+    if (bind_small) { h->err = "ttc_bind_cores: the bound buffer is too small for the cores of this run (ttc_cores still returns them)"; return TTC_ERR_ARG; }
     return TTC_OK;
 }
 
@@ -1612,6 +1641,7 @@ int ttc_create(ttc_handle** out, int kind, int d, const int* n, const double* pa
 
 void ttc_destroy(ttc_handle* h) {
     if (!h) return;
+    if (h->bind_out && h->bind_pinned) { cudaHostUnregister(h->bind_out); cudaGetLastError(); }
     if (h->stream || !h->allocs.empty()) free_device(h);      // (switches to the device the blocks were allocated on)
     if (h->win) { cudaSetDevice(h->device); window_teardown(h); }
     if (h->comm) { cudaSetDevice(h->device); nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
@@ -1727,6 +1757,7 @@ int ttc_cores(ttc_handle* h, double* out, long long cap) {
     size_t tot = 0;
     for (int k = klo; k <= khi; ++k) tot += (size_t)h->rk_h[k - 1] * h->n[k] * h->rk_h[k];
     if ((long long)tot > cap) { h->err = "ttc_cores: output buffer too small"; return TTC_ERR_ARG; }
+    if (h->bind_filled && out == h->bind_out && tot == h->bind_count) return TTC_OK;     // ttc_dmrgg already delivered them (ttc_bind_cores)
     { int st = ensure_pack(h, tot); if (st) return st; }
     size_t off = 0;
     for (int k = klo; k <= khi; ++k) {
@@ -1759,6 +1790,20 @@ int ttc_cores(ttc_handle* h, double* out, long long cap) {
     }
     for (int q = 0; q < nsl; ++q) cudaEventDestroy(evs[q]);
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return TTC_OK;
+}
+int ttc_bind_cores(ttc_handle* h, double* out, long long cap) {
+    if (!h || (out && cap <= 0)) return TTC_ERR_ARG;
+    if (h->bind_out && h->bind_pinned) { cudaHostUnregister(h->bind_out); cudaGetLastError(); }
+    h->bind_out = nullptr; h->bind_cap = 0; h->bind_pinned = false; h->bind_filled = false; h->bind_count = 0;
+    if (!out) return TTC_OK;
+    { int st = check_device(h); if (st) return st; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    // page-lock the caller's pages so the device writes into them directly; a buffer that cannot be registered (already
+    // registered by the caller, exotic mapping) goes through the pinned staging block and one host copy instead
+    if (cudaHostRegister(out, (size_t)cap * sizeof(double), cudaHostRegisterPortable) == cudaSuccess) h->bind_pinned = true;
+    else cudaGetLastError();
+    h->bind_out = out; h->bind_cap = cap;
     return TTC_OK;
 }
 long long ttc_neval(const ttc_handle* h) { return h ? h->neval : 0; }
@@ -1875,17 +1920,19 @@ int qr_geometry(int nsm, int m, int n, int& G, int& rpb, size_t& smem) {
     smem = ((size_t)rpb * n + n) * sizeof(double);
     return smem <= 200 * 1024 ? 0 : TTC_ERR_ARG;
 }
-// TSQR (ttc_qr.cuh): level-1 blocks of ~4n rows, a tree of stacked R factors with fan-in 4, the chain of Q slices applied to the
-// first-level blocks, LAPACK's signs by Householder reconstruction.  Applies to m >= 8n, n <= 64; TTC_NO_TSQR=1 keeps k_qr_panel.
+// TSQR (ttc_qr.cuh): level-1 blocks of ~256 rows, a tree of stacked R factors with fan-in 256/n, the chain of Q slices applied to
+// the first-level blocks, LAPACK's signs by Householder reconstruction.  Applies to m >= 8n, n <= 64; TTC_NO_TSQR=1 keeps k_qr_panel.
 static bool tsqr_applicable(int m, int n) { return n >= 1 && n <= 64 && m >= 8 * n && !std::getenv("TTC_NO_TSQR"); }
 cudaError_t tsqr_launch(cudaStream_t s, const double* da, int m, int n, double* dq, double* dr, QrScratch& sc) {
-    const int G1 = (m + 4 * n - 1) / (4 * n);
+    // blocks of <= 256 rows (8 per lane, ttc_qr.cuh): first-level blocks of ~256 rows, upper nodes stack F = 256 / n (>= 4) R factors
+    const int F = std::max(4, 256 / n);
+    const int G1 = (m + 255) / 256;
     std::vector<int> G = {G1};
-    while (G.back() > 1) G.push_back((G.back() + 3) / 4);
+    while (G.back() > 1) G.push_back((G.back() + F - 1) / F);
     const int L = (int)G.size();                                  // levels 1 .. L (level L has one node)
     if (L > 8) return cudaErrorInvalidValue;
     size_t need = (size_t)n + 8;
-    for (int l = 0; l < L; ++l) need += (size_t)G[l] * n * n + (l >= 1 ? (size_t)G[l] * 4 * n * n : 0);
+    for (int l = 0; l < L; ++l) need += (size_t)G[l] * n * n + (l >= 1 ? (size_t)G[l] * F * n * n : 0);
     if (need > sc.cap_t) {
         if (sc.tsqr) cudaFree(sc.tsqr);
         sc.tsqr = nullptr; sc.cap_t = 0;
@@ -1896,18 +1943,18 @@ cudaError_t tsqr_launch(cudaStream_t s, const double* da, int m, int n, double* 
     std::vector<double*> Rl(L), Ql(L, nullptr);
     double* p = sc.tsqr;
     double* sgn = p; p += n + 8;
-    for (int l = 0; l < L; ++l) { Rl[l] = p; p += (size_t)G[l] * n * n; if (l >= 1) { Ql[l] = p; p += (size_t)G[l] * 4 * n * n; } }
-    const int rows1 = (m + G1 - 1) / G1 + 1;
-    const size_t sm_f = ((size_t)std::max(rows1, 4 * n) * n + n + 40) * sizeof(double);
+    for (int l = 0; l < L; ++l) { Rl[l] = p; p += (size_t)G[l] * n * n; if (l >= 1) { Ql[l] = p; p += (size_t)G[l] * F * n * n; } }
+    const int rows1 = (m + G1 - 1) / G1;                          // <= 256
+    const size_t sm_f = ((size_t)n * 256 + 2 * n) * sizeof(double);                 // V (n reflectors, ld <= 256) | tau | one mbarrier per reflector
     const size_t sm_a = ((size_t)2 * n * n + (size_t)rows1 * n) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(k_tsqr_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tsqr_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a);
     if (e != cudaSuccess) return e;
-    k_tsqr_factor<<<G1, TSQR_THREADS, sm_f, s>>>(da, 1, m, n, m, G1, 0, Rl[0], dq, m);
-    for (int l = 1; l < L; ++l) k_tsqr_factor<<<G[l], TSQR_THREADS, sm_f, s>>>(Rl[l - 1], l + 1, m, n, m, G1, G[l - 1], Rl[l], Ql[l], m);
+    k_tsqr_factor<<<G1, TQ_THREADS, sm_f, s>>>(da, 1, m, n, m, G1, 0, F, Rl[0], dq, m);
+    for (int l = 1; l < L; ++l) k_tsqr_factor<<<G[l], TQ_THREADS, sm_f, s>>>(Rl[l - 1], l + 1, m, n, m, G1, G[l - 1], F, Rl[l], Ql[l], m);
     TsqrLevels LV; LV.count = L - 1;
     for (int l = 1; l < L; ++l) LV.q[l - 1] = Ql[l];
-    if (L > 1) k_tsqr_apply<<<G1, TSQR_THREADS, sm_a, s>>>(dq, m, n, m, G1, LV);
+    if (L > 1) k_tsqr_apply<<<G1, TSQR_THREADS, sm_a, s>>>(dq, m, n, m, G1, F, LV);
     e = cudaMemcpyAsync(dr, Rl[L - 1], (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice, s);
     if (e != cudaSuccess) return e;
     k_tsqr_sign<<<1, TSQR_THREADS, ((size_t)n * n + n) * sizeof(double), s>>>(dq, n, m, dr, sgn);
@@ -1938,7 +1985,7 @@ cudaError_t qr_launch(cudaStream_t s, int nsm, const double* da, int m, int n, d
 // r(k) <= r(k-1) n(k), the only case handled).  Single process only.
 int ttc_ort(ttc_handle* h) {
     if (!h) return TTC_ERR_ARG;
-    h->quad_cached = false;
+    h->quad_cached = false; h->bind_filled = false;
     if (!h->ran) { h->err = "ttc_ort before ttc_dmrgg"; return TTC_ERR_STATE; }
     if (h->nproc > 1) { h->err = "ttc_ort: not collective yet (run it on a single-process handle)"; return TTC_ERR_STATE; }
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -2010,7 +2057,7 @@ static int chop_ref(const std::vector<double>& sv, bool has_tol, double tol, boo
 // ttc_ranks / ttc_core / ttc_quad see the rounded train.  Single process only; needs r <= 64.
 int ttc_svd(ttc_handle* h, double tol, int rmax) {
     if (!h) return TTC_ERR_ARG;
-    h->quad_cached = false;
+    h->quad_cached = false; h->bind_filled = false;
     if (!h->ran) { h->err = "ttc_svd before ttc_dmrgg"; return TTC_ERR_STATE; }
     if (h->nproc > 1) { h->err = "ttc_svd: not collective yet (run it on a single-process handle)"; return TTC_ERR_STATE; }
     for (int k = 0; k <= h->d; ++k) if (h->rk_h[k] > 64) { h->err = "ttc_svd: ranks above 64 are not supported"; return TTC_ERR_ARG; }

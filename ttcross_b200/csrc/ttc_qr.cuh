@@ -166,113 +166,190 @@ __global__ void __launch_bounds__(QR_THREADS) k_qr_panel(const double* __restric
 // then R_H = S R and Q_H = Q S are the Householder (LAPACK) factors.  k_tsqr_sign does that in one CTA, k_tsqr_scale applies
 // S to the columns of Q.  Checked against numpy.linalg.qr (tests/test_qr.py, unchanged).
 // =============================================================================
-constexpr int TSQR_THREADS = 1024;     // 32 warps: with two trailing columns per warp a reflector is applied in one round for n <= 64
+constexpr int TSQR_THREADS = 1024;     // k_tsqr_apply / k_tsqr_sign
+// ---- block factorisation: columns in REGISTERS, reflectors published through shared memory, no block barrier per column.
+// A CTA of 16 warps factors a block of rows <= 256, n <= 64.  Warp w owns columns w, w+16, w+32, w+48; a lane holds rows
+// lane, lane+32, ... of each (8 per column).  The algorithm is left-looking per warp: reflector k is generated by the owner of
+// column k as soon as H(0..k-1) have been applied to THAT column, written to V (shared memory) and announced through a
+// counter; every other warp applies H(k) to its columns when it sees the counter pass k.  The critical path of a step is one
+// warp's apply (dot, 5 shuffles, update) + generate (sum of squares, 5 shuffles, sqrt, two divisions) + the flag, ~0.45 us,
+// instead of three 1024-thread barriers around shared-memory passes (1.35 us); the other warps' updates run beside it.
+// dorg2r needs no synchronisation at all: column j of Q is H(0) ... H(j) e_j, a chain private to the warp that owns column j.
+constexpr int TQ_THREADS = 512, TQ_WARPS = 16, TQ_NC = 4, TQ_RPL = 8;
+constexpr unsigned TQ_FULL = 0xffffffffu;
+// One mbarrier per reflector (arrival count 1): the owner arrives (release) once the reflector is in shared memory, the
+// consumers wait on phase 0 with mbarrier.try_wait (acquire), which parks the warp in hardware instead of polling shared memory
+// -- 15 warps spinning on a flag word saturate the shared-memory pipe the critical warp's shuffles go through (measured: a
+// polled counter made the kernel 10x slower than the barrier-per-column version it replaced).
+__device__ __forceinline__ unsigned tq_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tq_mbar_init(unsigned long long* bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tq_smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void tq_mbar_arrive(unsigned long long* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tq_smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void tq_mbar_wait(unsigned long long* bar) {
+    unsigned ok = 0;
+    for (int spins = 0; !ok && spins < (1 << 20); ++spins)          // (bounded: a lost reflector must not hang the GPU)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(tq_smem_u32(bar)) : "memory");
+}
 
-// H(k) = I - tau v v^T (v(k) = 1, v(i) = S(i,k) below) applied to the trailing columns, TWO columns per warp at a time (they
-// share the loads of v); dot product and update of a column stay inside its warp
-__device__ __forceinline__ void cta_apply_reflector(double* S, int rows, int n, int k, double tk, double* next_ss = nullptr) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int j0 = k + 1 + wid; j0 < n; j0 += 2 * nw) {
-        const int j1 = j0 + nw;
-        const bool two = j1 < n;
-        const double* v = S + (size_t)rows * k;
-        double* c0 = S + (size_t)rows * j0; double* c1 = S + (size_t)rows * (two ? j1 : j0);
-        double w0 = 0.0, w1 = 0.0;
-        for (int i = k + 1 + lane; i < rows; i += 32) { const double vi = v[i]; w0 += vi * c0[i]; w1 += vi * c1[i]; }
-        for (int o = 16; o > 0; o >>= 1) { w0 += __shfl_xor_sync(0xffffffffu, w0, o); w1 += __shfl_xor_sync(0xffffffffu, w1, o); }
-        w0 += c0[k]; w1 += c1[k];
-        const double t0 = tk * w0, t1 = tk * w1;
-        double ss = 0.0;                                   // (warp 0's first column is column k+1: its norm below row k+1 feeds the next reflector)
-        for (int i = k + 1 + lane; i < rows; i += 32) {
-            const double vi = v[i];
-            const double x = c0[i] - t0 * vi;
-            c0[i] = x;
-            if (i > k + 1) ss += x * x;
-            if (two) c1[i] -= t1 * vi;
+// H(k) = I - tau v v^T applied to the columns in `mask` (bit q = column slot q; warp-uniform).  vk: reflector k in shared memory,
+// valid for rows >= k (vk[k] = 1, zeros in the padding).
+// nt = 32-row slices the block spans (rows beyond it are never touched: c stays 0 there and V has no storage for them).
+__device__ __forceinline__ void tq_apply(double (&c)[TQ_NC][TQ_RPL], unsigned mask, const double* vk, int k, double tau, int lane, int nt) {
+    const int t0 = k >> 5;
+    double v[TQ_RPL];
+#pragma unroll
+    for (int t = 0; t < TQ_RPL; ++t) { const int i = lane + 32 * t; v[t] = (t < nt && i >= k) ? vk[i] : 0.0; }
+    double w[TQ_NC];
+#pragma unroll
+    for (int q = 0; q < TQ_NC; ++q) {
+        w[q] = 0.0;
+        if ((mask >> q) & 1u) {
+            double wa = 0.0, wb = 0.0;
+#pragma unroll
+            for (int t = 0; t < TQ_RPL; t += 2) {
+                if (t >= t0) wa += v[t] * c[q][t];
+                if (t + 1 >= t0) wb += v[t + 1] * c[q][t + 1];
+            }
+            w[q] = wa + wb;
         }
-        if (lane == 0) { c0[k] -= t0; if (two) c1[k] -= t1; }
-        if (next_ss && j0 == k + 1) {
-            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-            if (lane == 0) *next_ss = ss;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < TQ_NC; ++q) if ((mask >> q) & 1u) w[q] += __shfl_xor_sync(TQ_FULL, w[q], o);
+    }
+#pragma unroll
+    for (int q = 0; q < TQ_NC; ++q) {
+        if ((mask >> q) & 1u) {
+            const double tw = tau * w[q];
+#pragma unroll
+            for (int t = 0; t < TQ_RPL; ++t) if (t >= t0) c[q][t] -= tw * v[t];
         }
     }
 }
-// Householder QR of the rows x n block S (column-major, leading dimension rows, rows >= n) held in shared memory, by one CTA.
-// On return the upper triangle holds R, the columns below the diagonal the reflector vectors (v(k) = 1 implicit), tau[k] the
-// scalars.  One warp per trailing column: dot product and update of a column stay inside its warp, so a reflector costs two
-// block barriers.  sh: scratch >= 34 doubles.
-__device__ __forceinline__ void cta_house_qr(double* S, int rows, int n, double* tau, double* sh) {
-    for (int k = 0; k < n; ++k) {
-        double ss;
-        if (k == 0) {
-            ss = 0.0;
-            for (int i = 1 + threadIdx.x; i < rows; i += blockDim.x) { const double x = S[i]; ss += x * x; }
-            ss = qr_block_sum(ss, sh);
-        } else ss = sh[33];                               // left by the warp that updated column k in the previous step
-        const double alpha = S[k + rows * k];
-        double beta = alpha, scale = 0.0, tk = 0.0;
-        if (ss != 0.0) {
-            beta = -copysign(sqrt(alpha * alpha + ss), alpha);
-            tk = (beta - alpha) / beta;
-            scale = 1.0 / (alpha - beta);
-        }
-        __syncthreads();                                  // everybody has read alpha
-        for (int i = k + 1 + threadIdx.x; i < rows; i += blockDim.x) S[i + rows * k] *= scale;
-        if (threadIdx.x == 0) { S[k + rows * k] = beta; tau[k] = tk; }
-        __syncthreads();
-        cta_apply_reflector(S, rows, n, k, tk, sh + 33);
-        __syncthreads();
+// dlarfg on column slot q (= global column k, every earlier reflector applied): beta on the diagonal, v below it (also left in
+// the registers), published as reflector k
+__device__ __forceinline__ void tq_generate(double (&cq)[TQ_RPL], int k, double* vk, double* tau_s, unsigned long long* bars, int lane, int nt) {
+    double ss = 0.0, al = 0.0;
+#pragma unroll
+    for (int t = 0; t < TQ_RPL; ++t) {
+        const int i = lane + 32 * t;
+        const double x = cq[t];
+        if (i > k) ss += x * x;
+        if (i == k) al = x;
     }
-}
-// dorg2r in place: the reflectors left by cta_house_qr become the explicit rows x n factor Q
-__device__ __forceinline__ void cta_house_formq(double* S, int rows, int n, const double* tau) {
-    for (int k = n - 1; k >= 0; --k) {
-        const double tk = tau[k];
-        cta_apply_reflector(S, rows, n, k, tk);
-        __syncthreads();
-        for (int i = threadIdx.x; i < rows; i += blockDim.x) {
-            double x = S[i + rows * k];
-            if (i > k) x = -tk * x; else if (i == k) x = 1.0 - tk; else x = 0.0;
-            S[i + rows * k] = x;
-        }
-        __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(TQ_FULL, ss, o);
+    const double alpha = __shfl_sync(TQ_FULL, al, k & 31);
+    double beta = alpha, scale = 0.0, tk = 0.0;
+    if (ss != 0.0) {
+        beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+        tk = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
     }
+#pragma unroll
+    for (int t = 0; t < TQ_RPL; ++t) {
+        const int i = lane + 32 * t;
+        if (t < nt) {
+            if (i > k) { const double x = cq[t] * scale; cq[t] = x; vk[i] = x; }
+            else if (i == k) { cq[t] = beta; vk[i] = 1.0; }
+        }
+    }
+    if (lane == 0) tau_s[k] = tk;
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) tq_mbar_arrive(bars + k);
 }
 // One level of the tree.  Node b factors `cnt` stacked source blocks:
 //   level 1 : src = A (m x n, lda), block b = rows [b*m/G, (b+1)*m/G);                     Q block -> qout (ldq = m) at those rows
-//   level>1 : src = the previous level's R factors (n x n each, contiguous), node b stacks R[4b .. 4b+3];  Q block (cnt*n x n) -> qout + b*4n*n
-// rout + b*n*n receives the node's R (upper triangular, zeros below).  dynamic smem: (maxrows*n + n + 40) doubles.
-__global__ void __launch_bounds__(TSQR_THREADS) k_tsqr_factor(const double* __restrict__ src, int level, int m, int n, int lda, int G, int nsrc,
-                                                             double* __restrict__ rout, double* __restrict__ qout, int ldq) {
+//   level>1 : src = the previous level's R factors (n x n each, contiguous), node b stacks R[F b .. F b + F-1];  Q block (cnt*n x n) -> qout + b*F n*n (ld F n)
+// rout + b*n*n receives the node's R (upper triangular, zeros below).  dynamic smem: (n * ldv + 2 n) doubles, ldv = rows rounded up to 32.
+__global__ void __launch_bounds__(TQ_THREADS, 1) k_tsqr_factor(const double* __restrict__ src, int level, int m, int n, int lda, int G, int nsrc, int F,
+                                                              double* __restrict__ rout, double* __restrict__ qout, int ldq) {
     extern __shared__ double smem[];
-    const int b = blockIdx.x;
+    const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int rows, row0 = 0;
     if (level == 1) { row0 = (int)((long long)b * m / G); rows = (int)((long long)(b + 1) * m / G) - row0; }
-    else { const int c0 = 4 * b; rows = min(4, nsrc - c0) * n; }
-    double* S = smem; double* tau = S + (size_t)rows * n; double* sh = tau + n;
-    if (level == 1) {
-        for (int e = threadIdx.x; e < rows * n; e += blockDim.x) { const int j = e / rows, i = e - j * rows; S[e] = src[(size_t)(row0 + i) + (size_t)lda * j]; }
-    } else {
-        for (int e = threadIdx.x; e < rows * n; e += blockDim.x) {
-            const int j = e / rows, i = e - j * rows, blk = i / n, ii = i - blk * n;
-            S[e] = src[((size_t)(4 * b + blk) * n + j) * n + ii];
+    else { const int c0 = F * b; rows = min(F, nsrc - c0) * n; }
+    const int ldv = (rows + 31) & ~31, nt = ldv >> 5;
+    double* V = smem; double* tau_s = V + (size_t)n * ldv;
+    unsigned long long* bars = (unsigned long long*)(tau_s + n);
+    for (int k = threadIdx.x; k < n; k += blockDim.x) tq_mbar_init(bars + k);
+    double c[TQ_NC][TQ_RPL];
+#pragma unroll
+    for (int q = 0; q < TQ_NC; ++q) {
+        const int j = wid + TQ_WARPS * q;
+#pragma unroll
+        for (int t = 0; t < TQ_RPL; ++t) {
+            const int i = lane + 32 * t;
+            double x = 0.0;
+            if (j < n && i < rows) {
+                if (level == 1) x = src[(size_t)(row0 + i) + (size_t)lda * j];
+                else { const int blk = i / n, ii = i - blk * n; x = src[((size_t)(F * b + blk) * n + j) * n + ii]; }
+            }
+            c[q][t] = x;
         }
     }
     __syncthreads();
-    cta_house_qr(S, rows, n, tau, sh);
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) { const int j = e / n, i = e - j * n; rout[(size_t)b * n * n + e] = (i <= j) ? S[i + rows * j] : 0.0; }
+    // ---------------- dgeqr2
+    if (wid == 0) tq_generate(c[0], 0, V, tau_s, bars, lane, nt);
+    for (int k = 0; k + 1 < n; ++k) {
+        unsigned mask = 0;
+#pragma unroll
+        for (int q = 0; q < TQ_NC; ++q) { const int j = wid + TQ_WARPS * q; if (j > k && j < n) mask |= 1u << q; }
+        if (!mask) break;
+        tq_mbar_wait(bars + k);
+        const double tk = tau_s[k];
+        const double* vk = V + (size_t)k * ldv;
+        const int qn = (((k + 1) & (TQ_WARPS - 1)) == wid) ? ((k + 1) >> 4) : -1;      // column k+1 is mine: it goes first
+        if (qn >= 0) {
+            tq_apply(c, 1u << qn, vk, k, tk, lane, nt);
+#pragma unroll
+            for (int q = 0; q < TQ_NC; ++q) if (q == qn) tq_generate(c[q], k + 1, V + (size_t)(k + 1) * ldv, tau_s, bars, lane, nt);
+            mask &= ~(1u << qn);
+        }
+        if (mask) tq_apply(c, mask, vk, k, tk, lane, nt);
+    }
     __syncthreads();
-    cta_house_formq(S, rows, n, tau);
-    if (level == 1) {
-        for (int e = threadIdx.x; e < rows * n; e += blockDim.x) { const int j = e / rows, i = e - j * rows; qout[(size_t)(row0 + i) + (size_t)ldq * j] = S[e]; }
-    } else {
-        double* qb = qout + (size_t)b * 4 * n * n;                 // (4n x n, leading dimension 4n)
-        for (int e = threadIdx.x; e < rows * n; e += blockDim.x) { const int j = e / rows, i = e - j * rows; qb[i + (size_t)4 * n * j] = S[e]; }
+    // ---------------- R out (registers: rows <= j of column j), then dorg2r in place
+    int jmax = -1;
+#pragma unroll
+    for (int q = 0; q < TQ_NC; ++q) {
+        const int j = wid + TQ_WARPS * q;
+        if (j < n) {
+            jmax = j;
+            const double tj = tau_s[j];
+#pragma unroll
+            for (int t = 0; t < TQ_RPL; ++t) {
+                const int i = lane + 32 * t;
+                if (i < n) rout[(size_t)b * n * n + i + (size_t)n * j] = (i <= j) ? c[q][t] : 0.0;
+                c[q][t] = (i < j) ? 0.0 : ((i == j) ? 1.0 - tj : -tj * c[q][t]);
+            }
+        }
+    }
+    for (int k = jmax - 1; k >= 0; --k) {
+        unsigned mask = 0;
+#pragma unroll
+        for (int q = 0; q < TQ_NC; ++q) { const int j = wid + TQ_WARPS * q; if (j > k && j < n) mask |= 1u << q; }
+        tq_apply(c, mask, V + (size_t)k * ldv, k, tau_s[k], lane, nt);
+    }
+#pragma unroll
+    for (int q = 0; q < TQ_NC; ++q) {
+        const int j = wid + TQ_WARPS * q;
+        if (j < n) {
+#pragma unroll
+            for (int t = 0; t < TQ_RPL; ++t) {
+                const int i = lane + 32 * t;
+                if (i < rows) {
+                    if (level == 1) qout[(size_t)(row0 + i) + (size_t)ldq * j] = c[q][t];
+                    else qout[(size_t)b * F * n * n + i + (size_t)F * n * j] = c[q][t];
+                }
+            }
+        }
     }
 }
-// Q(block b) <- Q1(block b) * Q2[slice] * Q3[slice] * ... (levels 2..L); qlev[l] = that level's Q blocks (4n x n each, ld 4n).
+// Q(block b) <- Q1(block b) * Q2[slice] * Q3[slice] * ... (levels 2..L); qlev[l] = that level's Q blocks (F n x n each, ld F n).
 struct TsqrLevels { const double* q[8]; int count; };
-__global__ void __launch_bounds__(TSQR_THREADS) k_tsqr_apply(double* __restrict__ q, int m, int n, int ldq, int G, TsqrLevels LV) {
+__global__ void __launch_bounds__(TSQR_THREADS) k_tsqr_apply(double* __restrict__ q, int m, int n, int ldq, int G, int F, TsqrLevels LV) {
     extern __shared__ double smem[];
     const int b = blockIdx.x;
     const int row0 = (int)((long long)b * m / G), rows = (int)((long long)(b + 1) * m / G) - row0;
@@ -280,15 +357,15 @@ __global__ void __launch_bounds__(TSQR_THREADS) k_tsqr_apply(double* __restrict_
     for (int e = threadIdx.x; e < rows * n; e += blockDim.x) { const int j = e / rows, i = e - j * rows; QB[e] = q[(size_t)(row0 + i) + (size_t)ldq * j]; }
     int idx = b;
     for (int l = 0; l < LV.count; ++l) {
-        const int node = idx / 4, slot = idx - 4 * node;
-        const double* ql = LV.q[l] + (size_t)node * 4 * n * n + (size_t)slot * n;        // rows slot*n .. of the 4n x n block
+        const int node = idx / F, slot = idx - F * node;
+        const double* ql = LV.q[l] + (size_t)node * F * n * n + (size_t)slot * n;        // rows slot*n .. of the F n x n block
         if (l == 0) {
-            for (int e = threadIdx.x; e < n * n; e += blockDim.x) { const int j = e / n, i = e - j * n; M[e] = ql[i + (size_t)4 * n * j]; }
+            for (int e = threadIdx.x; e < n * n; e += blockDim.x) { const int j = e / n, i = e - j * n; M[e] = ql[i + (size_t)F * n * j]; }
         } else {
             for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
                 const int j = e / n, i = e - j * n;
                 double t = 0.0;
-                for (int x = 0; x < n; ++x) t += M[i + n * x] * ql[x + (size_t)4 * n * j];
+                for (int x = 0; x < n; ++x) t += M[i + n * x] * ql[x + (size_t)F * n * j];
                 T[e] = t;
             }
             __syncthreads();
