@@ -1947,11 +1947,22 @@ cudaError_t tsqr_launch(cudaStream_t s, const double* da, int m, int n, double* 
     const int rows1 = (m + G1 - 1) / G1;                          // <= 256
     const size_t sm_f = ((size_t)n * 256 + 2 * n) * sizeof(double);                 // V (n reflectors, ld <= 256) | tau | one mbarrier per reflector
     const size_t sm_a = ((size_t)2 * n * n + (size_t)rows1 * n) * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(k_tsqr_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tsqr_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a);
+    cudaError_t e = cudaFuncSetAttribute(k_tsqr_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a);
     if (e != cudaSuccess) return e;
-    k_tsqr_factor<<<G1, TQ_THREADS, sm_f, s>>>(da, 1, m, n, m, G1, 0, F, Rl[0], dq, m);
-    for (int l = 1; l < L; ++l) k_tsqr_factor<<<G[l], TQ_THREADS, sm_f, s>>>(Rl[l - 1], l + 1, m, n, m, G1, G[l - 1], F, Rl[l], Ql[l], m);
+    auto factor_levels = [&](auto kern) -> cudaError_t {          // kern = k_tsqr_factor<columns per warp>
+        cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
+        if (e2 != cudaSuccess) return e2;
+        kern<<<G1, TQ_THREADS, sm_f, s>>>(da, 1, m, n, m, G1, 0, F, Rl[0], dq, m);
+        for (int l = 1; l < L; ++l) kern<<<G[l], TQ_THREADS, sm_f, s>>>(Rl[l - 1], l + 1, m, n, m, G1, G[l - 1], F, Rl[l], Ql[l], m);
+        return cudaSuccess;
+    };
+    switch ((n + TQ_WARPS - 1) / TQ_WARPS) {
+        case 1: e = factor_levels(k_tsqr_factor<1>); break;
+        case 2: e = factor_levels(k_tsqr_factor<2>); break;
+        case 3: e = factor_levels(k_tsqr_factor<3>); break;
+        default: e = factor_levels(k_tsqr_factor<4>); break;
+    }
+    if (e != cudaSuccess) return e;
     TsqrLevels LV; LV.count = L - 1;
     for (int l = 1; l < L; ++l) LV.q[l - 1] = Ql[l];
     if (L > 1) k_tsqr_apply<<<G1, TSQR_THREADS, sm_a, s>>>(dq, m, n, m, G1, F, LV);

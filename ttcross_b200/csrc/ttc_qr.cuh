@@ -175,7 +175,7 @@ constexpr int TSQR_THREADS = 1024;     // k_tsqr_apply / k_tsqr_sign
 // warp's apply (dot, 5 shuffles, update) + generate (sum of squares, 5 shuffles, sqrt, two divisions) + the flag, ~0.45 us,
 // instead of three 1024-thread barriers around shared-memory passes (1.35 us); the other warps' updates run beside it.
 // dorg2r needs no synchronisation at all: column j of Q is H(0) ... H(j) e_j, a chain private to the warp that owns column j.
-constexpr int TQ_THREADS = 512, TQ_WARPS = 16, TQ_NC = 4, TQ_RPL = 8;
+constexpr int TQ_THREADS = 512, TQ_WARPS = 16, TQ_RPL = 8, TQ_LDV = 32 * TQ_RPL;
 constexpr unsigned TQ_FULL = 0xffffffffu;
 // One mbarrier per reflector (arrival count 1): the owner arrives (release) once the reflector is in shared memory, the
 // consumers wait on phase 0 with mbarrier.try_wait (acquire), which parks the warp in hardware instead of polling shared memory
@@ -190,45 +190,60 @@ __device__ __forceinline__ void tq_mbar_wait(unsigned long long* bar) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(tq_smem_u32(bar)) : "memory");
 }
 
-// H(k) = I - tau v v^T applied to the columns in `mask` (bit q = column slot q; warp-uniform).  vk: reflector k in shared memory,
-// valid for rows >= k (vk[k] = 1, zeros in the padding).
-// nt = 32-row slices the block spans (rows beyond it are never touched: c stays 0 there and V has no storage for them).
-__device__ __forceinline__ void tq_apply(double (&c)[TQ_NC][TQ_RPL], unsigned mask, const double* vk, int k, double tau, int lane, int nt) {
-    const int t0 = k >> 5;
+// H(k) = I - tau v v^T applied to column slots QA .. QB-1 of this warp (compile-time range: straight-line code, no predicates --
+// the first version of this kernel spent half of its issue slots on FSEL / ISETP / BSSY around per-slice conditions,
+// profiles/r02f_ncu_tsqr.txt).  vk: reflector k in shared memory, all TQ_LDV rows valid (zeros above row k and in the padding).
+template <int NC, int QA, int QB>
+__device__ __forceinline__ void tq_apply(double (&c)[NC][TQ_RPL], const double* vk, double tau, int lane) {
+    if constexpr (QA < QB) {
     double v[TQ_RPL];
 #pragma unroll
-    for (int t = 0; t < TQ_RPL; ++t) { const int i = lane + 32 * t; v[t] = (t < nt && i >= k) ? vk[i] : 0.0; }
-    double w[TQ_NC];
+    for (int t = 0; t < TQ_RPL; ++t) v[t] = vk[lane + 32 * t];
+    double w[NC];
 #pragma unroll
-    for (int q = 0; q < TQ_NC; ++q) {
-        w[q] = 0.0;
-        if ((mask >> q) & 1u) {
-            double wa = 0.0, wb = 0.0;
+    for (int q = QA; q < QB; ++q) {
+        double wa = v[0] * c[q][0], wb = v[1] * c[q][1];
 #pragma unroll
-            for (int t = 0; t < TQ_RPL; t += 2) {
-                if (t >= t0) wa += v[t] * c[q][t];
-                if (t + 1 >= t0) wb += v[t + 1] * c[q][t + 1];
-            }
-            w[q] = wa + wb;
-        }
+        for (int t = 2; t < TQ_RPL; t += 2) { wa += v[t] * c[q][t]; wb += v[t + 1] * c[q][t + 1]; }
+        w[q] = wa + wb;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-        for (int q = 0; q < TQ_NC; ++q) if ((mask >> q) & 1u) w[q] += __shfl_xor_sync(TQ_FULL, w[q], o);
+        for (int q = QA; q < QB; ++q) w[q] += __shfl_xor_sync(TQ_FULL, w[q], o);
     }
 #pragma unroll
-    for (int q = 0; q < TQ_NC; ++q) {
-        if ((mask >> q) & 1u) {
-            const double tw = tau * w[q];
+    for (int q = QA; q < QB; ++q) {
+        const double tw = tau * w[q];
 #pragma unroll
-            for (int t = 0; t < TQ_RPL; ++t) if (t >= t0) c[q][t] -= tw * v[t];
-        }
+        for (int t = 0; t < TQ_RPL; ++t) c[q][t] -= tw * v[t];
+    }
     }
 }
-// dlarfg on column slot q (= global column k, every earlier reflector applied): beta on the diagonal, v below it (also left in
-// the registers), published as reflector k
-__device__ __forceinline__ void tq_generate(double (&cq)[TQ_RPL], int k, double* vk, double* tau_s, unsigned long long* bars, int lane, int nt) {
+// the same for the runtime (warp-uniform) range q0 .. NC-1
+template <int NC>
+__device__ __forceinline__ void tq_apply_from(double (&c)[NC][TQ_RPL], int q0, const double* vk, double tau, int lane) {
+    switch (q0) {
+        case 0: tq_apply<NC, 0, NC>(c, vk, tau, lane); break;
+        case 1: tq_apply<NC, (1 < NC ? 1 : NC), NC>(c, vk, tau, lane); break;
+        case 2: tq_apply<NC, (2 < NC ? 2 : NC), NC>(c, vk, tau, lane); break;
+        case 3: tq_apply<NC, (3 < NC ? 3 : NC), NC>(c, vk, tau, lane); break;
+        default: break;
+    }
+}
+template <int NC>
+__device__ __forceinline__ void tq_apply_one(double (&c)[NC][TQ_RPL], int q, const double* vk, double tau, int lane) {
+    switch (q) {
+        case 0: tq_apply<NC, 0, 1>(c, vk, tau, lane); break;
+        case 1: tq_apply<NC, (1 < NC ? 1 : NC), (1 < NC ? 2 : NC)>(c, vk, tau, lane); break;
+        case 2: tq_apply<NC, (2 < NC ? 2 : NC), (2 < NC ? 3 : NC)>(c, vk, tau, lane); break;
+        case 3: tq_apply<NC, (3 < NC ? 3 : NC), (3 < NC ? 4 : NC)>(c, vk, tau, lane); break;
+        default: break;
+    }
+}
+// dlarfg on one column (= global column k, every earlier reflector applied): beta on the diagonal, v below it (also left in the
+// registers), published as reflector k with explicit zeros above row k
+__device__ __forceinline__ void tq_generate(double (&cq)[TQ_RPL], int k, double* vk, double* tau_s, unsigned long long* bars, int lane) {
     double ss = 0.0, al = 0.0;
 #pragma unroll
     for (int t = 0; t < TQ_RPL; ++t) {
@@ -249,10 +264,10 @@ __device__ __forceinline__ void tq_generate(double (&cq)[TQ_RPL], int k, double*
 #pragma unroll
     for (int t = 0; t < TQ_RPL; ++t) {
         const int i = lane + 32 * t;
-        if (t < nt) {
-            if (i > k) { const double x = cq[t] * scale; cq[t] = x; vk[i] = x; }
-            else if (i == k) { cq[t] = beta; vk[i] = 1.0; }
-        }
+        double x = 0.0;
+        if (i > k) { x = cq[t] * scale; cq[t] = x; }
+        else if (i == k) { cq[t] = beta; x = 1.0; }
+        vk[i] = x;
     }
     if (lane == 0) tau_s[k] = tk;
     __threadfence_block();
@@ -262,7 +277,9 @@ __device__ __forceinline__ void tq_generate(double (&cq)[TQ_RPL], int k, double*
 // One level of the tree.  Node b factors `cnt` stacked source blocks:
 //   level 1 : src = A (m x n, lda), block b = rows [b*m/G, (b+1)*m/G);                     Q block -> qout (ldq = m) at those rows
 //   level>1 : src = the previous level's R factors (n x n each, contiguous), node b stacks R[F b .. F b + F-1];  Q block (cnt*n x n) -> qout + b*F n*n (ld F n)
-// rout + b*n*n receives the node's R (upper triangular, zeros below).  dynamic smem: (n * ldv + 2 n) doubles, ldv = rows rounded up to 32.
+// rout + b*n*n receives the node's R (upper triangular, zeros below).  NC = columns per warp = ceil(n / 16).
+// dynamic smem: (n * TQ_LDV + 2 n) doubles.
+template <int NC>
 __global__ void __launch_bounds__(TQ_THREADS, 1) k_tsqr_factor(const double* __restrict__ src, int level, int m, int n, int lda, int G, int nsrc, int F,
                                                               double* __restrict__ rout, double* __restrict__ qout, int ldq) {
     extern __shared__ double smem[];
@@ -270,13 +287,12 @@ __global__ void __launch_bounds__(TQ_THREADS, 1) k_tsqr_factor(const double* __r
     int rows, row0 = 0;
     if (level == 1) { row0 = (int)((long long)b * m / G); rows = (int)((long long)(b + 1) * m / G) - row0; }
     else { const int c0 = F * b; rows = min(F, nsrc - c0) * n; }
-    const int ldv = (rows + 31) & ~31, nt = ldv >> 5;
-    double* V = smem; double* tau_s = V + (size_t)n * ldv;
+    double* V = smem; double* tau_s = V + (size_t)n * TQ_LDV;
     unsigned long long* bars = (unsigned long long*)(tau_s + n);
     for (int k = threadIdx.x; k < n; k += blockDim.x) tq_mbar_init(bars + k);
-    double c[TQ_NC][TQ_RPL];
+    double c[NC][TQ_RPL];
 #pragma unroll
-    for (int q = 0; q < TQ_NC; ++q) {
+    for (int q = 0; q < NC; ++q) {
         const int j = wid + TQ_WARPS * q;
 #pragma unroll
         for (int t = 0; t < TQ_RPL; ++t) {
@@ -290,30 +306,26 @@ __global__ void __launch_bounds__(TQ_THREADS, 1) k_tsqr_factor(const double* __r
         }
     }
     __syncthreads();
-    // ---------------- dgeqr2
-    if (wid == 0) tq_generate(c[0], 0, V, tau_s, bars, lane, nt);
+    // ---------------- dgeqr2 (columns >= n of a warp hold zeros and simply ride along)
+    if (wid == 0) tq_generate(c[0], 0, V, tau_s, bars, lane);
     for (int k = 0; k + 1 < n; ++k) {
-        unsigned mask = 0;
-#pragma unroll
-        for (int q = 0; q < TQ_NC; ++q) { const int j = wid + TQ_WARPS * q; if (j > k && j < n) mask |= 1u << q; }
-        if (!mask) break;
+        const int q0 = (k >= wid) ? ((k - wid) >> 4) + 1 : 0;          // my column slots below q0 are columns <= k: finished
+        if (q0 >= NC || wid + TQ_WARPS * q0 >= n) break;
         tq_mbar_wait(bars + k);
         const double tk = tau_s[k];
-        const double* vk = V + (size_t)k * ldv;
-        const int qn = (((k + 1) & (TQ_WARPS - 1)) == wid) ? ((k + 1) >> 4) : -1;      // column k+1 is mine: it goes first
-        if (qn >= 0) {
-            tq_apply(c, 1u << qn, vk, k, tk, lane, nt);
+        const double* vk = V + (size_t)k * TQ_LDV;
+        if (wid + TQ_WARPS * q0 == k + 1) {                            // column k+1 is mine: it goes first, and its reflector right after
+            tq_apply_one<NC>(c, q0, vk, tk, lane);
 #pragma unroll
-            for (int q = 0; q < TQ_NC; ++q) if (q == qn) tq_generate(c[q], k + 1, V + (size_t)(k + 1) * ldv, tau_s, bars, lane, nt);
-            mask &= ~(1u << qn);
-        }
-        if (mask) tq_apply(c, mask, vk, k, tk, lane, nt);
+            for (int q = 0; q < NC; ++q) if (q == q0) tq_generate(c[q], k + 1, V + (size_t)(k + 1) * TQ_LDV, tau_s, bars, lane);
+            tq_apply_from<NC>(c, q0 + 1, vk, tk, lane);
+        } else tq_apply_from<NC>(c, q0, vk, tk, lane);
     }
     __syncthreads();
     // ---------------- R out (registers: rows <= j of column j), then dorg2r in place
     int jmax = -1;
 #pragma unroll
-    for (int q = 0; q < TQ_NC; ++q) {
+    for (int q = 0; q < NC; ++q) {
         const int j = wid + TQ_WARPS * q;
         if (j < n) {
             jmax = j;
@@ -327,13 +339,11 @@ __global__ void __launch_bounds__(TQ_THREADS, 1) k_tsqr_factor(const double* __r
         }
     }
     for (int k = jmax - 1; k >= 0; --k) {
-        unsigned mask = 0;
-#pragma unroll
-        for (int q = 0; q < TQ_NC; ++q) { const int j = wid + TQ_WARPS * q; if (j > k && j < n) mask |= 1u << q; }
-        tq_apply(c, mask, V + (size_t)k * ldv, k, tau_s[k], lane, nt);
+        const int q0 = (k >= wid) ? ((k - wid) >> 4) + 1 : 0;
+        tq_apply_from<NC>(c, q0, V + (size_t)k * TQ_LDV, tau_s[k], lane);
     }
 #pragma unroll
-    for (int q = 0; q < TQ_NC; ++q) {
+    for (int q = 0; q < NC; ++q) {
         const int j = wid + TQ_WARPS * q;
         if (j < n) {
 #pragma unroll
@@ -349,38 +359,68 @@ __global__ void __launch_bounds__(TQ_THREADS, 1) k_tsqr_factor(const double* __r
 }
 // Q(block b) <- Q1(block b) * Q2[slice] * Q3[slice] * ... (levels 2..L); qlev[l] = that level's Q blocks (F n x n each, ld F n).
 struct TsqrLevels { const double* q[8]; int count; };
+// The chain M = slice(level 2) * slice(level 3) * ... is formed in shared memory (each slice staged with coalesced loads first);
+// the block product Q1 * M runs on 4 x 4 register tiles (rows ti + 64 r, columns tj + 16 c: conflict-free loads of Q1, broadcast
+// loads of M; 8 shared-memory loads per 16 multiply-adds instead of 2 per 1).
 __global__ void __launch_bounds__(TSQR_THREADS) k_tsqr_apply(double* __restrict__ q, int m, int n, int ldq, int G, int F, TsqrLevels LV) {
     extern __shared__ double smem[];
     const int b = blockIdx.x;
     const int row0 = (int)((long long)b * m / G), rows = (int)((long long)(b + 1) * m / G) - row0;
     double* M = smem; double* T = M + n * n; double* QB = T + n * n;      // M, T: n x n (ld n); QB: rows x n
+    if (LV.count == 0) return;
     for (int e = threadIdx.x; e < rows * n; e += blockDim.x) { const int j = e / rows, i = e - j * rows; QB[e] = q[(size_t)(row0 + i) + (size_t)ldq * j]; }
     int idx = b;
     for (int l = 0; l < LV.count; ++l) {
         const int node = idx / F, slot = idx - F * node;
         const double* ql = LV.q[l] + (size_t)node * F * n * n + (size_t)slot * n;        // rows slot*n .. of the F n x n block
-        if (l == 0) {
-            for (int e = threadIdx.x; e < n * n; e += blockDim.x) { const int j = e / n, i = e - j * n; M[e] = ql[i + (size_t)F * n * j]; }
-        } else {
-            for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-                const int j = e / n, i = e - j * n;
-                double t = 0.0;
-                for (int x = 0; x < n; ++x) t += M[i + n * x] * ql[x + (size_t)F * n * j];
-                T[e] = t;
+        double* dst = (l == 0) ? M : T;
+        for (int e = threadIdx.x; e < n * n; e += blockDim.x) { const int j = e / n, i = e - j * n; dst[e] = ql[i + (size_t)F * n * j]; }
+        __syncthreads();
+        if (l > 0) {
+            double acc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = threadIdx.x + u * TSQR_THREADS;
+                acc[u] = 0.0;
+                if (e < n * n) {
+                    const int j = e / n, i = e - j * n;
+                    double t = 0.0;
+                    for (int x = 0; x < n; ++x) t += M[i + n * x] * T[x + n * j];
+                    acc[u] = t;
+                }
             }
             __syncthreads();
-            for (int e = threadIdx.x; e < n * n; e += blockDim.x) M[e] = T[e];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int e = threadIdx.x + u * TSQR_THREADS; if (e < n * n) M[e] = acc[u]; }
+            __syncthreads();
         }
-        __syncthreads();
         idx = node;
     }
-    if (LV.count == 0) return;
-    for (int e = threadIdx.x; e < rows * n; e += blockDim.x) {
-        const int j = e / rows, i = e - j * rows;
-        double t = 0.0;
-        for (int x = 0; x < n; ++x) t += QB[i + rows * x] * M[x + n * j];
-        q[(size_t)(row0 + i) + (size_t)ldq * j] = t;
+    const int ti = threadIdx.x & 63, tj = threadIdx.x >> 6;
+    int ir[4], jc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { ir[r] = min(ti + 64 * r, rows - 1); jc[r] = min(tj + 16 * r, n - 1); }
+    double acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+    for (int x = 0; x < n; ++x) {
+        double av[4], bv[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { av[r] = QB[ir[r] + rows * x]; bv[r] = M[x + n * jc[r]]; }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] += av[r] * bv[c];
     }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = ti + 64 * r, j = tj + 16 * c;
+            if (i < rows && j < n) q[(size_t)(row0 + i) + (size_t)ldq * j] = acc[r][c];
+        }
 }
 // Householder reconstruction of LAPACK's signs: modified LU (no pivoting) of the top n x n block of Q; sgn[k] = S_kk; r <- S r.
 __global__ void __launch_bounds__(TSQR_THREADS) k_tsqr_sign(const double* __restrict__ q, int n, int ldq, double* __restrict__ r, double* __restrict__ sgn) {
@@ -388,15 +428,17 @@ __global__ void __launch_bounds__(TSQR_THREADS) k_tsqr_sign(const double* __rest
     double* W = smem; double* S = W + n * n;
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) { const int j = e / n, i = e - j * n; W[e] = q[(size_t)i + (size_t)ldq * j]; }
     __syncthreads();
+    // one barrier per step: every thread reads the (final) diagonal entry, forms the sign and the shifted pivot itself, and
+    // divides on the fly (|pivot| >= 1 by construction); the multipliers are not needed afterwards, only the signs
     for (int k = 0; k < n; ++k) {
-        if (threadIdx.x == 0) { const double sk = (W[k + n * k] >= 0.0) ? -1.0 : 1.0; S[k] = sk; W[k + n * k] -= sk; }
-        __syncthreads();
-        const double piv = W[k + n * k];
-        for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) W[i + n * k] /= piv;
-        __syncthreads();
-        for (int e = threadIdx.x; e < (n - k - 1) * (n - k - 1); e += blockDim.x) {
-            const int jj = e / (n - k - 1), ii = e - jj * (n - k - 1), i = k + 1 + ii, j = k + 1 + jj;
-            W[i + n * j] -= W[i + n * k] * W[k + n * j];
+        const double d = W[k + n * k];
+        const double sk = (d >= 0.0) ? -1.0 : 1.0;
+        const double piv = d - sk;
+        if (threadIdx.x == 0) S[k] = sk;
+        const int nk = n - k - 1;
+        for (int e = threadIdx.x; e < nk * nk; e += blockDim.x) {
+            const int jj = e / nk, ii = e - jj * nk, i = k + 1 + ii, j = k + 1 + jj;
+            W[i + n * j] -= (W[i + n * k] / piv) * W[k + n * j];
         }
         __syncthreads();
     }
