@@ -1932,7 +1932,7 @@ cudaError_t tsqr_launch(cudaStream_t s, const double* da, int m, int n, double* 
     const int L = (int)G.size();                                  // levels 1 .. L (level L has one node)
     if (L > 8) return cudaErrorInvalidValue;
     size_t need = (size_t)n + 8;
-    for (int l = 0; l < L; ++l) need += (size_t)G[l] * n * n + (l >= 1 ? (size_t)G[l] * F * n * n : 0);
+    for (int l = 0; l < L; ++l) need += (size_t)G[l] * n * n + (size_t)G[l] * n + (l >= 1 ? (size_t)G[l] * F * n * n : 0);
     if (need > sc.cap_t) {
         if (sc.tsqr) cudaFree(sc.tsqr);
         sc.tsqr = nullptr; sc.cap_t = 0;
@@ -1940,32 +1940,39 @@ cudaError_t tsqr_launch(cudaStream_t s, const double* da, int m, int n, double* 
         if (e != cudaSuccess) return e;
         sc.cap_t = need;
     }
-    std::vector<double*> Rl(L), Ql(L, nullptr);
+    std::vector<double*> Rl(L), Ql(L, nullptr), Tl(L);
     double* p = sc.tsqr;
     double* sgn = p; p += n + 8;
-    for (int l = 0; l < L; ++l) { Rl[l] = p; p += (size_t)G[l] * n * n; if (l >= 1) { Ql[l] = p; p += (size_t)G[l] * F * n * n; } }
-    const int rows1 = (m + G1 - 1) / G1;                          // <= 256
-    const size_t sm_f = ((size_t)n * 256 + 2 * n) * sizeof(double);                 // V (n reflectors, ld <= 256) | tau | one mbarrier per reflector
-    const size_t sm_a = ((size_t)2 * n * n + (size_t)rows1 * n) * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(k_tsqr_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a);
-    if (e != cudaSuccess) return e;
-    auto factor_levels = [&](auto kern) -> cudaError_t {          // kern = k_tsqr_factor<columns per warp>
-        cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
+    for (int l = 0; l < L; ++l) {
+        Rl[l] = p; p += (size_t)G[l] * n * n;
+        Tl[l] = p; p += (size_t)G[l] * n;
+        if (l >= 1) { Ql[l] = p; p += (size_t)G[l] * F * n * n; }
+    }
+    const size_t sm_f = ((size_t)n * TQ_LDV + 2 * n) * sizeof(double);                  // V (n reflectors, ld 256) | tau | one mbarrier per reflector
+    const size_t sm_l = ((size_t)n * TQ_LDV + n + (size_t)2 * n * n) * sizeof(double);  // V / Q1 | tau | M | T
+    TsqrLevels LV; LV.count = L - 1; LV.first[0] = 0;
+    for (int l = 1; l < L; ++l) { LV.q[l - 1] = Ql[l]; LV.tau[l - 1] = Tl[l]; LV.nsrc[l - 1] = G[l - 1]; LV.first[l] = LV.first[l - 1] + G[l]; }
+    // the chain of factor launches (only R feeds the next level), then the explicit Q of all upper nodes in one launch, then the
+    // first-level blocks: dorg2r + chain of slices + block product in one kernel
+    auto run = [&](auto kfac, auto kformq, auto kleaf) -> cudaError_t {
+        cudaError_t e2 = cudaFuncSetAttribute(kfac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(kformq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(kleaf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_l);
         if (e2 != cudaSuccess) return e2;
-        kern<<<G1, TQ_THREADS, sm_f, s>>>(da, 1, m, n, m, G1, 0, F, Rl[0], dq, m);
-        for (int l = 1; l < L; ++l) kern<<<G[l], TQ_THREADS, sm_f, s>>>(Rl[l - 1], l + 1, m, n, m, G1, G[l - 1], F, Rl[l], Ql[l], m);
+        kfac<<<G1, TQ_THREADS, sm_f, s>>>(da, 1, m, n, m, G1, 0, F, Rl[0], dq, m, Tl[0]);
+        for (int l = 1; l < L; ++l) kfac<<<G[l], TQ_THREADS, sm_f, s>>>(Rl[l - 1], l + 1, m, n, m, G1, G[l - 1], F, Rl[l], Ql[l], m, Tl[l]);
+        if (L > 1) kformq<<<LV.first[L - 1], TQ_THREADS, sm_f, s>>>(n, F, LV);
+        kleaf<<<G1, TQ_THREADS, sm_l, s>>>(dq, m, n, m, G1, F, Tl[0], LV);
         return cudaSuccess;
     };
+    cudaError_t e;
     switch ((n + TQ_WARPS - 1) / TQ_WARPS) {
-        case 1: e = factor_levels(k_tsqr_factor<1>); break;
-        case 2: e = factor_levels(k_tsqr_factor<2>); break;
-        case 3: e = factor_levels(k_tsqr_factor<3>); break;
-        default: e = factor_levels(k_tsqr_factor<4>); break;
+        case 1: e = run(k_tsqr_factor<1>, k_tsqr_formq<1>, k_tsqr_leaf<1>); break;
+        case 2: e = run(k_tsqr_factor<2>, k_tsqr_formq<2>, k_tsqr_leaf<2>); break;
+        case 3: e = run(k_tsqr_factor<3>, k_tsqr_formq<3>, k_tsqr_leaf<3>); break;
+        default: e = run(k_tsqr_factor<4>, k_tsqr_formq<4>, k_tsqr_leaf<4>); break;
     }
     if (e != cudaSuccess) return e;
-    TsqrLevels LV; LV.count = L - 1;
-    for (int l = 1; l < L; ++l) LV.q[l - 1] = Ql[l];
-    if (L > 1) k_tsqr_apply<<<G1, TSQR_THREADS, sm_a, s>>>(dq, m, n, m, G1, F, LV);
     e = cudaMemcpyAsync(dr, Rl[L - 1], (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice, s);
     if (e != cudaSuccess) return e;
     k_tsqr_sign<<<1, TSQR_THREADS, ((size_t)n * n + n) * sizeof(double), s>>>(dq, n, m, dr, sgn);

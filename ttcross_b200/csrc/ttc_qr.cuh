@@ -274,14 +274,16 @@ __device__ __forceinline__ void tq_generate(double (&cq)[TQ_RPL], int k, double*
     __syncwarp();
     if (lane == 0) tq_mbar_arrive(bars + k);
 }
-// One level of the tree.  Node b factors `cnt` stacked source blocks:
-//   level 1 : src = A (m x n, lda), block b = rows [b*m/G, (b+1)*m/G);                     Q block -> qout (ldq = m) at those rows
-//   level>1 : src = the previous level's R factors (n x n each, contiguous), node b stacks R[F b .. F b + F-1];  Q block (cnt*n x n) -> qout + b*F n*n (ld F n)
-// rout + b*n*n receives the node's R (upper triangular, zeros below).  NC = columns per warp = ceil(n / 16).
-// dynamic smem: (n * TQ_LDV + 2 n) doubles.
+// One level of the tree, FACTOR phase only.  Node b factors `cnt` stacked source blocks:
+//   level 1 : src = A (m x n, lda), block b = rows [b*m/G, (b+1)*m/G);                     raw block -> qout (ldq = m) at those rows
+//   level>1 : src = the previous level's R factors (n x n each, contiguous), node b stacks R[F b .. F b + F-1];  raw block (cnt*n x n) -> qout + b*F n*n (ld F n)
+// "raw block" = LAPACK's dgeqr2 storage (R on and above the diagonal, reflector vectors below), tau_out + b*n its scalars:
+// forming the explicit Q from it (dorg2r) does not feed the next level -- only R does (rout + b*n*n, upper triangular, zeros
+// below) -- so it is left to k_tsqr_formq / k_tsqr_leaf, which run once for all levels after the chain of factor launches.
+// NC = columns per warp = ceil(n / 16).  dynamic smem: (n * TQ_LDV + 2 n) doubles.
 template <int NC>
 __global__ void __launch_bounds__(TQ_THREADS, 1) k_tsqr_factor(const double* __restrict__ src, int level, int m, int n, int lda, int G, int nsrc, int F,
-                                                              double* __restrict__ rout, double* __restrict__ qout, int ldq) {
+                                                              double* __restrict__ rout, double* __restrict__ qout, int ldq, double* __restrict__ tau_out) {
     extern __shared__ double smem[];
     const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int rows, row0 = 0;
@@ -321,54 +323,119 @@ __global__ void __launch_bounds__(TQ_THREADS, 1) k_tsqr_factor(const double* __r
             tq_apply_from<NC>(c, q0 + 1, vk, tk, lane);
         } else tq_apply_from<NC>(c, q0, vk, tk, lane);
     }
-    __syncthreads();
-    // ---------------- R out (registers: rows <= j of column j), then dorg2r in place
-    int jmax = -1;
+    // ---------------- R and the raw block out (every column is final once its owner leaves the loop)
+    double* qb = (level == 1) ? qout + row0 : qout + (size_t)b * F * n * n;
+    const size_t ldb = (level == 1) ? (size_t)ldq : (size_t)F * n;
 #pragma unroll
     for (int q = 0; q < NC; ++q) {
         const int j = wid + TQ_WARPS * q;
         if (j < n) {
-            jmax = j;
-            const double tj = tau_s[j];
 #pragma unroll
             for (int t = 0; t < TQ_RPL; ++t) {
                 const int i = lane + 32 * t;
                 if (i < n) rout[(size_t)b * n * n + i + (size_t)n * j] = (i <= j) ? c[q][t] : 0.0;
-                c[q][t] = (i < j) ? 0.0 : ((i == j) ? 1.0 - tj : -tj * c[q][t]);
+                if (i < rows) qb[i + ldb * j] = c[q][t];
             }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) tau_out[(size_t)b * n + k] = tau_s[k];
+}
+// dorg2r of a raw block held column-wise in registers: reload (raw block at qb, leading dimension ldb), publish the reflectors
+// in shared memory, then every warp runs the chains of its own columns -- column j of Q is H(0) ... H(j) e_j -- with no
+// synchronisation at all.  On return c holds the explicit Q block.
+template <int NC>
+__device__ __forceinline__ void tq_formq(double (&c)[NC][TQ_RPL], const double* __restrict__ qb, size_t ldb, int rows, int n,
+                                         const double* __restrict__ tau_g, double* V, double* tau_s, int lane, int wid) {
+    for (int k = threadIdx.x; k < n; k += blockDim.x) tau_s[k] = tau_g[k];
+    int jmax = -1;
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+        const int j = wid + TQ_WARPS * q;
+#pragma unroll
+        for (int t = 0; t < TQ_RPL; ++t) {
+            const int i = lane + 32 * t;
+            const double x = (j < n && i < rows && i > j) ? qb[i + ldb * j] : 0.0;
+            c[q][t] = x;
+            if (j < n) V[(size_t)j * TQ_LDV + i] = (i == j) ? 1.0 : x;
+        }
+        if (j < n) jmax = j;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+        const int j = wid + TQ_WARPS * q;
+        if (j < n) {
+            const double tj = tau_s[j];
+#pragma unroll
+            for (int t = 0; t < TQ_RPL; ++t) { const int i = lane + 32 * t; c[q][t] = (i == j) ? 1.0 - tj : -tj * c[q][t]; }
         }
     }
     for (int k = jmax - 1; k >= 0; --k) {
         const int q0 = (k >= wid) ? ((k - wid) >> 4) + 1 : 0;
         tq_apply_from<NC>(c, q0, V + (size_t)k * TQ_LDV, tau_s[k], lane);
     }
+}
+// Explicit Q of every UPPER node (levels 2 .. L) in one launch, in place over the raw blocks.  blockIdx.x runs over the nodes
+// of all upper levels: level l (0-based among the upper ones) owns blocks first[l] .. first[l+1]-1.
+struct TsqrLevels { double* q[8]; const double* tau[8]; int first[9]; int nsrc[8]; int count; };
+template <int NC>
+__global__ void __launch_bounds__(TQ_THREADS, 1) k_tsqr_formq(int n, int F, TsqrLevels LV) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int l = 0;
+    while (l + 1 < LV.count && (int)blockIdx.x >= LV.first[l + 1]) ++l;
+    const int b = blockIdx.x - LV.first[l];
+    const int rows = min(F, LV.nsrc[l] - F * b) * n;
+    double* V = smem; double* tau_s = V + (size_t)n * TQ_LDV;
+    double* qb = LV.q[l] + (size_t)b * F * n * n;
+    const size_t ldb = (size_t)F * n;
+    double c[NC][TQ_RPL];
+    tq_formq<NC>(c, qb, ldb, rows, n, LV.tau[l] + (size_t)b * n, V, tau_s, lane, wid);
 #pragma unroll
     for (int q = 0; q < NC; ++q) {
         const int j = wid + TQ_WARPS * q;
         if (j < n) {
 #pragma unroll
-            for (int t = 0; t < TQ_RPL; ++t) {
-                const int i = lane + 32 * t;
-                if (i < rows) {
-                    if (level == 1) qout[(size_t)(row0 + i) + (size_t)ldq * j] = c[q][t];
-                    else qout[(size_t)b * F * n * n + i + (size_t)F * n * j] = c[q][t];
-                }
-            }
+            for (int t = 0; t < TQ_RPL; ++t) { const int i = lane + 32 * t; if (i < rows) qb[i + ldb * j] = c[q][t]; }
         }
     }
 }
-// Q(block b) <- Q1(block b) * Q2[slice] * Q3[slice] * ... (levels 2..L); qlev[l] = that level's Q blocks (F n x n each, ld F n).
-struct TsqrLevels { const double* q[8]; int count; };
-// The chain M = slice(level 2) * slice(level 3) * ... is formed in shared memory (each slice staged with coalesced loads first);
-// the block product Q1 * M runs on 4 x 4 register tiles (rows ti + 64 r, columns tj + 16 c: conflict-free loads of Q1, broadcast
-// loads of M; 8 shared-memory loads per 16 multiply-adds instead of 2 per 1).
-__global__ void __launch_bounds__(TSQR_THREADS) k_tsqr_apply(double* __restrict__ q, int m, int n, int ldq, int G, int F, TsqrLevels LV) {
+// First-level block b: explicit Q1 from its raw block (registers -> shared memory, over the reflector storage, which is dead by
+// then), the chain M = slice(level 2) * slice(level 3) * ... formed in shared memory (each slice staged with coalesced loads
+// first), and the final rows Q1 * M on 4 x 8 register tiles (rows ti + 64 r, columns tj + 8 c: conflict-free loads of Q1,
+// broadcast loads of M; 12 shared-memory loads per 32 multiply-adds).  One launch replaces dorg2r + the block product and
+// Q1 never travels through HBM.  dynamic smem: (n * TQ_LDV + n + 2 n^2) doubles.
+template <int NC>
+__global__ void __launch_bounds__(TQ_THREADS, 1) k_tsqr_leaf(double* __restrict__ q, int m, int n, int ldq, int G, int F, const double* __restrict__ tau1, TsqrLevels LV) {
     extern __shared__ double smem[];
-    const int b = blockIdx.x;
+    const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int row0 = (int)((long long)b * m / G), rows = (int)((long long)(b + 1) * m / G) - row0;
-    double* M = smem; double* T = M + n * n; double* QB = T + n * n;      // M, T: n x n (ld n); QB: rows x n
-    if (LV.count == 0) return;
-    for (int e = threadIdx.x; e < rows * n; e += blockDim.x) { const int j = e / rows, i = e - j * rows; QB[e] = q[(size_t)(row0 + i) + (size_t)ldq * j]; }
+    double* V = smem; double* tau_s = V + (size_t)n * TQ_LDV; double* M = tau_s + n; double* T = M + n * n;
+    double* qb = q + row0;
+    double c[NC][TQ_RPL];
+    tq_formq<NC>(c, qb, (size_t)ldq, rows, n, tau1 + (size_t)b * n, V, tau_s, lane, wid);
+    if (LV.count == 0) {                                  // a single block: Q1 is the answer
+#pragma unroll
+        for (int q2 = 0; q2 < NC; ++q2) {
+            const int j = wid + TQ_WARPS * q2;
+            if (j < n) {
+#pragma unroll
+                for (int t = 0; t < TQ_RPL; ++t) { const int i = lane + 32 * t; if (i < rows) qb[i + (size_t)ldq * j] = c[q2][t]; }
+            }
+        }
+        return;
+    }
+    __syncthreads();                                      // every chain has finished reading the reflectors
+    double* QB = V;                                       // Q1 (TQ_LDV x n, leading dimension TQ_LDV)
+#pragma unroll
+    for (int q2 = 0; q2 < NC; ++q2) {
+        const int j = wid + TQ_WARPS * q2;
+        if (j < n) {
+#pragma unroll
+            for (int t = 0; t < TQ_RPL; ++t) QB[(size_t)j * TQ_LDV + lane + 32 * t] = c[q2][t];
+        }
+    }
     int idx = b;
     for (int l = 0; l < LV.count; ++l) {
         const int node = idx / F, slot = idx - F * node;
@@ -377,10 +444,10 @@ __global__ void __launch_bounds__(TSQR_THREADS) k_tsqr_apply(double* __restrict_
         for (int e = threadIdx.x; e < n * n; e += blockDim.x) { const int j = e / n, i = e - j * n; dst[e] = ql[i + (size_t)F * n * j]; }
         __syncthreads();
         if (l > 0) {
-            double acc[4];
+            double acc[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = threadIdx.x + u * TSQR_THREADS;
+            for (int u = 0; u < 8; ++u) {
+                const int e = threadIdx.x + u * TQ_THREADS;
                 acc[u] = 0.0;
                 if (e < n * n) {
                     const int j = e / n, i = e - j * n;
@@ -391,35 +458,34 @@ __global__ void __launch_bounds__(TSQR_THREADS) k_tsqr_apply(double* __restrict_
             }
             __syncthreads();
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { const int e = threadIdx.x + u * TSQR_THREADS; if (e < n * n) M[e] = acc[u]; }
+            for (int u = 0; u < 8; ++u) { const int e = threadIdx.x + u * TQ_THREADS; if (e < n * n) M[e] = acc[u]; }
             __syncthreads();
         }
         idx = node;
     }
     const int ti = threadIdx.x & 63, tj = threadIdx.x >> 6;
-    int ir[4], jc[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) { ir[r] = min(ti + 64 * r, rows - 1); jc[r] = min(tj + 16 * r, n - 1); }
-    double acc[4][4];
+    double acc[4][8];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+        for (int cc = 0; cc < 8; ++cc) acc[r][cc] = 0.0;
     for (int x = 0; x < n; ++x) {
-        double av[4], bv[4];
+        double av[4], bv[8];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) { av[r] = QB[ir[r] + rows * x]; bv[r] = M[x + n * jc[r]]; }
+        for (int r = 0; r < 4; ++r) av[r] = QB[(size_t)x * TQ_LDV + ti + 64 * r];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) bv[cc] = M[x + n * min(tj + 8 * cc, n - 1)];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r][c] += av[r] * bv[c];
+            for (int cc = 0; cc < 8; ++cc) acc[r][cc] += av[r] * bv[cc];
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int i = ti + 64 * r, j = tj + 16 * c;
-            if (i < rows && j < n) q[(size_t)(row0 + i) + (size_t)ldq * j] = acc[r][c];
+        for (int cc = 0; cc < 8; ++cc) {
+            const int i = ti + 64 * r, j = tj + 8 * cc;
+            if (i < rows && j < n) q[(size_t)(row0 + i) + (size_t)ldq * j] = acc[r][cc];
         }
 }
 // Householder reconstruction of LAPACK's signs: modified LU (no pivoting) of the top n x n block of Q; sgn[k] = S_kk; r <- S r.
@@ -435,10 +501,11 @@ __global__ void __launch_bounds__(TSQR_THREADS) k_tsqr_sign(const double* __rest
         const double sk = (d >= 0.0) ? -1.0 : 1.0;
         const double piv = d - sk;
         if (threadIdx.x == 0) S[k] = sk;
-        const int nk = n - k - 1;
-        for (int e = threadIdx.x; e < nk * nk; e += blockDim.x) {
-            const int jj = e / nk, ii = e - jj * nk, i = k + 1 + ii, j = k + 1 + jj;
-            W[i + n * j] -= (W[i + n * k] / piv) * W[k + n * j];
+        const int i = threadIdx.x & 63, tj = threadIdx.x >> 6;          // thread = (row i, columns tj + 16 c): no index arithmetic in the chain
+        if (i > k && i < n) {
+            const double l = W[i + n * k] / piv;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { const int j = tj + 16 * c; if (j > k && j < n) W[i + n * j] -= l * W[k + n * j]; }
         }
         __syncthreads();
     }
