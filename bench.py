@@ -421,6 +421,27 @@ def main():
         except Exception as e:  # noqa: BLE001
             line["roofline_superblock"] = {"error": str(e)}
 
+    # ---- the tall-skinny QR of ort0_d (lib/ort.f90:17-81; SURVEY 8 row a21, north-star item 3) at this config's unfolding shape
+    # (r n) x r: not called by the sweep -- reported beside it, against the measured FP64 ceilings
+    if not args.no_superblock and rank == 0 and world == 1:
+        try:
+            mq, nq = R * nn, R
+            rngq = np.random.default_rng(7)
+            aq = np.asfortranarray(rngq.standard_normal((mq, nq)) * np.exp(rngq.uniform(-3, 3, size=(1, nq))))
+            qq_, rq_, ms_q = T.qr_thin(aq, device=local_rank, reps=10)
+            fl_q = 4.0 * mq * nq * nq - 4.0 * nq ** 3 / 3.0            # dgeqrf + dorgqr
+            pk_nofma_q = line.get("roofline_superblock", {}).get("fp64_peak_measured_tflops", {}).get("dmul_dadd") or T.fp64_peak(local_rank, False)
+            line["roofline_qr"] = {
+                "kernel": "TSQR of ttc_qr.cuh (k_tsqr_factor per tree level, k_tsqr_formq, k_tsqr_leaf, k_tsqr_sign, k_tsqr_scale): thin Householder QR with LAPACK's signs, explicit Q",
+                "shape": [mq, nq], "ms": ms_q, "algorithmic_flops": fl_q, "achieved": fl_q / (ms_q * 1e-3) / 1e12, "unit": "TFLOP/s",
+                "peak": pk_nofma_q, "frac": fl_q / (ms_q * 1e-3) / 1e12 / pk_nofma_q, "bound": "latency",
+                "hbm_frac": 2.0 * 8.0 * mq * nq / (ms_q * 1e-3) / 1e9 / hbm_peak,
+                "residual_vs_lapack": float(np.abs(rq_ - np.linalg.qr(aq)[1]).max() / np.linalg.norm(aq)),
+                "note": "n dependent reflectors per tree level (sum of squares, sqrt, two divisions, rank-1 update each): latency-bound by construction; "
+                        "DMMA does not apply -- the only dense contraction (Q1 * M per block) is < 10 % of the time (profiles/r02f_ncu_tsqr.txt)"}
+        except Exception as e:  # noqa: BLE001
+            line["roofline_qr"] = {"error": str(e)}
+
     # ---- CPU baseline beside it: the oracle on the host cores, bounded sample
     if not args.no_cpu_baseline and rank == 0 and args.gpus == 1:
         from oracle import oracle as O
