@@ -202,9 +202,10 @@ __device__ __forceinline__ void tq_apply(double (&c)[NC][TQ_RPL], const double* 
     double w[NC];
 #pragma unroll
     for (int q = QA; q < QB; ++q) {
+        // (explicit FMA: this QR is held to LAPACK by tolerance, not bit for bit -- the library's -fmad=false is for the sweep)
         double wa = v[0] * c[q][0], wb = v[1] * c[q][1];
 #pragma unroll
-        for (int t = 2; t < TQ_RPL; t += 2) { wa += v[t] * c[q][t]; wb += v[t + 1] * c[q][t + 1]; }
+        for (int t = 2; t < TQ_RPL; t += 2) { wa = fma(v[t], c[q][t], wa); wb = fma(v[t + 1], c[q][t + 1], wb); }
         w[q] = wa + wb;
     }
 #pragma unroll
@@ -214,9 +215,9 @@ __device__ __forceinline__ void tq_apply(double (&c)[NC][TQ_RPL], const double* 
     }
 #pragma unroll
     for (int q = QA; q < QB; ++q) {
-        const double tw = tau * w[q];
+        const double tw = -(tau * w[q]);
 #pragma unroll
-        for (int t = 0; t < TQ_RPL; ++t) c[q][t] -= tw * v[t];
+        for (int t = 0; t < TQ_RPL; ++t) c[q][t] = fma(tw, v[t], c[q][t]);
     }
     }
 }
@@ -243,13 +244,13 @@ __device__ __forceinline__ void tq_apply_one(double (&c)[NC][TQ_RPL], int q, con
 }
 // dlarfg on one column (= global column k, every earlier reflector applied): beta on the diagonal, v below it (also left in the
 // registers), published as reflector k with explicit zeros above row k
-__device__ __forceinline__ void tq_generate(double (&cq)[TQ_RPL], int k, double* vk, double* tau_s, unsigned long long* bars, int lane) {
+__device__ __forceinline__ double tq_generate(double (&cq)[TQ_RPL], int k, double* vk, double* tau_s, unsigned long long* bars, int lane) {
     double ss = 0.0, al = 0.0;
 #pragma unroll
     for (int t = 0; t < TQ_RPL; ++t) {
         const int i = lane + 32 * t;
         const double x = cq[t];
-        if (i > k) ss += x * x;
+        if (i > k) ss = fma(x, x, ss);
         if (i == k) al = x;
     }
 #pragma unroll
@@ -273,6 +274,19 @@ __device__ __forceinline__ void tq_generate(double (&cq)[TQ_RPL], int k, double*
     __threadfence_block();
     __syncwarp();
     if (lane == 0) tq_mbar_arrive(bars + k);
+    return tk;
+}
+// the panel of one warp (compile-time recursion over its column slots)
+template <int NC, int Q>
+__device__ __forceinline__ void tq_panel(double (&c)[NC][TQ_RPL], int j0, int n, double* V, double* tau_s, unsigned long long* bars, int lane) {
+    if constexpr (Q < NC) {
+        const int j = j0 + Q;
+        if (j < n) {
+            const double tj = tq_generate(c[Q], j, V + (size_t)j * TQ_LDV, tau_s, bars, lane);
+            tq_apply<NC, Q + 1, NC>(c, V + (size_t)j * TQ_LDV, tj, lane);
+            tq_panel<NC, Q + 1>(c, j0, n, V, tau_s, bars, lane);
+        }
+    }
 }
 // One level of the tree, FACTOR phase only.  Node b factors `cnt` stacked source blocks:
 //   level 1 : src = A (m x n, lda), block b = rows [b*m/G, (b+1)*m/G);                     raw block -> qout (ldq = m) at those rows
@@ -292,10 +306,13 @@ __global__ void __launch_bounds__(TQ_THREADS, 1) k_tsqr_factor(const double* __r
     double* V = smem; double* tau_s = V + (size_t)n * TQ_LDV;
     unsigned long long* bars = (unsigned long long*)(tau_s + n);
     for (int k = threadIdx.x; k < n; k += blockDim.x) tq_mbar_init(bars + k);
+    // PANEL ownership in this phase: warp w holds the NC consecutive columns NC w .. NC w + NC-1, so the chain of dependent
+    // reflectors changes warps only once per panel (16 hand-offs instead of 64) and stays inside one warp's registers between
+    const int j0 = NC * wid;
     double c[NC][TQ_RPL];
 #pragma unroll
     for (int q = 0; q < NC; ++q) {
-        const int j = wid + TQ_WARPS * q;
+        const int j = j0 + q;
 #pragma unroll
         for (int t = 0; t < TQ_RPL; ++t) {
             const int i = lane + 32 * t;
@@ -308,27 +325,20 @@ __global__ void __launch_bounds__(TQ_THREADS, 1) k_tsqr_factor(const double* __r
         }
     }
     __syncthreads();
-    // ---------------- dgeqr2 (columns >= n of a warp hold zeros and simply ride along)
-    if (wid == 0) tq_generate(c[0], 0, V, tau_s, bars, lane);
-    for (int k = 0; k + 1 < n; ++k) {
-        const int q0 = (k >= wid) ? ((k - wid) >> 4) + 1 : 0;          // my column slots below q0 are columns <= k: finished
-        if (q0 >= NC || wid + TQ_WARPS * q0 >= n) break;
-        tq_mbar_wait(bars + k);
-        const double tk = tau_s[k];
-        const double* vk = V + (size_t)k * TQ_LDV;
-        if (wid + TQ_WARPS * q0 == k + 1) {                            // column k+1 is mine: it goes first, and its reflector right after
-            tq_apply_one<NC>(c, q0, vk, tk, lane);
-#pragma unroll
-            for (int q = 0; q < NC; ++q) if (q == q0) tq_generate(c[q], k + 1, V + (size_t)(k + 1) * TQ_LDV, tau_s, bars, lane);
-            tq_apply_from<NC>(c, q0 + 1, vk, tk, lane);
-        } else tq_apply_from<NC>(c, q0, vk, tk, lane);
+    // ---------------- dgeqr2
+    if (j0 < n) {
+        for (int k = 0; k < j0; ++k) {                     // reflectors of the earlier panels, as they are published
+            tq_mbar_wait(bars + k);
+            tq_apply<NC, 0, NC>(c, V + (size_t)k * TQ_LDV, tau_s[k], lane);
+        }
+        tq_panel<NC, 0>(c, j0, n, V, tau_s, bars, lane);   // my panel: generate, apply to the rest of the panel, next column
     }
-    // ---------------- R and the raw block out (every column is final once its owner leaves the loop)
+    // ---------------- R and the raw block out
     double* qb = (level == 1) ? qout + row0 : qout + (size_t)b * F * n * n;
     const size_t ldb = (level == 1) ? (size_t)ldq : (size_t)F * n;
 #pragma unroll
     for (int q = 0; q < NC; ++q) {
-        const int j = wid + TQ_WARPS * q;
+        const int j = j0 + q;
         if (j < n) {
 #pragma unroll
             for (int t = 0; t < TQ_RPL; ++t) {
@@ -452,7 +462,7 @@ __global__ void __launch_bounds__(TQ_THREADS, 1) k_tsqr_leaf(double* __restrict_
                 if (e < n * n) {
                     const int j = e / n, i = e - j * n;
                     double t = 0.0;
-                    for (int x = 0; x < n; ++x) t += M[i + n * x] * T[x + n * j];
+                    for (int x = 0; x < n; ++x) t = fma(M[i + n * x], T[x + n * j], t);     // (a plain product of orthogonal factors: FMA is welcome)
                     acc[u] = t;
                 }
             }
@@ -478,7 +488,7 @@ __global__ void __launch_bounds__(TQ_THREADS, 1) k_tsqr_leaf(double* __restrict_
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int cc = 0; cc < 8; ++cc) acc[r][cc] += av[r] * bv[cc];
+            for (int cc = 0; cc < 8; ++cc) acc[r][cc] = fma(av[r], bv[cc], acc[r][cc]);
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r)
