@@ -188,13 +188,14 @@ def test_uniform_callback_feeds_the_host_lottery():
 
 @pytest.mark.parametrize("kind,index,n,R,piv,P", [("c", 8, 32, 12, 2, 4), ("e", 6, 24, 10, 1, 1), ("d", 7, 16, 9, 3, 3)])
 def test_sweep_schedules_agree(kind, index, n, R, piv, P, monkeypatch):
-    """overlapped quadrature + fused exchange/close (default), quadrature in line, separate exchange kernels:
-    the same pivots, per-sweep values, cores and integral, bit for bit, and all equal to the oracle."""
+    """overlapped quadrature + fused exchange/close (default), quadrature in line, separate exchange kernels, the
+    wavefront finalisation kernels instead of k_lua_fused: the same pivots, per-sweep values, cores and integral, bit for bit,
+    and all equal to the oracle."""
     p = T.drivers.ising(kind, index, n)
     t, g, o = run_both(p, R, piv, P=P)
     assert_parity(t, g, o, exact=True)
     for env in ({"TTC_QUAD_OVERLAP": "0"}, {"TTC_FUSED_SWEEP": "0"}, {"TTC_QUAD_OVERLAP": "0", "TTC_FUSED_SWEEP": "0"},
-                {"TTC_GRAPH_SWEEPS": "2"}):
+                {"TTC_GRAPH_SWEEPS": "2"}, {"TTC_NO_LUA_FUSED": "1"}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         t2 = p.make(); t2.set_partition(P); t2.set_seed(1)

@@ -475,7 +475,7 @@ class TTCross:
         special = {40: "k_visits", 100: "fold_done", 41: "v:staged", 42: "v:lot_setup", 43: "v:lot_eval", 44: "v:lot_fold",
                    45: "v:fiber_eval", 46: "v:fiber_fold", 47: "v:rook_done", 48: "v:nbr_done", 49: "v:append_done", 50: "f:xs_staged", 51: "f:pref_issued", 52: "f:eval_done",
                    53: "f:resid_done", 54: "f:stored", 55: "l:drawn", 56: "l:evaluated", 34: "k_quad_inc", 60: "q:lu_staged", 61: "q:chunk_staged", 62: "q:chunk_summed",
-                   63: "q:luar_done", 64: "q:end", 35: "k_superblock_t", 36: "k_sweeps", 70: "s:announced", 71: "s:nbr_ready",
+                   63: "q:luar_done", 64: "q:end", 35: "k_superblock_t", 36: "k_sweeps", 37: "k_lua_fused", 70: "s:announced", 71: "s:nbr_ready",
                    72: "s:exchanged", 73: "s:all_ready", 74: "s:closed", 75: "x:staged", 76: "x:corner", 77: "x:chains"}
         out = [(special.get(int(i), nm[i] if i < 64 else "?"), int(t)) for i, t in zip(ids[:n], ts[:n])]
         return sorted(out, key=lambda x: x[1])

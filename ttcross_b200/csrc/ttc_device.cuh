@@ -2113,6 +2113,132 @@ __global__ void k_lua_l_w(DevPlan P) {
     }
 }
 
+// Finalisation in ONE kernel (dtt_lua, dmrgg.f90:1169-1258): a warp owns the r0 x r1 slab arg(p)(:, j, :) of one mode index.  The slab
+// is staged in shared memory with coalesced loads (the left index is contiguous in HBM), d2_luar (lr.f90:124-137) runs down its
+// columns with one THREAD per column, d2_lual (lr.f90:139-154) along its rows with one thread per row; both packed LUs sit in
+// shared memory and are read as broadcasts.  Every output accumulates the same terms in the same ascending order as the
+// reference and as warp_luar / warp_lual -- four rows at a time share the pass over the finished prefix, which only interleaves
+// independent chains -- so the cores come out bit-identical to k_lua_r_w + k_lua_l_w, at 1/32 of their dependent steps per
+// element (a thread walks its chain out of shared memory; the wavefront kernels spend a whole warp and a shuffle per step).
+// With `pack` the finished slab also lands in the caller-bound packed copy (k_pack_all's layout), saving its pass over the cores.
+constexpr int LF_WARPS = 4;
+__host__ __device__ __forceinline__ size_t lua_fused_smem(int Rmax) {
+    return ((size_t)2 * Rmax * Rmax + Rmax + (size_t)LF_WARPS * (Rmax | 1) * Rmax) * sizeof(double);
+}
+__global__ void __launch_bounds__(32 * LF_WARPS) k_lua_fused(DevPlan P, double* pack) {
+    tl_stamp(P, 37);
+    extern __shared__ double smem[];
+    const int p = P.c_lo + blockIdx.y;
+    const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
+    const bool do_r = r0 >= 2, do_l = p < P.d;
+    if (!do_r && !do_l && !pack) return;
+    double* TL = smem;                         // TL[u*r0 + s] = g_left(s,u), u < s      (stage_luar)
+    double* TR = TL + P.Rmax * P.Rmax;         // TR[u*r1 + c] = g_right(c,u), u < c     (stage_lual)
+    double* DI = TR + P.Rmax * P.Rmax;         // 1 / pivot(c)
+    const int ld = r0 | 1;                     // odd leading dimension: a thread per column walks its column without bank conflicts
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double* S = DI + P.Rmax + (size_t)wid * (P.Rmax | 1) * P.Rmax;
+    if (do_r) stage_luar(P.inv + (i64)(p - 1) * P.Rmax * P.Rmax, r0, TL);
+    if (do_l) stage_lual(P.inv + (i64)p * P.Rmax * P.Rmax, r1, TR, DI);
+    __syncthreads();
+    i64 poff = 0;
+    if (pack) for (int k = P.c_lo; k < p; ++k) poff += (i64)P.rk[k - 1] * P.n[k] * P.rk[k];
+    double* a = P.arg + P.coreOff[p];
+    const i64 ys = (i64)P.Rmax * n;
+    for (int j = blockIdx.x * LF_WARPS + wid; j < n; j += gridDim.x * LF_WARPS) {
+        double* base = a + (i64)P.Rmax * j;
+#pragma unroll 8
+        for (int c = 0; c < r1; ++c)
+            for (int i = lane; i < r0; i += 32) S[c * ld + i] = base[i + c * ys];
+        __syncwarp();
+        if (do_r) {
+            for (int c = lane; c < r1; c += 32) {
+                double* y = S + c * ld;
+                for (int s0 = 1; s0 < r0; s0 += 4) {
+                    const int sb = min(s0 + 1, r0 - 1), sc = min(s0 + 2, r0 - 1), sd = min(s0 + 3, r0 - 1);
+                    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll 4
+                    for (int u = 0; u < s0; ++u) {
+                        const double yu = y[u];
+                        const double* g = TL + u * r0;
+                        t0 = t0 + yu * g[s0]; t1 = t1 + yu * g[sb]; t2 = t2 + yu * g[sc]; t3 = t3 + yu * g[sd];
+                    }
+                    const double y0 = y[s0] + (-t0);
+                    y[s0] = y0;
+                    if (s0 + 1 < r0) {
+                        t1 = t1 + y0 * TL[s0 * r0 + s0 + 1];
+                        const double y1 = y[s0 + 1] + (-t1);
+                        y[s0 + 1] = y1;
+                        if (s0 + 2 < r0) {
+                            t2 = t2 + y0 * TL[s0 * r0 + s0 + 2];
+                            t2 = t2 + y1 * TL[(s0 + 1) * r0 + s0 + 2];
+                            const double y2 = y[s0 + 2] + (-t2);
+                            y[s0 + 2] = y2;
+                            if (s0 + 3 < r0) {
+                                t3 = t3 + y0 * TL[s0 * r0 + s0 + 3];
+                                t3 = t3 + y1 * TL[(s0 + 1) * r0 + s0 + 3];
+                                t3 = t3 + y2 * TL[(s0 + 2) * r0 + s0 + 3];
+                                y[s0 + 3] = y[s0 + 3] + (-t3);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (do_l) {
+            for (int i = lane; i < r0; i += 32) {
+                double* y = S + i;          // y(c) = y[c*ld]
+                y[0] = DI[0] * y[0];
+                for (int c0 = 1; c0 < r1; c0 += 4) {
+                    const int cb = min(c0 + 1, r1 - 1), cc = min(c0 + 2, r1 - 1), cd = min(c0 + 3, r1 - 1);
+                    double v0 = y[c0 * ld], v1 = y[cb * ld], v2 = y[cc * ld], v3 = y[cd * ld];
+#pragma unroll 4
+                    for (int u = 0; u < c0; ++u) {
+                        const double yu = y[u * ld];
+                        const double* g = TR + u * r1;
+                        v0 = v0 + (-g[c0]) * yu; v1 = v1 + (-g[cb]) * yu; v2 = v2 + (-g[cc]) * yu; v3 = v3 + (-g[cd]) * yu;
+                    }
+                    v0 = DI[c0] * v0;
+                    y[c0 * ld] = v0;
+                    if (c0 + 1 < r1) {
+                        v1 = v1 + (-TR[c0 * r1 + c0 + 1]) * v0;
+                        v1 = DI[c0 + 1] * v1;
+                        y[(c0 + 1) * ld] = v1;
+                        if (c0 + 2 < r1) {
+                            v2 = v2 + (-TR[c0 * r1 + c0 + 2]) * v0;
+                            v2 = v2 + (-TR[(c0 + 1) * r1 + c0 + 2]) * v1;
+                            v2 = DI[c0 + 2] * v2;
+                            y[(c0 + 2) * ld] = v2;
+                            if (c0 + 3 < r1) {
+                                v3 = v3 + (-TR[c0 * r1 + c0 + 3]) * v0;
+                                v3 = v3 + (-TR[(c0 + 1) * r1 + c0 + 3]) * v1;
+                                v3 = v3 + (-TR[(c0 + 2) * r1 + c0 + 3]) * v2;
+                                v3 = DI[c0 + 3] * v3;
+                                y[(c0 + 3) * ld] = v3;
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (do_r || do_l) {
+#pragma unroll 8
+            for (int c = 0; c < r1; ++c)
+                for (int i = lane; i < r0; i += 32) base[i + c * ys] = S[c * ld + i];
+        }
+        if (pack) {
+            double* o = pack + poff + (i64)r0 * j;
+            const i64 os = (i64)r0 * n;
+#pragma unroll 8
+            for (int c = 0; c < r1; ++c)
+                for (int i = lane; i < r0; i += 32) o[i + c * os] = S[c * ld + i];
+        }
+        __syncwarp();
+    }
+}
+
 // factors of the initial cross (dmrgg.f90:234-248): inv(p)(1) = pivot, col(p) = arg(p)/pivot (d2_lual, r = 1),
 // row(p) = arg(p) (d2_luar with r = 1 is the identity).  blockIdx.y = core - 1.
 __global__ void k_init_factors(DevPlan P) {
@@ -2372,5 +2498,5 @@ __global__ void k_mp_unpack2(DevPlan P, int final) {
     }
 }
 
-static const char* const tl_names[] = {"k_lot", "k_fiber", "k_superblock", "k_accept", "k_update_main", "k_update_nbr", "k_allreduce", "k_run_begin", "k_sweep_log", "k_exchange_corner", "k_exchange_extend", "k_quad_contract", "k_quad_lua", "k_quad_chain", "k_quad_tree", "k_lua_r", "k_lua_l", "k_pack_core", "k_init_search", "k_init_cross", "k_quad_contract_sm", "k_quad_lua_sm", "k_quad_chain_sm", "k_quad_tree_sm", "k_update_nbr_w", "k_exchange_extend_w", "k_lua_r_w", "k_lua_l_w", "k_init_factors", "k_mp_pack1", "k_mp_unpack1", "k_mp_unpack1b", "k_mp_pack2", "k_mp_unpack2", "k_quad_inc", "k_sweeps"};
+static const char* const tl_names[] = {"k_lot", "k_fiber", "k_superblock", "k_accept", "k_update_main", "k_update_nbr", "k_allreduce", "k_run_begin", "k_sweep_log", "k_exchange_corner", "k_exchange_extend", "k_quad_contract", "k_quad_lua", "k_quad_chain", "k_quad_tree", "k_lua_r", "k_lua_l", "k_pack_core", "k_init_search", "k_init_cross", "k_quad_contract_sm", "k_quad_lua_sm", "k_quad_chain_sm", "k_quad_tree_sm", "k_update_nbr_w", "k_exchange_extend_w", "k_lua_r_w", "k_lua_l_w", "k_init_factors", "k_mp_pack1", "k_mp_unpack1", "k_mp_unpack1b", "k_mp_pack2", "k_mp_unpack2", "k_quad_inc", "k_superblock_t", "k_sweeps", "k_lua_fused"};
 }  // namespace ttc

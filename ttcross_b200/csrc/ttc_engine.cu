@@ -126,6 +126,7 @@ struct ttc_handle {
     std::vector<cudaEvent_t> ev_fork, ev_join;         // main -> quadrature stream / back, one pair per sweep of a graph
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t evs0 = nullptr, evs1 = nullptr;        // around the persistent sweep kernel
+    cudaEvent_t ev_lua = nullptr, ev_bind = nullptr;   // finalised cores packed / bound cores delivered (early copy-out on stream_q)
     double sweep_ms = 0; int persistent_used = 0;
     char* log_h = nullptr; size_t log_cap = 0;       // pinned mirror of ctrl | slog | rklog | vlog | rk (one synchronisation for all logs)
     bool quad_cached = false; double quad_value = 0;   // dtt_quad of the finalised train, taken at the end of ttc_dmrgg (one process)
@@ -142,6 +143,7 @@ struct ttc_handle {
     long long graph_kc[2][16] = {{0}};
     long long setup_serial = 0;
     int no_graph = 0;
+    bool lua_fused_ok = false;           // k_lua_fused replaces k_lua_r_w + k_lua_l_w (+ k_pack_all) when its slabs fit in shared memory
     bool use_wave = true;                // warp-wavefront / shared-memory support kernels (needs Rmax <= 32*MAXRPL)
     size_t sm_contract = 0, sm_lua = 0, sm_mat3 = 0, sm_ext = 0, sm_lot = 0, sm_fiber = 0, sm_sb = 0;
     size_t sm_xf = 0; bool xf_ok = false;             // k_exchange_fused: aux | 2 d | two staged LU tables
@@ -357,6 +359,8 @@ void free_device(ttc_handle* h) {
     if (h->ev1) { cudaEventDestroy(h->ev1); h->ev1 = nullptr; }
     if (h->evs0) { cudaEventDestroy(h->evs0); h->evs0 = nullptr; }
     if (h->evs1) { cudaEventDestroy(h->evs1); h->evs1 = nullptr; }
+    if (h->ev_lua) { cudaEventDestroy(h->ev_lua); h->ev_lua = nullptr; }
+    if (h->ev_bind) { cudaEventDestroy(h->ev_bind); h->ev_bind = nullptr; }
     for (cudaEvent_t e : h->ev_fork) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_join) cudaEventDestroy(e);
     h->ev_fork.clear(); h->ev_join.clear();
@@ -369,6 +373,7 @@ void free_device(ttc_handle* h) {
 struct Launcher {
     ttc_handle* h;
     cudaEvent_t a = nullptr, b = nullptr;
+    const bool trace = std::getenv("TTC_TRACE") != nullptr;
     explicit Launcher(ttc_handle* hh) : h(hh) {
         if (h->profile) { cudaEventCreate(&a); cudaEventCreate(&b); }
     }
@@ -379,6 +384,10 @@ struct Launcher {
         f();
         h->launches += 1;
         h->kc_launch[kc] += 1;
+        if (trace) {        // TTC_TRACE: name the launch a configuration error belongs to (the error itself stays pending for the caller)
+            const cudaError_t e = cudaPeekAtLastError();
+            if (e != cudaSuccess) std::fprintf(stderr, "[ttc trace] launch %lld (class %d): %s\n", (long long)h->launches, (int)kc, cudaGetErrorString(e));
+        }
         if (h->profile) {
             cudaEventRecord(b, h->stream);
             cudaEventSynchronize(b);
@@ -485,6 +494,8 @@ int setup_device(ttc_handle* h, int maxrank) {
     CUDA_TRY(h, cudaEventCreate(&h->ev1));
     CUDA_TRY(h, cudaEventCreate(&h->evs0));
     CUDA_TRY(h, cudaEventCreate(&h->evs1));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_lua, cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_bind, cudaEventDisableTiming));
 
     const int d = h->d, P = h->P;
     h->Rmax = maxrank > 0 ? maxrank : 64;
@@ -653,6 +664,9 @@ int setup_device(ttc_handle* h, int maxrank) {
             cudaFuncSetAttribute(k_lua_r_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_ext);
             cudaFuncSetAttribute(k_lua_l_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_ext);
         }
+        // fused finalisation (k_lua_fused): both packed LUs + one slab per warp in shared memory
+        h->lua_fused_ok = !h->force_simple && lua_fused_smem(Rmax) <= 200 * 1024 && !std::getenv("TTC_NO_LUA_FUSED");
+        if (h->lua_fused_ok) cudaFuncSetAttribute(k_lua_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lua_fused_smem(Rmax));
     }
     // tiled superblock kernel (ttc_superblock.cuh): column-factor slab + per-tile tables in shared memory
     {
@@ -788,18 +802,18 @@ int setup_device(ttc_handle* h, int maxrank) {
     {
         const int bl = (int)h->sm_lot, bf = (int)h->sm_fiber, bs = (int)h->sm_sb, ba = (int)aux_smem(h);
         KIND_SWITCH(h->kind,
-            if (bl > 48 * 1024) cudaFuncSetAttribute(k_lot<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, bl);
-            if (bf > 48 * 1024) { cudaFuncSetAttribute(k_fiber<K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf);
+            if (bl > 32 * 1024) cudaFuncSetAttribute(k_lot<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, bl);
+            if (bf > 32 * 1024) { cudaFuncSetAttribute(k_fiber<K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf);
                                   cudaFuncSetAttribute(k_fiber<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf); }
-            if (bs > 48 * 1024) { cudaFuncSetAttribute(k_superblock<K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs);
+            if (bs > 32 * 1024) { cudaFuncSetAttribute(k_superblock<K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs);
                                   cudaFuncSetAttribute(k_superblock<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs); }
-            if (ba + 16 * h->d > 48 * 1024) cudaFuncSetAttribute(k_exchange_corner<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba + 16 * h->d);
+            if (ba + 16 * h->d > 32 * 1024) cudaFuncSetAttribute(k_exchange_corner<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba + 16 * h->d);
             {
                 h->sm_xf = (size_t)ba + ((size_t)2 * h->d + (size_t)2 * h->Rmax * h->Rmax + h->Rmax) * sizeof(double);
                 h->xf_ok = h->sm_xf <= (size_t)200 * 1024 &&
                            cudaFuncSetAttribute(k_exchange_fused<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_xf) == cudaSuccess;
             }
-            if (ba > 48 * 1024) {
+            if (ba > 32 * 1024) {
                                   cudaFuncSetAttribute(k_init_search<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba);
                                   cudaFuncSetAttribute(k_init_cross<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba); }
         );
@@ -1018,9 +1032,18 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         KIND_SWITCH(h->kind, L(KC_INIT, [&] { k_init_cross<K><<<dim3(cdiv(h->nmax, TB), d), TB, smA, s>>>(D); }));
         L(KC_INIT, [&] { k_init_factors<<<dim3(cdiv(h->nmax, 256), d), 256, 0, s>>>(D); });
         {
-            const size_t smi = (size_t)d * h->nmax * sizeof(double);
-            if (smi > 48 * 1024) cudaFuncSetAttribute(k_init_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smi);
-            L(KC_INIT, [&] { k_init_state<<<1, 1024, smi, s>>>(D, nn, snum, h->init_scal, h->init_ind0, has_quad ? 1 : 0); });
+            const size_t smf = (size_t)d * h->nmax * sizeof(double);
+            const int stage_w = (has_quad && 2 * smf <= 200 * 1024) ? 1 : 0;       // quadrature weights staged beside the fibers
+            const size_t smi = stage_w ? 2 * smf : smf;
+            // the 48 KB default covers static + dynamic shared memory together (the kernel holds ~9 KB of static tables)
+            if (smi > 32 * 1024) CUDA_TRY(h, cudaFuncSetAttribute(k_init_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smi));
+            if (std::getenv("TTC_TRACE")) {
+                cudaFuncAttributes fa{};
+                cudaFuncGetAttributes(&fa, k_init_state);
+                std::fprintf(stderr, "[ttc trace] k_init_state: dynamic %zu B (weights staged: %d), static %zu B, opt-in %d B, regs %d, max threads %d\n", smi, stage_w,
+                             fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.numRegs, fa.maxThreadsPerBlock);
+            }
+            L(KC_INIT, [&] { k_init_state<<<1, 1024, smi, s>>>(D, nn, snum, h->init_scal, h->init_ind0, has_quad ? 1 : 0, stage_w); });
         }
         h->rk_h.assign(d + 2, 1); h->rks_h.assign(d + 2, 1);
         h->rng_k.assign(P, 0);
@@ -1450,34 +1473,15 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     { int e = quad_rejoin(); if (e) return e; }      // (eager mode; a graph rejoins at its end) the finalisation rewrites the cores
     // ---- finalise (dmrgg.f90:1028-1029); not gated by the ready flag.  Each process finalises the cores it owns.
     const int ncore_own = D.c_hi - D.c_lo + 1;
-    if (h->use_wave) {
-        L(KC_FINAL, [&] { k_lua_r_w<<<dim3(std::min(512, cdiv((i64)h->nmax * Rmax, 8)), ncore_own), 256, h->sm_ext, s>>>(D); });
-        L(KC_FINAL, [&] { k_lua_l_w<<<dim3(std::min(512, cdiv((i64)h->nmax * Rmax, 8)), ncore_own), 256, h->sm_ext, s>>>(D); });
-    } else {
-        L(KC_FINAL, [&] { k_lua_r<<<dim3(cdiv((i64)h->nmax * Rmax, 128), ncore_own), 128, 0, s>>>(D); });
-        L(KC_FINAL, [&] { k_lua_l<<<dim3(cdiv((i64)h->nmax * Rmax, 128), ncore_own), 128, 0, s>>>(D); });
-    }
-    if (persist_quad_pending) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_join[0], 0));      // the per-sweep values are part of the run
-    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
-    // Every reference driver follows dtt_dmrgg with dtt_quad of the finalised train (test_crs_ising.f90:158): with one process
-    // its few small kernels are enqueued right here (after the timed region of ttc_device_ms) and ttc_quad returns the value
-    // without another launch + synchronisation round.
-    h->quad_cached = false;
-    if (h->nproc == 1) {
-        int stq = launch_quad(h, L, false, !h->quad.empty(), 1);
-        if (stq) return stq;
-        CUDA_TRY(h, cudaMemcpyAsync(h->sweep_h, h->plan.sweep_out, sizeof(SweepOut), cudaMemcpyDeviceToHost, s));
-    }
-    // ttc_bind_cores: the packed copy of this process's cores is formed on the device right here, with offsets from the device-side
-    // ranks; its transfer into the caller's buffer starts as soon as the logs (which carry the ranks) have arrived, and runs
-    // beside the host's log processing below
+    // ttc_bind_cores: the packed copy of this process's cores is formed on the device right here (by the fused finalisation
+    // kernel, else by k_pack_all below), with offsets from the device-side ranks; its transfer into the caller's buffer starts
+    // as soon as the logs (which carry the ranks) have arrived, and runs beside the host's log processing below
     h->bind_filled = false;
     const bool bound = h->bind_out != nullptr;
     if (bound) {
         size_t capcnt = 0;
         for (int k = D.c_lo; k <= D.c_hi; ++k) capcnt += (size_t)std::min<i64>(Rmax, k == 1 ? 1 : Rmax) * h->n[k] * std::min<i64>(Rmax, k == d ? 1 : Rmax);
         { int st = ensure_pack(h, capcnt, !h->bind_pinned); if (st) return st; }
-        L(KC_FINAL, [&] { k_pack_all<<<dim3(std::min(256, cdiv((i64)Rmax * h->nmax * Rmax, 256)), ncore_own), 256, 0, s>>>(D, h->pack_d); });
     }
     // the logs travel with the same synchronisation: ctrl | slog | rklog | vlog | rk into one pinned block (capacity-sized)
     const size_t lb_ctrl = 0, lb_slog = 256, lb_rklog = lb_slog + (((size_t)(Rmax + 1) * sizeof(SweepOut) + 63) & ~(size_t)63),
@@ -1490,20 +1494,69 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         h->host_blocks.push_back({q, lb_tot});
         h->log_h = (char*)q; h->log_cap = lb_tot;
     }
+    const bool lua_fused = h->lua_fused_ok;
+    if (lua_fused) {
+        L(KC_FINAL, [&] { k_lua_fused<<<dim3(cdiv(h->nmax, LF_WARPS), ncore_own), 32 * LF_WARPS, lua_fused_smem(Rmax), s>>>(D, bound ? h->pack_d : nullptr); });
+    } else if (h->use_wave) {
+        L(KC_FINAL, [&] { k_lua_r_w<<<dim3(std::min(512, cdiv((i64)h->nmax * Rmax, 8)), ncore_own), 256, h->sm_ext, s>>>(D); });
+        L(KC_FINAL, [&] { k_lua_l_w<<<dim3(std::min(512, cdiv((i64)h->nmax * Rmax, 8)), ncore_own), 256, h->sm_ext, s>>>(D); });
+    } else {
+        L(KC_FINAL, [&] { k_lua_r<<<dim3(cdiv((i64)h->nmax * Rmax, 128), ncore_own), 128, 0, s>>>(D); });
+        L(KC_FINAL, [&] { k_lua_l<<<dim3(cdiv((i64)h->nmax * Rmax, 128), ncore_own), 128, 0, s>>>(D); });
+    }
+    // Early copy-out of bound cores: k_lua_fused has packed them already, so the final ranks travel right now and the transfer
+    // into the caller's buffer is enqueued on the second stream as soon as they are known -- beside the closing quadrature and
+    // the log transfers instead of behind them.
+    const bool early_bind = bound && lua_fused && h->stream_q != nullptr;
+    if (early_bind) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->log_h + lb_rk, D.rk, (size_t)(d + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaEventRecord(h->ev_lua, s));
+    }
+    if (persist_quad_pending) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_join[0], 0));      // the per-sweep values are part of the run
+    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    // Every reference driver follows dtt_dmrgg with dtt_quad of the finalised train (test_crs_ising.f90:158): with one process
+    // its few small kernels are enqueued right here (after the timed region of ttc_device_ms) and ttc_quad returns the value
+    // without another launch + synchronisation round.
+    h->quad_cached = false;
+    if (h->nproc == 1) {
+        int stq = launch_quad(h, L, false, !h->quad.empty(), 1);
+        if (stq) return stq;
+        CUDA_TRY(h, cudaMemcpyAsync(h->sweep_h, h->plan.sweep_out, sizeof(SweepOut), cudaMemcpyDeviceToHost, s));
+    }
+    if (bound && !lua_fused)
+        L(KC_FINAL, [&] { k_pack_all<<<dim3(std::min(256, cdiv((i64)Rmax * h->nmax * Rmax, 256)), ncore_own), 256, 0, s>>>(D, h->pack_d); });
     CUDA_TRY(h, cudaMemcpyAsync(h->log_h + lb_ctrl, D.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaMemcpyAsync(h->log_h + lb_slog, D.slog, (size_t)(Rmax + 1) * sizeof(SweepOut), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaMemcpyAsync(h->log_h + lb_rklog, D.rklog, (size_t)(Rmax + 1) * (d + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaMemcpyAsync(h->log_h + lb_vlog, D.vlog, (size_t)Rmax * maxnb * P * sizeof(VisitOut), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(h, cudaMemcpyAsync(h->log_h + lb_rk, D.rk, (size_t)(d + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(h, cudaStreamSynchronize(s));
-    CUDA_TRY(h, cudaGetLastError());
-    if (h->nproc == 1) { h->quad_value = h->sweep_h->val; h->quad_cached = true; }
+    if (!early_bind) CUDA_TRY(h, cudaMemcpyAsync(h->log_h + lb_rk, D.rk, (size_t)(d + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
     size_t bind_tot = 0;
-    bool bind_small = false;
-    if (bound) {
+    bool bind_small = false, bind_on_q = false;
+    auto bind_size = [&]() {
         const int* rkd = (const int*)(h->log_h + lb_rk);
         for (int k = D.c_lo; k <= D.c_hi; ++k) bind_tot += (size_t)rkd[k - 1] * h->n[k] * rkd[k];
         bind_small = (long long)bind_tot > h->bind_cap;
+    };
+    if (early_bind) {
+        CUDA_TRY(h, cudaEventSynchronize(h->ev_lua));
+        bind_size();
+        if (!bind_small && bind_tot > 0) {
+            CUDA_TRY(h, cudaStreamWaitEvent(h->stream_q, h->ev_lua, 0));
+            // in pieces of 2 MB: the small log transfers of the main stream slip in between them instead of queueing behind 13 MB
+            char* dst = (char*)(h->bind_pinned ? h->bind_out : h->stage_h);
+            const char* src = (const char*)h->pack_d;
+            const size_t nbytes = bind_tot * sizeof(double), piece = (size_t)2 << 20;
+            for (size_t o = 0; o < nbytes; o += piece)
+                CUDA_TRY(h, cudaMemcpyAsync(dst + o, src + o, std::min(piece, nbytes - o), cudaMemcpyDeviceToHost, h->stream_q));
+            CUDA_TRY(h, cudaEventRecord(h->ev_bind, h->stream_q));
+            bind_on_q = true;                                         // awaited below, after the host's log processing
+        }
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    CUDA_TRY(h, cudaGetLastError());
+    if (h->nproc == 1) { h->quad_value = h->sweep_h->val; h->quad_cached = true; }
+    if (bound && !early_bind) {
+        bind_size();
         if (!bind_small && bind_tot > 0)
             CUDA_TRY(h, cudaMemcpyAsync(h->bind_pinned ? h->bind_out : h->stage_h, h->pack_d, bind_tot * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
@@ -1512,6 +1565,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     // ---- read the logs back and rebuild the reference's report
     Ctrl ctrl;
     std::memcpy(&ctrl, h->log_h + lb_ctrl, sizeof ctrl);
+    if (ctrl.error && bind_on_q) cudaEventSynchronize(h->ev_bind);        // no transfer in flight behind an error return
     if (ctrl.error == 3) { h->err = "multi-GPU exchange timed out waiting for a peer rank"; return TTC_ERR_COMM; }
     if (ctrl.error == 2) { h->err = "internal: the incremental quadrature saw a rank grow by more than one in a sweep"; return TTC_ERR_STATE; }
     if (ctrl.error) { h->err = "rank capacity exceeded (pass maxrank)"; return TTC_ERR_RANK; }
@@ -1577,7 +1631,8 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     if (persistent) { float sm = 0; cudaEventElapsedTime(&sm, h->evs0, h->evs1); h->sweep_ms = sm; }
     h->neval = nevalall;
     if (bound && !bind_small) {
-        CUDA_TRY(h, cudaStreamSynchronize(s));
+        if (bind_on_q) CUDA_TRY(h, cudaEventSynchronize(h->ev_bind));
+        else CUDA_TRY(h, cudaStreamSynchronize(s));
         if (!h->bind_pinned) std::memcpy(h->bind_out, h->stage_h, bind_tot * sizeof(double));
         h->bind_filled = true; h->bind_count = bind_tot;
         tr.lap("bound cores");
@@ -2109,7 +2164,7 @@ int ttc_svd(ttc_handle* h, double tol, int rmax) {
         e = qr_launch(s, h->nsm, T, (int)nn, mm, Q, Rm, sc);
         if (e != cudaSuccess) break;
         const size_t smem = (2 * (size_t)mm * mm + 2 * (size_t)mm) * sizeof(double) + (2 * (size_t)mm + 4) * sizeof(int);
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_svd_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > 32 * 1024) cudaFuncSetAttribute(k_svd_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_svd_small<<<1, 32 * std::max(1, std::min(32, (mm + 1) / 2)), smem, s>>>(Rm, mm, U, sv, W);
         std::vector<double> svh(mm);
         e = cudaMemcpyAsync(svh.data(), sv, mm * sizeof(double), cudaMemcpyDeviceToHost, s);
@@ -2262,7 +2317,7 @@ int ttc_accchk(ttc_handle* h, long long nlot, unsigned long long seed, double* o
     const size_t smem = aux_smem(h) + (size_t)nw * (2 * h->Rmax + h->d) * sizeof(double);
     if (e == cudaSuccess) {
         KIND_SWITCH(h->kind,
-            if (smem > 48 * 1024) cudaFuncSetAttribute(k_accchk<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (smem > 32 * 1024) cudaFuncSetAttribute(k_accchk<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             k_accchk<K><<<grid, 32 * nw, smem, h->stream>>>(h->plan, nlot, seed, dpart, darg));
         h->launches += 1;
         e = cudaGetLastError();

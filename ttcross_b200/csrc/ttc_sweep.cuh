@@ -773,24 +773,35 @@ __global__ void k_init_pick(DevPlan P, int nn, int snum, const double* b, double
         if (pos < d - p) P.Ridx[P.offR[p] + (i64)pos * Rmax] = I0(p + pos + 1);
     }
 }
-__global__ void k_init_state(DevPlan P, int nn, int snum, const double* scal, const int* ind0, int has_quad) {
+__global__ void k_init_state(DevPlan P, int nn, int snum, const double* scal, const int* ind0, int has_quad, int stage_w) {
     extern __shared__ double fibs[];                      // fibs[(p-1) * nmax + j]: the initial fiber of every core, staged by all threads
-    __shared__ double s_dot[MAXD_LOCAL * 8 + 2], s_part[64];
+    __shared__ double s_dot[MAXD_LOCAL * 8 + 2], s_part[64], s_am[MAXD_LOCAL * 8 + 2];
     const int d = P.d, NP = P.P;
     const double gmax = scal[0];
+    double* wsm = fibs + (size_t)d * P.nmax;              // the weights beside them (stage_w): the ordered sums below never wait for HBM
     for (int x = threadIdx.x; x < d * P.nmax; x += blockDim.x) {
         const int p = x / P.nmax + 1, j = x - (p - 1) * P.nmax;
         fibs[x] = (j < P.n[p]) ? P.arg[P.coreOff[p] + (i64)P.Rmax * j] : 0.0;
+        if (has_quad && stage_w) wsm[x] = (j < P.n[p]) ? P.quadw[P.quadOff[p] + j] : 0.0;
     }
     __syncthreads();
     // ddot(fiber(p), quad(p)) per core, sequential in j like the reference's ddot (out of shared memory: no load latency on the chain)
     for (int p = 1 + threadIdx.x; p <= d; p += blockDim.x) {
         double t = 0.0;
         if (has_quad && p < (int)(sizeof(s_dot) / sizeof(double))) {
-            const double* a = fibs + (size_t)(p - 1) * P.nmax; const double* w = P.quadw + P.quadOff[p];
+            const double* a = fibs + (size_t)(p - 1) * P.nmax;
+            const double* w = stage_w ? wsm + (size_t)(p - 1) * P.nmax : P.quadw + P.quadOff[p];
             for (int j = 0; j < P.n[p]; ++j) t = t + a[j] * w[j];
             s_dot[p] = t;
         }
+    }
+    // max |fiber(p)| per core: a warp per core (a maximum does not depend on the order)
+    for (int p = 1 + (int)(threadIdx.x >> 5); p <= d && p < (int)(sizeof(s_am) / sizeof(double)); p += (int)(blockDim.x >> 5)) {
+        const double* a = fibs + (size_t)(p - 1) * P.nmax;
+        double am = 0.0;
+        for (int j = threadIdx.x & 31; j < P.n[p]; j += 32) am = fmax(am, fabs(a[j]));
+        for (int o = 16; o; o >>= 1) am = fmax(am, __shfl_xor_sync(0xffffffffu, am, o));
+        if ((threadIdx.x & 31) == 0) s_am[p] = am;
     }
     __syncthreads();
     for (int v = threadIdx.x; v < NP; v += blockDim.x) {
@@ -799,8 +810,8 @@ __global__ void k_init_state(DevPlan P, int nn, int snum, const double* scal, co
         long long ne = (long long)nn * (s1 - s0);
         for (int p = P.own[v]; p <= P.own[v + 1]; ++p) {
             ne += P.n[p];
-            const double* a = fibs + (size_t)(p - 1) * P.nmax;
-            for (int j = 0; j < P.n[p]; ++j) am = fmax(am, fabs(a[j]));
+            if (p < (int)(sizeof(s_am) / sizeof(double))) am = fmax(am, s_am[p]);
+            else { const double* a = fibs + (size_t)(p - 1) * P.nmax; for (int j = 0; j < P.n[p]; ++j) am = fmax(am, fabs(a[j])); }
         }
         VState S;
         S.ii = S.jj = S.kk = S.qq = 0; S.pivot = 0.0; S.done = S.havecol = S.haverow = S.crs = 0; S.upd = 0; S.pad0 = 0;
