@@ -1707,29 +1707,49 @@ __device__ __forceinline__ void stage_lual(const double* g, int r, double* T, do
 // ----------------------------------------------------------------------------
 // quadrature, shared-memory versions (same arithmetic as k_quad_contract / k_quad_lua / k_quad_chain / k_quad_tree)
 // ----------------------------------------------------------------------------
-// ttqq(p)(i,k) = sum_j arg(p)(i,j,k)*w(j): CTA (k, p) stages the slice arg(p)(:,:,k) chunk by chunk with all threads
-// (deep memory-level parallelism), then r0 threads run the ordered sums out of shared memory.
-__global__ void k_quad_contract_sm(DevPlan P, int use_weights, int chunk_doubles) {
+// ttqq(p)(i,k) = sum_j arg(p)(i,j,k)*w(j), j ascending (dgemv order, dmrgg.f90:986-991).  A warp owns one k, a lane one i: the
+// left index is contiguous in HBM, so every step of the ordered sum is one coalesced 256 B row; the rows are fetched QC_U at a
+// time into registers, the next batch in flight while the current one is summed, so the dependent additions never wait for
+// L2.  Two warps per CTA spread the 13 MB of config B over all SMs.  (The first version staged a whole slice in shared memory
+// with 256 threads and let r0 of them do the sums: 28 us per launch at config B, two launches per run.)
+constexpr int QC_U = 32, QC_WARPS = 2;
+__global__ void __launch_bounds__(32 * QC_WARPS) k_quad_contract_sm(DevPlan P, int use_weights) {
     tl_stamp(P, 20);
-    extern __shared__ double smem[];
-    const int p = P.c_lo + blockIdx.y, k = blockIdx.x;
+    extern __shared__ double smem[];           // the weights of this core (nmax doubles)
+    const int p = P.c_lo + blockIdx.y;
     const int r0 = P.rk[p - 1], r1 = P.rk[p], n = P.n[p];
+    if (use_weights) { const double* w = P.quadw + P.quadOff[p]; for (int j = threadIdx.x; j < n; j += blockDim.x) smem[j] = w[j]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, k = blockIdx.x * QC_WARPS + (threadIdx.x >> 5);
     if (k >= r1) return;
-    const double* a = P.arg + P.coreOff[p] + (i64)P.Rmax * n * k;
-    const double* w = P.quadw + P.quadOff[p];
-    int Jc = chunk_doubles / r0; if (Jc > n) Jc = n;
-    double y = 0.0;
-    for (int j0 = 0; j0 < n; j0 += Jc) {
-        const int jc = min(Jc, n - j0);
-        for (int e = threadIdx.x; e < r0 * jc; e += blockDim.x) { int jj = e / r0, i = e - jj * r0; smem[e] = a[i + (i64)P.Rmax * (j0 + jj)]; }
-        __syncthreads();
-        if (threadIdx.x < r0) {
-            if (use_weights) for (int jj = 0; jj < jc; ++jj) y = y + w[j0 + jj] * smem[threadIdx.x + r0 * jj];
-            else             for (int jj = 0; jj < jc; ++jj) y = y + smem[threadIdx.x + r0 * jj];
+    const i64 ld = P.Rmax;
+    for (int i = lane; i < r0; i += 32) {
+        const double* a = P.arg + P.coreOff[p] + ld * n * k + i;
+        double y = 0.0, cur[QC_U], nxt[QC_U];
+        const int nb = n / QC_U;
+        if (nb > 0) {
+#pragma unroll
+            for (int u = 0; u < QC_U; ++u) cur[u] = a[ld * u];
         }
-        __syncthreads();
+        for (int b = 0; b < nb; ++b) {
+            const int j0 = b * QC_U;
+            if (b + 1 < nb) {
+#pragma unroll
+                for (int u = 0; u < QC_U; ++u) nxt[u] = a[ld * (j0 + QC_U + u)];
+            }
+            if (use_weights) {
+#pragma unroll
+                for (int u = 0; u < QC_U; ++u) y = y + smem[j0 + u] * cur[u];
+            } else {
+#pragma unroll
+                for (int u = 0; u < QC_U; ++u) y = y + cur[u];
+            }
+#pragma unroll
+            for (int u = 0; u < QC_U; ++u) cur[u] = nxt[u];
+        }
+        for (int j = nb * QC_U; j < n; ++j) y = use_weights ? y + smem[j] * a[ld * j] : y + a[ld * j];
+        P.ttqq[(i64)p * P.Rmax * P.Rmax + i + ld * k] = y;
     }
-    if (threadIdx.x < r0) P.ttqq[(i64)p * P.Rmax * P.Rmax + threadIdx.x + (i64)P.Rmax * k] = y;
 }
 // dtt_lua on the contracted cores: one CTA per core, matrix and both packed LUs staged in shared memory,
 // one warp per column (d2_luar) then one warp per row (d2_lual).  Requires r <= 32*MAXRPL.

@@ -126,7 +126,6 @@ struct ttc_handle {
     std::vector<cudaEvent_t> ev_fork, ev_join;         // main -> quadrature stream / back, one pair per sweep of a graph
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t evs0 = nullptr, evs1 = nullptr;        // around the persistent sweep kernel
-    cudaEvent_t ev_lua = nullptr, ev_bind = nullptr;   // finalised cores packed / bound cores delivered (early copy-out on stream_q)
     double sweep_ms = 0; int persistent_used = 0;
     char* log_h = nullptr; size_t log_cap = 0;       // pinned mirror of ctrl | slog | rklog | vlog | rk (one synchronisation for all logs)
     bool quad_cached = false; double quad_value = 0;   // dtt_quad of the finalised train, taken at the end of ttc_dmrgg (one process)
@@ -359,8 +358,6 @@ void free_device(ttc_handle* h) {
     if (h->ev1) { cudaEventDestroy(h->ev1); h->ev1 = nullptr; }
     if (h->evs0) { cudaEventDestroy(h->evs0); h->evs0 = nullptr; }
     if (h->evs1) { cudaEventDestroy(h->evs1); h->evs1 = nullptr; }
-    if (h->ev_lua) { cudaEventDestroy(h->ev_lua); h->ev_lua = nullptr; }
-    if (h->ev_bind) { cudaEventDestroy(h->ev_bind); h->ev_bind = nullptr; }
     for (cudaEvent_t e : h->ev_fork) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_join) cudaEventDestroy(e);
     h->ev_fork.clear(); h->ev_join.clear();
@@ -494,8 +491,6 @@ int setup_device(ttc_handle* h, int maxrank) {
     CUDA_TRY(h, cudaEventCreate(&h->ev1));
     CUDA_TRY(h, cudaEventCreate(&h->evs0));
     CUDA_TRY(h, cudaEventCreate(&h->evs1));
-    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_lua, cudaEventDisableTiming));
-    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_bind, cudaEventDisableTiming));
 
     const int d = h->d, P = h->P;
     h->Rmax = maxrank > 0 ? maxrank : 64;
@@ -641,8 +636,7 @@ int setup_device(ttc_handle* h, int maxrank) {
     {
         const size_t R = (size_t)Rmax;
         h->use_wave = (Rmax <= 32 * MAXRPL) && !h->force_simple;
-        h->sm_contract = std::min<size_t>(R * h->nmax * sizeof(double), 96 * 1024);
-        h->sm_contract = std::max<size_t>(h->sm_contract, R * sizeof(double));
+        h->sm_contract = (size_t)h->nmax * sizeof(double);      // k_quad_contract_sm: the weights of one core
         h->sm_lua = (3 * R * R + R) * sizeof(double);
         h->sm_mat3 = 3 * R * R * sizeof(double);
         h->sm_ext = (R * R + R) * sizeof(double);
@@ -655,7 +649,7 @@ int setup_device(ttc_handle* h, int maxrank) {
             if (h->use_wave) cudaFuncSetAttribute(k_quad_inc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_qinc);
         }
         if (h->use_wave) {
-            cudaFuncSetAttribute(k_quad_contract_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_contract);
+            if (h->sm_contract > 32 * 1024) cudaFuncSetAttribute(k_quad_contract_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_contract);
             cudaFuncSetAttribute(k_quad_lua_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_lua);
             cudaFuncSetAttribute(k_quad_chain_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_mat3);
             cudaFuncSetAttribute(k_quad_tree_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_mat3);
@@ -937,7 +931,7 @@ int launch_quad(ttc_handle* h, Launcher& L, bool with_lua, bool use_weights, int
         // per-sweep path: only the new row / column of every contracted core (k_quad_inc)
         L(KC_QUAD, [&] { k_quad_inc<<<ncore, QINC_THREADS, h->sm_qinc, s>>>(D, use_weights ? 1 : 0, h->qinc_stage, ovl); });
     } else {
-        L(KC_QUAD, [&] { k_quad_contract_sm<<<dim3(R, ncore), 256, h->sm_contract, s>>>(D, use_weights ? 1 : 0, (int)(h->sm_contract / sizeof(double))); });
+        L(KC_QUAD, [&] { k_quad_contract_sm<<<dim3(cdiv(R, QC_WARPS), ncore), 32 * QC_WARPS, h->sm_contract, s>>>(D, use_weights ? 1 : 0); });
         if (with_lua) L(KC_QUAD, [&] { k_quad_lua_sm<<<ncore, 512, h->sm_lua, s>>>(D); });
     }
     L(KC_QUAD, [&] { k_quad_chain_sm<<<D.nv, 512, h->sm_mat3, s>>>(D, log_maxrank); });
@@ -1037,12 +1031,6 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
             const size_t smi = stage_w ? 2 * smf : smf;
             // the 48 KB default covers static + dynamic shared memory together (the kernel holds ~9 KB of static tables)
             if (smi > 32 * 1024) CUDA_TRY(h, cudaFuncSetAttribute(k_init_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smi));
-            if (std::getenv("TTC_TRACE")) {
-                cudaFuncAttributes fa{};
-                cudaFuncGetAttributes(&fa, k_init_state);
-                std::fprintf(stderr, "[ttc trace] k_init_state: dynamic %zu B (weights staged: %d), static %zu B, opt-in %d B, regs %d, max threads %d\n", smi, stage_w,
-                             fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.numRegs, fa.maxThreadsPerBlock);
-            }
             L(KC_INIT, [&] { k_init_state<<<1, 1024, smi, s>>>(D, nn, snum, h->init_scal, h->init_ind0, has_quad ? 1 : 0, stage_w); });
         }
         h->rk_h.assign(d + 2, 1); h->rks_h.assign(d + 2, 1);
@@ -1388,7 +1376,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
             const int R = h->Rmax, ncore = D.c_hi - D.c_lo + 1;
             // The contraction reads the raw cores, which the finalisation (dtt_lua below) rewrites in place: it stays on the sweep
             // stream; the rest works on the contracted copies only and runs on the second stream beside the finalisation.
-            L(KC_QUAD, [&] { k_quad_contract_sm<<<dim3(R, ncore), 256, h->sm_contract, s>>>(D, 1, (int)(h->sm_contract / sizeof(double))); });
+            L(KC_QUAD, [&] { k_quad_contract_sm<<<dim3(cdiv(R, QC_WARPS), ncore), 32 * QC_WARPS, h->sm_contract, s>>>(D, 1); });
             if (h->ev_fork.empty()) {
                 cudaEvent_t a = nullptr, b = nullptr;
                 CUDA_TRY(h, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -1504,14 +1492,6 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
         L(KC_FINAL, [&] { k_lua_r<<<dim3(cdiv((i64)h->nmax * Rmax, 128), ncore_own), 128, 0, s>>>(D); });
         L(KC_FINAL, [&] { k_lua_l<<<dim3(cdiv((i64)h->nmax * Rmax, 128), ncore_own), 128, 0, s>>>(D); });
     }
-    // Early copy-out of bound cores: k_lua_fused has packed them already, so the final ranks travel right now and the transfer
-    // into the caller's buffer is enqueued on the second stream as soon as they are known -- beside the closing quadrature and
-    // the log transfers instead of behind them.
-    const bool early_bind = bound && lua_fused && h->stream_q != nullptr;
-    if (early_bind) {
-        CUDA_TRY(h, cudaMemcpyAsync(h->log_h + lb_rk, D.rk, (size_t)(d + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(h, cudaEventRecord(h->ev_lua, s));
-    }
     if (persist_quad_pending) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_join[0], 0));      // the per-sweep values are part of the run
     CUDA_TRY(h, cudaEventRecord(h->ev1, s));
     // Every reference driver follows dtt_dmrgg with dtt_quad of the finalised train (test_crs_ising.f90:158): with one process
@@ -1529,34 +1509,20 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     CUDA_TRY(h, cudaMemcpyAsync(h->log_h + lb_slog, D.slog, (size_t)(Rmax + 1) * sizeof(SweepOut), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaMemcpyAsync(h->log_h + lb_rklog, D.rklog, (size_t)(Rmax + 1) * (d + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaMemcpyAsync(h->log_h + lb_vlog, D.vlog, (size_t)Rmax * maxnb * P * sizeof(VisitOut), cudaMemcpyDeviceToHost, s));
-    if (!early_bind) CUDA_TRY(h, cudaMemcpyAsync(h->log_h + lb_rk, D.rk, (size_t)(d + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
-    size_t bind_tot = 0;
-    bool bind_small = false, bind_on_q = false;
-    auto bind_size = [&]() {
-        const int* rkd = (const int*)(h->log_h + lb_rk);
-        for (int k = D.c_lo; k <= D.c_hi; ++k) bind_tot += (size_t)rkd[k - 1] * h->n[k] * rkd[k];
-        bind_small = (long long)bind_tot > h->bind_cap;
-    };
-    if (early_bind) {
-        CUDA_TRY(h, cudaEventSynchronize(h->ev_lua));
-        bind_size();
-        if (!bind_small && bind_tot > 0) {
-            CUDA_TRY(h, cudaStreamWaitEvent(h->stream_q, h->ev_lua, 0));
-            // in pieces of 2 MB: the small log transfers of the main stream slip in between them instead of queueing behind 13 MB
-            char* dst = (char*)(h->bind_pinned ? h->bind_out : h->stage_h);
-            const char* src = (const char*)h->pack_d;
-            const size_t nbytes = bind_tot * sizeof(double), piece = (size_t)2 << 20;
-            for (size_t o = 0; o < nbytes; o += piece)
-                CUDA_TRY(h, cudaMemcpyAsync(dst + o, src + o, std::min(piece, nbytes - o), cudaMemcpyDeviceToHost, h->stream_q));
-            CUDA_TRY(h, cudaEventRecord(h->ev_bind, h->stream_q));
-            bind_on_q = true;                                         // awaited below, after the host's log processing
-        }
-    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->log_h + lb_rk, D.rk, (size_t)(d + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     CUDA_TRY(h, cudaGetLastError());
     if (h->nproc == 1) { h->quad_value = h->sweep_h->val; h->quad_cached = true; }
-    if (bound && !early_bind) {
-        bind_size();
+    // bound cores: the transfer of the packed copy into the caller's buffer starts as soon as the logs (which carry the ranks)
+    // have arrived and runs beside the host's log processing below.  (Measured: starting it right behind k_lua_fused on the
+    // second stream, after an early read of the ranks, is 0.07 ms SLOWER end to end at config B -- a second host wake-up and
+    // the log transfers queueing behind 13 MB cost more than the closing quadrature it would hide.)
+    size_t bind_tot = 0;
+    bool bind_small = false;
+    if (bound) {
+        const int* rkd = (const int*)(h->log_h + lb_rk);
+        for (int k = D.c_lo; k <= D.c_hi; ++k) bind_tot += (size_t)rkd[k - 1] * h->n[k] * rkd[k];
+        bind_small = (long long)bind_tot > h->bind_cap;
         if (!bind_small && bind_tot > 0)
             CUDA_TRY(h, cudaMemcpyAsync(h->bind_pinned ? h->bind_out : h->stage_h, h->pack_d, bind_tot * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
@@ -1565,7 +1531,6 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     // ---- read the logs back and rebuild the reference's report
     Ctrl ctrl;
     std::memcpy(&ctrl, h->log_h + lb_ctrl, sizeof ctrl);
-    if (ctrl.error && bind_on_q) cudaEventSynchronize(h->ev_bind);        // no transfer in flight behind an error return
     if (ctrl.error == 3) { h->err = "multi-GPU exchange timed out waiting for a peer rank"; return TTC_ERR_COMM; }
     if (ctrl.error == 2) { h->err = "internal: the incremental quadrature saw a rank grow by more than one in a sweep"; return TTC_ERR_STATE; }
     if (ctrl.error) { h->err = "rank capacity exceeded (pass maxrank)"; return TTC_ERR_RANK; }
@@ -1631,8 +1596,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
     if (persistent) { float sm = 0; cudaEventElapsedTime(&sm, h->evs0, h->evs1); h->sweep_ms = sm; }
     h->neval = nevalall;
     if (bound && !bind_small) {
-        if (bind_on_q) CUDA_TRY(h, cudaEventSynchronize(h->ev_bind));
-        else CUDA_TRY(h, cudaStreamSynchronize(s));
+        CUDA_TRY(h, cudaStreamSynchronize(s));
         if (!h->bind_pinned) std::memcpy(h->bind_out, h->stage_h, bind_tot * sizeof(double));
         h->bind_filled = true; h->bind_count = bind_tot;
         tr.lap("bound cores");
