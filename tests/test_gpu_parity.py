@@ -152,6 +152,19 @@ def test_superblock_sweep_moderate_shape_bit_exact(P):
     assert_parity(t, g, o, exact=True)
 
 
+@pytest.mark.parametrize("P", [1, 4])
+def test_superblock_sweep_config_B_mode_size_bit_exact(P):
+    """pivoting = -1 at the MODE SIZE of BASELINE config B (n = 257 nodes, d = 9 cores): every bond visit evaluates the whole
+    r x 257 x 257 x r superblock (up to 4.2 M elements at rank 8, 65-70 M evaluations in the run) through the tiled kernel, many
+    column tiles and row blocks per visit.  Tape, ranks, neval, per-sweep values and cores against the oracle, bit for bit.
+    (The full-rank B shape, 32 x 257 x 257 x 32 per visit, is 2 G evaluations per sweep -- minutes of oracle time; it is covered
+    by the timing in bench.py's roofline_superblock and the kernel-against-kernel checks above.)"""
+    p = T.drivers.ising("c", 10, 256)
+    t, g, o = run_both(p, 8, -1, P=P)
+    assert_parity(t, g, o, exact=True)
+    assert g.neval > 60_000_000
+
+
 def test_superblock_kernel_mvn_matches_plain():
     p = T.drivers.mvn(4, 16)
     t = p.make()
