@@ -22,7 +22,7 @@ def _build():
 def test_programs_build_and_fail_loudly_without_gpu(has_gpu):
     T.load_library()
     _build()
-    for prog in ("test_crs_ising", "test_crs_mvn", "test_crs_stdnorm", "test_crs_chf", "test_crs_pdf"):
+    for prog in ("test_crs_ising", "test_crs_mvn", "test_crs_stdnorm", "test_crs_chf", "test_crs_pdf", "test_crs_store"):
         assert os.access(os.path.join(BIN, prog), os.X_OK)
     if not has_gpu:
         r = subprocess.run([os.path.join(BIN, "test_crs_ising"), "c", "4", "8", "4", "1"], capture_output=True, text=True, timeout=120)
@@ -60,3 +60,25 @@ def test_stdnorm_and_mvn_programs_run():
     assert r.returncode == 0 and "Good bye." in r.stdout, r.stdout + r.stderr
     r = subprocess.run([os.path.join(BIN, "test_crs_mvn"), "6", "16", "6"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "Good bye." in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_store_program_writes_the_train(tmp_path):
+    """test_crs_store.f90:129-136: the MVN cross of the pdf pipeline, then the train goes to a file (HDF5 in the reference; the TT
+    stream format of lib/ttio.f90 here).  The stored cores must be the ones the same cross leaves in the Python mirror, and
+    the rest of the pipeline (phis, COS density) must still run."""
+    _build()
+    tt_out, pdf_out = tmp_path / "tensor_train.tt", tmp_path / "pdf.txt"
+    env = dict(os.environ, TTC_TT_OUT=str(tt_out), TTC_PDF_OUT=str(pdf_out), TTC_SEED="1", TTC_QUIET="1")
+    r = subprocess.run([os.path.join(BIN, "test_crs_store"), "4", "32", "12", "1"], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "Train written to:" in r.stdout and "Writing PDF output to:" in r.stdout, r.stdout + r.stderr
+    l, cores = T.tt_read(str(tt_out))
+    p = T.drivers.mvn(4, 32)
+    t = p.make(use_quad=False, use_tru=False); t.set_seed(1)
+    t.dmrgg(12, p.accuracy, 1)
+    want = t.cores()
+    assert l == 1 and len(cores) == len(want)
+    for a, b in zip(cores, want):       # (the C++ driver and the Python mirror build par / the MVN matrix with their own host arithmetic)
+        assert a.shape == b.shape
+        np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12 * float(np.abs(b).max()))
+    assert np.loadtxt(pdf_out).shape == (200, 2)

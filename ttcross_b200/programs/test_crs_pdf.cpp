@@ -3,7 +3,8 @@
 // series of the density of mean_j exp(X_j) on 200 points of [0, 300] (cos_approximate_array, lib/cos_approx.f90:90-127)
 // written as two es25.17 columns (:186-199).  Output file: ./out/tt-cross-pdf.txt like the reference, or $TTC_PDF_OUT.
 // The reference then shells out to its matplotlib scripts (:206-214); this twin stops at the file.  With $TTC_TT_OUT set it
-// also stores the train like test_crs_store.f90:136 does (in the reference's TT stream format instead of HDF5).
+// also stores the train like test_crs_store.f90:136 does (in the reference's TT stream format instead of HDF5); the binary
+// test_crs_store is this file compiled with -DTTC_STORE_TWIN, which makes that step unconditional (./out/tensor_train.tt).
 #include "driver_common.hpp"
 #include <complex>
 
@@ -50,8 +51,15 @@ int main(int argc, char** argv) {
     }
     st = ttc_quad_complex(h, K, wre.data(), wim.data(), ore.data(), oim.data());
     if (st) drv::die(h, st, "ttc_quad_complex");
-    if (const char* tt_out = std::getenv("TTC_TT_OUT")) {      // test_crs_store.f90:136 saves the train (HDF5 there; the TT stream
-        st = ttc_write(h, tt_out);                              // format of lib/ttio.f90 here -- no HDF5 library in this build)
+    // test_crs_store.f90:136 saves the train right after the cross ("out/tensor_train.h5", HDF5 there; the TT stream format of
+    // lib/ttio.f90 here -- no HDF5 library in this build).  Built with -DTTC_STORE_TWIN this file IS the twin of
+    // test_crs_store.f90 (the same pipeline as test_crs_pdf.f90 plus the store step): the train is always written.
+    const char* tt_out = std::getenv("TTC_TT_OUT");
+#ifdef TTC_STORE_TWIN
+    if (!tt_out) tt_out = "./out/tensor_train.tt";
+#endif
+    if (tt_out) {
+        st = ttc_write(h, tt_out);
         if (st) drv::die(h, st, "ttc_write");
         std::printf("   Train written to: %s\n", tt_out);
     }
