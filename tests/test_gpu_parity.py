@@ -222,6 +222,21 @@ def test_sweep_schedules_agree(kind, index, n, R, piv, P, monkeypatch):
             assert np.array_equal(a, b)
 
 
+def test_handles_with_different_rank_capacities_alternate():
+    """The opt-in to large dynamic shared memory is a per-kernel cap shared by every handle of the process: a handle with a small
+    rank capacity must not lower what a handle with a large one asked for (optin_smem in ttc_engine.cu is monotonic).  Before
+    that, the third run below failed with 'invalid argument'."""
+    p = T.drivers.ising("c", 6, 24)
+    big, small = p.make(), p.make()
+    g1 = big.dmrgg(64, p.accuracy, 2)
+    gs = small.dmrgg(6, p.accuracy, 2)
+    g2 = big.dmrgg(64, p.accuracy, 2)
+    assert gs.ranks.max() <= 6
+    assert np.array_equal(g1.pivlog, g2.pivlog) and np.array_equal(g1.vals, g2.vals) and np.array_equal(g1.ranks, g2.ranks)
+    for a, b in zip(big.cores(), [c.copy() for c in big.cores()]):
+        assert np.array_equal(a, b)
+
+
 def test_no_quadrature_run_with_partitions():
     # dtt_dmrgg without quad= (test_crs_chf.f90:122): no quadrature group at all, the fused kernels still close the sweeps
     p = T.drivers.ising("c", 8, 24)

@@ -396,6 +396,24 @@ struct Launcher {
 
 inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
 
+// Opt-in to large dynamic shared memory, MONOTONIC per (device, kernel): the attribute is a per-function cap shared by every handle
+// of the process, so a handle with small ranks must never lower what a handle with large ranks has asked for (its next launch
+// would fail with "invalid argument").  The cap does not influence occupancy -- that follows the size passed at launch.
+template <class F>
+cudaError_t optin_smem(F fn, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> cur;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& c = cur[{dev, reinterpret_cast<const void*>(fn)}];
+    if (bytes <= c) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) c = bytes;
+    return e;
+}
+
+
 // dispatch on the integrand family
 #define KIND_SWITCH(kind, ...)                                                   \
     switch (kind) {                                                              \
@@ -646,21 +664,21 @@ int setup_device(ttc_handle* h, int maxrank) {
             size_t stage = std::min<size_t>((size_t)(2 * R + 1) * (h->nmax + 1) + 64, fixed < 136 * 1024 ? (200 * 1024 - fixed) / sizeof(double) - 16 : (64 * 1024) / sizeof(double));
             if (fixed + stage * sizeof(double) > 200 * 1024) h->use_wave = false;
             h->qinc_stage = (int)stage; h->sm_qinc = fixed + stage * sizeof(double);
-            if (h->use_wave) cudaFuncSetAttribute(k_quad_inc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_qinc);
+            if (h->use_wave) optin_smem(k_quad_inc, (int)h->sm_qinc);
         }
         if (h->use_wave) {
-            if (h->sm_contract > 32 * 1024) cudaFuncSetAttribute(k_quad_contract_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_contract);
-            cudaFuncSetAttribute(k_quad_lua_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_lua);
-            cudaFuncSetAttribute(k_quad_chain_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_mat3);
-            cudaFuncSetAttribute(k_quad_tree_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_mat3);
-            cudaFuncSetAttribute(k_update_nbr_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_ext);
-            cudaFuncSetAttribute(k_exchange_extend_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_ext);
-            cudaFuncSetAttribute(k_lua_r_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_ext);
-            cudaFuncSetAttribute(k_lua_l_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_ext);
+            if (h->sm_contract > 32 * 1024) optin_smem(k_quad_contract_sm, (int)h->sm_contract);
+            optin_smem(k_quad_lua_sm, (int)h->sm_lua);
+            optin_smem(k_quad_chain_sm, (int)h->sm_mat3);
+            optin_smem(k_quad_tree_sm, (int)h->sm_mat3);
+            optin_smem(k_update_nbr_w, (int)h->sm_ext);
+            optin_smem(k_exchange_extend_w, (int)h->sm_ext);
+            optin_smem(k_lua_r_w, (int)h->sm_ext);
+            optin_smem(k_lua_l_w, (int)h->sm_ext);
         }
         // fused finalisation (k_lua_fused): both packed LUs + one slab per warp in shared memory
         h->lua_fused_ok = !h->force_simple && lua_fused_smem(Rmax) <= 200 * 1024 && !std::getenv("TTC_NO_LUA_FUSED");
-        if (h->lua_fused_ok) cudaFuncSetAttribute(k_lua_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lua_fused_smem(Rmax));
+        if (h->lua_fused_ok) optin_smem(k_lua_fused, (int)lua_fused_smem(Rmax));
     }
     // tiled superblock kernel (ttc_superblock.cuh): column-factor slab + per-tile tables in shared memory
     {
@@ -671,11 +689,11 @@ int setup_device(ttc_handle* h, int maxrank) {
             cudaError_t ce = cudaSuccess;
             const int bt = (int)h->sm_sbt;
             KIND_SWITCH(h->kind,
-                ce = cudaFuncSetAttribute(k_superblock_t<K, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bt);
-                if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_superblock_t<K, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bt);
-                if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_superblock_t<K, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bt);
+                ce = optin_smem(k_superblock_t<K, 0, 0>, bt);
+                if (ce == cudaSuccess) ce = optin_smem(k_superblock_t<K, 1, 0>, bt);
+                if (ce == cudaSuccess) ce = optin_smem(k_superblock_t<K, 0, 1>, bt);
                 h->sbm_ok = ce == cudaSuccess && h->sm_sbm <= 220 * 1024 && Rmax % 4 == 0 &&
-                            cudaFuncSetAttribute(k_superblock_t<K, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_sbm) == cudaSuccess;
+                            optin_smem(k_superblock_t<K, 0, 2>, (int)h->sm_sbm) == cudaSuccess;
                 (void)cudaGetLastError();
             );
             if (ce != cudaSuccess) { (void)cudaGetLastError(); h->sbt_ok = false; }
@@ -702,7 +720,7 @@ int setup_device(ttc_handle* h, int maxrank) {
         if (h->cluster_ok) {
             cudaError_t ce = cudaSuccess;
             VISIT_KIND_SWITCH(h,
-                ce = cudaFuncSetAttribute(k_visits<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_visit);
+                ce = optin_smem(k_visits<K>, (int)h->sm_visit);
                 if (ce == cudaSuccess && h->cluster_size > 8) ce = cudaFuncSetAttribute(k_visits<K>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             );
             if (ce != cudaSuccess) { (void)cudaGetLastError(); h->cluster_ok = false; }
@@ -749,7 +767,7 @@ int setup_device(ttc_handle* h, int maxrank) {
             }
             cudaError_t ce = cudaSuccess;
             VISIT_KIND_SWITCH(h,
-                ce = cudaFuncSetAttribute(k_sweeps<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_sweep);
+                ce = optin_smem(k_sweeps<K>, (int)h->sm_sweep);
                 if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_sweeps<K>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             );
             for (size_t ci = 0; ci < cand.size() && ce == cudaSuccess && !h->persist_ok; ++ci) {
@@ -787,29 +805,29 @@ int setup_device(ttc_handle* h, int maxrank) {
             if (h->kind == TTC_ISING) for (int x = 0; x < h->nmax; ++x) ptv[D.NT + x] = h->par[h->n[1] + x];
             if (dev_upload(h, &pt, ptv)) return TTC_ERR_CUDA;
             D.XLg = xl; D.WLg = wl; D.XRg = xr; D.WRg = wr; D.parT = pt;
-            cudaFuncSetAttribute(k_quad_lua_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_lua);
-            cudaFuncSetAttribute(k_quad_chain_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_mat3);
-            cudaFuncSetAttribute(k_quad_tree_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_mat3);
+            optin_smem(k_quad_lua_all, (int)h->sm_lua);
+            optin_smem(k_quad_chain_all, (int)h->sm_mat3);
+            optin_smem(k_quad_tree_all, (int)h->sm_mat3);
         }
     }
     // opt in to more than 48 KB of dynamic shared memory where the staging areas need it
     {
         const int bl = (int)h->sm_lot, bf = (int)h->sm_fiber, bs = (int)h->sm_sb, ba = (int)aux_smem(h);
         KIND_SWITCH(h->kind,
-            if (bl > 32 * 1024) cudaFuncSetAttribute(k_lot<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, bl);
-            if (bf > 32 * 1024) { cudaFuncSetAttribute(k_fiber<K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf);
-                                  cudaFuncSetAttribute(k_fiber<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf); }
-            if (bs > 32 * 1024) { cudaFuncSetAttribute(k_superblock<K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs);
-                                  cudaFuncSetAttribute(k_superblock<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs); }
-            if (ba + 16 * h->d > 32 * 1024) cudaFuncSetAttribute(k_exchange_corner<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba + 16 * h->d);
+            if (bl > 32 * 1024) optin_smem(k_lot<K>, bl);
+            if (bf > 32 * 1024) { optin_smem(k_fiber<K, 0>, bf);
+                                  optin_smem(k_fiber<K, 1>, bf); }
+            if (bs > 32 * 1024) { optin_smem(k_superblock<K, 0>, bs);
+                                  optin_smem(k_superblock<K, 1>, bs); }
+            if (ba + 16 * h->d > 32 * 1024) optin_smem(k_exchange_corner<K>, ba + 16 * h->d);
             {
                 h->sm_xf = (size_t)ba + ((size_t)2 * h->d + (size_t)2 * h->Rmax * h->Rmax + h->Rmax) * sizeof(double);
                 h->xf_ok = h->sm_xf <= (size_t)200 * 1024 &&
-                           cudaFuncSetAttribute(k_exchange_fused<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sm_xf) == cudaSuccess;
+                           optin_smem(k_exchange_fused<K>, (int)h->sm_xf) == cudaSuccess;
             }
             if (ba > 32 * 1024) {
-                                  cudaFuncSetAttribute(k_init_search<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba);
-                                  cudaFuncSetAttribute(k_init_cross<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba); }
+                                  optin_smem(k_init_search<K>, ba);
+                                  optin_smem(k_init_cross<K>, ba); }
         );
     }
     return 0;
@@ -1030,7 +1048,7 @@ int run_dmrgg(ttc_handle* h, int maxrank, double accuracy, int pivoting) {
             const int stage_w = (has_quad && 2 * smf <= 200 * 1024) ? 1 : 0;       // quadrature weights staged beside the fibers
             const size_t smi = stage_w ? 2 * smf : smf;
             // the 48 KB default covers static + dynamic shared memory together (the kernel holds ~9 KB of static tables)
-            if (smi > 32 * 1024) CUDA_TRY(h, cudaFuncSetAttribute(k_init_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smi));
+            if (smi > 32 * 1024) CUDA_TRY(h, optin_smem(k_init_state, (int)smi));
             L(KC_INIT, [&] { k_init_state<<<1, 1024, smi, s>>>(D, nn, snum, h->init_scal, h->init_ind0, has_quad ? 1 : 0, stage_w); });
         }
         h->rk_h.assign(d + 2, 1); h->rks_h.assign(d + 2, 1);
@@ -1974,9 +1992,9 @@ cudaError_t tsqr_launch(cudaStream_t s, const double* da, int m, int n, double* 
     // the chain of factor launches (only R feeds the next level), then the explicit Q of all upper nodes in one launch, then the
     // first-level blocks: dorg2r + chain of slices + block product in one kernel
     auto run = [&](auto kfac, auto kformq, auto kleaf) -> cudaError_t {
-        cudaError_t e2 = cudaFuncSetAttribute(kfac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
-        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(kformq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
-        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(kleaf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_l);
+        cudaError_t e2 = optin_smem(kfac, (int)sm_f);
+        if (e2 == cudaSuccess) e2 = optin_smem(kformq, (int)sm_f);
+        if (e2 == cudaSuccess) e2 = optin_smem(kleaf, (int)sm_l);
         if (e2 != cudaSuccess) return e2;
         kfac<<<G1, TQ_THREADS, sm_f, s>>>(da, 1, m, n, m, G1, 0, F, Rl[0], dq, m, Tl[0]);
         for (int l = 1; l < L; ++l) kfac<<<G[l], TQ_THREADS, sm_f, s>>>(Rl[l - 1], l + 1, m, n, m, G1, G[l - 1], F, Rl[l], Ql[l], m, Tl[l]);
@@ -2010,7 +2028,7 @@ cudaError_t qr_launch(cudaStream_t s, int nsm, const double* da, int m, int n, d
         if (e != cudaSuccess) return e;
         sc.cap_g = nsm; sc.cap_n = std::max(n, 128);
     }
-    cudaError_t e = cudaFuncSetAttribute(k_qr_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = optin_smem(k_qr_panel, (int)smem);
     if (e != cudaSuccess) return e;
     int lda = m;
     void* args[] = {(void*)&da, (void*)&m, (void*)&n, (void*)&lda, (void*)&dq, (void*)&dr, (void*)&sc.part, (void*)&sc.pw, (void*)&sc.head, (void*)&rpb};
@@ -2128,7 +2146,7 @@ int ttc_svd(ttc_handle* h, double tol, int rmax) {
         e = qr_launch(s, h->nsm, T, (int)nn, mm, Q, Rm, sc);
         if (e != cudaSuccess) break;
         const size_t smem = (2 * (size_t)mm * mm + 2 * (size_t)mm) * sizeof(double) + (2 * (size_t)mm + 4) * sizeof(int);
-        if (smem > 32 * 1024) cudaFuncSetAttribute(k_svd_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > 32 * 1024) optin_smem(k_svd_small, (int)smem);
         k_svd_small<<<1, 32 * std::max(1, std::min(32, (mm + 1) / 2)), smem, s>>>(Rm, mm, U, sv, W);
         std::vector<double> svh(mm);
         e = cudaMemcpyAsync(svh.data(), sv, mm * sizeof(double), cudaMemcpyDeviceToHost, s);
@@ -2281,7 +2299,7 @@ int ttc_accchk(ttc_handle* h, long long nlot, unsigned long long seed, double* o
     const size_t smem = aux_smem(h) + (size_t)nw * (2 * h->Rmax + h->d) * sizeof(double);
     if (e == cudaSuccess) {
         KIND_SWITCH(h->kind,
-            if (smem > 32 * 1024) cudaFuncSetAttribute(k_accchk<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (smem > 32 * 1024) optin_smem(k_accchk<K>, (int)smem);
             k_accchk<K><<<grid, 32 * nw, smem, h->stream>>>(h->plan, nlot, seed, dpart, darg));
         h->launches += 1;
         e = cudaGetLastError();
