@@ -160,6 +160,10 @@ def main():
     ap.add_argument("--config", default="B", choices=sorted(CONFIGS), help="BASELINE.json configuration (B = the headline workload)")
     args = ap.parse_args()
     if args.impl == "reference":
+        # the CPU arm at its best: idle OpenMP workers spin between the (many, short) parallel regions instead of sleeping --
+        # +12 % on the GPU box's 16 cores (tests/_ref_arm_probe.py: 1.70e7 -> 1.92e7 evals/s; pinning threads halves it).  Must be
+        # in the environment before libgomp initialises, i.e. before the oracle library is loaded.
+        os.environ.setdefault("OMP_WAIT_POLICY", "active")
         return reference_arm(args)
 
     import numpy as np
